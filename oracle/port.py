@@ -1,0 +1,183 @@
+"""ctypes binding of ``cnn_oracle.c`` (TEST INFRASTRUCTURE, see ``oracle/__init__.py``)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "cnn_oracle.c")
+LIB = os.path.join(HERE, "libcnn_oracle.so")
+
+_lib = None
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+        subprocess.run(
+            ["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", SRC, "-o", LIB, "-lm"],
+            check=True,
+        )
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB)
+        L.cnn_oracle_distance.restype = C.c_double
+        L.cnn_oracle_distance.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_int64, C.c_int]
+        L.cnn_oracle_adjust_radius.restype = C.c_double
+        L.cnn_oracle_adjust_radius.argtypes = [C.c_double, C.c_int]
+        for name in ("brute", "grid"):
+            f = getattr(L, f"cnn_oracle_neighbours_{name}_count")
+            f.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_double, C.c_int, _i64p]
+            f = getattr(L, f"cnn_oracle_neighbours_{name}_fill")
+            f.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_double, C.c_int, _i64p, _i64p]
+        L.cnn_oracle_neighbours_brute_count.restype = None
+        L.cnn_oracle_neighbours_brute_fill.restype = None
+        for name in ("check_sorted", "check_contains"):
+            f = getattr(L, f"cnn_oracle_{name}")
+            f.restype = C.c_int
+            f.argtypes = [_i64p, C.c_int64, _i64p, C.c_int64, C.c_int64]
+        L.cnn_oracle_count_sorted.restype = C.c_int64
+        L.cnn_oracle_count_sorted.argtypes = [_i64p, C.c_int64, _i64p, C.c_int64]
+        L.cnn_oracle_fit_bfs.restype = C.c_int
+        L.cnn_oracle_fit_bfs.argtypes = [_i64p, _i64p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                         _i64p, _u8p, _i64p]
+        L.cnn_oracle_sort_by_size.restype = C.c_int
+        L.cnn_oracle_sort_by_size.argtypes = [_i64p, C.c_int64, C.c_int64, C.c_int64]
+        L.cnn_oracle_csr_to_padded.restype = None
+        L.cnn_oracle_csr_to_padded.argtypes = [_i64p, _i64p, C.c_int64, C.c_int64, _i64p, _i64p]
+        _lib = L
+    return _lib
+
+
+METRICS = {"euclidean_r": 0, "euclidean": 1}
+
+
+def set_threads(n: int) -> None:
+    """Number of OpenMP threads for the neighbour search (the BFS is always single-threaded)."""
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        omp = C.CDLL("libgomp.so.1")
+        omp.omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
+def adjust_radius(r: float, metric: str = "euclidean_r") -> float:
+    return lib().cnn_oracle_adjust_radius(float(r), METRICS[metric])
+
+
+def neighbours(x, radius_cutoff: float, metric: str = "euclidean_r", method: str = "auto"):
+    """CSR (row_ptr int64[n+1], col_idx int64[nnz]) of {j: dist(i,j) <= radius_cutoff}.
+
+    ``radius_cutoff`` is already metric-adjusted (r*r for ``euclidean_r``)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n, d = x.shape
+    L = lib()
+    if method == "auto":
+        method = "grid" if (d <= 3 and n > 4000) else "brute"
+    deg = np.zeros(n, dtype=np.int64)
+    m = METRICS[metric]
+    cnt = getattr(L, f"cnn_oracle_neighbours_{method}_count")
+    fil = getattr(L, f"cnn_oracle_neighbours_{method}_fill")
+    rc = cnt(x, n, d, float(radius_cutoff), m, deg)
+    assert not rc, rc
+    row_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(deg, out=row_ptr[1:])
+    col_idx = np.empty(max(int(row_ptr[-1]), 1), dtype=np.int64)
+    rc = fil(x, n, d, float(radius_cutoff), m, row_ptr, col_idx)
+    assert not rc, rc
+    return row_ptr, col_idx[: int(row_ptr[-1])]
+
+
+def check(a, b, c: int, kind: str = "sorted") -> bool:
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    b = np.ascontiguousarray(b, dtype=np.int64)
+    f = lib().cnn_oracle_check_sorted if kind == "sorted" else lib().cnn_oracle_check_contains
+    return bool(f(a, a.size, b, b.size, int(c)))
+
+
+def count_common(a, b) -> int:
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    b = np.ascontiguousarray(b, dtype=np.int64)
+    return int(lib().cnn_oracle_count_sorted(a, a.size, b, b.size))
+
+
+def make_parameters(r: float, c: int, metric="euclidean_r", selfcounting=True, current_start=1):
+    """FitterExtInterface.make_parameters, _fit.pyx:129-161."""
+    return {
+        "radius_cutoff": adjust_radius(r, metric) if metric is not None else float(r),
+        "similarity_cutoff": c + 2 if selfcounting else c,
+        "n_member_cutoff": c + 1 if selfcounting else c,
+        "current_start": current_start,
+    }
+
+
+def fit_bfs(row_ptr, col_idx, n_member_cutoff, similarity_cutoff, current_start=1,
+            labels=None, consider=None, return_stats=False):
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    col_idx = np.ascontiguousarray(col_idx, dtype=np.int64)
+    if col_idx.size == 0:
+        col_idx = np.zeros(1, dtype=np.int64)
+    n = row_ptr.size - 1
+    if labels is None:
+        labels = np.zeros(n, dtype=np.int64)
+    if consider is None:
+        consider = np.ones(n, dtype=np.uint8)
+    stats = np.zeros(2, dtype=np.int64)
+    rc = lib().cnn_oracle_fit_bfs(row_ptr, col_idx, n, int(n_member_cutoff), int(similarity_cutoff),
+                                  int(current_start), labels, consider, stats)
+    assert rc == 0, rc
+    return (labels, stats) if return_stats else labels
+
+
+def sort_by_size(labels, member_cutoff=None, max_clusters=None):
+    labels = np.ascontiguousarray(labels, dtype=np.int64)
+    rc = lib().cnn_oracle_sort_by_size(
+        labels, labels.size, -1 if member_cutoff is None else int(member_cutoff),
+        -1 if max_clusters is None else int(max_clusters))
+    assert rc == 0, rc
+    return labels
+
+
+def csr_to_padded(row_ptr, col_idx):
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    col_idx = np.ascontiguousarray(col_idx, dtype=np.int64)
+    n = row_ptr.size - 1
+    max_deg = int(np.diff(row_ptr).max()) if n else 0
+    padded = np.zeros((n, max(max_deg, 1)), dtype=np.int64)
+    counts = np.zeros(n, dtype=np.int64)
+    if col_idx.size == 0:
+        col_idx = np.zeros(1, dtype=np.int64)
+    lib().cnn_oracle_csr_to_padded(row_ptr, col_idx, n, padded.shape[1], padded, counts)
+    return padded, counts
+
+
+def fit_csr(row_ptr, col_idx, c: int, member_cutoff=None, max_clusters=None, sort=True,
+            selfcounting=True, current_start=1, return_stats=False):
+    """Clustering.fit on precomputed neighbourhoods (cluster.pyx:256-392, lookup recipe)."""
+    p = make_parameters(0.0, c, metric=None, selfcounting=selfcounting, current_start=current_start)
+    out = fit_bfs(row_ptr, col_idx, p["n_member_cutoff"], p["similarity_cutoff"], current_start,
+                  return_stats=return_stats)
+    labels, stats = out if return_stats else (out, None)
+    if sort:
+        sort_by_size(labels, member_cutoff, max_clusters)
+    return (labels, stats) if return_stats else labels
+
+
+def fit_points(x, r: float, c: int, member_cutoff=None, max_clusters=None, sort=True,
+               metric="euclidean_r", method="auto", current_start=1):
+    """Clustering.fit with the default "coordinates" recipe (cluster.pyx:256-392)."""
+    p = make_parameters(r, c, metric=metric, current_start=current_start)
+    row_ptr, col_idx = neighbours(x, p["radius_cutoff"], metric, method)
+    labels = fit_bfs(row_ptr, col_idx, p["n_member_cutoff"], p["similarity_cutoff"], current_start)
+    if sort:
+        sort_by_size(labels, member_cutoff, max_clusters)
+    return labels

@@ -1,0 +1,295 @@
+"""ctypes binding of ``libcnnb200.so`` (the C-ABI declared in ``include/cnnb200.h``).
+
+There is no CPU fallback: if the library is missing or cannot be loaded, importing the compute
+path raises.  ``__graft_entry__.build()`` / ``python -m commonnnclustering_b200.build`` compile it.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcnnb200.so")
+
+HOST, DEVICE = 0, 1
+METRIC_IDS = {"euclidean_r": 0, "euclidean": 1}
+METHOD_IDS = {"auto": 0, "grid": 1, "tiled": 2, "tensor": 3}
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
+FREE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+
+_P = C.c_void_p
+_I64 = C.c_int64
+
+# name -> (argtypes); every function returns int except the two noted below
+SIGNATURES = {
+    "cnnb200_ctx_create": [C.c_int, C.POINTER(_P)],
+    "cnnb200_ctx_destroy": [_P],
+    "cnnb200_ctx_set_stream": [_P, _P],
+    "cnnb200_ctx_set_allocator": [_P, ALLOC_FN, FREE_FN, _P],
+    "cnnb200_ctx_synchronize": [_P],
+    "cnnb200_ctx_release": [_P],
+    "cnnb200_neighbours_from_points": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int, C.c_int, C.POINTER(_I64)],
+    "cnnb200_neighbours_from_csr": [_P, _P, _P, C.c_int, C.c_int, C.c_int, _I64, _I64],
+    "cnnb200_neighbours_from_padded": [_P, _P, _P, C.c_int, _I64, _I64],
+    "cnnb200_neighbours_info": [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)],
+    "cnnb200_neighbours_export": [_P, _P, _P, C.c_int],
+    "cnnb200_neighbours_device_view": [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)],
+    "cnnb200_cn_count": [_P, _I64, _P, C.c_int, C.POINTER(_I64)],
+    "cnnb200_fit": [_P, _I64, _I64, _I64, _P, _P, C.c_int, C.POINTER(_I64)],
+    "cnnb200_components_begin": [_P, _I64, _I64, _P, C.c_int],
+    "cnnb200_components_edges": [_P, _I64, _I64],
+    "cnnb200_components_parents": [_P, C.POINTER(_P)],
+    "cnnb200_components_merge": [_P, _P, _I64],
+    "cnnb200_components_labels": [_P, _I64, _P, C.c_int, C.c_int, C.POINTER(_I64)],
+    "cnnb200_sort_by_size": [_P, _P, C.c_int, _I64, _I64, _I64, _P, _I64],
+    "cnnb200_fit_points": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int, C.c_int, _I64, _I64, _I64,
+                           C.c_int, _I64, _I64, _P, C.POINTER(_I64)],
+    "cnnb200_stats": [_P, _P, _I64],
+}
+
+_lib = None
+
+
+class CnnB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (once).  Raises ImportError when it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA library has not been built "
+            "(run `python -m commonnnclustering_b200.build`); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.cnnb200_version.restype = C.c_int
+    lib.cnnb200_version.argtypes = []
+    lib.cnnb200_last_error.restype = C.c_char_p
+    lib.cnnb200_last_error.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        f = getattr(lib, name)
+        f.restype = C.c_int
+        f.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+_ERRORS = {-1: ValueError, -3: MemoryError}
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().cnnb200_last_error().decode(errors="replace")
+        raise _ERRORS.get(rc, CnnB200Error)(f"cnnb200 error {rc}: {msg}")
+
+
+def _ptr_loc(a):
+    """(raw pointer, HOST|DEVICE) of a numpy array or a torch tensor."""
+    if a is None:
+        return None, HOST
+    if isinstance(a, np.ndarray):
+        if not a.flags.c_contiguous:
+            raise ValueError("array must be C-contiguous")
+        return a.ctypes.data, HOST
+    # torch tensor (duck-typed so that numpy-only callers never import torch)
+    if not a.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return a.data_ptr(), (DEVICE if a.is_cuda else HOST)
+
+
+class Context:
+    """One ``cnnb200_ctx``: a CUDA device, a stream and the device scratch of the fit path."""
+
+    def __init__(self, device: int = 0, stream=None, torch_allocator: bool = False):
+        self._lib = load()
+        h = _P()
+        check(self._lib.cnnb200_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self._keep = []
+        if stream is not None:
+            self.set_stream(stream)
+        if torch_allocator:
+            self.use_torch_allocator()
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cnnb200_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream):
+        ptr = getattr(stream, "cuda_stream", stream)
+        check(self._lib.cnnb200_ctx_set_stream(self._h, _P(int(ptr) if ptr else None)))
+
+    def use_torch_allocator(self):
+        """Route device scratch through torch's caching allocator (PyTorch as buffer carrier)."""
+        import torch
+
+        dev = self.device
+
+        def _alloc(nbytes, _user):
+            try:
+                return torch.cuda.caching_allocator_alloc(int(nbytes), dev)
+            except Exception:
+                return None
+
+        def _free(ptr, _user):
+            torch.cuda.caching_allocator_delete(ptr)
+
+        a, f = ALLOC_FN(_alloc), FREE_FN(_free)
+        self._keep = [a, f]
+        check(self._lib.cnnb200_ctx_set_allocator(self._h, a, f, None))
+
+    def synchronize(self):
+        check(self._lib.cnnb200_ctx_synchronize(self._h))
+
+    def release(self):
+        check(self._lib.cnnb200_ctx_release(self._h))
+
+    # -- neighbourhoods ---------------------------------------------------------------------
+    def neighbours_from_points(self, x, radius_cutoff, metric="euclidean_r", method="auto"):
+        p, loc = _ptr_loc(x)
+        n, d = x.shape
+        nnz = _I64()
+        check(self._lib.cnnb200_neighbours_from_points(
+            self._h, p, loc, n, d, float(radius_cutoff), METRIC_IDS[metric], METHOD_IDS[method], C.byref(nnz)))
+        return nnz.value
+
+    def neighbours_from_csr(self, row_ptr, col_idx, borrow=False):
+        rp, loc = _ptr_loc(row_ptr)
+        cp, loc2 = _ptr_loc(col_idx)
+        if loc != loc2:
+            raise ValueError("row_ptr and col_idx must live in the same memory space")
+        n = row_ptr.shape[0] - 1
+        nnz = col_idx.shape[0]
+        isz = 8 if "64" in str(col_idx.dtype) else 4
+        if borrow:
+            self._borrowed = (row_ptr, col_idx)
+        check(self._lib.cnnb200_neighbours_from_csr(self._h, rp, cp, isz, loc, int(bool(borrow)), n, nnz))
+
+    def neighbours_from_padded(self, padded, counts):
+        pp, loc = _ptr_loc(padded)
+        cp, loc2 = _ptr_loc(counts)
+        if loc != loc2:
+            raise ValueError("padded and counts must live in the same memory space")
+        n, max_deg = padded.shape
+        check(self._lib.cnnb200_neighbours_from_padded(self._h, pp, cp, loc, n, max_deg))
+
+    def neighbours_info(self):
+        n, nnz, md = _I64(), _I64(), _I64()
+        check(self._lib.cnnb200_neighbours_info(self._h, C.byref(n), C.byref(nnz), C.byref(md)))
+        return n.value, nnz.value, md.value
+
+    def neighbours_export(self):
+        """(row_ptr int64[n+1], col_idx int64[nnz]) in the caller's index space, rows ascending."""
+        n, nnz, _ = self.neighbours_info()
+        row_ptr = np.empty(n + 1, dtype=np.int64)
+        col_idx = np.empty(max(nnz, 1), dtype=np.int64)
+        check(self._lib.cnnb200_neighbours_export(self._h, row_ptr.ctypes.data, col_idx.ctypes.data, HOST))
+        return row_ptr, col_idx[:nnz]
+
+    def neighbours_device_view(self):
+        a, b, c = _P(), _P(), _P()
+        check(self._lib.cnnb200_neighbours_device_view(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    # -- similarity ---------------------------------------------------------------------------
+    def cn_count(self, n_member_cutoff, out=None):
+        """uint32 common-neighbour count per CSR slot (internal CSR order); 0xFFFFFFFF = not an edge."""
+        _, nnz, _ = self.neighbours_info()
+        if out is None:
+            out = np.empty(max(nnz, 1), dtype=np.uint32)
+        p, loc = _ptr_loc(out)
+        ne = _I64()
+        check(self._lib.cnnb200_cn_count(self._h, int(n_member_cutoff), p, loc, C.byref(ne)))
+        return out[:nnz], ne.value
+
+    # -- components -----------------------------------------------------------------------------
+    def fit(self, n_member_cutoff, similarity_cutoff, current_start, labels, consider=None):
+        lp, loc = _ptr_loc(labels)
+        cp, loc2 = _ptr_loc(consider)
+        if consider is not None and loc != loc2:
+            raise ValueError("labels and consider must live in the same memory space")
+        nc = _I64()
+        check(self._lib.cnnb200_fit(self._h, int(n_member_cutoff), int(similarity_cutoff), int(current_start),
+                                    lp, cp, loc, C.byref(nc)))
+        return nc.value
+
+    def components_begin(self, n_member_cutoff, similarity_cutoff, consider=None):
+        cp, loc = _ptr_loc(consider)
+        check(self._lib.cnnb200_components_begin(self._h, int(n_member_cutoff), int(similarity_cutoff), cp, loc))
+
+    def components_edges(self, row_begin, row_end):
+        check(self._lib.cnnb200_components_edges(self._h, int(row_begin), int(row_end)))
+
+    def components_parents_ptr(self):
+        p = _P()
+        check(self._lib.cnnb200_components_parents(self._h, C.byref(p)))
+        return p.value
+
+    def components_merge(self, others, count):
+        p, loc = _ptr_loc(others)
+        if loc != DEVICE:
+            raise ValueError("foreign parent arrays must be device tensors")
+        check(self._lib.cnnb200_components_merge(self._h, p, int(count)))
+
+    def components_labels(self, current_start, labels, fresh=True):
+        lp, loc = _ptr_loc(labels)
+        nc = _I64()
+        check(self._lib.cnnb200_components_labels(self._h, int(current_start), lp, loc, int(bool(fresh)), C.byref(nc)))
+        return nc.value
+
+    def sort_by_size(self, labels, member_cutoff=None, max_clusters=None, return_map=False, max_label=None):
+        lp, loc = _ptr_loc(labels)
+        n = labels.shape[0]
+        mc = -1 if member_cutoff is None else int(member_cutoff)
+        mx = -1 if max_clusters is None else int(max_clusters)
+        if return_map:
+            if max_label is None:
+                max_label = int(labels.max()) if n else 0
+            m = np.zeros(max_label + 1, dtype=np.int64)
+            check(self._lib.cnnb200_sort_by_size(self._h, lp, loc, n, mc, mx, m.ctypes.data, m.shape[0]))
+            return m
+        check(self._lib.cnnb200_sort_by_size(self._h, lp, loc, n, mc, mx, None, 0))
+        return None
+
+    def fit_points(self, x, radius_cutoff, n_member_cutoff, similarity_cutoff, labels, current_start=1,
+                   metric="euclidean_r", method="auto", sort_by_size=True, member_cutoff=None, max_clusters=None):
+        xp, loc = _ptr_loc(x)
+        lp, loc2 = _ptr_loc(labels)
+        if loc != loc2:
+            raise ValueError("x and labels must live in the same memory space")
+        n, d = x.shape
+        nc = _I64()
+        check(self._lib.cnnb200_fit_points(
+            self._h, xp, loc, n, d, float(radius_cutoff), METRIC_IDS[metric], METHOD_IDS[method],
+            int(n_member_cutoff), int(similarity_cutoff), int(current_start), int(bool(sort_by_size)),
+            -1 if member_cutoff is None else int(member_cutoff),
+            -1 if max_clusters is None else int(max_clusters), lp, C.byref(nc)))
+        return nc.value
+
+    def stats(self):
+        s = np.zeros(8, dtype=np.int64)
+        check(self._lib.cnnb200_stats(self._h, s.ctypes.data, 8))
+        return {"candidate_edges": int(s[0]), "checks": int(s[1]), "accepted": int(s[2]),
+                "skipped": int(s[3]), "distance_evals": int(s[4]), "rechecks": int(s[5])}
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx

@@ -1,0 +1,237 @@
+// api.cu -- context management, scratch allocation, error reporting, host-buffer pipeline.
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void cnn_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int cnnb200_version(void) { return CNNB200_VERSION; }
+extern "C" const char *cnnb200_last_error(void) { return g_err; }
+
+static void *default_alloc(size_t bytes, void *) {
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+static void default_free(void *p, void *) { cudaFree(p); }
+
+int cnn_ensure(cnnb200_ctx *ctx, Buf &b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return CNNB200_OK;
+    if (b.p) {
+        // the old block may still be in use by work enqueued on the stream
+        CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->free_(b.p, ctx->alloc_user);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8;  // head-room so that slightly larger inputs do not realloc
+    want = (want + 255) & ~(size_t)255;
+    void *p = ctx->alloc(want, ctx->alloc_user);
+    if (!p) {
+        want = (bytes + 255) & ~(size_t)255;
+        p = ctx->alloc(want, ctx->alloc_user);
+    }
+    if (!p) CNN_FAIL(CNNB200_E_NOMEM, "device allocation of %zu bytes failed", want);
+    b.p = p;
+    b.cap = want;
+    return CNNB200_OK;
+}
+
+void cnn_release(cnnb200_ctx *ctx, Buf &b) {
+    if (b.p) ctx->free_(b.p, ctx->alloc_user);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+int cnn_pinned(cnnb200_ctx *ctx, size_t bytes, void **out) {
+    if (ctx->h_pinned_cap < bytes) {
+        if (ctx->h_pinned) {
+            CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFreeHost(ctx->h_pinned);
+            ctx->h_pinned = nullptr;
+            ctx->h_pinned_cap = 0;
+        }
+        size_t want = bytes < 4096 ? 4096 : bytes;
+        CNN_CUDA(cudaMallocHost(&ctx->h_pinned, want));
+        ctx->h_pinned_cap = want;
+    }
+    *out = ctx->h_pinned;
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_ctx_create(int device, cnnb200_ctx **out) {
+    if (!out) CNN_FAIL(CNNB200_E_INVALID, "ctx_create: out is NULL");
+    int count = 0;
+    CNN_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count)
+        CNN_FAIL(CNNB200_E_INVALID, "ctx_create: device %d out of range (%d devices)", device, count);
+    CNN_CUDA(cudaSetDevice(device));
+    cnnb200_ctx *ctx = new (std::nothrow) cnnb200_ctx();
+    if (!ctx) CNN_FAIL(CNNB200_E_NOMEM, "ctx_create: host allocation failed");
+    ctx->device = device;
+    ctx->alloc = default_alloc;
+    ctx->free_ = default_free;
+    cudaDeviceProp prop;
+    CNN_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return CNNB200_OK;
+}
+
+#define FOR_EACH_BUF(c, F)                                                                          \
+    F(c->b_row_ptr) F(c->b_col_idx) F(c->b_perm) F(c->b_deg) F(c->b_x) F(c->b_xs) F(c->b_cell_id)   \
+    F(c->b_cell_id_sorted) F(c->b_idx) F(c->b_cell_start) F(c->b_bbox) F(c->b_cub) F(c->b_tmp0)     \
+    F(c->b_tmp1) F(c->b_tmp2) F(c->b_parent) F(c->b_core) F(c->b_minorig) F(c->b_flags)             \
+    F(c->b_rank) F(c->b_labels) F(c->b_consider) F(c->b_stats) F(c->b_lab_count) F(c->b_lab_first)  \
+    F(c->b_lab_keys) F(c->b_lab_keys2) F(c->b_lab_vals) F(c->b_lab_vals2) F(c->b_lab_map)
+
+extern "C" int cnnb200_ctx_release(cnnb200_ctx *ctx) {
+    if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+#define REL(b) cnn_release(ctx, b);
+    FOR_EACH_BUF(ctx, REL)
+#undef REL
+    ctx->have_nb = false;
+    ctx->have_comp = false;
+    ctx->row_ptr = nullptr;
+    ctx->col_idx = nullptr;
+    ctx->perm = nullptr;
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_ctx_destroy(cnnb200_ctx *ctx) {
+    if (!ctx) return CNNB200_OK;
+    int rc = cnnb200_ctx_release(ctx);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    delete ctx;
+    return rc;
+}
+
+extern "C" int cnnb200_ctx_set_stream(cnnb200_ctx *ctx, void *stream) {
+    if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");
+    ctx->stream = (cudaStream_t)stream;
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_ctx_set_allocator(cnnb200_ctx *ctx, cnnb200_alloc_fn alloc, cnnb200_free_fn free_,
+                                         void *user) {
+    if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");
+    CNN_TRY(cnnb200_ctx_release(ctx));  // blocks from the old allocator must go back to it
+    if (alloc && free_) {
+        ctx->alloc = alloc;
+        ctx->free_ = free_;
+        ctx->alloc_user = user;
+    } else {
+        ctx->alloc = default_alloc;
+        ctx->free_ = default_free;
+        ctx->alloc_user = nullptr;
+    }
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_ctx_synchronize(cnnb200_ctx *ctx) {
+    if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");
+    CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_stats(cnnb200_ctx *ctx, int64_t *stats, int64_t len) {
+    if (!ctx || !stats) CNN_FAIL(CNNB200_E_INVALID, "stats: NULL argument");
+    for (int64_t i = 0; i < len; ++i) stats[i] = i < ST_N ? ctx->stats[i] : 0;
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_neighbours_info(cnnb200_ctx *ctx, int64_t *n, int64_t *nnz, int64_t *max_deg) {
+    if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");
+    if (!ctx->have_nb) CNN_FAIL(CNNB200_E_STATE, "no neighbourhoods held by this context");
+    if (n) *n = ctx->n;
+    if (nnz) *nnz = ctx->nnz;
+    if (max_deg) *max_deg = ctx->max_deg;
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_neighbours_device_view(cnnb200_ctx *ctx, const int64_t **row_ptr,
+                                              const int32_t **col_idx, const int32_t **perm) {
+    if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");
+    if (!ctx->have_nb) CNN_FAIL(CNNB200_E_STATE, "no neighbourhoods held by this context");
+    if (row_ptr) *row_ptr = (const int64_t *)ctx->row_ptr;
+    if (col_idx) *col_idx = ctx->col_idx;
+    if (perm) *perm = ctx->perm;
+    return CNNB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Radius search front end: stage the coordinates on the device, dispatch on method.
+// ------------------------------------------------------------------------------------------
+extern "C" int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x, int loc, int64_t n,
+                                              int64_t d, double radius_cutoff, int metric, int method,
+                                              int64_t *nnz_out) {
+    if (!ctx || !x) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_points: NULL argument");
+    if (n < 1 || d < 1) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_points: need n >= 1 and d >= 1");
+    if (n >= (1ll << 31) - 1) CNN_FAIL(CNNB200_E_RANGE, "neighbours_from_points: n must be < 2^31-1");
+    if (metric != CNNB200_METRIC_EUCLIDEAN_REDUCED && metric != CNNB200_METRIC_EUCLIDEAN)
+        CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_points: unknown metric %d", metric);
+    if (!(radius_cutoff >= 0.0)) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_points: radius_cutoff must be >= 0");
+    if (method == 0) method = d <= 3 ? 1 : 2;
+    if (method == 1 && d > 3) CNN_FAIL(CNNB200_E_INVALID, "grid method needs d <= 3 (got %lld)", (ll)d);
+    if (method < 1 || method > 3) CNN_FAIL(CNNB200_E_INVALID, "unknown method %d", method);
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    ctx->have_nb = false;
+    ctx->have_comp = false;
+    const double *d_x = x;
+    if (loc == CNNB200_HOST) {
+        CNN_TRY(cnn_ensure(ctx, ctx->b_x, sizeof(double) * (size_t)n * (size_t)d));
+        CNN_CUDA(cudaMemcpyAsync(ctx->b_x.p, x, sizeof(double) * (size_t)n * (size_t)d,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+        d_x = ctx->b_x.as<double>();
+    }
+    if (method == 1)
+        CNN_TRY(cnn_grid_search(ctx, d_x, n, d, radius_cutoff, metric));
+    else
+        CNN_TRY(cnn_dense_search(ctx, d_x, n, d, radius_cutoff, metric, method));
+    ctx->have_nb = true;
+    if (nnz_out) *nnz_out = ctx->nnz;
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_fit_points(cnnb200_ctx *ctx, const double *x, int loc, int64_t n, int64_t d,
+                                  double radius_cutoff, int metric, int method, int64_t n_member_cutoff,
+                                  int64_t similarity_cutoff, int64_t current_start, int sort_by_size,
+                                  int64_t member_cutoff, int64_t max_clusters, int64_t *labels,
+                                  int64_t *n_clusters_out) {
+    if (!labels) CNN_FAIL(CNNB200_E_INVALID, "fit_points: labels is NULL");
+    CNN_TRY(cnnb200_neighbours_from_points(ctx, x, loc, n, d, radius_cutoff, metric, method, nullptr));
+    if (!sort_by_size)
+        return cnnb200_fit(ctx, n_member_cutoff, similarity_cutoff, current_start, labels, nullptr, loc,
+                           n_clusters_out);
+    // keep the labels on the device between the fit and the relabel: one D2H at the end
+    CNN_TRY(cnn_ensure(ctx, ctx->b_labels, sizeof(ll) * (size_t)n));
+    int64_t *d_labels = loc == CNNB200_HOST ? (int64_t *)ctx->b_labels.p : labels;
+    if (loc == CNNB200_HOST) CNN_CUDA(cudaMemsetAsync(d_labels, 0, sizeof(ll) * (size_t)n, ctx->stream));
+    CNN_TRY(cnnb200_components_begin(ctx, n_member_cutoff, similarity_cutoff, nullptr, CNNB200_DEVICE));
+    CNN_TRY(cnnb200_components_edges(ctx, 0, n));
+    int64_t n_clusters = 0;  // asking for it also refreshes the counters behind cnnb200_stats
+    CNN_TRY(cnnb200_components_labels(ctx, current_start, d_labels, CNNB200_DEVICE, /*fresh=*/1, &n_clusters));
+    if (n_clusters_out) *n_clusters_out = n_clusters;
+    CNN_TRY(cnnb200_sort_by_size(ctx, d_labels, CNNB200_DEVICE, n, member_cutoff, max_clusters, nullptr, 0));
+    if (loc == CNNB200_HOST) {
+        CNN_CUDA(cudaMemcpyAsync(labels, d_labels, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return CNNB200_OK;
+}

@@ -1,0 +1,106 @@
+// common.cuh -- context, scratch buffers and error plumbing shared by all translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "cnnb200.h"
+
+typedef int64_t ll;  // the ABI index type (long on LP64)
+
+void cnn_set_error(const char *fmt, ...);
+
+#define CNN_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            cnn_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return CNNB200_E_CUDA;                                                          \
+        }                                                                                   \
+    } while (0)
+
+#define CNN_TRY(call)                  \
+    do {                               \
+        int rc__ = (call);             \
+        if (rc__ != CNNB200_OK) return rc__; \
+    } while (0)
+
+#define CNN_KERNEL_CHECK() CNN_CUDA(cudaGetLastError())
+
+#define CNN_FAIL(code, ...)        \
+    do {                           \
+        cnn_set_error(__VA_ARGS__); \
+        return (code);             \
+    } while (0)
+
+// A growable device scratch buffer owned by the context.
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+enum StatSlot {
+    ST_EDGES = 0,
+    ST_CHECKS = 1,
+    ST_ACCEPTED = 2,
+    ST_SKIPPED = 3,
+    ST_DIST = 4,
+    ST_RECHECK = 5,
+    ST_N = 8
+};
+
+struct cnnb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cnnb200_alloc_fn alloc = nullptr;
+    cnnb200_free_fn free_ = nullptr;
+    void *alloc_user = nullptr;
+    int sm_count = 148;
+
+    // ---- neighbourhood structure (internal index space) -------------------------------
+    bool have_nb = false;
+    ll n = 0, nnz = 0, max_deg = 0;
+    const ll *row_ptr = nullptr;       // [n+1]  (points into b_row_ptr or borrowed memory)
+    const int32_t *col_idx = nullptr;  // [nnz]
+    const int32_t *perm = nullptr;     // [n] internal -> caller index; nullptr = identity
+    Buf b_row_ptr, b_col_idx, b_perm, b_deg;
+
+    // ---- neighbour search scratch ------------------------------------------------------
+    Buf b_x;         // f64 [n, d] as given by the caller (device copy)
+    Buf b_xs;        // f64 SoA [d][n] in cell-sorted order
+    Buf b_cell_id, b_cell_id_sorted, b_idx, b_cell_start, b_bbox, b_cub;
+    Buf b_tmp0, b_tmp1, b_tmp2;
+
+    // ---- components ----------------------------------------------------------------------
+    bool have_comp = false;
+    ll n_member_cutoff = 0, similarity_cutoff = 0;
+    Buf b_parent;  // int32 [n]
+    Buf b_core;    // uint8 [n]
+    Buf b_minorig, b_flags, b_rank, b_labels, b_consider, b_stats;
+    Buf b_lab_count, b_lab_first, b_lab_keys, b_lab_keys2, b_lab_vals, b_lab_vals2, b_lab_map;
+
+    // ---- pinned host staging ---------------------------------------------------------------
+    void *h_pinned = nullptr;
+    size_t h_pinned_cap = 0;
+
+    ll stats[ST_N] = {0};
+};
+
+int cnn_ensure(cnnb200_ctx *ctx, Buf &b, size_t bytes);
+void cnn_release(cnnb200_ctx *ctx, Buf &b);
+int cnn_pinned(cnnb200_ctx *ctx, size_t bytes, void **out);
+
+static inline int cnn_blocks(ll work_items, int per_block) {
+    ll b = (work_items + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// --- stage entry points implemented across the .cu files ----------------------------------
+int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric);
+int cnn_dense_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric,
+                     int method);
+int cnn_scan_deg_to_row_ptr(cnnb200_ctx *ctx, const int32_t *deg, ll n, ll *row_ptr, ll *nnz_out,
+                            ll *max_deg_out);

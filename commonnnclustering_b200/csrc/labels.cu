@@ -1,0 +1,267 @@
+// labels.cu -- K7: cluster numbering as FitterExtBFS produces it and Labels.sort_by_size.
+//
+// (1) Numbering.  The reference's outer loop (_fit.pyx:434-491) visits points in ascending index
+//     and opens a new cluster number whenever it meets an unassigned core point, so cluster k
+//     (counting from current_start) is the component with the k-th smallest minimum member
+//     index.  Here: per component the smallest caller-space member index (atomicMin through
+//     perm[]), a flag per such index, an exclusive scan of the flags = the rank.
+// (2) Labels.sort_by_size (_types.pyx:212-286): Counter(labels).most_common() is a stable sort by
+//     count descending over first-occurrence order; rank > max_clusters -> 0, size < member_cutoff
+//     -> 0, survivors renumbered 1, 2, ...  Here: per-label count and first occurrence by
+//     warp-aggregated atomics, one 64-bit key (inverted count : first index) per label, radix
+//     sort, survivor scan, gather through the map.
+#include <cub/cub.cuh>
+#include <string.h>
+
+#include "common.cuh"
+
+int cnn_fetch_comp_stats(cnnb200_ctx *ctx);
+
+__global__ void fill_int_kernel(int *a, ll n, int v) {
+    ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+__global__ void minorig_kernel(const int *__restrict__ parent, const uint8_t *__restrict__ core,
+                               const int *__restrict__ perm, ll n, int *minorig) {
+    ll p = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (p >= n || !core[p]) return;
+    atomicMin(minorig + parent[p], perm[p]);
+}
+
+// flags[min caller index of each component] = 1
+__global__ void root_flag_kernel(const int *__restrict__ parent, const uint8_t *__restrict__ core,
+                                 const int *__restrict__ minorig, ll n, int *flags) {
+    ll p = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (p >= n || !core[p] || parent[p] != (int)p) return;
+    flags[minorig ? minorig[p] : (int)p] = 1;
+}
+
+__global__ void write_labels_kernel(const int *__restrict__ parent, const uint8_t *__restrict__ core,
+                                    const int *__restrict__ perm, const int *__restrict__ minorig,
+                                    const int *__restrict__ rank, ll n, ll current_start, ll *labels,
+                                    int fresh) {
+    ll p = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    ll o = perm ? perm[p] : p;
+    if (core[p]) {
+        int r = parent[p];
+        labels[o] = current_start + rank[minorig ? minorig[r] : r];
+    } else if (fresh) {
+        labels[o] = 0;
+    }
+}
+
+extern "C" int cnnb200_components_labels(cnnb200_ctx *ctx, int64_t current_start, int64_t *labels, int loc,
+                                         int fresh, int64_t *n_clusters_out) {
+    if (!ctx || !labels) CNN_FAIL(CNNB200_E_INVALID, "components_labels: NULL argument");
+    if (!ctx->have_comp) CNN_FAIL(CNNB200_E_STATE, "components_labels: call components_begin first");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ll n = ctx->n;
+    const int *parent = ctx->b_parent.as<int>();
+    const uint8_t *core = ctx->b_core.as<uint8_t>();
+    int nb = cnn_blocks(n, 256);
+    int *minorig = nullptr;
+    if (ctx->perm) {
+        CNN_TRY(cnn_ensure(ctx, ctx->b_minorig, sizeof(int) * (size_t)n));
+        minorig = ctx->b_minorig.as<int>();
+        fill_int_kernel<<<nb, 256, 0, st>>>(minorig, n, 0x7fffffff);
+        minorig_kernel<<<nb, 256, 0, st>>>(parent, core, ctx->perm, n, minorig);
+    }
+    CNN_TRY(cnn_ensure(ctx, ctx->b_flags, sizeof(int) * (size_t)(n + 1)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_rank, sizeof(int) * (size_t)(n + 1)));
+    CNN_CUDA(cudaMemsetAsync(ctx->b_flags.p, 0, sizeof(int) * (size_t)(n + 1), st));
+    root_flag_kernel<<<nb, 256, 0, st>>>(parent, core, minorig, n, ctx->b_flags.as<int>());
+    CNN_KERNEL_CHECK();
+    size_t need = 0;
+    CNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->b_flags.as<int>(), ctx->b_rank.as<int>(),
+                                           (int)(n + 1), st));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
+    size_t cap = ctx->b_cub.cap;
+    CNN_CUDA(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, cap, ctx->b_flags.as<int>(), ctx->b_rank.as<int>(),
+                                           (int)(n + 1), st));
+    ll *d_labels = labels;
+    if (loc == CNNB200_HOST) {
+        CNN_TRY(cnn_ensure(ctx, ctx->b_labels, sizeof(ll) * (size_t)n));
+        d_labels = ctx->b_labels.as<ll>();
+        if (!fresh) CNN_CUDA(cudaMemcpyAsync(d_labels, labels, sizeof(ll) * (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    write_labels_kernel<<<nb, 256, 0, st>>>(parent, core, ctx->perm, minorig, ctx->b_rank.as<int>(), n,
+                                            current_start, d_labels, fresh);
+    CNN_KERNEL_CHECK();
+    if (loc == CNNB200_HOST)
+        CNN_CUDA(cudaMemcpyAsync(labels, d_labels, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (n_clusters_out || loc == CNNB200_HOST) {
+        int *h;
+        CNN_TRY(cnn_pinned(ctx, 128, (void **)&h));
+        CNN_CUDA(cudaMemcpyAsync(h + 24, ctx->b_rank.as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CNN_TRY(cnn_fetch_comp_stats(ctx));  // synchronises
+        if (n_clusters_out) *n_clusters_out = h[24];
+    }
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_fit(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_t similarity_cutoff,
+                           int64_t current_start, int64_t *labels, uint8_t *consider, int loc,
+                           int64_t *n_clusters_out) {
+    if (!ctx || !labels) CNN_FAIL(CNNB200_E_INVALID, "fit: NULL argument");
+    if (!ctx->have_nb) CNN_FAIL(CNNB200_E_STATE, "fit: no neighbourhoods held by this context");
+    CNN_TRY(cnnb200_components_begin(ctx, n_member_cutoff, similarity_cutoff, consider, loc));
+    CNN_TRY(cnnb200_components_edges(ctx, 0, ctx->n));
+    int fresh = (consider == nullptr && loc == CNNB200_HOST) ? 1 : 0;
+    CNN_TRY(cnnb200_components_labels(ctx, current_start, labels, loc, fresh, n_clusters_out));
+    if (consider) {  // every point has been visited: consider[:] = 0 (_fit.pyx:434-437)
+        if (loc == CNNB200_HOST)
+            memset(consider, 0, (size_t)ctx->n);
+        else
+            CNN_CUDA(cudaMemsetAsync(consider, 0, (size_t)ctx->n, ctx->stream));
+    }
+    return CNNB200_OK;
+}
+
+// ---- Labels.sort_by_size ------------------------------------------------------------------------
+__global__ void label_hist_kernel(const ll *__restrict__ labels, ll n, int *count, int *first, int *flag,
+                                  ll max_label) {
+    ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    bool active = i < n;
+    ll l = active ? labels[i] : 0;
+    if (active && (l < 0 || l > max_label)) { *flag = 1; active = false; }
+    active = active && l > 0;
+    // warp-aggregate equal labels: one atomic per distinct label per warp
+    unsigned am = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    unsigned peers = __match_any_sync(am, l);
+    int leader = __ffs(peers) - 1;
+    if ((int)(threadIdx.x & 31) == leader) {
+        atomicAdd(count + l, __popc(peers));
+        atomicMin(first + l, (int)i);  // lanes ascend with i: the leader holds the smallest index
+    }
+}
+
+__global__ void label_keys_kernel(const int *__restrict__ count, const int *__restrict__ first, ll L,
+                                  unsigned long long *keys, int *vals) {
+    ll l = blockIdx.x * (ll)blockDim.x + threadIdx.x + 1;  // labels 1 .. L-1
+    if (l >= L) return;
+    int c = count[l];
+    keys[l - 1] = c > 0 ? ((unsigned long long)(0xffffffffu - (unsigned)c) << 32) | (unsigned)first[l]
+                        : 0xffffffffffffffffull;
+    vals[l - 1] = (int)l;
+}
+
+// survivors in rank order: t-th entry (rank t+1) survives if it exists, rank <= max_clusters and
+// size >= member_cutoff
+__global__ void label_survivor_kernel(const unsigned long long *__restrict__ keys, ll m, ll member_cutoff,
+                                      ll max_clusters, int *surv) {
+    ll t = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (t > m) return;
+    if (t == m) { surv[m] = 0; return; }
+    unsigned long long k = keys[t];
+    bool ok = k != 0xffffffffffffffffull;
+    ll size = (ll)(0xffffffffu - (unsigned)(k >> 32));
+    ok = ok && (max_clusters < 0 || t + 1 <= max_clusters) && size >= member_cutoff;
+    surv[t] = ok ? 1 : 0;
+}
+
+__global__ void label_map_kernel(const int *__restrict__ vals, const int *__restrict__ surv,
+                                 const int *__restrict__ surv_rank, ll m, ll *map) {
+    ll t = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    map[vals[t]] = surv[t] ? (ll)surv_rank[t] + 1 : 0;
+}
+
+__global__ void label_apply_kernel(ll *labels, ll n, const ll *__restrict__ map, ll max_label) {
+    ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ll l = labels[i];
+    if (l >= 0 && l <= max_label) labels[i] = map[l];  // negative labels are reported through the flag
+}
+
+extern "C" int cnnb200_sort_by_size(cnnb200_ctx *ctx, int64_t *labels, int loc, int64_t n,
+                                    int64_t member_cutoff, int64_t max_clusters, int64_t *map_out,
+                                    int64_t map_len) {
+    if (!ctx || !labels) CNN_FAIL(CNNB200_E_INVALID, "sort_by_size: NULL argument");
+    if (n < 0 || n >= (1ll << 31) - 1) CNN_FAIL(CNNB200_E_RANGE, "sort_by_size: n out of range");
+    if (n == 0) return CNNB200_OK;
+    if (member_cutoff < 0) member_cutoff = 2;  // None -> 2 (_types.pyx:235-237)
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ll *d_labels = labels;
+    if (loc == CNNB200_HOST) {
+        CNN_TRY(cnn_ensure(ctx, ctx->b_labels, sizeof(ll) * (size_t)n));
+        d_labels = ctx->b_labels.as<ll>();
+        CNN_CUDA(cudaMemcpyAsync(d_labels, labels, sizeof(ll) * (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    // largest label -> table size
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
+    ll *d_max = ctx->b_tmp2.as<ll>() + 2;
+    size_t need = 0;
+    CNN_CUDA(cub::DeviceReduce::Max(nullptr, need, d_labels, d_max, (int)n, st));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
+    size_t cap = ctx->b_cub.cap;
+    CNN_CUDA(cub::DeviceReduce::Max(ctx->b_cub.p, cap, d_labels, d_max, (int)n, st));
+    ll *h;
+    CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
+    CNN_CUDA(cudaMemcpyAsync(h, d_max, sizeof(ll), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaStreamSynchronize(st));
+    ll max_label = h[0];
+    if (max_label < 0) CNN_FAIL(CNNB200_E_INVALID, "sort_by_size: negative labels");
+    if (max_label >= (1ll << 31) - 2) CNN_FAIL(CNNB200_E_RANGE, "sort_by_size: label %lld too large", max_label);
+    ll L = max_label + 1, m = L - 1;
+    if (m > 0) {
+        CNN_TRY(cnn_ensure(ctx, ctx->b_lab_count, sizeof(int) * (size_t)L));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_lab_first, sizeof(int) * (size_t)L));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_lab_keys, sizeof(ll) * (size_t)m));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_lab_keys2, sizeof(ll) * (size_t)m));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_lab_vals, sizeof(int) * (size_t)(m + 1)));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_lab_vals2, sizeof(int) * (size_t)(m + 1)));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_lab_map, sizeof(ll) * (size_t)L));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_flags, sizeof(int) * (size_t)(m + 1)));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_rank, sizeof(int) * (size_t)(m + 1)));
+        int *count = ctx->b_lab_count.as<int>(), *first = ctx->b_lab_first.as<int>();
+        int *flag = ctx->b_tmp2.as<int>();
+        CNN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+        CNN_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)L, st));
+        fill_int_kernel<<<cnn_blocks(L, 256), 256, 0, st>>>(first, L, 0x7fffffff);
+        label_hist_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_labels, n, count, first, flag, max_label);
+        unsigned long long *keys = ctx->b_lab_keys.as<unsigned long long>();
+        unsigned long long *keys2 = ctx->b_lab_keys2.as<unsigned long long>();
+        int *vals = ctx->b_lab_vals.as<int>(), *vals2 = ctx->b_lab_vals2.as<int>();
+        label_keys_kernel<<<cnn_blocks(m, 256), 256, 0, st>>>(count, first, L, keys, vals);
+        CNN_KERNEL_CHECK();
+        size_t need_sort = 0, need_scan = 0;
+        CNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need_sort, keys, keys2, vals, vals2, (int)m, 0, 64, st));
+        CNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need_scan, ctx->b_flags.as<int>(), ctx->b_rank.as<int>(),
+                                               (int)(m + 1), st));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need_sort > need_scan ? need_sort : need_scan));
+        cap = ctx->b_cub.cap;
+        CNN_CUDA(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, cap, keys, keys2, vals, vals2, (int)m, 0, 64, st));
+        label_survivor_kernel<<<cnn_blocks(m + 1, 256), 256, 0, st>>>(keys2, m, member_cutoff, max_clusters,
+                                                                        ctx->b_flags.as<int>());
+        cap = ctx->b_cub.cap;
+        CNN_CUDA(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, cap, ctx->b_flags.as<int>(), ctx->b_rank.as<int>(),
+                                               (int)(m + 1), st));
+        ll *map = ctx->b_lab_map.as<ll>();
+        CNN_CUDA(cudaMemsetAsync(map, 0, sizeof(ll), st));
+        label_map_kernel<<<cnn_blocks(m, 256), 256, 0, st>>>(vals2, ctx->b_flags.as<int>(), ctx->b_rank.as<int>(), m, map);
+        label_apply_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_labels, n, map, max_label);
+        CNN_KERNEL_CHECK();
+        if (map_out && map_len > 0) {
+            ll cnt = map_len < L ? map_len : L;
+            CNN_CUDA(cudaMemcpyAsync(map_out, map, sizeof(ll) * (size_t)cnt, cudaMemcpyDeviceToHost, st));
+            for (ll k = cnt; k < map_len; ++k) map_out[k] = 0;
+        }
+    } else if (map_out && map_len > 0) {
+        for (ll k = 0; k < map_len; ++k) map_out[k] = 0;
+    }
+    if (loc == CNNB200_HOST)
+        CNN_CUDA(cudaMemcpyAsync(labels, d_labels, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (loc == CNNB200_HOST || map_out) {
+        int *hf = (int *)h + 8;
+        *hf = 0;
+        if (m > 0) CNN_CUDA(cudaMemcpyAsync(hf, ctx->b_tmp2.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CNN_CUDA(cudaStreamSynchronize(st));
+        if (*hf) CNN_FAIL(CNNB200_E_INVALID, "sort_by_size: negative labels");
+    }
+    return CNNB200_OK;
+}

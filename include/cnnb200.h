@@ -1,0 +1,198 @@
+/*
+ * cnnb200.h -- C-ABI of the B200-native common-nearest-neighbour clustering fit path.
+ *
+ * This is the drop-in boundary: what a maintainer of the reference (cnnclustering 0.5.0,
+ * Python/Cython) would bind with ctypes/cffi/Cython `cdef extern` to run `Clustering.fit`
+ * on a B200.  Plain pointers and sizes only; no torch / C++ types.  Citations below name the
+ * reference interface (path relative to the reference root) each entry point replaces.
+ *
+ * The reference drives its components through per-point virtual calls
+ * (`_get(index)`, `_check(na, nb)`; src/cnnclustering/_types.pxd:144-251).  That granularity
+ * cannot survive on a GPU, so every entry point here is a BULK version of a reference role:
+ * the whole neighbourhood structure of a data set, all candidate edges, all labels.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative CNNB200_E_* code otherwise;
+ *     cnnb200_last_error() returns a thread-local message for the last failure.
+ *   - `loc` arguments say where a caller buffer lives: CNNB200_HOST or CNNB200_DEVICE.
+ *   - element types at the boundary are the reference's (_primitive_types.pxd:4-7):
+ *     coordinates double, indices/labels int64_t, consider uint8_t.
+ *   - a context is bound to one CUDA device and one stream; it is not thread-safe.
+ *     All work is enqueued on the context's stream; calls that return data in HOST
+ *     buffers synchronise that stream before returning.
+ *   - device scratch (CSR, parents, ...) is owned by the context and reused across calls;
+ *     it is obtained through the allocator hook (cudaMalloc by default; the Python host
+ *     layer routes it to torch's caching allocator).
+ */
+#ifndef CNNB200_H
+#define CNNB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNNB200_VERSION 100 /* 0.1.0 */
+
+#define CNNB200_HOST 0
+#define CNNB200_DEVICE 1
+
+/* Metric ids: MetricExtEuclideanReduced (_types.pyx:2250-2287, recipe key "euclidean_r") and
+ * MetricExtEuclidean (_types.pyx:2170-2207, "euclidean"). */
+#define CNNB200_METRIC_EUCLIDEAN_REDUCED 0
+#define CNNB200_METRIC_EUCLIDEAN 1
+
+#define CNNB200_OK 0
+#define CNNB200_E_INVALID -1   /* bad argument                                  */
+#define CNNB200_E_CUDA -2      /* a CUDA runtime call failed                    */
+#define CNNB200_E_NOMEM -3     /* device or host allocation failed              */
+#define CNNB200_E_STATE -4     /* call order: no neighbourhoods / components yet */
+#define CNNB200_E_RANGE -5     /* size exceeds an implementation limit          */
+
+typedef struct cnnb200_ctx cnnb200_ctx;
+
+/* Allocator hook: alloc returns a device pointer for `bytes` on the context's device
+ * (NULL on failure); free releases it.  `user` is passed through. */
+typedef void *(*cnnb200_alloc_fn)(size_t bytes, void *user);
+typedef void (*cnnb200_free_fn)(void *ptr, void *user);
+
+int cnnb200_version(void);
+const char *cnnb200_last_error(void);
+
+int cnnb200_ctx_create(int device, cnnb200_ctx **out);
+int cnnb200_ctx_destroy(cnnb200_ctx *ctx);
+/* `stream` is a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = default. */
+int cnnb200_ctx_set_stream(cnnb200_ctx *ctx, void *stream);
+int cnnb200_ctx_set_allocator(cnnb200_ctx *ctx, cnnb200_alloc_fn alloc, cnnb200_free_fn free_,
+                              void *user);
+int cnnb200_ctx_synchronize(cnnb200_ctx *ctx);
+/* Releases all device scratch held by the context (it is re-acquired on demand). */
+int cnnb200_ctx_release(cnnb200_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------
+ * Radius-neighbour search -> sorted CSR held by the context.
+ * Replaces NeighboursGetterExtBruteForce._get (_types.pyx:1692-1710) over
+ * DistanceGetterExtMetric._get_single (:1979-1985) and Metric._calc_distance (:2253-2267 /
+ * :2173-2187) for ALL points at once.  `radius_cutoff` is already metric-adjusted
+ * (ClusterParameters.radius_cutoff, _types.pxd:119-125: r*r for the reduced metric).
+ * Neighbour sets are exactly the reference's: the acceptance test is the same f64
+ * expression (sequential sum of squared differences, no FMA, `<=`); self is included.
+ *
+ * x: row-major double [n, d] (InputDataExtComponentsMemoryview layout, _types.pyx:1040-1059).
+ * method: 0 = auto (grid for d <= 3, tiled otherwise), 1 = uniform-grid cell list (d <= 3),
+ *         2 = tiled all-pairs in f64, 3 = tiled tensor-core filter + f64 boundary recheck.
+ * The CSR lives in an internal index space (cell-sorted for the grid method) together with
+ * the permutation back to the caller's indices; cnnb200_neighbours_export converts.
+ * nnz_out (optional): total number of neighbour entries.
+ * ------------------------------------------------------------------------------------- */
+int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x, int loc, int64_t n,
+                                   int64_t d, double radius_cutoff, int metric, int method,
+                                   int64_t *nnz_out);
+
+/* Precomputed neighbourhoods, CSR form (row_ptr int64 [n+1]; col_idx int32 or int64 [nnz],
+ * `idx_bytes` = 4 or 8), rows ascending.  Replaces NeighboursGetterExtLookup._get
+ * (_types.pyx:1806-1817) for all rows.  With loc == CNNB200_DEVICE, idx_bytes == 4 and
+ * borrow != 0 the buffers are used in place (caller keeps them alive); otherwise copied. */
+int cnnb200_neighbours_from_csr(cnnb200_ctx *ctx, const int64_t *row_ptr, const void *col_idx,
+                                int idx_bytes, int loc, int borrow, int64_t n, int64_t nnz);
+
+/* Precomputed neighbourhoods in the reference's own container layout: zero-padded int64
+ * [n, max_deg] plus int64 counts [n] (InputDataExtNeighbourhoodsMemoryview,
+ * _types.pyx:1153-1217; produced by recipes.prepare_neighbourhoods, recipes.py:150-179). */
+int cnnb200_neighbours_from_padded(cnnb200_ctx *ctx, const int64_t *padded,
+                                   const int64_t *counts, int loc, int64_t n, int64_t max_deg);
+
+/* Sizes of the neighbourhood structure currently held. */
+int cnnb200_neighbours_info(cnnb200_ctx *ctx, int64_t *n, int64_t *nnz, int64_t *max_deg);
+
+/* Copies the neighbourhoods out in the CALLER's index space, rows ascending:
+ * row_ptr int64 [n+1], col_idx int64 [nnz] (either may be NULL to skip). */
+int cnnb200_neighbours_export(cnnb200_ctx *ctx, int64_t *row_ptr, int64_t *col_idx, int loc);
+
+/* Raw view of the internal CSR (device pointers, valid until the next neighbours_* call):
+ * row_ptr int64 [n+1], col_idx int32 [nnz], perm int32 [n] (internal -> caller index; NULL
+ * when the internal space is the caller's). */
+int cnnb200_neighbours_device_view(cnnb200_ctx *ctx, const int64_t **row_ptr,
+                                   const int32_t **col_idx, const int32_t **perm);
+
+/* ---------------------------------------------------------------------------------------
+ * Common-neighbour similarity, bulk.  Replaces SimilarityCheckerExt*._get
+ * (_types.pyx:2541-2556, :2612-2634, :2708-2753): counts[k] = |N(i) ∩ N(j)| for the k-th CSR
+ * entry (row i, column j) when i < j and both rows have more than n_member_cutoff entries
+ * (`_enough`, _types.pyx:1408-1411); every other slot gets 0xFFFFFFFF.
+ * counts: uint32 [nnz] in the internal CSR order, DEVICE or HOST.
+ * n_edges_out (optional): number of evaluated (i<j, both core) edges.
+ * ------------------------------------------------------------------------------------- */
+int cnnb200_cn_count(cnnb200_ctx *ctx, int64_t n_member_cutoff, uint32_t *counts, int loc,
+                     int64_t *n_edges_out);
+
+/* ---------------------------------------------------------------------------------------
+ * Density-connected components.  Replaces FitterExtBFS._fit (_fit.pyx:408-491) including its
+ * use of SimilarityCheckerExt*._check (_types.pyx:2580-2610 / :2654-2706) and `_enough`.
+ *
+ * cnnb200_fit: labels int64 [n] in/out, consider uint8 [n] in/out (NULL = all points
+ *   considered = a fresh fit).  Semantics are exactly the reference's: point i is a core
+ *   point when consider[i] and |N(i)| > n_member_cutoff; core points i,j are linked when j is
+ *   in N(i) and |N(i) ∩ N(j)| >= similarity_cutoff (similarity_cutoff == 0 links always);
+ *   components are numbered current_start, current_start+1, ... by ascending smallest member
+ *   index and written to labels[]; labels of non-core points are left as they are;
+ *   consider[] is zeroed.  With consider == NULL and loc == HOST, labels need not be
+ *   initialised (treated as all zero, as Clustering.fit does, cluster.pyx:316-326).
+ *   n_clusters_out (optional): number of components numbered.
+ *
+ * The three-step form exists for row-sharded multi-GPU runs:
+ *   components_begin   -> every rank (full neighbourhoods on every rank)
+ *   components_edges   -> each rank on its own row block [row_begin, row_end)
+ *   (all-gather of the parent arrays, cnnb200_components_parents / _merge)
+ *   components_labels  -> numbering + label write-out
+ * ------------------------------------------------------------------------------------- */
+int cnnb200_fit(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_t similarity_cutoff,
+                int64_t current_start, int64_t *labels, uint8_t *consider, int loc,
+                int64_t *n_clusters_out);
+
+int cnnb200_components_begin(cnnb200_ctx *ctx, int64_t n_member_cutoff,
+                             int64_t similarity_cutoff, const uint8_t *consider, int loc);
+int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end);
+/* Device pointer to the int32 [n] parent array (internal index space). */
+int cnnb200_components_parents(cnnb200_ctx *ctx, int32_t **parents);
+/* Unions (i, other[i]) for every i of `count` foreign parent arrays laid out back to back
+ * (int32 [count, n], DEVICE). */
+int cnnb200_components_merge(cnnb200_ctx *ctx, const int32_t *others, int64_t count);
+int cnnb200_components_labels(cnnb200_ctx *ctx, int64_t current_start, int64_t *labels, int loc,
+                              int fresh, int64_t *n_clusters_out);
+
+/* ---------------------------------------------------------------------------------------
+ * Labels.sort_by_size (_types.pyx:212-286), in place on labels int64 [n] (HOST or DEVICE):
+ * clusters ranked by size descending, ties by first occurrence (Counter.most_common order);
+ * rank > max_clusters -> 0; size < member_cutoff -> 0; survivors renumbered 1, 2, ...
+ * member_cutoff < 0 means None (2); max_clusters < 0 means None.
+ * map_out (optional, HOST int64 [max_label+1], sized by the caller via map_len): old -> new.
+ * ------------------------------------------------------------------------------------- */
+int cnnb200_sort_by_size(cnnb200_ctx *ctx, int64_t *labels, int loc, int64_t n,
+                         int64_t member_cutoff, int64_t max_clusters, int64_t *map_out,
+                         int64_t map_len);
+
+/* ---------------------------------------------------------------------------------------
+ * One call for the whole of `Clustering.fit` on coordinates (cluster.pyx:256-392 with the
+ * "coordinates" recipe, recipes.py:318-328): neighbour search, fit, optional sort_by_size.
+ * x and labels in HOST or DEVICE memory (`loc`).  Fresh fit (labels fully overwritten).
+ * ------------------------------------------------------------------------------------- */
+int cnnb200_fit_points(cnnb200_ctx *ctx, const double *x, int loc, int64_t n, int64_t d,
+                       double radius_cutoff, int metric, int method, int64_t n_member_cutoff,
+                       int64_t similarity_cutoff, int64_t current_start, int sort_by_size,
+                       int64_t member_cutoff, int64_t max_clusters, int64_t *labels,
+                       int64_t *n_clusters_out);
+
+/* Counters of the last fit / search, for measurement (all optional, HOST):
+ *   stats[0] candidate edges (i<j, both core)      stats[1] CN checks executed
+ *   stats[2] edges accepted by a check             stats[3] edges skipped (already connected)
+ *   stats[4] distance evaluations (neighbour search, count pass)
+ *   stats[5] pairs re-checked in f64 (tensor-core filter path) */
+int cnnb200_stats(cnnb200_ctx *ctx, int64_t *stats, int64_t len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNNB200_H */

@@ -46,7 +46,12 @@ SIGNATURES = {
     "cnnb200_fit_points": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int, C.c_int, _I64, _I64, _I64,
                            C.c_int, _I64, _I64, _P, C.POINTER(_I64)],
     "cnnb200_stats": [_P, _P, _I64],
+    "cnnb200_ctx_set_timing": [_P, C.c_int],
+    "cnnb200_timings": [_P, _P, _P, _I64, C.POINTER(_I64), C.c_int],
 }
+
+TIME_SLOTS = ["h2d", "grid_build", "search_count", "scan", "search_fill", "ingest", "comp_init", "comp_sample",
+              "comp_edges", "comp_flatten", "labels", "sort_by_size", "d2h", "cn_count"]
 
 _lib = None
 
@@ -277,6 +282,19 @@ class Context:
             -1 if member_cutoff is None else int(member_cutoff),
             -1 if max_clusters is None else int(max_clusters), lp, C.byref(nc)))
         return nc.value
+
+    def set_timing(self, enabled: bool):
+        check(self._lib.cnnb200_ctx_set_timing(self._h, int(bool(enabled))))
+
+    def timings(self, reset: bool = True):
+        """Per-stage device time (CUDA events on the context's stream) accumulated since the last
+        reset: {stage: (total ms, calls)} plus the number of hand-written kernels launched."""
+        k = len(TIME_SLOTS)
+        ms = np.zeros(k, dtype=np.float64)
+        calls = np.zeros(k, dtype=np.int64)
+        launches = _I64()
+        check(self._lib.cnnb200_timings(self._h, ms.ctypes.data, calls.ctypes.data, k, C.byref(launches), int(reset)))
+        return {name: (float(ms[i]), int(calls[i])) for i, name in enumerate(TIME_SLOTS)}, launches.value
 
     def stats(self):
         s = np.zeros(8, dtype=np.int64)

@@ -1,0 +1,474 @@
+"""Component types of the B200 fit path -- the host-side mirror of the reference's ``_types``.
+
+Same roles and names as the reference (``src/cnnclustering/_types.pyx``): ``ClusterParameters``,
+``Labels``, InputData, NeighboursGetter, Metric, SimilarityChecker.  The reference drives them one
+point / one pair at a time through virtual calls; here each role exposes a BULK method that runs
+on the device through the C-ABI (``include/cnnb200.h``):
+
+    NeighboursGetter.get_all(input_data, cluster_params)    -> Neighbourhoods (CSR in HBM)
+    SimilarityChecker.get_all(neighbourhoods, cluster_params) -> common-neighbour count per edge
+    Fitter.fit(input_data, labels, cluster_params)            (in ``_fit.py``)
+
+The per-item reference methods that are cheap to answer from the bulk result (``get``, ``check``,
+``calc_distance``) are provided too so that the reference's unit tests translate one to one.
+"""
+from collections import defaultdict
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+
+P_AINDEX = np.int64    # _primitive_types.pyx:4
+P_AVALUE = np.float64  # _primitive_types.pyx:5
+P_ABOOL = np.uint8     # _primitive_types.pyx:7
+
+
+class ClusterParameters:
+    """Reference: ``_types.pyx:22-85``."""
+
+    def __init__(self, radius_cutoff: float, similarity_cutoff: int = 0,
+                 similarity_cutoff_continuous: float = 0., n_member_cutoff: Optional[int] = None,
+                 current_start: int = 1):
+        if n_member_cutoff is None:
+            n_member_cutoff = similarity_cutoff
+        self.radius_cutoff = float(radius_cutoff)
+        self.similarity_cutoff = int(similarity_cutoff)
+        self.similarity_cutoff_continuous = float(similarity_cutoff_continuous)
+        self.n_member_cutoff = int(n_member_cutoff)
+        self.current_start = int(current_start)
+
+    def to_dict(self):
+        return {
+            "radius_cutoff": self.radius_cutoff,
+            "similarity_cutoff": self.similarity_cutoff,
+            "similarity_cutoff_continuous": self.similarity_cutoff_continuous,
+            "n_member_cutoff": self.n_member_cutoff,
+            "current_start": self.current_start,
+        }
+
+    def __repr__(self):
+        return f"{self.to_dict()!r}"
+
+    __str__ = __repr__
+
+
+class Labels:
+    """Cluster label assignments.  Reference: ``_types.pyx:88-286``.
+
+    ``labels`` (int64) and ``consider`` (uint8) are NumPy arrays that fitters mutate in place, as
+    in the reference (``Labels.labels`` is a view, ``_types.pyx:143-144``)."""
+
+    def __init__(self, labels, *, consider=None, meta=None):
+        self._labels = np.ascontiguousarray(labels, dtype=P_AINDEX) if not (
+            isinstance(labels, np.ndarray) and labels.dtype == P_AINDEX and labels.flags.c_contiguous) else labels
+        if consider is None:
+            self._consider = np.ones_like(self._labels, dtype=P_ABOOL)
+        else:
+            self._consider = consider if (
+                isinstance(consider, np.ndarray) and consider.dtype == P_ABOOL and consider.flags.c_contiguous
+            ) else np.ascontiguousarray(consider, dtype=P_ABOOL)
+            if self._labels.shape[0] != self._consider.shape[0]:
+                raise ValueError("'labels' and 'consider' must have the same length")
+        self.meta = {} if meta is None else meta
+        self._consider_set = set()
+
+    @property
+    def mapping(self):
+        return self.to_mapping()
+
+    @property
+    def set(self):
+        return self.to_set()
+
+    @property
+    def labels(self):
+        return self._labels
+
+    @property
+    def consider(self):
+        return self._consider
+
+    @property
+    def consider_set(self):
+        return self._consider_set
+
+    @consider_set.setter
+    def consider_set(self, value):
+        self._consider_set = value
+
+    @property
+    def n_points(self):
+        return self._labels.shape[0]
+
+    def __repr__(self):
+        return f"{type(self).__name__}({list(self.labels)!s})"
+
+    def __str__(self):
+        return f"{self.labels!s}"
+
+    @classmethod
+    def from_sequence(cls, labels, *, consider=None, meta=None):
+        labels = np.array(labels, order="C", dtype=P_AINDEX)
+        if consider is not None:
+            consider = np.array(consider, order="C", dtype=P_ABOOL)
+        return cls(labels, consider=consider, meta=meta)
+
+    @classmethod
+    def from_length(cls, n: int, meta=None):
+        return cls(np.zeros(n, order="C", dtype=P_AINDEX), meta=meta)
+
+    def to_mapping(self):
+        """label -> list of point indices (``_types.pyx:187-198``); vectorised."""
+        mapping = defaultdict(list)
+        if self._labels.size:
+            order = np.argsort(self._labels, kind="stable")
+            sl = self._labels[order]
+            bounds = np.flatnonzero(np.diff(sl)) + 1
+            for chunk in np.split(order, bounds):
+                mapping[int(self._labels[chunk[0]])] = chunk.tolist()
+        return mapping
+
+    def to_set(self):
+        return set(np.unique(self._labels).tolist())
+
+    def sort_by_size(self, member_cutoff: Optional[int] = None, max_clusters: Optional[int] = None,
+                     bundle=None, ctx=None):
+        """Re-number clusters by size, in place, on the device.  Reference: ``_types.pyx:212-286``."""
+        if self._labels.size == 0:
+            return
+        ctx = ctx or _lib.default_context()
+        max_label = int(self._labels.max())
+        if max_label <= 0:
+            return  # only noise: `if frequencies:` is false in the reference, nothing happens
+        reassign = ctx.sort_by_size(self._labels, member_cutoff, max_clusters, return_map=True, max_label=max_label)
+        params = self.meta.get("params", {})
+        self.meta["params"] = {
+            int(reassign[k]): v for k, v in params.items()
+            if 0 <= k <= max_label and reassign[k] != 0
+        }
+        if bundle is not None and getattr(bundle, "_children", None) is not None:
+            processed = {}
+            for old_label, child in bundle._children.items():
+                new_label = int(reassign[old_label]) if 0 <= old_label <= max_label else 0
+                if new_label != 0:
+                    processed[new_label] = child
+            bundle._children = processed
+
+
+# ---- InputData ------------------------------------------------------------------------------------
+class InputData:
+    """Role marker (reference ABC ``InputData``, ``_types.pyx:305-436``)."""
+    n_points: int
+    n_dim: int
+    meta: dict
+
+
+class InputDataComponents(InputData):
+    """Point coordinates, f64 row-major ``[n, d]`` (host NumPy array or CUDA tensor).
+
+    Reference: ``InputDataExtComponentsMemoryview``, ``_types.pyx:1034-1109``."""
+
+    def __init__(self, data, *, meta=None):
+        if isinstance(data, np.ndarray) or not hasattr(data, "is_cuda"):
+            data = np.ascontiguousarray(data, dtype=P_AVALUE)
+            if data.ndim == 1:
+                data = data.reshape(1, -1)
+        else:
+            import torch
+
+            if data.dtype != torch.float64 or not data.is_contiguous():
+                data = data.to(torch.float64).contiguous()
+        if data.ndim != 2:
+            raise ValueError("coordinates must be a 2-D array [n_points, n_dim]")
+        self._data = data
+        self.n_points, self.n_dim = int(data.shape[0]), int(data.shape[1])
+        _meta = {"access_coords": True}
+        if meta is not None:
+            _meta.update(meta)
+        self.meta = _meta
+
+    @property
+    def data(self):
+        return self.to_components_array()
+
+    def to_components_array(self):
+        return self._data if isinstance(self._data, np.ndarray) else self._data.cpu().numpy()
+
+    @property
+    def device_or_host_array(self):
+        return self._data
+
+    def get_component(self, point: int, dimension: int) -> float:
+        return float(self._data[point, dimension])
+
+    def get_subset(self, indices):
+        idx = np.asarray(indices)
+        sub = self._data[idx] if isinstance(self._data, np.ndarray) else self._data[idx.tolist()]
+        return type(self)(sub)
+
+    def by_parts(self):
+        """Yield the parts delimited by ``meta["edges"]`` (``_types.pyx:1089-1109``)."""
+        if self.n_points > 0:
+            edges = self.meta.get("edges", None)
+            if not edges:
+                edges = [self.n_points]
+            arr = self.to_components_array()
+            start = 0
+            for end in np.cumsum(edges):
+                yield arr[start:end, :]
+                start = end
+        else:
+            yield from ()
+
+
+class InputDataNeighbourhoods(InputData):
+    """Precomputed neighbourhoods in the reference's padded layout: int64 ``[n, max_deg]`` plus
+    int64 counts ``[n]``.  Reference: ``InputDataExtNeighbourhoodsMemoryview``, ``_types.pyx:1153-1217``."""
+
+    def __init__(self, data, n_neighbours, *, meta=None):
+        self._data = np.ascontiguousarray(data, dtype=P_AINDEX)
+        self._n_neighbours = np.ascontiguousarray(n_neighbours, dtype=P_AINDEX)
+        if self._data.ndim != 2 or self._n_neighbours.shape != (self._data.shape[0],):
+            raise ValueError("need data [n, max_deg] and n_neighbours [n]")
+        self.n_points = int(self._data.shape[0])
+        self.n_dim = 0
+        _meta = {"access_neighbours": True}
+        if meta is not None:
+            _meta.update(meta)
+        self.meta = _meta
+
+    @property
+    def data(self):
+        return [row[:m] for row, m in zip(self._data, self._n_neighbours)]
+
+    @property
+    def n_neighbours(self):
+        return self._n_neighbours
+
+    @property
+    def padded(self):
+        return self._data
+
+    def get_n_neighbours(self, point: int) -> int:
+        return int(self._n_neighbours[point])
+
+    def get_neighbour(self, point: int, member: int) -> int:
+        return int(self._data[point, member])
+
+
+class InputDataNeighbourhoodsCSR(InputData):
+    """Precomputed neighbourhoods in CSR form (row_ptr int64 ``[n+1]``, col_idx int32/int64
+    ``[nnz]``; host arrays or CUDA tensors).  No reference twin: the padded layout costs
+    8*n*max_deg bytes, which is what makes the reference's large runs memory bound."""
+
+    def __init__(self, row_ptr, col_idx, *, meta=None):
+        self.row_ptr = row_ptr
+        self.col_idx = col_idx
+        self.n_points = int(row_ptr.shape[0]) - 1
+        self.n_dim = 0
+        _meta = {"access_neighbours": True}
+        if meta is not None:
+            _meta.update(meta)
+        self.meta = _meta
+
+
+class Neighbourhoods:
+    """Handle on the CSR neighbourhood structure held in HBM by a context (the bulk analogue of
+    the reference's per-point ``Neighbours`` scratch containers, ``_types.pyx:1285-1576``)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.n_points, self.nnz, self.max_n_neighbours = ctx.neighbours_info()
+        self._host = None
+
+    def to_csr(self):
+        """(row_ptr, col_idx) int64 in the caller's index space, rows ascending."""
+        if self._host is None:
+            self._host = self.ctx.neighbours_export()
+        return self._host
+
+    def get(self, index: int):
+        row_ptr, col_idx = self.to_csr()
+        return col_idx[row_ptr[index]:row_ptr[index + 1]]
+
+    def enough(self, index: int, member_cutoff: int) -> bool:
+        """``Neighbours.enough``: strictly more than ``member_cutoff`` (``_types.pyx:1408-1411``)."""
+        row_ptr, _ = self.to_csr()
+        return bool(row_ptr[index + 1] - row_ptr[index] > member_cutoff)
+
+
+# ---- Metric -----------------------------------------------------------------------------------------
+class Metric:
+    name = None
+
+    def adjust_radius(self, radius_cutoff: float) -> float:
+        raise NotImplementedError
+
+
+class MetricEuclideanReduced(Metric):
+    """Squared Euclidean distance; ``adjust_radius(r) = r*r``.  Reference:
+    ``MetricExtEuclideanReduced``, ``_types.pyx:2250-2287`` (recipe key ``euclidean_r``)."""
+    name = "euclidean_r"
+
+    def adjust_radius(self, radius_cutoff: float) -> float:
+        r = float(radius_cutoff)
+        return r * r
+
+    def calc_distance(self, index_a: int, index_b: int, input_data) -> float:
+        a = input_data.to_components_array()
+        total = 0.0
+        for k in range(a.shape[1]):
+            t = float(a[index_a, k]) - float(a[index_b, k])
+            total += t * t
+        return total
+
+
+class MetricEuclidean(Metric):
+    """Euclidean distance; radius unchanged.  Reference: ``MetricExtEuclidean``, ``_types.pyx:2170-2207``."""
+    name = "euclidean"
+
+    def adjust_radius(self, radius_cutoff: float) -> float:
+        return float(radius_cutoff)
+
+    def calc_distance(self, index_a: int, index_b: int, input_data) -> float:
+        return float(np.sqrt(MetricEuclideanReduced().calc_distance(index_a, index_b, input_data)))
+
+
+class DistanceGetterMetric:
+    """Reference: ``DistanceGetterExtMetric``, ``_types.pyx:1966-2017`` (pure indirection)."""
+
+    def __init__(self, metric=None):
+        self._metric = metric if metric is not None else MetricEuclideanReduced()
+
+    @classmethod
+    def get_builder_kwargs(cls):
+        return [("metric", None)]
+
+    def get_single(self, point_a: int, point_b: int, input_data) -> float:
+        return self._metric.calc_distance(point_a, point_b, input_data)
+
+
+# ---- NeighboursGetter ------------------------------------------------------------------------------
+class NeighboursGetter:
+    is_sorted = True
+    is_selfcounting = True
+
+    def get_all(self, input_data, cluster_params, ctx=None) -> Neighbourhoods:
+        raise NotImplementedError
+
+    def get(self, index: int, input_data, cluster_params, ctx=None):
+        """Neighbours of one point (reference per-point ``get``); answered from the bulk result."""
+        return self.get_all(input_data, cluster_params, ctx).get(index)
+
+
+class NeighboursGetterRadius(NeighboursGetter):
+    """Exact radius-neighbour search on coordinates for all points at once.
+
+    Bulk replacement of ``NeighboursGetterExtBruteForce`` (``_types.pyx:1658-1735``): same neighbour
+    sets (self included, ascending), found with a cell list for ``n_dim <= 3`` (``method="grid"``)
+    or a tiled all-pairs kernel (``"tiled"`` exact f64, ``"tensor"`` tcgen05 filter + f64 recheck)."""
+
+    def __init__(self, distance_getter=None, method: str = "auto"):
+        self._distance_getter = distance_getter if distance_getter is not None else DistanceGetterMetric()
+        if method not in _lib.METHOD_IDS:
+            raise ValueError(f"unknown method {method!r}")
+        self.method = method
+
+    @classmethod
+    def get_builder_kwargs(cls):
+        return [("distance_getter", None)]
+
+    @property
+    def metric(self):
+        return self._distance_getter._metric
+
+    def get_all(self, input_data, cluster_params, ctx=None) -> Neighbourhoods:
+        ctx = ctx or _lib.default_context()
+        ctx.neighbours_from_points(input_data.device_or_host_array, cluster_params.radius_cutoff,
+                                   metric=self.metric.name, method=self.method)
+        return Neighbourhoods(ctx)
+
+
+class NeighboursGetterGrid(NeighboursGetterRadius):
+    def __init__(self, distance_getter=None):
+        super().__init__(distance_getter, "grid")
+
+
+class NeighboursGetterTiled(NeighboursGetterRadius):
+    def __init__(self, distance_getter=None):
+        super().__init__(distance_getter, "tiled")
+
+
+class NeighboursGetterTensor(NeighboursGetterRadius):
+    def __init__(self, distance_getter=None):
+        super().__init__(distance_getter, "tensor")
+
+
+class NeighboursGetterLookup(NeighboursGetter):
+    """Precomputed neighbourhoods.  Bulk replacement of ``NeighboursGetterExtLookup``
+    (``_types.pyx:1791-1832``): uploads the padded matrix or CSR once and converts it to int32 CSR.
+    Rows must be ascending (the reference's ``sorted_neighbourhoods`` recipe, ``recipes.py:349-357``)."""
+
+    def __init__(self, is_sorted: bool = True, is_selfcounting: bool = True):
+        if not is_sorted:
+            raise ValueError("the B200 lookup getter needs ascending neighbour lists (is_sorted=True)")
+        self.is_sorted = True
+        self.is_selfcounting = bool(is_selfcounting)
+
+    def get_all(self, input_data, cluster_params=None, ctx=None) -> Neighbourhoods:
+        ctx = ctx or _lib.default_context()
+        if isinstance(input_data, InputDataNeighbourhoodsCSR):
+            ctx.neighbours_from_csr(input_data.row_ptr, input_data.col_idx,
+                                    borrow=hasattr(input_data.col_idx, "is_cuda"))
+        elif isinstance(input_data, InputDataNeighbourhoods):
+            ctx.neighbours_from_padded(input_data.padded, input_data.n_neighbours)
+        else:
+            raise TypeError("NeighboursGetterLookup needs InputDataNeighbourhoods or InputDataNeighbourhoodsCSR")
+        return Neighbourhoods(ctx)
+
+
+# ---- SimilarityChecker -----------------------------------------------------------------------------
+class SimilarityChecker:
+    pass
+
+
+class SimilarityCheckerCommonNN(SimilarityChecker):
+    """Common-nearest-neighbour criterion over sorted CSR rows, evaluated by warp-cooperative
+    intersection on the device.
+
+    Bulk replacement of ``SimilarityCheckerExtContains`` / ``...SwitchContains`` /
+    ``...Screensorted`` (``_types.pyx:2496-2753``): ``check`` = at least ``similarity_cutoff``
+    common neighbours (early exit), ``get`` = the full count."""
+
+    def get_all(self, neighbourhoods: Neighbourhoods, cluster_params, out=None):
+        """uint32 count per CSR slot in the device's CSR order (0xFFFFFFFF where the slot is not a
+        candidate edge i<j between two points with more than ``n_member_cutoff`` neighbours)."""
+        return neighbourhoods.ctx.cn_count(cluster_params.n_member_cutoff, out=out)
+
+    # per-pair forms of the reference, for small inputs / tests: two ascending index lists
+    def get(self, neighbours_a, neighbours_b, cluster_params=None, ctx=None) -> int:
+        ctx = ctx or _lib.default_context()
+        a = np.unique(np.asarray(neighbours_a, dtype=np.int64))
+        b = np.unique(np.asarray(neighbours_b, dtype=np.int64))
+        if a.size == 0 or b.size == 0:
+            return 0
+        # a two-row neighbourhood structure over a private index space: row 0 = a, row 1 = b, where
+        # both rows additionally contain each other (0 and 1 are fresh indices) so that (0, 1) is an edge
+        both = np.unique(np.concatenate([a, b]))
+        ra = np.searchsorted(both, a) + 2
+        rb = np.searchsorted(both, b) + 2
+        n = both.size + 2
+        rows = [np.concatenate([[1], ra]), np.concatenate([[0], rb])] + [np.empty(0, np.int64)] * both.size
+        row_ptr = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([len(r) for r in rows], out=row_ptr[1:])
+        col_idx = np.concatenate(rows).astype(np.int64)
+        ctx.neighbours_from_csr(row_ptr, col_idx)
+        counts, _ = ctx.cn_count(0)
+        return int(counts[0])
+
+    def check(self, neighbours_a, neighbours_b, cluster_params, ctx=None) -> bool:
+        c = cluster_params.similarity_cutoff
+        if c == 0:
+            return True  # _types.pyx:2589-2590
+        return self.get(neighbours_a, neighbours_b, cluster_params, ctx) >= c

@@ -1,0 +1,140 @@
+"""User API -- mirror of the reference's ``cluster.Clustering`` for the fit path
+(``cluster.pyx:102-147`` construction, ``:256-392`` ``fit``, ``:155-177`` ``labels``)."""
+import time
+import weakref
+
+import numpy as np
+
+from . import recipes
+from ._fit import Fitter, FitterB200Fused
+from ._types import InputData, InputDataComponents, Labels
+from .report import Record, Summary
+
+
+class Bundle:
+    """Input data + labels + summary of one clustering (reference ``_bundle.pyx:20-53``; the
+    hierarchy bookkeeping of the reference's Bundle is outside the fit path)."""
+
+    def __init__(self, input_data=None, labels=None, summary=None):
+        self._input_data = input_data
+        self._labels = labels
+        self._summary = summary if summary is not None else Summary()
+        self._children = None
+
+    input_data = property(lambda self: self._input_data)
+    labels = property(lambda self: self._labels)
+    summary = property(lambda self: self._summary)
+
+
+class Clustering:
+    """``Clustering(data).fit(radius_cutoff, cnn_cutoff, member_cutoff)`` on a B200."""
+
+    def __init__(self, data=None, *, fitter=None, recipe=None, **recipe_kwargs):
+        builder = recipes.Builder(recipe, **recipe_kwargs)
+        if data is None:
+            self._bundle = None
+        elif isinstance(data, Bundle):
+            self._bundle = data
+        elif isinstance(data, InputData):
+            self._bundle = Bundle(data)
+        else:
+            self._bundle = Bundle(builder.make_input_data(data))
+        if isinstance(fitter, Fitter):
+            self._fitter = fitter
+        else:
+            if fitter is not None:
+                builder.recipe["fitter"] = fitter
+            f = builder.make_component("fitter")
+            self._fitter = None if f is object else f
+
+    @property
+    def root(self):
+        return self._bundle
+
+    @property
+    def input_data(self):
+        return None if self._bundle is None or self._bundle._input_data is None else self._bundle._input_data.data
+
+    @property
+    def labels(self):
+        """Cluster label assignments as a NumPy array (reference ``cluster.pyx:155-177``)."""
+        if self._bundle is None or self._bundle._labels is None:
+            return None
+        return self._bundle._labels.labels
+
+    @labels.setter
+    def labels(self, value):
+        self._bundle._labels = value if isinstance(value, Labels) else Labels.from_sequence(value)
+
+    @property
+    def summary(self):
+        return self._bundle._summary
+
+    @property
+    def fitter(self):
+        return self._fitter
+
+    @fitter.setter
+    def fitter(self, value):
+        if value is not None and not isinstance(value, Fitter):
+            raise TypeError(f"Can't use object of type {type(value).__name__} as fitter.")
+        self._fitter = value
+
+    def fit(self, radius_cutoff: float, cnn_cutoff: int, member_cutoff: int = None, max_clusters: int = None,
+            cnn_offset: int = None, sort_by_size: bool = True, info: bool = True, record: bool = True,
+            record_time: bool = True, v: bool = True, purge: bool = False, bundle=None) -> None:
+        """Same arguments and effects as the reference's ``Clustering.fit`` (``cluster.pyx:256-392``)."""
+        if bundle is None:
+            bundle = self._bundle
+        if cnn_offset is None:
+            cnn_offset = 0
+        cnn_cutoff -= cnn_offset
+        assert cnn_cutoff >= 0
+        n = bundle._input_data.n_points
+        if (bundle._labels is None) or purge or (not bundle._labels.meta.get("frozen", False)):
+            bundle._labels = Labels(np.zeros(n, order="C", dtype=np.int64))
+            old_label_set = set()
+            current_start = 1
+            fresh = True
+        else:
+            old_label_set = bundle._labels.to_set()
+            current_start = max(old_label_set) + 1
+            fresh = False
+        cluster_params = self._fitter.make_parameters(radius_cutoff, cnn_cutoff, current_start)
+
+        # a fresh fit on coordinates with size sorting can keep the labels on the device
+        # between FitterExtBFS.fit and Labels.sort_by_size: one C-ABI call, one D2H copy
+        fused = (fresh and sort_by_size and isinstance(self._fitter, FitterB200Fused)
+                 and isinstance(bundle._input_data, InputDataComponents))
+        t0 = time.perf_counter()
+        if fused:
+            n_found = self._fitter.fit_sorted(bundle._input_data, bundle._labels, cluster_params,
+                                              member_cutoff, max_clusters)
+        else:
+            self._fitter.fit(bundle._input_data, bundle._labels, cluster_params)
+        execution_time = time.perf_counter() - t0 if record_time else None
+
+        if info:
+            if fused:
+                n_kept = int(bundle._labels.labels.max()) if n else 0
+                params = {k: (radius_cutoff, cnn_cutoff) for k in range(1, n_kept + 1)}
+                del n_found
+            else:
+                new_label_set = bundle._labels.to_set()
+                params = {k: (radius_cutoff, cnn_cutoff) for k in new_label_set - old_label_set if k != 0}
+            old_params = bundle._labels.meta.get("params", {})
+            old_params.update(params)
+            bundle._labels.meta.update({"params": old_params, "reference": weakref.proxy(bundle), "origin": "fit"})
+        if sort_by_size and not fused:
+            bundle._labels.sort_by_size(member_cutoff, max_clusters, ctx=getattr(self._fitter, "ctx", None))
+        if record:
+            lab = bundle._labels.labels
+            counts = np.bincount(lab) if n else np.zeros(1, dtype=np.int64)
+            n_noise = int(counts[0]) if counts.size else 0
+            rest = counts[1:]
+            rec = Record(n, radius_cutoff, cnn_cutoff, member_cutoff, max_clusters,
+                         int(np.count_nonzero(rest)), (int(rest.max()) if rest.size else 0) / n,
+                         n_noise / n, execution_time)
+            if v:
+                print(rec)
+            bundle._summary.append(rec)

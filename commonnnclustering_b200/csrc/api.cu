@@ -118,6 +118,10 @@ extern "C" int cnnb200_ctx_destroy(cnnb200_ctx *ctx) {
     if (!ctx) return CNNB200_OK;
     int rc = cnnb200_ctx_release(ctx);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int k = 0; k < ctx->n_events_made; ++k) {
+        cudaEventDestroy(ctx->span_ev[k][0]);
+        cudaEventDestroy(ctx->span_ev[k][1]);
+    }
     delete ctx;
     return rc;
 }
@@ -153,6 +157,39 @@ extern "C" int cnnb200_ctx_synchronize(cnnb200_ctx *ctx) {
 extern "C" int cnnb200_stats(cnnb200_ctx *ctx, int64_t *stats, int64_t len) {
     if (!ctx || !stats) CNN_FAIL(CNNB200_E_INVALID, "stats: NULL argument");
     for (int64_t i = 0; i < len; ++i) stats[i] = i < ST_N ? ctx->stats[i] : 0;
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_ctx_set_timing(cnnb200_ctx *ctx, int enabled) {
+    if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");
+    ctx->timing = enabled != 0;
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_timings(cnnb200_ctx *ctx, double *ms, int64_t *calls, int64_t len, int64_t *launches,
+                               int reset) {
+    if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < ctx->n_spans; ++k) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ctx->span_ev[k][0], ctx->span_ev[k][1]) == cudaSuccess) {
+            ctx->t_ms[ctx->span_slot[k]] += t;
+            ctx->t_calls[ctx->span_slot[k]] += 1;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    ctx->n_spans = 0;
+    for (int64_t i = 0; i < len; ++i) {
+        if (ms) ms[i] = i < T_N ? ctx->t_ms[i] : 0.0;
+        if (calls) calls[i] = i < T_N ? ctx->t_calls[i] : 0;
+    }
+    if (launches) *launches = ctx->n_launches;
+    if (reset) {
+        for (int i = 0; i < T_N; ++i) { ctx->t_ms[i] = 0; ctx->t_calls[i] = 0; }
+        ctx->n_launches = 0;
+    }
     return CNNB200_OK;
 }
 
@@ -196,6 +233,7 @@ extern "C" int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x,
     const double *d_x = x;
     if (loc == CNNB200_HOST) {
         CNN_TRY(cnn_ensure(ctx, ctx->b_x, sizeof(double) * (size_t)n * (size_t)d));
+        Span sp(ctx, T_H2D);
         CNN_CUDA(cudaMemcpyAsync(ctx->b_x.p, x, sizeof(double) * (size_t)n * (size_t)d,
                                  cudaMemcpyHostToDevice, ctx->stream));
         d_x = ctx->b_x.as<double>();
@@ -230,7 +268,10 @@ extern "C" int cnnb200_fit_points(cnnb200_ctx *ctx, const double *x, int loc, in
     if (n_clusters_out) *n_clusters_out = n_clusters;
     CNN_TRY(cnnb200_sort_by_size(ctx, d_labels, CNNB200_DEVICE, n, member_cutoff, max_clusters, nullptr, 0));
     if (loc == CNNB200_HOST) {
-        CNN_CUDA(cudaMemcpyAsync(labels, d_labels, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        {
+            Span sp(ctx, T_D2H);
+            CNN_CUDA(cudaMemcpyAsync(labels, d_labels, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         CNN_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     return CNNB200_OK;

@@ -295,9 +295,13 @@ extern "C" int cnnb200_components_begin(cnnb200_ctx *ctx, int64_t n_member_cutof
         CNN_CUDA(cudaMemcpyAsync(ctx->b_consider.p, consider, (size_t)n, cudaMemcpyHostToDevice, st));
         d_consider = ctx->b_consider.as<uint8_t>();
     }
-    comp_init_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(ctx->row_ptr, ctx->perm, d_consider, n,
-                                                          n_member_cutoff, ctx->b_parent.as<int>(),
-                                                          ctx->b_core.as<uint8_t>());
+    {
+        Span sp(ctx, T_COMP_INIT);
+        comp_init_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(ctx->row_ptr, ctx->perm, d_consider, n,
+                                                              n_member_cutoff, ctx->b_parent.as<int>(),
+                                                              ctx->b_core.as<uint8_t>());
+        CNN_LAUNCHED(ctx, 1);
+    }
     CNN_KERNEL_CHECK();
     ctx->n_member_cutoff = n_member_cutoff;
     ctx->similarity_cutoff = similarity_cutoff;
@@ -320,12 +324,25 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
     int cap = ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
     unsigned long long *stats = (unsigned long long *)ctx->b_stats.p;
-    comp_sample_kernel<<<blocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, ctx->b_core.as<uint8_t>(), row_begin,
-                                               row_end, cutoff, ctx->b_parent.as<int>(), stats);
-    comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(ctx->b_parent.as<int>(), ctx->n);
-    comp_edges_kernel<<<blocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, ctx->b_core.as<uint8_t>(), row_begin,
-                                              row_end, cutoff, ctx->b_parent.as<int>(), stats);
-    comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(ctx->b_parent.as<int>(), ctx->n);
+    {
+        Span sp(ctx, T_COMP_SAMPLE);
+        comp_sample_kernel<<<blocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, ctx->b_core.as<uint8_t>(), row_begin,
+                                                   row_end, cutoff, ctx->b_parent.as<int>(), stats);
+    }
+    {
+        Span sp(ctx, T_COMP_FLATTEN);
+        comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(ctx->b_parent.as<int>(), ctx->n);
+    }
+    {
+        Span sp(ctx, T_COMP_EDGES);
+        comp_edges_kernel<<<blocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, ctx->b_core.as<uint8_t>(), row_begin,
+                                                  row_end, cutoff, ctx->b_parent.as<int>(), stats);
+    }
+    {
+        Span sp(ctx, T_COMP_FLATTEN);
+        comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(ctx->b_parent.as<int>(), ctx->n);
+    }
+    CNN_LAUNCHED(ctx, 4);
     CNN_KERNEL_CHECK();
     return CNNB200_OK;
 }
@@ -342,6 +359,8 @@ extern "C" int cnnb200_components_merge(cnnb200_ctx *ctx, const int32_t *others,
     if (!ctx->have_comp) CNN_FAIL(CNNB200_E_STATE, "components_merge: call components_begin first");
     if (count < 1) return CNNB200_OK;
     CNN_CUDA(cudaSetDevice(ctx->device));
+    Span sp(ctx, T_COMP_FLATTEN);
+    CNN_LAUNCHED(ctx, 2);
     comp_merge_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(others, ctx->n, count, ctx->b_parent.as<int>());
     comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->b_parent.as<int>(), ctx->n);
     CNN_KERNEL_CHECK();
@@ -365,8 +384,12 @@ extern "C" int cnnb200_cn_count(cnnb200_ctx *ctx, int64_t n_member_cutoff, uint3
     int blocks = (int)((n + 7) / 8);
     int cap = ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
-    cn_count_kernel<<<blocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, n, n_member_cutoff, d_counts,
-                                            (unsigned long long *)ctx->b_stats.p);
+    {
+        Span sp(ctx, T_CN_COUNT);
+        cn_count_kernel<<<blocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, n, n_member_cutoff, d_counts,
+                                                (unsigned long long *)ctx->b_stats.p);
+        CNN_LAUNCHED(ctx, 1);
+    }
     CNN_KERNEL_CHECK();
     if (loc == CNNB200_HOST)
         CNN_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof(unsigned) * (size_t)nnz, cudaMemcpyDeviceToHost, st));

@@ -51,6 +51,26 @@ enum StatSlot {
     ST_N = 8
 };
 
+// timing slots (cnnb200_timings): device time of the stages of the path, by CUDA events
+enum TimeSlot {
+    T_H2D = 0,      // host -> device copies of inputs
+    T_GRID_BUILD,   // K1: bounding box, cell ids, sort by cell, cell starts, gather
+    T_SEARCH_COUNT, // K2/K3 count pass
+    T_SCAN,         // degree scan (CUB)
+    T_SEARCH_FILL,  // K2/K3 fill pass
+    T_INGEST,       // K4: CSR / padded ingest
+    T_COMP_INIT,    // core flags + parent init
+    T_COMP_SAMPLE,  // K5/K6 sampling pass
+    T_COMP_EDGES,   // K5/K6 full edge pass
+    T_COMP_FLATTEN, // pointer-jumping passes + multi-GPU merge
+    T_LABELS,       // K7 numbering
+    T_SORT_BY_SIZE, // K7 Labels.sort_by_size
+    T_D2H,          // device -> host copies of results
+    T_CN_COUNT,     // K5 count mode
+    T_N
+};
+#define CNN_MAX_SPANS 256
+
 struct cnnb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -86,7 +106,38 @@ struct cnnb200_ctx {
     size_t h_pinned_cap = 0;
 
     ll stats[ST_N] = {0};
+
+    // ---- measurement ---------------------------------------------------------------------------
+    bool timing = false;
+    int n_spans = 0;
+    int span_slot[CNN_MAX_SPANS];
+    cudaEvent_t span_ev[CNN_MAX_SPANS][2];
+    int n_events_made = 0;
+    double t_ms[T_N] = {0};
+    ll t_calls[T_N] = {0};
+    ll n_launches = 0;  // hand-written kernels launched (library kernels such as CUB are not counted)
 };
+
+// RAII span: records an event pair around a stage when timing is enabled
+struct Span {
+    cnnb200_ctx *c;
+    int k;
+    Span(cnnb200_ctx *ctx, int slot) : c(ctx), k(-1) {
+        if (!c->timing || c->n_spans >= CNN_MAX_SPANS) return;
+        k = c->n_spans++;
+        if (k >= c->n_events_made) {
+            cudaEventCreate(&c->span_ev[k][0]);
+            cudaEventCreate(&c->span_ev[k][1]);
+            c->n_events_made = k + 1;
+        }
+        c->span_slot[k] = slot;
+        cudaEventRecord(c->span_ev[k][0], c->stream);
+    }
+    ~Span() {
+        if (k >= 0) cudaEventRecord(c->span_ev[k][1], c->stream);
+    }
+};
+#define CNN_LAUNCHED(ctx, k) ((ctx)->n_launches += (k))
 
 int cnn_ensure(cnnb200_ctx *ctx, Buf &b, size_t bytes);
 void cnn_release(cnnb200_ctx *ctx, Buf &b);

@@ -108,6 +108,7 @@ extern "C" int cnnb200_neighbours_from_csr(cnnb200_ctx *ctx, const int64_t *row_
     ctx->have_nb = false;
     ctx->have_comp = false;
     cudaMemcpyKind kind = loc == CNNB200_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    Span sp(ctx, T_INGEST);
     if (loc == CNNB200_HOST && (row_ptr[0] != 0 || row_ptr[n] != nnz))
         CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_csr: row_ptr[0] must be 0 and row_ptr[n] == nnz");
 
@@ -174,6 +175,7 @@ extern "C" int cnnb200_neighbours_from_padded(cnnb200_ctx *ctx, const int64_t *p
     ctx->have_nb = false;
     ctx->have_comp = false;
     cudaMemcpyKind kind = loc == CNNB200_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    Span sp(ctx, T_INGEST);
     CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
     int *flag = ctx->b_tmp2.as<int>();
     CNN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));

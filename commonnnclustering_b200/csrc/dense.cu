@@ -109,22 +109,30 @@ int cnn_dense_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double rad
     CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>() + n, 0, sizeof(int), st));
     int blocks = (int)((n + DT - 1) / DT);
     bool sq = metric == CNNB200_METRIC_EUCLIDEAN;
+    {
+    Span sp(ctx, T_SEARCH_COUNT);
     if (sq)
         dense_rows_kernel<true, false><<<blocks, 256, 0, st>>>(d_x, n, (int)d, radius_cutoff,
                                                                ctx->b_deg.as<int>(), nullptr, nullptr);
     else
         dense_rows_kernel<false, false><<<blocks, 256, 0, st>>>(d_x, n, (int)d, radius_cutoff,
                                                                 ctx->b_deg.as<int>(), nullptr, nullptr);
+    }
+    CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     ll nnz = 0, max_deg = 0;
     CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
     CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
+    {
+    Span sp(ctx, T_SEARCH_FILL);
     if (sq)
         dense_rows_kernel<true, true><<<blocks, 256, 0, st>>>(d_x, n, (int)d, radius_cutoff, nullptr,
                                                               ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
     else
         dense_rows_kernel<false, true><<<blocks, 256, 0, st>>>(d_x, n, (int)d, radius_cutoff, nullptr,
                                                                ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
+    }
+    CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     ctx->n = n;
     ctx->nnz = nnz;

@@ -12,6 +12,8 @@
 #include <cub/cub.cuh>
 #include <math.h>
 
+#include <memory>
+
 #include "common.cuh"
 
 struct GridDesc {
@@ -143,6 +145,7 @@ int cnn_scan_deg_to_row_ptr(cnnb200_ctx *ctx, const int32_t *deg, ll n, ll *row_
                             ll *max_deg_out) {
     // deg has n+1 entries, the last one 0, so that row_ptr[n] = nnz comes out of the scan
     // int32 in, int64 out: the accumulator type follows the int64 initial value
+    Span sp(ctx, T_SCAN);
     size_t need1 = 0, need2 = 0;
     CNN_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, need1, deg, row_ptr, ::cuda::std::plus<>{}, (ll)0, (int)(n + 1), ctx->stream));
     CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
@@ -177,6 +180,7 @@ static int launch_rows(cnnb200_ctx *ctx, ll n, const GridDesc &g, double rc, boo
     else
         grid_rows_kernel<D, SQRT, true><<<blocks, 256, 0, ctx->stream>>>(
             xs, n, cs, cstart, g, rc, nullptr, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
+    CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     return CNNB200_OK;
 }
@@ -195,6 +199,7 @@ static int launch_rows_any(cnnb200_ctx *ctx, ll n, const GridDesc &g, double rc,
 
 int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric) {
     cudaStream_t st = ctx->stream;
+    std::unique_ptr<Span> sp_build(new Span(ctx, T_GRID_BUILD));
     // --- bounding box --------------------------------------------------------------------
     int rb = ctx->sm_count * 2;
     if (rb > (int)((n + 255) / 256)) rb = (int)((n + 255) / 256);
@@ -202,6 +207,7 @@ int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radi
     double *partial = ctx->b_bbox.as<double>();
     bbox_partial_kernel<<<rb, 256, 0, st>>>(d_x, n, (int)d, partial + 6);
     bbox_final_kernel<<<1, 32, 0, st>>>(partial + 6, rb, partial);
+    CNN_LAUNCHED(ctx, 2);
     CNN_KERNEL_CHECK();
     double *hb;
     CNN_TRY(cnn_pinned(ctx, 64, (void **)&hb));
@@ -254,6 +260,7 @@ int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radi
     CNN_CUDA(cudaMemsetAsync(cell_count, 0, sizeof(int) * (size_t)(ncell + 1), st));
     cell_id_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_x, n, g, ctx->b_cell_id.as<int>(),
                                                          ctx->b_idx.as<int>(), cell_count);
+    CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     int bits = 1;
     while ((1ll << bits) < ncell) ++bits;
@@ -273,15 +280,23 @@ int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radi
                                            (int)(ncell + 1), st));
     gather_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_x, ctx->b_perm.as<int>(), n, (int)d,
                                                         ctx->b_xs.as<double>());
+    CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
+    sp_build.reset();
 
     // --- K2: count, scan, fill ------------------------------------------------------------------
     CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>() + n, 0, sizeof(int), st));
-    CNN_TRY(launch_rows_any(ctx, n, g, radius_cutoff, metric, false));
+    {
+        Span sp(ctx, T_SEARCH_COUNT);
+        CNN_TRY(launch_rows_any(ctx, n, g, radius_cutoff, metric, false));
+    }
     ll nnz = 0, max_deg = 0;
     CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
     CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
-    CNN_TRY(launch_rows_any(ctx, n, g, radius_cutoff, metric, true));
+    {
+        Span sp(ctx, T_SEARCH_FILL);
+        CNN_TRY(launch_rows_any(ctx, n, g, radius_cutoff, metric, true));
+    }
 
     ctx->n = n;
     ctx->nnz = nnz;

@@ -13,6 +13,8 @@
 #include <cub/cub.cuh>
 #include <string.h>
 
+#include <memory>
+
 #include "common.cuh"
 
 int cnn_fetch_comp_stats(cnnb200_ctx *ctx);
@@ -62,6 +64,8 @@ extern "C" int cnnb200_components_labels(cnnb200_ctx *ctx, int64_t current_start
     const int *parent = ctx->b_parent.as<int>();
     const uint8_t *core = ctx->b_core.as<uint8_t>();
     int nb = cnn_blocks(n, 256);
+    std::unique_ptr<Span> sp(new Span(ctx, T_LABELS));
+    CNN_LAUNCHED(ctx, ctx->perm ? 4 : 2);
     int *minorig = nullptr;
     if (ctx->perm) {
         CNN_TRY(cnn_ensure(ctx, ctx->b_minorig, sizeof(int) * (size_t)n));
@@ -90,8 +94,11 @@ extern "C" int cnnb200_components_labels(cnnb200_ctx *ctx, int64_t current_start
     write_labels_kernel<<<nb, 256, 0, st>>>(parent, core, ctx->perm, minorig, ctx->b_rank.as<int>(), n,
                                             current_start, d_labels, fresh);
     CNN_KERNEL_CHECK();
-    if (loc == CNNB200_HOST)
+    sp.reset();
+    if (loc == CNNB200_HOST) {
+        Span sd(ctx, T_D2H);
         CNN_CUDA(cudaMemcpyAsync(labels, d_labels, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    }
     if (n_clusters_out || loc == CNNB200_HOST) {
         int *h;
         CNN_TRY(cnn_pinned(ctx, 128, (void **)&h));
@@ -190,8 +197,10 @@ extern "C" int cnnb200_sort_by_size(cnnb200_ctx *ctx, int64_t *labels, int loc, 
     if (loc == CNNB200_HOST) {
         CNN_TRY(cnn_ensure(ctx, ctx->b_labels, sizeof(ll) * (size_t)n));
         d_labels = ctx->b_labels.as<ll>();
+        Span sh(ctx, T_H2D);
         CNN_CUDA(cudaMemcpyAsync(d_labels, labels, sizeof(ll) * (size_t)n, cudaMemcpyHostToDevice, st));
     }
+    std::unique_ptr<Span> sp(new Span(ctx, T_SORT_BY_SIZE));
     // largest label -> table size
     CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
     ll *d_max = ctx->b_tmp2.as<ll>() + 2;
@@ -245,6 +254,7 @@ extern "C" int cnnb200_sort_by_size(cnnb200_ctx *ctx, int64_t *labels, int loc, 
         CNN_CUDA(cudaMemsetAsync(map, 0, sizeof(ll), st));
         label_map_kernel<<<cnn_blocks(m, 256), 256, 0, st>>>(vals2, ctx->b_flags.as<int>(), ctx->b_rank.as<int>(), m, map);
         label_apply_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_labels, n, map, max_label);
+        CNN_LAUNCHED(ctx, 6);
         CNN_KERNEL_CHECK();
         if (map_out && map_len > 0) {
             ll cnt = map_len < L ? map_len : L;
@@ -254,8 +264,11 @@ extern "C" int cnnb200_sort_by_size(cnnb200_ctx *ctx, int64_t *labels, int loc, 
     } else if (map_out && map_len > 0) {
         for (ll k = 0; k < map_len; ++k) map_out[k] = 0;
     }
-    if (loc == CNNB200_HOST)
+    sp.reset();
+    if (loc == CNNB200_HOST) {
+        Span sd(ctx, T_D2H);
         CNN_CUDA(cudaMemcpyAsync(labels, d_labels, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    }
     if (loc == CNNB200_HOST || map_out) {
         int *hf = (int *)h + 8;
         *hf = 0;

@@ -192,6 +192,29 @@ int cnnb200_fit_points(cnnb200_ctx *ctx, const double *x, int loc, int64_t n, in
  *   stats[5] pairs re-checked in f64 (tensor-core filter path) */
 int cnnb200_stats(cnnb200_ctx *ctx, int64_t *stats, int64_t len);
 
+/* Stage timing by CUDA events on the context's stream (off by default).  cnnb200_timings
+ * synchronises the stream, folds the event pairs recorded since the last call into per-stage sums
+ * and returns: ms[k] / calls[k] for stage k (CNNB200_T_* below, `len` entries each, either may be
+ * NULL) and the number of hand-written kernels launched since the last reset. */
+#define CNNB200_T_H2D 0
+#define CNNB200_T_GRID_BUILD 1
+#define CNNB200_T_SEARCH_COUNT 2
+#define CNNB200_T_SCAN 3
+#define CNNB200_T_SEARCH_FILL 4
+#define CNNB200_T_INGEST 5
+#define CNNB200_T_COMP_INIT 6
+#define CNNB200_T_COMP_SAMPLE 7
+#define CNNB200_T_COMP_EDGES 8
+#define CNNB200_T_COMP_FLATTEN 9
+#define CNNB200_T_LABELS 10
+#define CNNB200_T_SORT_BY_SIZE 11
+#define CNNB200_T_D2H 12
+#define CNNB200_T_CN_COUNT 13
+#define CNNB200_T_COUNT 14
+int cnnb200_ctx_set_timing(cnnb200_ctx *ctx, int enabled);
+int cnnb200_timings(cnnb200_ctx *ctx, double *ms, int64_t *calls, int64_t len, int64_t *launches,
+                    int reset);
+
 #ifdef __cplusplus
 }
 #endif

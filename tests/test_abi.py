@@ -1,0 +1,85 @@
+"""The C-ABI shared library loads and exports every symbol include/cnnb200.h declares; the product
+package never touches the oracle; without a GPU the product fails loudly instead of falling back."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "cnnb200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cnnb200_[a-z0-9_]+)\s*\(", text)) - {"cnnb200_alloc_fn", "cnnb200_free_fn"})
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from commonnnclustering_b200 import build
+
+    lib_path = build.build()
+    lib = ctypes.CDLL(lib_path)
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for name in syms:
+        assert hasattr(lib, name), f"{name} declared in include/cnnb200.h but not exported"
+
+
+def test_python_binding_covers_the_header():
+    from commonnnclustering_b200 import _lib
+
+    bound = set(_lib.SIGNATURES) | {"cnnb200_version", "cnnb200_last_error"}
+    assert set(declared_symbols()) == bound
+
+
+def test_version_and_error_string():
+    from commonnnclustering_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.cnnb200_version() == 100
+    assert isinstance(lib.cnnb200_last_error(), bytes)
+
+
+def test_sass_is_sm100a():
+    from commonnnclustering_b200 import build
+
+    out = subprocess.run(["cuobjdump", "-lelf", build.build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "commonnnclustering_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "cnn_oracle" not in text, f
+    code = "import sys; import commonnnclustering_b200.cluster, commonnnclustering_b200._lib; " \
+           "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_fails_loudly_without_a_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from commonnnclustering_b200 import _lib
+
+    with pytest.raises(Exception) as e:
+        _lib.Context(0)
+    assert "cnnb200 error" in str(e.value)
+
+
+def test_missing_library_raises_import_error(tmp_path, monkeypatch):
+    from commonnnclustering_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError):
+        _lib.load()

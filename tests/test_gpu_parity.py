@@ -1,0 +1,342 @@
+"""Parity of the CUDA fit path (through the C-ABI) against the oracle, the golden fixtures the
+reference itself produced, and size-independent properties at BASELINE.json's full sizes.
+
+Everything here is bit-exact (integer labels / indices / counts); no tolerances."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+import cases  # noqa: E402
+from commonnnclustering_b200 import _lib, _types, cluster, datasets  # noqa: E402
+from oracle import port  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(HERE, "golden", "ref_labels.npz"))
+
+
+def fit_via_api(x, r, c, recipe=None, **kw):
+    metric = kw.pop("metric", None)
+    extra = {"fitter__ngetter__dgetter__metric": metric} if metric else {}
+    method = kw.pop("method", None)
+    cl = cluster.Clustering(x, recipe=recipe, **extra)
+    if method:
+        cl.fitter._neighbours_getter.method = method
+    cl.fit(r, c, v=False, **kw)
+    return cl
+
+
+# ---- golden fixtures produced by the reference -----------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_clustering_fit_equals_reference_golden(name):
+    case = cases.CASES[name]
+    x = case["data"]()
+    kw = dict(case["fit"])
+    cl = fit_via_api(x, kw.pop("r"), kw.pop("c"), **kw)
+    np.testing.assert_array_equal(cl.labels, GOLD[name].astype(np.int64))
+    assert cl.labels.dtype == np.int64
+    assert not cl.root.labels.consider.any()  # consider[:] = 0 after a fit (_fit.pyx:434-437)
+
+
+@pytest.mark.parametrize("name", ["blobs1500_r010_c20", "md5000_r04_c5", "lattice3d", "lattice1d", "blobs1500_euclid"])
+def test_tiled_search_equals_reference_golden(name):
+    case = cases.CASES[name]
+    x = case["data"]()
+    kw = dict(case["fit"])
+    cl = fit_via_api(x, kw.pop("r"), kw.pop("c"), method="tiled", **kw)
+    np.testing.assert_array_equal(cl.labels, GOLD[name].astype(np.int64))
+
+
+def test_readme_doctest():
+    cl = cluster.Clustering(datasets.README_POINTS)
+    cl.fit(1.5, 1, v=False)
+    assert cl.labels.tolist() == [1, 1, 1, 1, 1, 0, 0, 0, 0, 2, 2, 2]
+    rec = cl.summary[-1]
+    assert (rec.n_points, rec.n_clusters, rec.cnn_cutoff) == (12, 2, 1)
+    assert abs(rec.ratio_noise - 4 / 12) < 1e-15 and rec.execution_time > 0
+    assert cl.root.labels.meta["params"] == {1: (1.5, 1), 2: (1.5, 1)}
+
+
+# ---- neighbour sets ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("maker,r,metric", [
+    (lambda: datasets.blobs_2d(3000), 0.1, "euclidean_r"),
+    (lambda: datasets.md_like_3d(4000), 0.5, "euclidean_r"),
+    (lambda: cases.lattice(900, 3, 11), 0.25, "euclidean_r"),   # distances exactly on the cutoff
+    (lambda: cases.lattice(900, 2, 12), 0.375, "euclidean"),
+    (lambda: cases.lattice(300, 1, 13), 0.25, "euclidean_r"),
+    (lambda: cases.gauss(500, 3, 5), 0.0, "euclidean_r"),        # radius 0: only self / duplicates
+])
+@pytest.mark.parametrize("method", ["grid", "tiled"])
+def test_neighbour_sets_equal_brute_force(ctx, maker, r, metric, method):
+    x = maker()
+    rc = port.adjust_radius(r, metric)
+    want_rp, want_ci = port.neighbours(x, rc, metric, method="brute")
+    nnz = ctx.neighbours_from_points(x, rc, metric=metric, method=method)
+    rp, ci = ctx.neighbours_export()
+    assert nnz == want_rp[-1]
+    np.testing.assert_array_equal(rp, want_rp)
+    np.testing.assert_array_equal(ci, want_ci)
+
+
+def test_neighbour_search_high_dim_and_odd_sizes(ctx):
+    for n, d in [(1, 3), (2, 2), (63, 7), (65, 17), (257, 33), (130, 64)]:
+        x = cases.gauss(n, d, n + d)
+        r = 0.9 * np.sqrt(d)
+        want = port.neighbours(x, r * r, method="brute")
+        ctx.neighbours_from_points(x, r * r, method="auto")
+        got = ctx.neighbours_export()
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+
+
+# ---- precomputed neighbourhoods (lookup path) ------------------------------------------------------------
+def test_lookup_recipes_equal_oracle():
+    x = datasets.md_like_3d(6000)
+    rp, ci = port.neighbours(x, 0.3 ** 2)
+    want = port.fit_csr(rp, ci, 8, member_cutoff=5)
+    # reference container layout: list of lists -> padded int64 + counts
+    nb = [ci[rp[i]:rp[i + 1]] for i in range(x.shape[0])]
+    cl = fit_via_api(nb, 0.3, 8, recipe="sorted_neighbourhoods", member_cutoff=5)
+    np.testing.assert_array_equal(cl.labels, want)
+    # CSR input, int64 and int32 indices
+    for dt in (np.int64, np.int32):
+        cl = fit_via_api((rp, ci.astype(dt)), 0.3, 8, recipe="neighbourhoods_csr", member_cutoff=5)
+        np.testing.assert_array_equal(cl.labels, want)
+
+
+def test_lookup_without_selfcounting(ctx):
+    # lists without the point itself: n_member_cutoff = c, similarity_cutoff = c (_fit.pyx:143-151)
+    x = datasets.blobs_2d(2000)
+    rp, ci = port.neighbours(x, 0.12 ** 2)
+    keep = ci != np.repeat(np.arange(x.shape[0]), np.diff(rp))
+    ci2 = ci[keep]
+    rp2 = np.zeros_like(rp)
+    np.cumsum(np.diff(rp) - 1, out=rp2[1:])
+    for c in (0, 3, 10):
+        want = port.fit_csr(rp2, ci2, c, selfcounting=False)
+        ctx.neighbours_from_csr(rp2, ci2)
+        lab = np.zeros(x.shape[0], dtype=np.int64)
+        ctx.fit(c, c, 1, lab)
+        ctx.sort_by_size(lab)
+        np.testing.assert_array_equal(lab, want)
+
+
+def test_ingest_rejects_bad_input(ctx):
+    rp = np.array([0, 2, 3], dtype=np.int64)
+    with pytest.raises(ValueError):
+        ctx.neighbours_from_csr(rp, np.array([0, 5, 1], dtype=np.int64))  # index out of range
+    with pytest.raises(ValueError):
+        ctx.neighbours_from_csr(np.array([0, 3, 2], dtype=np.int64), np.array([0, 1, 1], dtype=np.int64))
+    with pytest.raises(ValueError):
+        ctx.neighbours_from_padded(np.zeros((2, 2), dtype=np.int64), np.array([3, 0], dtype=np.int64))
+    with pytest.raises(ValueError):
+        ctx.neighbours_from_points(np.array([[0.0, np.nan]]), 1.0)
+    with pytest.raises(_lib.CnnB200Error):
+        _lib.Context(0).fit(1, 2, 1, np.zeros(3, dtype=np.int64))  # no neighbourhoods yet
+
+
+# ---- similarity checker ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("a,b,c,expected", [
+    # reference test/unit/test_check_similarity.py:41-48 (sorted cases)
+    ([], [], 0, True),
+    ([], [], 1, False),
+    ([1, 2, 3], [2, 5], 1, True),
+    ([1, 2, 3], [2, 5, 8, 9], 2, False),
+    ([1, 2, 3, 9, 10], [2, 5, 8, 9, 10], 3, True),
+])
+def test_check_truth_table(a, b, c, expected):
+    chk = _types.SimilarityCheckerCommonNN()
+    assert chk.check(a, b, _types.ClusterParameters(0.0, c)) == expected
+
+
+def test_common_neighbour_counts_equal_oracle(ctx):
+    x = datasets.blobs_2d(2500)
+    rp, ci = port.neighbours(x, 0.15 ** 2)
+    ctx.neighbours_from_csr(rp, ci)
+    cutoff = 6
+    counts, n_edges = ctx.cn_count(cutoff)
+    deg = np.diff(rp)
+    rows = np.repeat(np.arange(x.shape[0]), deg)
+    is_edge = (ci > rows) & (deg[rows] > cutoff) & (deg[ci] > cutoff)
+    assert n_edges == int(is_edge.sum())
+    assert (counts[~is_edge] == 0xFFFFFFFF).all()
+    idx = np.flatnonzero(is_edge)
+    pick = idx[:: max(1, idx.size // 3000)]
+    for k in pick:
+        i, j = rows[k], ci[k]
+        assert counts[k] == port.count_common(ci[rp[i]:rp[i + 1]], ci[rp[j]:rp[j + 1]])
+    # long lists (reference benchmark case equal_c50: identical lists, docsrc/benchmark/bm_similarity.ipynb)
+    chk = _types.SimilarityCheckerCommonNN()
+    a = np.arange(20000)
+    assert chk.get(a, a) == 20000
+    assert chk.get(a[::2], a[1::2]) == 0
+
+
+# ---- fitter: frozen labels / consider masks / numbering ----------------------------------------------------
+def test_partial_consider_mask_and_current_start(ctx):
+    x = datasets.blobs_2d(2500)
+    rp, ci = port.neighbours(x, 0.1 ** 2)
+    rng = np.random.default_rng(5)
+    consider = (rng.random(x.shape[0]) < 0.7).astype(np.uint8)
+    base = np.where(consider == 0, 3, 0).astype(np.int64)  # "frozen" points carry label 3
+    want = port.fit_bfs(rp, ci, 6, 7, current_start=4, labels=base.copy(), consider=consider.copy())
+    ctx.neighbours_from_csr(rp, ci)
+    lab, con = base.copy(), consider.copy()
+    ctx.fit(6, 7, 4, lab, con)
+    np.testing.assert_array_equal(lab, want)
+    assert not con.any()
+
+
+def test_frozen_labels_through_clustering_api():
+    x = datasets.blobs_2d(2000)
+    cl = cluster.Clustering(x)
+    cl.fit(0.1, 10, v=False)
+    first = cl.labels.copy()
+    cl.root.labels.meta["frozen"] = True
+    cl.root.labels.consider[:] = (first == 0).astype(np.uint8)  # recluster the noise, keep the rest
+    cl.fit(0.2, 3, v=False, sort_by_size=False)
+    rp, ci = port.neighbours(x, 0.2 ** 2)
+    want = port.fit_bfs(rp, ci, 4, 5, current_start=int(first.max()) + 1, labels=first.copy(),
+                        consider=(first == 0).astype(np.uint8))
+    np.testing.assert_array_equal(cl.labels, want)
+
+
+@pytest.mark.parametrize("kwargs,expected", [
+    # reference test/unit/test_types.py:98-117
+    ({"member_cutoff": 1}, [1, 1, 3, 3, 0, 1, 2, 2, 2, 1, 4]),
+    ({}, [1, 1, 3, 3, 0, 1, 2, 2, 2, 1, 0]),
+    ({"member_cutoff": 2, "max_clusters": 2}, [1, 1, 0, 0, 0, 1, 2, 2, 2, 1, 0]),
+])
+def test_sort_by_size_known_answers(kwargs, expected):
+    lab = _types.Labels(np.array([1, 1, 2, 2, 0, 1, 3, 3, 3, 1, 5], dtype=np.int64))
+    lab.meta["params"] = {1: "a", 2: "b", 3: "c", 5: "e"}
+    lab.sort_by_size(**kwargs)
+    assert lab.labels.tolist() == expected
+    # meta["params"] is re-keyed like the labels (_types.pyx:268-273)
+    want = {e: v for o, e, v in [(1, expected[0], "a"), (2, expected[2], "b"), (3, expected[6], "c"), (5, expected[10], "e")] if e}
+    assert lab.meta["params"] == want
+
+
+def test_sort_by_size_random_equals_oracle(ctx):
+    rng = np.random.default_rng(3)
+    for trial in range(10):
+        n = int(rng.integers(1, 50000))
+        lab = rng.integers(0, max(2, int(rng.integers(2, 400))), n).astype(np.int64)
+        if trial % 3 == 0:
+            lab[rng.random(n) < 0.5] = 7  # one dominant label: heavy same-address atomics
+        mc = [None, 1, 5, 50][trial % 4]
+        mx = [None, 3, None, 10][trial % 4]
+        want = port.sort_by_size(lab.copy(), mc, mx)
+        got = lab.copy()
+        ctx.sort_by_size(got, mc, mx)
+        np.testing.assert_array_equal(got, want)
+    zero = np.zeros(10, dtype=np.int64)
+    ctx.sort_by_size(zero)
+    assert not zero.any()
+
+
+def test_random_configs_equal_oracle():
+    rng = np.random.default_rng(11)
+    for trial in range(25):
+        n = int(rng.integers(1, 3000))
+        d = int(rng.choice([1, 2, 3, 4, 6]))
+        x = rng.standard_normal((n, d)) if trial % 3 else cases.lattice(n, d, trial)
+        r = float(rng.uniform(0.1, 0.8)) * (1.0 if d <= 3 else np.sqrt(d) / 1.5)
+        c = int(rng.integers(0, 12))
+        opts = [dict(), dict(member_cutoff=5), dict(sort_by_size=False), dict(member_cutoff=1, max_clusters=3)][trial % 4]
+        o = dict(opts)
+        want = port.fit_points(x, r, c, sort=o.pop("sort_by_size", True), **o)
+        got = fit_via_api(x, r, c, **opts).labels
+        np.testing.assert_array_equal(got, want, err_msg=f"trial {trial} n={n} d={d} r={r} c={c} {opts}")
+
+
+def test_vendored_scan_records():
+    """All sampled cells of the reference's vendored scan records (docsrc/benchmark/records)."""
+    with open(os.path.join(HERE, "golden", "records_sample.json")) as fp:
+        sample = json.load(fp)
+    for name, recs in sample.items():
+        x = cases.RECORD_SETS[name]()
+        cl = cluster.Clustering(x)
+        for rec in recs:
+            cl.fit(rec["radius_cutoff"], rec["cnn_cutoff"], member_cutoff=rec["member_cutoff"], v=False)
+            got = cl.summary[-1]
+            assert got.n_clusters == rec["n_clusters"], (name, rec)
+            assert abs(got.ratio_noise - rec["ratio_noise"]) < 1e-12, (name, rec)
+            assert abs(got.ratio_largest - rec["ratio_largest"]) < 1e-12, (name, rec)
+
+
+# ---- device-resident inputs --------------------------------------------------------------------------------
+def test_device_resident_inputs_equal_host_path(ctx):
+    import torch
+
+    x = datasets.md_like_3d(30000)
+    want = np.empty(x.shape[0], dtype=np.int64)
+    ctx.fit_points(x, 0.2 ** 2, 11, 12, want, member_cutoff=10)
+    xd = torch.from_numpy(x).cuda()
+    lab = torch.empty(x.shape[0], dtype=torch.int64, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream())
+    ctx.fit_points(xd, 0.2 ** 2, 11, 12, lab, member_cutoff=10)
+    np.testing.assert_array_equal(lab.cpu().numpy(), want)
+    np.testing.assert_array_equal(want, port.fit_points(x, 0.2, 10, member_cutoff=10))
+    ctx.set_stream(None)
+
+
+def test_torch_allocator_hook():
+    import torch
+
+    c2 = _lib.Context(0, torch_allocator=True)
+    x = datasets.blobs_2d(3000)
+    lab = np.empty(3000, dtype=np.int64)
+    before = torch.cuda.memory_allocated()
+    c2.fit_points(x, 0.01, 11, 12, lab)
+    assert torch.cuda.memory_allocated() > before  # scratch came from torch's caching allocator
+    np.testing.assert_array_equal(lab, port.fit_points(x, 0.1, 10))
+    c2.close()
+
+
+# ---- full-size configurations: properties that do not need the oracle's answer ---------------------------------
+def test_c2_full_size_properties_and_oracle(ctx):
+    """BASELINE configs[1]: N = 1e6 3-D MD-like, r = 0.09, c = 20, member_cutoff = 10."""
+    n = 1_000_000
+    x = datasets.md_like_3d(n)
+    p = datasets.C2_PARAMS
+    r, c = p["radius_cutoff"], p["cnn_cutoff"]
+    lab = np.empty(n, dtype=np.int64)
+    ctx.fit_points(x, r * r, c + 1, c + 2, lab, member_cutoff=p["member_cutoff"])
+    _, nnz, max_deg = ctx.neighbours_info()
+    assert (nnz, max_deg) == (72_661_402, 484)      # SURVEY 8(d), measured with the reference
+    assert int(lab.max()) == 167
+    # idempotence: relabelling canonical labels is the identity
+    again = lab.copy()
+    ctx.sort_by_size(again, p["member_cutoff"])
+    np.testing.assert_array_equal(again, lab)
+    # sizes are non-increasing in the label and every kept cluster has >= member_cutoff members
+    sizes = np.bincount(lab)[1:]
+    assert (np.diff(sizes) <= 0).all() and sizes.min() >= p["member_cutoff"]
+    # invariance under a permutation of the input points (labels follow the points; numbering is
+    # by size, ties by first occurrence, so compare partitions)
+    perm = np.random.default_rng(1).permutation(n)
+    lab_p = np.empty(n, dtype=np.int64)
+    ctx.fit_points(np.ascontiguousarray(x[perm]), r * r, c + 1, c + 2, lab_p, member_cutoff=p["member_cutoff"])
+    assert ((lab_p == 0) == (lab[perm] == 0)).all()
+    pairs = np.unique(np.stack([lab[perm], lab_p]), axis=1)
+    assert pairs.shape[1] == 168 and np.unique(pairs[0]).size == 168 and np.unique(pairs[1]).size == 168
+    np.testing.assert_array_equal(np.bincount(lab_p), np.bincount(lab))
+    # and the oracle itself (grid neighbour search + BFS, ~10 s on one core)
+    np.testing.assert_array_equal(lab, port.fit_points(x, r, c, member_cutoff=p["member_cutoff"]))
+
+
+def test_c1_through_lookup_equals_coordinates():
+    """BASELINE configs[0] by both routes the reference offers (coordinates / sorted neighbourhoods)."""
+    x = datasets.blobs_2d(10_000)
+    a = fit_via_api(x, 0.3, 10).labels
+    rp, ci = port.neighbours(x, 0.3 ** 2)
+    b = fit_via_api((rp, ci), 0.3, 10, recipe="neighbourhoods_csr").labels
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(a, GOLD["c1_full"].astype(np.int64))

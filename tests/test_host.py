@@ -1,0 +1,90 @@
+"""Host-side mirror of the reference interface: parameters, labels container, recipes, hooks."""
+import numpy as np
+import pytest
+
+from commonnnclustering_b200 import _fit, _types, cluster, datasets, recipes
+
+
+def test_cluster_parameters_defaults():
+    # reference test/unit/test_types/test_create_params_0_1_1_.txt
+    p = _types.ClusterParameters(0.1, 1, 1.)
+    assert p.to_dict() == {"radius_cutoff": 0.1, "similarity_cutoff": 1, "similarity_cutoff_continuous": 1.0,
+                           "n_member_cutoff": 1, "current_start": 1}
+
+
+def test_make_parameters_coordinates_recipe():
+    f = _fit.FitterB200()
+    p = f.make_parameters(0.3, 10, 1)
+    assert p.radius_cutoff == 0.3 * 0.3 and p.similarity_cutoff == 12 and p.n_member_cutoff == 11
+    f = _fit.FitterB200(_types.NeighboursGetterRadius(_types.DistanceGetterMetric(_types.MetricEuclidean())))
+    assert f.make_parameters(0.3, 10, 4).radius_cutoff == 0.3
+    f = _fit.FitterB200(_types.NeighboursGetterLookup(is_selfcounting=False))
+    p = f.make_parameters(0.3, 10, 1)
+    assert (p.radius_cutoff, p.similarity_cutoff, p.n_member_cutoff) == (0.3, 10, 10)
+
+
+def test_labels_container():
+    lab = _types.Labels.from_sequence([1, 1, 2, 2, 0, 1])
+    assert lab.n_points == 6 and lab.set == {0, 1, 2}
+    assert dict(lab.mapping) == {0: [4], 1: [0, 1, 5], 2: [2, 3]}
+    assert lab.consider.tolist() == [1] * 6
+    with pytest.raises(ValueError):
+        _types.Labels(np.zeros(3, dtype=np.int64), consider=np.ones(2, dtype=np.uint8))
+    a = np.zeros(4, dtype=np.int64)
+    assert _types.Labels(a).labels is a  # a view: in-place writes by a fitter are visible
+
+
+def test_builder_default_recipe():
+    b = recipes.Builder()
+    f = b.make_component("fitter")
+    assert isinstance(f, _fit.FitterB200Fused)
+    assert isinstance(f._neighbours_getter, _types.NeighboursGetterRadius)
+    assert isinstance(f._neighbours_getter.metric, _types.MetricEuclideanReduced)
+    b = recipes.Builder(fitter__ngetter__dgetter__metric="euclidean")
+    assert isinstance(b.make_component("fitter")._neighbours_getter.metric, _types.MetricEuclidean)
+    b = recipes.Builder("sorted_neighbourhoods")
+    f = b.make_component("fitter")
+    assert isinstance(f._neighbours_getter, _types.NeighboursGetterLookup) and f._neighbours_getter.is_selfcounting
+
+
+def test_prepare_points_from_parts():
+    # reference test/unit/test_hooks.py
+    (a,), kw = recipes.prepare_points_from_parts([[0, 0], [1, 1]])
+    assert a.shape == (2, 2) and kw["meta"]["edges"] == [2] and a.dtype == np.float64 and a.flags.c_contiguous
+    (a,), kw = recipes.prepare_points_from_parts([[[0, 0], [1, 1]], [[2, 2]]])
+    assert a.shape == (3, 2) and kw["meta"]["edges"] == [2, 1]
+    (a,), kw = recipes.prepare_points_from_parts([1, 2, 3])
+    assert a.shape == (1, 3)
+
+
+def test_prepare_neighbourhoods_padding():
+    (padded, counts), _ = recipes.prepare_neighbourhoods([[0, 1], [0, 1, 2], [2]])
+    assert padded.tolist() == [[0, 1, 0], [0, 1, 2], [2, 0, 0]] and counts.tolist() == [2, 3, 1]
+
+
+def test_clustering_construction():
+    c = cluster.Clustering(datasets.README_POINTS)
+    assert c.root.input_data.n_points == 12 and c.labels is None
+    assert isinstance(c.fitter, _fit.Fitter)
+    with pytest.raises(TypeError):
+        c.fitter = object()
+
+
+def test_datasets_are_deterministic():
+    a, b = datasets.md_like_3d(2000), datasets.md_like_3d(2000)
+    assert np.array_equal(a, b) and a.shape == (2000, 3)
+    # the state chain is sequential by definition; the vectorised form must equal a plain loop
+    rng = np.random.default_rng(0)
+    rng.random((12, 3)); rng.uniform(0.25, 0.6, 12)
+    n = 5000
+    switch = rng.random(n) < 1e-3
+    new_state = rng.integers(0, 12, n)
+    state = np.zeros(n, dtype=np.int64)
+    prev = 0
+    for i in range(n):
+        prev = new_state[i] if switch[i] else prev
+        state[i] = prev
+    idx = np.where(switch, np.arange(n), -1)
+    last = np.maximum.accumulate(idx)
+    assert np.array_equal(state, np.where(last >= 0, new_state[np.maximum(last, 0)], 0))
+    assert datasets.features_64d(500).shape == (500, 64)

@@ -181,14 +181,20 @@ def stage_rooflines(timings, steps, n, d, nnz, stats, peak):
         return {"kernel": kernel, "stage": stage, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": None, "ms_per_launch": dur, "algorithmic_bytes": nbytes, "note": note}
 
+    gapped = timings["search_fill"][0] < 0.5 * timings["search_count"][0]  # single-pass search + compaction
     out = [
-        entry("search_count", "grid_rows_kernel<count>", 8 * d * n + 4 * n, "8*D*N coords in + 4*N degrees out"),
-        entry("search_fill", "grid_rows_kernel<fill>", 8 * d * n + 4 * nnz + 8 * (n + 1),
-              "8*D*N coords in + 4*nnz col_idx out + 8*(N+1) row_ptr in"),
-        entry("comp_edges", "comp_edges_kernel", 4 * nnz + 8 * (n + 1) + 5 * n + 8 * stats["accepted"],
-              "CSR scanned once (4*nnz + 8*(N+1)) + core/parent (5*N) + 8*accepted edges; rows re-read by the "
-              "executed CN checks are not counted"),
-        entry("comp_sample", "comp_sample_kernel", 8 * (n + 1) + 5 * n + 4 * 4 * n, "row_ptr + core/parent + 4 sampled rows heads"),
+        entry("search_count", "grid_rows_kernel<single pass>" if gapped else "grid_rows_kernel<count>",
+              8 * d * n + 4 * n + (4 * nnz if gapped else 0),
+              "8*D*N coords in + 4*N degrees out" + (" + 4*nnz hits out (gapped rows)" if gapped else "")),
+        entry("search_fill", "compact_rows_kernel" if gapped else "grid_rows_kernel<fill>",
+              (8 * nnz + 16 * (n + 1)) if gapped else (8 * d * n + 4 * nnz + 8 * (n + 1)),
+              "4*nnz in + 4*nnz out + 16*(N+1) offsets" if gapped else "8*D*N coords in + 4*nnz col_idx out + 8*(N+1) row_ptr in"),
+        entry("comp_edges", "comp_scan_kernel + comp_worklist_kernel",
+              4 * nnz + 8 * (n + 1) + 4 * n + 4 * stats["candidate_edges"] + 8 * (stats["candidate_edges"] - stats["skipped"]),
+              "CSR scanned once (4*nnz + 8*(N+1)) + 4*N parents + one 4-byte parent look-up per candidate edge + 8 B per "
+              "work-list entry; rows re-read by the executed CN checks are not counted"),
+        entry("comp_sample", "comp_sample_kernel + comp_union_kernel", 8 * (n + 1) + 4 * n + 2 * 4 * n,
+              "row_ptr + parents + the sampled edge slots; rows read by the executed CN checks are not counted"),
     ]
     return [e for e in out if e]
 

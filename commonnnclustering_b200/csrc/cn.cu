@@ -54,12 +54,13 @@ __device__ __forceinline__ bool uf_union(int *parent, int a, int b) {
     return false;
 }
 
-// Warp-cooperative |A ∩ B| over ascending int32 lists.
+// Warp-cooperative |A ∩ B| over ascending int32 lists in global memory (L1/L2 resident: a row
+// and the rows of its neighbours sit next to each other in the cell-sorted CSR).
 //   CHECK = true : early exit, returns 1 as soon as `cutoff` common elements are found, 0 when
 //                  that has become impossible (SimilarityChecker._check semantics).
 //   CHECK = false: returns the full count (SimilarityChecker._get semantics).
-// Lanes take 32 consecutive elements of the shorter list and binary-search them in the
-// not-yet-consumed tail of the longer one.
+// The shorter list is streamed 32 consecutive entries at a time (one coalesced load); each lane
+// binary-searches its entry in the not-yet-consumed tail of the longer list.
 template <bool CHECK>
 __device__ __forceinline__ int warp_common(const int *__restrict__ a, int na, const int *__restrict__ b,
                                            int nb, int cutoff, int lane) {
@@ -91,6 +92,26 @@ __device__ __forceinline__ int warp_common(const int *__restrict__ a, int na, co
     return CHECK ? 0 : count;
 }
 
+// One-thread form of the check for short lists: a branch-free two-pointer merge with early exit,
+// the direct analogue of SimilarityCheckerExtScreensorted._check (_types.pyx:2654-2706).  Used
+// where every lane of a warp has its OWN pair of rows to compare (32 independent merges in
+// flight per warp hide the load latency that a single cooperative intersection cannot).
+__device__ __forceinline__ int lane_check(const int *__restrict__ a, int na, const int *__restrict__ b, int nb,
+                                          int cutoff) {
+    if (cutoff <= 0) return 1;
+    if (na < cutoff || nb < cutoff) return 0;
+    int ia = 0, ib = 0, count = 0;
+    while (ia < na && ib < nb) {
+        const int va = a[ia], vb = b[ib];
+        count += va == vb ? 1 : 0;
+        ia += va <= vb ? 1 : 0;
+        ib += vb <= va ? 1 : 0;
+        if (count >= cutoff) return 1;
+    }
+    return 0;
+}
+
+// parent[p] = p for core points, -1 for the others (so one load answers "core?" and "which tree?")
 __global__ void comp_init_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ perm,
                                  const uint8_t *__restrict__ consider, ll n, ll n_member_cutoff,
                                  int *parent, uint8_t *core) {
@@ -100,56 +121,56 @@ __global__ void comp_init_kernel(const ll *__restrict__ row_ptr, const int *__re
     bool c = deg > n_member_cutoff;  // `_enough`: n_points > cutoff (_types.pyx:1408-1411)
     if (c && consider) c = consider[perm ? perm[p] : p] != 0;
     core[p] = c ? 1 : 0;
-    parent[p] = (int)p;
+    parent[p] = c ? (int)p : -1;
 }
 
-// Sampling pass: every core row links with the core neighbours that sit next to it in its own
-// row (closest in the cell-sorted order) and with the first and last core entries of the row.
+#define MAX_SAMPLES 2
+
+// Sampling pass (Afforest-style).  A warp takes 32 consecutive rows; everything that is a chain of
+// dependent loads per row (core flag, row bounds, picking the sampled neighbour, its core flag and
+// row bounds) is done with one row per LANE, so 32 such chains are in flight per warp; only the
+// intersection itself is warp-cooperative.  Sample s = 0 is the first entry above i (the nearest
+// point in the cell-sorted order), s = 1 the last entry of the row.  Accepted edges are recorded
+// and linked afterwards by comp_union_kernel with one thread per edge -- no union-find traffic here.
 __global__ void __launch_bounds__(256)
-comp_sample_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx,
-                   const uint8_t *__restrict__ core, ll row_begin, ll row_end, int cutoff, int *parent,
+comp_sample_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll row_begin, ll row_end,
+                   int cutoff, int n_samples, const int *__restrict__ parent, int *__restrict__ edge_out,
                    unsigned long long *stats) {
+    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     unsigned long long n_checks = 0, n_acc = 0;
-    for (ll i = row_begin + warp; i < row_end; i += nwarps) {
-        if (!core[i]) continue;
-        ll b = row_ptr[i];
-        int m = (int)(row_ptr[i + 1] - b);
-        const int *row = col_idx + b;
-        // position of the first entry > i (rows are ascending)
-        int l = 0, h = m;
-        while (l < h) {
-            int mid = (l + h) >> 1;
-            if (row[mid] <= (int)i) l = mid + 1; else h = mid;
-        }
-        // candidates: next after self, previous before self, first, last
-        int cand[4];
-        cand[0] = l < m ? row[l] : -1;
-        int ps = l - 1;
-        if (ps >= 0 && row[ps] == (int)i) --ps;
-        cand[1] = ps >= 0 ? row[ps] : -1;
-        cand[2] = m > 0 ? row[0] : -1;
-        cand[3] = m > 0 ? row[m - 1] : -1;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            int j = cand[t];
-            if (j < 0 || j == (int)i || !core[j]) continue;
-            bool dup = false;
-            for (int u = 0; u < t; ++u) dup |= cand[u] == j;
-            if (dup) continue;
-            int same = 0;
-            if (lane == 0) same = uf_find(parent, (int)i) == uf_find(parent, j);
-            same = __shfl_sync(0xffffffffu, same, 0);
-            if (same) continue;
-            ll bj = row_ptr[j];
-            int mj = (int)(row_ptr[j + 1] - bj);
-            ++n_checks;
-            if (warp_common<true>(row, m, col_idx + bj, mj, cutoff, lane)) {
-                if (lane == 0) uf_union(parent, (int)i, j);
-                ++n_acc;
+    for (ll i0 = row_begin + warp * 32; i0 < row_end; i0 += nwarps * 32) {
+        const ll i = i0 + lane;
+        const bool valid = i < row_end;
+        const bool core_i = valid && parent[i] >= 0;
+        const ll rb = valid ? row_ptr[i] : 0;
+        const int m = valid ? (int)(row_ptr[i + 1] - rb) : 0;
+        int first_above = -1;
+        for (int smp = 0; smp < n_samples; ++smp) {
+            int j = -1;
+            if (core_i && m > 0) {
+                if (smp == 0) {
+                    int l = 0, h = m;  // first entry > i
+                    while (l < h) {
+                        int mid = (l + h) >> 1;
+                        if (col_idx[rb + mid] <= (int)i) l = mid + 1; else h = mid;
+                    }
+                    if (l < m) j = col_idx[rb + l];
+                    first_above = j;
+                } else {
+                    j = col_idx[rb + m - 1];
+                    if (j <= (int)i || j == first_above) j = -1;
+                }
             }
+            bool ok = j >= 0 && parent[j] >= 0;
+            const ll jb = ok ? row_ptr[j] : 0;
+            const int mj = ok ? (int)(row_ptr[j + 1] - jb) : 0;
+            const int acc = ok ? lane_check(col_idx + rb, m, col_idx + jb, mj, cutoff) : 0;
+            n_checks += __popc(__ballot_sync(full, ok));
+            n_acc += __popc(__ballot_sync(full, acc != 0));
+            if (valid) edge_out[(i - row_begin) * n_samples + smp] = acc ? j : -1;
         }
     }
     if (lane == 0) {
@@ -158,65 +179,112 @@ comp_sample_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_i
     }
 }
 
+// one thread per recorded edge slot
+__global__ void comp_union_kernel(const int *__restrict__ edge_out, ll row_begin, ll slots, int n_samples,
+                                  int *parent) {
+    ll t = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (t >= slots) return;
+    int j = edge_out[t];
+    if (j >= 0) uf_union(parent, (int)(row_begin + t / n_samples), j);
+}
+
 __global__ void comp_compress_kernel(int *parent, ll n) {
     ll p = blockIdx.x * (ll)blockDim.x + threadIdx.x;
     if (p >= n) return;
+    if (ld_parent(parent, (int)p) < 0) return;
     int r = uf_find_ro(parent, (int)p);
     parent[p] = r;
 }
 
-// Full pass: every candidate edge (i < j, both core) of the row block is settled -- skipped when
-// both ends already share a root, otherwise evaluated and linked when similar enough.
+// Edge scan.  Runs on flattened (root-pointing) parents, which do not change during this kernel:
+// a candidate edge (i < j, both core) is settled for free when parent[i] == parent[j]; the others
+// go to a work list.  A warp takes 32 consecutive rows and streams their entries as ONE contiguous
+// range of the CSR, 32 entries per step, independent of the row boundaries; the row of an entry is
+// found by a 5-step binary search over the 32 row starts held one per lane (shuffles).
 __global__ void __launch_bounds__(256)
-comp_edges_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx,
-                  const uint8_t *__restrict__ core, ll row_begin, ll row_end, int cutoff, int *parent,
-                  unsigned long long *stats) {
+comp_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll row_begin, ll row_end,
+                 const int *__restrict__ parent, int2 *__restrict__ worklist, unsigned long long *wl_count,
+                 unsigned long long *stats) {
+    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
-    unsigned long long n_edges = 0, n_checks = 0, n_acc = 0, n_skip = 0;
-    for (ll i = row_begin + warp; i < row_end; i += nwarps) {
-        if (!core[i]) continue;
-        ll b = row_ptr[i];
-        int m = (int)(row_ptr[i + 1] - b);
-        const int *row = col_idx + b;
-        int ri = 0;
-        if (lane == 0) ri = uf_find(parent, (int)i);
-        ri = __shfl_sync(0xffffffffu, ri, 0);
-        for (int base = 0; base < m; base += 32) {
-            int k = base + lane;
-            int j = k < m ? row[k] : -1;
-            bool cand = j > (int)i && core[j];
-            bool need = cand && uf_find_ro(parent, j) != ri;
-            unsigned cm = __ballot_sync(0xffffffffu, cand);
-            unsigned nm = __ballot_sync(0xffffffffu, need);
-            n_edges += __popc(cm);
-            n_skip += __popc(cm & ~nm);
-            while (nm) {
-                int src = __ffs(nm) - 1;
-                nm &= nm - 1;
-                int jj = __shfl_sync(0xffffffffu, j, src);
-                int same = 0;
-                if (lane == 0) {
-                    ri = uf_find(parent, (int)i);
-                    same = uf_find(parent, jj) == ri;
-                }
-                same = __shfl_sync(0xffffffffu, same, 0);
-                if (same) { ++n_skip; continue; }
-                ll bj = row_ptr[jj];
-                int mj = (int)(row_ptr[jj + 1] - bj);
-                ++n_checks;
-                if (warp_common<true>(row, m, col_idx + bj, mj, cutoff, lane)) {
-                    if (lane == 0) uf_union(parent, (int)i, jj);
-                    ++n_acc;
-                }
+    unsigned long long n_edges = 0, n_need = 0;
+    for (ll i0 = row_begin + warp * 32; i0 < row_end; i0 += nwarps * 32) {
+        const ll i = i0 + lane;
+        const bool valid = i < row_end;
+        const ll rb = row_ptr[valid ? i : row_end];  // lanes past the end hold the end offset
+        const int ri = valid ? parent[i] : -1;
+        const ll beg = __shfl_sync(full, rb, 0);
+        const ll last_row = (i0 + 32 < row_end ? i0 + 32 : row_end);
+        const ll end = row_ptr[last_row];
+        for (ll k0 = beg; k0 < end; k0 += 32) {
+            const ll k = k0 + lane;
+            const bool in = k < end;
+            const int j = in ? col_idx[k] : -1;
+            // row of entry k: last lane t with rb_t <= k
+            int lo = 0;
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+                const ll probe = __shfl_sync(full, rb, lo + step);
+                if (probe <= k) lo += step;
             }
-            if (lane == 0) ri = uf_find(parent, (int)i);
-            ri = __shfl_sync(0xffffffffu, ri, 0);
+            const int r_i = __shfl_sync(full, ri, lo);
+            const int ii = (int)i0 + lo;
+            const int pj = (in && r_i >= 0 && j > ii) ? parent[j] : -1;
+            const bool cand = pj >= 0;
+            const bool need = cand && pj != r_i;
+            const unsigned cm = __ballot_sync(full, cand), nm = __ballot_sync(full, need);
+            n_edges += __popc(cm);
+            if (nm) {
+                unsigned long long pos = 0;
+                if (lane == 0) pos = atomicAdd(wl_count, (unsigned long long)__popc(nm));
+                pos = __shfl_sync(full, pos, 0);
+                if (need) worklist[pos + __popc(nm & lt)] = make_int2(ii, j);
+                n_need += __popc(nm);
+            }
         }
     }
     if (lane == 0) {
         if (n_edges) atomicAdd(stats + ST_EDGES, n_edges);
+        if (n_edges - n_need) atomicAdd(stats + ST_SKIPPED, n_edges - n_need);
+    }
+}
+
+// Work-list pass: the edges the scan could not settle.  32 edges per warp step: the finds (with
+// path halving) and the row bounds are fetched one edge per LANE; edges whose ends meanwhile share
+// a root are dropped; the rest is evaluated warp-cooperatively and linked when similar enough.
+__global__ void __launch_bounds__(256)
+comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, const int2 *__restrict__ worklist,
+                     const unsigned long long *__restrict__ wl_count, int cutoff, int *parent,
+                     unsigned long long *stats) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    const ll count = (ll)*wl_count;
+    unsigned long long n_checks = 0, n_acc = 0, n_skip = 0;
+    for (ll e0 = warp * 32; e0 < count; e0 += nwarps * 32) {
+        const ll e = e0 + lane;
+        const bool valid = e < count;
+        const int2 ed = valid ? worklist[e] : make_int2(0, 0);
+        int ri = valid ? uf_find(parent, ed.x) : 0;
+        int rj = valid ? uf_find(parent, ed.y) : 0;
+        const bool need = valid && ri != rj;
+        const ll bi = need ? row_ptr[ed.x] : 0, bj = need ? row_ptr[ed.y] : 0;
+        const int mi = need ? (int)(row_ptr[ed.x + 1] - bi) : 0, mj = need ? (int)(row_ptr[ed.y + 1] - bj) : 0;
+        const unsigned work = __ballot_sync(full, need);
+        n_skip += __popc(__ballot_sync(full, valid)) - __popc(work);
+        n_checks += __popc(work);
+        int acc = 0;
+        if (need) {
+            acc = lane_check(col_idx + bi, mi, col_idx + bj, mj, cutoff);
+            if (acc) uf_union(parent, ri, rj);
+        }
+        n_acc += __popc(__ballot_sync(full, acc != 0));
+    }
+    if (lane == 0) {
         if (n_checks) atomicAdd(stats + ST_CHECKS, n_checks);
         if (n_acc) atomicAdd(stats + ST_ACCEPTED, n_acc);
         if (n_skip) atomicAdd(stats + ST_SKIPPED, n_skip);
@@ -230,7 +298,7 @@ __global__ void comp_merge_kernel(const int *__restrict__ others, ll n, ll count
     for (; t < n * count; t += stride) {
         int i = (int)(t % n);
         int o = others[t];
-        if (o != i) uf_union(parent, i, o);
+        if (o >= 0 && o != i) uf_union(parent, i, o);
     }
 }
 
@@ -320,27 +388,41 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
     if (rows == 0) return CNNB200_OK;
     // a similarity cutoff beyond any possible intersection size links nothing
     int cutoff = ctx->similarity_cutoff > 0x7fffffffll ? 0x7fffffff : (int)ctx->similarity_cutoff;
-    int blocks = (int)((rows + 7) / 8);
-    int cap = ctx->sm_count * 8;
-    if (blocks > cap) blocks = cap;
     unsigned long long *stats = (unsigned long long *)ctx->b_stats.p;
-    {
+    const int ns = ctx->n_samples < MAX_SAMPLES ? ctx->n_samples : MAX_SAMPLES;
+    int *parent = ctx->b_parent.as<int>();
+    if (ns > 0) {
         Span sp(ctx, T_COMP_SAMPLE);
-        comp_sample_kernel<<<blocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, ctx->b_core.as<uint8_t>(), row_begin,
-                                                   row_end, cutoff, ctx->b_parent.as<int>(), stats);
+        ll slots = rows * ns;
+        CNN_TRY(cnn_ensure(ctx, ctx->b_edges, sizeof(int) * (size_t)slots));
+        int sblocks = (int)((rows + 255) / 256);
+        if (sblocks > ctx->sm_count * 32) sblocks = ctx->sm_count * 32;
+        comp_sample_kernel<<<sblocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, cutoff, ns, parent,
+                                                    ctx->b_edges.as<int>(), stats);
+        comp_union_kernel<<<cnn_blocks(slots, 256), 256, 0, st>>>(ctx->b_edges.as<int>(), row_begin, slots, ns, parent);
+        CNN_LAUNCHED(ctx, 2);
     }
     {
         Span sp(ctx, T_COMP_FLATTEN);
-        comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(ctx->b_parent.as<int>(), ctx->n);
+        comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(parent, ctx->n);
     }
     {
         Span sp(ctx, T_COMP_EDGES);
-        comp_edges_kernel<<<blocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, ctx->b_core.as<uint8_t>(), row_begin,
-                                                  row_end, cutoff, ctx->b_parent.as<int>(), stats);
+        // work list: at most one entry per CSR entry of the row block (candidate edges are the entries j > i)
+        ll cap_edges = ctx->nnz + 64;
+        CNN_TRY(cnn_ensure(ctx, ctx->b_worklist, sizeof(int2) * (size_t)cap_edges));
+        unsigned long long *wl_count = stats + ST_N - 1;
+        CNN_CUDA(cudaMemsetAsync(wl_count, 0, sizeof(unsigned long long), st));
+        int sblocks = (int)((rows + 255) / 256);
+        if (sblocks > ctx->sm_count * 32) sblocks = ctx->sm_count * 32;
+        comp_scan_kernel<<<sblocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, parent,
+                                                  ctx->b_worklist.as<int2>(), wl_count, stats);
+        comp_worklist_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, ctx->b_worklist.as<int2>(),
+                                                               wl_count, cutoff, parent, stats);
     }
     {
         Span sp(ctx, T_COMP_FLATTEN);
-        comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(ctx->b_parent.as<int>(), ctx->n);
+        comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(parent, ctx->n);
     }
     CNN_LAUNCHED(ctx, 4);
     CNN_KERNEL_CHECK();

@@ -78,6 +78,8 @@ struct cnnb200_ctx {
     cnnb200_free_fn free_ = nullptr;
     void *alloc_user = nullptr;
     int sm_count = 148;
+    ll single_pass_limit = 8ll << 30;  // bytes of gapped scratch the single-pass search may use (0 = two-pass)
+    int n_samples = 2;  // edges per core row tried by the sampling pass (tunable: CNNB200_SAMPLES)
 
     // ---- neighbourhood structure (internal index space) -------------------------------
     bool have_nb = false;
@@ -98,6 +100,8 @@ struct cnnb200_ctx {
     ll n_member_cutoff = 0, similarity_cutoff = 0;
     Buf b_parent;  // int32 [n]
     Buf b_core;    // uint8 [n]
+    Buf b_edges;     // int32 [rows * samples]: edges accepted by the sampling pass
+    Buf b_worklist;  // int2 [<= nnz/2]: candidate edges the scan could not settle
     Buf b_minorig, b_flags, b_rank, b_labels, b_consider, b_stats;
     Buf b_lab_count, b_lab_first, b_lab_keys, b_lab_keys2, b_lab_vals, b_lab_vals2, b_lab_map;
 

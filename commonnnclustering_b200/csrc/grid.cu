@@ -103,40 +103,120 @@ __device__ __forceinline__ bool within(double qx, double qy, double qz, const do
     return s <= rc;
 }
 
-template <int D, bool SQRT, bool FILL>
+// One warp per tile of 32 consecutive cell-sorted points.  Within the tile, points of the same
+// cell form a group of g contiguous lanes that shares one candidate list (the 3^D cells around
+// it = 3^(D-1) contiguous index runs).  The 32 lanes are laid out as gp x k (gp = g rounded up to
+// a power of two, k = 32 / gp): lane = sub * gp + jq tests query jq against candidate q0 + sub,
+// so dense cells (g = 32, k = 1: one candidate broadcast to 32 queries) and isolated points
+// (g = 1, k = 32: one query against 32 candidates) both keep the lanes busy.
+//   count pass: per-lane hit counts, summed over `sub` by shuffles -> deg[]
+//   fill pass : hits of one step are ranked with a ballot restricted to the lanes of the same
+//               query (mask rep << jq); candidates ascend with the lane index, so rows come out
+//               ascending in the cell-sorted index space.
+__constant__ unsigned c_rep[6] = {0xffffffffu, 0x55555555u, 0x11111111u, 0x01010101u, 0x00010001u, 0x00000001u};
+
+// MODE 0: count pass (deg[] only)            } the two-pass form, used when the single-pass
+// MODE 1: fill pass (recomputes the distances) } scratch would not fit
+// MODE 2: single pass -- hits are written straight into a gapped buffer in which row p owns
+//         cap[p] slots (cap = size of its candidate list >= its degree) and deg[] comes out of
+//         the same pass; compact_rows_kernel then squeezes the rows into the CSR.
+template <int D, bool SQRT, int MODE>
 __global__ void __launch_bounds__(256)
 grid_rows_kernel(const double *__restrict__ xs, ll n, const int *__restrict__ cell_sorted,
                  const int *__restrict__ cell_start, GridDesc g, double rc, int *__restrict__ deg,
                  const ll *__restrict__ row_ptr, int *__restrict__ col_idx) {
+    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
-    for (ll p = warp; p < n; p += nwarps) {
-        int cid = cell_sorted[p];
-        int cx = cid % g.dims[0];
-        int t = cid / g.dims[0];
-        int cy = t % g.dims[1];
-        int cz = t / g.dims[1];
-        double qx = xs[p], qy = D > 1 ? xs[n + p] : 0.0, qz = D > 2 ? xs[2 * n + p] : 0.0;
-        int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
-        int y0 = D > 1 ? max(cy - 1, 0) : 0, y1 = D > 1 ? min(cy + 1, g.dims[1] - 1) : 0;
-        int z0 = D > 2 ? max(cz - 1, 0) : 0, z1 = D > 2 ? min(cz + 1, g.dims[2] - 1) : 0;
-        ll base = FILL ? row_ptr[p] : 0;
-        int cnt = 0;
-        for (int z = z0; z <= z1; ++z)
-            for (int y = y0; y <= y1; ++y) {
-                int cb = (z * g.dims[1] + y) * g.dims[0];
-                int s = cell_start[cb + x0], e = cell_start[cb + x1 + 1];
-                for (int q0 = s; q0 < e; q0 += 32) {
-                    int q = q0 + lane;
-                    bool hit = q < e && within<D, SQRT>(qx, qy, qz, xs, n, q, rc);
-                    unsigned m = __ballot_sync(0xffffffffu, hit);
-                    if (FILL && hit) col_idx[base + cnt + __popc(m & lt)] = q;
-                    cnt += __popc(m);
+    for (ll p0 = warp * 32; p0 < n; p0 += nwarps * 32) {
+        ll p = p0 + lane;
+        int cid = p < n ? cell_sorted[p] : -1;
+        unsigned todo = __ballot_sync(full, p < n);
+        while (todo) {
+            const int a = __ffs(todo) - 1;  // first lane of the next group
+            const int c = __shfl_sync(full, cid, a);
+            const unsigned grp = __ballot_sync(full, cid == c) & todo;
+            todo &= ~grp;
+            const int gsz = __popc(grp);
+            const int lg = gsz <= 1 ? 0 : 32 - __clz(gsz - 1);
+            const int gp = 1 << lg, k = 32 >> lg;
+            const int jq = lane & (gp - 1), sub = lane >> lg;
+            const bool qvalid = jq < gsz;
+            const ll pq = p0 + a + (qvalid ? jq : 0);
+            const double qx = xs[pq], qy = D > 1 ? xs[n + pq] : 0.0, qz = D > 2 ? xs[2 * n + pq] : 0.0;
+            const unsigned qm = c_rep[lg] << jq;
+            const ll base = MODE ? row_ptr[pq] : 0;
+            const int cx = c % g.dims[0];
+            const int t = c / g.dims[0];
+            const int cy = t % g.dims[1];
+            const int cz = t / g.dims[1];
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
+            const int y0 = D > 1 ? max(cy - 1, 0) : 0, y1 = D > 1 ? min(cy + 1, g.dims[1] - 1) : 0;
+            const int z0 = D > 2 ? max(cz - 1, 0) : 0, z1 = D > 2 ? min(cz + 1, g.dims[2] - 1) : 0;
+            int cnt = 0;
+            for (int z = z0; z <= z1; ++z)
+                for (int y = y0; y <= y1; ++y) {
+                    const int cb = (z * g.dims[1] + y) * g.dims[0];
+                    const int s = cell_start[cb + x0], e = cell_start[cb + x1 + 1];
+#pragma unroll 4
+                    for (int q0 = s; q0 < e; q0 += k) {
+                        const int q = q0 + sub;
+                        const bool inb = q < e;
+                        // branch-free: out-of-range lanes re-test entry s (always valid here) and are masked
+                        const bool hit = within<D, SQRT>(qx, qy, qz, xs, n, inb ? q : s, rc) && inb && qvalid;
+                        if (MODE) {
+                            const unsigned m = __ballot_sync(full, hit) & qm;
+                            if (hit) col_idx[base + cnt + __popc(m & lt)] = q;
+                            cnt += __popc(m);
+                        } else {
+                            cnt += hit ? 1 : 0;
+                        }
+                    }
                 }
-            }
-        if (!FILL && lane == 0) deg[p] = cnt;
+            if (MODE == 0)
+                for (int off = gp; off < 32; off <<= 1) cnt += __shfl_xor_sync(full, cnt, off);
+            if (MODE != 1 && sub == 0 && qvalid) deg[pq] = cnt;
+        }
+    }
+}
+
+// cap[p] = size of the candidate list of point p (all points of the 3^D cells around its cell)
+template <int D>
+__global__ void grid_cap_kernel(ll n, const int *__restrict__ cell_sorted, const int *__restrict__ cell_start,
+                                GridDesc g, int *__restrict__ cap) {
+    ll p = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (p > n) return;
+    if (p == n) { cap[n] = 0; return; }
+    const int c = cell_sorted[p];
+    const int cx = c % g.dims[0];
+    const int t = c / g.dims[0];
+    const int cy = t % g.dims[1];
+    const int cz = t / g.dims[1];
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
+    const int y0 = D > 1 ? max(cy - 1, 0) : 0, y1 = D > 1 ? min(cy + 1, g.dims[1] - 1) : 0;
+    const int z0 = D > 2 ? max(cz - 1, 0) : 0, z1 = D > 2 ? min(cz + 1, g.dims[2] - 1) : 0;
+    int tot = 0;
+    for (int z = z0; z <= z1; ++z)
+        for (int y = y0; y <= y1; ++y) {
+            const int cb = (z * g.dims[1] + y) * g.dims[0];
+            tot += cell_start[cb + x1 + 1] - cell_start[cb + x0];
+        }
+    cap[p] = tot;
+}
+
+// one warp per row: gapped[goff[p] .. +deg[p]) -> col_idx[row_ptr[p] .. +deg[p])
+__global__ void __launch_bounds__(256)
+compact_rows_kernel(const int *__restrict__ gapped, const ll *__restrict__ goff, const ll *__restrict__ row_ptr,
+                    ll n, int *__restrict__ col_idx) {
+    const int lane = threadIdx.x & 31;
+    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    for (ll p = warp; p < n; p += nwarps) {
+        const ll src = goff[p], dst = row_ptr[p];
+        const int m = (int)(row_ptr[p + 1] - dst);
+        for (int k = lane; k < m; k += 32) col_idx[dst + k] = gapped[src + k];
     }
 }
 
@@ -167,34 +247,45 @@ int cnn_scan_deg_to_row_ptr(cnnb200_ctx *ctx, const int32_t *deg, ll n, ll *row_
 }
 
 template <int D, bool SQRT>
-static int launch_rows(cnnb200_ctx *ctx, ll n, const GridDesc &g, double rc, bool fill) {
+static int launch_rows(cnnb200_ctx *ctx, ll n, const GridDesc &g, double rc, int mode, const ll *offsets, int *out) {
     const double *xs = ctx->b_xs.as<double>();
     const int *cs = ctx->b_cell_id_sorted.as<int>();
     const int *cstart = ctx->b_cell_start.as<int>();
-    int blocks = (int)((n + 7) / 8);
+    int blocks = (int)((n + 255) / 256);  // one warp per tile of 32 points, 8 warps per CTA
     int cap = ctx->sm_count * 64;
     if (blocks > cap) blocks = cap;
-    if (!fill)
-        grid_rows_kernel<D, SQRT, false><<<blocks, 256, 0, ctx->stream>>>(
-            xs, n, cs, cstart, g, rc, ctx->b_deg.as<int>(), nullptr, nullptr);
+    int *deg = ctx->b_deg.as<int>();
+    if (mode == 0)
+        grid_rows_kernel<D, SQRT, 0><<<blocks, 256, 0, ctx->stream>>>(xs, n, cs, cstart, g, rc, deg, nullptr, nullptr);
+    else if (mode == 1)
+        grid_rows_kernel<D, SQRT, 1><<<blocks, 256, 0, ctx->stream>>>(xs, n, cs, cstart, g, rc, nullptr, offsets, out);
     else
-        grid_rows_kernel<D, SQRT, true><<<blocks, 256, 0, ctx->stream>>>(
-            xs, n, cs, cstart, g, rc, nullptr, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
+        grid_rows_kernel<D, SQRT, 2><<<blocks, 256, 0, ctx->stream>>>(xs, n, cs, cstart, g, rc, deg, offsets, out);
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     return CNNB200_OK;
 }
 
-static int launch_rows_any(cnnb200_ctx *ctx, ll n, const GridDesc &g, double rc, int metric, bool fill) {
+static int launch_rows_any(cnnb200_ctx *ctx, ll n, const GridDesc &g, double rc, int metric, int mode,
+                           const ll *offsets, int *out) {
     bool sq = metric == CNNB200_METRIC_EUCLIDEAN;
     switch (g.d * 2 + (sq ? 1 : 0)) {
-        case 2: return launch_rows<1, false>(ctx, n, g, rc, fill);
-        case 3: return launch_rows<1, true>(ctx, n, g, rc, fill);
-        case 4: return launch_rows<2, false>(ctx, n, g, rc, fill);
-        case 5: return launch_rows<2, true>(ctx, n, g, rc, fill);
-        case 6: return launch_rows<3, false>(ctx, n, g, rc, fill);
-        default: return launch_rows<3, true>(ctx, n, g, rc, fill);
+        case 2: return launch_rows<1, false>(ctx, n, g, rc, mode, offsets, out);
+        case 3: return launch_rows<1, true>(ctx, n, g, rc, mode, offsets, out);
+        case 4: return launch_rows<2, false>(ctx, n, g, rc, mode, offsets, out);
+        case 5: return launch_rows<2, true>(ctx, n, g, rc, mode, offsets, out);
+        case 6: return launch_rows<3, false>(ctx, n, g, rc, mode, offsets, out);
+        default: return launch_rows<3, true>(ctx, n, g, rc, mode, offsets, out);
     }
+}
+
+static int scan_int_to_ll(cnnb200_ctx *ctx, const int *in, ll *out, ll count) {
+    size_t need = 0;
+    CNN_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, need, in, out, ::cuda::std::plus<>{}, (ll)0, (int)count, ctx->stream));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
+    size_t cap = ctx->b_cub.cap;
+    CNN_CUDA(cub::DeviceScan::ExclusiveScan(ctx->b_cub.p, cap, in, out, ::cuda::std::plus<>{}, (ll)0, (int)count, ctx->stream));
+    return CNNB200_OK;
 }
 
 int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric) {
@@ -247,7 +338,7 @@ int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radi
     ll ncell = (ll)g.dims[0] * g.dims[1] * g.dims[2];
 
     // --- K1: cell ids, sort by cell, cell starts, gather --------------------------------------
-    CNN_TRY(cnn_ensure(ctx, ctx->b_cell_id, sizeof(int) * (size_t)n));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_cell_id, sizeof(int) * (size_t)(n + 1)));
     CNN_TRY(cnn_ensure(ctx, ctx->b_cell_id_sorted, sizeof(int) * (size_t)n));
     CNN_TRY(cnn_ensure(ctx, ctx->b_idx, sizeof(int) * (size_t)n));
     CNN_TRY(cnn_ensure(ctx, ctx->b_perm, sizeof(int) * (size_t)n));
@@ -284,18 +375,57 @@ int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radi
     CNN_KERNEL_CHECK();
     sp_build.reset();
 
-    // --- K2: count, scan, fill ------------------------------------------------------------------
+    // --- K2: single pass into a gapped buffer + compaction, or count / scan / fill -----------------
     CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>() + n, 0, sizeof(int), st));
-    {
-        Span sp(ctx, T_SEARCH_COUNT);
-        CNN_TRY(launch_rows_any(ctx, n, g, radius_cutoff, metric, false));
-    }
     ll nnz = 0, max_deg = 0;
-    CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
-    CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
-    {
-        Span sp(ctx, T_SEARCH_FILL);
-        CNN_TRY(launch_rows_any(ctx, n, g, radius_cutoff, metric, true));
+    ll gapped_total = -1;
+    if (ctx->single_pass_limit > 0) {
+        // candidate-list sizes -> offsets of the gapped rows
+        Span sp(ctx, T_SCAN);
+        CNN_TRY(cnn_ensure(ctx, ctx->b_tmp1, sizeof(ll) * (size_t)(n + 1)));
+        // the cell ids in input order are dead after the sort: reuse that buffer for cap[] (n+1 ints)
+        int *cap = ctx->b_cell_id.as<int>();
+        int nb1 = cnn_blocks(n + 1, 256);
+        if (d == 1) grid_cap_kernel<1><<<nb1, 256, 0, st>>>(n, ctx->b_cell_id_sorted.as<int>(), ctx->b_cell_start.as<int>(), g, cap);
+        else if (d == 2) grid_cap_kernel<2><<<nb1, 256, 0, st>>>(n, ctx->b_cell_id_sorted.as<int>(), ctx->b_cell_start.as<int>(), g, cap);
+        else grid_cap_kernel<3><<<nb1, 256, 0, st>>>(n, ctx->b_cell_id_sorted.as<int>(), ctx->b_cell_start.as<int>(), g, cap);
+        CNN_LAUNCHED(ctx, 1);
+        CNN_KERNEL_CHECK();
+        CNN_TRY(scan_int_to_ll(ctx, cap, ctx->b_tmp1.as<ll>(), n + 1));
+        ll *h;
+        CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
+        CNN_CUDA(cudaMemcpyAsync(h, ctx->b_tmp1.as<ll>() + n, sizeof(ll), cudaMemcpyDeviceToHost, st));
+        CNN_CUDA(cudaStreamSynchronize(st));
+        gapped_total = h[0];
+    }
+    if (gapped_total >= 0 && gapped_total * 4 <= ctx->single_pass_limit) {
+        CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(int) * (size_t)gapped_total));
+        {
+            Span sp(ctx, T_SEARCH_COUNT);
+            CNN_TRY(launch_rows_any(ctx, n, g, radius_cutoff, metric, 2, ctx->b_tmp1.as<ll>(), ctx->b_tmp0.as<int>()));
+        }
+        CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
+        {
+            Span sp(ctx, T_SEARCH_FILL);
+            int blocks = (int)((n + 7) / 8);
+            if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+            compact_rows_kernel<<<blocks, 256, 0, st>>>(ctx->b_tmp0.as<int>(), ctx->b_tmp1.as<ll>(), ctx->b_row_ptr.as<ll>(),
+                                                       n, ctx->b_col_idx.as<int>());
+            CNN_LAUNCHED(ctx, 1);
+            CNN_KERNEL_CHECK();
+        }
+    } else {
+        {
+            Span sp(ctx, T_SEARCH_COUNT);
+            CNN_TRY(launch_rows_any(ctx, n, g, radius_cutoff, metric, 0, nullptr, nullptr));
+        }
+        CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
+        {
+            Span sp(ctx, T_SEARCH_FILL);
+            CNN_TRY(launch_rows_any(ctx, n, g, radius_cutoff, metric, 1, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>()));
+        }
     }
 
     ctx->n = n;

@@ -27,8 +27,14 @@ __global__ void fill_int_kernel(int *a, ll n, int v) {
 __global__ void minorig_kernel(const int *__restrict__ parent, const uint8_t *__restrict__ core,
                                const int *__restrict__ perm, ll n, int *minorig) {
     ll p = blockIdx.x * (ll)blockDim.x + threadIdx.x;
-    if (p >= n || !core[p]) return;
-    atomicMin(minorig + parent[p], perm[p]);
+    bool active = p < n && core[p];
+    unsigned am = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    // one atomic per distinct root per warp (a giant cluster would otherwise serialise on one address)
+    int r = parent[p];
+    unsigned peers = __match_any_sync(am, r);
+    int mn = __reduce_min_sync(peers, perm[p]);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicMin(minorig + r, mn);
 }
 
 // flags[min caller index of each component] = 1

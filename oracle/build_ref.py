@@ -12,8 +12,9 @@ no reference source into the repository:
   ``cython`` compiler into ``oracle/_ref/build/<mod>.cpp`` and compiled with ``g++``
   into ``oracle/_ref/cnnclustering/<mod>.<abi>.so``;
 * the three pure-Python modules the extension modules import at run time
-  (``__init__``, ``recipes``, ``report``) are byte-compiled into sourceless
-  ``.pyc`` files next to the ``.so`` files.
+  (``__init__``, ``recipes``, ``report``) are compiled to code objects and stored as
+  marshalled ``.code`` files next to the ``.so`` files (``.pyc`` files do not travel to the GPU
+  box); ``oracle/ref.py`` loads them.
 
 ``oracle/_ref/`` is git-ignored (build output only) but travels to the GPU box.
 
@@ -25,7 +26,8 @@ exception check is emitted for ``cdef ... nogil`` functions; Cython 3 emits both
 otherwise, which makes the as-shipped build ~8x slower than the published timings.
 """
 import os
-import py_compile
+import marshal
+import shutil
 import subprocess
 import sys
 import sysconfig
@@ -60,7 +62,7 @@ def available() -> bool:
 def built() -> bool:
     suffix = sysconfig.get_config_var("EXT_SUFFIX")
     return all(os.path.exists(os.path.join(PKG, m + suffix)) for m in MODULES) and all(
-        os.path.exists(os.path.join(PKG, p + ".pyc")) for p in PURE
+        os.path.exists(os.path.join(PKG, p + ".code")) for p in PURE
     )
 
 
@@ -100,11 +102,12 @@ def build(force: bool = False) -> bool:
     with ThreadPoolExecutor(max_workers=len(MODULES)) as ex:
         list(ex.map(_build_one, MODULES))
     for p in PURE:
-        py_compile.compile(
-            os.path.join(REF_SRC, "cnnclustering", p + ".py"),
-            cfile=os.path.join(PKG, p + ".pyc"),
-            doraise=True,
-        )
+        src = os.path.join(REF_SRC, "cnnclustering", p + ".py")
+        with open(src) as fp:
+            code = compile(fp.read(), f"<reference>/cnnclustering/{p}.py", "exec")
+        with open(os.path.join(PKG, p + ".code"), "wb") as fp:
+            marshal.dump(code, fp)
+    shutil.rmtree(BUILD, ignore_errors=True)  # generated C++ is not needed once the modules are linked
     return built()
 
 

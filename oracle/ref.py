@@ -27,11 +27,32 @@ def module():
     """The reference's ``cnnclustering.cluster`` module."""
     global _cluster
     if _cluster is None:
-        if REF_DIR not in sys.path:
-            sys.path.insert(0, REF_DIR)
+        import importlib
+        import marshal
+        import types
+
+        pkg_dir = os.path.join(REF_DIR, "cnnclustering")
+
+        def load_pure(name, fullname, is_pkg=False):
+            mod = types.ModuleType(fullname)
+            mod.__file__ = os.path.join(pkg_dir, name + ".code")
+            if is_pkg:
+                mod.__path__ = [pkg_dir]
+                mod.__package__ = fullname
+            else:
+                mod.__package__ = fullname.rpartition(".")[0]
+            sys.modules[fullname] = mod
+            with open(mod.__file__, "rb") as fp:
+                exec(marshal.load(fp), mod.__dict__)
+            return mod
+
         with contextlib.redirect_stdout(io.StringIO()):  # "Optional dependency ... matplotlib"
-            from cnnclustering import cluster
-        _cluster = cluster
+            # the pure-Python parts of the reference travel as marshalled code objects (build_ref.py);
+            # the extension modules are found through the package's __path__ as usual
+            pkg = load_pure("__init__", "cnnclustering", is_pkg=True)
+            pkg.report = load_pure("report", "cnnclustering.report")
+            pkg.recipes = load_pure("recipes", "cnnclustering.recipes")
+            _cluster = importlib.import_module("cnnclustering.cluster")
     return _cluster
 
 

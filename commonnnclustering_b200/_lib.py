@@ -30,6 +30,11 @@ SIGNATURES = {
     "cnnb200_ctx_synchronize": [_P],
     "cnnb200_ctx_release": [_P],
     "cnnb200_neighbours_from_points": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int, C.c_int, C.POINTER(_I64)],
+    "cnnb200_grid_begin": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int],
+    "cnnb200_grid_balance": [_P, C.c_int, _P],
+    "cnnb200_grid_degrees": [_P, _I64, _I64, _P],
+    "cnnb200_grid_fill": [_P, _I64, _I64, _P, _P],
+    "cnnb200_neighbours_adopt": [_P, _P, _P, _I64, _I64, _I64, C.c_int],
     "cnnb200_neighbours_from_csr": [_P, _P, _P, C.c_int, C.c_int, C.c_int, _I64, _I64],
     "cnnb200_neighbours_from_padded": [_P, _P, _P, C.c_int, _I64, _I64],
     "cnnb200_neighbours_info": [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)],
@@ -148,8 +153,13 @@ class Context:
             except Exception:
                 return None
 
+        delete = torch.cuda.caching_allocator_delete  # bound now: module globals vanish at shutdown
+
         def _free(ptr, _user):
-            torch.cuda.caching_allocator_delete(ptr)
+            try:
+                delete(ptr)
+            except Exception:
+                pass
 
         a, f = ALLOC_FN(_alloc), FREE_FN(_free)
         self._keep = [a, f]
@@ -169,6 +179,36 @@ class Context:
         check(self._lib.cnnb200_neighbours_from_points(
             self._h, p, loc, n, d, float(radius_cutoff), METRIC_IDS[metric], METHOD_IDS[method], C.byref(nnz)))
         return nnz.value
+
+    # -- row-sharded construction (multi-GPU building blocks) ------------------------------------
+    def grid_begin(self, x, radius_cutoff, metric="euclidean_r"):
+        p, loc = _ptr_loc(x)
+        n, d = x.shape
+        check(self._lib.cnnb200_grid_begin(self._h, p, loc, n, d, float(radius_cutoff), METRIC_IDS[metric]))
+
+    def grid_balance(self, parts: int):
+        b = np.zeros(parts + 1, dtype=np.int64)
+        check(self._lib.cnnb200_grid_balance(self._h, int(parts), b.ctypes.data))
+        return b
+
+    def grid_degrees(self, row_begin, row_end, deg):
+        p, loc = _ptr_loc(deg)
+        assert loc == DEVICE
+        check(self._lib.cnnb200_grid_degrees(self._h, int(row_begin), int(row_end), p))
+
+    def grid_fill(self, row_begin, row_end, row_ptr, col_idx):
+        rp, loc = _ptr_loc(row_ptr)
+        cp, loc2 = _ptr_loc(col_idx)
+        assert loc == DEVICE and loc2 == DEVICE
+        check(self._lib.cnnb200_grid_fill(self._h, int(row_begin), int(row_end), rp, cp))
+
+    def neighbours_adopt(self, row_ptr, col_idx, max_deg, grid_perm):
+        rp, loc = _ptr_loc(row_ptr)
+        cp, loc2 = _ptr_loc(col_idx)
+        assert loc == DEVICE and loc2 == DEVICE
+        self._borrowed = (row_ptr, col_idx)
+        check(self._lib.cnnb200_neighbours_adopt(self._h, rp, cp, row_ptr.shape[0] - 1, col_idx.shape[0],
+                                                 int(max_deg), int(bool(grid_perm))))
 
     def neighbours_from_csr(self, row_ptr, col_idx, borrow=False):
         rp, loc = _ptr_loc(row_ptr)

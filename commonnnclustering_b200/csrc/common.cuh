@@ -34,6 +34,13 @@ void cnn_set_error(const char *fmt, ...);
         return (code);             \
     } while (0)
 
+struct GridDesc {
+    double lo[3];
+    double h;
+    int dims[3];
+    int d;
+};
+
 // A growable device scratch buffer owned by the context.
 struct Buf {
     void *p = nullptr;
@@ -88,6 +95,16 @@ struct cnnb200_ctx {
     const int32_t *col_idx = nullptr;  // [nnz]
     const int32_t *perm = nullptr;     // [n] internal -> caller index; nullptr = identity
     Buf b_row_ptr, b_col_idx, b_perm, b_deg;
+
+    // ---- uniform grid of the last cnn_grid_build + the row block being searched ---------------
+    bool have_grid = false;
+    GridDesc grid;
+    ll grid_n = 0;
+    double grid_rc = 0;
+    int grid_metric = 0;
+    ll blk_begin = 0, blk_end = 0, blk_goff0 = 0;
+    bool blk_single = false;
+    Buf b_cell_count;
 
     // ---- neighbour search scratch ------------------------------------------------------
     Buf b_x;         // f64 [n, d] as given by the caller (device copy)
@@ -154,6 +171,9 @@ static inline int cnn_blocks(ll work_items, int per_block) {
 }
 
 // --- stage entry points implemented across the .cu files ----------------------------------
+int cnn_grid_build(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric);
+int cnn_grid_rows(cnnb200_ctx *ctx, ll pb, ll pe, int *deg);
+int cnn_grid_fill(cnnb200_ctx *ctx, ll pb, ll pe, const ll *row_ptr, int *col_idx);
 int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric);
 int cnn_dense_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric,
                      int method);

@@ -16,12 +16,6 @@
 
 #include "common.cuh"
 
-struct GridDesc {
-    double lo[3];
-    double h;
-    int dims[3];
-    int d;
-};
 
 // ---- bounding box -------------------------------------------------------------------------
 __global__ void bbox_partial_kernel(const double *__restrict__ x, ll n, int d, double *partial) {
@@ -124,16 +118,16 @@ template <int D, bool SQRT, int MODE>
 __global__ void __launch_bounds__(256)
 grid_rows_kernel(const double *__restrict__ xs, ll n, const int *__restrict__ cell_sorted,
                  const int *__restrict__ cell_start, GridDesc g, double rc, int *__restrict__ deg,
-                 const ll *__restrict__ row_ptr, int *__restrict__ col_idx) {
+                 const ll *__restrict__ row_ptr, int *__restrict__ col_idx, ll p_begin, ll p_end) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
-    for (ll p0 = warp * 32; p0 < n; p0 += nwarps * 32) {
+    for (ll p0 = p_begin + warp * 32; p0 < p_end; p0 += nwarps * 32) {
         ll p = p0 + lane;
-        int cid = p < n ? cell_sorted[p] : -1;
-        unsigned todo = __ballot_sync(full, p < n);
+        int cid = p < p_end ? cell_sorted[p] : -1;
+        unsigned todo = __ballot_sync(full, p < p_end);
         while (todo) {
             const int a = __ffs(todo) - 1;  // first lane of the next group
             const int c = __shfl_sync(full, cid, a);
@@ -209,11 +203,11 @@ __global__ void grid_cap_kernel(ll n, const int *__restrict__ cell_sorted, const
 // one warp per row: gapped[goff[p] .. +deg[p]) -> col_idx[row_ptr[p] .. +deg[p])
 __global__ void __launch_bounds__(256)
 compact_rows_kernel(const int *__restrict__ gapped, const ll *__restrict__ goff, const ll *__restrict__ row_ptr,
-                    ll n, int *__restrict__ col_idx) {
+                    ll p_begin, ll p_end, int *__restrict__ col_idx) {
     const int lane = threadIdx.x & 31;
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
-    for (ll p = warp; p < n; p += nwarps) {
+    for (ll p = p_begin + warp; p < p_end; p += nwarps) {
         const ll src = goff[p], dst = row_ptr[p];
         const int m = (int)(row_ptr[p + 1] - dst);
         for (int k = lane; k < m; k += 32) col_idx[dst + k] = gapped[src + k];
@@ -247,35 +241,37 @@ int cnn_scan_deg_to_row_ptr(cnnb200_ctx *ctx, const int32_t *deg, ll n, ll *row_
 }
 
 template <int D, bool SQRT>
-static int launch_rows(cnnb200_ctx *ctx, ll n, const GridDesc &g, double rc, int mode, const ll *offsets, int *out) {
+static int launch_rows(cnnb200_ctx *ctx, ll pb, ll pe, int mode, int *deg, const ll *offsets, int *out) {
+    const GridDesc &g = ctx->grid;
+    const ll n = ctx->grid_n;
+    const double rc = ctx->grid_rc;
     const double *xs = ctx->b_xs.as<double>();
     const int *cs = ctx->b_cell_id_sorted.as<int>();
     const int *cstart = ctx->b_cell_start.as<int>();
-    int blocks = (int)((n + 255) / 256);  // one warp per tile of 32 points, 8 warps per CTA
+    int blocks = (int)((pe - pb + 255) / 256);  // one warp per tile of 32 points, 8 warps per CTA
     int cap = ctx->sm_count * 64;
     if (blocks > cap) blocks = cap;
-    int *deg = ctx->b_deg.as<int>();
+    if (blocks < 1) blocks = 1;
     if (mode == 0)
-        grid_rows_kernel<D, SQRT, 0><<<blocks, 256, 0, ctx->stream>>>(xs, n, cs, cstart, g, rc, deg, nullptr, nullptr);
+        grid_rows_kernel<D, SQRT, 0><<<blocks, 256, 0, ctx->stream>>>(xs, n, cs, cstart, g, rc, deg, nullptr, nullptr, pb, pe);
     else if (mode == 1)
-        grid_rows_kernel<D, SQRT, 1><<<blocks, 256, 0, ctx->stream>>>(xs, n, cs, cstart, g, rc, nullptr, offsets, out);
+        grid_rows_kernel<D, SQRT, 1><<<blocks, 256, 0, ctx->stream>>>(xs, n, cs, cstart, g, rc, nullptr, offsets, out, pb, pe);
     else
-        grid_rows_kernel<D, SQRT, 2><<<blocks, 256, 0, ctx->stream>>>(xs, n, cs, cstart, g, rc, deg, offsets, out);
+        grid_rows_kernel<D, SQRT, 2><<<blocks, 256, 0, ctx->stream>>>(xs, n, cs, cstart, g, rc, deg, offsets, out, pb, pe);
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     return CNNB200_OK;
 }
 
-static int launch_rows_any(cnnb200_ctx *ctx, ll n, const GridDesc &g, double rc, int metric, int mode,
-                           const ll *offsets, int *out) {
-    bool sq = metric == CNNB200_METRIC_EUCLIDEAN;
-    switch (g.d * 2 + (sq ? 1 : 0)) {
-        case 2: return launch_rows<1, false>(ctx, n, g, rc, mode, offsets, out);
-        case 3: return launch_rows<1, true>(ctx, n, g, rc, mode, offsets, out);
-        case 4: return launch_rows<2, false>(ctx, n, g, rc, mode, offsets, out);
-        case 5: return launch_rows<2, true>(ctx, n, g, rc, mode, offsets, out);
-        case 6: return launch_rows<3, false>(ctx, n, g, rc, mode, offsets, out);
-        default: return launch_rows<3, true>(ctx, n, g, rc, mode, offsets, out);
+static int launch_rows_any(cnnb200_ctx *ctx, ll pb, ll pe, int mode, int *deg, const ll *offsets, int *out) {
+    bool sq = ctx->grid_metric == CNNB200_METRIC_EUCLIDEAN;
+    switch (ctx->grid.d * 2 + (sq ? 1 : 0)) {
+        case 2: return launch_rows<1, false>(ctx, pb, pe, mode, deg, offsets, out);
+        case 3: return launch_rows<1, true>(ctx, pb, pe, mode, deg, offsets, out);
+        case 4: return launch_rows<2, false>(ctx, pb, pe, mode, deg, offsets, out);
+        case 5: return launch_rows<2, true>(ctx, pb, pe, mode, deg, offsets, out);
+        case 6: return launch_rows<3, false>(ctx, pb, pe, mode, deg, offsets, out);
+        default: return launch_rows<3, true>(ctx, pb, pe, mode, deg, offsets, out);
     }
 }
 
@@ -288,9 +284,11 @@ static int scan_int_to_ll(cnnb200_ctx *ctx, const int *in, ll *out, ll count) {
     return CNNB200_OK;
 }
 
-int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric) {
+// ---- K1: grid geometry, sort by cell, candidate-list prefix --------------------------------------
+int cnn_grid_build(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric) {
     cudaStream_t st = ctx->stream;
-    std::unique_ptr<Span> sp_build(new Span(ctx, T_GRID_BUILD));
+    ctx->have_grid = false;
+    Span sp_build(ctx, T_GRID_BUILD);
     // --- bounding box --------------------------------------------------------------------
     int rb = ctx->sm_count * 2;
     if (rb > (int)((n + 255) / 256)) rb = (int)((n + 255) / 256);
@@ -337,17 +335,16 @@ int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radi
     }
     ll ncell = (ll)g.dims[0] * g.dims[1] * g.dims[2];
 
-    // --- K1: cell ids, sort by cell, cell starts, gather --------------------------------------
+    // --- cell ids, sort by cell, cell starts, gather ------------------------------------------
     CNN_TRY(cnn_ensure(ctx, ctx->b_cell_id, sizeof(int) * (size_t)(n + 1)));
     CNN_TRY(cnn_ensure(ctx, ctx->b_cell_id_sorted, sizeof(int) * (size_t)n));
     CNN_TRY(cnn_ensure(ctx, ctx->b_idx, sizeof(int) * (size_t)n));
     CNN_TRY(cnn_ensure(ctx, ctx->b_perm, sizeof(int) * (size_t)n));
     CNN_TRY(cnn_ensure(ctx, ctx->b_cell_start, sizeof(int) * (size_t)(ncell + 2)));
-    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(int) * (size_t)(ncell + 2)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_cell_count, sizeof(int) * (size_t)(ncell + 2)));
     CNN_TRY(cnn_ensure(ctx, ctx->b_xs, sizeof(double) * (size_t)n * (size_t)d));
-    CNN_TRY(cnn_ensure(ctx, ctx->b_deg, sizeof(int) * (size_t)(n + 1)));
-    CNN_TRY(cnn_ensure(ctx, ctx->b_row_ptr, sizeof(ll) * (size_t)(n + 1)));
-    int *cell_count = ctx->b_tmp0.as<int>();
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp1, sizeof(ll) * (size_t)(n + 1)));
+    int *cell_count = ctx->b_cell_count.as<int>();
     CNN_CUDA(cudaMemsetAsync(cell_count, 0, sizeof(int) * (size_t)(ncell + 1), st));
     cell_id_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_x, n, g, ctx->b_cell_id.as<int>(),
                                                          ctx->b_idx.as<int>(), cell_count);
@@ -372,67 +369,177 @@ int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radi
     gather_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_x, ctx->b_perm.as<int>(), n, (int)d,
                                                         ctx->b_xs.as<double>());
     CNN_LAUNCHED(ctx, 1);
+    // candidate-list sizes (the cell ids in input order are dead after the sort: reuse that buffer)
+    // and their prefix = offsets of the gapped rows / the work measure used to balance row blocks
+    int *capv = ctx->b_cell_id.as<int>();
+    int nb1 = cnn_blocks(n + 1, 256);
+    const int *cs = ctx->b_cell_id_sorted.as<int>(), *cst = ctx->b_cell_start.as<int>();
+    if (d == 1) grid_cap_kernel<1><<<nb1, 256, 0, st>>>(n, cs, cst, g, capv);
+    else if (d == 2) grid_cap_kernel<2><<<nb1, 256, 0, st>>>(n, cs, cst, g, capv);
+    else grid_cap_kernel<3><<<nb1, 256, 0, st>>>(n, cs, cst, g, capv);
+    CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
-    sp_build.reset();
+    CNN_TRY(scan_int_to_ll(ctx, capv, ctx->b_tmp1.as<ll>(), n + 1));
+    ctx->grid = g;
+    ctx->grid_n = n;
+    ctx->grid_rc = radius_cutoff;
+    ctx->grid_metric = metric;
+    ctx->have_grid = true;
+    ctx->perm = ctx->b_perm.as<int>();
+    return CNNB200_OK;
+}
 
-    // --- K2: single pass into a gapped buffer + compaction, or count / scan / fill -----------------
-    CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>() + n, 0, sizeof(int), st));
-    ll nnz = 0, max_deg = 0;
-    ll gapped_total = -1;
-    if (ctx->single_pass_limit > 0) {
-        // candidate-list sizes -> offsets of the gapped rows
-        Span sp(ctx, T_SCAN);
-        CNN_TRY(cnn_ensure(ctx, ctx->b_tmp1, sizeof(ll) * (size_t)(n + 1)));
-        // the cell ids in input order are dead after the sort: reuse that buffer for cap[] (n+1 ints)
-        int *cap = ctx->b_cell_id.as<int>();
-        int nb1 = cnn_blocks(n + 1, 256);
-        if (d == 1) grid_cap_kernel<1><<<nb1, 256, 0, st>>>(n, ctx->b_cell_id_sorted.as<int>(), ctx->b_cell_start.as<int>(), g, cap);
-        else if (d == 2) grid_cap_kernel<2><<<nb1, 256, 0, st>>>(n, ctx->b_cell_id_sorted.as<int>(), ctx->b_cell_start.as<int>(), g, cap);
-        else grid_cap_kernel<3><<<nb1, 256, 0, st>>>(n, ctx->b_cell_id_sorted.as<int>(), ctx->b_cell_start.as<int>(), g, cap);
+// ---- K2 on a row block [pb, pe) of the cell-sorted points: degrees (and, single pass, the hits) -------
+int cnn_grid_rows(cnnb200_ctx *ctx, ll pb, ll pe, int *deg) {
+    cudaStream_t st = ctx->stream;
+    ll *h;
+    CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
+    const ll *goff = ctx->b_tmp1.as<ll>();
+    CNN_CUDA(cudaMemcpyAsync(h, goff + pb, sizeof(ll), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaMemcpyAsync(h + 1, goff + pe, sizeof(ll), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaStreamSynchronize(st));
+    const ll g0 = h[0], gapped = h[1] - h[0];
+    ctx->blk_begin = pb;
+    ctx->blk_end = pe;
+    ctx->blk_goff0 = g0;
+    ctx->blk_single = ctx->single_pass_limit > 0 && gapped * 4 <= ctx->single_pass_limit;
+    ctx->stats[ST_DIST] = gapped;
+    Span sp(ctx, T_SEARCH_COUNT);
+    if (ctx->blk_single) {
+        CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(int) * (size_t)gapped));
+        // row p writes at gapped[goff[p] - g0 ...]: shift the base pointer instead of the offsets
+        CNN_TRY(launch_rows_any(ctx, pb, pe, 2, deg, goff, ctx->b_tmp0.as<int>() - g0));
+    } else {
+        CNN_TRY(launch_rows_any(ctx, pb, pe, 0, deg, nullptr, nullptr));
+    }
+    return CNNB200_OK;
+}
+
+// ---- K2 fill of the same row block into a CSR whose row_ptr covers all rows ----------------------------
+int cnn_grid_fill(cnnb200_ctx *ctx, ll pb, ll pe, const ll *row_ptr, int *col_idx) {
+    if (pb != ctx->blk_begin || pe != ctx->blk_end)
+        CNN_FAIL(CNNB200_E_STATE, "grid fill: row block differs from the one the degrees were computed for");
+    Span sp(ctx, T_SEARCH_FILL);
+    if (ctx->blk_single) {
+        int blocks = (int)((pe - pb + 7) / 8);
+        if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+        if (blocks < 1) blocks = 1;
+        compact_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->b_tmp0.as<int>() - ctx->blk_goff0, ctx->b_tmp1.as<ll>(),
+                                                            row_ptr, pb, pe, col_idx);
         CNN_LAUNCHED(ctx, 1);
         CNN_KERNEL_CHECK();
-        CNN_TRY(scan_int_to_ll(ctx, cap, ctx->b_tmp1.as<ll>(), n + 1));
-        ll *h;
-        CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
-        CNN_CUDA(cudaMemcpyAsync(h, ctx->b_tmp1.as<ll>() + n, sizeof(ll), cudaMemcpyDeviceToHost, st));
-        CNN_CUDA(cudaStreamSynchronize(st));
-        gapped_total = h[0];
-    }
-    if (gapped_total >= 0 && gapped_total * 4 <= ctx->single_pass_limit) {
-        CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(int) * (size_t)gapped_total));
-        {
-            Span sp(ctx, T_SEARCH_COUNT);
-            CNN_TRY(launch_rows_any(ctx, n, g, radius_cutoff, metric, 2, ctx->b_tmp1.as<ll>(), ctx->b_tmp0.as<int>()));
-        }
-        CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
-        CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
-        {
-            Span sp(ctx, T_SEARCH_FILL);
-            int blocks = (int)((n + 7) / 8);
-            if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-            compact_rows_kernel<<<blocks, 256, 0, st>>>(ctx->b_tmp0.as<int>(), ctx->b_tmp1.as<ll>(), ctx->b_row_ptr.as<ll>(),
-                                                       n, ctx->b_col_idx.as<int>());
-            CNN_LAUNCHED(ctx, 1);
-            CNN_KERNEL_CHECK();
-        }
     } else {
-        {
-            Span sp(ctx, T_SEARCH_COUNT);
-            CNN_TRY(launch_rows_any(ctx, n, g, radius_cutoff, metric, 0, nullptr, nullptr));
-        }
-        CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
-        CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
-        {
-            Span sp(ctx, T_SEARCH_FILL);
-            CNN_TRY(launch_rows_any(ctx, n, g, radius_cutoff, metric, 1, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>()));
-        }
+        CNN_TRY(launch_rows_any(ctx, pb, pe, 1, nullptr, row_ptr, col_idx));
     }
+    return CNNB200_OK;
+}
 
+int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric) {
+    cudaStream_t st = ctx->stream;
+    CNN_TRY(cnn_grid_build(ctx, d_x, n, d, radius_cutoff, metric));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_deg, sizeof(int) * (size_t)(n + 1)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_row_ptr, sizeof(ll) * (size_t)(n + 1)));
+    CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>() + n, 0, sizeof(int), st));
+    CNN_TRY(cnn_grid_rows(ctx, 0, n, ctx->b_deg.as<int>()));
+    ll nnz = 0, max_deg = 0;
+    CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
+    CNN_TRY(cnn_grid_fill(ctx, 0, n, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>()));
     ctx->n = n;
     ctx->nnz = nnz;
     ctx->max_deg = max_deg;
     ctx->row_ptr = ctx->b_row_ptr.as<ll>();
     ctx->col_idx = ctx->b_col_idx.as<int>();
     ctx->perm = ctx->b_perm.as<int>();
+    return CNNB200_OK;
+}
+
+// ---- row-sharded construction (multi-GPU): C-ABI -----------------------------------------------------
+__global__ void balance_kernel(const ll *__restrict__ goff, ll n, int parts, ll *bounds) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > parts) return;
+    if (k == 0) { bounds[0] = 0; return; }
+    if (k == parts) { bounds[parts] = n; return; }
+    // first row whose candidate prefix reaches k/parts of the total, rounded to a multiple of 32 rows
+    const ll total = goff[n];
+    const ll target = (ll)((double)total * k / parts);
+    ll lo = 0, hi = n;
+    while (lo < hi) {
+        ll mid = (lo + hi) >> 1;
+        if (goff[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    lo = (lo + 16) / 32 * 32;
+    bounds[k] = lo > n ? n : lo;
+}
+
+extern "C" int cnnb200_grid_begin(cnnb200_ctx *ctx, const double *x, int loc, int64_t n, int64_t d,
+                                  double radius_cutoff, int metric) {
+    if (!ctx || !x) CNN_FAIL(CNNB200_E_INVALID, "grid_begin: NULL argument");
+    if (n < 1 || d < 1 || d > 3) CNN_FAIL(CNNB200_E_INVALID, "grid_begin: need n >= 1 and 1 <= d <= 3");
+    if (n >= (1ll << 31) - 1) CNN_FAIL(CNNB200_E_RANGE, "grid_begin: n must be < 2^31-1");
+    if (metric != CNNB200_METRIC_EUCLIDEAN_REDUCED && metric != CNNB200_METRIC_EUCLIDEAN)
+        CNN_FAIL(CNNB200_E_INVALID, "grid_begin: unknown metric %d", metric);
+    if (!(radius_cutoff >= 0.0)) CNN_FAIL(CNNB200_E_INVALID, "grid_begin: radius_cutoff must be >= 0");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    ctx->have_nb = false;
+    ctx->have_comp = false;
+    const double *d_x = x;
+    if (loc == CNNB200_HOST) {
+        CNN_TRY(cnn_ensure(ctx, ctx->b_x, sizeof(double) * (size_t)n * (size_t)d));
+        Span sp(ctx, T_H2D);
+        CNN_CUDA(cudaMemcpyAsync(ctx->b_x.p, x, sizeof(double) * (size_t)n * (size_t)d, cudaMemcpyHostToDevice, ctx->stream));
+        d_x = ctx->b_x.as<double>();
+    }
+    return cnn_grid_build(ctx, d_x, n, d, radius_cutoff, metric);
+}
+
+extern "C" int cnnb200_grid_balance(cnnb200_ctx *ctx, int parts, int64_t *bounds) {
+    if (!ctx || !bounds || parts < 1 || parts > 1024) CNN_FAIL(CNNB200_E_INVALID, "grid_balance: bad argument");
+    if (!ctx->have_grid) CNN_FAIL(CNNB200_E_STATE, "grid_balance: call grid_begin first");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_bbox, sizeof(ll) * (size_t)(parts + 1)));
+    balance_kernel<<<cnn_blocks(parts + 1, 128), 128, 0, ctx->stream>>>(ctx->b_tmp1.as<ll>(), ctx->grid_n, parts,
+                                                                         ctx->b_bbox.as<ll>());
+    CNN_KERNEL_CHECK();
+    ll *h;
+    CNN_TRY(cnn_pinned(ctx, sizeof(ll) * (size_t)(parts + 1), (void **)&h));
+    CNN_CUDA(cudaMemcpyAsync(h, ctx->b_bbox.p, sizeof(ll) * (size_t)(parts + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k <= parts; ++k) bounds[k] = h[k];
+    for (int k = 1; k <= parts; ++k)
+        if (bounds[k] < bounds[k - 1]) bounds[k] = bounds[k - 1];
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_grid_degrees(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end, int32_t *deg) {
+    if (!ctx || !deg) CNN_FAIL(CNNB200_E_INVALID, "grid_degrees: NULL argument");
+    if (!ctx->have_grid) CNN_FAIL(CNNB200_E_STATE, "grid_degrees: call grid_begin first");
+    if (row_begin < 0 || row_end > ctx->grid_n || row_begin > row_end)
+        CNN_FAIL(CNNB200_E_INVALID, "grid_degrees: bad row range");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    return cnn_grid_rows(ctx, row_begin, row_end, deg);
+}
+
+extern "C" int cnnb200_grid_fill(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end, const int64_t *row_ptr,
+                                 int32_t *col_idx) {
+    if (!ctx || !row_ptr || !col_idx) CNN_FAIL(CNNB200_E_INVALID, "grid_fill: NULL argument");
+    if (!ctx->have_grid) CNN_FAIL(CNNB200_E_STATE, "grid_fill: call grid_begin first");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    return cnn_grid_fill(ctx, row_begin, row_end, (const ll *)row_ptr, col_idx);
+}
+
+extern "C" int cnnb200_neighbours_adopt(cnnb200_ctx *ctx, const int64_t *row_ptr, const int32_t *col_idx, int64_t n,
+                                        int64_t nnz, int64_t max_deg, int grid_perm) {
+    if (!ctx || !row_ptr || (!col_idx && nnz > 0)) CNN_FAIL(CNNB200_E_INVALID, "neighbours_adopt: NULL argument");
+    if (grid_perm && (!ctx->have_grid || ctx->grid_n != n))
+        CNN_FAIL(CNNB200_E_STATE, "neighbours_adopt: no grid of that size (call grid_begin first)");
+    ctx->n = n;
+    ctx->nnz = nnz;
+    ctx->max_deg = max_deg;
+    ctx->row_ptr = (const ll *)row_ptr;
+    ctx->col_idx = col_idx;
+    ctx->perm = grid_perm ? ctx->b_perm.as<int>() : nullptr;
+    ctx->have_nb = true;
+    ctx->have_comp = false;
     return CNNB200_OK;
 }

@@ -1,0 +1,153 @@
+"""Row-sharded fit over the GPUs of one box: one process per GPU, ``torch.distributed`` for the
+plumbing (NCCL on the box, gloo in the CPU tests).  SURVEY.md section 8(e):
+
+* coordinates are replicated, query rows (points in cell-sorted order) are split into contiguous
+  blocks that balance the number of candidate pairs;
+* exchange 1 -- the CSR: degrees by an all-reduce of the row-indexed int32 array (each rank fills
+  only its block), then every rank writes its rows straight into its slice of the gathered
+  ``col_idx`` buffer and the slices are broadcast (variable sizes);
+* every rank settles the candidate edges of its own row block on a private parent array;
+* exchange 2 -- the parent arrays: all-gather of ``G x N`` int32, then each rank unions
+  ``(i, parent_g[i])`` for all g.  Hooking always goes towards the smaller root, so the merged
+  forest -- and with it every label -- is identical on all ranks and independent of ``G``.
+
+The collectives are ordinary ``torch.distributed`` calls on tensors that alias the buffers the C
+library works on; the compute between them is the same C-ABI used on a single GPU.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class _DevPtr:
+    """Exposes a raw device pointer to torch through ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def tensor_from_ptr(ptr, shape, typestr, device):
+    return torch.as_tensor(_DevPtr(ptr, shape, typestr), device=device)
+
+
+# ---- backend-agnostic plumbing (also exercised with gloo on CPU tensors) ---------------------------
+def block_of(bounds, rank):
+    return int(bounds[rank]), int(bounds[rank + 1])
+
+
+def exchange_degrees(deg, group=None):
+    """deg: row-indexed int32 [n+1], zero outside the caller's row block -> full degrees on every rank;
+    returns row_ptr int64 [n+1]."""
+    dist.all_reduce(deg, op=dist.ReduceOp.SUM, group=group)
+    row_ptr = torch.zeros(deg.shape[0], dtype=torch.int64, device=deg.device)
+    torch.cumsum(deg[:-1], 0, dtype=torch.int64, out=row_ptr[1:])
+    return row_ptr
+
+
+def exchange_slices(col_idx, slice_bounds, group=None):
+    """col_idx [nnz] holds the caller's slice [slice_bounds[rank], slice_bounds[rank+1]) -> all slices."""
+    world = dist.get_world_size(group)
+    works = []
+    for g in range(world):
+        s, e = int(slice_bounds[g]), int(slice_bounds[g + 1])
+        if e > s:
+            src = dist.get_global_rank(group, g) if group is not None else g
+            works.append(dist.broadcast(col_idx[s:e], src=src, group=group, async_op=True))
+    for w in works:
+        w.wait()
+
+
+def gather_parents(parents, group=None):
+    """parents int32 [n] of this rank -> int32 [G, n] of all ranks."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world, parents.shape[0]), dtype=parents.dtype, device=parents.device)
+    if parents.is_cuda:
+        dist.all_gather_into_tensor(out, parents, group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), parents, group=group)
+    return out
+
+
+class ShardedFit:
+    """``Clustering.fit`` hot path on ``world_size`` GPUs; every rank ends up with the full labels."""
+
+    def __init__(self, ctx, group=None):
+        self.ctx = ctx
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.device = torch.device("cuda", ctx.device)
+        ctx.set_stream(torch.cuda.current_stream(self.device))  # collectives are ordered against this stream
+        self.last = {}
+
+    # -- neighbourhoods from coordinates, rows sharded ---------------------------------------------
+    def neighbours_from_points(self, x, radius_cutoff, metric="euclidean_r"):
+        ctx, G = self.ctx, self.world
+        n = x.shape[0]
+        ctx.grid_begin(x, radius_cutoff, metric)          # replicated: every rank sorts all points
+        bounds = ctx.grid_balance(G)                      # identical on every rank (same data)
+        b, e = block_of(bounds, self.rank)
+        deg = torch.zeros(n + 1, dtype=torch.int32, device=self.device)
+        ctx.grid_degrees(b, e, deg)
+        row_ptr = exchange_degrees(deg, self.group)
+        bt = torch.as_tensor(bounds, device=self.device)
+        host = torch.cat([row_ptr[bt], deg.max().to(torch.int64).view(1)]).cpu().numpy()
+        slice_bounds, max_deg = host[:-1], int(host[-1])
+        nnz = int(slice_bounds[-1])
+        col_idx = torch.empty(max(nnz, 1), dtype=torch.int32, device=self.device)[:nnz]
+        ctx.grid_fill(b, e, row_ptr, col_idx)             # lands directly in this rank's slice
+        exchange_slices(col_idx, slice_bounds, self.group)
+        ctx.neighbours_adopt(row_ptr, col_idx, max_deg, grid_perm=True)
+        self.last = dict(bounds=bounds, slice_bounds=slice_bounds, nnz=nnz)
+        return bounds
+
+    # -- neighbourhoods from a precomputed CSR: each rank uploads only its row block ------------------
+    def neighbours_from_csr_host(self, row_ptr_host, col_idx_host):
+        """row_ptr int64 [n+1] / col_idx int32|int64 [nnz] in host memory (every rank sees the arrays,
+        e.g. memory-mapped; each rank reads and uploads only its own rows)."""
+        ctx, G = self.ctx, self.world
+        n = row_ptr_host.shape[0] - 1
+        nnz = int(row_ptr_host[-1])
+        # balance by entries
+        targets = (np.arange(G + 1, dtype=np.float64) * nnz / G).astype(np.int64)
+        bounds = np.searchsorted(row_ptr_host, targets, side="left").astype(np.int64)
+        bounds[0], bounds[-1] = 0, n
+        bounds = np.maximum.accumulate(bounds)
+        slice_bounds = row_ptr_host[bounds]
+        s, e = int(slice_bounds[self.rank]), int(slice_bounds[self.rank + 1])
+        row_ptr = torch.from_numpy(np.ascontiguousarray(row_ptr_host)).to(self.device)
+        col_idx = torch.empty(max(nnz, 1), dtype=torch.int32, device=self.device)[:nnz]
+        mine = torch.from_numpy(np.ascontiguousarray(col_idx_host[s:e]))
+        col_idx[s:e].copy_(mine.to(self.device, non_blocking=True).to(torch.int32))
+        exchange_slices(col_idx, slice_bounds, self.group)
+        max_deg = int(np.diff(row_ptr_host).max()) if n else 0
+        ctx.neighbours_adopt(row_ptr, col_idx, max_deg, grid_perm=False)
+        self.last = dict(bounds=bounds, slice_bounds=slice_bounds, nnz=nnz)
+        return bounds
+
+    # -- components on the gathered CSR, rows sharded ----------------------------------------------------
+    def fit(self, bounds, n_member_cutoff, similarity_cutoff, labels, current_start=1, sort_by_size=True,
+            member_cutoff=None, max_clusters=None):
+        ctx = self.ctx
+        n = int(bounds[-1])
+        b, e = block_of(bounds, self.rank)
+        ctx.components_begin(n_member_cutoff, similarity_cutoff)
+        ctx.components_edges(b, e)
+        parents = tensor_from_ptr(ctx.components_parents_ptr(), (n,), "<i4", self.device)
+        gathered = gather_parents(parents, self.group)
+        ctx.components_merge(gathered, self.world)
+        on_host = isinstance(labels, np.ndarray)
+        lab_dev = torch.zeros(n, dtype=torch.int64, device=self.device) if on_host else labels.zero_()
+        n_clusters = ctx.components_labels(current_start, lab_dev, fresh=True)
+        if sort_by_size:
+            ctx.sort_by_size(lab_dev, member_cutoff, max_clusters)
+        if on_host:
+            torch.from_numpy(labels).copy_(lab_dev)  # D2H (synchronises)
+        return n_clusters
+
+    def fit_points(self, x, radius_cutoff, n_member_cutoff, similarity_cutoff, labels, current_start=1,
+                   metric="euclidean_r", sort_by_size=True, member_cutoff=None, max_clusters=None, **_):
+        bounds = self.neighbours_from_points(x, radius_cutoff, metric)
+        return self.fit(bounds, n_member_cutoff, similarity_cutoff, labels, current_start, sort_by_size,
+                        member_cutoff, max_clusters)

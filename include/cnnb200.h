@@ -91,6 +91,28 @@ int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x, int loc, i
                                    int64_t d, double radius_cutoff, int metric, int method,
                                    int64_t *nnz_out);
 
+/* ---------------------------------------------------------------------------------------
+ * Row-sharded form of the cell-list search, for one process per GPU (coordinates replicated,
+ * query rows sharded).  Rows are the points in cell-sorted order.
+ *   grid_begin    every rank: grid geometry, sort by cell, candidate-list prefix
+ *   grid_balance  row-block boundaries bounds[0..parts] (HOST) that balance the candidate pairs
+ *   grid_degrees  this rank's block: deg[row_begin..row_end) (DEVICE int32, indexed by row)
+ *   (all ranks exchange the degrees; row_ptr = exclusive prefix sum over all rows)
+ *   grid_fill     this rank's block written into col_idx at row_ptr[row] (DEVICE buffers that
+ *                 span ALL rows: the block lands directly in its slice of the gathered CSR)
+ *   (all ranks exchange the col_idx slices)
+ *   neighbours_adopt  use the gathered CSR (borrowed DEVICE buffers); grid_perm != 0 attaches
+ *                 the cell-sort permutation of this context's grid.
+ * ------------------------------------------------------------------------------------- */
+int cnnb200_grid_begin(cnnb200_ctx *ctx, const double *x, int loc, int64_t n, int64_t d,
+                       double radius_cutoff, int metric);
+int cnnb200_grid_balance(cnnb200_ctx *ctx, int parts, int64_t *bounds);
+int cnnb200_grid_degrees(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end, int32_t *deg);
+int cnnb200_grid_fill(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end, const int64_t *row_ptr,
+                      int32_t *col_idx);
+int cnnb200_neighbours_adopt(cnnb200_ctx *ctx, const int64_t *row_ptr, const int32_t *col_idx,
+                             int64_t n, int64_t nnz, int64_t max_deg, int grid_perm);
+
 /* Precomputed neighbourhoods, CSR form (row_ptr int64 [n+1]; col_idx int32 or int64 [nnz],
  * `idx_bytes` = 4 or 8), rows ascending.  Replaces NeighboursGetterExtLookup._get
  * (_types.pyx:1806-1817) for all rows.  With loc == CNNB200_DEVICE, idx_bytes == 4 and

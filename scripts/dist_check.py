@@ -1,0 +1,47 @@
+"""torchrun target: row-sharded fit on all visible GPUs must equal the single-GPU fit and the oracle."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from commonnnclustering_b200 import _lib, datasets
+from commonnnclustering_b200 import dist as cdist
+
+local = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank, world = dist.get_rank(), dist.get_world_size()
+ctx = _lib.Context(local, torch_allocator=True)
+ctx.set_stream(torch.cuda.current_stream())
+sf = cdist.ShardedFit(ctx)
+ok = True
+for n, r, c, mc in [(20000, 0.25, 10, None), (300000, 0.13, 20, 10)]:
+    x = datasets.md_like_3d(n)
+    lab = np.empty(n, dtype=np.int64)
+    sf.fit_points(x, r * r, c + 1, c + 2, lab, member_cutoff=mc)
+    single = np.empty(n, dtype=np.int64)
+    _lib.Context(local).fit_points(x, r * r, c + 1, c + 2, single, member_cutoff=mc)
+    same = np.array_equal(lab, single)
+    if n <= 20000:
+        from oracle import port
+        same &= np.array_equal(lab, port.fit_points(x, r, c, member_cutoff=mc))
+    # precomputed-CSR route: every rank uploads only its rows
+    rp, ci = _lib.Context(local), None
+    c1 = _lib.Context(local)
+    c1.neighbours_from_points(x, r * r)
+    rp, ci = c1.neighbours_export()
+    bounds = sf.neighbours_from_csr_host(rp, ci)
+    lab2 = np.empty(n, dtype=np.int64)
+    sf.fit(bounds, c + 1, c + 2, lab2, member_cutoff=mc)
+    same &= np.array_equal(lab2, single)
+    print(f"rank {rank}/{world} n={n}: sharded == single: {same}; clusters {int(lab.max())}", flush=True)
+    ok &= bool(same)
+t = torch.tensor([int(ok)], device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("DIST OK" if t.item() else "DIST FAILED", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if t.item() else 1)

@@ -142,8 +142,3 @@ int cnn_dense_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double rad
     ctx->perm = nullptr;
     return CNNB200_OK;
 }
-
-// Placeholder until the tcgen05 filter kernel lands in tensor.cu (method 3).
-__attribute__((weak)) int cnn_tensor_search(cnnb200_ctx *, const double *, ll, ll, double, int) {
-    CNN_FAIL(CNNB200_E_INVALID, "method 3 (tensor-core filter) is not built into this library");
-}

@@ -1,0 +1,461 @@
+// tensor.cu -- K3: radius-neighbour search for high-dimensional points on the 5th-generation
+// tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA) with an exact f64
+// recheck of every pair near the cutoff.
+//
+// Bulk replacement of NeighboursGetterExtBruteForce._get (reference _types.pyx:1692-1710) with
+// MetricExtEuclideanReduced / MetricExtEuclidean (_types.pyx:2253-2267, :2173-2187).  The
+// reference evaluates N^2 distances in f64, one virtual call each; here the N^2 part is a dense
+// contraction d2(i,j) = |x_i|^2 + |x_j|^2 - 2 x_i.x_j and runs as a bf16 GEMM:
+//
+//   * the (mean-centred) coordinates are split x = hi + lo into two bf16 parts; the three
+//     products hi.hi + hi.lo + lo.hi are ONE MMA chain over the concatenated K axis
+//     A' = [hi | hi | lo], B' = [hi | lo | hi] (K = 3 D, fp32 accumulation in TMEM);
+//   * the epilogue reads the accumulator tile with tcgen05.ld, forms d2~ and classifies:
+//       d2~ <= R - eps  -> neighbour,   d2~ > R + eps -> not a neighbour,
+//       otherwise       -> the pair is re-evaluated right there with the reference's own f64
+//                          expression (sequential sum, no FMA, sqrt for the non-reduced metric);
+//     eps is a bound on |d2~ - d2| derived from the largest norm, so the neighbour
+//     SETS are exactly the reference's;
+//   * a CTA owns 128 rows and walks over all 128-column tiles in ascending order, so each CSR
+//     row is emitted ascending (count pass -> scan -> fill pass, as for the other producers).
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one
+// elected lane) + TMEM allocation, warps 2-5 = epilogue (one TMEM lane quarter each).
+// Pipelines: smem B stages full/empty (TMA <-> MMA), TMEM accumulator stages full/empty
+// (MMA <-> epilogue), two stages each.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+#define TT 128            // tile edge (rows of A' = UMMA M, rows of B' = UMMA N)
+#define KATOM 64          // bf16 elements per 128-byte swizzle atom
+#define ATOM_BYTES (TT * 128)
+#define MAX_ATOMS 4
+#define NUM_THREADS 192
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 in, f32 accumulate (kind::f16)
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;             // leading byte offset (not used by swizzled K-major layouts)
+    d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;             // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+    return d;
+}
+// 32 lanes x 32 columns of 32-bit: thread l of the warp gets columns [c, c+32) of its TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t *r = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+        " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------
+// operand preparation
+// ---------------------------------------------------------------------------------------------------
+__global__ void col_mean_kernel(const double *__restrict__ x, ll n, int d, double *mean) {
+    // one block per dimension
+    int k = blockIdx.x;
+    double s = 0;
+    for (ll i = threadIdx.x; i < n; i += blockDim.x) s += x[i * d + k];
+    __shared__ double sh[256];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) mean[k] = sh[0] / (double)n;
+}
+
+// A'[i] = [hi | hi | lo | 0..], B'[i] = [hi | lo | hi | 0..] (bf16, row length kt), norm[i] = |x_i - mean|^2;
+// padding rows (i >= n) are zero with an infinite norm so that they never come near the cutoff.
+__global__ void split_kernel(const double *__restrict__ x, const double *__restrict__ mean, ll n, ll n_pad, int d,
+                             int kt, __nv_bfloat16 *A, __nv_bfloat16 *B, float *norm, int *maxnorm_bits) {
+    ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    __nv_bfloat16 *a = A + i * kt, *b = B + i * kt;
+    const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+    if (i >= n) {
+        for (int k = 0; k < kt; ++k) { a[k] = zero; b[k] = zero; }
+        norm[i] = INFINITY;
+        return;
+    }
+    double s = 0;
+    for (int k = 0; k < d; ++k) {
+        double xc = x[i * d + k] - mean[k];
+        s += xc * xc;
+        __nv_bfloat16 hi = __float2bfloat16_rn((float)xc);
+        __nv_bfloat16 lo = __float2bfloat16_rn((float)(xc - (double)__bfloat162float(hi)));
+        a[k] = hi; a[d + k] = hi; a[2 * d + k] = lo;
+        b[k] = hi; b[d + k] = lo; b[2 * d + k] = hi;
+    }
+    for (int k = 3 * d; k < kt; ++k) { a[k] = zero; b[k] = zero; }
+    float sf = (float)s;
+    norm[i] = sf;
+    atomicMax(maxnorm_bits, __float_as_int(sf));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exact f64 distance, the reference's expression (_types.pyx:2253-2267)
+// ---------------------------------------------------------------------------------------------------
+template <bool SQRT>
+__device__ __noinline__ bool exact_within(const double *__restrict__ x, int d, ll i, ll j, double rc) {
+    const double *a = x + i * d, *b = x + j * d;
+    double s = 0.0;
+    for (int k = 0; k < d; ++k) {
+        double t = __dsub_rn(a[k], b[k]);
+        s = __dadd_rn(s, __dmul_rn(t, t));
+    }
+    if (SQRT) s = __dsqrt_rn(s);
+    return s <= rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the tile kernel
+// ---------------------------------------------------------------------------------------------------
+struct TensorParams {
+    const double *x;      // original coordinates [n, d] (exact recheck)
+    const float *norm;    // [n_pad]
+    ll n, n_tiles;
+    int d, atoms;
+    float r2_lo, r2_hi;   // R - eps, R + eps in squared-distance units
+    double rc;            // the metric-adjusted cutoff of the exact test
+    int *deg;             // count pass out
+    const ll *row_ptr;    // fill pass in
+    int *col_idx;         // fill pass out
+    unsigned long long *stats;
+};
+
+template <bool FILL, bool SQRT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tensor_rows_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   const TensorParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: A tile | B stage 0 | B stage 1 | barriers | tmem slot | column norms
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int atoms = P.atoms;
+    const uint32_t tile_bytes = (uint32_t)atoms * ATOM_BYTES;
+    uint8_t *sA = smem;
+    uint8_t *sB[2] = {smem + tile_bytes, smem + 2 * tile_bytes};
+    uint64_t *bars = (uint64_t *)(smem + 3 * tile_bytes);
+    uint64_t *a_full = bars + 0, *full = bars + 1, *empty = bars + 3, *t_full = bars + 5, *t_empty = bars + 7;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 9);
+    float *ncs = (float *)(bars + 10);  // [2][TT]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ll i0 = (ll)blockIdx.x * TT;
+    const ll n_tiles = P.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        mbar_init(a_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+            mbar_init(t_full + s, 1);
+            mbar_init(t_empty + s, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(a_full, tile_bytes);
+            for (int a = 0; a < atoms; ++a) tma_load_2d(sA + a * ATOM_BYTES, &mapA, a * KATOM, (int)i0, a_full);
+            for (ll j = 0; j < n_tiles; ++j) {
+                const int s = (int)(j & 1);
+                const uint32_t ph = (uint32_t)((j >> 1) & 1);
+                mbar_wait(empty + s, ph ^ 1);
+                mbar_expect_tx(full + s, tile_bytes);
+                for (int a = 0; a < atoms; ++a)
+                    tma_load_2d(sB[s] + a * ATOM_BYTES, &mapB, a * KATOM, (int)(j * TT), full + s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor: D f32, A/B bf16, both K-major, N = 128, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(TT >> 4) << 24);
+            mbar_wait(a_full, 0);
+            const uint32_t a_addr = smem_u32(sA);
+            for (ll j = 0; j < n_tiles; ++j) {
+                const int s = (int)(j & 1);
+                const uint32_t ph = (uint32_t)((j >> 1) & 1);
+                mbar_wait(t_empty + s, ph ^ 1);   // epilogue has drained this accumulator stage
+                mbar_wait(full + s, ph);          // TMA has landed this B tile
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(sB[s]);
+                const uint32_t d_tmem = tmem_base + (uint32_t)s * TT;
+                for (int k = 0; k < atoms * 4; ++k) {  // UMMA K = 16 bf16 = 32 bytes inside the swizzle atom
+                    const uint32_t off = (uint32_t)(k >> 2) * ATOM_BYTES + (uint32_t)(k & 3) * 32;
+                    tc_mma(d_tmem, umma_desc(a_addr + off), umma_desc(b_addr + off), idesc, k > 0);
+                }
+                tc_commit(empty + s);   // smem stage free once these MMAs have read it
+                tc_commit(t_full + s);  // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> classify -> (count | write) =====
+        const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;       // accumulator row = TMEM lane
+        const int te = (warp - 2) * 32 + lane;  // 0..127 among the epilogue threads
+        const ll gi = i0 + row;
+        const float nr = P.norm[gi];
+        const bool live = gi < P.n;
+        ll base = (FILL && live) ? P.row_ptr[gi] : 0;
+        int cnt = 0;
+        unsigned long long n_recheck = 0;
+        for (ll j = 0; j < n_tiles; ++j) {
+            const int s = (int)(j & 1);
+            const uint32_t ph = (uint32_t)((j >> 1) & 1);
+            ncs[s * TT + te] = P.norm[j * TT + te];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(t_full + s, ph);
+            tc_fence_after();
+            const float *nc = ncs + s * TT;
+            for (int chunk = 0; chunk < 4; ++chunk) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * TT + chunk * 32), v);
+                tmem_ld_wait();
+                if (chunk == 3) {  // all reads of this accumulator stage are done: hand it back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(t_empty + s);
+                }
+                // d2~ = |xi|^2 + |xj|^2 - 2 acc ; cheap screen first: hits are rare
+                float best = INFINITY;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    v[c] = fmaf(-2.f, v[c], nr + nc[chunk * 32 + c]);
+                    best = fminf(best, v[c]);
+                }
+                if (best <= P.r2_hi && live) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        if (v[c] <= P.r2_hi) {
+                            const ll gj = j * TT + chunk * 32 + c;
+                            bool hit = v[c] <= P.r2_lo;
+                            if (!hit) {
+                                ++n_recheck;
+                                hit = exact_within<SQRT>(P.x, P.d, gi, gj, P.rc);
+                            }
+                            if (hit) {
+                                if (FILL) P.col_idx[base + cnt] = (int)gj;
+                                ++cnt;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (!FILL && live) P.deg[gi] = cnt;
+        if (!FILL && n_recheck) atomicAdd(P.stats + ST_RECHECK, n_recheck);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap *map, void *base, ll n_pad, int kt) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) CNN_FAIL(CNNB200_E_CUDA, "tensor search: cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)kt, (cuuint64_t)n_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)kt * 2};
+    cuuint32_t box[2] = {KATOM, TT};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) CNN_FAIL(CNNB200_E_CUDA, "tensor search: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return CNNB200_OK;
+}
+
+int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric) {
+    cudaStream_t st = ctx->stream;
+    const int atoms = (int)((3 * d + KATOM - 1) / KATOM);
+    if (atoms > MAX_ATOMS)
+        CNN_FAIL(CNNB200_E_RANGE, "tensor search supports up to %d dimensions (got %lld); use the tiled method",
+                 MAX_ATOMS * KATOM / 3, (long long)d);
+    const int kt = atoms * KATOM;
+    const ll n_tiles = (n + TT - 1) / TT, n_pad = n_tiles * TT;
+    const bool sq = metric == CNNB200_METRIC_EUCLIDEAN;
+    const double R = sq ? radius_cutoff * radius_cutoff : radius_cutoff;
+
+    // ---- operands -----------------------------------------------------------------------------
+    CNN_TRY(cnn_ensure(ctx, ctx->b_xs, sizeof(__nv_bfloat16) * (size_t)n_pad * kt * 2));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp1, sizeof(float) * (size_t)n_pad));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_bbox, sizeof(double) * (size_t)(d + 2)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_deg, sizeof(int) * (size_t)(n + 1)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_row_ptr, sizeof(ll) * (size_t)(n + 1)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_stats, sizeof(unsigned long long) * ST_N));
+    __nv_bfloat16 *A = ctx->b_xs.as<__nv_bfloat16>(), *B = A + (size_t)n_pad * kt;
+    float *norm = ctx->b_tmp1.as<float>();
+    double *mean = ctx->b_bbox.as<double>();
+    int *maxbits = (int *)(mean + d);
+    {
+        Span sp(ctx, T_GRID_BUILD);
+        CNN_CUDA(cudaMemsetAsync(maxbits, 0, sizeof(int), st));
+        CNN_CUDA(cudaMemsetAsync(ctx->b_stats.p, 0, sizeof(unsigned long long) * ST_N, st));
+        col_mean_kernel<<<(int)d, 256, 0, st>>>(d_x, n, (int)d, mean);
+        split_kernel<<<cnn_blocks(n_pad, 128), 128, 0, st>>>(d_x, mean, n, n_pad, (int)d, kt, A, B, norm, maxbits);
+        CNN_LAUNCHED(ctx, 2);
+        CNN_KERNEL_CHECK();
+    }
+    float *hm;
+    CNN_TRY(cnn_pinned(ctx, 64, (void **)&hm));
+    CNN_CUDA(cudaMemcpyAsync(hm, maxbits, sizeof(float), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaStreamSynchronize(st));
+    const double maxnorm = hm[0];
+    if (!isfinite(maxnorm)) CNN_FAIL(CNNB200_E_INVALID, "neighbour search: coordinates contain NaN or infinity");
+    // |d2~ - d2| <= 2 * maxnorm * (2^-15 [bf16 split: dropped lo.lo and residuals] + K * 2^-22 [fp32
+    // accumulation in the tensor core]) + 2^-21 * maxnorm [norms rounded to f32]; see DESIGN.md
+    const double eps = 2.0 * maxnorm * (ldexp(1.0, -15) + (double)kt * ldexp(1.0, -22)) + ldexp(maxnorm, -21) + 1e-30;
+
+    CUtensorMap mapA, mapB;
+    CNN_TRY(make_map(&mapA, A, n_pad, kt));
+    CNN_TRY(make_map(&mapB, B, n_pad, kt));
+
+    TensorParams P;
+    P.x = d_x;
+    P.norm = norm;
+    P.n = n;
+    P.n_tiles = n_tiles;
+    P.d = (int)d;
+    P.atoms = atoms;
+    P.r2_lo = (float)(R - eps);
+    P.r2_hi = (float)(R + eps);
+    // keep the f32 thresholds on the safe side of the f64 ones
+    P.r2_lo = nextafterf(P.r2_lo, -INFINITY);
+    P.r2_hi = nextafterf(P.r2_hi, INFINITY);
+    P.rc = radius_cutoff;
+    P.deg = ctx->b_deg.as<int>();
+    P.row_ptr = nullptr;
+    P.col_idx = nullptr;
+    P.stats = (unsigned long long *)ctx->b_stats.p;
+
+    const size_t smem = (size_t)3 * atoms * ATOM_BYTES + 1024 /*alignment*/ + 80 + 4 + 2 * TT * sizeof(float) + 64;
+    auto k_count = sq ? tensor_rows_kernel<false, true> : tensor_rows_kernel<false, false>;
+    auto k_fill = sq ? tensor_rows_kernel<true, true> : tensor_rows_kernel<true, false>;
+    CNN_CUDA(cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CNN_CUDA(cudaFuncSetAttribute(k_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>() + n, 0, sizeof(int), st));
+    {
+        Span sp(ctx, T_SEARCH_COUNT);
+        k_count<<<(int)n_tiles, NUM_THREADS, smem, st>>>(mapA, mapB, P);
+        CNN_LAUNCHED(ctx, 1);
+        CNN_KERNEL_CHECK();
+    }
+    ll nnz = 0, max_deg = 0;
+    CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
+    P.row_ptr = ctx->b_row_ptr.as<ll>();
+    P.col_idx = ctx->b_col_idx.as<int>();
+    {
+        Span sp(ctx, T_SEARCH_FILL);
+        k_fill<<<(int)n_tiles, NUM_THREADS, smem, st>>>(mapA, mapB, P);
+        CNN_LAUNCHED(ctx, 1);
+        CNN_KERNEL_CHECK();
+    }
+    unsigned long long *hs;
+    CNN_TRY(cnn_pinned(ctx, 64, (void **)&hs));
+    CNN_CUDA(cudaMemcpyAsync(hs, (unsigned long long *)ctx->b_stats.p + ST_RECHECK, sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaStreamSynchronize(st));
+    ctx->stats[ST_RECHECK] = (ll)hs[0];
+    ctx->stats[ST_DIST] = n * n;
+    ctx->n = n;
+    ctx->nnz = nnz;
+    ctx->max_deg = max_deg;
+    ctx->row_ptr = ctx->b_row_ptr.as<ll>();
+    ctx->col_idx = ctx->b_col_idx.as<int>();
+    ctx->perm = nullptr;
+    return CNNB200_OK;
+}

@@ -1,0 +1,52 @@
+"""Tensor-core neighbour search (method 'tensor') vs the exact f64 tiled search."""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from commonnnclustering_b200 import _lib, datasets
+
+ctx = _lib.Context(0)
+ok = True
+sizes = [int(s) for s in os.environ.get("SIZES", "1000,5000,20000").split(",")]
+for n in sizes:
+    x = datasets.features_64d(n)
+    r = 0.6 if n >= 100000 else 0.9
+    t0 = time.perf_counter(); nnz_t = ctx.neighbours_from_points(x, r * r, method="tensor"); t1 = time.perf_counter() - t0
+    a = ctx.neighbours_export(); st = ctx.stats()
+    t0 = time.perf_counter(); nnz_e = ctx.neighbours_from_points(x, r * r, method="tiled"); t2 = time.perf_counter() - t0
+    b = ctx.neighbours_export()
+    same = np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    ok &= same
+    print(f"n={n} r={r} nnz tensor {nnz_t} exact {nnz_e} equal {same} rechecks {st['rechecks']} ({st['rechecks']/n:.1f}/row) t_tensor {t1*1e3:.1f} ms t_exact {t2*1e3:.1f} ms", flush=True)
+# other shapes: small d, euclidean metric, n not a multiple of 128
+for n, d, r, metric in [(777, 8, 1.5, "euclidean_r"), (3001, 20, 3.0, "euclidean"), (130, 3, 0.5, "euclidean_r")]:
+    x = np.random.default_rng(n).standard_normal((n, d))
+    rc = r * r if metric == "euclidean_r" else r
+    ctx.neighbours_from_points(x, rc, metric=metric, method="tensor"); a = ctx.neighbours_export()
+    ctx.neighbours_from_points(x, rc, metric=metric, method="tiled"); b = ctx.neighbours_export()
+    same = np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    ok &= same
+    print(f"n={n} d={d} {metric}: equal {same} nnz {a[0][-1]}", flush=True)
+if os.environ.get("FULL"):
+    n = 200000
+    x = datasets.features_64d(n)
+    xd = torch.from_numpy(x).cuda()
+    ctx.set_timing(True)
+    for it in range(2):
+        ctx.timings()
+        nnz = ctx.neighbours_from_points(xd, 0.36, method="tensor")
+        t, _ = ctx.timings()
+        print("C3 tensor", {k: round(v[0], 2) for k, v in t.items() if v[1]}, "nnz", nnz, ctx.stats(), flush=True)
+    lab = np.empty(n, dtype=np.int64)
+    t0 = time.perf_counter()
+    ctx.fit_points(x, 0.36, 21, 22, lab, method="tensor", member_cutoff=10)
+    print("C3 fit e2e", time.perf_counter() - t0, "clusters", lab.max(), "noise", (lab == 0).mean(), flush=True)
+    np.save("gpurun_out/c3_labels_tensor.npy", lab)
+    if os.environ.get("EXACT"):
+        ctx.timings()
+        lab2 = np.empty(n, dtype=np.int64)
+        t0 = time.perf_counter()
+        ctx.fit_points(x, 0.36, 21, 22, lab2, method="tiled", member_cutoff=10)
+        print("C3 fit exact-tiled e2e", time.perf_counter() - t0, "labels equal", np.array_equal(lab, lab2), flush=True)
+        ok &= np.array_equal(lab, lab2)
+print("ALL OK" if ok else "FAILURES")

@@ -53,6 +53,41 @@ def test_tiled_search_equals_reference_golden(name):
     np.testing.assert_array_equal(cl.labels, GOLD[name].astype(np.int64))
 
 
+@pytest.mark.parametrize("name", ["feat64d_2000", "gauss5d", "gauss8d_euclid", "blobs1500_r010_c20", "lattice3d"])
+def test_tensor_core_search_equals_reference_golden(name):
+    """tcgen05 filter + f64 boundary recheck: labels identical to the reference's."""
+    case = cases.CASES[name]
+    x = case["data"]()
+    kw = dict(case["fit"])
+    cl = fit_via_api(x, kw.pop("r"), kw.pop("c"), method="tensor", **kw)
+    np.testing.assert_array_equal(cl.labels, GOLD[name].astype(np.int64))
+
+
+def test_tensor_core_neighbour_sets_are_exact(ctx):
+    """Neighbour sets of the tensor-core path equal the exact f64 all-pairs sets, including data with
+    many distances exactly on the cutoff, large norms (far from the origin) and odd sizes."""
+    rng = np.random.default_rng(21)
+    sets = [
+        (datasets.features_64d(6000), 0.9, "euclidean_r"),
+        (cases.lattice(1000, 6, 31), 0.5, "euclidean_r"),              # exact ties at the cutoff
+        (cases.lattice(700, 4, 32), 0.375, "euclidean"),
+        (rng.standard_normal((1500, 33)) + 50.0, 7.0, "euclidean_r"),   # |x|^2 ~ 8e4 >> r^2: wide band
+        (rng.standard_normal((129, 85)), 12.0, "euclidean_r"),          # largest supported dimension
+        (rng.standard_normal((1, 10)), 1.0, "euclidean_r"),
+    ]
+    for x, r, metric in sets:
+        rc = port.adjust_radius(r, metric)
+        ctx.neighbours_from_points(x, rc, metric=metric, method="tiled")
+        want = ctx.neighbours_export()
+        ctx.neighbours_from_points(x, rc, metric=metric, method="tensor")
+        got = ctx.neighbours_export()
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+    assert ctx.stats()["rechecks"] >= 0
+    with pytest.raises(_lib.CnnB200Error):
+        ctx.neighbours_from_points(rng.standard_normal((10, 86)), 1.0, method="tensor")  # > 85 dims
+
+
 def test_readme_doctest():
     cl = cluster.Clustering(datasets.README_POINTS)
     cl.fit(1.5, 1, v=False)

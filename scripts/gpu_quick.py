@@ -31,6 +31,12 @@ for it in range(4):
     ctx.fit_points(xd, r * r, c + 1, c + 2, labd, member_cutoff=10)
     t, launches = ctx.timings()
     print({k: round(v[0], 3) for k, v in t.items() if v[1]}, "total", round(sum(v[0] for v in t.values()), 3), ctx.stats(), flush=True)
+_, nnz, _ = ctx.neighbours_info()
+cnt = torch.empty(nnz, dtype=torch.int32, device="cuda")
+for it in range(3):
+    _, ne = ctx.cn_count(c + 1, cnt)
+    t, _l = ctx.timings()
+    print("cn_count ms", round(t["cn_count"][0], 3), "edges", ne, flush=True)
 lab = labd.cpu().numpy()
 ref = np.load("gpurun_out/c2_labels.npy") if os.path.exists("gpurun_out/c2_labels.npy") and n == 1000000 else None
 if ref is not None:

@@ -135,7 +135,7 @@ __global__ void comp_init_kernel(const ll *__restrict__ row_ptr, const int *__re
 __global__ void __launch_bounds__(256)
 comp_sample_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll row_begin, ll row_end,
                    int cutoff, int n_samples, const int *__restrict__ parent, int *__restrict__ edge_out,
-                   unsigned long long *stats) {
+                   int *__restrict__ above, unsigned long long *stats) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
@@ -159,6 +159,7 @@ comp_sample_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_i
                     }
                     if (l < m) j = col_idx[rb + l];
                     first_above = j;
+                    above[i] = l;  // position of the first entry > i: the edge pass starts there
                 } else {
                     j = col_idx[rb + m - 1];
                     if (j <= (int)i || j == first_above) j = -1;
@@ -179,13 +180,30 @@ comp_sample_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_i
     }
 }
 
-// one thread per recorded edge slot
-__global__ void comp_union_kernel(const int *__restrict__ edge_out, ll row_begin, ll slots, int n_samples,
+// One thread per row, all samples of the row.  Sample 0 is usually the next row (j == i + 1); linking
+// every such pair concurrently would build parent chains as long as a dense run of rows, which the
+// later finds then have to walk.  A run of consecutive linked rows inside the warp's 32-row tile is
+// therefore collapsed first: every edge of a row is applied to the run's FIRST row (its `head`, found
+// with a ballot), which is connected to the row by the accepted edges of the lanes in between.
+__global__ void comp_union_kernel(const int *__restrict__ edge_out, ll row_begin, ll rows, int n_samples,
                                   int *parent) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     ll t = blockIdx.x * (ll)blockDim.x + threadIdx.x;
-    if (t >= slots) return;
-    int j = edge_out[t];
-    if (j >= 0) uf_union(parent, (int)(row_begin + t / n_samples), j);
+    const bool valid = t < rows;
+    const ll i = row_begin + t;
+    const int j0 = valid ? edge_out[t * n_samples] : -1;
+    const unsigned linked = __ballot_sync(full, j0 == (int)i + 1 && lane < 31);  // bit l: row l ~ row l+1
+    // lowest lane h with bits h .. lane-1 all set
+    const unsigned below = ~linked & ((1u << lane) - 1u);
+    const int head = below ? 32 - __clz(below) : 0;
+    if (!valid) return;
+    const int hi = (int)(i - lane + head);
+    if (j0 >= 0) uf_union(parent, hi, j0);
+    for (int s = 1; s < n_samples; ++s) {
+        const int j = edge_out[t * n_samples + s];
+        if (j >= 0) uf_union(parent, hi, j);
+    }
 }
 
 __global__ void comp_compress_kernel(int *parent, ll n) {
@@ -196,15 +214,78 @@ __global__ void comp_compress_kernel(int *parent, ll n) {
     parent[p] = r;
 }
 
+// ---- shared-memory row window -----------------------------------------------------------------------
+// Rows of a cell-sorted CSR are clustered: a row with 10^2 entries spans a few 10^4 indices.  A warp
+// that has to intersect ONE row N(i) with MANY rows N(j) turns N(i) into a bitmap over the index
+// window [first, last] of the row in shared memory; every element of a streamed N(j) then costs one
+// probe (subtract, range check, word load, shift) instead of a binary search, and the loads of N(j)
+// are coalesced.  The kernels built on it are bound by memory latency, not by issue slots, so the
+// first WIN_PF chunks of the NEXT row to stream are fetched into registers while the current one is
+// being probed.  A row whose window does not fit (span == 0) falls back to warp_common.
+#define WIN_BITS 65536  // window bits per warp (8 KB)
+#define WIN_WARPS 4     // warps per CTA (32 KB of windows)
+#define WIN_PF 5        // chunks (of 32 entries) prefetched per streamed row
+
+struct RowWin {
+    unsigned *bits;  // WIN_BITS / 32 words owned by the warp; all zero between rows
+    int first;
+    unsigned span;  // 0: no window
+};
+
+__device__ __forceinline__ void win_set(RowWin &w, const int *__restrict__ row, int m, int lane) {
+    w.first = row[0];
+    const unsigned span = (unsigned)(row[m - 1] - w.first) + 1u;
+    w.span = span <= (unsigned)WIN_BITS ? span : 0u;
+    if (w.span)
+        for (int k = lane; k < m; k += 32) {
+            const unsigned idx = (unsigned)(row[k] - w.first);
+            atomicOr(&w.bits[idx >> 5], 1u << (idx & 31));
+        }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void win_clear(RowWin &w, const int *__restrict__ row, int m, int lane) {
+    __syncwarp();
+    if (w.span)
+        for (int k = lane; k < m; k += 32) w.bits[(unsigned)(row[k] - w.first) >> 5] = 0;
+    w.span = 0;
+    __syncwarp();
+}
+
+// 1 when v is an entry of the windowed row.  v = -1 (padding) never is: first >= 0 puts it out of range.
+__device__ __forceinline__ int win_probe(const RowWin &w, int v) {
+    const unsigned idx = (unsigned)(v - w.first);
+    return idx < w.span ? (int)((w.bits[idx >> 5] >> (idx & 31)) & 1u) : 0;
+}
+
+__device__ __forceinline__ void row_prefetch(int (&buf)[WIN_PF], const int *__restrict__ rj, int mj, int lane) {
+#pragma unroll
+    for (int u = 0; u < WIN_PF; ++u) {
+        const int t = lane + 32 * u;
+        buf[u] = t < mj ? rj[t] : -1;
+    }
+}
+
+// |windowed row ∩ N(j)|, N(j)'s first WIN_PF chunks already in registers
+__device__ __forceinline__ int row_count(const int (&buf)[WIN_PF], const int *__restrict__ rj, int mj, int lane,
+                                         const RowWin &w) {
+    int c = 0;
+#pragma unroll
+    for (int u = 0; u < WIN_PF; ++u) c += win_probe(w, buf[u]);
+#pragma unroll 4
+    for (int t = lane + 32 * WIN_PF; t < mj; t += 32) c += win_probe(w, rj[t]);
+    return __reduce_add_sync(0xffffffffu, c);
+}
+
 // Edge scan.  Runs on flattened (root-pointing) parents, which do not change during this kernel:
 // a candidate edge (i < j, both core) is settled for free when parent[i] == parent[j]; the others
-// go to a work list.  A warp takes 32 consecutive rows and streams their entries as ONE contiguous
-// range of the CSR, 32 entries per step, independent of the row boundaries; the row of an entry is
-// found by a 5-step binary search over the 32 row starts held one per lane (shuffles).
+// go to a work list.  A warp takes 32 consecutive rows (bounds, root and the position of the first
+// entry above i are fetched one row per lane) and then streams the upper part of each core row,
+// 32 entries per step.
 __global__ void __launch_bounds__(256)
 comp_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll row_begin, ll row_end,
-                 const int *__restrict__ parent, int2 *__restrict__ worklist, unsigned long long *wl_count,
-                 unsigned long long *stats) {
+                 const int *__restrict__ above, const int *__restrict__ parent, int2 *__restrict__ worklist,
+                 unsigned long long *wl_count, unsigned long long *stats) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -212,37 +293,35 @@ comp_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx
     ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     unsigned long long n_edges = 0, n_need = 0;
     for (ll i0 = row_begin + warp * 32; i0 < row_end; i0 += nwarps * 32) {
-        const ll i = i0 + lane;
-        const bool valid = i < row_end;
-        const ll rb = row_ptr[valid ? i : row_end];  // lanes past the end hold the end offset
-        const int ri = valid ? parent[i] : -1;
-        const ll beg = __shfl_sync(full, rb, 0);
-        const ll last_row = (i0 + 32 < row_end ? i0 + 32 : row_end);
-        const ll end = row_ptr[last_row];
-        for (ll k0 = beg; k0 < end; k0 += 32) {
-            const ll k = k0 + lane;
-            const bool in = k < end;
-            const int j = in ? col_idx[k] : -1;
-            // row of entry k: last lane t with rb_t <= k
-            int lo = 0;
-#pragma unroll
-            for (int step = 16; step; step >>= 1) {
-                const ll probe = __shfl_sync(full, rb, lo + step);
-                if (probe <= k) lo += step;
-            }
-            const int r_i = __shfl_sync(full, ri, lo);
-            const int ii = (int)i0 + lo;
-            const int pj = (in && r_i >= 0 && j > ii) ? parent[j] : -1;
-            const bool cand = pj >= 0;
-            const bool need = cand && pj != r_i;
-            const unsigned cm = __ballot_sync(full, cand), nm = __ballot_sync(full, need);
-            n_edges += __popc(cm);
-            if (nm) {
-                unsigned long long pos = 0;
-                if (lane == 0) pos = atomicAdd(wl_count, (unsigned long long)__popc(nm));
-                pos = __shfl_sync(full, pos, 0);
-                if (need) worklist[pos + __popc(nm & lt)] = make_int2(ii, j);
-                n_need += __popc(nm);
+        const ll il = i0 + lane;
+        const int rl = il < row_end ? parent[il] : -1;
+        ll bl = 0, el = 0;
+        if (rl >= 0) {
+            el = row_ptr[il + 1];
+            bl = row_ptr[il] + above[il];
+        }
+        unsigned rows = __ballot_sync(full, rl >= 0 && bl < el);
+        while (rows) {
+            const int r = __ffs(rows) - 1;
+            rows &= rows - 1;
+            const int r_i = __shfl_sync(full, rl, r);
+            const ll beg = __shfl_sync(full, bl, r), end = __shfl_sync(full, el, r);
+            const int ii = (int)i0 + r;
+            for (ll k0 = beg; k0 < end; k0 += 32) {
+                const ll k = k0 + lane;
+                const int j = k < end ? col_idx[k] : -1;
+                const int pj = j >= 0 ? parent[j] : -1;
+                const bool cand = pj >= 0;
+                const bool need = cand && pj != r_i;
+                const unsigned cm = __ballot_sync(full, cand), nm = __ballot_sync(full, need);
+                n_edges += __popc(cm);
+                if (nm) {
+                    unsigned long long pos = 0;
+                    if (lane == 0) pos = atomicAdd(wl_count, (unsigned long long)__popc(nm));
+                    pos = __shfl_sync(full, pos, 0);
+                    if (need) worklist[pos + __popc(nm & lt)] = make_int2(ii, j);
+                    n_need += __popc(nm);
+                }
             }
         }
     }
@@ -252,15 +331,25 @@ comp_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx
     }
 }
 
-// Work-list pass: the edges the scan could not settle.  32 edges per warp step: the finds (with
-// path halving) and the row bounds are fetched one edge per LANE; edges whose ends meanwhile share
-// a root are dropped; the rest is evaluated warp-cooperatively and linked when similar enough.
-__global__ void __launch_bounds__(256)
+// Work-list pass: the edges the scan could not settle, 32 per warp step.  The finds (with path
+// halving) and the row bounds are fetched one edge per LANE; edges whose ends meanwhile share a root
+// are dropped.  The rest is evaluated by the whole warp, one edge after the other, against the
+// shared-memory window of row i -- the scan emits the work list row by row, so consecutive entries
+// mostly share i and the window is rebuilt only when i changes -- while the entries of the next
+// N(j) are already in flight.
+__global__ void __launch_bounds__(WIN_WARPS * 32)
 comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, const int2 *__restrict__ worklist,
                      const unsigned long long *__restrict__ wl_count, int cutoff, int *parent,
                      unsigned long long *stats) {
+    __shared__ unsigned win_all[WIN_WARPS][WIN_BITS / 32];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    RowWin w;
+    w.bits = win_all[threadIdx.x >> 5];
+    w.first = 0;
+    w.span = 0;
+    for (int t = lane; t < WIN_BITS / 32; t += 32) w.bits[t] = 0;
+    __syncwarp();
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     const ll count = (ll)*wl_count;
@@ -269,19 +358,59 @@ comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col
         const ll e = e0 + lane;
         const bool valid = e < count;
         const int2 ed = valid ? worklist[e] : make_int2(0, 0);
-        int ri = valid ? uf_find(parent, ed.x) : 0;
-        int rj = valid ? uf_find(parent, ed.y) : 0;
+        const int ri = valid ? uf_find(parent, ed.x) : 0;
+        const int rj = valid ? uf_find(parent, ed.y) : 0;
         const bool need = valid && ri != rj;
         const ll bi = need ? row_ptr[ed.x] : 0, bj = need ? row_ptr[ed.y] : 0;
         const int mi = need ? (int)(row_ptr[ed.x + 1] - bi) : 0, mj = need ? (int)(row_ptr[ed.y + 1] - bj) : 0;
-        const unsigned work = __ballot_sync(full, need);
-        n_skip += __popc(__ballot_sync(full, valid)) - __popc(work);
-        n_checks += __popc(work);
-        int acc = 0;
-        if (need) {
-            acc = lane_check(col_idx + bi, mi, col_idx + bj, mj, cutoff);
-            if (acc) uf_union(parent, ri, rj);
+        int acc = need && cutoff <= 0 ? 1 : 0;
+        unsigned work = __ballot_sync(full, need && cutoff > 0 && mi >= cutoff && mj >= cutoff);
+        const unsigned nd = __ballot_sync(full, need);
+        n_skip += __popc(__ballot_sync(full, valid)) - __popc(nd);
+        n_checks += __popc(nd);
+        // software pipeline over the edges of `work`
+        int cur_x = -1, cur_m = 0;
+        const int *cur_row = nullptr;
+        int buf[WIN_PF], nbuf[WIN_PF];
+        int src = -1, smj = 0;
+        const int *sj = nullptr;
+        if (work) {
+            src = __ffs(work) - 1;
+            work &= work - 1;
+            sj = col_idx + __shfl_sync(full, bj, src);
+            smj = __shfl_sync(full, mj, src);
+            row_prefetch(buf, sj, smj, lane);
         }
+        while (src >= 0) {
+            int nsrc = -1, nsmj = 0;
+            const int *nsj = nullptr;
+            if (work) {
+                nsrc = __ffs(work) - 1;
+                work &= work - 1;
+                nsj = col_idx + __shfl_sync(full, bj, nsrc);
+                nsmj = __shfl_sync(full, mj, nsrc);
+                row_prefetch(nbuf, nsj, nsmj, lane);
+            }
+            const int x = __shfl_sync(full, ed.x, src);
+            if (x != cur_x) {
+                if (cur_x >= 0) win_clear(w, cur_row, cur_m, lane);
+                cur_x = x;
+                cur_row = col_idx + __shfl_sync(full, bi, src);
+                cur_m = __shfl_sync(full, mi, src);
+                win_set(w, cur_row, cur_m, lane);
+            }
+            int ok;
+            if (w.span) ok = row_count(buf, sj, smj, lane, w) >= cutoff;
+            else ok = warp_common<true>(cur_row, cur_m, sj, smj, cutoff, lane);
+            if (lane == src) acc = ok;
+            src = nsrc;
+            sj = nsj;
+            smj = nsmj;
+#pragma unroll
+            for (int u = 0; u < WIN_PF; ++u) buf[u] = nbuf[u];
+        }
+        if (cur_x >= 0) win_clear(w, cur_row, cur_m, lane);
+        if (acc) uf_union(parent, ri, rj);
         n_acc += __popc(__ballot_sync(full, acc != 0));
     }
     if (lane == 0) {
@@ -289,6 +418,20 @@ comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col
         if (n_acc) atomicAdd(stats + ST_ACCEPTED, n_acc);
         if (n_skip) atomicAdd(stats + ST_SKIPPED, n_skip);
     }
+}
+
+// above[i] = position of the first entry > i in row i (only needed when the sampling pass is off)
+__global__ void comp_above_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll row_begin,
+                                  ll row_end, int *__restrict__ above) {
+    ll i = row_begin + blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (i >= row_end) return;
+    const ll rb = row_ptr[i];
+    int l = 0, h = (int)(row_ptr[i + 1] - rb);
+    while (l < h) {
+        int mid = (l + h) >> 1;
+        if (col_idx[rb + mid] <= (int)i) l = mid + 1; else h = mid;
+    }
+    above[i] = l;
 }
 
 // merge step of the row-sharded multi-GPU run: union (i, other[i]) for each foreign parent array
@@ -303,33 +446,90 @@ __global__ void comp_merge_kernel(const int *__restrict__ others, ll n, ll count
 }
 
 // ---- count mode -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// |N(i) ∩ N(j)| for every candidate edge (SimilarityChecker._get semantics, no early exit).
+// One warp per row i: N(i) becomes the shared-memory window, every N(j) with j in N(i), j > i is
+// streamed through it (see above).  The row bounds of the 32 edges of a block are fetched by 32
+// lanes at once, the counts of the block are written with one coalesced store.  Rows are handed out
+// in small batches by an atomic counter: concurrently running warps work on neighbouring rows
+// (their N(j) overlap in L1/L2) and the heavy rows of dense regions do not serialise behind a static
+// partition.
+#define CNW_BATCH 4
+
+__global__ void __launch_bounds__(WIN_WARPS * 32)
 cn_count_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll n, ll n_member_cutoff,
-                unsigned *__restrict__ counts, unsigned long long *stats) {
+                unsigned *__restrict__ counts, unsigned long long *stats, unsigned long long *row_counter) {
+    __shared__ unsigned win_all[WIN_WARPS][WIN_BITS / 32];
+    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
-    ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
-    unsigned long long n_edges = 0;
-    for (ll i = warp; i < n; i += nwarps) {
-        ll b = row_ptr[i];
-        int m = (int)(row_ptr[i + 1] - b);
-        const int *row = col_idx + b;
-        bool core_i = m > n_member_cutoff;
-        for (int k = 0; k < m; ++k) {
-            int j = row[k];
-            unsigned out = 0xffffffffu;
-            if (core_i && j > (int)i) {
-                ll bj = row_ptr[j];
-                int mj = (int)(row_ptr[j + 1] - bj);
-                if (mj > n_member_cutoff) {
-                    out = (unsigned)warp_common<false>(row, m, col_idx + bj, mj, 0, lane);
-                    ++n_edges;
-                }
+    RowWin w;
+    w.bits = win_all[threadIdx.x >> 5];
+    w.first = 0;
+    w.span = 0;
+    for (int t = lane; t < WIN_BITS / 32; t += 32) w.bits[t] = 0;
+    __syncwarp();
+    unsigned long long n_edges = 0, n_fallback = 0;
+    for (;;) {
+        ll i0 = 0;
+        if (lane == 0) i0 = (ll)atomicAdd(row_counter, (unsigned long long)CNW_BATCH);
+        i0 = __shfl_sync(full, i0, 0);
+        if (i0 >= n) break;
+        const ll i1 = i0 + CNW_BATCH < n ? i0 + CNW_BATCH : n;
+        for (ll i = i0; i < i1; ++i) {
+            const ll b = row_ptr[i];
+            const int m = (int)(row_ptr[i + 1] - b);
+            const int *row = col_idx + b;
+            if (m <= n_member_cutoff) {  // not a core row (`_enough`): no slot of it is an edge
+                for (int k = lane; k < m; k += 32) counts[b + k] = 0xffffffffu;
+                continue;
             }
-            if (lane == 0) counts[b + k] = out;
+            win_set(w, row, m, lane);
+            if (!w.span) ++n_fallback;
+            for (int k0 = 0; k0 < m; k0 += 32) {
+                const int k = k0 + lane;
+                const int j = k < m ? row[k] : -1;
+                const bool valid = j > (int)i;
+                const ll bj = valid ? row_ptr[j] : 0;
+                const int mj = valid ? (int)(row_ptr[j + 1] - bj) : 0;
+                unsigned todo = __ballot_sync(full, valid && mj > n_member_cutoff);
+                unsigned out = 0xffffffffu;
+                n_edges += __popc(todo);
+                int buf[WIN_PF], nbuf[WIN_PF];
+                int src = -1, smj = 0;
+                const int *sj = nullptr;
+                if (todo) {
+                    src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    sj = col_idx + __shfl_sync(full, bj, src);
+                    smj = __shfl_sync(full, mj, src);
+                    if (w.span) row_prefetch(buf, sj, smj, lane);
+                }
+                while (src >= 0) {
+                    int nsrc = -1, nsmj = 0;
+                    const int *nsj = nullptr;
+                    if (todo) {
+                        nsrc = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        nsj = col_idx + __shfl_sync(full, bj, nsrc);
+                        nsmj = __shfl_sync(full, mj, nsrc);
+                        if (w.span) row_prefetch(nbuf, nsj, nsmj, lane);
+                    }
+                    const int c = w.span ? row_count(buf, sj, smj, lane, w) : warp_common<false>(row, m, sj, smj, 0, lane);
+                    if (lane == src) out = (unsigned)c;
+                    src = nsrc;
+                    sj = nsj;
+                    smj = nsmj;
+#pragma unroll
+                    for (int u = 0; u < WIN_PF; ++u) buf[u] = nbuf[u];
+                }
+                if (k < m) counts[b + k] = out;
+            }
+            win_clear(w, row, m, lane);
         }
     }
-    if (lane == 0 && n_edges) atomicAdd(stats + ST_EDGES, n_edges);
+    if (lane == 0) {
+        if (n_edges) atomicAdd(stats + ST_EDGES, n_edges);
+        if (n_fallback) atomicAdd(stats + ST_FALLBACK, n_fallback);
+    }
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -391,6 +591,8 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
     unsigned long long *stats = (unsigned long long *)ctx->b_stats.p;
     const int ns = ctx->n_samples < MAX_SAMPLES ? ctx->n_samples : MAX_SAMPLES;
     int *parent = ctx->b_parent.as<int>();
+    CNN_TRY(cnn_ensure(ctx, ctx->b_above, sizeof(int) * (size_t)ctx->n));
+    int *above = ctx->b_above.as<int>();
     if (ns > 0) {
         Span sp(ctx, T_COMP_SAMPLE);
         ll slots = rows * ns;
@@ -398,9 +600,12 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         int sblocks = (int)((rows + 255) / 256);
         if (sblocks > ctx->sm_count * 32) sblocks = ctx->sm_count * 32;
         comp_sample_kernel<<<sblocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, cutoff, ns, parent,
-                                                    ctx->b_edges.as<int>(), stats);
-        comp_union_kernel<<<cnn_blocks(slots, 256), 256, 0, st>>>(ctx->b_edges.as<int>(), row_begin, slots, ns, parent);
+                                                    ctx->b_edges.as<int>(), above, stats);
+        comp_union_kernel<<<cnn_blocks(rows, 256), 256, 0, st>>>(ctx->b_edges.as<int>(), row_begin, rows, ns, parent);
         CNN_LAUNCHED(ctx, 2);
+    } else {
+        comp_above_kernel<<<cnn_blocks(rows, 256), 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, above);
+        CNN_LAUNCHED(ctx, 1);
     }
     {
         Span sp(ctx, T_COMP_FLATTEN);
@@ -415,16 +620,17 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         CNN_CUDA(cudaMemsetAsync(wl_count, 0, sizeof(unsigned long long), st));
         int sblocks = (int)((rows + 255) / 256);
         if (sblocks > ctx->sm_count * 32) sblocks = ctx->sm_count * 32;
-        comp_scan_kernel<<<sblocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, parent,
+        comp_scan_kernel<<<sblocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, above, parent,
                                                   ctx->b_worklist.as<int2>(), wl_count, stats);
-        comp_worklist_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, ctx->b_worklist.as<int2>(),
-                                                               wl_count, cutoff, parent, stats);
+        comp_worklist_kernel<<<ctx->sm_count * 7, WIN_WARPS * 32, 0, st>>>(
+            ctx->row_ptr, ctx->col_idx, ctx->b_worklist.as<int2>(), wl_count, cutoff, parent, stats);
+        CNN_LAUNCHED(ctx, 2);
     }
     {
         Span sp(ctx, T_COMP_FLATTEN);
         comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(parent, ctx->n);
     }
-    CNN_LAUNCHED(ctx, 4);
+    CNN_LAUNCHED(ctx, 2);
     CNN_KERNEL_CHECK();
     return CNNB200_OK;
 }
@@ -463,13 +669,16 @@ extern "C" int cnnb200_cn_count(cnnb200_ctx *ctx, int64_t n_member_cutoff, uint3
         CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(unsigned) * (size_t)nnz));
         d_counts = ctx->b_tmp0.as<unsigned>();
     }
-    int blocks = (int)((n + 7) / 8);
-    int cap = ctx->sm_count * 8;
-    if (blocks > cap) blocks = cap;
+    // persistent grid: as many CTAs as fit (32 KB of window bitmaps each), rows handed out dynamically
+    int blocks = ctx->sm_count * 7;
+    ll want = (n + WIN_WARPS * CNW_BATCH - 1) / (WIN_WARPS * CNW_BATCH);
+    if (blocks > want) blocks = (int)want;
+    if (blocks < 1) blocks = 1;
+    unsigned long long *row_counter = (unsigned long long *)ctx->b_stats.p + ST_N - 1;
     {
         Span sp(ctx, T_CN_COUNT);
-        cn_count_kernel<<<blocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, n, n_member_cutoff, d_counts,
-                                                (unsigned long long *)ctx->b_stats.p);
+        cn_count_kernel<<<blocks, WIN_WARPS * 32, 0, st>>>(ctx->row_ptr, ctx->col_idx, n, n_member_cutoff, d_counts,
+                                                          (unsigned long long *)ctx->b_stats.p, row_counter);
         CNN_LAUNCHED(ctx, 1);
     }
     CNN_KERNEL_CHECK();

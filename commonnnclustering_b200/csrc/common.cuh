@@ -55,6 +55,7 @@ enum StatSlot {
     ST_SKIPPED = 3,
     ST_DIST = 4,
     ST_RECHECK = 5,
+    ST_FALLBACK = 6,  // count mode: rows whose index window did not fit the shared-memory bitmap
     ST_N = 8
 };
 
@@ -117,6 +118,7 @@ struct cnnb200_ctx {
     ll n_member_cutoff = 0, similarity_cutoff = 0;
     Buf b_parent;  // int32 [n]
     Buf b_core;    // uint8 [n]
+    Buf b_above;     // int32 [n]: position of the first entry > i in row i
     Buf b_edges;     // int32 [rows * samples]: edges accepted by the sampling pass
     Buf b_worklist;  // int2 [<= nnz/2]: candidate edges the scan could not settle
     Buf b_minorig, b_flags, b_rank, b_labels, b_consider, b_stats;

@@ -277,6 +277,27 @@ __device__ __forceinline__ int row_count(const int (&buf)[WIN_PF], const int *__
     return __reduce_add_sync(0xffffffffu, c);
 }
 
+// One streamed row in flight: where it is, which lane of the current 32-edge block it belongs to, and
+// its first WIN_PF chunks.  Three of them rotate (fetch two ahead, consume the oldest), so that two
+// memory round trips overlap the probing of one row.
+struct RowFetch {
+    int buf[WIN_PF];
+    const int *rj;
+    int mj;
+    int src;  // lane that owns the edge; -1: nothing fetched
+};
+
+// takes the next edge out of `todo` (bj / mj are the per-lane row bounds of the block's edges)
+__device__ __forceinline__ void fetch_next(RowFetch &f, unsigned &todo, const int *__restrict__ col_idx, ll bj, int mj,
+                                           bool windowed, int lane) {
+    if (!todo) { f.src = -1; return; }
+    f.src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    f.rj = col_idx + __shfl_sync(0xffffffffu, bj, f.src);
+    f.mj = __shfl_sync(0xffffffffu, mj, f.src);
+    if (windowed) row_prefetch(f.buf, f.rj, f.mj, lane);
+}
+
 // Edge scan.  Runs on flattened (root-pointing) parents, which do not change during this kernel:
 // a candidate edge (i < j, both core) is settled for free when parent[i] == parent[j]; the others
 // go to a work list.  A warp takes 32 consecutive rows (bounds, root and the position of the first
@@ -292,6 +313,7 @@ comp_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     unsigned long long n_edges = 0, n_need = 0;
+    constexpr int R = 4;  // chunks in flight per warp
     for (ll i0 = row_begin + warp * 32; i0 < row_end; i0 += nwarps * 32) {
         const ll il = i0 + lane;
         const int rl = il < row_end ? parent[il] : -1;
@@ -300,26 +322,46 @@ comp_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx
             el = row_ptr[il + 1];
             bl = row_ptr[il] + above[il];
         }
-        unsigned rows = __ballot_sync(full, rl >= 0 && bl < el);
-        while (rows) {
-            const int r = __ffs(rows) - 1;
-            rows &= rows - 1;
-            const int r_i = __shfl_sync(full, rl, r);
-            const ll beg = __shfl_sync(full, bl, r), end = __shfl_sync(full, el, r);
-            const int ii = (int)i0 + r;
-            for (ll k0 = beg; k0 < end; k0 += 32) {
-                const ll k = k0 + lane;
-                const int j = k < end ? col_idx[k] : -1;
-                const int pj = j >= 0 ? parent[j] : -1;
-                const bool cand = pj >= 0;
-                const bool need = cand && pj != r_i;
+        // the tile's work items are its (row, chunk of 32 entries) pairs; incl = inclusive prefix of the
+        // chunk counts, so item t belongs to row popc(ballot(incl <= t))
+        const int nch = (int)((el - bl + 31) >> 5);
+        int incl = nch;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int excl = incl - nch;
+        const int total = __shfl_sync(full, incl, 31);
+        for (int t0 = 0; t0 < total; t0 += R) {
+            int rr[R], r_i[R], jv[R], pjv[R];
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const int t = t0 + u;
+                rr[u] = -1;
+                jv[u] = -1;
+                if (t < total) {
+                    const int r = __popc(__ballot_sync(full, incl <= t));
+                    rr[u] = r;
+                    r_i[u] = __shfl_sync(full, rl, r);
+                    const ll k = __shfl_sync(full, bl, r) + 32 * (t - __shfl_sync(full, excl, r)) + lane;
+                    if (k < __shfl_sync(full, el, r)) jv[u] = col_idx[k];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < R; ++u) pjv[u] = jv[u] >= 0 ? parent[jv[u]] : -1;
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                if (rr[u] < 0) break;
+                const bool cand = pjv[u] >= 0;
+                const bool need = cand && pjv[u] != r_i[u];
                 const unsigned cm = __ballot_sync(full, cand), nm = __ballot_sync(full, need);
                 n_edges += __popc(cm);
                 if (nm) {
                     unsigned long long pos = 0;
                     if (lane == 0) pos = atomicAdd(wl_count, (unsigned long long)__popc(nm));
                     pos = __shfl_sync(full, pos, 0);
-                    if (need) worklist[pos + __popc(nm & lt)] = make_int2(ii, j);
+                    if (need) worklist[pos + __popc(nm & lt)] = make_int2((int)i0 + rr[u], jv[u]);
                     n_need += __popc(nm);
                 }
             }
@@ -371,43 +413,33 @@ comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col
         // software pipeline over the edges of `work`
         int cur_x = -1, cur_m = 0;
         const int *cur_row = nullptr;
-        int buf[WIN_PF], nbuf[WIN_PF];
-        int src = -1, smj = 0;
-        const int *sj = nullptr;
-        if (work) {
-            src = __ffs(work) - 1;
-            work &= work - 1;
-            sj = col_idx + __shfl_sync(full, bj, src);
-            smj = __shfl_sync(full, mj, src);
-            row_prefetch(buf, sj, smj, lane);
-        }
-        while (src >= 0) {
-            int nsrc = -1, nsmj = 0;
-            const int *nsj = nullptr;
-            if (work) {
-                nsrc = __ffs(work) - 1;
-                work &= work - 1;
-                nsj = col_idx + __shfl_sync(full, bj, nsrc);
-                nsmj = __shfl_sync(full, mj, nsrc);
-                row_prefetch(nbuf, nsj, nsmj, lane);
-            }
-            const int x = __shfl_sync(full, ed.x, src);
+        auto consume = [&](const RowFetch &f) {
+            const int x = __shfl_sync(full, ed.x, f.src);
             if (x != cur_x) {
                 if (cur_x >= 0) win_clear(w, cur_row, cur_m, lane);
                 cur_x = x;
-                cur_row = col_idx + __shfl_sync(full, bi, src);
-                cur_m = __shfl_sync(full, mi, src);
+                cur_row = col_idx + __shfl_sync(full, bi, f.src);
+                cur_m = __shfl_sync(full, mi, f.src);
                 win_set(w, cur_row, cur_m, lane);
             }
             int ok;
-            if (w.span) ok = row_count(buf, sj, smj, lane, w) >= cutoff;
-            else ok = warp_common<true>(cur_row, cur_m, sj, smj, cutoff, lane);
-            if (lane == src) acc = ok;
-            src = nsrc;
-            sj = nsj;
-            smj = nsmj;
-#pragma unroll
-            for (int u = 0; u < WIN_PF; ++u) buf[u] = nbuf[u];
+            if (w.span) ok = row_count(f.buf, f.rj, f.mj, lane, w) >= cutoff;
+            else ok = warp_common<true>(cur_row, cur_m, f.rj, f.mj, cutoff, lane);
+            if (lane == f.src) acc = ok;
+        };
+        RowFetch f0, f1, f2;
+        fetch_next(f0, work, col_idx, bj, mj, true, lane);
+        fetch_next(f1, work, col_idx, bj, mj, true, lane);
+        for (;;) {
+            if (f0.src < 0) break;
+            fetch_next(f2, work, col_idx, bj, mj, true, lane);
+            consume(f0);
+            if (f1.src < 0) break;
+            fetch_next(f0, work, col_idx, bj, mj, true, lane);
+            consume(f1);
+            if (f2.src < 0) break;
+            fetch_next(f1, work, col_idx, bj, mj, true, lane);
+            consume(f2);
         }
         if (cur_x >= 0) win_clear(w, cur_row, cur_m, lane);
         if (acc) uf_union(parent, ri, rj);
@@ -493,33 +525,25 @@ cn_count_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx,
                 unsigned todo = __ballot_sync(full, valid && mj > n_member_cutoff);
                 unsigned out = 0xffffffffu;
                 n_edges += __popc(todo);
-                int buf[WIN_PF], nbuf[WIN_PF];
-                int src = -1, smj = 0;
-                const int *sj = nullptr;
-                if (todo) {
-                    src = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    sj = col_idx + __shfl_sync(full, bj, src);
-                    smj = __shfl_sync(full, mj, src);
-                    if (w.span) row_prefetch(buf, sj, smj, lane);
-                }
-                while (src >= 0) {
-                    int nsrc = -1, nsmj = 0;
-                    const int *nsj = nullptr;
-                    if (todo) {
-                        nsrc = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        nsj = col_idx + __shfl_sync(full, bj, nsrc);
-                        nsmj = __shfl_sync(full, mj, nsrc);
-                        if (w.span) row_prefetch(nbuf, nsj, nsmj, lane);
-                    }
-                    const int c = w.span ? row_count(buf, sj, smj, lane, w) : warp_common<false>(row, m, sj, smj, 0, lane);
-                    if (lane == src) out = (unsigned)c;
-                    src = nsrc;
-                    sj = nsj;
-                    smj = nsmj;
-#pragma unroll
-                    for (int u = 0; u < WIN_PF; ++u) buf[u] = nbuf[u];
+                const bool windowed = w.span != 0;
+                auto consume = [&](const RowFetch &f) {
+                    const int c = windowed ? row_count(f.buf, f.rj, f.mj, lane, w)
+                                           : warp_common<false>(row, m, f.rj, f.mj, 0, lane);
+                    if (lane == f.src) out = (unsigned)c;
+                };
+                RowFetch f0, f1, f2;
+                fetch_next(f0, todo, col_idx, bj, mj, windowed, lane);
+                fetch_next(f1, todo, col_idx, bj, mj, windowed, lane);
+                for (;;) {
+                    if (f0.src < 0) break;
+                    fetch_next(f2, todo, col_idx, bj, mj, windowed, lane);
+                    consume(f0);
+                    if (f1.src < 0) break;
+                    fetch_next(f0, todo, col_idx, bj, mj, windowed, lane);
+                    consume(f1);
+                    if (f2.src < 0) break;
+                    fetch_next(f1, todo, col_idx, bj, mj, windowed, lane);
+                    consume(f2);
                 }
                 if (k < m) counts[b + k] = out;
             }
@@ -533,6 +557,17 @@ cn_count_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx,
 }
 
 // ---- host side ----------------------------------------------------------------------------------
+// resident CTAs per SM of a persistent kernel (grid = SMs x this), asked once per kernel
+template <typename K>
+static int resident_ctas(K kernel, int threads) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    return per_sm;
+}
+
 static int fetch_stats(cnnb200_ctx *ctx) {
     unsigned long long *h;
     CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
@@ -622,7 +657,8 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         if (sblocks > ctx->sm_count * 32) sblocks = ctx->sm_count * 32;
         comp_scan_kernel<<<sblocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, above, parent,
                                                   ctx->b_worklist.as<int2>(), wl_count, stats);
-        comp_worklist_kernel<<<ctx->sm_count * 7, WIN_WARPS * 32, 0, st>>>(
+        static const int wl_ctas = resident_ctas(comp_worklist_kernel, WIN_WARPS * 32);
+        comp_worklist_kernel<<<ctx->sm_count * wl_ctas, WIN_WARPS * 32, 0, st>>>(
             ctx->row_ptr, ctx->col_idx, ctx->b_worklist.as<int2>(), wl_count, cutoff, parent, stats);
         CNN_LAUNCHED(ctx, 2);
     }
@@ -670,7 +706,8 @@ extern "C" int cnnb200_cn_count(cnnb200_ctx *ctx, int64_t n_member_cutoff, uint3
         d_counts = ctx->b_tmp0.as<unsigned>();
     }
     // persistent grid: as many CTAs as fit (32 KB of window bitmaps each), rows handed out dynamically
-    int blocks = ctx->sm_count * 7;
+    static const int cn_ctas = resident_ctas(cn_count_kernel, WIN_WARPS * 32);
+    int blocks = ctx->sm_count * cn_ctas;
     ll want = (n + WIN_WARPS * CNW_BATCH - 1) / (WIN_WARPS * CNW_BATCH);
     if (blocks > want) blocks = (int)want;
     if (blocks < 1) blocks = 1;

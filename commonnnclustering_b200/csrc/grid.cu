@@ -70,13 +70,41 @@ __global__ void cell_id_kernel(const double *__restrict__ x, ll n, GridDesc g, i
     atomicAdd(&cell_count[cid], 1);
 }
 
-// gather coordinates into cell-sorted SoA: xs[k][p] = x[perm[p]][k]
-__global__ void gather_kernel(const double *__restrict__ x, const int *__restrict__ perm, ll n, int d,
-                              double *xs) {
+// Origin of cell index c along one axis.  The SAME expression is used wherever a cell-local
+// coordinate is formed, so that differences of cell-local coordinates are differences of the true
+// coordinates up to the stated rounding (see the filter kernel below).
+__device__ __forceinline__ double cell_origin(double lo, double h, int c) {
+    return __dadd_rn(lo, __dmul_rn((double)c, h));
+}
+
+// gather coordinates into cell-sorted SoA: xs[k][p] = x[perm[p]][k]; and the fp32 cell-local copy used by
+// the filter kernel: xf[p] = (x relative to lattice A, x relative to lattice B, y and z relative to the
+// point's own cell).  Lattices A and B have period 4 cells along x and are offset by 2 cells: any run of
+// up to 3 neighbouring cells lies inside one period of A or of B, so that all candidates of a run and
+// the query share one origin and their fp32 differences are accurate to ~2^-24 of 4h.
+__global__ void gather_kernel(const double *__restrict__ x, const int *__restrict__ perm,
+                              const int *__restrict__ cell_sorted, ll n, GridDesc g, double *xs, float4 *xf) {
     ll p = blockIdx.x * (ll)blockDim.x + threadIdx.x;
     if (p >= n) return;
+    const int d = g.d;
     ll src = perm[p];
-    for (int k = 0; k < d; ++k) xs[k * n + p] = x[src * d + k];
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int k = 0; k < d; ++k) {
+        v[k] = x[src * d + k];
+        xs[k * n + p] = v[k];
+    }
+    if (!xf) return;
+    const int c = cell_sorted[p];
+    const int cx = c % g.dims[0];
+    const int t = c / g.dims[0];
+    const int cy = t % g.dims[1];
+    const int cz = t / g.dims[1];
+    float4 f;
+    f.x = (float)__dsub_rn(v[0], cell_origin(g.lo[0], g.h, cx & ~3));
+    f.y = (float)__dsub_rn(v[0], cell_origin(g.lo[0], g.h, ((cx + 2) & ~3) - 2));
+    f.z = d > 1 ? (float)__dsub_rn(v[1], cell_origin(g.lo[1], g.h, cy)) : 0.f;
+    f.w = d > 2 ? (float)__dsub_rn(v[2], cell_origin(g.lo[2], g.h, cz)) : 0.f;
+    xf[p] = f;
 }
 
 // ---- K2: one warp per query row ---------------------------------------------------------------
@@ -176,6 +204,189 @@ grid_rows_kernel(const double *__restrict__ xs, ll n, const int *__restrict__ ce
     }
 }
 
+// ---- K2, fp32 filter form (the default single-pass kernel) ------------------------------------------------
+// Same tiles and groups as above (warp = 32 consecutive cell-sorted points, group = the points of one
+// cell), but the lanes hold CANDIDATES and the warp loops over the group's queries:
+//   * a chunk of 32 candidates of a run is loaded once (one coalesced float4 per lane: cell-local fp32
+//     coordinates) and tested against every query of the group, whose coordinates come out of shared
+//     memory as a broadcast; the result of (query, chunk) is one ballot word;
+//   * the test is an fp32 FILTER with a proven error bound: d2 <= R - eps is a neighbour, d2 > R + eps is
+//     not, and the (rare) pairs in between are decided by the reference's own f64 expression on the
+//     original coordinates (`within`), so the neighbour sets are exactly those of the f64 kernel.
+//     fp32 is accurate enough because all coordinates are relative to a nearby cell origin: with
+//     delta = h * 2^-20 bounding the error of every coordinate difference,
+//     |d2_fp32 - d2| <= 2*sqrt(3)*delta*sqrt(d2) + 3*delta^2 + 2^-22*d2 < eps = h*r*2^-18 + h^2*2^-38 + R*2^-21.
+//   * the ballot words of up to 32 chunks are parked in shared memory and then expanded by the lane
+//     that owns the query straight into its (gapped) row -- candidates ascend, so rows come out sorted.
+// Per 32 distance tests the loop issues ~13 instructions (one LDS.128, 6 FP32, 2 compares, 2 votes,
+// one STS) instead of ~47 (3 LDG.64, 9 FP64, ballot ranking, scattered store) in the f64 form.
+#define GF_WARPS 8
+#define GF_CHUNKS 32
+#define GF_LANE_PER_QUERY 14  // groups at least this large run one query per lane
+
+struct FilterParams {
+    float t_lo, t_hi;  // definite hit: d2 <= t_lo; definite miss: d2 > t_hi
+};
+
+template <int D, bool SQRT>
+__global__ void __launch_bounds__(GF_WARPS * 32)
+grid_rows_f32_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, ll n,
+                     const int *__restrict__ cell_sorted, const int *__restrict__ cell_start, GridDesc g, double rc,
+                     FilterParams fp, int *__restrict__ deg, const ll *__restrict__ goff, int *__restrict__ out,
+                     ll p_begin, ll p_end, unsigned long long *stats) {
+    __shared__ float4 s_q[GF_WARPS][32];
+    __shared__ unsigned s_words[GF_WARPS][GF_CHUNKS][32];
+    __shared__ int s_q0[GF_WARPS][GF_CHUNKS];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float4 *qf = s_q[wid];
+    unsigned(*words)[32] = s_words[wid];
+    int *chunk_q0 = s_q0[wid];
+    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    unsigned long long n_recheck = 0;
+    for (ll p0 = p_begin + warp * 32; p0 < p_end; p0 += nwarps * 32) {
+        const ll p = p0 + lane;
+        const bool pvalid = p < p_end;
+        const int cid = pvalid ? cell_sorted[p] : -1;
+        const float4 my4 = pvalid ? xf[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const ll my_base = pvalid ? goff[p] : 0;
+        unsigned todo = __ballot_sync(full, pvalid);
+        while (todo) {
+            const int a = __ffs(todo) - 1;  // first lane of the next group (groups are runs of lanes)
+            const int c = __shfl_sync(full, cid, a);
+            const unsigned grp = __ballot_sync(full, cid == c) & todo;
+            todo &= ~grp;
+            const int gsz = __popc(grp);
+            const int jme = lane - a;  // my query slot when I belong to the group
+            const bool mine = jme >= 0 && jme < gsz;
+            const int cx = c % g.dims[0];
+            const int t = c / g.dims[0];
+            const int cy = t % g.dims[1];
+            const int cz = t / g.dims[1];
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
+            const int y0 = D > 1 ? max(cy - 1, 0) : 0, y1 = D > 1 ? min(cy + 1, g.dims[1] - 1) : 0;
+            const int z0 = D > 2 ? max(cz - 1, 0) : 0, z1 = D > 2 ? min(cz + 1, g.dims[2] - 1) : 0;
+            const bool use_b = (x0 >> 2) != (x1 >> 2);  // the run straddles a period boundary of lattice A
+            // run bounds: one run per lane, fetched together
+            const int ny = y1 - y0 + 1, nruns = ny * (z1 - z0 + 1);
+            int rs = 0, re = 0;
+            float shy = 0.f, shz = 0.f;
+            if (lane < nruns) {
+                const int ry = y0 + lane % ny, rz = z0 + lane / ny;
+                const int cb = (rz * g.dims[1] + ry) * g.dims[0];
+                rs = cell_start[cb + x0];
+                re = cell_start[cb + x1 + 1];
+                // candidate coordinates of this run, moved to the query cell's origin
+                if (D > 1) shy = (float)__dsub_rn(cell_origin(g.lo[1], g.h, ry), cell_origin(g.lo[1], g.h, cy));
+                if (D > 2) shz = (float)__dsub_rn(cell_origin(g.lo[2], g.h, rz), cell_origin(g.lo[2], g.h, cz));
+            }
+            int cnt = 0;
+            if (gsz >= GF_LANE_PER_QUERY) {
+                // ---- big group: one query per lane; the chunk's candidates go through shared memory and
+                // are read back as broadcasts.  No votes, no ranking: a lane appends to its own row.
+                const float qx = use_b ? my4.y : my4.x, qy = my4.z, qz = my4.w;
+                for (int r = 0; r < nruns; ++r) {
+                    const int s = __shfl_sync(full, rs, r), e = __shfl_sync(full, re, r);
+                    const float sy = __shfl_sync(full, shy, r), sz = __shfl_sync(full, shz, r);
+                    for (int q0 = s; q0 < e; q0 += 32) {
+                        const int q = q0 + lane;
+                        const float4 c4 = q < e ? xf[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        __syncwarp();
+                        qf[lane] = make_float4(use_b ? c4.y : c4.x, c4.z + sy, c4.w + sz, 0.f);
+                        __syncwarp();
+                        const int nc = min(32, e - q0);
+#pragma unroll 4
+                        for (int tq = 0; tq < nc; ++tq) {
+                            const float4 cv = qf[tq];
+                            const float dx = qx - cv.x;
+                            float s2 = dx * dx;
+                            if (D > 1) { const float dy = qy - cv.y; s2 = fmaf(dy, dy, s2); }
+                            if (D > 2) { const float dz = qz - cv.z; s2 = fmaf(dz, dz, s2); }
+                            bool hit = s2 <= fp.t_lo;
+                            if (mine && s2 > fp.t_lo && s2 <= fp.t_hi) {  // borderline: the reference's own f64 test
+                                hit = within<D, SQRT>(xs[p], D > 1 ? xs[n + p] : 0.0, D > 2 ? xs[2 * n + p] : 0.0, xs, n,
+                                                      q0 + tq, rc);
+                                ++n_recheck;
+                            }
+                            if (hit && mine) out[my_base + cnt++] = q0 + tq;
+                        }
+                    }
+                }
+                if (mine) deg[p] = cnt;
+                continue;
+            }
+            // ---- small group: lanes hold candidates, the warp loops over the group's queries
+            __syncwarp();
+            if (mine) qf[jme] = make_float4(use_b ? my4.y : my4.x, my4.z, my4.w, 0.f);
+            __syncwarp();
+            int ncc = 0;
+            auto flush = [&]() {
+                __syncwarp();
+                if (mine)
+                    for (int cc = 0; cc < ncc; ++cc) {
+                        unsigned w = words[cc][jme];
+                        const int q0 = chunk_q0[cc];
+#pragma unroll 1
+                        while (w) {
+                            const int b = __ffs(w) - 1;
+                            w &= w - 1;
+                            out[my_base + cnt++] = q0 + b;
+                        }
+                    }
+                __syncwarp();
+                ncc = 0;
+            };
+            for (int r = 0; r < nruns; ++r) {
+                const int s = __shfl_sync(full, rs, r), e = __shfl_sync(full, re, r);
+                const float sy = __shfl_sync(full, shy, r), sz = __shfl_sync(full, shz, r);
+                for (int q0 = s; q0 < e; q0 += 32) {
+                    const int q = q0 + lane;
+                    const bool inb = q < e;
+                    const float4 c4 = inb ? xf[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float ccx = use_b ? c4.y : c4.x;
+                    const float ccy = c4.z + sy, ccz = c4.w + sz;
+                    auto step = [&](int jq) {
+                        const float4 qv = qf[jq];
+                        const float dx = qv.x - ccx;
+                        float s2 = dx * dx;
+                        if (D > 1) { const float dy = qv.y - ccy; s2 = fmaf(dy, dy, s2); }
+                        if (D > 2) { const float dz = qv.z - ccz; s2 = fmaf(dz, dz, s2); }
+                        const bool maybe = inb && s2 <= fp.t_hi;
+                        unsigned w = __ballot_sync(full, maybe);
+                        const bool band = maybe && s2 > fp.t_lo;
+                        if (__any_sync(full, band)) {
+                            // decide the borderline pairs exactly as the reference does
+                            bool res = false;
+                            if (band) {
+                                const ll pq = p0 + a + jq;
+                                res = within<D, SQRT>(xs[pq], D > 1 ? xs[n + pq] : 0.0, D > 2 ? xs[2 * n + pq] : 0.0, xs, n,
+                                                      q, rc);
+                                ++n_recheck;
+                            }
+                            const unsigned bm = __ballot_sync(full, band), rm = __ballot_sync(full, res);
+                            w = (w & ~bm) | rm;
+                        }
+                        if (lane == 0) words[ncc][jq] = w;
+                    };
+                    int jq = 0;
+                    for (; jq + 4 <= gsz; jq += 4) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) step(jq + u);
+                    }
+                    for (; jq < gsz; ++jq) step(jq);
+                    if (lane == 0) chunk_q0[ncc] = q0;
+                    if (++ncc == GF_CHUNKS) flush();
+                }
+            }
+            flush();
+            if (mine) deg[p] = cnt;
+        }
+    }
+    n_recheck = __reduce_add_sync(full, (unsigned)n_recheck);
+    if (lane == 0 && n_recheck) atomicAdd(stats, n_recheck);
+}
+
 // cap[p] = size of the candidate list of point p (all points of the 3^D cells around its cell)
 template <int D>
 __global__ void grid_cap_kernel(ll n, const int *__restrict__ cell_sorted, const int *__restrict__ cell_start,
@@ -234,7 +445,13 @@ int cnn_scan_deg_to_row_ptr(cnnb200_ctx *ctx, const int32_t *deg, ll n, ll *row_
     CNN_TRY(cnn_pinned(ctx, 64, &h));
     CNN_CUDA(cudaMemcpyAsync(h, row_ptr + n, sizeof(ll), cudaMemcpyDeviceToHost, ctx->stream));
     CNN_CUDA(cudaMemcpyAsync((char *)h + 8, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->grid_recheck_pending)  // pairs the fp32 filter handed to the exact test (counter next to d_max)
+        CNN_CUDA(cudaMemcpyAsync((char *)h + 16, ctx->b_tmp2.as<char>() + 40, sizeof(ll), cudaMemcpyDeviceToHost, ctx->stream));
     CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->grid_recheck_pending) {
+        ctx->stats[ST_RECHECK] = *(ll *)((char *)h + 16);
+        ctx->grid_recheck_pending = false;
+    }
     *nnz_out = *(ll *)h;
     *max_deg_out = *(int *)((char *)h + 8);
     return CNNB200_OK;
@@ -261,6 +478,52 @@ static int launch_rows(cnnb200_ctx *ctx, ll pb, ll pe, int mode, int *deg, const
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     return CNNB200_OK;
+}
+
+// thresholds of the fp32 filter (see grid_rows_f32_kernel); false when fp32 cannot represent the problem
+static bool filter_params(const cnnb200_ctx *ctx, FilterParams *fp) {
+    const double h = ctx->grid.h;
+    if (!(h > 1e-12 && h < 1e12)) return false;
+    const double R = ctx->grid_metric == CNNB200_METRIC_EUCLIDEAN ? ctx->grid_rc * ctx->grid_rc : ctx->grid_rc;
+    const double r = sqrt(R);
+    const double eps = ldexp(h * r, -18) + ldexp(h * h, -38) + ldexp(R, -21);
+    const double lo = R - eps, hi = R + eps;
+    float flo = (float)lo, fhi = (float)hi;
+    if ((double)flo > lo) flo = nextafterf(flo, -INFINITY);
+    if ((double)fhi < hi) fhi = nextafterf(fhi, INFINITY);
+    if (!isfinite(flo) || !isfinite(fhi)) return false;
+    fp->t_lo = flo;
+    fp->t_hi = fhi;
+    return true;
+}
+
+template <int D, bool SQRT>
+static int launch_rows_f32(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg, const ll *offsets, int *out) {
+    int blocks = (int)((pe - pb + GF_WARPS * 32 - 1) / (GF_WARPS * 32));
+    int cap = ctx->sm_count * 48;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    unsigned long long *recheck = (unsigned long long *)(ctx->b_tmp2.as<char>() + 40);
+    CNN_CUDA(cudaMemsetAsync(recheck, 0, sizeof(unsigned long long), ctx->stream));
+    grid_rows_f32_kernel<D, SQRT><<<blocks, GF_WARPS * 32, 0, ctx->stream>>>(
+        ctx->b_xs.as<double>(), ctx->b_xf.as<float4>(), ctx->grid_n, ctx->b_cell_id_sorted.as<int>(),
+        ctx->b_cell_start.as<int>(), ctx->grid, ctx->grid_rc, fp, deg, offsets, out, pb, pe, recheck);
+    CNN_LAUNCHED(ctx, 1);
+    CNN_KERNEL_CHECK();
+    ctx->grid_recheck_pending = true;
+    return CNNB200_OK;
+}
+
+static int launch_rows_f32_any(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg, const ll *offsets, int *out) {
+    bool sq = ctx->grid_metric == CNNB200_METRIC_EUCLIDEAN;
+    switch (ctx->grid.d * 2 + (sq ? 1 : 0)) {
+        case 2: return launch_rows_f32<1, false>(ctx, pb, pe, fp, deg, offsets, out);
+        case 3: return launch_rows_f32<1, true>(ctx, pb, pe, fp, deg, offsets, out);
+        case 4: return launch_rows_f32<2, false>(ctx, pb, pe, fp, deg, offsets, out);
+        case 5: return launch_rows_f32<2, true>(ctx, pb, pe, fp, deg, offsets, out);
+        case 6: return launch_rows_f32<3, false>(ctx, pb, pe, fp, deg, offsets, out);
+        default: return launch_rows_f32<3, true>(ctx, pb, pe, fp, deg, offsets, out);
+    }
 }
 
 static int launch_rows_any(cnnb200_ctx *ctx, ll pb, ll pe, int mode, int *deg, const ll *offsets, int *out) {
@@ -366,8 +629,9 @@ int cnn_grid_build(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radiu
     cap = ctx->b_cub.cap;
     CNN_CUDA(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, cap, cell_count, ctx->b_cell_start.as<int>(),
                                            (int)(ncell + 1), st));
-    gather_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_x, ctx->b_perm.as<int>(), n, (int)d,
-                                                        ctx->b_xs.as<double>());
+    CNN_TRY(cnn_ensure(ctx, ctx->b_xf, sizeof(float4) * (size_t)n));
+    gather_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_x, ctx->b_perm.as<int>(), ctx->b_cell_id_sorted.as<int>(), n, g,
+                                                        ctx->b_xs.as<double>(), ctx->b_xf.as<float4>());
     CNN_LAUNCHED(ctx, 1);
     // candidate-list sizes (the cell ids in input order are dead after the sort: reuse that buffer)
     // and their prefix = offsets of the gapped rows / the work measure used to balance row blocks
@@ -408,7 +672,12 @@ int cnn_grid_rows(cnnb200_ctx *ctx, ll pb, ll pe, int *deg) {
     if (ctx->blk_single) {
         CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(int) * (size_t)gapped));
         // row p writes at gapped[goff[p] - g0 ...]: shift the base pointer instead of the offsets
-        CNN_TRY(launch_rows_any(ctx, pb, pe, 2, deg, goff, ctx->b_tmp0.as<int>() - g0));
+        FilterParams fp;
+        CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
+        if (ctx->use_filter && filter_params(ctx, &fp))
+            CNN_TRY(launch_rows_f32_any(ctx, pb, pe, fp, deg, goff, ctx->b_tmp0.as<int>() - g0));
+        else
+            CNN_TRY(launch_rows_any(ctx, pb, pe, 2, deg, goff, ctx->b_tmp0.as<int>() - g0));
     } else {
         CNN_TRY(launch_rows_any(ctx, pb, pe, 0, deg, nullptr, nullptr));
     }

@@ -27,15 +27,15 @@ r, c = 0.09, 20
 xd = torch.from_numpy(x).cuda()
 labd = torch.empty(n, dtype=torch.int64, device="cuda")
 ref = np.load("gpurun_out/c2_labels.npy") if os.path.exists("gpurun_out/c2_labels.npy") and n == 1000000 else None
-for edge_pass in os.environ.get("EDGE_PASSES", "1,0").split(","):
-    os.environ["CNNB200_EDGE_PASS"] = edge_pass
+for edge_pass in os.environ.get("FILTERS", "0,1").split(","):
+    os.environ["CNNB200_FILTER"] = edge_pass
     ctx = _lib.Context(0)
     ctx.set_timing(True)
     for it in range(4):
         ctx.fit_points(xd, r * r, c + 1, c + 2, labd, member_cutoff=10)
         t, launches = ctx.timings()
         if it:
-            print("edge_pass", edge_pass, {k: round(v[0], 3) for k, v in t.items() if v[1]}, "total", round(sum(v[0] for v in t.values()), 3), ctx.stats(), flush=True)
+            print("filter", edge_pass, {k: round(v[0], 3) for k, v in t.items() if v[1]}, "total", round(sum(v[0] for v in t.values()), 3), ctx.stats(), flush=True)
     if ref is None:
         ref = labd.cpu().numpy()
     else:

@@ -119,6 +119,52 @@ def test_neighbour_sets_equal_brute_force(ctx, maker, r, metric, method):
     np.testing.assert_array_equal(ci, want_ci)
 
 
+@pytest.mark.parametrize("name,maker,r,metric", [
+    # coordinates far from the origin: the fp32 filter works on cell-local coordinates, so a large offset
+    # must change nothing (the f64 test itself loses bits: many pairs land exactly on the cutoff)
+    ("offset3d", lambda: cases.gauss(3000, 3, 21) * 0.2 + 1.0e6, 0.05, "euclidean_r"),
+    ("offset2d", lambda: cases.gauss(3000, 2, 22) * 0.2 - 3.0e7, 0.03, "euclidean"),
+    # lattice with every distance a tie, shifted off the origin
+    ("lattice_shifted", lambda: cases.lattice(1000, 3, 23) + 1234.5, 0.25, "euclidean_r"),
+    # duplicates and a dense clump inside a sparse box (coarse cells, long candidate runs)
+    ("duplicates", lambda: np.repeat(cases.gauss(400, 3, 24), 5, axis=0), 0.3, "euclidean_r"),
+    ("clump", lambda: np.concatenate([cases.gauss(2500, 3, 25) * 1e-3, cases.gauss(50, 3, 26) * 1e3]), 1e-3,
+     "euclidean_r"),
+    # tiny and huge scales
+    ("tiny", lambda: cases.gauss(2000, 3, 27) * 1e-9, 3e-10, "euclidean_r"),
+    ("huge", lambda: cases.gauss(2000, 2, 28) * 1e9, 2e8, "euclidean"),
+    ("one_dim", lambda: cases.gauss(5000, 1, 29), 0.01, "euclidean_r"),
+])
+def test_filter_kernel_neighbour_sets_are_exact(ctx, name, maker, r, metric):
+    """The single-pass cell-list kernel tests in fp32 and re-decides borderline pairs in f64
+    (grid.cu, grid_rows_f32_kernel): its neighbour sets must equal the reference's f64 test."""
+    x = np.ascontiguousarray(maker(), dtype=np.float64)
+    rc = port.adjust_radius(r, metric)
+    want_rp, want_ci = port.neighbours(x, rc, metric, method="brute")
+    ctx.neighbours_from_points(x, rc, metric=metric, method="grid")
+    rp, ci = ctx.neighbours_export()
+    np.testing.assert_array_equal(rp, want_rp)
+    np.testing.assert_array_equal(ci, want_ci)
+
+
+def test_filter_kernel_equals_f64_kernel_on_c2_sample(ctx):
+    """Same CSR from the fp32-filter kernel and from the all-f64 kernel (CNNB200_FILTER=0)."""
+    import os
+    x = datasets.md_like_3d(200_000)
+    ctx.neighbours_from_points(x, 0.12 ** 2)
+    a = ctx.neighbours_export()
+    assert ctx.stats()["distance_evals"] > 0
+    os.environ["CNNB200_FILTER"] = "0"
+    try:
+        ctx2 = _lib.Context(0)
+    finally:
+        del os.environ["CNNB200_FILTER"]
+    ctx2.neighbours_from_points(x, 0.12 ** 2)
+    b = ctx2.neighbours_export()
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+
+
 def test_neighbour_search_high_dim_and_odd_sizes(ctx):
     for n, d in [(1, 3), (2, 2), (63, 7), (65, 17), (257, 33), (130, 64)]:
         x = cases.gauss(n, d, n + d)

@@ -32,6 +32,7 @@ SIGNATURES = {
     "cnnb200_neighbours_from_points": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int, C.c_int, C.POINTER(_I64)],
     "cnnb200_grid_begin": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int],
     "cnnb200_grid_balance": [_P, C.c_int, _P],
+    "cnnb200_grid_halo": [_P, _I64, _I64, C.POINTER(_I64), C.POINTER(_I64)],
     "cnnb200_grid_degrees": [_P, _I64, _I64, _P],
     "cnnb200_grid_fill": [_P, _I64, _I64, _P, _P],
     "cnnb200_neighbours_adopt": [_P, _P, _P, _I64, _I64, _I64, C.c_int],
@@ -190,6 +191,11 @@ class Context:
         b = np.zeros(parts + 1, dtype=np.int64)
         check(self._lib.cnnb200_grid_balance(self._h, int(parts), b.ctypes.data))
         return b
+
+    def grid_halo(self, row_begin, row_end):
+        lo, hi = _I64(), _I64()
+        check(self._lib.cnnb200_grid_halo(self._h, int(row_begin), int(row_end), C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
 
     def grid_degrees(self, row_begin, row_end, deg):
         p, loc = _ptr_loc(deg)

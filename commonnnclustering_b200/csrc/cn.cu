@@ -466,6 +466,19 @@ __global__ void comp_above_kernel(const ll *__restrict__ row_ptr, const int *__r
     above[i] = l;
 }
 
+// A rank that built only the rows around its block sees every other row as empty, hence not core.
+// Before merging, rows that ANY rank reports as core (parent >= 0) become singleton trees here too.
+__global__ void comp_adopt_core_kernel(const int *__restrict__ others, ll n, ll count, int *parent, uint8_t *core) {
+    ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (i >= n || parent[i] >= 0) return;
+    for (ll g = 0; g < count; ++g)
+        if (others[g * n + i] >= 0) {
+            parent[i] = (int)i;
+            core[i] = 1;
+            return;
+        }
+}
+
 // merge step of the row-sharded multi-GPU run: union (i, other[i]) for each foreign parent array
 __global__ void comp_merge_kernel(const int *__restrict__ others, ll n, ll count, int *parent) {
     ll t = blockIdx.x * (ll)blockDim.x + threadIdx.x;
@@ -684,7 +697,9 @@ extern "C" int cnnb200_components_merge(cnnb200_ctx *ctx, const int32_t *others,
     if (count < 1) return CNNB200_OK;
     CNN_CUDA(cudaSetDevice(ctx->device));
     Span sp(ctx, T_COMP_FLATTEN);
-    CNN_LAUNCHED(ctx, 2);
+    CNN_LAUNCHED(ctx, 3);
+    comp_adopt_core_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, ctx->stream>>>(others, ctx->n, count, ctx->b_parent.as<int>(),
+                                                                           ctx->b_core.as<uint8_t>());
     comp_merge_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(others, ctx->n, count, ctx->b_parent.as<int>());
     comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->b_parent.as<int>(), ctx->n);
     CNN_KERNEL_CHECK();

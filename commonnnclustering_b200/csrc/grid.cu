@@ -780,6 +780,39 @@ extern "C" int cnnb200_grid_balance(cnnb200_ctx *ctx, int parts, int64_t *bounds
     return CNNB200_OK;
 }
 
+// Rows whose neighbourhoods a rank needs in order to settle the candidate edges of its row block
+// [row_begin, row_end): the block itself plus every row that can occur in one of its neighbour lists.
+// In the cell-sorted order that is one contiguous range -- from the first point of the lowest cell
+// adjacent to the block's first cell to the last point of the highest cell adjacent to its last cell.
+extern "C" int cnnb200_grid_halo(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end, int64_t *lo, int64_t *hi) {
+    if (!ctx || !lo || !hi) CNN_FAIL(CNNB200_E_INVALID, "grid_halo: NULL argument");
+    if (!ctx->have_grid) CNN_FAIL(CNNB200_E_STATE, "grid_halo: call grid_begin first");
+    const ll n = ctx->grid_n;
+    if (row_begin < 0 || row_end > n || row_begin > row_end) CNN_FAIL(CNNB200_E_INVALID, "grid_halo: bad row range");
+    if (row_begin == row_end) { *lo = *hi = row_begin; return CNNB200_OK; }
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const GridDesc &g = ctx->grid;
+    const ll ncell = (ll)g.dims[0] * g.dims[1] * g.dims[2];
+    int *h;
+    CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
+    const int *cs = ctx->b_cell_id_sorted.as<int>(), *cst = ctx->b_cell_start.as<int>();
+    CNN_CUDA(cudaMemcpyAsync(h, cs + row_begin, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaMemcpyAsync(h + 1, cs + row_end - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaStreamSynchronize(st));
+    // cell ids are x-fastest: the window of cell id c lies within [c - reach, c + reach]
+    const ll reach = (g.d > 2 ? (ll)g.dims[0] * g.dims[1] : 0) + (g.d > 1 ? g.dims[0] : 0) + 1;
+    ll c_lo = (ll)h[0] - reach, c_hi = (ll)h[1] + reach + 1;
+    if (c_lo < 0) c_lo = 0;
+    if (c_hi > ncell) c_hi = ncell;
+    CNN_CUDA(cudaMemcpyAsync(h + 2, cst + c_lo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaMemcpyAsync(h + 3, cst + c_hi, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaStreamSynchronize(st));
+    *lo = h[2] < row_begin ? h[2] : row_begin;
+    *hi = h[3] > row_end ? h[3] : row_end;
+    return CNNB200_OK;
+}
+
 extern "C" int cnnb200_grid_degrees(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end, int32_t *deg) {
     if (!ctx || !deg) CNN_FAIL(CNNB200_E_INVALID, "grid_degrees: NULL argument");
     if (!ctx->have_grid) CNN_FAIL(CNNB200_E_STATE, "grid_degrees: call grid_begin first");

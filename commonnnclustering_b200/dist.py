@@ -3,9 +3,11 @@ plumbing (NCCL on the box, gloo in the CPU tests).  SURVEY.md section 8(e):
 
 * coordinates are replicated, query rows (points in cell-sorted order) are split into contiguous
   blocks that balance the number of candidate pairs;
-* exchange 1 -- the CSR: degrees by an all-reduce of the row-indexed int32 array (each rank fills
-  only its block), then every rank writes its rows straight into its slice of the gathered
-  ``col_idx`` buffer and the slices are broadcast (variable sizes);
+* coordinates input: no CSR exchange at all -- every rank searches its block plus the halo of rows its
+  block's neighbour lists refer to (contiguous in the cell-sorted order); rows outside stay empty;
+* precomputed neighbourhoods (and ``exchange=True``): exchange 1 -- the CSR: degrees by an all-reduce
+  of the row-indexed int32 array (each rank fills only its block), then every rank writes its rows
+  straight into its slice of the gathered ``col_idx`` buffer and the slices are broadcast;
 * every rank settles the candidate edges of its own row block on a private parent array;
 * exchange 2 -- the parent arrays: all-gather of ``G x N`` int32, then each rank unions
   ``(i, parent_g[i])`` for all g.  Hooking always goes towards the smaller root, so the merged
@@ -82,13 +84,30 @@ class ShardedFit:
         self.last = {}
 
     # -- neighbourhoods from coordinates, rows sharded ---------------------------------------------
-    def neighbours_from_points(self, x, radius_cutoff, metric="euclidean_r"):
+    def neighbours_from_points(self, x, radius_cutoff, metric="euclidean_r", exchange=False):
+        """Coordinates are replicated, so a rank can build every row it will ever read by itself: its
+        row block plus the halo of rows that occur in the block's neighbour lists (one contiguous range
+        of the cell-sorted order, ``grid_halo``).  No CSR travels; rows outside the range stay empty.
+        ``exchange=True`` builds the block only and all-gathers the CSR instead (the layout used for
+        precomputed neighbourhoods, kept for comparison)."""
         ctx, G = self.ctx, self.world
         n = x.shape[0]
         ctx.grid_begin(x, radius_cutoff, metric)          # replicated: every rank sorts all points
         bounds = ctx.grid_balance(G)                      # identical on every rank (same data)
         b, e = block_of(bounds, self.rank)
         deg = torch.zeros(n + 1, dtype=torch.int32, device=self.device)
+        if not exchange:
+            lo, hi = ctx.grid_halo(b, e)
+            ctx.grid_degrees(lo, hi, deg)
+            row_ptr = torch.zeros(n + 1, dtype=torch.int64, device=self.device)
+            torch.cumsum(deg[:-1], 0, dtype=torch.int64, out=row_ptr[1:])
+            host = torch.stack([row_ptr[-1], deg.max().to(torch.int64)]).cpu().numpy()
+            nnz, max_deg = int(host[0]), int(host[1])
+            col_idx = torch.empty(max(nnz, 1), dtype=torch.int32, device=self.device)[:nnz]
+            ctx.grid_fill(lo, hi, row_ptr, col_idx)
+            ctx.neighbours_adopt(row_ptr, col_idx, max_deg, grid_perm=True)
+            self.last = dict(bounds=bounds, halo=(lo, hi), nnz=nnz)
+            return bounds
         ctx.grid_degrees(b, e, deg)
         row_ptr = exchange_degrees(deg, self.group)
         bt = torch.as_tensor(bounds, device=self.device)
@@ -147,7 +166,7 @@ class ShardedFit:
         return n_clusters
 
     def fit_points(self, x, radius_cutoff, n_member_cutoff, similarity_cutoff, labels, current_start=1,
-                   metric="euclidean_r", sort_by_size=True, member_cutoff=None, max_clusters=None, **_):
-        bounds = self.neighbours_from_points(x, radius_cutoff, metric)
+                   metric="euclidean_r", sort_by_size=True, member_cutoff=None, max_clusters=None, exchange=False, **_):
+        bounds = self.neighbours_from_points(x, radius_cutoff, metric, exchange=exchange)
         return self.fit(bounds, n_member_cutoff, similarity_cutoff, labels, current_start, sort_by_size,
                         member_cutoff, max_clusters)

@@ -96,6 +96,10 @@ int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x, int loc, i
  * query rows sharded).  Rows are the points in cell-sorted order.
  *   grid_begin    every rank: grid geometry, sort by cell, candidate-list prefix
  *   grid_balance  row-block boundaries bounds[0..parts] (HOST) that balance the candidate pairs
+ *   grid_halo     [lo, hi) = the block plus every row that can occur in a neighbour list of the block
+ *                 (contiguous in the cell-sorted order).  A rank that searches [lo, hi) itself holds all
+ *                 rows its block's common-neighbour checks read and needs no CSR exchange at all
+ *                 (rows outside get degree 0; cnnb200_components_merge adopts their core flags).
  *   grid_degrees  this rank's block: deg[row_begin..row_end) (DEVICE int32, indexed by row)
  *   (all ranks exchange the degrees; row_ptr = exclusive prefix sum over all rows)
  *   grid_fill     this rank's block written into col_idx at row_ptr[row] (DEVICE buffers that
@@ -107,6 +111,7 @@ int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x, int loc, i
 int cnnb200_grid_begin(cnnb200_ctx *ctx, const double *x, int loc, int64_t n, int64_t d,
                        double radius_cutoff, int metric);
 int cnnb200_grid_balance(cnnb200_ctx *ctx, int parts, int64_t *bounds);
+int cnnb200_grid_halo(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end, int64_t *lo, int64_t *hi);
 int cnnb200_grid_degrees(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end, int32_t *deg);
 int cnnb200_grid_fill(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end, const int64_t *row_ptr,
                       int32_t *col_idx);
@@ -180,7 +185,8 @@ int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_en
 /* Device pointer to the int32 [n] parent array (internal index space). */
 int cnnb200_components_parents(cnnb200_ctx *ctx, int32_t **parents);
 /* Unions (i, other[i]) for every i of `count` foreign parent arrays laid out back to back
- * (int32 [count, n], DEVICE). */
+ * (int32 [count, n], DEVICE).  A row some rank reports as a core point (other[i] >= 0) that this
+ * context holds as empty (halo construction) becomes a core point here as well. */
 int cnnb200_components_merge(cnnb200_ctx *ctx, const int32_t *others, int64_t count);
 int cnnb200_components_labels(cnnb200_ctx *ctx, int64_t current_start, int64_t *labels, int loc,
                               int fresh, int64_t *n_clusters_out);

@@ -25,6 +25,9 @@ for n, r, c, mc in [(20000, 0.25, 10, None), (300000, 0.13, 20, 10)]:
     single = np.empty(n, dtype=np.int64)
     _lib.Context(local).fit_points(x, r * r, c + 1, c + 2, single, member_cutoff=mc)
     same = np.array_equal(lab, single)
+    lab_x = np.empty(n, dtype=np.int64)
+    sf.fit_points(x, r * r, c + 1, c + 2, lab_x, member_cutoff=mc, exchange=True)   # CSR all-gather layout
+    same &= np.array_equal(lab_x, single)
     if n <= 20000:
         from oracle import port
         same &= np.array_equal(lab, port.fit_points(x, r, c, member_cutoff=mc))

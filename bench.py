@@ -170,33 +170,85 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # this repository's arm
 # ------------------------------------------------------------------------------------------------
-def stage_rooflines(timings, steps, n, d, nnz, stats, peak):
+def ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the hand-written kernels, from
+    the committed `ncu --set full` capture of this workload (profiles/ncu_traffic.json, written by
+    scripts/ncu_summary.py); {} when there is none."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return {}
+    with open(path) as fp:
+        return json.load(fp).get("kernels", {})
+
+
+def stage_rooflines(timings, steps, n, d, nnz, stats, peak, count_mode=None):
     """Algorithmic bytes per launch (SURVEY.md 8d / DESIGN.md) over the measured mean duration."""
-    def entry(stage, kernel, nbytes, note):
+    traffic = ncu_traffic()
+
+    def entry(stage, kernels, nbytes, note, bound_by):
         ms, calls = timings[stage]
         if calls == 0 or ms <= 0:
             return None
         dur = ms / calls
         ach = nbytes / (dur * 1e-3) / 1e9
-        return {"kernel": kernel, "stage": stage, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "ms_per_launch": dur, "algorithmic_bytes": nbytes, "note": note}
+        tr = [traffic.get(k, {}).get("dram_bytes") for k in kernels]
+        return {"kernel": " + ".join(kernels), "stage": stage, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": sum(tr) if all(t is not None for t in tr) else None,
+                "ms_per_launch": dur, "algorithmic_bytes": nbytes, "limited_by": bound_by, "note": note}
 
-    gapped = timings["search_fill"][0] < 0.5 * timings["search_count"][0]  # single-pass search + compaction
+    cand, unsettled = stats["candidate_edges"], stats["candidate_edges"] - stats["skipped"]
     out = [
-        entry("search_count", "grid_rows_kernel<single pass>" if gapped else "grid_rows_kernel<count>",
-              8 * d * n + 4 * n + (4 * nnz if gapped else 0),
-              "8*D*N coords in + 4*N degrees out" + (" + 4*nnz hits out (gapped rows)" if gapped else "")),
-        entry("search_fill", "compact_rows_kernel" if gapped else "grid_rows_kernel<fill>",
-              (8 * nnz + 16 * (n + 1)) if gapped else (8 * d * n + 4 * nnz + 8 * (n + 1)),
-              "4*nnz in + 4*nnz out + 16*(N+1) offsets" if gapped else "8*D*N coords in + 4*nnz col_idx out + 8*(N+1) row_ptr in"),
-        entry("comp_edges", "comp_scan_kernel + comp_worklist_kernel",
-              4 * nnz + 8 * (n + 1) + 4 * n + 4 * stats["candidate_edges"] + 8 * (stats["candidate_edges"] - stats["skipped"]),
-              "CSR scanned once (4*nnz + 8*(N+1)) + 4*N parents + one 4-byte parent look-up per candidate edge + 8 B per "
-              "work-list entry; rows re-read by the executed CN checks are not counted"),
-        entry("comp_sample", "comp_sample_kernel + comp_union_kernel", 8 * (n + 1) + 4 * n + 2 * 4 * n,
-              "row_ptr + parents + the sampled edge slots; rows read by the executed CN checks are not counted"),
+        entry("search_count", ["grid_rows_f32_kernel"], 8 * d * n + 16 * n + 4 * n + 4 * nnz,
+              "coords in (f64 for the exact recheck + float4 cell-local copy) + 4*N degrees out + 4*nnz hits out (gapped rows)",
+              "issue slots: ~450 distance tests per point; the compulsory bytes are small (see DESIGN.md 4)"),
+        entry("search_fill", ["compact_rows_kernel"], 8 * nnz + 16 * (n + 1), "4*nnz in + 4*nnz out + 16*(N+1) offsets", "HBM"),
+        entry("comp_sample", ["comp_sample_kernel", "comp_union_kernel"], 8 * (n + 1) + 4 * n + 2 * 4 * n + 4 * n,
+              "row_ptr + parents + the sampled edge slots + first-above positions; rows read by the executed CN checks "
+              "are not counted", "memory latency (dependent row look-ups, union-find chains)"),
+        entry("comp_edges", ["comp_scan_kernel", "comp_worklist_kernel"],
+              2 * nnz + 8 * (n + 1) + 8 * n + 4 * cand + 16 * unsettled,
+              "upper half of every core row (about 2*nnz bytes) + row_ptr + parents + first-above positions + one 4-byte "
+              "parent look-up per candidate edge + 8 B written and read per work-list entry; rows re-read by the "
+              "executed CN checks are not counted", "memory latency (scan) / issue slots (work list)"),
     ]
+    if count_mode:
+        ms, nb, edges = count_mode
+        tr = traffic.get("cn_count_kernel", {}).get("dram_bytes")
+        out.append({"kernel": "cn_count_kernel", "stage": "cn_count (count mode: every candidate edge, no early exit; not part "
+                    "of the timed fit step)", "bound": "hbm", "achieved": nb / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": nb / (ms * 1e-3) / 1e9 / peak, "traffic": tr, "ms_per_launch": ms, "algorithmic_bytes": nb,
+                    "limited_by": "issue slots (one shared-memory probe per streamed entry)", "cn_checks_per_s": edges / (ms * 1e-3),
+                    "note": "no-reuse model of SURVEY 8d: 4*sum over candidate edges of (deg_i + deg_j) + 8 B per edge; the rows "
+                            "are in fact served from L1/L2 (N(i) sits in a shared-memory bitmap), so `traffic` is close to the "
+                            "compulsory 4*nnz in + 4*nnz out"})
     return [e for e in out if e]
+
+
+def count_mode_bytes(ctx, n_member_cutoff):
+    """SURVEY 8d's algorithmic bytes of count mode for the CSR the context holds (computed on the device)."""
+    import torch
+
+    from commonnnclustering_b200 import dist as cdist
+
+    n, nnz, _ = ctx.neighbours_info()
+    rp_ptr, ci_ptr, _ = ctx.neighbours_device_view()
+    dev = torch.device("cuda", ctx.device)
+    rp = cdist.tensor_from_ptr(rp_ptr, (n + 1,), "<i8", dev)
+    ci = cdist.tensor_from_ptr(ci_ptr, (nnz,), "<i4", dev)
+    deg = rp[1:] - rp[:-1]
+    core = deg > n_member_cutoff
+    total = 0
+    edges = 0
+    step = 1 << 17  # rows per slab keeps the temporaries small
+    for b in range(0, n, step):
+        e = min(n, b + step)
+        s0, s1 = int(rp[b]), int(rp[e])
+        rows = torch.repeat_interleave(torch.arange(b, e, device=dev), deg[b:e])
+        cols = ci[s0:s1].long()
+        m = (cols > rows) & core[rows] & core[cols]
+        total += int((deg[rows][m] + deg[cols][m]).sum())
+        edges += int(m.sum())
+    return 4 * total + 8 * edges, edges
 
 
 def run_b200(args):
@@ -323,14 +375,34 @@ def run_b200(args):
                "fitter_points_per_s": n / cl.summary[-1].execution_time}
         assert np.array_equal(cl.labels, lab_dev)
 
-    roofs = stage_rooflines(timings, args.steps, n, d, nnz, stats, peak)
-    top = max(roofs, key=lambda e: e["ms_per_launch"]) if roofs else None
+    # ---- count mode (SimilarityChecker._get for every candidate edge): the intersection kernel on its own -------
+    count_mode = None
+    if world == 1:
+        ctx.fit_points(xd, r2, nmc, sim, labd, member_cutoff=w["member_cutoff"])
+        nb_count, n_edges = count_mode_bytes(ctx, nmc)
+        counts = torch.empty(nnz, dtype=torch.int32, device="cuda")
+        for _ in range(2):
+            ctx.cn_count(nmc, counts)
+        ctx.set_timing(True)
+        ctx.timings(reset=True)
+        reps = 5
+        for i in range(reps):
+            flush.fill_(i)
+            ctx.cn_count(nmc, counts)
+        t_count, _ = ctx.timings(reset=True)
+        ctx.set_timing(False)
+        count_mode = (t_count["cn_count"][0] / reps, nb_count, n_edges)
+        del counts
+
+    roofs = stage_rooflines(timings, args.steps, n, d, nnz, stats, peak, count_mode)
+    fit_roofs = [e for e in roofs if not e["stage"].startswith("cn_count")]
+    top = max(fit_roofs, key=lambda e: e["ms_per_launch"]) if fit_roofs else None
     stage_ms = {k: v[0] / args.steps for k, v in timings.items() if v[1]}
     t_cn = (timings["comp_sample"][0] + timings["comp_edges"][0]) / args.steps * 1e-3
     line = {
         "metric": METRIC, "value": n * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64 distances / int32 indices / int64 labels",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64 (fp32 filter + exact f64 recheck of borderline pairs) / int32 indices / int64 labels",
         "data": "synthetic",
         "config": {"workload": w["name"], "l2_flush_between_steps": True, "parallelism": f"row-sharded x{world}",
                    "n_points": n, "n_dim": d, "nnz": nnz, "max_degree": max_deg},
@@ -340,7 +412,7 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": ({k: top[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")} | {
-            "kernel": top["kernel"], "peak_source": peak_src}) if top else None,
+            "kernel": top["kernel"], "limited_by": top["limited_by"], "peak_source": peak_src}) if top else None,
         "kernels": roofs,
         "stage_ms_per_step": stage_ms,
         "cn_checks": {"candidate_edges": stats["candidate_edges"], "checks_executed": stats["checks"],

@@ -466,6 +466,109 @@ __global__ void comp_above_kernel(const ll *__restrict__ row_ptr, const int *__r
     above[i] = l;
 }
 
+// ---- components from precomputed common-neighbour counts (parameter sweeps) ---------------------------
+// counts[k] of cnnb200_cn_count answer every similarity cutoff at once: slot k (row i, column j > i)
+// links i and j when both have more than n_member_cutoff entries and counts[k] >= similarity_cutoff.
+// Same two-step shape as the check-mode pass: link every core row with its first accepted neighbour
+// above it, flatten, then look only at the candidate edges whose ends still sit in different trees.
+__device__ __forceinline__ bool count_accepts(unsigned cnt, unsigned cutoff) {
+    return cutoff == 0 || (cnt != 0xffffffffu && cnt >= cutoff);
+}
+
+__global__ void __launch_bounds__(256)
+counts_sample_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, const unsigned *__restrict__ counts,
+                     ll n, unsigned cutoff, const int *__restrict__ parent, int *__restrict__ edge_out,
+                     int *__restrict__ above) {
+    ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int j_out = -1;
+    if (parent[i] >= 0) {
+        const ll rb = row_ptr[i];
+        const int m = (int)(row_ptr[i + 1] - rb);
+        int l = 0, h = m;  // first entry > i
+        while (l < h) {
+            int mid = (l + h) >> 1;
+            if (col_idx[rb + mid] <= (int)i) l = mid + 1; else h = mid;
+        }
+        above[i] = l;
+        for (int k = l; k < m; ++k) {
+            const int j = col_idx[rb + k];
+            if (parent[j] >= 0 && count_accepts(counts[rb + k], cutoff)) { j_out = j; break; }
+        }
+    }
+    edge_out[i] = j_out;
+}
+
+__global__ void __launch_bounds__(256)
+counts_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, const unsigned *__restrict__ counts,
+                   ll n, const int *__restrict__ above, unsigned cutoff, int *parent, unsigned long long *stats) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    unsigned long long n_edges = 0, n_acc = 0, n_looked = 0;
+    constexpr int R = 4;
+    for (ll i0 = warp * 32; i0 < n; i0 += nwarps * 32) {
+        const ll il = i0 + lane;
+        const int rl = il < n ? ld_parent(parent, (int)il) : -1;
+        ll bl = 0, el = 0;
+        if (rl >= 0) {
+            el = row_ptr[il + 1];
+            bl = row_ptr[il] + above[il];
+        }
+        const int nch = (int)((el - bl + 31) >> 5);
+        int incl = nch;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int excl = incl - nch;
+        const int total = __shfl_sync(full, incl, 31);
+        for (int t0 = 0; t0 < total; t0 += R) {
+            int rr[R], r_i[R], jv[R], pjv[R];
+            ll kv[R];
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const int t = t0 + u;
+                rr[u] = -1;
+                jv[u] = -1;
+                kv[u] = 0;
+                if (t < total) {
+                    const int r = __popc(__ballot_sync(full, incl <= t));
+                    rr[u] = r;
+                    r_i[u] = __shfl_sync(full, rl, r);
+                    const ll k = __shfl_sync(full, bl, r) + 32 * (t - __shfl_sync(full, excl, r)) + lane;
+                    if (k < __shfl_sync(full, el, r)) { jv[u] = col_idx[k]; kv[u] = k; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < R; ++u) pjv[u] = jv[u] >= 0 ? ld_parent(parent, jv[u]) : -1;
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                if (rr[u] < 0) break;
+                const bool cand = pjv[u] >= 0;
+                // parents move while this kernel runs: a stale mismatch only costs a look at the count
+                const bool look = cand && pjv[u] != r_i[u];
+                bool acc = false;
+                if (look) {
+                    acc = count_accepts(counts[kv[u]], cutoff);
+                    if (acc) uf_union(parent, (int)i0 + rr[u], jv[u]);
+                }
+                n_edges += __popc(__ballot_sync(full, cand));
+                n_looked += __popc(__ballot_sync(full, look));
+                n_acc += __popc(__ballot_sync(full, acc));
+            }
+        }
+    }
+    if (lane == 0) {
+        if (n_edges) atomicAdd(stats + ST_EDGES, n_edges);
+        if (n_looked) atomicAdd(stats + ST_CHECKS, n_looked);
+        if (n_acc) atomicAdd(stats + ST_ACCEPTED, n_acc);
+        if (n_edges - n_looked) atomicAdd(stats + ST_SKIPPED, n_edges - n_looked);
+    }
+}
+
 // A rank that built only the rows around its block sees every other row as empty, hence not core.
 // Before merging, rows that ANY rank reports as core (parent >= 0) become singleton trees here too.
 __global__ void comp_adopt_core_kernel(const int *__restrict__ others, ll n, ll count, int *parent, uint8_t *core) {
@@ -680,6 +783,44 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(parent, ctx->n);
     }
     CNN_LAUNCHED(ctx, 2);
+    CNN_KERNEL_CHECK();
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_components_from_counts(cnnb200_ctx *ctx, const uint32_t *counts) {
+    if (!ctx || !counts) CNN_FAIL(CNNB200_E_INVALID, "components_from_counts: NULL argument");
+    if (!ctx->have_comp) CNN_FAIL(CNNB200_E_STATE, "components_from_counts: call components_begin first");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const ll n = ctx->n;
+    if (n == 0) return CNNB200_OK;
+    const unsigned cutoff = ctx->similarity_cutoff > 0xfffffffell ? 0xfffffffeu : (unsigned)ctx->similarity_cutoff;
+    unsigned long long *stats = (unsigned long long *)ctx->b_stats.p;
+    int *parent = ctx->b_parent.as<int>();
+    CNN_TRY(cnn_ensure(ctx, ctx->b_above, sizeof(int) * (size_t)n));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_edges, sizeof(int) * (size_t)n));
+    {
+        Span sp(ctx, T_COMP_SAMPLE);
+        counts_sample_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, counts, n, cutoff, parent,
+                                                                 ctx->b_edges.as<int>(), ctx->b_above.as<int>());
+        comp_union_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(ctx->b_edges.as<int>(), 0, n, 1, parent);
+    }
+    {
+        Span sp(ctx, T_COMP_FLATTEN);
+        comp_compress_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(parent, n);
+    }
+    {
+        Span sp(ctx, T_COMP_EDGES);
+        int sblocks = (int)((n + 255) / 256);
+        if (sblocks > ctx->sm_count * 32) sblocks = ctx->sm_count * 32;
+        counts_scan_kernel<<<sblocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, counts, n, ctx->b_above.as<int>(), cutoff,
+                                                    parent, stats);
+    }
+    {
+        Span sp(ctx, T_COMP_FLATTEN);
+        comp_compress_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(parent, n);
+    }
+    CNN_LAUNCHED(ctx, 5);
     CNN_KERNEL_CHECK();
     return CNNB200_OK;
 }

@@ -182,6 +182,13 @@ int cnnb200_fit(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_t similarity_cu
 int cnnb200_components_begin(cnnb200_ctx *ctx, int64_t n_member_cutoff,
                              int64_t similarity_cutoff, const uint8_t *consider, int loc);
 int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end);
+/* Parameter sweeps (the reference's scan loop calls Clustering.fit once per (radius_cutoff, cnn_cutoff)
+ * cell, docsrc/benchmark/scans.ipynb; HierarchicalFitterRepeat._fit does the same per step,
+ * _fit.pyx:1058-1187).  For one radius the counts of cnnb200_cn_count answer EVERY cnn_cutoff:
+ * after components_begin(n_member_cutoff, similarity_cutoff) this links the slots with
+ * counts >= similarity_cutoff between rows with more than n_member_cutoff entries -- the same components
+ * components_edges finds.  counts: DEVICE uint32 [nnz], computed with a member cutoff <= n_member_cutoff. */
+int cnnb200_components_from_counts(cnnb200_ctx *ctx, const uint32_t *counts);
 /* Device pointer to the int32 [n] parent array (internal index space). */
 int cnnb200_components_parents(cnnb200_ctx *ctx, int32_t **parents);
 /* Unions (i, other[i]) for every i of `count` foreign parent arrays laid out back to back

@@ -12,14 +12,48 @@ from .report import Record, Summary
 
 
 class Bundle:
-    """Input data + labels + summary of one clustering (reference ``_bundle.pyx:20-53``; the
-    hierarchy bookkeeping of the reference's Bundle is outside the fit path)."""
+    """Input data + labels + summary of one clustering and its place in a hierarchy (reference
+    ``_bundle.pyx:20-53``): ``children`` maps a cluster label to the Bundle of that cluster's points,
+    ``parent_indices`` / ``root_indices`` say where a child's points sit in its parent / the root
+    (``ReferenceIndices``, ``_types.pyx:289-305``)."""
 
-    def __init__(self, input_data=None, labels=None, summary=None):
+    def __init__(self, input_data=None, labels=None, summary=None, parent=None, alias=""):
         self._input_data = input_data
         self._labels = labels
         self._summary = summary if summary is not None else Summary()
         self._children = None
+        self._parent = parent
+        self.alias = alias
+        self.parent_indices = None
+        self.root_indices = None
+
+    children = property(lambda self: self._children)
+    parent = property(lambda self: self._parent)
+
+    def isolate(self, purge: bool = True, isolate_input_data: bool = True) -> None:
+        """Child bundles from the cluster labels (reference ``_bundle.pyx:275-352``): one child per
+        label != 0 holding the indices of its members (ascending) and, optionally, that subset of the
+        input data.  The member lists come from one stable argsort instead of a Python loop."""
+        if purge or self._children is None:
+            self._children = {}
+        lab = self._labels.labels
+        order = np.argsort(lab, kind="stable")
+        sorted_lab = lab[order]
+        starts = np.flatnonzero(np.r_[True, sorted_lab[1:] != sorted_lab[:-1]])
+        ends = np.r_[starts[1:], sorted_lab.shape[0]]
+        # children in order of first occurrence of their label, as the reference's label mapping yields them
+        # (reel() shifts child labels by the parent's running maximum, so the order is observable)
+        for s, e in sorted(zip(starts, ends), key=lambda se: order[se[0]]):
+            label = int(sorted_lab[s])
+            if label == 0:
+                continue
+            parent_indices = order[s:e].astype(np.intp)   # ascending: the argsort is stable
+            child = Bundle(parent=self, alias=f"{self.alias} - {label}")
+            child.parent_indices = parent_indices
+            child.root_indices = parent_indices if self.root_indices is None else self.root_indices[parent_indices]
+            if isolate_input_data:
+                child._input_data = self._input_data.get_subset(parent_indices)
+            self._children[label] = child
 
     input_data = property(lambda self: self._input_data)
     labels = property(lambda self: self._labels)
@@ -69,6 +103,58 @@ class Clustering:
     @property
     def summary(self):
         return self._bundle._summary
+
+    @property
+    def children(self):
+        return self._bundle._children
+
+    def isolate(self, purge: bool = True, isolate_input_data: bool = True, bundle=None) -> None:
+        """Reference ``Clustering.isolate`` (``cluster.pyx:394-413``)."""
+        (bundle if bundle is not None else self._bundle).isolate(purge, isolate_input_data)
+
+    def reel(self, depth=None, bundle=None) -> None:
+        """Wrap up the label assignments of lower hierarchy levels (reference ``cluster.pyx:502-558``):
+        depth first, every child's non-zero labels are shifted by the parent's current maximum and
+        written over the parent's labels at the child's ``parent_indices``; parameters move along."""
+        if bundle is None:
+            bundle = self._bundle
+        if depth is not None:
+            assert depth > 0
+
+        def _reel(parent, depth):
+            if not parent._children:
+                return
+            if depth is not None:
+                depth -= 1
+            parent._labels.meta["origin"] = "reel"
+            parent_labels = parent._labels.labels
+            for label, child in parent._children.items():
+                if child._labels is None:
+                    continue
+                if depth is None or depth > 0:
+                    _reel(child, depth)
+                n_clusters = int(parent_labels.max())
+                child_labels = child._labels.labels
+                parent_labels[child.parent_indices] = np.where(child_labels == 0, 0, child_labels + n_clusters)
+                params_parent = parent._labels.meta.setdefault("params", {})
+                params_parent.pop(label, None)
+                for old_label, p in child._labels.meta.get("params", {}).items():
+                    params_parent[old_label + n_clusters] = p
+
+        _reel(bundle, depth)
+
+    def fit_sweep(self, radius_cutoffs, cnn_cutoffs, member_cutoff=None, max_clusters=None, return_labels=True):
+        """Every cell of a ``radius_cutoffs x cnn_cutoffs`` scan, labels identical to one ``fit`` per cell
+        (see ``sweep.fit_sweep``); the records are appended to ``summary``."""
+        from . import sweep
+
+        g = self._fitter._neighbours_getter
+        labels, summary = sweep.fit_sweep(self._bundle._input_data.device_or_host_array, radius_cutoffs, cnn_cutoffs,
+                                          member_cutoff, max_clusters, metric=g.metric.name, ctx=self._fitter.ctx,
+                                          return_labels=return_labels)
+        for rec in summary:
+            self._bundle._summary.append(rec)
+        return labels, summary
 
     @property
     def fitter(self):

@@ -421,3 +421,57 @@ def test_c1_through_lookup_equals_coordinates():
     b = fit_via_api((rp, ci), 0.3, 10, recipe="neighbourhoods_csr").labels
     np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(a, GOLD["c1_full"].astype(np.int64))
+
+
+# ---- parameter sweeps and hierarchy --------------------------------------------------------
+def test_sweep_cells_equal_oracle(ctx):
+    from commonnnclustering_b200 import sweep
+
+    x = datasets.blobs_2d(3000)
+    rs, cs = [0.08, 0.12, 0.2], [0, 3, 10, 25]
+    labels, summary = sweep.fit_sweep(x, rs, cs, member_cutoff=5, ctx=ctx)
+    assert labels.shape == (3, 4, 3000) and len(summary) == 12
+    k = 0
+    for ir, r in enumerate(rs):
+        for ic, c in enumerate(cs):
+            want = port.fit_points(x, r, c, member_cutoff=5)
+            np.testing.assert_array_equal(labels[ir, ic], want, err_msg=f"cell r={r} c={c}")
+            rec = summary[k]
+            k += 1
+            assert (rec.radius_cutoff, rec.cnn_cutoff, rec.n_clusters) == (r, c, int(want.max()))
+            assert abs(rec.ratio_noise - float((want == 0).mean())) < 1e-15
+
+
+def test_sweep_3d_equals_one_fit_per_cell(ctx):
+    from commonnnclustering_b200 import sweep
+
+    x = datasets.md_like_3d(120_000)
+    rs, cs = [0.12, 0.2], [2, 20, 60]
+    labels, _ = sweep.fit_sweep(x, rs, cs, member_cutoff=10, ctx=ctx)
+    single = np.empty(x.shape[0], dtype=np.int64)
+    for ir, r in enumerate(rs):
+        for ic, c in enumerate(cs):
+            ctx.fit_points(x, r * r, c + 1, c + 2, single, member_cutoff=10)
+            np.testing.assert_array_equal(labels[ir, ic], single, err_msg=f"cell r={r} c={c}")
+
+
+def test_hierarchical_recluster_equals_reference():
+    """fit -> isolate -> recluster the children -> reel, against the reference doing the same."""
+    from oracle import ref
+
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rmod = ref.module()
+    x = datasets.blobs_2d(1500)
+    out = []
+    for mod in (cluster, rmod):
+        cl = mod.Clustering(x)
+        cl.fit(0.25, 5, member_cutoff=10, v=False)
+        cl.isolate()
+        for label, child in cl.root._children.items():
+            if child._input_data.n_points >= 100:
+                cl.fit(0.12, 12, member_cutoff=5, v=False, bundle=child)
+        cl.reel()
+        out.append(np.array(cl.labels))
+    np.testing.assert_array_equal(out[0], out[1])
+    assert out[0].max() > 2

@@ -88,3 +88,66 @@ def test_datasets_are_deterministic():
     last = np.maximum.accumulate(idx)
     assert np.array_equal(state, np.where(last >= 0, new_state[np.maximum(last, 0)], 0))
     assert datasets.features_64d(500).shape == (500, 64)
+
+
+# ---- hierarchy helpers (host logic): isolate / reel --------------------------------------------------------
+def _toy_hierarchy(cluster_mod, labels_cls, x, parent_labels, child_labels_by_label):
+    cl = cluster_mod.Clustering(x)
+    cl.labels = labels_cls(np.array(parent_labels, dtype=np.int64))
+    cl.root._labels.meta["params"] = {int(k): (1.0, 1) for k in set(parent_labels) if k != 0}
+    cl.isolate()
+    for label, child_labels in child_labels_by_label.items():
+        child = cl.root._children[label]
+        child._labels = labels_cls(np.array(child_labels, dtype=np.int64))
+        child._labels.meta["params"] = {int(k): (0.5, 2) for k in set(child_labels) if k != 0}
+    return cl
+
+
+def test_isolate_and_reel_known_answer():
+    from commonnnclustering_b200 import cluster
+    from commonnnclustering_b200._types import Labels
+
+    x = np.arange(24, dtype=np.float64).reshape(12, 2)
+    parent = [2, 2, 1, 0, 1, 2, 1, 0, 3, 3, 1, 2]
+    cl = _toy_hierarchy(cluster, Labels, x, parent, {1: [1, 1, 0, 2], 2: [0, 1, 1, 2]})
+    # children in order of first occurrence; members ascending; data subsets attached
+    assert list(cl.root.children) == [2, 1, 3]
+    assert cl.root.children[1].parent_indices.tolist() == [2, 4, 6, 10]
+    assert cl.root.children[2].parent_indices.tolist() == [0, 1, 5, 11]
+    np.testing.assert_array_equal(cl.root.children[3].input_data.data, x[[8, 9]])
+    cl.reel()
+    # child 2 first (labels + 3), then child 1 (labels + current max 5); child 3 has no labels
+    assert cl.labels.tolist() == [0, 4, 6, 0, 6, 4, 0, 0, 3, 3, 7, 5]
+    assert cl.root._labels.meta["origin"] == "reel"
+    assert set(cl.root._labels.meta["params"]) == {3, 4, 5, 6, 7}
+
+
+def test_isolate_and_reel_equal_reference():
+    from oracle import ref
+
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    from commonnnclustering_b200 import cluster
+    from commonnnclustering_b200._types import Labels
+
+    rmod = ref.module()
+    from cnnclustering import _types as rtypes
+
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((400, 2))
+    parent = rng.integers(0, 6, 400)
+    kids = {}
+    for label in range(1, 6):
+        m = int((parent == label).sum())
+        if label != 4:
+            kids[label] = rng.integers(0, 4, m).tolist()
+    ours = _toy_hierarchy(cluster, Labels, x, parent.tolist(), kids)
+    theirs = _toy_hierarchy(rmod, rtypes.Labels, x, parent.tolist(), kids)
+    assert list(ours.root._children) == list(theirs.root._children)
+    for label in ours.root._children:
+        np.testing.assert_array_equal(ours.root._children[label].parent_indices,
+                                      theirs.root._children[label]._reference_indices.parent)
+    ours.reel()
+    theirs.reel()
+    np.testing.assert_array_equal(ours.labels, theirs.labels)
+    assert ours.root._labels.meta["params"] == theirs.root._labels.meta["params"]

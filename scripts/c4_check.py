@@ -1,0 +1,87 @@
+"""C4 (BASELINE configs[3]): precomputed-neighbourhood input, N = 1e7, self-counting sorted CSR (int32 indices, int64
+offsets; mean degree ~50), cnn_cutoff 10, member_cutoff 10.  Run alone (1 GPU) or under torchrun (row-sharded:
+every rank uploads its rows, NCCL all-gather of the CSR, parent all-gather + merge).
+The CSR is produced once by the cell-list search on the C2 generator (r = 0.037) and then treated as caller data."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from commonnnclustering_b200 import _lib, datasets
+
+n = int(os.environ.get("N", 10_000_000))
+r, c, mc = float(os.environ.get("R", 0.037)), 10, 10
+world = int(os.environ.get("WORLD_SIZE", 1))
+local = int(os.environ.get("LOCAL_RANK", 0))
+rank = int(os.environ.get("RANK", 0))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+    from commonnnclustering_b200 import dist as cdist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+x = datasets.md_like_3d(n)
+ctx = _lib.Context(local, torch_allocator=True)
+ctx.set_stream(torch.cuda.current_stream())
+# produce the "precomputed" neighbourhoods (caller index space, rows ascending) -- not part of the measured step
+ctx.neighbours_from_points(x, r * r)
+rp, ci = ctx.neighbours_export()
+nnz = int(rp[-1])
+ci32 = ci.astype(np.int32)
+del ci
+out = {"workload": f"C4: precomputed neighbourhoods N={n}, nnz={nnz}, mean degree {nnz / n:.1f}, c={c}, member_cutoff={mc}",
+       "n_gpus": world}
+lab = np.empty(n, dtype=np.int64)
+if world == 1:
+    rp_d, ci_d = torch.from_numpy(rp).cuda(), torch.from_numpy(ci32).cuda()
+    lab_d = torch.empty(n, dtype=torch.int64, device="cuda")
+    times = []
+    for it in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.neighbours_from_csr(rp_d, ci_d, borrow=True)
+        ctx.fit(c + 1, c + 2, 1, lab_d.zero_(), None)
+        ctx.sort_by_size(lab_d, mc)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    lab = lab_d.cpu().numpy()
+    out.update(device_resident_fit_ms=1e3 * min(times[1:]), points_per_s=n / min(times[1:]), stats=ctx.stats())
+    # host-resident input: H2D of the CSR inside the timed region
+    t0 = time.perf_counter()
+    ctx.neighbours_from_csr(rp, ci32)
+    ctx.fit(c + 1, c + 2, 1, lab, None)
+    ctx.sort_by_size(lab, mc)
+    out["host_resident_fit_ms"] = 1e3 * (time.perf_counter() - t0)
+    out["host_equals_device"] = bool(np.array_equal(lab, lab_d.cpu().numpy()))
+    if os.environ.get("ORACLE", "1") != "0":
+        from oracle import port
+        port.set_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        want = port.fit_csr(rp, ci32.astype(np.int64), c, member_cutoff=mc)
+        out["oracle_bfs_s"] = time.perf_counter() - t0
+        out["labels_equal_oracle"] = bool(np.array_equal(want, lab))
+else:
+    sf = cdist.ShardedFit(ctx)
+    times = []
+    for it in range(3):
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        bounds = sf.neighbours_from_csr_host(rp, ci32)
+        sf.fit(bounds, c + 1, c + 2, lab, member_cutoff=mc)
+        torch.cuda.synchronize(); dist.barrier()
+        times.append(time.perf_counter() - t0)
+    out.update(sharded_fit_ms_incl_h2d=1e3 * min(times[1:]), points_per_s=n / min(times[1:]))
+    single = np.empty(n, dtype=np.int64)
+    c1 = _lib.Context(local)
+    c1.neighbours_from_csr(rp, ci32)
+    c1.fit(c + 1, c + 2, 1, single, None)
+    c1.sort_by_size(single, mc)
+    out["labels_equal_single_gpu_run"] = bool(np.array_equal(single, lab))
+out["n_clusters"] = int(lab.max())
+if rank == 0:
+    print(json.dumps(out), flush=True)
+if world > 1:
+    dist.destroy_process_group()

@@ -271,6 +271,7 @@ extern "C" int cnnb200_fit_points(cnnb200_ctx *ctx, const double *x, int loc, in
     int64_t n_clusters = 0;  // asking for it also refreshes the counters behind cnnb200_stats
     CNN_TRY(cnnb200_components_labels(ctx, current_start, d_labels, CNNB200_DEVICE, /*fresh=*/1, &n_clusters));
     if (n_clusters_out) *n_clusters_out = n_clusters;
+    ctx->known_max_label = n_clusters > 0 ? current_start + n_clusters - 1 : 0;  // fresh fit: no reduce, no sync
     CNN_TRY(cnnb200_sort_by_size(ctx, d_labels, CNNB200_DEVICE, n, member_cutoff, max_clusters, nullptr, 0));
     if (loc == CNNB200_HOST) {
         {

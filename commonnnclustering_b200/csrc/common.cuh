@@ -132,6 +132,7 @@ struct cnnb200_ctx {
     size_t h_pinned_cap = 0;
 
     ll stats[ST_N] = {0};
+    ll known_max_label = -1;  // set by cnnb200_fit_points for the sort_by_size call that follows a fresh fit
 
     // ---- measurement ---------------------------------------------------------------------------
     bool timing = false;

@@ -44,12 +44,17 @@ __global__ void bbox_partial_kernel(const double *__restrict__ x, ll n, int d, d
     }
 }
 
+// one warp per component (3 minima, 3 maxima)
 __global__ void bbox_final_kernel(const double *partial, int nblocks, double *out) {
-    int k = threadIdx.x;
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (k >= 6) return;
-    double v = partial[k];
-    for (int b = 1; b < nblocks; ++b) v = k < 3 ? fmin(v, partial[b * 6 + k]) : fmax(v, partial[b * 6 + k]);
-    out[k] = v;
+    double v = k < 3 ? INFINITY : -INFINITY;
+    for (int b = lane; b < nblocks; b += 32) v = k < 3 ? fmin(v, partial[b * 6 + k]) : fmax(v, partial[b * 6 + k]);
+    for (int o = 16; o; o >>= 1) {
+        const double w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = k < 3 ? fmin(v, w) : fmax(v, w);
+    }
+    if (lane == 0) out[k] = v;
 }
 
 // ---- cell assignment ------------------------------------------------------------------------
@@ -79,9 +84,9 @@ __device__ __forceinline__ double cell_origin(double lo, double h, int c) {
 
 // gather coordinates into cell-sorted SoA: xs[k][p] = x[perm[p]][k]; and the fp32 cell-local copy used by
 // the filter kernel: xf[p] = (x relative to lattice A, x relative to lattice B, y and z relative to the
-// point's own cell).  Lattices A and B have period 4 cells along x and are offset by 2 cells: any run of
-// up to 3 neighbouring cells lies inside one period of A or of B, so that all candidates of a run and
-// the query share one origin and their fp32 differences are accurate to ~2^-24 of 4h.
+// point's own cell).  Lattices A and B have period 16 cells along x and are offset by 8 cells: any run of
+// up to 8 neighbouring cells lies inside one period of A or of B, so that all candidates of a run and
+// the queries share one origin and their fp32 differences are accurate to ~2^-24 of 16h.
 __global__ void gather_kernel(const double *__restrict__ x, const int *__restrict__ perm,
                               const int *__restrict__ cell_sorted, ll n, GridDesc g, double *xs, float4 *xf) {
     ll p = blockIdx.x * (ll)blockDim.x + threadIdx.x;
@@ -100,8 +105,8 @@ __global__ void gather_kernel(const double *__restrict__ x, const int *__restric
     const int cy = t % g.dims[1];
     const int cz = t / g.dims[1];
     float4 f;
-    f.x = (float)__dsub_rn(v[0], cell_origin(g.lo[0], g.h, cx & ~3));
-    f.y = (float)__dsub_rn(v[0], cell_origin(g.lo[0], g.h, ((cx + 2) & ~3) - 2));
+    f.x = (float)__dsub_rn(v[0], cell_origin(g.lo[0], g.h, cx & ~15));
+    f.y = (float)__dsub_rn(v[0], cell_origin(g.lo[0], g.h, ((cx + 8) & ~15) - 8));
     f.z = d > 1 ? (float)__dsub_rn(v[1], cell_origin(g.lo[1], g.h, cy)) : 0.f;
     f.w = d > 2 ? (float)__dsub_rn(v[2], cell_origin(g.lo[2], g.h, cz)) : 0.f;
     xf[p] = f;
@@ -213,16 +218,17 @@ grid_rows_kernel(const double *__restrict__ xs, ll n, const int *__restrict__ ce
 //   * the test is an fp32 FILTER with a proven error bound: d2 <= R - eps is a neighbour, d2 > R + eps is
 //     not, and the (rare) pairs in between are decided by the reference's own f64 expression on the
 //     original coordinates (`within`), so the neighbour sets are exactly those of the f64 kernel.
-//     fp32 is accurate enough because all coordinates are relative to a nearby cell origin: with
-//     delta = h * 2^-20 bounding the error of every coordinate difference,
-//     |d2_fp32 - d2| <= 2*sqrt(3)*delta*sqrt(d2) + 3*delta^2 + 2^-22*d2 < eps = h*r*2^-18 + h^2*2^-38 + R*2^-21.
+//     fp32 is accurate enough because all coordinates are relative to a nearby cell origin (|value| < 16h):
+//     every coordinate difference carries an error below delta = h * 2^-18, hence
+//     |d2_fp32 - d2| <= 2*sqrt(3)*delta*sqrt(d2) + 3*delta^2 + 2^-22*d2 < eps = h*r*2^-16 + h^2*2^-34 + R*2^-21.
 //   * the ballot words of up to 32 chunks are parked in shared memory and then expanded by the lane
 //     that owns the query straight into its (gapped) row -- candidates ascend, so rows come out sorted.
 // Per 32 distance tests the loop issues ~13 instructions (one LDS.128, 6 FP32, 2 compares, 2 votes,
 // one STS) instead of ~47 (3 LDG.64, 9 FP64, ballot ranking, scattered store) in the f64 form.
 #define GF_WARPS 8
 #define GF_CHUNKS 32
-#define GF_LANE_PER_QUERY 14  // groups at least this large run one query per lane
+#define GF_LANE_PER_QUERY 8  // groups at least this large run one query per lane
+#define GF_XSPAN 3            // a group spans at most GF_XSPAN + 1 cells along x
 
 struct FilterParams {
     float t_lo, t_hi;  // definite hit: d2 <= t_lo; definite miss: d2 > t_hi
@@ -249,25 +255,30 @@ grid_rows_f32_kernel(const double *__restrict__ xs, const float4 *__restrict__ x
         const ll p = p0 + lane;
         const bool pvalid = p < p_end;
         const int cid = pvalid ? cell_sorted[p] : -1;
+        const int my_row = pvalid ? cid / g.dims[0] : -1, my_cx = pvalid ? cid - my_row * g.dims[0] : 0;
         const float4 my4 = pvalid ? xf[p] : make_float4(0.f, 0.f, 0.f, 0.f);
         const ll my_base = pvalid ? goff[p] : 0;
         unsigned todo = __ballot_sync(full, pvalid);
         while (todo) {
-            const int a = __ffs(todo) - 1;  // first lane of the next group (groups are runs of lanes)
+            // next group: the run of lanes, starting at the first open one, whose points lie in the same x-row
+            // of cells and at most GF_XSPAN cells apart.  They share one candidate list, the union of their
+            // 3^D windows (a query also meets candidates outside its own window; the distance test is exact,
+            // so that only costs time) -- neighbouring sparse cells are served as ONE well-filled group.
+            const int a = __ffs(todo) - 1;
             const int c = __shfl_sync(full, cid, a);
-            const unsigned grp = __ballot_sync(full, cid == c) & todo;
+            const int row_a = c / g.dims[0], cx = c - row_a * g.dims[0];
+            const unsigned grp = __ballot_sync(full, my_row == row_a && my_cx - cx <= GF_XSPAN) & todo;
             todo &= ~grp;
             const int gsz = __popc(grp);
             const int jme = lane - a;  // my query slot when I belong to the group
             const bool mine = jme >= 0 && jme < gsz;
-            const int cx = c % g.dims[0];
-            const int t = c / g.dims[0];
-            const int cy = t % g.dims[1];
-            const int cz = t / g.dims[1];
-            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
+            const int cx_max = __shfl_sync(full, my_cx, a + gsz - 1);
+            const int cy = row_a % g.dims[1];
+            const int cz = row_a / g.dims[1];
+            const int x0 = max(cx - 1, 0), x1 = min(cx_max + 1, g.dims[0] - 1);
             const int y0 = D > 1 ? max(cy - 1, 0) : 0, y1 = D > 1 ? min(cy + 1, g.dims[1] - 1) : 0;
             const int z0 = D > 2 ? max(cz - 1, 0) : 0, z1 = D > 2 ? min(cz + 1, g.dims[2] - 1) : 0;
-            const bool use_b = (x0 >> 2) != (x1 >> 2);  // the run straddles a period boundary of lattice A
+            const bool use_b = (x0 >> 4) != (x1 >> 4);  // the run straddles a period boundary of lattice A
             // run bounds: one run per lane, fetched together
             const int ny = y1 - y0 + 1, nruns = ny * (z1 - z0 + 1);
             int rs = 0, re = 0;
@@ -486,7 +497,7 @@ static bool filter_params(const cnnb200_ctx *ctx, FilterParams *fp) {
     if (!(h > 1e-12 && h < 1e12)) return false;
     const double R = ctx->grid_metric == CNNB200_METRIC_EUCLIDEAN ? ctx->grid_rc * ctx->grid_rc : ctx->grid_rc;
     const double r = sqrt(R);
-    const double eps = ldexp(h * r, -18) + ldexp(h * h, -38) + ldexp(R, -21);
+    const double eps = ldexp(h * r, -16) + ldexp(h * h, -34) + ldexp(R, -21);
     const double lo = R - eps, hi = R + eps;
     float flo = (float)lo, fhi = (float)hi;
     if ((double)flo > lo) flo = nextafterf(flo, -INFINITY);
@@ -558,7 +569,7 @@ int cnn_grid_build(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radiu
     CNN_TRY(cnn_ensure(ctx, ctx->b_bbox, sizeof(double) * (size_t)(rb + 1) * 6));
     double *partial = ctx->b_bbox.as<double>();
     bbox_partial_kernel<<<rb, 256, 0, st>>>(d_x, n, (int)d, partial + 6);
-    bbox_final_kernel<<<1, 32, 0, st>>>(partial + 6, rb, partial);
+    bbox_final_kernel<<<1, 192, 0, st>>>(partial + 6, rb, partial);
     CNN_LAUNCHED(ctx, 2);
     CNN_KERNEL_CHECK();
     double *hb;

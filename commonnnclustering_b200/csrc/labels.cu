@@ -152,26 +152,26 @@ __global__ void label_hist_kernel(const ll *__restrict__ labels, ll n, int *coun
     }
 }
 
-__global__ void label_keys_kernel(const int *__restrict__ count, const int *__restrict__ first, ll L,
+// key = (n - size) : first occurrence, kb bits each (n < 2^kb): ascending keys = size descending, ties by first
+// occurrence; labels that do not occur get the largest key.  Only 2*kb bits are sorted.
+__global__ void label_keys_kernel(const int *__restrict__ count, const int *__restrict__ first, ll L, ll n, int kb,
                                   unsigned long long *keys, int *vals) {
     ll l = blockIdx.x * (ll)blockDim.x + threadIdx.x + 1;  // labels 1 .. L-1
     if (l >= L) return;
     int c = count[l];
-    keys[l - 1] = c > 0 ? ((unsigned long long)(0xffffffffu - (unsigned)c) << 32) | (unsigned)first[l]
-                        : 0xffffffffffffffffull;
+    keys[l - 1] = ((unsigned long long)(n - c) << kb) | (unsigned long long)(c > 0 ? first[l] : 0);
     vals[l - 1] = (int)l;
 }
 
 // survivors in rank order: t-th entry (rank t+1) survives if it exists, rank <= max_clusters and
 // size >= member_cutoff
-__global__ void label_survivor_kernel(const unsigned long long *__restrict__ keys, ll m, ll member_cutoff,
-                                      ll max_clusters, int *surv) {
+__global__ void label_survivor_kernel(const unsigned long long *__restrict__ keys, ll m, ll n, int kb,
+                                      ll member_cutoff, ll max_clusters, int *surv) {
     ll t = blockIdx.x * (ll)blockDim.x + threadIdx.x;
     if (t > m) return;
     if (t == m) { surv[m] = 0; return; }
-    unsigned long long k = keys[t];
-    bool ok = k != 0xffffffffffffffffull;
-    ll size = (ll)(0xffffffffu - (unsigned)(k >> 32));
+    const ll size = n - (ll)(keys[t] >> kb);
+    bool ok = size > 0;
     ok = ok && (max_clusters < 0 || t + 1 <= max_clusters) && size >= member_cutoff;
     surv[t] = ok ? 1 : 0;
 }
@@ -207,19 +207,24 @@ extern "C" int cnnb200_sort_by_size(cnnb200_ctx *ctx, int64_t *labels, int loc, 
         CNN_CUDA(cudaMemcpyAsync(d_labels, labels, sizeof(ll) * (size_t)n, cudaMemcpyHostToDevice, st));
     }
     std::unique_ptr<Span> sp(new Span(ctx, T_SORT_BY_SIZE));
-    // largest label -> table size
+    // largest label -> table size (known to the caller after a fresh fit: ctx->known_max_label)
     CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
-    ll *d_max = ctx->b_tmp2.as<ll>() + 2;
-    size_t need = 0;
-    CNN_CUDA(cub::DeviceReduce::Max(nullptr, need, d_labels, d_max, (int)n, st));
-    CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
-    size_t cap = ctx->b_cub.cap;
-    CNN_CUDA(cub::DeviceReduce::Max(ctx->b_cub.p, cap, d_labels, d_max, (int)n, st));
+    size_t cap = 0;
     ll *h;
     CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
-    CNN_CUDA(cudaMemcpyAsync(h, d_max, sizeof(ll), cudaMemcpyDeviceToHost, st));
-    CNN_CUDA(cudaStreamSynchronize(st));
-    ll max_label = h[0];
+    ll max_label = ctx->known_max_label;
+    ctx->known_max_label = -1;
+    if (max_label < 0) {
+        ll *d_max = ctx->b_tmp2.as<ll>() + 2;
+        size_t need = 0;
+        CNN_CUDA(cub::DeviceReduce::Max(nullptr, need, d_labels, d_max, (int)n, st));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
+        cap = ctx->b_cub.cap;
+        CNN_CUDA(cub::DeviceReduce::Max(ctx->b_cub.p, cap, d_labels, d_max, (int)n, st));
+        CNN_CUDA(cudaMemcpyAsync(h, d_max, sizeof(ll), cudaMemcpyDeviceToHost, st));
+        CNN_CUDA(cudaStreamSynchronize(st));
+        max_label = h[0];
+    }
     if (max_label < 0) CNN_FAIL(CNNB200_E_INVALID, "sort_by_size: negative labels");
     if (max_label >= (1ll << 31) - 2) CNN_FAIL(CNNB200_E_RANGE, "sort_by_size: label %lld too large", max_label);
     ll L = max_label + 1, m = L - 1;
@@ -242,16 +247,18 @@ extern "C" int cnnb200_sort_by_size(cnnb200_ctx *ctx, int64_t *labels, int loc, 
         unsigned long long *keys = ctx->b_lab_keys.as<unsigned long long>();
         unsigned long long *keys2 = ctx->b_lab_keys2.as<unsigned long long>();
         int *vals = ctx->b_lab_vals.as<int>(), *vals2 = ctx->b_lab_vals2.as<int>();
-        label_keys_kernel<<<cnn_blocks(m, 256), 256, 0, st>>>(count, first, L, keys, vals);
+        int kb = 1;
+        while ((1ll << kb) <= n) ++kb;
+        label_keys_kernel<<<cnn_blocks(m, 256), 256, 0, st>>>(count, first, L, n, kb, keys, vals);
         CNN_KERNEL_CHECK();
         size_t need_sort = 0, need_scan = 0;
-        CNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need_sort, keys, keys2, vals, vals2, (int)m, 0, 64, st));
+        CNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need_sort, keys, keys2, vals, vals2, (int)m, 0, 2 * kb, st));
         CNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need_scan, ctx->b_flags.as<int>(), ctx->b_rank.as<int>(),
                                                (int)(m + 1), st));
         CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need_sort > need_scan ? need_sort : need_scan));
         cap = ctx->b_cub.cap;
-        CNN_CUDA(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, cap, keys, keys2, vals, vals2, (int)m, 0, 64, st));
-        label_survivor_kernel<<<cnn_blocks(m + 1, 256), 256, 0, st>>>(keys2, m, member_cutoff, max_clusters,
+        CNN_CUDA(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, cap, keys, keys2, vals, vals2, (int)m, 0, 2 * kb, st));
+        label_survivor_kernel<<<cnn_blocks(m + 1, 256), 256, 0, st>>>(keys2, m, n, kb, member_cutoff, max_clusters,
                                                                         ctx->b_flags.as<int>());
         cap = ctx->b_cub.cap;
         CNN_CUDA(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, cap, ctx->b_flags.as<int>(), ctx->b_rank.as<int>(),

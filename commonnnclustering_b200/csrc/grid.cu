@@ -232,6 +232,7 @@ grid_rows_kernel(const double *__restrict__ xs, ll n, const int *__restrict__ ce
 
 struct FilterParams {
     float t_lo, t_hi;  // definite hit: d2 <= t_lo; definite miss: d2 > t_hi
+    float r2, band;    // |d2 - r2| <= band for every d2 in (t_lo, t_hi] (computed in fp32, rounded outwards)
 };
 
 template <int D, bool SQRT>
@@ -296,7 +297,9 @@ grid_rows_f32_kernel(const double *__restrict__ xs, const float4 *__restrict__ x
             if (gsz >= GF_LANE_PER_QUERY) {
                 // ---- big group: one query per lane; the chunk's candidates go through shared memory and
                 // are read back as broadcasts.  No votes, no ranking: a lane appends to its own row.
-                const float qx = use_b ? my4.y : my4.x, qy = my4.z, qz = my4.w;
+                // lanes outside the group carry a query parked far away: it never hits and never is borderline
+                const float qx = mine ? (use_b ? my4.y : my4.x) : 1e30f, qy = my4.z, qz = my4.w;
+                int *const orow = out + my_base;
                 for (int r = 0; r < nruns; ++r) {
                     const int s = __shfl_sync(full, rs, r), e = __shfl_sync(full, re, r);
                     const float sy = __shfl_sync(full, shy, r), sz = __shfl_sync(full, shz, r);
@@ -307,6 +310,8 @@ grid_rows_f32_kernel(const double *__restrict__ xs, const float4 *__restrict__ x
                         qf[lane] = make_float4(use_b ? c4.y : c4.x, c4.z + sy, c4.w + sz, 0.f);
                         __syncwarp();
                         const int nc = min(32, e - q0);
+                        const int cnt0 = cnt;
+                        float near = INFINITY;  // smallest |d2 - R| this lane meets in the chunk
 #pragma unroll 4
                         for (int tq = 0; tq < nc; ++tq) {
                             const float4 cv = qf[tq];
@@ -314,13 +319,27 @@ grid_rows_f32_kernel(const double *__restrict__ xs, const float4 *__restrict__ x
                             float s2 = dx * dx;
                             if (D > 1) { const float dy = qy - cv.y; s2 = fmaf(dy, dy, s2); }
                             if (D > 2) { const float dz = qz - cv.z; s2 = fmaf(dz, dz, s2); }
-                            bool hit = s2 <= fp.t_lo;
-                            if (mine && s2 > fp.t_lo && s2 <= fp.t_hi) {  // borderline: the reference's own f64 test
-                                hit = within<D, SQRT>(xs[p], D > 1 ? xs[n + p] : 0.0, D > 2 ? xs[2 * n + p] : 0.0, xs, n,
-                                                      q0 + tq, rc);
-                                ++n_recheck;
+                            near = fminf(near, fabsf(s2 - fp.r2));
+                            if (s2 <= fp.t_lo) orow[cnt++] = q0 + tq;
+                        }
+                        if (near <= fp.band) {
+                            // rare: a pair of this lane is borderline.  Redo the lane's chunk, deciding such pairs
+                            // with the reference's own f64 test (the row must stay ascending, hence the redo).
+                            cnt = cnt0;
+                            for (int tq = 0; tq < nc; ++tq) {
+                                const float4 cv = qf[tq];
+                                const float dx = qx - cv.x;
+                                float s2 = dx * dx;
+                                if (D > 1) { const float dy = qy - cv.y; s2 = fmaf(dy, dy, s2); }
+                                if (D > 2) { const float dz = qz - cv.z; s2 = fmaf(dz, dz, s2); }
+                                bool hit = s2 <= fp.t_lo;
+                                if (s2 > fp.t_lo && s2 <= fp.t_hi) {
+                                    hit = within<D, SQRT>(xs[p], D > 1 ? xs[n + p] : 0.0, D > 2 ? xs[2 * n + p] : 0.0, xs, n,
+                                                          q0 + tq, rc);
+                                    ++n_recheck;
+                                }
+                                if (hit) orow[cnt++] = q0 + tq;
                             }
-                            if (hit && mine) out[my_base + cnt++] = q0 + tq;
                         }
                     }
                 }
@@ -505,6 +524,9 @@ static bool filter_params(const cnnb200_ctx *ctx, FilterParams *fp) {
     if (!isfinite(flo) || !isfinite(fhi)) return false;
     fp->t_lo = flo;
     fp->t_hi = fhi;
+    fp->r2 = (float)R;
+    const double half = fmax((double)fp->r2 - (double)flo, (double)fhi - (double)fp->r2);
+    fp->band = nextafterf((float)(half * (1.0 + ldexp(1.0, -20))), INFINITY);
     return true;
 }
 

@@ -313,14 +313,18 @@ comp_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     unsigned long long n_edges = 0, n_need = 0;
-    constexpr int R = 4;  // chunks in flight per warp
+    constexpr int R = 8;  // chunks in flight per warp
     for (ll i0 = row_begin + warp * 32; i0 < row_end; i0 += nwarps * 32) {
         const ll il = i0 + lane;
-        const int rl = il < row_end ? parent[il] : -1;
+        const bool lv = il < row_end;
+        // independent loads (no branch on the root): one memory round trip for the whole tile header
+        const int rl = lv ? parent[il] : -1;
+        const ll e_raw = lv ? row_ptr[il + 1] : 0, b_raw = lv ? row_ptr[il] : 0;
+        const int ab = lv ? above[il] : 0;
         ll bl = 0, el = 0;
         if (rl >= 0) {
-            el = row_ptr[il + 1];
-            bl = row_ptr[il] + above[il];
+            el = e_raw;
+            bl = b_raw + ab;
         }
         // the tile's work items are its (row, chunk of 32 entries) pairs; incl = inclusive prefix of the
         // chunk counts, so item t belongs to row popc(ballot(incl <= t))
@@ -350,20 +354,26 @@ comp_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx
             }
 #pragma unroll
             for (int u = 0; u < R; ++u) pjv[u] = jv[u] >= 0 ? parent[jv[u]] : -1;
+            // one reservation in the work list for the whole batch of R chunks
+            unsigned nmv[R];
+            int tot = 0;
 #pragma unroll
             for (int u = 0; u < R; ++u) {
-                if (rr[u] < 0) break;
-                const bool cand = pjv[u] >= 0;
-                const bool need = cand && pjv[u] != r_i[u];
-                const unsigned cm = __ballot_sync(full, cand), nm = __ballot_sync(full, need);
-                n_edges += __popc(cm);
-                if (nm) {
-                    unsigned long long pos = 0;
-                    if (lane == 0) pos = atomicAdd(wl_count, (unsigned long long)__popc(nm));
-                    pos = __shfl_sync(full, pos, 0);
-                    if (need) worklist[pos + __popc(nm & lt)] = make_int2((int)i0 + rr[u], jv[u]);
-                    n_need += __popc(nm);
+                const bool cand = rr[u] >= 0 && pjv[u] >= 0;
+                nmv[u] = __ballot_sync(full, cand && pjv[u] != r_i[u]);
+                n_edges += __popc(__ballot_sync(full, cand));
+                tot += __popc(nmv[u]);
+            }
+            if (tot) {
+                unsigned long long pos = 0;
+                if (lane == 0) pos = atomicAdd(wl_count, (unsigned long long)tot);
+                pos = __shfl_sync(full, pos, 0);
+#pragma unroll
+                for (int u = 0; u < R; ++u) {
+                    if ((nmv[u] >> lane) & 1u) worklist[pos + __popc(nmv[u] & lt)] = make_int2((int)i0 + rr[u], jv[u]);
+                    pos += __popc(nmv[u]);
                 }
+                n_need += tot;
             }
         }
     }

@@ -23,7 +23,9 @@
 // elected lane) + TMEM allocation, warps 2-5 = epilogue (one TMEM lane quarter each).
 // Pipelines: smem B stages full/empty (TMA <-> MMA), TMEM accumulator stages full/empty
 // (MMA <-> epilogue), two stages each.
+#include <cub/cub.cuh>
 #include <cuda.h>
+#include <string.h>
 #include <cuda_bf16.h>
 #include <math.h>
 
@@ -171,34 +173,49 @@ __device__ __noinline__ bool exact_within(const double *__restrict__ x, int d, l
 // ---------------------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------------------
+#define NSB 3   // shared-memory stages of the B operand (TMA <-> MMA); 2 when a tile has 4 swizzle atoms (64 KB)
+#define NST 4   // TMEM accumulator stages of 128 columns (MMA <-> epilogue): the whole 512-column TMEM
+#define BAND_BUF 16  // band pairs a thread collects before it reserves space in the global list
+
 struct TensorParams {
-    const double *x;      // original coordinates [n, d] (exact recheck)
     const float *norm;    // [n_pad]
     ll n, n_tiles;
-    int d, atoms;
+    int atoms, nsb;
     float r2_lo, r2_hi;   // R - eps, R + eps in squared-distance units
-    double rc;            // the metric-adjusted cutoff of the exact test
-    int *deg;             // count pass out
+    int *deg;             // count pass out: definite neighbours per row
+    int *band_deg;        // count pass out: borderline pairs per row
+    int2 *band;           // count pass out: the borderline pairs (row, column), per row in ascending column order
+    unsigned long long *band_count;  // running length of `band` (may exceed band_cap: then nothing is stored)
+    ll band_cap;
     const ll *row_ptr;    // fill pass in
+    const ll *band_ptr;   // fill pass in: first entry of each row in band_res
+    const int *band_res;  // fill pass in: the row's borderline columns in ascending order, sign bit set = rejected
     int *col_idx;         // fill pass out
-    unsigned long long *stats;
 };
 
-template <bool FILL, bool SQRT>
+// One CTA owns 128 rows and walks over all 128-column tiles in ascending order.
+//   count pass: definite neighbours (d2~ <= R - eps) are counted, pairs inside the +-eps band are only
+//               RECORDED (per-thread buffers of BAND_BUF pairs, flushed with one atomic each); they are decided
+//               afterwards by band_resolve_kernel with the reference's own f64 expression, fully parallel,
+//               instead of stalling the epilogue warp (and, through it, the MMA pipeline) for ~1 us each;
+//   fill pass : the MMA chain is deterministic, so the same pairs come up in the same order -- the k-th
+//               borderline pair of a row simply reads the k-th resolved entry of that row.
+template <bool FILL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tensor_rows_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const TensorParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: A tile | B stage 0 | B stage 1 | barriers | tmem slot | column norms
+    // carve: A tile | NSB B stages | barriers | tmem slot | per-warp column norms | per-thread band buffers
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int atoms = P.atoms;
+    const int atoms = P.atoms, nsb = P.nsb;
     const uint32_t tile_bytes = (uint32_t)atoms * ATOM_BYTES;
     uint8_t *sA = smem;
-    uint8_t *sB[2] = {smem + tile_bytes, smem + 2 * tile_bytes};
-    uint64_t *bars = (uint64_t *)(smem + 3 * tile_bytes);
-    uint64_t *a_full = bars + 0, *full = bars + 1, *empty = bars + 3, *t_full = bars + 5, *t_empty = bars + 7;
-    uint32_t *tmem_slot = (uint32_t *)(bars + 9);
-    float *ncs = (float *)(bars + 10);  // [2][TT]
+    uint8_t *sB = smem + tile_bytes;
+    uint64_t *bars = (uint64_t *)(smem + (1 + nsb) * tile_bytes);
+    uint64_t *a_full = bars, *full = bars + 1, *empty = full + NSB, *t_full = empty + NSB, *t_empty = t_full + NST;
+    uint32_t *tmem_slot = (uint32_t *)(t_empty + NST);
+    float *ncs = (float *)(bars + 16);                // [4 warps][2][TT], 16-byte aligned (15 barriers + the tmem slot above)
+    int *bbuf = (int *)(ncs + 4 * 2 * TT);            // [128 threads][BAND_BUF]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const ll i0 = (ll)blockIdx.x * TT;
@@ -206,17 +223,13 @@ tensor_rows_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
     if (warp == 0 && lane == 0) {
         mbar_init(a_full, 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(full + s, 1);
-            mbar_init(empty + s, 1);
-            mbar_init(t_full + s, 1);
-            mbar_init(t_empty + s, 128);
-        }
+        for (int s = 0; s < nsb; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(NST * TT));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
@@ -230,12 +243,12 @@ tensor_rows_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             mbar_expect_tx(a_full, tile_bytes);
             for (int a = 0; a < atoms; ++a) tma_load_2d(sA + a * ATOM_BYTES, &mapA, a * KATOM, (int)i0, a_full);
             for (ll j = 0; j < n_tiles; ++j) {
-                const int s = (int)(j & 1);
-                const uint32_t ph = (uint32_t)((j >> 1) & 1);
+                const int s = (int)(j % nsb);
+                const uint32_t ph = (uint32_t)((j / nsb) & 1);
                 mbar_wait(empty + s, ph ^ 1);
                 mbar_expect_tx(full + s, tile_bytes);
                 for (int a = 0; a < atoms; ++a)
-                    tma_load_2d(sB[s] + a * ATOM_BYTES, &mapB, a * KATOM, (int)(j * TT), full + s);
+                    tma_load_2d(sB + s * tile_bytes + a * ATOM_BYTES, &mapB, a * KATOM, (int)(j * TT), full + s);
             }
         }
     } else if (warp == 1) {
@@ -246,19 +259,18 @@ tensor_rows_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             mbar_wait(a_full, 0);
             const uint32_t a_addr = smem_u32(sA);
             for (ll j = 0; j < n_tiles; ++j) {
-                const int s = (int)(j & 1);
-                const uint32_t ph = (uint32_t)((j >> 1) & 1);
-                mbar_wait(t_empty + s, ph ^ 1);   // epilogue has drained this accumulator stage
-                mbar_wait(full + s, ph);          // TMA has landed this B tile
+                const int s = (int)(j % nsb), ts = (int)(j % NST);
+                mbar_wait(t_empty + ts, (uint32_t)((j / NST) & 1) ^ 1);   // epilogue has drained this accumulator stage
+                mbar_wait(full + s, (uint32_t)((j / nsb) & 1));          // TMA has landed this B tile
                 tc_fence_after();
-                const uint32_t b_addr = smem_u32(sB[s]);
-                const uint32_t d_tmem = tmem_base + (uint32_t)s * TT;
+                const uint32_t b_addr = smem_u32(sB + s * tile_bytes);
+                const uint32_t d_tmem = tmem_base + (uint32_t)ts * TT;
                 for (int k = 0; k < atoms * 4; ++k) {  // UMMA K = 16 bf16 = 32 bytes inside the swizzle atom
                     const uint32_t off = (uint32_t)(k >> 2) * ATOM_BYTES + (uint32_t)(k & 3) * 32;
                     tc_mma(d_tmem, umma_desc(a_addr + off), umma_desc(b_addr + off), idesc, k > 0);
                 }
-                tc_commit(empty + s);   // smem stage free once these MMAs have read it
-                tc_commit(t_full + s);  // accumulator ready for the epilogue
+                tc_commit(empty + s);    // smem stage free once these MMAs have read it
+                tc_commit(t_full + ts);  // accumulator ready for the epilogue
             }
         }
     } else {
@@ -267,61 +279,99 @@ tensor_rows_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         const int row = q * 32 + lane;       // accumulator row = TMEM lane
         const int te = (warp - 2) * 32 + lane;  // 0..127 among the epilogue threads
         const ll gi = i0 + row;
-        const float nr = P.norm[gi];
         const bool live = gi < P.n;
-        ll base = (FILL && live) ? P.row_ptr[gi] : 0;
-        int cnt = 0;
-        unsigned long long n_recheck = 0;
+        const float nr = P.norm[gi];
+        // d2~ = nr + nc - 2 acc <= t   <=>   w = nc - 2 acc <= t - nr ; dead rows never pass
+        const float thr_hi = live ? P.r2_hi - nr : -INFINITY, thr_lo = live ? P.r2_lo - nr : -INFINITY;
+        float *ncw = ncs + (warp - 2) * 2 * TT;
+        int *mybuf = bbuf + te * BAND_BUF;
+        const ll base = (FILL && live) ? P.row_ptr[gi] : 0;
+        ll cursor = (FILL && live) ? P.band_ptr[gi] : 0;
+        int cnt = 0, n_band = 0, n_buf = 0;
+        auto flush_band = [&]() {
+            const ll pos = (ll)atomicAdd(P.band_count, (unsigned long long)n_buf);
+            if (pos + n_buf <= P.band_cap)
+                for (int k = 0; k < n_buf; ++k) P.band[pos + k] = make_int2((int)gi, mybuf[k]);
+            n_buf = 0;
+        };
+        float4 nn = reinterpret_cast<const float4 *>(P.norm)[lane];  // column norms of tile 0: 4 per lane
         for (ll j = 0; j < n_tiles; ++j) {
-            const int s = (int)(j & 1);
-            const uint32_t ph = (uint32_t)((j >> 1) & 1);
-            ncs[s * TT + te] = P.norm[j * TT + te];
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            mbar_wait(t_full + s, ph);
+            const int ts = (int)(j % NST);
+            float *nc = ncw + (int)(j & 1) * TT;
+            reinterpret_cast<float4 *>(nc)[lane] = nn;
+            if (j + 1 < n_tiles) nn = reinterpret_cast<const float4 *>(P.norm)[(j + 1) * (TT / 4) + lane];
+            __syncwarp();
+            mbar_wait(t_full + ts, (uint32_t)((j / NST) & 1));
             tc_fence_after();
-            const float *nc = ncs + s * TT;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * TT);
+            float va[32], vb[32];
+            tmem_ld32(taddr, va);
+#pragma unroll
             for (int chunk = 0; chunk < 4; ++chunk) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * TT + chunk * 32), v);
                 tmem_ld_wait();
+                float *cur = (chunk & 1) ? vb : va;
+                if (chunk < 3) tmem_ld32(taddr + (uint32_t)((chunk + 1) * 32), (chunk & 1) ? va : vb);
                 if (chunk == 3) {  // all reads of this accumulator stage are done: hand it back to the MMA warp
                     tc_fence_before();
-                    mbar_arrive(t_empty + s);
+                    mbar_arrive(t_empty + ts);
                 }
-                // d2~ = |xi|^2 + |xj|^2 - 2 acc ; cheap screen first: hits are rare
-                float best = INFINITY;
+                // two bit masks per lane, element c at bit 31 - c: funnel-shift the sign of (t - w) in
+                unsigned m_hi = 0, m_lo = 0;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    v[c] = fmaf(-2.f, v[c], nr + nc[chunk * 32 + c]);
-                    best = fminf(best, v[c]);
+                    const float w = fmaf(-2.f, cur[c], nc[chunk * 32 + c]);
+                    m_hi = __funnelshift_l(__float_as_uint(thr_hi - w), m_hi, 1);
+                    m_lo = __funnelshift_l(__float_as_uint(thr_lo - w), m_lo, 1);
                 }
-                if (best <= P.r2_hi && live) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        if (v[c] <= P.r2_hi) {
-                            const ll gj = j * TT + chunk * 32 + c;
-                            bool hit = v[c] <= P.r2_lo;
-                            if (!hit) {
-                                ++n_recheck;
-                                hit = exact_within<SQRT>(P.x, P.d, gi, gj, P.rc);
-                            }
-                            if (hit) {
-                                if (FILL) P.col_idx[base + cnt] = (int)gj;
-                                ++cnt;
-                            }
+                m_hi = ~m_hi;  // bit set <=> w <= thr (sign of t - w clear; NaN never occurs: norms are finite or +inf)
+                m_lo = ~m_lo;
+                if (!live) m_hi = 0;
+                while (m_hi) {
+                    const int c = __clz(m_hi);             // ascending column order
+                    const unsigned bit = 0x80000000u >> c;
+                    m_hi &= ~bit;
+                    const int gj = (int)(j * TT) + chunk * 32 + c;
+                    bool hit = (m_lo & bit) != 0;
+                    if (!hit) {  // inside the band
+                        if (FILL) {
+                            hit = P.band_res[cursor++] >= 0;
+                        } else {
+                            ++n_band;
+                            mybuf[n_buf++] = gj;
+                            if (n_buf == BAND_BUF) flush_band();
                         }
+                    }
+                    if (hit) {
+                        if (FILL) P.col_idx[base + cnt] = gj;
+                        ++cnt;
                     }
                 }
             }
         }
-        if (!FILL && live) P.deg[gi] = cnt;
-        if (!FILL && n_recheck) atomicAdd(P.stats + ST_RECHECK, n_recheck);
+        if (!FILL) {
+            if (n_buf) flush_band();
+            if (live) { P.deg[gi] = cnt; P.band_deg[gi] = n_band; }
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NST * TT));
     }
+}
+
+// the borderline pairs, decided exactly: key = row, value = column (sign bit set when the pair is NOT within the
+// cutoff); accepted pairs are added to the row's degree
+template <bool SQRT>
+__global__ void band_resolve_kernel(const double *__restrict__ x, int d, const int2 *__restrict__ band, ll count, double rc,
+                                    int *__restrict__ keys, int *__restrict__ vals, int *deg) {
+    ll k = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int2 pr = band[k];
+    const bool ok = exact_within<SQRT>(x, d, pr.x, pr.y, rc);
+    keys[k] = pr.x;
+    vals[k] = ok ? pr.y : (pr.y | (int)0x80000000);
+    if (ok) atomicAdd(deg + pr.x, 1);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -395,61 +445,112 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     const double maxnorm = hm[0];
     if (!isfinite(maxnorm)) CNN_FAIL(CNNB200_E_INVALID, "neighbour search: coordinates contain NaN or infinity");
     // |d2~ - d2| <= 2 * maxnorm * (2^-15 [bf16 split: dropped lo.lo and residuals] + K * 2^-22 [fp32
-    // accumulation in the tensor core]) + 2^-21 * maxnorm [norms rounded to f32]; see DESIGN.md
-    const double eps = 2.0 * maxnorm * (ldexp(1.0, -15) + (double)kt * ldexp(1.0, -22)) + ldexp(maxnorm, -21) + 1e-30;
+    // accumulation in the tensor core]) + 2^-20 * maxnorm [norms rounded to f32, the f32 roundings of
+    // nc - 2 acc and of t - nr in the epilogue]; see DESIGN.md
+    const double eps = 2.0 * maxnorm * (ldexp(1.0, -15) + (double)kt * ldexp(1.0, -22)) + ldexp(maxnorm, -20) + 1e-30;
 
     CUtensorMap mapA, mapB;
     CNN_TRY(make_map(&mapA, A, n_pad, kt));
     CNN_TRY(make_map(&mapB, B, n_pad, kt));
 
+    CNN_TRY(cnn_ensure(ctx, ctx->b_cell_id, sizeof(int) * (size_t)(n + 1)));   // borderline pairs per row
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
+    unsigned long long *band_count = (unsigned long long *)(ctx->b_tmp2.as<char>() + 48);
+    int *band_deg = ctx->b_cell_id.as<int>();
+
     TensorParams P;
-    P.x = d_x;
+    memset(&P, 0, sizeof(P));
     P.norm = norm;
     P.n = n;
     P.n_tiles = n_tiles;
-    P.d = (int)d;
     P.atoms = atoms;
+    P.nsb = atoms >= 4 ? 2 : NSB;
     P.r2_lo = (float)(R - eps);
     P.r2_hi = (float)(R + eps);
     // keep the f32 thresholds on the safe side of the f64 ones
     P.r2_lo = nextafterf(P.r2_lo, -INFINITY);
     P.r2_hi = nextafterf(P.r2_hi, INFINITY);
-    P.rc = radius_cutoff;
     P.deg = ctx->b_deg.as<int>();
-    P.row_ptr = nullptr;
-    P.col_idx = nullptr;
-    P.stats = (unsigned long long *)ctx->b_stats.p;
+    P.band_deg = band_deg;
+    P.band_count = band_count;
 
-    const size_t smem = (size_t)3 * atoms * ATOM_BYTES + 1024 /*alignment*/ + 80 + 4 + 2 * TT * sizeof(float) + 64;
-    auto k_count = sq ? tensor_rows_kernel<false, true> : tensor_rows_kernel<false, false>;
-    auto k_fill = sq ? tensor_rows_kernel<true, true> : tensor_rows_kernel<true, false>;
-    CNN_CUDA(cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CNN_CUDA(cudaFuncSetAttribute(k_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)(1 + P.nsb) * atoms * ATOM_BYTES + 1024 /*alignment*/ + 16 * 8 +
+                        4 * 2 * TT * sizeof(float) + 128 * BAND_BUF * sizeof(int) + 64;
+    CNN_CUDA(cudaFuncSetAttribute(tensor_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CNN_CUDA(cudaFuncSetAttribute(tensor_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
-    CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>() + n, 0, sizeof(int), st));
+    // ---- count pass (rerun once with a larger list should the borderline pairs not fit) ----------------------
+    ll band_total = 0;
+    ll band_cap = ctx->tensor_band_cap > 0 ? ctx->tensor_band_cap : (64 * n > (1ll << 20) ? 64 * n : (1ll << 20));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CNN_TRY(cnn_ensure(ctx, ctx->b_worklist, sizeof(int2) * (size_t)band_cap));
+        P.band = ctx->b_worklist.as<int2>();
+        P.band_cap = band_cap;
+        CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>(), 0, sizeof(int) * (size_t)(n + 1), st));
+        CNN_CUDA(cudaMemsetAsync(band_deg, 0, sizeof(int) * (size_t)(n + 1), st));
+        CNN_CUDA(cudaMemsetAsync(band_count, 0, sizeof(unsigned long long), st));
+        {
+            Span sp(ctx, T_SEARCH_COUNT);
+            tensor_rows_kernel<false><<<(int)n_tiles, NUM_THREADS, smem, st>>>(mapA, mapB, P);
+            CNN_LAUNCHED(ctx, 1);
+            CNN_KERNEL_CHECK();
+        }
+        unsigned long long *hb;
+        CNN_TRY(cnn_pinned(ctx, 64, (void **)&hb));
+        CNN_CUDA(cudaMemcpyAsync(hb, band_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CNN_CUDA(cudaStreamSynchronize(st));
+        band_total = (ll)hb[0];
+        if (band_total <= band_cap) break;
+        if (attempt == 1) CNN_FAIL(CNNB200_E_STATE, "tensor search: borderline-pair list overflowed twice");
+        band_cap = band_total + band_total / 16 + 1024;
+    }
+    ctx->tensor_band_cap = band_cap;
+
+    // ---- borderline pairs: exact decision, then grouped by row (stable: columns stay ascending) -------------
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(int) * (size_t)(band_total + 1) * 4));
+    int *keys = ctx->b_tmp0.as<int>(), *vals = keys + (band_total + 1), *keys2 = vals + (band_total + 1),
+        *vals2 = keys2 + (band_total + 1);
+    CNN_TRY(cnn_ensure(ctx, ctx->b_lab_keys, sizeof(ll) * (size_t)(n + 1)));
+    ll *band_ptr = ctx->b_lab_keys.as<ll>();
     {
-        Span sp(ctx, T_SEARCH_COUNT);
-        k_count<<<(int)n_tiles, NUM_THREADS, smem, st>>>(mapA, mapB, P);
-        CNN_LAUNCHED(ctx, 1);
-        CNN_KERNEL_CHECK();
+        Span sp(ctx, T_SCAN);
+        if (band_total > 0) {
+            if (sq)
+                band_resolve_kernel<true><<<cnn_blocks(band_total, 256), 256, 0, st>>>(d_x, (int)d, P.band, band_total,
+                                                                                   radius_cutoff, keys, vals, P.deg);
+            else
+                band_resolve_kernel<false><<<cnn_blocks(band_total, 256), 256, 0, st>>>(d_x, (int)d, P.band, band_total,
+                                                                                    radius_cutoff, keys, vals, P.deg);
+            CNN_LAUNCHED(ctx, 1);
+            CNN_KERNEL_CHECK();
+            int bits = 1;
+            while ((1ll << bits) < n) ++bits;
+            size_t need = 0;
+            CNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys2, vals, vals2, (int)band_total, 0, bits, st));
+            CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
+            size_t cap = ctx->b_cub.cap;
+            CNN_CUDA(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, cap, keys, keys2, vals, vals2, (int)band_total, 0, bits, st));
+        }
+        size_t need = 0;
+        CNN_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, need, band_deg, band_ptr, ::cuda::std::plus<>{}, (ll)0, (int)(n + 1), st));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
+        size_t cap = ctx->b_cub.cap;
+        CNN_CUDA(cub::DeviceScan::ExclusiveScan(ctx->b_cub.p, cap, band_deg, band_ptr, ::cuda::std::plus<>{}, (ll)0, (int)(n + 1), st));
     }
     ll nnz = 0, max_deg = 0;
     CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
     CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
     P.row_ptr = ctx->b_row_ptr.as<ll>();
     P.col_idx = ctx->b_col_idx.as<int>();
+    P.band_ptr = band_ptr;
+    P.band_res = vals2;
     {
         Span sp(ctx, T_SEARCH_FILL);
-        k_fill<<<(int)n_tiles, NUM_THREADS, smem, st>>>(mapA, mapB, P);
+        tensor_rows_kernel<true><<<(int)n_tiles, NUM_THREADS, smem, st>>>(mapA, mapB, P);
         CNN_LAUNCHED(ctx, 1);
         CNN_KERNEL_CHECK();
     }
-    unsigned long long *hs;
-    CNN_TRY(cnn_pinned(ctx, 64, (void **)&hs));
-    CNN_CUDA(cudaMemcpyAsync(hs, (unsigned long long *)ctx->b_stats.p + ST_RECHECK, sizeof(unsigned long long),
-                             cudaMemcpyDeviceToHost, st));
-    CNN_CUDA(cudaStreamSynchronize(st));
-    ctx->stats[ST_RECHECK] = (ll)hs[0];
+    ctx->stats[ST_RECHECK] = band_total;
     ctx->stats[ST_DIST] = n * n;
     ctx->n = n;
     ctx->nnz = nnz;

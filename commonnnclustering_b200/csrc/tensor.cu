@@ -35,7 +35,6 @@
 #define KATOM 64          // bf16 elements per 128-byte swizzle atom
 #define ATOM_BYTES (TT * 128)
 #define MAX_ATOMS 4
-#define NUM_THREADS 192
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -175,56 +174,57 @@ __device__ __noinline__ bool exact_within(const double *__restrict__ x, int d, l
 // ---------------------------------------------------------------------------------------------------
 #define NSB 3   // shared-memory stages of the B operand (TMA <-> MMA); 2 when a tile has 4 swizzle atoms (64 KB)
 #define NST 4   // TMEM accumulator stages of 128 columns (MMA <-> epilogue): the whole 512-column TMEM
-#define BAND_BUF 16  // band pairs a thread collects before it reserves space in the global list
+#define PAIR_BUF 16     // pairs a thread collects before it reserves space in the global list
+#define EPI_WARPS 8     // epilogue warps: two per TMEM lane quarter, 64 columns of a tile each
+#define NUM_THREADS ((2 + EPI_WARPS) * 32)
+#define BAND_FLAG 0x80000000u
 
 struct TensorParams {
     const float *norm;    // [n_pad]
     ll n, n_tiles;
     int atoms, nsb;
     float r2_lo, r2_hi;   // R - eps, R + eps in squared-distance units
-    int *deg;             // count pass out: definite neighbours per row
-    int *band_deg;        // count pass out: borderline pairs per row
-    int2 *band;           // count pass out: the borderline pairs (row, column), per row in ascending column order
-    unsigned long long *band_count;  // running length of `band` (may exceed band_cap: then nothing is stored)
-    ll band_cap;
-    const ll *row_ptr;    // fill pass in
-    const ll *band_ptr;   // fill pass in: first entry of each row in band_res
-    const int *band_res;  // fill pass in: the row's borderline columns in ascending order, sign bit set = rejected
-    int *col_idx;         // fill pass out
+    int2 *pairs;          // out: (i, j) with i < j; j carries BAND_FLAG when the pair is inside the +-eps band
+    unsigned long long *pair_count;  // running length of `pairs` (may exceed pair_cap: then nothing is stored)
+    ll pair_cap;
 };
 
-// One CTA owns 128 rows and walks over all 128-column tiles in ascending order.
-//   count pass: definite neighbours (d2~ <= R - eps) are counted, pairs inside the +-eps band are only
-//               RECORDED (per-thread buffers of BAND_BUF pairs, flushed with one atomic each); they are decided
-//               afterwards by band_resolve_kernel with the reference's own f64 expression, fully parallel,
-//               instead of stalling the epilogue warp (and, through it, the MMA pipeline) for ~1 us each;
-//   fill pass : the MMA chain is deterministic, so the same pairs come up in the same order -- the k-th
-//               borderline pair of a row simply reads the k-th resolved entry of that row.
-template <bool FILL>
+// SINGLE pass over the upper triangle of the tile grid.  CTA c owns the row tiles c and n_tiles-1-c (together
+// n_tiles+1 column tiles: every CTA does the same amount of work) and walks each one's column tiles J >= I.
+// The epilogue classifies every accumulator element -- d2~ <= R - eps: neighbours, d2~ > R + eps: not, otherwise
+// borderline -- and only EMITS pairs (i < j) into a global list (per-thread buffers of PAIR_BUF pairs, one atomic
+// per flush).  Borderline pairs are decided afterwards by pair_resolve_kernel with the reference's own f64
+// expression, fully parallel, instead of stalling an epilogue warp (and, through it, the MMA pipeline) for ~1 us
+// each; degrees, row offsets and the two directed entries of every pair follow from the list, and one segmented
+// sort puts the rows in ascending order.  Nothing depends on the order in which tiles are visited.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tensor_rows_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                   const TensorParams P) {
+tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const TensorParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: A tile | NSB B stages | barriers | tmem slot | per-warp column norms | per-thread band buffers
+    // carve: A tile | nsb B stages | barriers | tmem slot | per-warp column norms | per-thread pair buffers
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int atoms = P.atoms, nsb = P.nsb;
     const uint32_t tile_bytes = (uint32_t)atoms * ATOM_BYTES;
     uint8_t *sA = smem;
     uint8_t *sB = smem + tile_bytes;
     uint64_t *bars = (uint64_t *)(smem + (1 + nsb) * tile_bytes);
-    uint64_t *a_full = bars, *full = bars + 1, *empty = full + NSB, *t_full = empty + NSB, *t_empty = t_full + NST;
+    uint64_t *a_full = bars, *a_empty = bars + 1, *full = bars + 2, *empty = full + NSB, *t_full = empty + NSB,
+             *t_empty = t_full + NST;
     uint32_t *tmem_slot = (uint32_t *)(t_empty + NST);
-    float *ncs = (float *)(bars + 16);                // [4 warps][2][TT], 16-byte aligned (15 barriers + the tmem slot above)
-    int *bbuf = (int *)(ncs + 4 * 2 * TT);            // [128 threads][BAND_BUF]
+    float *ncs = (float *)(bars + 20);                  // [EPI_WARPS][2][64], 16-byte aligned
+    int *pbuf = (int *)(ncs + EPI_WARPS * 2 * 64);      // [EPI_WARPS * 32][PAIR_BUF]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const ll i0 = (ll)blockIdx.x * TT;
     const ll n_tiles = P.n_tiles;
+    // the CTA's row tiles
+    const ll I_a = blockIdx.x, I_b = n_tiles - 1 - (ll)blockIdx.x;
+    const int n_rows_tiles = I_b > I_a ? 2 : 1;
 
     if (warp == 0 && lane == 0) {
         mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
         for (int s = 0; s < nsb; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < NST; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 128); }
+        for (int s = 0; s < NST; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, EPI_WARPS * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -240,15 +240,19 @@ tensor_rows_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            mbar_expect_tx(a_full, tile_bytes);
-            for (int a = 0; a < atoms; ++a) tma_load_2d(sA + a * ATOM_BYTES, &mapA, a * KATOM, (int)i0, a_full);
-            for (ll j = 0; j < n_tiles; ++j) {
-                const int s = (int)(j % nsb);
-                const uint32_t ph = (uint32_t)((j / nsb) & 1);
-                mbar_wait(empty + s, ph ^ 1);
-                mbar_expect_tx(full + s, tile_bytes);
-                for (int a = 0; a < atoms; ++a)
-                    tma_load_2d(sB + s * tile_bytes + a * ATOM_BYTES, &mapB, a * KATOM, (int)(j * TT), full + s);
+            ll t = 0;  // running tile count: stage and phase bookkeeping continues across the row tiles
+            for (int rt = 0; rt < n_rows_tiles; ++rt) {
+                const ll I = rt == 0 ? I_a : I_b;
+                if (rt > 0) mbar_wait(a_empty, 0);  // every MMA of the first row tile has read sA
+                mbar_expect_tx(a_full, tile_bytes);
+                for (int a = 0; a < atoms; ++a) tma_load_2d(sA + a * ATOM_BYTES, &mapA, a * KATOM, (int)(I * TT), a_full);
+                for (ll j = I; j < n_tiles; ++j, ++t) {
+                    const int s = (int)(t % nsb);
+                    mbar_wait(empty + s, (uint32_t)((t / nsb) & 1) ^ 1);
+                    mbar_expect_tx(full + s, tile_bytes);
+                    for (int a = 0; a < atoms; ++a)
+                        tma_load_2d(sB + s * tile_bytes + a * ATOM_BYTES, &mapB, a * KATOM, (int)(j * TT), full + s);
+                }
             }
         }
     } else if (warp == 1) {
@@ -256,102 +260,99 @@ tensor_rows_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         if (lane == 0) {
             // instruction descriptor: D f32, A/B bf16, both K-major, N = 128, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(TT >> 4) << 24);
-            mbar_wait(a_full, 0);
             const uint32_t a_addr = smem_u32(sA);
-            for (ll j = 0; j < n_tiles; ++j) {
-                const int s = (int)(j % nsb), ts = (int)(j % NST);
-                mbar_wait(t_empty + ts, (uint32_t)((j / NST) & 1) ^ 1);   // epilogue has drained this accumulator stage
-                mbar_wait(full + s, (uint32_t)((j / nsb) & 1));          // TMA has landed this B tile
-                tc_fence_after();
-                const uint32_t b_addr = smem_u32(sB + s * tile_bytes);
-                const uint32_t d_tmem = tmem_base + (uint32_t)ts * TT;
-                for (int k = 0; k < atoms * 4; ++k) {  // UMMA K = 16 bf16 = 32 bytes inside the swizzle atom
-                    const uint32_t off = (uint32_t)(k >> 2) * ATOM_BYTES + (uint32_t)(k & 3) * 32;
-                    tc_mma(d_tmem, umma_desc(a_addr + off), umma_desc(b_addr + off), idesc, k > 0);
+            ll t = 0;
+            for (int rt = 0; rt < n_rows_tiles; ++rt) {
+                const ll I = rt == 0 ? I_a : I_b;
+                mbar_wait(a_full, (uint32_t)rt);
+                for (ll j = I; j < n_tiles; ++j, ++t) {
+                    const int s = (int)(t % nsb), ts = (int)(t % NST);
+                    mbar_wait(t_empty + ts, (uint32_t)((t / NST) & 1) ^ 1);   // epilogue has drained this accumulator stage
+                    mbar_wait(full + s, (uint32_t)((t / nsb) & 1));          // TMA has landed this B tile
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(sB + s * tile_bytes);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)ts * TT;
+                    for (int k = 0; k < atoms * 4; ++k) {  // UMMA K = 16 bf16 = 32 bytes inside the swizzle atom
+                        const uint32_t off = (uint32_t)(k >> 2) * ATOM_BYTES + (uint32_t)(k & 3) * 32;
+                        tc_mma(d_tmem, umma_desc(a_addr + off), umma_desc(b_addr + off), idesc, k > 0);
+                    }
+                    tc_commit(empty + s);    // smem stage free once these MMAs have read it
+                    tc_commit(t_full + ts);  // accumulator ready for the epilogue
                 }
-                tc_commit(empty + s);    // smem stage free once these MMAs have read it
-                tc_commit(t_full + ts);  // accumulator ready for the epilogue
+                tc_commit(a_empty);          // the A tile may be replaced
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> classify -> (count | write) =====
+        // ===== epilogue: TMEM -> registers -> classify -> emit pairs =====
+        const int ew = warp - 2;             // 0 .. EPI_WARPS-1
         const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const int half = ew >> 2;            // which 64 columns of a tile (warps 2-5 and 6-9 cover the quarters 2,3,0,1)
         const int row = q * 32 + lane;       // accumulator row = TMEM lane
-        const int te = (warp - 2) * 32 + lane;  // 0..127 among the epilogue threads
-        const ll gi = i0 + row;
-        const bool live = gi < P.n;
-        const float nr = P.norm[gi];
-        // d2~ = nr + nc - 2 acc <= t   <=>   w = nc - 2 acc <= t - nr ; dead rows never pass
-        const float thr_hi = live ? P.r2_hi - nr : -INFINITY, thr_lo = live ? P.r2_lo - nr : -INFINITY;
-        float *ncw = ncs + (warp - 2) * 2 * TT;
-        int *mybuf = bbuf + te * BAND_BUF;
-        const ll base = (FILL && live) ? P.row_ptr[gi] : 0;
-        ll cursor = (FILL && live) ? P.band_ptr[gi] : 0;
-        int cnt = 0, n_band = 0, n_buf = 0;
-        auto flush_band = [&]() {
-            const ll pos = (ll)atomicAdd(P.band_count, (unsigned long long)n_buf);
-            if (pos + n_buf <= P.band_cap)
-                for (int k = 0; k < n_buf; ++k) P.band[pos + k] = make_int2((int)gi, mybuf[k]);
+        float *ncw = ncs + ew * 2 * 64;
+        int *mybuf = pbuf + (ew * 32 + lane) * PAIR_BUF;
+        int n_buf = 0;
+        ll gi = 0;
+        auto flush = [&]() {
+            const ll pos = (ll)atomicAdd(P.pair_count, (unsigned long long)n_buf);
+            if (pos + n_buf <= P.pair_cap)
+                for (int k = 0; k < n_buf; ++k) P.pairs[pos + k] = make_int2((int)gi, mybuf[k]);
             n_buf = 0;
         };
-        float4 nn = reinterpret_cast<const float4 *>(P.norm)[lane];  // column norms of tile 0: 4 per lane
-        for (ll j = 0; j < n_tiles; ++j) {
-            const int ts = (int)(j % NST);
-            float *nc = ncw + (int)(j & 1) * TT;
-            reinterpret_cast<float4 *>(nc)[lane] = nn;
-            if (j + 1 < n_tiles) nn = reinterpret_cast<const float4 *>(P.norm)[(j + 1) * (TT / 4) + lane];
-            __syncwarp();
-            mbar_wait(t_full + ts, (uint32_t)((j / NST) & 1));
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * TT);
-            float va[32], vb[32];
-            tmem_ld32(taddr, va);
-#pragma unroll
-            for (int chunk = 0; chunk < 4; ++chunk) {
+        ll t = 0;
+        for (int rt = 0; rt < n_rows_tiles; ++rt) {
+            const ll I = rt == 0 ? I_a : I_b;
+            if (n_buf) flush();  // the buffered pairs belong to the previous row
+            gi = I * TT + row;
+            const bool live = gi < P.n;
+            const float nr = P.norm[gi];
+            // d2~ = nr + nc - 2 acc <= thr   <=>   w = nc - 2 acc <= thr - nr ; dead rows never pass
+            const float thr_hi = live ? P.r2_hi - nr : -INFINITY, thr_lo = live ? P.r2_lo - nr : -INFINITY;
+            // column norms of this thread's 64 columns of the next tile: 2 per lane
+            float2 nn = reinterpret_cast<const float2 *>(P.norm + I * TT + half * 64)[lane];
+            for (ll j = I; j < n_tiles; ++j, ++t) {
+                const int ts = (int)(t % NST);
+                float *nc = ncw + (int)(t & 1) * 64;
+                reinterpret_cast<float2 *>(nc)[lane] = nn;
+                if (j + 1 < n_tiles) nn = reinterpret_cast<const float2 *>(P.norm + (j + 1) * TT + half * 64)[lane];
+                __syncwarp();
+                mbar_wait(t_full + ts, (uint32_t)((t / NST) & 1));
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * TT + half * 64);
+                float va[32], vb[32];
+                tmem_ld32(taddr, va);
+                tmem_ld32(taddr + 32, vb);
                 tmem_ld_wait();
-                float *cur = (chunk & 1) ? vb : va;
-                if (chunk < 3) tmem_ld32(taddr + (uint32_t)((chunk + 1) * 32), (chunk & 1) ? va : vb);
-                if (chunk == 3) {  // all reads of this accumulator stage are done: hand it back to the MMA warp
-                    tc_fence_before();
-                    mbar_arrive(t_empty + ts);
-                }
-                // two bit masks per lane, element c at bit 31 - c: funnel-shift the sign of (t - w) in
-                unsigned m_hi = 0, m_lo = 0;
+                // both chunks are in registers: hand the accumulator stage back to the MMA warp
+                tc_fence_before();
+                mbar_arrive(t_empty + ts);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float w = fmaf(-2.f, cur[c], nc[chunk * 32 + c]);
-                    m_hi = __funnelshift_l(__float_as_uint(thr_hi - w), m_hi, 1);
-                    m_lo = __funnelshift_l(__float_as_uint(thr_lo - w), m_lo, 1);
-                }
-                m_hi = ~m_hi;  // bit set <=> w <= thr (sign of t - w clear; NaN never occurs: norms are finite or +inf)
-                m_lo = ~m_lo;
-                if (!live) m_hi = 0;
-                while (m_hi) {
-                    const int c = __clz(m_hi);             // ascending column order
-                    const unsigned bit = 0x80000000u >> c;
-                    m_hi &= ~bit;
-                    const int gj = (int)(j * TT) + chunk * 32 + c;
-                    bool hit = (m_lo & bit) != 0;
-                    if (!hit) {  // inside the band
-                        if (FILL) {
-                            hit = P.band_res[cursor++] >= 0;
-                        } else {
-                            ++n_band;
-                            mybuf[n_buf++] = gj;
-                            if (n_buf == BAND_BUF) flush_band();
-                        }
+                for (int chunk = 0; chunk < 2; ++chunk) {
+                    const float *cur = chunk ? vb : va;
+                    // two bit masks per lane, element c at bit 31 - c: funnel-shift the sign of (thr - w) in
+                    unsigned m_hi = 0, m_lo = 0;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float w = fmaf(-2.f, cur[c], nc[chunk * 32 + c]);
+                        m_hi = __funnelshift_l(__float_as_uint(thr_hi - w), m_hi, 1);
+                        m_lo = __funnelshift_l(__float_as_uint(thr_lo - w), m_lo, 1);
                     }
-                    if (hit) {
-                        if (FILL) P.col_idx[base + cnt] = gj;
-                        ++cnt;
+                    m_hi = ~m_hi;  // bit set <=> w <= thr (the difference is never NaN: norms are finite or +inf)
+                    m_lo = ~m_lo;
+                    if (!live) m_hi = 0;
+                    const int col0 = (int)(j * TT) + half * 64 + chunk * 32;
+                    while (m_hi) {
+                        const int c = __clz(m_hi);
+                        const unsigned bit = 0x80000000u >> c;
+                        m_hi &= ~bit;
+                        const int gj = col0 + c;
+                        if (gj <= (int)gi) continue;  // diagonal tile: lower triangle and self are not emitted
+                        mybuf[n_buf++] = (m_lo & bit) ? gj : (int)((unsigned)gj | BAND_FLAG);
+                        if (n_buf == PAIR_BUF) flush();
                     }
                 }
             }
         }
-        if (!FILL) {
-            if (n_buf) flush_band();
-            if (live) { P.deg[gi] = cnt; P.band_deg[gi] = n_band; }
-        }
+        if (n_buf) flush();
     }
     tc_fence_before();
     __syncthreads();
@@ -360,18 +361,51 @@ tensor_rows_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
 }
 
-// the borderline pairs, decided exactly: key = row, value = column (sign bit set when the pair is NOT within the
-// cutoff); accepted pairs are added to the row's degree
+// borderline pairs are decided exactly (rejected ones get i = -1); every surviving pair adds one to both degrees
 template <bool SQRT>
-__global__ void band_resolve_kernel(const double *__restrict__ x, int d, const int2 *__restrict__ band, ll count, double rc,
-                                    int *__restrict__ keys, int *__restrict__ vals, int *deg) {
+__global__ void pair_resolve_kernel(const double *__restrict__ x, int d, int2 *__restrict__ pairs, ll count, double rc,
+                                    int *deg, unsigned long long *n_band) {
     ll k = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    bool band = false;
+    if (k < count) {
+        int2 pr = pairs[k];
+        band = ((unsigned)pr.y & BAND_FLAG) != 0;
+        bool ok = true;
+        if (band) {
+            pr.y = (int)((unsigned)pr.y & ~BAND_FLAG);
+            ok = exact_within<SQRT>(x, d, pr.x, pr.y, rc);
+            pairs[k] = ok ? pr : make_int2(-1, -1);
+        }
+        if (ok) {
+            atomicAdd(deg + pr.x, 1);
+            atomicAdd(deg + pr.y, 1);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, band);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_band, (unsigned long long)__popc(m));
+}
+
+// Both directed entries of every surviving pair and the self entry of every row as 64-bit keys (row : column);
+// rejected pairs become all-ones keys that sort behind everything.  After one radix sort the low words of the first
+// nnz keys ARE col_idx (rows ascending, columns ascending within a row).
+__global__ void pair_keys_kernel(const int2 *__restrict__ pairs, ll count, ll n, unsigned long long *__restrict__ keys) {
+    ll k = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (k < n) keys[2 * count + k] = ((unsigned long long)k << 32) | (unsigned long long)k;
     if (k >= count) return;
-    const int2 pr = band[k];
-    const bool ok = exact_within<SQRT>(x, d, pr.x, pr.y, rc);
-    keys[k] = pr.x;
-    vals[k] = ok ? pr.y : (pr.y | (int)0x80000000);
-    if (ok) atomicAdd(deg + pr.x, 1);
+    const int2 pr = pairs[k];
+    const bool ok = pr.x >= 0;
+    keys[2 * k] = ok ? ((unsigned long long)(unsigned)pr.x << 32) | (unsigned)pr.y : ~0ull;
+    keys[2 * k + 1] = ok ? ((unsigned long long)(unsigned)pr.y << 32) | (unsigned)pr.x : ~0ull;
+}
+
+__global__ void keys_to_cols_kernel(const unsigned long long *__restrict__ keys, ll nnz, int *__restrict__ col_idx) {
+    ll k = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (k < nnz) col_idx[k] = (int)(unsigned)(keys[k] & 0xffffffffull);
+}
+
+__global__ void fill_ones_kernel(int *a, ll n, ll n_total) {
+    ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (i < n_total) a[i] = i < n ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -453,10 +487,9 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     CNN_TRY(make_map(&mapA, A, n_pad, kt));
     CNN_TRY(make_map(&mapB, B, n_pad, kt));
 
-    CNN_TRY(cnn_ensure(ctx, ctx->b_cell_id, sizeof(int) * (size_t)(n + 1)));   // borderline pairs per row
     CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
-    unsigned long long *band_count = (unsigned long long *)(ctx->b_tmp2.as<char>() + 48);
-    int *band_deg = ctx->b_cell_id.as<int>();
+    unsigned long long *pair_count = (unsigned long long *)(ctx->b_tmp2.as<char>() + 48);
+    unsigned long long *band_count = pair_count + 1;
 
     TensorParams P;
     memset(&P, 0, sizeof(P));
@@ -470,88 +503,83 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     // keep the f32 thresholds on the safe side of the f64 ones
     P.r2_lo = nextafterf(P.r2_lo, -INFINITY);
     P.r2_hi = nextafterf(P.r2_hi, INFINITY);
-    P.deg = ctx->b_deg.as<int>();
-    P.band_deg = band_deg;
-    P.band_count = band_count;
+    P.pair_count = pair_count;
 
-    const size_t smem = (size_t)(1 + P.nsb) * atoms * ATOM_BYTES + 1024 /*alignment*/ + 16 * 8 +
-                        4 * 2 * TT * sizeof(float) + 128 * BAND_BUF * sizeof(int) + 64;
-    CNN_CUDA(cudaFuncSetAttribute(tensor_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CNN_CUDA(cudaFuncSetAttribute(tensor_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)(1 + P.nsb) * atoms * ATOM_BYTES + 1024 /*alignment*/ + 20 * 8 +
+                        EPI_WARPS * 2 * 64 * sizeof(float) + EPI_WARPS * 32 * PAIR_BUF * sizeof(int) + 64;
+    CNN_CUDA(cudaFuncSetAttribute(tensor_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
-    // ---- count pass (rerun once with a larger list should the borderline pairs not fit) ----------------------
-    ll band_total = 0;
-    ll band_cap = ctx->tensor_band_cap > 0 ? ctx->tensor_band_cap : (64 * n > (1ll << 20) ? 64 * n : (1ll << 20));
+    // ---- the pass over the upper triangle (rerun once with a larger list should the pairs not fit) ------------
+    ll n_pairs = 0;
+    ll pair_cap = ctx->tensor_band_cap > 0 ? ctx->tensor_band_cap : (128 * n > (1ll << 20) ? 128 * n : (1ll << 20));
+    unsigned long long *hb;
+    CNN_TRY(cnn_pinned(ctx, 64, (void **)&hb));
     for (int attempt = 0; attempt < 2; ++attempt) {
-        CNN_TRY(cnn_ensure(ctx, ctx->b_worklist, sizeof(int2) * (size_t)band_cap));
-        P.band = ctx->b_worklist.as<int2>();
-        P.band_cap = band_cap;
-        CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>(), 0, sizeof(int) * (size_t)(n + 1), st));
-        CNN_CUDA(cudaMemsetAsync(band_deg, 0, sizeof(int) * (size_t)(n + 1), st));
-        CNN_CUDA(cudaMemsetAsync(band_count, 0, sizeof(unsigned long long), st));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_worklist, sizeof(int2) * (size_t)pair_cap));
+        P.pairs = ctx->b_worklist.as<int2>();
+        P.pair_cap = pair_cap;
+        CNN_CUDA(cudaMemsetAsync(pair_count, 0, 2 * sizeof(unsigned long long), st));
         {
             Span sp(ctx, T_SEARCH_COUNT);
-            tensor_rows_kernel<false><<<(int)n_tiles, NUM_THREADS, smem, st>>>(mapA, mapB, P);
+            tensor_pairs_kernel<<<(int)((n_tiles + 1) / 2), NUM_THREADS, smem, st>>>(mapA, mapB, P);
             CNN_LAUNCHED(ctx, 1);
             CNN_KERNEL_CHECK();
         }
-        unsigned long long *hb;
-        CNN_TRY(cnn_pinned(ctx, 64, (void **)&hb));
-        CNN_CUDA(cudaMemcpyAsync(hb, band_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CNN_CUDA(cudaMemcpyAsync(hb, pair_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CNN_CUDA(cudaStreamSynchronize(st));
-        band_total = (ll)hb[0];
-        if (band_total <= band_cap) break;
-        if (attempt == 1) CNN_FAIL(CNNB200_E_STATE, "tensor search: borderline-pair list overflowed twice");
-        band_cap = band_total + band_total / 16 + 1024;
+        n_pairs = (ll)hb[0];
+        if (n_pairs <= pair_cap) break;
+        if (attempt == 1) CNN_FAIL(CNNB200_E_STATE, "tensor search: pair list overflowed twice");
+        pair_cap = n_pairs + n_pairs / 16 + 1024;
     }
-    ctx->tensor_band_cap = band_cap;
+    ctx->tensor_band_cap = pair_cap;
 
-    // ---- borderline pairs: exact decision, then grouped by row (stable: columns stay ascending) -------------
-    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(int) * (size_t)(band_total + 1) * 4));
-    int *keys = ctx->b_tmp0.as<int>(), *vals = keys + (band_total + 1), *keys2 = vals + (band_total + 1),
-        *vals2 = keys2 + (band_total + 1);
-    CNN_TRY(cnn_ensure(ctx, ctx->b_lab_keys, sizeof(ll) * (size_t)(n + 1)));
-    ll *band_ptr = ctx->b_lab_keys.as<ll>();
+    // ---- degrees: self + both ends of every pair that survives the exact test of the borderline ones ----------
+    int *deg = ctx->b_deg.as<int>();
     {
         Span sp(ctx, T_SCAN);
-        if (band_total > 0) {
+        fill_ones_kernel<<<cnn_blocks(n + 1, 256), 256, 0, st>>>(deg, n, n + 1);
+        if (n_pairs > 0) {
             if (sq)
-                band_resolve_kernel<true><<<cnn_blocks(band_total, 256), 256, 0, st>>>(d_x, (int)d, P.band, band_total,
-                                                                                   radius_cutoff, keys, vals, P.deg);
+                pair_resolve_kernel<true><<<cnn_blocks(n_pairs, 256), 256, 0, st>>>(d_x, (int)d, P.pairs, n_pairs, radius_cutoff,
+                                                                                deg, band_count);
             else
-                band_resolve_kernel<false><<<cnn_blocks(band_total, 256), 256, 0, st>>>(d_x, (int)d, P.band, band_total,
-                                                                                    radius_cutoff, keys, vals, P.deg);
-            CNN_LAUNCHED(ctx, 1);
-            CNN_KERNEL_CHECK();
-            int bits = 1;
-            while ((1ll << bits) < n) ++bits;
-            size_t need = 0;
-            CNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys2, vals, vals2, (int)band_total, 0, bits, st));
-            CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
-            size_t cap = ctx->b_cub.cap;
-            CNN_CUDA(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, cap, keys, keys2, vals, vals2, (int)band_total, 0, bits, st));
+                pair_resolve_kernel<false><<<cnn_blocks(n_pairs, 256), 256, 0, st>>>(d_x, (int)d, P.pairs, n_pairs, radius_cutoff,
+                                                                                 deg, band_count);
         }
-        size_t need = 0;
-        CNN_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, need, band_deg, band_ptr, ::cuda::std::plus<>{}, (ll)0, (int)(n + 1), st));
-        CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
-        size_t cap = ctx->b_cub.cap;
-        CNN_CUDA(cub::DeviceScan::ExclusiveScan(ctx->b_cub.p, cap, band_deg, band_ptr, ::cuda::std::plus<>{}, (ll)0, (int)(n + 1), st));
-    }
-    ll nnz = 0, max_deg = 0;
-    CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
-    CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
-    P.row_ptr = ctx->b_row_ptr.as<ll>();
-    P.col_idx = ctx->b_col_idx.as<int>();
-    P.band_ptr = band_ptr;
-    P.band_res = vals2;
-    {
-        Span sp(ctx, T_SEARCH_FILL);
-        tensor_rows_kernel<true><<<(int)n_tiles, NUM_THREADS, smem, st>>>(mapA, mapB, P);
-        CNN_LAUNCHED(ctx, 1);
+        CNN_LAUNCHED(ctx, 2);
         CNN_KERNEL_CHECK();
     }
-    ctx->stats[ST_RECHECK] = band_total;
-    ctx->stats[ST_DIST] = n * n;
+    ll nnz = 0, max_deg = 0;
+    CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, deg, n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
+    if (nnz >= (1ll << 31) - 1) CNN_FAIL(CNNB200_E_RANGE, "tensor search: more than 2^31 neighbour entries");
+    // ---- (row : column) keys of both directions + self, one radix sort, low words = col_idx -----------------------
+    CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
+    const ll n_keys = 2 * n_pairs + n;
+    if (n_keys >= (1ll << 31) - 1) CNN_FAIL(CNNB200_E_RANGE, "tensor search: more than 2^31 sort keys");
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(unsigned long long) * (size_t)n_keys * 2));
+    unsigned long long *keys = ctx->b_tmp0.as<unsigned long long>(), *keys2 = keys + n_keys;
+    {
+        Span sp(ctx, T_SEARCH_FILL);
+        const ll work = n_pairs > n ? n_pairs : n;
+        pair_keys_kernel<<<cnn_blocks(work, 256), 256, 0, st>>>(P.pairs, n_pairs, n, keys);
+        int bits = 1;
+        while ((1ll << bits) < n) ++bits;
+        size_t need = 0;
+        CNN_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, need, keys, keys2, (int)n_keys, 0, 64, st));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
+        size_t cap = ctx->b_cub.cap;
+        // columns occupy bits [0, bits), rows bits [32, 32 + bits): the bits in between are zero for every valid key
+        // and one for the rejected ones, which therefore still end up last when bit 32 + bits is included
+        CNN_CUDA(cub::DeviceRadixSort::SortKeys(ctx->b_cub.p, cap, keys, keys2, (int)n_keys, 0, 32 + bits + 1, st));
+        keys_to_cols_kernel<<<cnn_blocks(nnz, 256), 256, 0, st>>>(keys2, nnz, ctx->b_col_idx.as<int>());
+        CNN_LAUNCHED(ctx, 2);
+        CNN_KERNEL_CHECK();
+    }
+    CNN_CUDA(cudaMemcpyAsync(hb, band_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaStreamSynchronize(st));
+    ctx->stats[ST_RECHECK] = (ll)hb[0];
+    ctx->stats[ST_DIST] = n * (n - 1) / 2;
     ctx->n = n;
     ctx->nnz = nnz;
     ctx->max_deg = max_deg;

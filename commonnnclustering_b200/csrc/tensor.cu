@@ -172,7 +172,7 @@ __device__ __noinline__ bool exact_within(const double *__restrict__ x, int d, l
 // ---------------------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------------------
-#define NSB 3   // shared-memory stages of the B operand (TMA <-> MMA); 2 when a tile has 4 swizzle atoms (64 KB)
+#define NSB 3   // barrier slots reserved for the shared-memory stages of the B operand (2 are used; 1 for 4-atom tiles)
 #define NST 4   // TMEM accumulator stages of 128 columns (MMA <-> epilogue): the whole 512-column TMEM
 #define PAIR_BUF 16     // pairs a thread collects before it reserves space in the global list
 #define EPI_WARPS 8     // epilogue warps: two per TMEM lane quarter, 64 columns of a tile each
@@ -189,42 +189,41 @@ struct TensorParams {
     ll pair_cap;
 };
 
-// SINGLE pass over the upper triangle of the tile grid.  CTA c owns the row tiles c and n_tiles-1-c (together
-// n_tiles+1 column tiles: every CTA does the same amount of work) and walks each one's column tiles J >= I.
-// The epilogue classifies every accumulator element -- d2~ <= R - eps: neighbours, d2~ > R + eps: not, otherwise
-// borderline -- and only EMITS pairs (i < j) into a global list (per-thread buffers of PAIR_BUF pairs, one atomic
-// per flush).  Borderline pairs are decided afterwards by pair_resolve_kernel with the reference's own f64
-// expression, fully parallel, instead of stalling an epilogue warp (and, through it, the MMA pipeline) for ~1 us
-// each; degrees, row offsets and the two directed entries of every pair follow from the list, and one segmented
-// sort puts the rows in ascending order.  Nothing depends on the order in which tiles are visited.
+// SINGLE pass over the upper triangle of the tile grid.  CTA c owns the TWO adjacent row tiles 2c and 2c+1 (256 rows,
+// both A tiles stay in shared memory) and walks the column tiles J >= 2c: every B tile that comes in by TMA feeds two
+// MMA groups, which halves the L2 -> shared-memory traffic per flop (a 128-row CTA needs ~12 TB/s of B tiles to keep
+// the tensor pipe busy at K = 192).  CTAs are launched in order of decreasing work.
+// The epilogue (warps 2-5: row tile 2c, warps 6-9: row tile 2c+1, one TMEM lane quarter each) classifies every
+// accumulator element -- d2~ <= R - eps: neighbours, d2~ > R + eps: not, otherwise borderline -- and only EMITS pairs
+// (i < j) into a global list (per-thread buffers of PAIR_BUF pairs, one atomic per flush).  Borderline pairs are
+// decided afterwards by pair_resolve_kernel with the reference's own f64 expression, fully parallel, instead of
+// stalling an epilogue warp (and, through it, the MMA pipeline) for ~1 us each; degrees, row offsets and the two
+// directed entries of every pair follow from the list, and one radix sort puts everything in CSR order.  Nothing
+// depends on the order in which tiles are visited.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const TensorParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: A tile | nsb B stages | barriers | tmem slot | per-warp column norms | per-thread pair buffers
+    // carve: 2 A tiles | nsb B stages | barriers | tmem slot | per-warp column norms | per-thread pair buffers
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int atoms = P.atoms, nsb = P.nsb;
     const uint32_t tile_bytes = (uint32_t)atoms * ATOM_BYTES;
     uint8_t *sA = smem;
-    uint8_t *sB = smem + tile_bytes;
-    uint64_t *bars = (uint64_t *)(smem + (1 + nsb) * tile_bytes);
-    uint64_t *a_full = bars, *a_empty = bars + 1, *full = bars + 2, *empty = full + NSB, *t_full = empty + NSB,
-             *t_empty = t_full + NST;
+    uint8_t *sB = smem + 2 * tile_bytes;
+    uint64_t *bars = (uint64_t *)(smem + (2 + nsb) * tile_bytes);
+    uint64_t *a_full = bars, *full = bars + 2, *empty = full + NSB, *t_full = empty + NSB, *t_empty = t_full + NST;
     uint32_t *tmem_slot = (uint32_t *)(t_empty + NST);
-    float *ncs = (float *)(bars + 20);                  // [EPI_WARPS][2][64], 16-byte aligned
-    int *pbuf = (int *)(ncs + EPI_WARPS * 2 * 64);      // [EPI_WARPS * 32][PAIR_BUF]
+    float *ncs = (float *)(bars + 20);                  // [EPI_WARPS][2][TT], 16-byte aligned
+    int *pbuf = (int *)(ncs + EPI_WARPS * 2 * TT);      // [EPI_WARPS * 32][PAIR_BUF]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const ll n_tiles = P.n_tiles;
-    // the CTA's row tiles
-    const ll I_a = blockIdx.x, I_b = n_tiles - 1 - (ll)blockIdx.x;
-    const int n_rows_tiles = I_b > I_a ? 2 : 1;
+    const ll I0 = 2 * (ll)blockIdx.x;  // first row tile; the second one (I0 + 1) may lie past the end (all rows dead)
 
     if (warp == 0 && lane == 0) {
         mbar_init(a_full, 1);
-        mbar_init(a_empty, 1);
         for (int s = 0; s < nsb; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < NST; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, EPI_WARPS * 32); }
+        for (int s = 0; s < NST; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -240,19 +239,17 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            ll t = 0;  // running tile count: stage and phase bookkeeping continues across the row tiles
-            for (int rt = 0; rt < n_rows_tiles; ++rt) {
-                const ll I = rt == 0 ? I_a : I_b;
-                if (rt > 0) mbar_wait(a_empty, 0);  // every MMA of the first row tile has read sA
-                mbar_expect_tx(a_full, tile_bytes);
-                for (int a = 0; a < atoms; ++a) tma_load_2d(sA + a * ATOM_BYTES, &mapA, a * KATOM, (int)(I * TT), a_full);
-                for (ll j = I; j < n_tiles; ++j, ++t) {
-                    const int s = (int)(t % nsb);
-                    mbar_wait(empty + s, (uint32_t)((t / nsb) & 1) ^ 1);
-                    mbar_expect_tx(full + s, tile_bytes);
-                    for (int a = 0; a < atoms; ++a)
-                        tma_load_2d(sB + s * tile_bytes + a * ATOM_BYTES, &mapB, a * KATOM, (int)(j * TT), full + s);
-                }
+            mbar_expect_tx(a_full, 2 * tile_bytes);   // rows past the end of the operand are zero-filled
+            for (int rt = 0; rt < 2; ++rt)
+                for (int a = 0; a < atoms; ++a)
+                    tma_load_2d(sA + rt * tile_bytes + a * ATOM_BYTES, &mapA, a * KATOM, (int)((I0 + rt) * TT), a_full);
+            ll t = 0;
+            for (ll j = I0; j < n_tiles; ++j, ++t) {
+                const int s = (int)(t % nsb);
+                mbar_wait(empty + s, (uint32_t)((t / nsb) & 1) ^ 1);
+                mbar_expect_tx(full + s, tile_bytes);
+                for (int a = 0; a < atoms; ++a)
+                    tma_load_2d(sB + s * tile_bytes + a * ATOM_BYTES, &mapB, a * KATOM, (int)(j * TT), full + s);
             }
         }
     } else if (warp == 1) {
@@ -261,91 +258,91 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             // instruction descriptor: D f32, A/B bf16, both K-major, N = 128, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(TT >> 4) << 24);
             const uint32_t a_addr = smem_u32(sA);
+            mbar_wait(a_full, 0);
             ll t = 0;
-            for (int rt = 0; rt < n_rows_tiles; ++rt) {
-                const ll I = rt == 0 ? I_a : I_b;
-                mbar_wait(a_full, (uint32_t)rt);
-                for (ll j = I; j < n_tiles; ++j, ++t) {
-                    const int s = (int)(t % nsb), ts = (int)(t % NST);
-                    mbar_wait(t_empty + ts, (uint32_t)((t / NST) & 1) ^ 1);   // epilogue has drained this accumulator stage
-                    mbar_wait(full + s, (uint32_t)((t / nsb) & 1));          // TMA has landed this B tile
+            for (ll j = I0; j < n_tiles; ++j, ++t) {
+                const int s = (int)(t % nsb);
+                mbar_wait(full + s, (uint32_t)((t / nsb) & 1));          // TMA has landed this B tile
+                const uint32_t b_addr = smem_u32(sB + s * tile_bytes);
+                // the tile (I0 + 1, I0) below the diagonal is computed too (its pairs are dropped by the epilogue):
+                // every accumulator stage is then used on every second step and the phases stay in lock step
+                for (int rt = 0; rt < 2; ++rt) {
+                    const int ts = (int)((t & 1) << 1) | rt;
+                    mbar_wait(t_empty + ts, (uint32_t)((t >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
                     tc_fence_after();
-                    const uint32_t b_addr = smem_u32(sB + s * tile_bytes);
                     const uint32_t d_tmem = tmem_base + (uint32_t)ts * TT;
                     for (int k = 0; k < atoms * 4; ++k) {  // UMMA K = 16 bf16 = 32 bytes inside the swizzle atom
                         const uint32_t off = (uint32_t)(k >> 2) * ATOM_BYTES + (uint32_t)(k & 3) * 32;
-                        tc_mma(d_tmem, umma_desc(a_addr + off), umma_desc(b_addr + off), idesc, k > 0);
+                        tc_mma(d_tmem, umma_desc(a_addr + rt * tile_bytes + off), umma_desc(b_addr + off), idesc, k > 0);
                     }
-                    tc_commit(empty + s);    // smem stage free once these MMAs have read it
                     tc_commit(t_full + ts);  // accumulator ready for the epilogue
                 }
-                tc_commit(a_empty);          // the A tile may be replaced
+                tc_commit(empty + s);        // smem stage free once these MMAs have read it
             }
         }
     } else {
         // ===== epilogue: TMEM -> registers -> classify -> emit pairs =====
         const int ew = warp - 2;             // 0 .. EPI_WARPS-1
         const int q = warp & 3;              // TMEM lane quarter this warp may access
-        const int half = ew >> 2;            // which 64 columns of a tile (warps 2-5 and 6-9 cover the quarters 2,3,0,1)
+        const int rt = ew >> 2;              // which of the CTA's two row tiles
         const int row = q * 32 + lane;       // accumulator row = TMEM lane
-        float *ncw = ncs + ew * 2 * 64;
+        float *ncw = ncs + ew * 2 * TT;
         int *mybuf = pbuf + (ew * 32 + lane) * PAIR_BUF;
         int n_buf = 0;
-        ll gi = 0;
+        const ll gi = (I0 + rt) * TT + row;
+        const bool live = gi < P.n;
+        const float nr = live ? P.norm[gi] : 0.f;
+        // d2~ = nr + nc - 2 acc <= thr   <=>   w = nc - 2 acc <= thr - nr ; dead rows never pass
+        const float thr_hi = live ? P.r2_hi - nr : -INFINITY, thr_lo = live ? P.r2_lo - nr : -INFINITY;
         auto flush = [&]() {
             const ll pos = (ll)atomicAdd(P.pair_count, (unsigned long long)n_buf);
             if (pos + n_buf <= P.pair_cap)
                 for (int k = 0; k < n_buf; ++k) P.pairs[pos + k] = make_int2((int)gi, mybuf[k]);
             n_buf = 0;
         };
+        float4 nn = reinterpret_cast<const float4 *>(P.norm + I0 * TT)[lane];  // column norms of the next tile: 4 per lane
         ll t = 0;
-        for (int rt = 0; rt < n_rows_tiles; ++rt) {
-            const ll I = rt == 0 ? I_a : I_b;
-            if (n_buf) flush();  // the buffered pairs belong to the previous row
-            gi = I * TT + row;
-            const bool live = gi < P.n;
-            const float nr = P.norm[gi];
-            // d2~ = nr + nc - 2 acc <= thr   <=>   w = nc - 2 acc <= thr - nr ; dead rows never pass
-            const float thr_hi = live ? P.r2_hi - nr : -INFINITY, thr_lo = live ? P.r2_lo - nr : -INFINITY;
-            // column norms of this thread's 64 columns of the next tile: 2 per lane
-            float2 nn = reinterpret_cast<const float2 *>(P.norm + I * TT + half * 64)[lane];
-            for (ll j = I; j < n_tiles; ++j, ++t) {
-                const int ts = (int)(t % NST);
-                float *nc = ncw + (int)(t & 1) * 64;
-                reinterpret_cast<float2 *>(nc)[lane] = nn;
-                if (j + 1 < n_tiles) nn = reinterpret_cast<const float2 *>(P.norm + (j + 1) * TT + half * 64)[lane];
-                __syncwarp();
-                mbar_wait(t_full + ts, (uint32_t)((t / NST) & 1));
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * TT + half * 64);
+        for (ll j = I0; j < n_tiles; ++j, ++t) {
+            const int ts = (int)((t & 1) << 1) | rt;
+            float *nc = ncw + (int)(t & 1) * TT;
+            reinterpret_cast<float4 *>(nc)[lane] = nn;
+            if (j + 1 < n_tiles) nn = reinterpret_cast<const float4 *>(P.norm + (j + 1) * TT)[lane];
+            __syncwarp();
+            mbar_wait(t_full + ts, (uint32_t)((t >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * TT);
+#pragma unroll
+            for (int hp = 0; hp < 2; ++hp) {  // 64 columns at a time: two tcgen05.ld in flight
                 float va[32], vb[32];
-                tmem_ld32(taddr, va);
-                tmem_ld32(taddr + 32, vb);
+                tmem_ld32(taddr + hp * 64, va);
+                tmem_ld32(taddr + hp * 64 + 32, vb);
                 tmem_ld_wait();
-                // both chunks are in registers: hand the accumulator stage back to the MMA warp
-                tc_fence_before();
-                mbar_arrive(t_empty + ts);
+                if (hp == 1) {  // the whole accumulator stage is in registers: hand it back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(t_empty + ts);
+                }
 #pragma unroll
                 for (int chunk = 0; chunk < 2; ++chunk) {
                     const float *cur = chunk ? vb : va;
+                    const int cbase = hp * 64 + chunk * 32;
                     // two bit masks per lane, element c at bit 31 - c: funnel-shift the sign of (thr - w) in
                     unsigned m_hi = 0, m_lo = 0;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
-                        const float w = fmaf(-2.f, cur[c], nc[chunk * 32 + c]);
+                        const float w = fmaf(-2.f, cur[c], nc[cbase + c]);
                         m_hi = __funnelshift_l(__float_as_uint(thr_hi - w), m_hi, 1);
                         m_lo = __funnelshift_l(__float_as_uint(thr_lo - w), m_lo, 1);
                     }
                     m_hi = ~m_hi;  // bit set <=> w <= thr (the difference is never NaN: norms are finite or +inf)
                     m_lo = ~m_lo;
                     if (!live) m_hi = 0;
-                    const int col0 = (int)(j * TT) + half * 64 + chunk * 32;
+                    const int col0 = (int)(j * TT) + cbase;
                     while (m_hi) {
                         const int c = __clz(m_hi);
                         const unsigned bit = 0x80000000u >> c;
                         m_hi &= ~bit;
                         const int gj = col0 + c;
-                        if (gj <= (int)gi) continue;  // diagonal tile: lower triangle and self are not emitted
+                        if (gj <= (int)gi) continue;  // diagonal and sub-diagonal tiles: only j > i is emitted
                         mybuf[n_buf++] = (m_lo & bit) ? gj : (int)((unsigned)gj | BAND_FLAG);
                         if (n_buf == PAIR_BUF) flush();
                     }
@@ -497,7 +494,7 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     P.n = n;
     P.n_tiles = n_tiles;
     P.atoms = atoms;
-    P.nsb = atoms >= 4 ? 2 : NSB;
+    P.nsb = atoms >= 4 ? 1 : 2;  // 2 A tiles + nsb B tiles must fit 227 KB
     P.r2_lo = (float)(R - eps);
     P.r2_hi = (float)(R + eps);
     // keep the f32 thresholds on the safe side of the f64 ones
@@ -505,8 +502,8 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     P.r2_hi = nextafterf(P.r2_hi, INFINITY);
     P.pair_count = pair_count;
 
-    const size_t smem = (size_t)(1 + P.nsb) * atoms * ATOM_BYTES + 1024 /*alignment*/ + 20 * 8 +
-                        EPI_WARPS * 2 * 64 * sizeof(float) + EPI_WARPS * 32 * PAIR_BUF * sizeof(int) + 64;
+    const size_t smem = (size_t)(2 + P.nsb) * atoms * ATOM_BYTES + 1024 /*alignment*/ + 20 * 8 +
+                        EPI_WARPS * 2 * TT * sizeof(float) + EPI_WARPS * 32 * PAIR_BUF * sizeof(int) + 64;
     CNN_CUDA(cudaFuncSetAttribute(tensor_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // ---- the pass over the upper triangle (rerun once with a larger list should the pairs not fit) ------------

@@ -91,13 +91,14 @@ extern "C" int cnnb200_ctx_create(int device, cnnb200_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char *e = getenv("CNNB200_SAMPLES")) ctx->n_samples = atoi(e);
     if (const char *e = getenv("CNNB200_FILTER")) ctx->use_filter = atoi(e) != 0;
+    if (const char *e = getenv("CNNB200_TENSOR_REORDER")) ctx->tensor_reorder = atoi(e) != 0;
     if (const char *e = getenv("CNNB200_SINGLE_PASS_MB")) ctx->single_pass_limit = (ll)atoll(e) << 20;
     *out = ctx;
     return CNNB200_OK;
 }
 
 #define FOR_EACH_BUF(c, F)                                                                          \
-    F(c->b_row_ptr) F(c->b_col_idx) F(c->b_perm) F(c->b_deg) F(c->b_x) F(c->b_xs) F(c->b_xf) F(c->b_cell_id)   \
+    F(c->b_row_ptr) F(c->b_col_idx) F(c->b_perm) F(c->b_deg) F(c->b_x) F(c->b_xs) F(c->b_xf) F(c->b_xperm) F(c->b_cell_id)   \
     F(c->b_cell_id_sorted) F(c->b_idx) F(c->b_cell_start) F(c->b_bbox) F(c->b_cub) F(c->b_tmp0)     \
     F(c->b_tmp1) F(c->b_tmp2) F(c->b_parent) F(c->b_core) F(c->b_above) F(c->b_edges) F(c->b_worklist) F(c->b_cell_count) F(c->b_minorig) F(c->b_flags)             \
     F(c->b_rank) F(c->b_labels) F(c->b_consider) F(c->b_stats) F(c->b_lab_count) F(c->b_lab_first)  \

@@ -110,6 +110,8 @@ struct cnnb200_ctx {
     // ---- neighbour search scratch ------------------------------------------------------
     Buf b_x;         // f64 [n, d] as given by the caller (device copy)
     Buf b_xs;        // f64 SoA [d][n] in cell-sorted order
+    Buf b_xperm;     // f64 [n, d]: coordinates in the pivot-sorted order of the tensor-core search
+    bool tensor_reorder = true;  // CNNB200_TENSOR_REORDER=0: keep the caller's order, visit every tile
     Buf b_xf;        // float4 [n]: cell-local fp32 coordinates (x on lattices A and B, y, z) for the filter kernel
     bool use_filter = true;  // fp32 filter + exact recheck in the cell-list search (CNNB200_FILTER=0: f64 kernel)
     bool grid_recheck_pending = false;

@@ -170,6 +170,145 @@ __device__ __noinline__ bool exact_within(const double *__restrict__ x, int d, l
 }
 
 // ---------------------------------------------------------------------------------------------------
+// reordering and tile pruning
+// ---------------------------------------------------------------------------------------------------
+// High-dimensional data that is worth clustering is clustered: after sorting the points by (nearest pivot, distance
+// to it) the 128-row tiles are spatially compact, and a tile pair whose bounding balls are further apart than the
+// radius cannot contain a neighbour pair (triangle inequality) -- it is skipped by all three warp roles.  The CSR
+// is produced in the sorted index space together with perm[] (sorted position -> caller index), as in the grid path.
+#define N_PIVOTS 64
+
+// one warp per point: lanes stride over the dimensions (coalesced row reads), pivots sit in shared memory as floats
+__global__ void __launch_bounds__(256)
+pivot_assign_kernel(const double *__restrict__ x, ll n, int d, int n_piv, unsigned long long *keys, int *idx) {
+    extern __shared__ float piv[];  // [n_piv][d]
+    for (int t = threadIdx.x; t < n_piv * d; t += blockDim.x) {
+        const int p = t / d, k = t - p * d;
+        piv[t] = (float)x[(ll)((double)p * (double)n / (double)n_piv) * d + k];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    for (ll i = warp; i < n; i += nwarps) {
+        float xi[3];  // d <= 85 < 96: at most 3 coordinates per lane
+#pragma unroll
+        for (int u = 0; u < 3; ++u) xi[u] = lane + 32 * u < d ? (float)x[i * d + lane + 32 * u] : 0.f;
+        float best = INFINITY;
+        int arg = 0;
+        for (int p = 0; p < n_piv; ++p) {
+            float s = 0.f;
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+                if (lane + 32 * u < d) {
+                    const float t = xi[u] - piv[p * d + lane + 32 * u];
+                    s = fmaf(t, t, s);
+                }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (s < best) { best = s; arg = p; }
+        }
+        if (lane == 0) {
+            keys[i] = ((unsigned long long)arg << 32) | (unsigned long long)__float_as_uint(best);  // best >= 0: bits are ordered
+            idx[i] = (int)i;
+        }
+    }
+}
+
+__global__ void gather_rows_kernel(const double *__restrict__ x, const int *__restrict__ perm, ll n, int d, double *out) {
+    ll t = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (t >= n * d) return;
+    const ll p = t / d;
+    const int k = (int)(t - p * d);
+    out[t] = x[(ll)perm[p] * d + k];
+}
+
+// one block per tile: centre (mean of its live rows) and radius (largest distance of a row to the centre, rounded up)
+__global__ void tile_ball_kernel(const double *__restrict__ x, ll n, int d, double *centre, double *radius) {
+    __shared__ double c[128];
+    __shared__ double rmax[TT];
+    const ll T = blockIdx.x;
+    const ll r0 = T * TT;
+    const int rows = (int)((n - r0) < TT ? (n - r0) : TT);
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < rows; ++r) s += x[(r0 + r) * d + k];
+        c[k] = s / rows;
+        centre[T * d + k] = c[k];
+    }
+    __syncthreads();
+    double dist = 0.0;
+    if ((int)threadIdx.x < rows) {
+        double s = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double t = x[(r0 + threadIdx.x) * d + k] - c[k];
+            s += t * t;
+        }
+        dist = sqrt(s);
+    }
+    rmax[threadIdx.x] = dist;
+    __syncthreads();
+    for (int o = TT / 2; o; o >>= 1) {
+        if ((int)threadIdx.x < o) rmax[threadIdx.x] = fmax(rmax[threadIdx.x], rmax[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) radius[T] = rmax[0] * (1.0 + 1e-12) + 1e-300;
+}
+
+// bit J of row I set <=> tile pair (I, J) can be skipped; one warp per 32 column tiles
+__global__ void tile_skip_kernel(const double *__restrict__ centre, const double *__restrict__ radius, ll n_tiles, int d,
+                                 int words, double r_true, unsigned *skip) {
+    const ll gw = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= n_tiles * words) return;
+    const ll I = gw / words;
+    const ll J = (gw - I * words) * 32 + lane;
+    bool sk = false;
+    if (J < n_tiles) {
+        double s = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double t = centre[I * d + k] - centre[J * d + k];
+            s += t * t;
+        }
+        // any i in I, j in J: |x_i - x_j| >= |c_I - c_J| - rho_I - rho_J
+        sk = sqrt(s) * (1.0 - 1e-12) - radius[I] - radius[J] > r_true * (1.0 + 1e-9);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, sk);
+    if (lane == 0) skip[gw] = m;
+}
+
+// the column tiles a CTA has to visit: J >= I0 that are needed by at least one of its row tiles I0, I0 + 1
+struct TileIter {
+    const unsigned *m0, *m1;  // skip rows of the two row tiles (nullptr: nothing is skipped)
+    ll n_tiles;
+    int w, words;
+    unsigned cur;
+    __device__ void init(const unsigned *skip, ll I0, ll n_tiles_, int words_) {
+        n_tiles = n_tiles_;
+        words = words_;
+        m0 = skip ? skip + I0 * words : nullptr;
+        m1 = (skip && I0 + 1 < n_tiles) ? skip + (I0 + 1) * words : m0;
+        w = (int)(I0 >> 5);
+        cur = load(w) & (0xffffffffu << (I0 & 31));
+    }
+    __device__ unsigned load(int ww) const {
+        unsigned need = m0 ? ~(m0[ww] & m1[ww]) : 0xffffffffu;
+        const ll base = (ll)ww * 32;
+        if (base + 32 > n_tiles) need &= (1u << (n_tiles - base)) - 1u;  // 1 .. 31 tiles in the last word
+        return need;
+    }
+    __device__ ll next() {  // -1 when exhausted
+        while (!cur) {
+            if (++w >= words) return -1;
+            cur = load(w);
+        }
+        const int b = __ffs(cur) - 1;
+        cur &= cur - 1;
+        return (ll)w * 32 + b;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------------------
 #define NSB 3   // barrier slots reserved for the shared-memory stages of the B operand (2 are used; 1 for 4-atom tiles)
@@ -184,6 +323,8 @@ struct TensorParams {
     ll n, n_tiles;
     int atoms, nsb;
     float r2_lo, r2_hi;   // R - eps, R + eps in squared-distance units
+    const unsigned *skip; // [n_tiles][words] tile pairs that cannot hold a neighbour pair (nullptr: visit all)
+    int words;
     int2 *pairs;          // out: (i, j) with i < j; j carries BAND_FLAG when the pair is inside the +-eps band
     unsigned long long *pair_count;  // running length of `pairs` (may exceed pair_cap: then nothing is stored)
     ll pair_cap;
@@ -244,7 +385,9 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 for (int a = 0; a < atoms; ++a)
                     tma_load_2d(sA + rt * tile_bytes + a * ATOM_BYTES, &mapA, a * KATOM, (int)((I0 + rt) * TT), a_full);
             ll t = 0;
-            for (ll j = I0; j < n_tiles; ++j, ++t) {
+            TileIter it;
+            it.init(P.skip, I0, n_tiles, P.words);
+            for (ll j = it.next(); j >= 0; j = it.next(), ++t) {
                 const int s = (int)(t % nsb);
                 mbar_wait(empty + s, (uint32_t)((t / nsb) & 1) ^ 1);
                 mbar_expect_tx(full + s, tile_bytes);
@@ -260,7 +403,9 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             const uint32_t a_addr = smem_u32(sA);
             mbar_wait(a_full, 0);
             ll t = 0;
-            for (ll j = I0; j < n_tiles; ++j, ++t) {
+            TileIter it;
+            it.init(P.skip, I0, n_tiles, P.words);
+            for (ll j = it.next(); j >= 0; j = it.next(), ++t) {
                 const int s = (int)(t % nsb);
                 mbar_wait(full + s, (uint32_t)((t / nsb) & 1));          // TMA has landed this B tile
                 const uint32_t b_addr = smem_u32(sB + s * tile_bytes);
@@ -300,13 +445,17 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 for (int k = 0; k < n_buf; ++k) P.pairs[pos + k] = make_int2((int)gi, mybuf[k]);
             n_buf = 0;
         };
-        float4 nn = reinterpret_cast<const float4 *>(P.norm + I0 * TT)[lane];  // column norms of the next tile: 4 per lane
-        ll t = 0;
-        for (ll j = I0; j < n_tiles; ++j, ++t) {
+        TileIter it;
+        it.init(P.skip, I0, n_tiles, P.words);
+        ll j = it.next();
+        float4 nn = make_float4(0.f, 0.f, 0.f, 0.f);  // column norms of the next tile: 4 per lane
+        if (j >= 0) nn = reinterpret_cast<const float4 *>(P.norm + j * TT)[lane];
+        for (ll t = 0; j >= 0; ++t) {
+            const ll j_next = it.next();
             const int ts = (int)((t & 1) << 1) | rt;
             float *nc = ncw + (int)(t & 1) * TT;
             reinterpret_cast<float4 *>(nc)[lane] = nn;
-            if (j + 1 < n_tiles) nn = reinterpret_cast<const float4 *>(P.norm + (j + 1) * TT)[lane];
+            if (j_next >= 0) nn = reinterpret_cast<const float4 *>(P.norm + j_next * TT)[lane];
             __syncwarp();
             mbar_wait(t_full + ts, (uint32_t)((t >> 1) & 1));
             tc_fence_after();
@@ -348,6 +497,7 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     }
                 }
             }
+            j = j_next;
         }
         if (n_buf) flush();
     }
@@ -449,6 +599,41 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     const bool sq = metric == CNNB200_METRIC_EUCLIDEAN;
     const double R = sq ? radius_cutoff * radius_cutoff : radius_cutoff;
 
+    // ---- sort the points by (nearest pivot, distance to it); everything below works in that order ---------------
+    const bool reorder = n >= 4096 && ctx->tensor_reorder;
+    const unsigned *skip = nullptr;
+    const int words = (int)((n_tiles + 31) / 32);
+    if (reorder) {
+        Span sp(ctx, T_GRID_BUILD);
+        const int n_piv = N_PIVOTS;
+        CNN_TRY(cnn_ensure(ctx, ctx->b_perm, sizeof(int) * (size_t)n));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_idx, sizeof(int) * (size_t)n));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_lab_keys, sizeof(unsigned long long) * (size_t)n));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_lab_keys2, sizeof(unsigned long long) * (size_t)n));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_xperm, sizeof(double) * (size_t)n * (size_t)d));
+        unsigned long long *pk = ctx->b_lab_keys.as<unsigned long long>(), *pk2 = ctx->b_lab_keys2.as<unsigned long long>();
+        pivot_assign_kernel<<<ctx->sm_count * 8, 256, sizeof(float) * (size_t)n_piv * (size_t)d, st>>>(d_x, n, (int)d, n_piv, pk,
+                                                                                                      ctx->b_idx.as<int>());
+        size_t need = 0;
+        CNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, pk, pk2, ctx->b_idx.as<int>(), ctx->b_perm.as<int>(), (int)n, 0, 40, st));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
+        size_t cap = ctx->b_cub.cap;
+        CNN_CUDA(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, cap, pk, pk2, ctx->b_idx.as<int>(), ctx->b_perm.as<int>(), (int)n, 0, 40, st));
+        gather_rows_kernel<<<cnn_blocks(n * d, 256), 256, 0, st>>>(d_x, ctx->b_perm.as<int>(), n, (int)d, ctx->b_xperm.as<double>());
+        d_x = ctx->b_xperm.as<double>();
+        // bounding balls of the tiles and the pairs of tiles that are too far apart to matter
+        CNN_TRY(cnn_ensure(ctx, ctx->b_cell_start, sizeof(double) * (size_t)n_tiles * (size_t)(d + 1)));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_cell_count, sizeof(unsigned) * (size_t)n_tiles * (size_t)words));
+        double *centre = ctx->b_cell_start.as<double>(), *radius = centre + n_tiles * d;
+        tile_ball_kernel<<<(int)n_tiles, TT, 0, st>>>(d_x, n, (int)d, centre, radius);
+        const double r_true = sq ? radius_cutoff : sqrt(radius_cutoff);
+        tile_skip_kernel<<<cnn_blocks(n_tiles * words * 32, 256), 256, 0, st>>>(centre, radius, n_tiles, (int)d, words, r_true,
+                                                                               ctx->b_cell_count.as<unsigned>());
+        skip = ctx->b_cell_count.as<unsigned>();
+        CNN_LAUNCHED(ctx, 4);
+        CNN_KERNEL_CHECK();
+    }
+
     // ---- operands -----------------------------------------------------------------------------
     CNN_TRY(cnn_ensure(ctx, ctx->b_xs, sizeof(__nv_bfloat16) * (size_t)n_pad * kt * 2));
     CNN_TRY(cnn_ensure(ctx, ctx->b_tmp1, sizeof(float) * (size_t)n_pad));
@@ -501,6 +686,8 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     P.r2_lo = nextafterf(P.r2_lo, -INFINITY);
     P.r2_hi = nextafterf(P.r2_hi, INFINITY);
     P.pair_count = pair_count;
+    P.skip = skip;
+    P.words = words;
 
     const size_t smem = (size_t)(2 + P.nsb) * atoms * ATOM_BYTES + 1024 /*alignment*/ + 20 * 8 +
                         EPI_WARPS * 2 * TT * sizeof(float) + EPI_WARPS * 32 * PAIR_BUF * sizeof(int) + 64;
@@ -582,6 +769,6 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     ctx->max_deg = max_deg;
     ctx->row_ptr = ctx->b_row_ptr.as<ll>();
     ctx->col_idx = ctx->b_col_idx.as<int>();
-    ctx->perm = nullptr;
+    ctx->perm = reorder ? ctx->b_perm.as<int>() : nullptr;
     return CNNB200_OK;
 }

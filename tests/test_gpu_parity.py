@@ -88,6 +88,31 @@ def test_tensor_core_neighbour_sets_are_exact(ctx):
         ctx.neighbours_from_points(rng.standard_normal((10, 86)), 1.0, method="tensor")  # > 85 dims
 
 
+def test_tensor_core_reordered_ties_and_pair_list_regrowth():
+    """Pivot-sorted order + tile pruning (n >= 4096) on data full of exact ties, with a pair list that is far too
+    small at first (the pass is repeated once with the size it asked for), with and without the reordering."""
+    x = cases.lattice(5000, 6, 33)
+    rc = 0.5 ** 2
+    want = None
+    for env in ({"CNNB200_TENSOR_PAIR_CAP": "1000"}, {"CNNB200_TENSOR_REORDER": "0"}, {}):
+        os.environ.update(env)
+        try:
+            c = _lib.Context(0)
+        finally:
+            for k in env:
+                del os.environ[k]
+        if want is None:
+            c.neighbours_from_points(x, rc, method="tiled")
+            want = c.neighbours_export()
+        c.neighbours_from_points(x, rc, method="tensor")
+        got = c.neighbours_export()
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+        lab = np.empty(x.shape[0], dtype=np.int64)
+        c.fit_points(x, rc, 6, 7, lab, method="tensor")
+        np.testing.assert_array_equal(lab, port.fit_points(x, 0.5, 5))
+
+
 def test_readme_doctest():
     cl = cluster.Clustering(datasets.README_POINTS)
     cl.fit(1.5, 1, v=False)

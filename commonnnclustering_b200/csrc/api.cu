@@ -99,7 +99,7 @@ extern "C" int cnnb200_ctx_create(int device, cnnb200_ctx **out) {
 }
 
 #define FOR_EACH_BUF(c, F)                                                                          \
-    F(c->b_row_ptr) F(c->b_col_idx) F(c->b_perm) F(c->b_deg) F(c->b_x) F(c->b_xs) F(c->b_xf) F(c->b_xperm) F(c->b_cell_id)   \
+    F(c->b_row_ptr) F(c->b_col_idx) F(c->b_perm) F(c->b_deg) F(c->b_x) F(c->b_xs) F(c->b_xf) F(c->b_xperm) F(c->b_o_x) F(c->b_o_deg) F(c->b_o_row_ptr) F(c->b_o_col_idx) F(c->b_o_labels) F(c->b_cell_id)   \
     F(c->b_cell_id_sorted) F(c->b_idx) F(c->b_cell_start) F(c->b_bbox) F(c->b_cub) F(c->b_tmp0)     \
     F(c->b_tmp1) F(c->b_tmp2) F(c->b_parent) F(c->b_core) F(c->b_above) F(c->b_edges) F(c->b_worklist) F(c->b_cell_count) F(c->b_minorig) F(c->b_flags)             \
     F(c->b_rank) F(c->b_labels) F(c->b_consider) F(c->b_stats) F(c->b_lab_count) F(c->b_lab_first)  \
@@ -115,6 +115,8 @@ extern "C" int cnnb200_ctx_release(cnnb200_ctx *ctx) {
     ctx->have_nb = false;
     ctx->have_comp = false;
     ctx->have_grid = false;
+    ctx->have_points = false;
+    ctx->have_other = false;
     ctx->row_ptr = nullptr;
     ctx->col_idx = nullptr;
     ctx->perm = nullptr;
@@ -237,6 +239,7 @@ extern "C" int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x,
     CNN_CUDA(cudaSetDevice(ctx->device));
     ctx->have_nb = false;
     ctx->have_comp = false;
+    ctx->have_points = false;
     const double *d_x = x;
     if (loc == CNNB200_HOST) {
         CNN_TRY(cnn_ensure(ctx, ctx->b_x, sizeof(double) * (size_t)n * (size_t)d));
@@ -250,6 +253,13 @@ extern "C" int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x,
     else
         CNN_TRY(cnn_dense_search(ctx, d_x, n, d, radius_cutoff, metric, method));
     ctx->have_nb = true;
+    ctx->have_other = false;
+    ctx->have_points = true;  // prediction for other points needs the coordinates, the cutoff and the metric again
+    ctx->pts_grid = method == 1;
+    ctx->pts_x = d_x;
+    ctx->pts_d = d;
+    ctx->pts_rc = radius_cutoff;
+    ctx->pts_metric = metric;
     if (nnz_out) *nnz_out = ctx->nnz;
     return CNNB200_OK;
 }

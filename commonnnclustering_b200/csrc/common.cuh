@@ -118,6 +118,16 @@ struct cnnb200_ctx {
     Buf b_cell_id, b_cell_id_sorted, b_idx, b_cell_start, b_bbox, b_cub;
     Buf b_tmp0, b_tmp1, b_tmp2;
 
+    // ---- the point set the neighbourhoods were built from + the OTHER set of a prediction --------------------------
+    bool have_points = false, pts_grid = false;
+    const double *pts_x = nullptr;   // row-major coordinates on the device (caller order), valid while have_points
+    ll pts_d = 0;
+    double pts_rc = 0;
+    int pts_metric = 0;
+    bool have_other = false;
+    ll o_m = 0, o_nnz = 0;
+    Buf b_o_x, b_o_deg, b_o_row_ptr, b_o_col_idx, b_o_labels;
+
     // ---- components ----------------------------------------------------------------------
     bool have_comp = false;
     ll n_member_cutoff = 0, similarity_cutoff = 0;

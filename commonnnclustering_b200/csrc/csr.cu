@@ -106,6 +106,8 @@ extern "C" int cnnb200_neighbours_from_csr(cnnb200_ctx *ctx, const int64_t *row_
     CNN_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     ctx->have_nb = false;
+    ctx->have_points = false;
+    ctx->have_other = false;
     ctx->have_comp = false;
     cudaMemcpyKind kind = loc == CNNB200_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     Span sp(ctx, T_INGEST);
@@ -173,6 +175,8 @@ extern "C" int cnnb200_neighbours_from_padded(cnnb200_ctx *ctx, const int64_t *p
     CNN_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     ctx->have_nb = false;
+    ctx->have_points = false;
+    ctx->have_other = false;
     ctx->have_comp = false;
     cudaMemcpyKind kind = loc == CNNB200_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     Span sp(ctx, T_INGEST);

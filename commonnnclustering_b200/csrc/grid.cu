@@ -785,6 +785,8 @@ extern "C" int cnnb200_grid_begin(cnnb200_ctx *ctx, const double *x, int loc, in
     CNN_CUDA(cudaSetDevice(ctx->device));
     ctx->have_nb = false;
     ctx->have_comp = false;
+    ctx->have_points = false;
+    ctx->have_other = false;
     const double *d_x = x;
     if (loc == CNNB200_HOST) {
         CNN_TRY(cnn_ensure(ctx, ctx->b_x, sizeof(double) * (size_t)n * (size_t)d));
@@ -876,5 +878,7 @@ extern "C" int cnnb200_neighbours_adopt(cnnb200_ctx *ctx, const int64_t *row_ptr
     ctx->perm = grid_perm ? ctx->b_perm.as<int>() : nullptr;
     ctx->have_nb = true;
     ctx->have_comp = false;
+    ctx->have_points = false;
+    ctx->have_other = false;
     return CNNB200_OK;
 }

@@ -99,3 +99,51 @@ class FitterB200Fused(FitterB200):
         labels.consider[:] = 0
         labels.meta["b200"] = dict(ctx.stats(), n_points=int(labels.labels.shape[0]))
         return n_clusters
+
+
+class Predictor:
+    """Role marker (reference ABC ``Predictor``, ``_fit.pyx:164-216``)."""
+
+    make_parameters = Fitter.make_parameters
+
+
+class PredictorB200(Predictor):
+    """Cluster labels for points outside the clustered set (reference ``PredictorFirstmatch``,
+    ``_fit.pyx:1189-1291``): a predictand point with enough neighbours in the clustered set gets the label of the
+    first of those neighbours (ascending index) that belongs to a considered cluster, has enough neighbours itself
+    and passes the common-neighbour check against the point's neighbour list."""
+
+    def __init__(self, neighbours_getter: NeighboursGetter = None, neighbours_getter_other=None, similarity_checker=None,
+                 ctx=None, **_ignored):
+        self._neighbours_getter = neighbours_getter if neighbours_getter is not None else NeighboursGetterRadius()
+        self._neighbours_getter_other = neighbours_getter_other if neighbours_getter_other is not None else self._neighbours_getter
+        self._similarity_checker = similarity_checker if similarity_checker is not None else SimilarityCheckerCommonNN()
+        self._ctx = ctx
+
+    @classmethod
+    def get_builder_kwargs(cls):
+        return [("neighbours_getter", None), ("neighbours_getter_other", "neighbours_getter"), ("similarity_checker", None)]
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = _lib.default_context()
+        return self._ctx
+
+    def predict(self, input_data, predictand_input_data, labels: Labels, predictand_labels: Labels,
+                cluster_params: ClusterParameters) -> None:
+        ctx = self.ctx
+        self._neighbours_getter.get_all(input_data, cluster_params, ctx)
+        if isinstance(predictand_input_data, InputDataComponents):
+            ctx.neighbours_other_from_points(predictand_input_data.to_components_array())
+        else:  # neighbourhoods of the predictand points IN the clustered set
+            row_ptr, col_idx = predictand_input_data.to_csr()
+            ctx.neighbours_other_from_csr(row_ptr, col_idx)
+        lab = labels.labels
+        max_label = int(lab.max()) if lab.size else 0
+        label_ok = np.zeros(max_label + 1, dtype=np.uint8)
+        for k in predictand_labels.consider_set:
+            if 0 <= k <= max_label:
+                label_ok[k] = 1
+        ctx.predict(cluster_params.n_member_cutoff, cluster_params.similarity_cutoff, lab, label_ok,
+                    predictand_labels.labels, predictand_labels.consider)

@@ -49,6 +49,9 @@ SIGNATURES = {
     "cnnb200_components_parents": [_P, C.POINTER(_P)],
     "cnnb200_components_merge": [_P, _P, _I64],
     "cnnb200_components_labels": [_P, _I64, _P, C.c_int, C.c_int, C.POINTER(_I64)],
+    "cnnb200_neighbours_other_from_points": [_P, _P, C.c_int, _I64, _I64, C.POINTER(_I64)],
+    "cnnb200_neighbours_other_from_csr": [_P, _P, _P, C.c_int, _I64, _I64],
+    "cnnb200_predict": [_P, _I64, _I64, _P, _P, _I64, _P, _P, C.c_int],
     "cnnb200_sort_by_size": [_P, _P, C.c_int, _I64, _I64, _I64, _P, _I64],
     "cnnb200_fit_points": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int, C.c_int, _I64, _I64, _I64,
                            C.c_int, _I64, _I64, _P, C.POINTER(_I64)],
@@ -306,6 +309,31 @@ class Context:
         nc = _I64()
         check(self._lib.cnnb200_components_labels(self._h, int(current_start), lp, loc, int(bool(fresh)), C.byref(nc)))
         return nc.value
+
+    # -- prediction ---------------------------------------------------------------------------------
+    def neighbours_other_from_points(self, x_other):
+        p, loc = _ptr_loc(x_other)
+        m, d = x_other.shape
+        nnz = _I64()
+        check(self._lib.cnnb200_neighbours_other_from_points(self._h, p, loc, m, d, C.byref(nnz)))
+        return nnz.value
+
+    def neighbours_other_from_csr(self, row_ptr, col_idx):
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+        col_idx = np.ascontiguousarray(col_idx, dtype=np.int64)
+        check(self._lib.cnnb200_neighbours_other_from_csr(self._h, row_ptr.ctypes.data, col_idx.ctypes.data, HOST,
+                                                          row_ptr.shape[0] - 1, col_idx.shape[0]))
+
+    def predict(self, n_member_cutoff, similarity_cutoff, labels, label_ok, other_labels, other_consider):
+        """In-place update of ``other_labels`` / ``other_consider`` (NumPy arrays)."""
+        lp, loc = _ptr_loc(labels)
+        op, loc2 = _ptr_loc(other_labels)
+        cp, loc3 = _ptr_loc(other_consider)
+        kp, loc4 = _ptr_loc(label_ok)
+        if not (loc == loc2 == loc3 == loc4):
+            raise ValueError("predict: all arrays must live in the same memory space")
+        check(self._lib.cnnb200_predict(self._h, int(n_member_cutoff), int(similarity_cutoff), lp, kp,
+                                        int(label_ok.shape[0] - 1), op, cp, loc))
 
     def sort_by_size(self, labels, member_cutoff=None, max_clusters=None, return_map=False, max_label=None):
         lp, loc = _ptr_loc(labels)

@@ -256,6 +256,13 @@ class InputDataNeighbourhoods(InputData):
     def get_neighbour(self, point: int, member: int) -> int:
         return int(self._data[point, member])
 
+    def to_csr(self):
+        """(row_ptr int64 [n+1], col_idx int64 [nnz]) of the valid entries."""
+        row_ptr = np.zeros(self.n_points + 1, dtype=P_AINDEX)
+        np.cumsum(self._n_neighbours, out=row_ptr[1:])
+        mask = np.arange(self._data.shape[1])[None, :] < self._n_neighbours[:, None]
+        return row_ptr, np.ascontiguousarray(self._data[mask])
+
 
 class InputDataNeighbourhoodsCSR(InputData):
     """Precomputed neighbourhoods in CSR form (row_ptr int64 ``[n+1]``, col_idx int32/int64
@@ -271,6 +278,12 @@ class InputDataNeighbourhoodsCSR(InputData):
         if meta is not None:
             _meta.update(meta)
         self.meta = _meta
+
+    def to_csr(self):
+        rp, ci = self.row_ptr, self.col_idx
+        if hasattr(rp, "is_cuda"):
+            rp, ci = rp.cpu().numpy(), ci.cpu().numpy()
+        return np.ascontiguousarray(rp, dtype=P_AINDEX), np.ascontiguousarray(ci, dtype=P_AINDEX)
 
 
 class Neighbourhoods:

@@ -6,7 +6,7 @@ import weakref
 import numpy as np
 
 from . import recipes
-from ._fit import Fitter, FitterB200Fused
+from ._fit import Fitter, FitterB200Fused, Predictor
 from ._types import InputData, InputDataComponents, Labels
 from .report import Record, Summary
 
@@ -63,8 +63,11 @@ class Bundle:
 class Clustering:
     """``Clustering(data).fit(radius_cutoff, cnn_cutoff, member_cutoff)`` on a B200."""
 
-    def __init__(self, data=None, *, fitter=None, recipe=None, **recipe_kwargs):
+    def __init__(self, data=None, *, fitter=None, predictor=None, recipe=None, **recipe_kwargs):
         builder = recipes.Builder(recipe, **recipe_kwargs)
+        self._predictor = predictor if isinstance(predictor, Predictor) else None
+        if predictor is not None and self._predictor is None:
+            builder.recipe["predictor"] = predictor
         if data is None:
             self._bundle = None
         elif isinstance(data, Bundle):
@@ -80,6 +83,9 @@ class Clustering:
                 builder.recipe["fitter"] = fitter
             f = builder.make_component("fitter")
             self._fitter = None if f is object else f
+        if self._predictor is None:
+            pr = builder.make_component("predictor")
+            self._predictor = None if pr is object else pr
 
     @property
     def root(self):
@@ -142,6 +148,35 @@ class Clustering:
                     params_parent[old_label + n_clusters] = p
 
         _reel(bundle, depth)
+
+    def predict(self, other, radius_cutoff: float, cnn_cutoff: int, clusters=None, cnn_offset=None, info: bool = True,
+                record: bool = True, record_time: bool = True, v: bool = True, purge: bool = False, bundle=None) -> None:
+        """Cluster labels for the points of ``other`` (a Bundle or a Clustering) from this clustering's labels:
+        same arguments and effects as the reference's ``Clustering.predict`` (``cluster.pyx:560-653``)."""
+        if bundle is None:
+            bundle = self._bundle
+        if isinstance(other, Clustering):
+            other = other._bundle
+        if cnn_offset is None:
+            cnn_offset = 0
+        cnn_cutoff -= cnn_offset
+        assert cnn_cutoff >= 0
+        if (other._labels is None) or purge or (not other._labels.meta.get("frozen", False)):
+            other._labels = Labels(np.zeros(other._input_data.n_points, order="C", dtype=np.int64))
+        cluster_params = self._predictor.make_parameters(radius_cutoff, cnn_cutoff, 0)
+        if clusters is None:
+            clusters = bundle._labels.to_set() - {0}
+        other._labels.consider_set = set(clusters)
+        t0 = time.perf_counter()
+        self._predictor.predict(bundle._input_data, other._input_data, bundle._labels, other._labels, cluster_params)
+        execution_time = time.perf_counter() - t0 if record_time else None
+        if info:
+            params = {k: (radius_cutoff, cnn_cutoff) for k in clusters if k != 0}
+            old_params = other._labels.meta.get("params", {})
+            old_params.update(params)
+            other._labels.meta.update({"params": old_params, "reference": weakref.proxy(bundle), "origin": "predict"})
+        other._labels.meta["frozen"] = True
+        del execution_time
 
     def fit_sweep(self, radius_cutoffs, cnn_cutoffs, member_cutoff=None, max_clusters=None, return_labels=True):
         """Every cell of a ``radius_cutoffs x cnn_cutoffs`` scan, labels identical to one ``fit`` per cell

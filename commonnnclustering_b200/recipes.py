@@ -82,6 +82,7 @@ COMPONENT_NAME_TYPE_MAP = {
         "screen": _types.SimilarityCheckerCommonNN,
     },
     "fitter": {"b200": _fit.FitterB200Fused, "b200_staged": _fit.FitterB200, "bfs": _fit.FitterB200Fused},
+    "predictor": {"b200": _fit.PredictorB200, "firstmatch": _fit.PredictorB200},
 }
 
 COMPONENT_ALT_KW_MAP = {
@@ -90,6 +91,9 @@ COMPONENT_ALT_KW_MAP = {
     "ngetter": "neighbours_getter", "ongetter": "neighbours_getter_other", "dgetter": "distance_getter",
     "checker": "similarity_checker", "q": "queue", "prep": "preparation_hook",
 }
+
+# component keywords that share the type table of another keyword (reference ``recipes.py``, COMPONENT_KW_TYPE_ALIAS_MAP)
+COMPONENT_KW_TYPE_ALIAS_MAP = {"neighbours_getter_other": "neighbours_getter", "neighbour_neighbours": "neighbours"}
 
 REGISTERED_RECIPES = {
     "none": {},
@@ -101,6 +105,11 @@ REGISTERED_RECIPES = {
         "fitter.checker": "commonnn_b200",
         "fitter.ngetter.dgetter": "metric",
         "fitter.ngetter.dgetter.metric": "euclidean_r",
+        "predictor": "b200",
+        "predictor.ngetter": "radius_b200",
+        "predictor.checker": "commonnn_b200",
+        "predictor.ngetter.dgetter": "metric",
+        "predictor.ngetter.dgetter.metric": "euclidean_r",
     },
     "sorted_neighbourhoods": {
         "input_data": "neighbourhoods_b200",
@@ -108,6 +117,9 @@ REGISTERED_RECIPES = {
         "fitter": "b200_staged",
         "fitter.ngetter": ("lookup", (), {"is_sorted": True}),
         "fitter.checker": "commonnn_b200",
+        "predictor": "b200",
+        "predictor.ngetter": ("lookup", (), {"is_sorted": True}),
+        "predictor.checker": "commonnn_b200",
     },
     "neighbourhoods_csr": {
         "input_data": "neighbourhoods_csr",
@@ -155,13 +167,14 @@ class Builder:
         if details is None:
             return None
         args, kwargs = (), {}
+        type_kw = COMPONENT_KW_TYPE_ALIAS_MAP.get(component_kw, component_kw)
         if isinstance(details, str):
-            ctype = COMPONENT_NAME_TYPE_MAP[component_kw][details]
+            ctype = COMPONENT_NAME_TYPE_MAP[type_kw][details]
         elif isinstance(details, tuple):
             ctype, args, kwargs = details
             kwargs = dict(kwargs)
             if isinstance(ctype, str):
-                ctype = COMPONENT_NAME_TYPE_MAP[component_kw][ctype]
+                ctype = COMPONENT_NAME_TYPE_MAP[type_kw][ctype]
         else:
             ctype = details
         if hasattr(ctype, "get_builder_kwargs"):

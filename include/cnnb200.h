@@ -199,6 +199,32 @@ int cnnb200_components_labels(cnnb200_ctx *ctx, int64_t current_start, int64_t *
                               int fresh, int64_t *n_clusters_out);
 
 /* ---------------------------------------------------------------------------------------
+ * Prediction for points OUTSIDE the clustered set.  Replaces PredictorFirstmatch.predict
+ * (_fit.pyx:1231-1291) with NeighboursGetterExtBruteForce._get_other (_types.pyx:1712-1731) or
+ * NeighboursGetterExtLookup._get_other (:1819-1832).
+ *
+ *   neighbours_other_from_points  N_o(p) = clustered points within the cutoff of other point p, for all p.
+ *       Needs cnnb200_neighbours_from_points on the clustered set first (same cutoff and metric are used;
+ *       methods grid and tiled; with device input the caller keeps the coordinates alive).
+ *   neighbours_other_from_csr     the same, precomputed: row_ptr int64 [m+1], col_idx int64 [nnz] (indices
+ *       into the clustered set, ascending); the clustered set's own neighbourhoods were given by
+ *       cnnb200_neighbours_from_csr / _from_padded.
+ *   predict   labels int64 [n] of the clustered set; label_ok uint8 [max_label+1] marks the labels of the
+ *       consider set (Clustering.predict's `clusters`, cluster.pyx:621-624).  other_labels int64 [m] and
+ *       other_consider uint8 [m] are updated in place exactly like the reference: a point with
+ *       other_consider != 0 and more than n_member_cutoff neighbours gets the label of the first member m
+ *       (ascending index) of N_o(p) whose label is in the consider set, which has more than n_member_cutoff
+ *       neighbours itself and |N_o(p) ∩ N(m)| >= similarity_cutoff; its other_consider becomes 0.
+ * ------------------------------------------------------------------------------------- */
+int cnnb200_neighbours_other_from_points(cnnb200_ctx *ctx, const double *x_other, int loc, int64_t m, int64_t d,
+                                         int64_t *nnz_out);
+int cnnb200_neighbours_other_from_csr(cnnb200_ctx *ctx, const int64_t *row_ptr, const int64_t *col_idx, int loc,
+                                      int64_t m, int64_t nnz);
+int cnnb200_predict(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_t similarity_cutoff, const int64_t *labels,
+                    const uint8_t *label_ok, int64_t max_label, int64_t *other_labels, uint8_t *other_consider,
+                    int loc);
+
+/* ---------------------------------------------------------------------------------------
  * Labels.sort_by_size (_types.pyx:212-286), in place on labels int64 [n] (HOST or DEVICE):
  * clusters ranked by size descending, ties by first occurrence (Counter.most_common order);
  * rank > max_clusters -> 0; size < member_cutoff -> 0; survivors renumbered 1, 2, ...

@@ -181,3 +181,63 @@ def fit_points(x, r: float, c: int, member_cutoff=None, max_clusters=None, sort=
     if sort:
         sort_by_size(labels, member_cutoff, max_clusters)
     return labels
+
+
+def neighbours_other(x, x_other, radius_cutoff: float, metric: str = "euclidean_r"):
+    """NeighboursGetterExtBruteForce._get_other (_types.pyx:1712-1731) for every other point: CSR of the clustered
+    points within the cutoff, ascending.  NumPy restatement of the reference's f64 expression (sequential sum of
+    squared differences, no FMA): for small cases."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    xo = np.ascontiguousarray(x_other, dtype=np.float64)
+    rows = []
+    for p in range(xo.shape[0]):
+        s = np.zeros(x.shape[0])
+        for k in range(x.shape[1]):
+            t = xo[p, k] - x[:, k]
+            s = s + t * t
+        if metric == "euclidean":
+            s = np.sqrt(s)
+        rows.append(np.flatnonzero(s <= radius_cutoff))
+    row_ptr = np.zeros(len(rows) + 1, dtype=np.int64)
+    np.cumsum([r.size for r in rows], out=row_ptr[1:])
+    return row_ptr, (np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)).astype(np.int64)
+
+
+def predict_csr(row_ptr, col_idx, o_row_ptr, o_col_idx, labels, n_member_cutoff, similarity_cutoff, clusters=None,
+                other_labels=None, other_consider=None):
+    """PredictorFirstmatch.predict (_fit.pyx:1231-1291), loop for loop."""
+    labels = np.asarray(labels)
+    m = o_row_ptr.size - 1
+    if other_labels is None:
+        other_labels = np.zeros(m, dtype=np.int64)
+    if other_consider is None:
+        other_consider = np.ones(m, dtype=np.uint8)
+    if clusters is None:
+        clusters = set(np.unique(labels).tolist()) - {0}
+    for p in range(m):
+        if other_consider[p] == 0:
+            continue
+        na = o_col_idx[o_row_ptr[p]:o_row_ptr[p + 1]]
+        if not na.size > n_member_cutoff:
+            continue
+        for member in na:
+            label = int(labels[member])
+            if label not in clusters:
+                continue
+            nb = col_idx[row_ptr[member]:row_ptr[member + 1]]
+            if not nb.size > n_member_cutoff:
+                continue
+            if similarity_cutoff == 0 or count_common(na, nb) >= similarity_cutoff:
+                other_consider[p] = 0
+                other_labels[p] = label
+                break
+    return other_labels, other_consider
+
+
+def predict_points(x, labels, x_other, r: float, c: int, clusters=None, metric="euclidean_r"):
+    """Clustering.predict with brute-force getters on coordinates (cluster.pyx:560-653)."""
+    p = make_parameters(r, c, metric=metric, current_start=0)
+    row_ptr, col_idx = neighbours(x, p["radius_cutoff"], metric, "brute")
+    o_row_ptr, o_col_idx = neighbours_other(x, x_other, p["radius_cutoff"], metric)
+    return predict_csr(row_ptr, col_idx, o_row_ptr, o_col_idx, labels, p["n_member_cutoff"], p["similarity_cutoff"],
+                       clusters)[0]

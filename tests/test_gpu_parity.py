@@ -500,3 +500,79 @@ def test_hierarchical_recluster_equals_reference():
         out.append(np.array(cl.labels))
     np.testing.assert_array_equal(out[0], out[1])
     assert out[0].max() > 2
+
+
+# ---- prediction --------------------------------------------------------------------------------
+@pytest.mark.parametrize("maker,r,c,r2,c2,method", [
+    (lambda: datasets.blobs_2d(2400), 0.12, 8, 0.15, 5, "auto"),          # cell list, 2-D
+    (lambda: datasets.md_like_3d(3000), 0.45, 6, 0.5, 4, "auto"),         # cell list, 3-D
+    (lambda: cases.gauss(1600, 5, 41) * 0.6, 0.9, 6, 1.0, 4, "tiled"),    # any dimension: all-pairs f64
+    (lambda: cases.lattice(1800, 2, 42), 0.25, 3, 0.25, 2, "auto"),       # exact ties
+])
+def test_predict_equals_oracle(maker, r, c, r2, c2, method):
+    pts = maker()
+    x, x_other = np.ascontiguousarray(pts[::2]), np.ascontiguousarray(pts)   # the reference's own test layout: stride 2
+    cl = cluster.Clustering(x, fitter__ngetter__method=method, predictor__ngetter__method=method) if method != "auto" \
+        else cluster.Clustering(x)
+    cl.fit(r, c, member_cutoff=5, v=False)
+    other = cluster.Clustering(x_other)
+    cl.predict(other, r2, c2)
+    want = port.predict_points(x, cl.labels, x_other, r2, c2)
+    np.testing.assert_array_equal(other.labels, want)
+    assert want.max() > 0 and (other.root._labels.consider[want > 0] == 0).all()
+    assert other.root._labels.meta["frozen"] and other.root._labels.meta["origin"] == "predict"
+    # restricted to one cluster, on frozen labels: a second call only fills points that are still considered
+    other2 = cluster.Clustering(x_other)
+    cl.predict(other2, r2, c2, clusters=[1])
+    want1 = port.predict_points(x, cl.labels, x_other, r2, c2, clusters={1})
+    np.testing.assert_array_equal(other2.labels, want1)
+
+
+def test_predict_from_neighbourhoods_equals_oracle():
+    """The reference's own predict test layout (test/integration/test_procedures.py:219-277): both sets given as
+    neighbourhoods, the other set's neighbourhoods being those of its points IN the clustered set."""
+    pts = datasets.blobs_2d(2000)
+    x, x_other = np.ascontiguousarray(pts[::2]), np.ascontiguousarray(pts)
+    r, c = 0.15, 4
+    rp, ci = port.neighbours(x, r * r)
+    orp, oci = port.neighbours_other(x, x_other, r * r)
+    labels = port.fit_points(x, 0.12, 8, member_cutoff=5)
+    cl = cluster.Clustering(_types.InputDataNeighbourhoodsCSR(rp, ci), recipe="neighbourhoods_csr",
+                            predictor="b200", predictor__ngetter=("lookup", (), {"is_sorted": True}))
+    cl.labels = labels.copy()
+    other = cluster.Clustering(_types.InputDataNeighbourhoodsCSR(orp, oci), recipe="neighbourhoods_csr")
+    cl.predict(other, r, c)
+    want, _ = port.predict_csr(rp, ci, orp, oci, labels, c + 1, c + 2)
+    np.testing.assert_array_equal(other.labels, want)
+
+
+def test_predict_equals_reference():
+    from oracle import ref
+
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rmod = ref.module()
+    from cnnclustering import _fit as rfit, _types as rtypes, recipes as rrecipes
+
+    pts = datasets.blobs_2d(1200)
+    x, x_other = np.ascontiguousarray(pts[::2]), np.ascontiguousarray(pts)
+    recipe = dict(rrecipes.get_registered_recipe("coordinates"))
+    # types instead of names: the reference's name table has no entry for the `*_other` / `neighbour_neighbours` keywords
+    recipe.update({"predictor": rfit.PredictorFirstmatch, "predictor.ngetter": rtypes.NeighboursGetterExtBruteForce,
+                   "predictor.ngetter.dgetter": rtypes.DistanceGetterExtMetric,
+                   "predictor.ngetter.dgetter.metric": rtypes.MetricExtEuclideanReduced,
+                   "predictor.ongetter": rtypes.NeighboursGetterExtBruteForce,
+                   "predictor.ongetter.dgetter": rtypes.DistanceGetterExtMetric,
+                   "predictor.ongetter.dgetter.metric": rtypes.MetricExtEuclideanReduced,
+                   "predictor.na": rtypes.NeighboursExtVectorCPPUnorderedSet,
+                   "predictor.nb": rtypes.NeighboursExtVectorCPPUnorderedSet,
+                   "predictor.checker": rtypes.SimilarityCheckerExtSwitchContains})
+    out = []
+    for mod, kw in ((cluster, {}), (rmod, {"recipe": recipe})):
+        cl = mod.Clustering(x, **kw)
+        cl.fit(0.15, 8, member_cutoff=5, v=False)
+        other = mod.Clustering(x_other, **kw)
+        cl.predict(other._bundle, 0.18, 5)
+        out.append(np.array(other.labels))
+    np.testing.assert_array_equal(out[0], out[1])
+    assert out[0].max() > 0

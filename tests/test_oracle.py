@@ -137,3 +137,39 @@ def test_port_equals_live_reference_on_random_configs():
         rp, ci = port.neighbours(x, r * r)
         got2 = ref.fit_neighbourhoods(rp, ci, c, **opts)
         np.testing.assert_array_equal(got2, want)
+
+
+def test_predict_port_equals_reference():
+    """The oracle's restatement of PredictorFirstmatch.predict (_fit.pyx:1231-1291) against the reference itself."""
+    from oracle import ref
+
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rmod = ref.module()
+    from cnnclustering import _fit as rfit, _types as rtypes, recipes as rrecipes
+
+    from commonnnclustering_b200 import datasets
+
+    pts = datasets.blobs_2d(700)
+    x, x_other = np.ascontiguousarray(pts[::2]), np.ascontiguousarray(pts)
+    recipe = dict(rrecipes.get_registered_recipe("coordinates"))
+    recipe.update({"predictor": rfit.PredictorFirstmatch, "predictor.ngetter": rtypes.NeighboursGetterExtBruteForce,
+                   "predictor.ngetter.dgetter": rtypes.DistanceGetterExtMetric,
+                   "predictor.ngetter.dgetter.metric": rtypes.MetricExtEuclideanReduced,
+                   "predictor.ongetter": rtypes.NeighboursGetterExtBruteForce,
+                   "predictor.ongetter.dgetter": rtypes.DistanceGetterExtMetric,
+                   "predictor.ongetter.dgetter.metric": rtypes.MetricExtEuclideanReduced,
+                   "predictor.na": rtypes.NeighboursExtVectorCPPUnorderedSet,
+                   "predictor.nb": rtypes.NeighboursExtVectorCPPUnorderedSet,
+                   "predictor.checker": rtypes.SimilarityCheckerExtSwitchContains})
+    cl = rmod.Clustering(x, recipe=recipe)
+    cl.fit(0.2, 6, member_cutoff=5, v=False)
+    other = rmod.Clustering(x_other, recipe=recipe)
+    cl.predict(other._bundle, 0.25, 4)
+    labels = np.array(cl.labels)
+    assert np.array_equal(labels, port.fit_points(x, 0.2, 6, member_cutoff=5))
+    got = port.predict_points(x, labels, x_other, 0.25, 4)
+    assert np.array_equal(got, np.array(other.labels)) and got.max() > 0
+    other1 = rmod.Clustering(x_other, recipe=recipe)
+    cl.predict(other1._bundle, 0.25, 4, clusters=[1])
+    assert np.array_equal(port.predict_points(x, labels, x_other, 0.25, 4, clusters={1}), np.array(other1.labels))

@@ -91,6 +91,7 @@ class FitterB200Fused(FitterB200):
                    member_cutoff=None, max_clusters=None) -> int:
         ctx = self.ctx
         g = self._neighbours_getter
+        g.prepare(ctx)
         n_clusters = ctx.fit_points(
             input_data.device_or_host_array, cluster_params.radius_cutoff, cluster_params.n_member_cutoff,
             cluster_params.similarity_cutoff, labels.labels, cluster_params.current_start,

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcnnb200.so")
 
 HOST, DEVICE = 0, 1
-METRIC_IDS = {"euclidean_r": 0, "euclidean": 1}
+METRIC_IDS = {"euclidean_r": 0, "euclidean": 1, "euclidean_periodic_r": 2}
 METHOD_IDS = {"auto": 0, "grid": 1, "tiled": 2, "tensor": 3}
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
@@ -28,6 +28,7 @@ SIGNATURES = {
     "cnnb200_ctx_set_stream": [_P, _P],
     "cnnb200_ctx_set_allocator": [_P, ALLOC_FN, FREE_FN, _P],
     "cnnb200_ctx_synchronize": [_P],
+    "cnnb200_ctx_set_periodic_bounds": [_P, _P, _I64],
     "cnnb200_ctx_release": [_P],
     "cnnb200_neighbours_from_points": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int, C.c_int, C.POINTER(_I64)],
     "cnnb200_grid_begin": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int],
@@ -169,6 +170,10 @@ class Context:
         a, f = ALLOC_FN(_alloc), FREE_FN(_free)
         self._keep = [a, f]
         check(self._lib.cnnb200_ctx_set_allocator(self._h, a, f, None))
+
+    def set_periodic_bounds(self, bounds):
+        b = np.ascontiguousarray(bounds, dtype=np.float64)
+        check(self._lib.cnnb200_ctx_set_periodic_bounds(self._h, b.ctypes.data, b.shape[0]))
 
     def synchronize(self):
         check(self._lib.cnnb200_ctx_synchronize(self._h))

@@ -348,6 +348,31 @@ class MetricEuclidean(Metric):
         return float(np.sqrt(MetricEuclideanReduced().calc_distance(index_a, index_b, input_data)))
 
 
+class MetricEuclideanPeriodicReduced(Metric):
+    """Squared Euclidean distance with per-dimension periods ``bounds`` (0 = not periodic).
+    Reference: ``MetricExtEuclideanPeriodicReduced``, ``_types.pyx:2290-2348``."""
+    name = "euclidean_periodic_r"
+
+    def __init__(self, bounds):
+        self.bounds = np.ascontiguousarray(bounds, dtype=P_AVALUE)
+
+    def adjust_radius(self, radius_cutoff: float) -> float:
+        return float(radius_cutoff) ** 2
+
+    def calc_distance(self, index_a: int, index_b: int, input_data) -> float:
+        x = input_data.to_components_array()
+        total = 0.0
+        for k in range(x.shape[1]):
+            bound = float(self.bounds[k])
+            distance = abs(float(x[index_a, k]) - float(x[index_b, k]))
+            if bound > 0:
+                distance = distance % bound
+                if distance > bound / 2:
+                    distance = bound - distance
+            total += distance * distance
+        return total
+
+
 class DistanceGetterMetric:
     """Reference: ``DistanceGetterExtMetric``, ``_types.pyx:1966-2017`` (pure indirection)."""
 
@@ -396,8 +421,14 @@ class NeighboursGetterRadius(NeighboursGetter):
     def metric(self):
         return self._distance_getter._metric
 
+    def prepare(self, ctx):
+        """Hands metric state the C library cannot take through the metric id (periods) to the context."""
+        if isinstance(self.metric, MetricEuclideanPeriodicReduced):
+            ctx.set_periodic_bounds(self.metric.bounds)
+
     def get_all(self, input_data, cluster_params, ctx=None) -> Neighbourhoods:
         ctx = ctx or _lib.default_context()
+        self.prepare(ctx)
         ctx.neighbours_from_points(input_data.device_or_host_array, cluster_params.radius_cutoff,
                                    metric=self.metric.name, method=self.method)
         return Neighbourhoods(ctx)

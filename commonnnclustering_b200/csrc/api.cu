@@ -99,7 +99,7 @@ extern "C" int cnnb200_ctx_create(int device, cnnb200_ctx **out) {
 }
 
 #define FOR_EACH_BUF(c, F)                                                                          \
-    F(c->b_row_ptr) F(c->b_col_idx) F(c->b_perm) F(c->b_deg) F(c->b_x) F(c->b_xs) F(c->b_xf) F(c->b_xperm) F(c->b_o_x) F(c->b_o_deg) F(c->b_o_row_ptr) F(c->b_o_col_idx) F(c->b_o_labels) F(c->b_cell_id)   \
+    F(c->b_row_ptr) F(c->b_col_idx) F(c->b_perm) F(c->b_deg) F(c->b_x) F(c->b_bounds) F(c->b_xs) F(c->b_xf) F(c->b_xperm) F(c->b_o_x) F(c->b_o_deg) F(c->b_o_row_ptr) F(c->b_o_col_idx) F(c->b_o_labels) F(c->b_cell_id)   \
     F(c->b_cell_id_sorted) F(c->b_idx) F(c->b_cell_start) F(c->b_bbox) F(c->b_cub) F(c->b_tmp0)     \
     F(c->b_tmp1) F(c->b_tmp2) F(c->b_parent) F(c->b_core) F(c->b_above) F(c->b_edges) F(c->b_worklist) F(c->b_cell_count) F(c->b_minorig) F(c->b_flags)             \
     F(c->b_rank) F(c->b_labels) F(c->b_consider) F(c->b_stats) F(c->b_lab_count) F(c->b_lab_first)  \
@@ -117,6 +117,7 @@ extern "C" int cnnb200_ctx_release(cnnb200_ctx *ctx) {
     ctx->have_grid = false;
     ctx->have_points = false;
     ctx->have_other = false;
+    ctx->n_bounds = 0;
     ctx->row_ptr = nullptr;
     ctx->col_idx = nullptr;
     ctx->perm = nullptr;
@@ -154,6 +155,16 @@ extern "C" int cnnb200_ctx_set_allocator(cnnb200_ctx *ctx, cnnb200_alloc_fn allo
         ctx->free_ = default_free;
         ctx->alloc_user = nullptr;
     }
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_ctx_set_periodic_bounds(cnnb200_ctx *ctx, const double *bounds, int64_t d) {
+    if (!ctx || !bounds || d < 1) CNN_FAIL(CNNB200_E_INVALID, "set_periodic_bounds: bad argument");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_bounds, sizeof(double) * (size_t)d));
+    CNN_CUDA(cudaMemcpyAsync(ctx->b_bounds.p, bounds, sizeof(double) * (size_t)d, cudaMemcpyHostToDevice, ctx->stream));
+    CNN_CUDA(cudaStreamSynchronize(ctx->stream));  // the host array may go away
+    ctx->n_bounds = d;
     return CNNB200_OK;
 }
 
@@ -230,8 +241,13 @@ extern "C" int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x,
     if (!ctx || !x) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_points: NULL argument");
     if (n < 1 || d < 1) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_points: need n >= 1 and d >= 1");
     if (n >= (1ll << 31) - 1) CNN_FAIL(CNNB200_E_RANGE, "neighbours_from_points: n must be < 2^31-1");
-    if (metric != CNNB200_METRIC_EUCLIDEAN_REDUCED && metric != CNNB200_METRIC_EUCLIDEAN)
+    if (metric != CNNB200_METRIC_EUCLIDEAN_REDUCED && metric != CNNB200_METRIC_EUCLIDEAN &&
+        metric != CNNB200_METRIC_EUCLIDEAN_PERIODIC_REDUCED)
         CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_points: unknown metric %d", metric);
+    if (metric == CNNB200_METRIC_EUCLIDEAN_PERIODIC_REDUCED) {
+        if (method != 0 && method != 2) CNN_FAIL(CNNB200_E_INVALID, "the periodic metric is served by the tiled method only");
+        method = 2;
+    }
     if (!(radius_cutoff >= 0.0)) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_points: radius_cutoff must be >= 0");
     if (method == 0) method = d <= 3 ? 1 : 2;
     if (method == 1 && d > 3) CNN_FAIL(CNNB200_E_INVALID, "grid method needs d <= 3 (got %lld)", (ll)d);

@@ -13,10 +13,13 @@
 #define DT 64   // tile edge (rows and columns)
 #define DK 16   // dimension chunk staged per step
 
-template <bool SQRT, bool FILL>
+// METRIC: 0 = MetricExtEuclideanReduced, 1 = MetricExtEuclidean, 2 = MetricExtEuclideanPeriodicReduced
+// (_types.pyx:2290-2318: |a - b| folded into [0, bound/2] per dimension when bound > 0, then squared and summed)
+template <int METRIC, bool FILL>
 __global__ void __launch_bounds__(256)
-dense_rows_kernel(const double *__restrict__ x, ll n, int d, double rc, int *__restrict__ deg,
-                  const ll *__restrict__ row_ptr, int *__restrict__ col_idx) {
+dense_rows_kernel(const double *__restrict__ x, ll n, int d, double rc, const double *__restrict__ bounds,
+                  int *__restrict__ deg, const ll *__restrict__ row_ptr, int *__restrict__ col_idx) {
+    constexpr bool SQRT = METRIC == 1;
     __shared__ double sa[DK][DT];
     __shared__ double sb[DK][DT];
     __shared__ unsigned long long smask[DT];
@@ -49,6 +52,7 @@ dense_rows_kernel(const double *__restrict__ x, ll n, int d, double rc, int *__r
 #pragma unroll
             for (int kk = 0; kk < DK; ++kk) {
                 double av[4], bv[4];
+                const double bound = (METRIC == 2 && k0 + kk < d) ? bounds[k0 + kk] : 0.0;
 #pragma unroll
                 for (int a = 0; a < 4; ++a) av[a] = sa[kk][ty * 4 + a];
 #pragma unroll
@@ -58,6 +62,13 @@ dense_rows_kernel(const double *__restrict__ x, ll n, int d, double rc, int *__r
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         double t = __dsub_rn(av[a], bv[b]);
+                        if (METRIC == 2) {
+                            t = fabs(t);
+                            if (bound > 0.0) {
+                                t = fmod(t, bound);  // exact, as in C
+                                if (t > bound * 0.5) t = __dsub_rn(bound, t);
+                            }
+                        }
                         acc[a][b] = __dadd_rn(acc[a][b], __dmul_rn(t, t));
                     }
             }
@@ -108,15 +119,22 @@ int cnn_dense_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double rad
     CNN_TRY(cnn_ensure(ctx, ctx->b_row_ptr, sizeof(ll) * (size_t)(n + 1)));
     CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>() + n, 0, sizeof(int), st));
     int blocks = (int)((n + DT - 1) / DT);
-    bool sq = metric == CNNB200_METRIC_EUCLIDEAN;
+    const double *bounds = nullptr;
+    if (metric == CNNB200_METRIC_EUCLIDEAN_PERIODIC_REDUCED) {
+        if (ctx->n_bounds != d) CNN_FAIL(CNNB200_E_STATE, "periodic metric: set %lld bounds with cnnb200_ctx_set_periodic_bounds first", (long long)d);
+        bounds = ctx->b_bounds.as<double>();
+    }
     {
     Span sp(ctx, T_SEARCH_COUNT);
-    if (sq)
-        dense_rows_kernel<true, false><<<blocks, 256, 0, st>>>(d_x, n, (int)d, radius_cutoff,
-                                                               ctx->b_deg.as<int>(), nullptr, nullptr);
+    if (metric == CNNB200_METRIC_EUCLIDEAN)
+        dense_rows_kernel<1, false><<<blocks, 256, 0, st>>>(d_x, n, (int)d, radius_cutoff, bounds,
+                                                            ctx->b_deg.as<int>(), nullptr, nullptr);
+    else if (metric == CNNB200_METRIC_EUCLIDEAN_PERIODIC_REDUCED)
+        dense_rows_kernel<2, false><<<blocks, 256, 0, st>>>(d_x, n, (int)d, radius_cutoff, bounds,
+                                                            ctx->b_deg.as<int>(), nullptr, nullptr);
     else
-        dense_rows_kernel<false, false><<<blocks, 256, 0, st>>>(d_x, n, (int)d, radius_cutoff,
-                                                                ctx->b_deg.as<int>(), nullptr, nullptr);
+        dense_rows_kernel<0, false><<<blocks, 256, 0, st>>>(d_x, n, (int)d, radius_cutoff, bounds,
+                                                            ctx->b_deg.as<int>(), nullptr, nullptr);
     }
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
@@ -125,12 +143,15 @@ int cnn_dense_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double rad
     CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
     {
     Span sp(ctx, T_SEARCH_FILL);
-    if (sq)
-        dense_rows_kernel<true, true><<<blocks, 256, 0, st>>>(d_x, n, (int)d, radius_cutoff, nullptr,
-                                                              ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
+    if (metric == CNNB200_METRIC_EUCLIDEAN)
+        dense_rows_kernel<1, true><<<blocks, 256, 0, st>>>(d_x, n, (int)d, radius_cutoff, bounds, nullptr,
+                                                           ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
+    else if (metric == CNNB200_METRIC_EUCLIDEAN_PERIODIC_REDUCED)
+        dense_rows_kernel<2, true><<<blocks, 256, 0, st>>>(d_x, n, (int)d, radius_cutoff, bounds, nullptr,
+                                                           ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
     else
-        dense_rows_kernel<false, true><<<blocks, 256, 0, st>>>(d_x, n, (int)d, radius_cutoff, nullptr,
-                                                               ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
+        dense_rows_kernel<0, true><<<blocks, 256, 0, st>>>(d_x, n, (int)d, radius_cutoff, bounds, nullptr,
+                                                           ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
     }
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();

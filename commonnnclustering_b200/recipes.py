@@ -74,6 +74,9 @@ COMPONENT_NAME_TYPE_MAP = {
     "metric": {
         "euclidean": _types.MetricEuclidean,
         "euclidean_r": _types.MetricEuclideanReduced,
+        "euclidean_reduced": _types.MetricEuclideanReduced,
+        "euclidean_periodic_r": _types.MetricEuclideanPeriodicReduced,
+        "euclidean_periodic_reduced": _types.MetricEuclideanPeriodicReduced,
     },
     "similarity_checker": {
         "commonnn_b200": _types.SimilarityCheckerCommonNN,

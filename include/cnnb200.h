@@ -43,6 +43,9 @@ extern "C" {
  * MetricExtEuclidean (_types.pyx:2170-2207, "euclidean"). */
 #define CNNB200_METRIC_EUCLIDEAN_REDUCED 0
 #define CNNB200_METRIC_EUCLIDEAN 1
+/* MetricExtEuclideanPeriodicReduced (_types.pyx:2290-2348, "euclidean_periodic_r"): per-dimension period `bounds[k]`
+ * (0 = not periodic), set with cnnb200_ctx_set_periodic_bounds; the tiled all-pairs method only. */
+#define CNNB200_METRIC_EUCLIDEAN_PERIODIC_REDUCED 2
 
 #define CNNB200_OK 0
 #define CNNB200_E_INVALID -1   /* bad argument                                  */
@@ -68,6 +71,8 @@ int cnnb200_ctx_set_stream(cnnb200_ctx *ctx, void *stream);
 int cnnb200_ctx_set_allocator(cnnb200_ctx *ctx, cnnb200_alloc_fn alloc, cnnb200_free_fn free_,
                               void *user);
 int cnnb200_ctx_synchronize(cnnb200_ctx *ctx);
+/* bounds: HOST double [d], the constructor argument of MetricExtEuclideanPeriodicReduced (_types.pyx:2293-2294). */
+int cnnb200_ctx_set_periodic_bounds(cnnb200_ctx *ctx, const double *bounds, int64_t d);
 /* Releases all device scratch held by the context (it is re-acquired on demand). */
 int cnnb200_ctx_release(cnnb200_ctx *ctx);
 

@@ -40,6 +40,10 @@ def lib():
             f.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_double, C.c_int, _i64p, _i64p]
         L.cnn_oracle_neighbours_brute_count.restype = None
         L.cnn_oracle_neighbours_brute_fill.restype = None
+        L.cnn_oracle_neighbours_periodic_count.restype = None
+        L.cnn_oracle_neighbours_periodic_count.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_double, _f64p, _i64p]
+        L.cnn_oracle_neighbours_periodic_fill.restype = None
+        L.cnn_oracle_neighbours_periodic_fill.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_double, _f64p, _i64p, _i64p]
         for name in ("check_sorted", "check_contains"):
             f = getattr(L, f"cnn_oracle_{name}")
             f.restype = C.c_int
@@ -241,3 +245,28 @@ def predict_points(x, labels, x_other, r: float, c: int, clusters=None, metric="
     o_row_ptr, o_col_idx = neighbours_other(x, x_other, p["radius_cutoff"], metric)
     return predict_csr(row_ptr, col_idx, o_row_ptr, o_col_idx, labels, p["n_member_cutoff"], p["similarity_cutoff"],
                        clusters)[0]
+
+
+def neighbours_periodic(x, radius_cutoff: float, bounds):
+    """Brute-force CSR under MetricExtEuclideanPeriodicReduced (_types.pyx:2290-2318); radius_cutoff = r*r."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    bounds = np.ascontiguousarray(bounds, dtype=np.float64)
+    n, d = x.shape
+    assert bounds.shape == (d,)
+    L = lib()
+    deg = np.zeros(n, dtype=np.int64)
+    L.cnn_oracle_neighbours_periodic_count(x, n, d, float(radius_cutoff), bounds, deg)
+    row_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(deg, out=row_ptr[1:])
+    col_idx = np.empty(max(int(row_ptr[-1]), 1), dtype=np.int64)
+    L.cnn_oracle_neighbours_periodic_fill(x, n, d, float(radius_cutoff), bounds, row_ptr, col_idx)
+    return row_ptr, col_idx[: int(row_ptr[-1])]
+
+
+def fit_points_periodic(x, r: float, c: int, bounds, member_cutoff=None, max_clusters=None, sort=True):
+    p = make_parameters(r, c, metric=None)
+    row_ptr, col_idx = neighbours_periodic(x, r * r, bounds)
+    labels = fit_bfs(row_ptr, col_idx, p["n_member_cutoff"], p["similarity_cutoff"], 1)
+    if sort:
+        sort_by_size(labels, member_cutoff, max_clusters)
+    return labels

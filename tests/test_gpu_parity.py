@@ -576,3 +576,35 @@ def test_predict_equals_reference():
         out.append(np.array(other.labels))
     np.testing.assert_array_equal(out[0], out[1])
     assert out[0].max() > 0
+
+
+# ---- periodic metric -----------------------------------------------------------------------------
+def test_periodic_metric_equals_oracle_and_reference(ctx):
+    rng = np.random.default_rng(3)
+    bounds = np.array([2 * np.pi, 0.0, 2 * np.pi])
+    x = np.ascontiguousarray(np.c_[rng.vonmises(3.0, 2.0, 2500) + np.pi, rng.standard_normal(2500) * 0.3,
+                                   rng.random(2500) * 2 * np.pi])
+    ctx.set_periodic_bounds(bounds)
+    ctx.neighbours_from_points(x, 0.35 ** 2, metric="euclidean_periodic_r")
+    rp, ci = ctx.neighbours_export()
+    want_rp, want_ci = port.neighbours_periodic(x, 0.35 ** 2, bounds)
+    np.testing.assert_array_equal(rp, want_rp)
+    np.testing.assert_array_equal(ci, want_ci)
+    cl = cluster.Clustering(x, fitter__ngetter__dgetter__metric=(_types.MetricEuclideanPeriodicReduced, (bounds,), {}))
+    cl.fit(0.35, 8, member_cutoff=5, v=False)
+    np.testing.assert_array_equal(cl.labels, port.fit_points_periodic(x, 0.35, 8, bounds, member_cutoff=5))
+    with pytest.raises(ValueError):
+        ctx.neighbours_from_points(x, 0.1, metric="euclidean_periodic_r", method="grid")
+    from oracle import ref
+
+    if ref.available():
+        rmod = ref.module()
+        from cnnclustering import _types as rtypes, recipes as rrecipes
+
+        recipe = dict(rrecipes.get_registered_recipe("coordinates"))
+        recipe["fitter.ngetter.dgetter.metric"] = (rtypes.MetricExtEuclideanPeriodicReduced, (bounds,), {})
+        rcl = rmod.Clustering(x[:1200], recipe=recipe)
+        rcl.fit(0.45, 6, member_cutoff=5, v=False)
+        ours = cluster.Clustering(x[:1200], fitter__ngetter__dgetter__metric=(_types.MetricEuclideanPeriodicReduced, (bounds,), {}))
+        ours.fit(0.45, 6, member_cutoff=5, v=False)
+        np.testing.assert_array_equal(ours.labels, np.array(rcl.labels))

@@ -173,3 +173,24 @@ def test_predict_port_equals_reference():
     other1 = rmod.Clustering(x_other, recipe=recipe)
     cl.predict(other1._bundle, 0.25, 4, clusters=[1])
     assert np.array_equal(port.predict_points(x, labels, x_other, 0.25, 4, clusters={1}), np.array(other1.labels))
+
+
+def test_periodic_metric_port_equals_reference():
+    """oracle: MetricExtEuclideanPeriodicReduced (_types.pyx:2290-2318) against the reference's own fit."""
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rmod = ref.module()
+    from cnnclustering import _types as rtypes, recipes as rrecipes
+
+    rng = np.random.default_rng(3)
+    bounds = np.array([2 * np.pi, 0.0, 2 * np.pi])
+    x = np.ascontiguousarray(np.c_[rng.vonmises(3.0, 2.0, 900) + np.pi, rng.standard_normal(900) * 0.3,
+                                   rng.random(900) * 2 * np.pi])
+    recipe = dict(rrecipes.get_registered_recipe("coordinates"))
+    recipe["fitter.ngetter.dgetter.metric"] = (rtypes.MetricExtEuclideanPeriodicReduced, (bounds,), {})
+    cl = rmod.Clustering(x, recipe=recipe)
+    for r, c in [(0.4, 5), (0.7, 12)]:
+        cl.fit(r, c, member_cutoff=3, v=False)
+        assert np.array_equal(np.array(cl.labels), port.fit_points_periodic(x, r, c, bounds, member_cutoff=3))
+    # wrap-around actually matters on this data
+    assert port.neighbours_periodic(x, 0.49, bounds)[0][-1] > port.neighbours(x, 0.49)[0][-1]

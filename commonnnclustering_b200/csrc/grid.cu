@@ -210,24 +210,23 @@ grid_rows_kernel(const double *__restrict__ xs, ll n, const int *__restrict__ ce
 }
 
 // ---- K2, fp32 filter form (the default single-pass kernel) ------------------------------------------------
-// Same tiles and groups as above (warp = 32 consecutive cell-sorted points, group = the points of one
-// cell), but the lanes hold CANDIDATES and the warp loops over the group's queries:
-//   * a chunk of 32 candidates of a run is loaded once (one coalesced float4 per lane: cell-local fp32
-//     coordinates) and tested against every query of the group, whose coordinates come out of shared
-//     memory as a broadcast; the result of (query, chunk) is one ballot word;
-//   * the test is an fp32 FILTER with a proven error bound: d2 <= R - eps is a neighbour, d2 > R + eps is
-//     not, and the (rare) pairs in between are decided by the reference's own f64 expression on the
-//     original coordinates (`within`), so the neighbour sets are exactly those of the f64 kernel.
-//     fp32 is accurate enough because all coordinates are relative to a nearby cell origin (|value| < 16h):
+// Same tiles as above (warp = 32 consecutive cell-sorted points).  A GROUP is a run of lanes whose points lie in
+// the same x-row of cells and at most GF_XSPAN cells apart; its candidate list is the union of the 3^D windows of
+// its cells (still 3^(D-1) contiguous index runs), so that neighbouring sparse cells are served as one well-filled
+// group.  Every lane of the group owns ONE query; the candidates of a run go through shared memory 32 at a time
+// (one coalesced float4 per lane: cell-local fp32 coordinates) and come back as broadcasts; a lane appends its
+// hits to its own (gapped) row -- candidates ascend, so rows come out sorted.  No votes, no ranking.
+//   * The test is an fp32 FILTER with a proven error bound: d2 <= R - eps is a neighbour, d2 > R + eps is not, and
+//     the (rare) pairs in between are decided by the reference's own f64 expression on the original coordinates
+//     (`within`), so the neighbour sets are exactly those of the f64 kernel.  A lane tracks the smallest |d2 - R| it
+//     meets in a chunk and, if that lies inside the band, redoes its chunk with the exact test for the borderline
+//     candidates (the row must stay ascending) -- no branch per candidate in the fast loop.
+//   * fp32 is accurate enough because all coordinates are relative to a nearby cell origin (|value| < 16h):
 //     every coordinate difference carries an error below delta = h * 2^-18, hence
 //     |d2_fp32 - d2| <= 2*sqrt(3)*delta*sqrt(d2) + 3*delta^2 + 2^-22*d2 < eps = h*r*2^-16 + h^2*2^-34 + R*2^-21.
-//   * the ballot words of up to 32 chunks are parked in shared memory and then expanded by the lane
-//     that owns the query straight into its (gapped) row -- candidates ascend, so rows come out sorted.
-// Per 32 distance tests the loop issues ~13 instructions (one LDS.128, 6 FP32, 2 compares, 2 votes,
-// one STS) instead of ~47 (3 LDG.64, 9 FP64, ballot ranking, scattered store) in the f64 form.
+// Per candidate the loop issues ~13 instructions for up to 32 distance tests (one LDS.128, 8 FP32, compare, store)
+// instead of ~47 per 32 tests (3 LDG.64, 9 FP64, ballot ranking, scattered store) in the f64 form.
 #define GF_WARPS 8
-#define GF_CHUNKS 32
-#define GF_LANE_PER_QUERY 8  // groups at least this large run one query per lane
 #define GF_XSPAN 3            // a group spans at most GF_XSPAN + 1 cells along x
 
 struct FilterParams {
@@ -236,19 +235,15 @@ struct FilterParams {
 };
 
 template <int D, bool SQRT>
-__global__ void __launch_bounds__(GF_WARPS * 32)
+__global__ void __launch_bounds__(GF_WARPS * 32, 4)
 grid_rows_f32_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, ll n,
                      const int *__restrict__ cell_sorted, const int *__restrict__ cell_start, GridDesc g, double rc,
                      FilterParams fp, int *__restrict__ deg, const ll *__restrict__ goff, int *__restrict__ out,
                      ll p_begin, ll p_end, unsigned long long *stats) {
     __shared__ float4 s_q[GF_WARPS][32];
-    __shared__ unsigned s_words[GF_WARPS][GF_CHUNKS][32];
-    __shared__ int s_q0[GF_WARPS][GF_CHUNKS];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float4 *qf = s_q[wid];
-    unsigned(*words)[32] = s_words[wid];
-    int *chunk_q0 = s_q0[wid];
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     unsigned long long n_recheck = 0;
@@ -294,122 +289,54 @@ grid_rows_f32_kernel(const double *__restrict__ xs, const float4 *__restrict__ x
                 if (D > 2) shz = (float)__dsub_rn(cell_origin(g.lo[2], g.h, rz), cell_origin(g.lo[2], g.h, cz));
             }
             int cnt = 0;
-            if (gsz >= GF_LANE_PER_QUERY) {
-                // ---- big group: one query per lane; the chunk's candidates go through shared memory and
-                // are read back as broadcasts.  No votes, no ranking: a lane appends to its own row.
-                // lanes outside the group carry a query parked far away: it never hits and never is borderline
-                const float qx = mine ? (use_b ? my4.y : my4.x) : 1e30f, qy = my4.z, qz = my4.w;
-                int *const orow = out + my_base;
-                for (int r = 0; r < nruns; ++r) {
-                    const int s = __shfl_sync(full, rs, r), e = __shfl_sync(full, re, r);
-                    const float sy = __shfl_sync(full, shy, r), sz = __shfl_sync(full, shz, r);
-                    for (int q0 = s; q0 < e; q0 += 32) {
-                        const int q = q0 + lane;
-                        const float4 c4 = q < e ? xf[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        __syncwarp();
-                        qf[lane] = make_float4(use_b ? c4.y : c4.x, c4.z + sy, c4.w + sz, 0.f);
-                        __syncwarp();
-                        const int nc = min(32, e - q0);
-                        const int cnt0 = cnt;
-                        float near = INFINITY;  // smallest |d2 - R| this lane meets in the chunk
+            // ---- big group: one query per lane; the chunk's candidates go through shared memory and
+            // are read back as broadcasts.  No votes, no ranking: a lane appends to its own row.
+            // lanes outside the group carry a query parked far away: it never hits and never is borderline
+            const float qx = mine ? (use_b ? my4.y : my4.x) : 1e30f, qy = my4.z, qz = my4.w;
+            int *const orow = out + my_base;
+            for (int r = 0; r < nruns; ++r) {
+                const int s = __shfl_sync(full, rs, r), e = __shfl_sync(full, re, r);
+                const float sy = __shfl_sync(full, shy, r), sz = __shfl_sync(full, shz, r);
+                float4 c4 = s + lane < e ? xf[s + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q0 = s; q0 < e; q0 += 32) {
+                    __syncwarp();
+                    qf[lane] = make_float4(use_b ? c4.y : c4.x, c4.z + sy, c4.w + sz, 0.f);
+                    __syncwarp();
+                    if (q0 + 32 + lane < e) c4 = xf[q0 + 32 + lane];  // next chunk's candidates, in flight during this one
+                    const int nc = min(32, e - q0);
+                    const int cnt0 = cnt;
+                    float near = INFINITY;  // smallest |d2 - R| this lane meets in the chunk
 #pragma unroll 4
+                    for (int tq = 0; tq < nc; ++tq) {
+                        const float4 cv = qf[tq];
+                        const float dx = qx - cv.x;
+                        float s2 = dx * dx;
+                        if (D > 1) { const float dy = qy - cv.y; s2 = fmaf(dy, dy, s2); }
+                        if (D > 2) { const float dz = qz - cv.z; s2 = fmaf(dz, dz, s2); }
+                        near = fminf(near, fabsf(s2 - fp.r2));
+                        if (s2 <= fp.t_lo) orow[cnt++] = q0 + tq;
+                    }
+                    if (near <= fp.band) {
+                        // rare: a pair of this lane is borderline.  Redo the lane's chunk, deciding such pairs
+                        // with the reference's own f64 test (the row must stay ascending, hence the redo).
+                        cnt = cnt0;
                         for (int tq = 0; tq < nc; ++tq) {
                             const float4 cv = qf[tq];
                             const float dx = qx - cv.x;
                             float s2 = dx * dx;
                             if (D > 1) { const float dy = qy - cv.y; s2 = fmaf(dy, dy, s2); }
                             if (D > 2) { const float dz = qz - cv.z; s2 = fmaf(dz, dz, s2); }
-                            near = fminf(near, fabsf(s2 - fp.r2));
-                            if (s2 <= fp.t_lo) orow[cnt++] = q0 + tq;
-                        }
-                        if (near <= fp.band) {
-                            // rare: a pair of this lane is borderline.  Redo the lane's chunk, deciding such pairs
-                            // with the reference's own f64 test (the row must stay ascending, hence the redo).
-                            cnt = cnt0;
-                            for (int tq = 0; tq < nc; ++tq) {
-                                const float4 cv = qf[tq];
-                                const float dx = qx - cv.x;
-                                float s2 = dx * dx;
-                                if (D > 1) { const float dy = qy - cv.y; s2 = fmaf(dy, dy, s2); }
-                                if (D > 2) { const float dz = qz - cv.z; s2 = fmaf(dz, dz, s2); }
-                                bool hit = s2 <= fp.t_lo;
-                                if (s2 > fp.t_lo && s2 <= fp.t_hi) {
-                                    hit = within<D, SQRT>(xs[p], D > 1 ? xs[n + p] : 0.0, D > 2 ? xs[2 * n + p] : 0.0, xs, n,
-                                                          q0 + tq, rc);
-                                    ++n_recheck;
-                                }
-                                if (hit) orow[cnt++] = q0 + tq;
-                            }
-                        }
-                    }
-                }
-                if (mine) deg[p] = cnt;
-                continue;
-            }
-            // ---- small group: lanes hold candidates, the warp loops over the group's queries
-            __syncwarp();
-            if (mine) qf[jme] = make_float4(use_b ? my4.y : my4.x, my4.z, my4.w, 0.f);
-            __syncwarp();
-            int ncc = 0;
-            auto flush = [&]() {
-                __syncwarp();
-                if (mine)
-                    for (int cc = 0; cc < ncc; ++cc) {
-                        unsigned w = words[cc][jme];
-                        const int q0 = chunk_q0[cc];
-#pragma unroll 1
-                        while (w) {
-                            const int b = __ffs(w) - 1;
-                            w &= w - 1;
-                            out[my_base + cnt++] = q0 + b;
-                        }
-                    }
-                __syncwarp();
-                ncc = 0;
-            };
-            for (int r = 0; r < nruns; ++r) {
-                const int s = __shfl_sync(full, rs, r), e = __shfl_sync(full, re, r);
-                const float sy = __shfl_sync(full, shy, r), sz = __shfl_sync(full, shz, r);
-                for (int q0 = s; q0 < e; q0 += 32) {
-                    const int q = q0 + lane;
-                    const bool inb = q < e;
-                    const float4 c4 = inb ? xf[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float ccx = use_b ? c4.y : c4.x;
-                    const float ccy = c4.z + sy, ccz = c4.w + sz;
-                    auto step = [&](int jq) {
-                        const float4 qv = qf[jq];
-                        const float dx = qv.x - ccx;
-                        float s2 = dx * dx;
-                        if (D > 1) { const float dy = qv.y - ccy; s2 = fmaf(dy, dy, s2); }
-                        if (D > 2) { const float dz = qv.z - ccz; s2 = fmaf(dz, dz, s2); }
-                        const bool maybe = inb && s2 <= fp.t_hi;
-                        unsigned w = __ballot_sync(full, maybe);
-                        const bool band = maybe && s2 > fp.t_lo;
-                        if (__any_sync(full, band)) {
-                            // decide the borderline pairs exactly as the reference does
-                            bool res = false;
-                            if (band) {
-                                const ll pq = p0 + a + jq;
-                                res = within<D, SQRT>(xs[pq], D > 1 ? xs[n + pq] : 0.0, D > 2 ? xs[2 * n + pq] : 0.0, xs, n,
-                                                      q, rc);
+                            bool hit = s2 <= fp.t_lo;
+                            if (s2 > fp.t_lo && s2 <= fp.t_hi) {
+                                hit = within<D, SQRT>(xs[p], D > 1 ? xs[n + p] : 0.0, D > 2 ? xs[2 * n + p] : 0.0, xs, n,
+                                                      q0 + tq, rc);
                                 ++n_recheck;
                             }
-                            const unsigned bm = __ballot_sync(full, band), rm = __ballot_sync(full, res);
-                            w = (w & ~bm) | rm;
+                            if (hit) orow[cnt++] = q0 + tq;
                         }
-                        if (lane == 0) words[ncc][jq] = w;
-                    };
-                    int jq = 0;
-                    for (; jq + 4 <= gsz; jq += 4) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) step(jq + u);
                     }
-                    for (; jq < gsz; ++jq) step(jq);
-                    if (lane == 0) chunk_q0[ncc] = q0;
-                    if (++ncc == GF_CHUNKS) flush();
                 }
             }
-            flush();
             if (mine) deg[p] = cnt;
         }
     }

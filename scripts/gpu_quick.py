@@ -27,8 +27,9 @@ r, c = 0.09, 20
 xd = torch.from_numpy(x).cuda()
 labd = torch.empty(n, dtype=torch.int64, device="cuda")
 ref = np.load("gpurun_out/c2_labels.npy") if os.path.exists("gpurun_out/c2_labels.npy") and n == 1000000 else None
+VAR = os.environ.get("SWEEP_VAR", "CNNB200_FILTER")
 for edge_pass in os.environ.get("FILTERS", "0,1").split(","):
-    os.environ["CNNB200_FILTER"] = edge_pass
+    os.environ[VAR] = edge_pass
     ctx = _lib.Context(0)
     ctx.set_timing(True)
     for it in range(4):

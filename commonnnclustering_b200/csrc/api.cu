@@ -90,6 +90,7 @@ extern "C" int cnnb200_ctx_create(int device, cnnb200_ctx **out) {
     CNN_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     if (const char *e = getenv("CNNB200_SAMPLES")) ctx->n_samples = atoi(e);
+    if (const char *e = getenv("CNNB200_FUSED_UNION")) ctx->fuse_union = atoi(e) != 0;
     if (const char *e = getenv("CNNB200_FILTER")) ctx->use_filter = atoi(e) != 0;
     if (const char *e = getenv("CNNB200_TENSOR_REORDER")) ctx->tensor_reorder = atoi(e) != 0;
     if (const char *e = getenv("CNNB200_TENSOR_PAIR_CAP")) ctx->tensor_band_cap = atoll(e);  // initial pair-list capacity (tests)

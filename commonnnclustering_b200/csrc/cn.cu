@@ -134,8 +134,8 @@ __global__ void comp_init_kernel(const ll *__restrict__ row_ptr, const int *__re
 // and linked afterwards by comp_union_kernel with one thread per edge -- no union-find traffic here.
 __global__ void __launch_bounds__(256)
 comp_sample_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll row_begin, ll row_end,
-                   int cutoff, int n_samples, const int *__restrict__ parent, int *__restrict__ edge_out,
-                   int *__restrict__ above, unsigned long long *stats) {
+                   int cutoff, int n_samples, int *parent, int *__restrict__ edge_out,
+                   int *__restrict__ above, unsigned long long *stats, int fuse_union) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
@@ -148,7 +148,12 @@ comp_sample_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_i
         const ll rb = valid ? row_ptr[i] : 0;
         const int m = valid ? (int)(row_ptr[i + 1] - rb) : 0;
         int first_above = -1;
-        for (int smp = 0; smp < n_samples; ++smp) {
+        int jacc[MAX_SAMPLES];
+#pragma unroll
+        for (int smp = 0; smp < MAX_SAMPLES; ++smp) jacc[smp] = -1;
+#pragma unroll
+        for (int smp = 0; smp < MAX_SAMPLES; ++smp) {
+            if (smp >= n_samples) break;
             int j = -1;
             if (core_i && m > 0) {
                 if (smp == 0) {
@@ -171,7 +176,19 @@ comp_sample_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_i
             const int acc = ok ? lane_check(col_idx + rb, m, col_idx + jb, mj, cutoff) : 0;
             n_checks += __popc(__ballot_sync(full, ok));
             n_acc += __popc(__ballot_sync(full, acc != 0));
-            if (valid) edge_out[(i - row_begin) * n_samples + smp] = acc ? j : -1;
+            jacc[smp] = acc ? j : -1;
+            if (!fuse_union && valid) edge_out[(i - row_begin) * n_samples + smp] = jacc[smp];
+        }
+        if (fuse_union) {
+            // link right here (see comp_union_kernel for the run-head trick): other warps keep the SM busy
+            // while this one waits for its atomics
+            const unsigned linked = __ballot_sync(full, jacc[0] == (int)i + 1 && lane < 31);
+            const unsigned below = ~linked & ((1u << lane) - 1u);
+            const int head = below ? 32 - __clz(below) : 0;
+            const int hi = (int)(i - lane + head);
+#pragma unroll
+            for (int smp = 0; smp < MAX_SAMPLES; ++smp)
+                if (jacc[smp] >= 0) uf_union(parent, hi, jacc[smp]);
         }
     }
     if (lane == 0) {
@@ -761,9 +778,10 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         int sblocks = (int)((rows + 255) / 256);
         if (sblocks > ctx->sm_count * 32) sblocks = ctx->sm_count * 32;
         comp_sample_kernel<<<sblocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, cutoff, ns, parent,
-                                                    ctx->b_edges.as<int>(), above, stats);
-        comp_union_kernel<<<cnn_blocks(rows, 256), 256, 0, st>>>(ctx->b_edges.as<int>(), row_begin, rows, ns, parent);
-        CNN_LAUNCHED(ctx, 2);
+                                                    ctx->b_edges.as<int>(), above, stats, ctx->fuse_union ? 1 : 0);
+        if (!ctx->fuse_union)
+            comp_union_kernel<<<cnn_blocks(rows, 256), 256, 0, st>>>(ctx->b_edges.as<int>(), row_begin, rows, ns, parent);
+        CNN_LAUNCHED(ctx, ctx->fuse_union ? 1 : 2);
     } else {
         comp_above_kernel<<<cnn_blocks(rows, 256), 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, above);
         CNN_LAUNCHED(ctx, 1);

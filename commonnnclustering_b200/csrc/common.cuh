@@ -86,7 +86,7 @@ struct cnnb200_ctx {
     cnnb200_free_fn free_ = nullptr;
     void *alloc_user = nullptr;
     int sm_count = 148;
-    ll single_pass_limit = 8ll << 30;  // bytes of gapped scratch the single-pass search may use (0 = two-pass)
+    ll single_pass_limit = 32ll << 30;  // bytes of gapped scratch the single-pass search may use (0 = two-pass)
     bool fuse_union = true;  // sampling pass links its accepted edges itself (CNNB200_FUSED_UNION=0: separate kernel)
     int n_samples = 2;  // edges per core row tried by the sampling pass (tunable: CNNB200_SAMPLES)
 

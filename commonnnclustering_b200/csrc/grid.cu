@@ -234,7 +234,9 @@ struct FilterParams {
     float r2, band;    // |d2 - r2| <= band for every d2 in (t_lo, t_hi] (computed in fp32, rounded outwards)
 };
 
-template <int D, bool SQRT>
+// MODE as for grid_rows_kernel: 0 = count pass (deg[] only), 1 = fill pass (rows at goff[] = row_ptr[]),
+// 2 = single pass into gapped rows (hits at goff[], deg[] from the same pass)
+template <int D, bool SQRT, int MODE>
 __global__ void __launch_bounds__(GF_WARPS * 32, 4)
 grid_rows_f32_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, ll n,
                      const int *__restrict__ cell_sorted, const int *__restrict__ cell_start, GridDesc g, double rc,
@@ -253,7 +255,7 @@ grid_rows_f32_kernel(const double *__restrict__ xs, const float4 *__restrict__ x
         const int cid = pvalid ? cell_sorted[p] : -1;
         const int my_row = pvalid ? cid / g.dims[0] : -1, my_cx = pvalid ? cid - my_row * g.dims[0] : 0;
         const float4 my4 = pvalid ? xf[p] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const ll my_base = pvalid ? goff[p] : 0;
+        const ll my_base = (MODE != 0 && pvalid) ? goff[p] : 0;
         unsigned todo = __ballot_sync(full, pvalid);
         while (todo) {
             // next group: the run of lanes, starting at the first open one, whose points lie in the same x-row
@@ -314,7 +316,10 @@ grid_rows_f32_kernel(const double *__restrict__ xs, const float4 *__restrict__ x
                         if (D > 1) { const float dy = qy - cv.y; s2 = fmaf(dy, dy, s2); }
                         if (D > 2) { const float dz = qz - cv.z; s2 = fmaf(dz, dz, s2); }
                         near = fminf(near, fabsf(s2 - fp.r2));
-                        if (s2 <= fp.t_lo) orow[cnt++] = q0 + tq;
+                        if (s2 <= fp.t_lo) {
+                            if (MODE != 0) orow[cnt] = q0 + tq;
+                            ++cnt;
+                        }
                     }
                     if (near <= fp.band) {
                         // rare: a pair of this lane is borderline.  Redo the lane's chunk, deciding such pairs
@@ -332,12 +337,15 @@ grid_rows_f32_kernel(const double *__restrict__ xs, const float4 *__restrict__ x
                                                       q0 + tq, rc);
                                 ++n_recheck;
                             }
-                            if (hit) orow[cnt++] = q0 + tq;
+                            if (hit) {
+                                if (MODE != 0) orow[cnt] = q0 + tq;
+                                ++cnt;
+                            }
                         }
                     }
                 }
             }
-            if (mine) deg[p] = cnt;
+            if (MODE != 1 && mine) deg[p] = cnt;
         }
     }
     n_recheck = __reduce_add_sync(full, (unsigned)n_recheck);
@@ -458,31 +466,34 @@ static bool filter_params(const cnnb200_ctx *ctx, FilterParams *fp) {
 }
 
 template <int D, bool SQRT>
-static int launch_rows_f32(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg, const ll *offsets, int *out) {
+static int launch_rows_f32(cnnb200_ctx *ctx, ll pb, ll pe, int mode, FilterParams fp, int *deg, const ll *offsets, int *out) {
     int blocks = (int)((pe - pb + GF_WARPS * 32 - 1) / (GF_WARPS * 32));
     int cap = ctx->sm_count * 48;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     unsigned long long *recheck = (unsigned long long *)(ctx->b_tmp2.as<char>() + 40);
     CNN_CUDA(cudaMemsetAsync(recheck, 0, sizeof(unsigned long long), ctx->stream));
-    grid_rows_f32_kernel<D, SQRT><<<blocks, GF_WARPS * 32, 0, ctx->stream>>>(
-        ctx->b_xs.as<double>(), ctx->b_xf.as<float4>(), ctx->grid_n, ctx->b_cell_id_sorted.as<int>(),
-        ctx->b_cell_start.as<int>(), ctx->grid, ctx->grid_rc, fp, deg, offsets, out, pb, pe, recheck);
+#define GF_ARGS ctx->b_xs.as<double>(), ctx->b_xf.as<float4>(), ctx->grid_n, ctx->b_cell_id_sorted.as<int>(),      \
+                ctx->b_cell_start.as<int>(), ctx->grid, ctx->grid_rc, fp, deg, offsets, out, pb, pe, recheck
+    if (mode == 0) grid_rows_f32_kernel<D, SQRT, 0><<<blocks, GF_WARPS * 32, 0, ctx->stream>>>(GF_ARGS);
+    else if (mode == 1) grid_rows_f32_kernel<D, SQRT, 1><<<blocks, GF_WARPS * 32, 0, ctx->stream>>>(GF_ARGS);
+    else grid_rows_f32_kernel<D, SQRT, 2><<<blocks, GF_WARPS * 32, 0, ctx->stream>>>(GF_ARGS);
+#undef GF_ARGS
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     ctx->grid_recheck_pending = true;
     return CNNB200_OK;
 }
 
-static int launch_rows_f32_any(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg, const ll *offsets, int *out) {
+static int launch_rows_f32_any(cnnb200_ctx *ctx, ll pb, ll pe, int mode, FilterParams fp, int *deg, const ll *offsets, int *out) {
     bool sq = ctx->grid_metric == CNNB200_METRIC_EUCLIDEAN;
     switch (ctx->grid.d * 2 + (sq ? 1 : 0)) {
-        case 2: return launch_rows_f32<1, false>(ctx, pb, pe, fp, deg, offsets, out);
-        case 3: return launch_rows_f32<1, true>(ctx, pb, pe, fp, deg, offsets, out);
-        case 4: return launch_rows_f32<2, false>(ctx, pb, pe, fp, deg, offsets, out);
-        case 5: return launch_rows_f32<2, true>(ctx, pb, pe, fp, deg, offsets, out);
-        case 6: return launch_rows_f32<3, false>(ctx, pb, pe, fp, deg, offsets, out);
-        default: return launch_rows_f32<3, true>(ctx, pb, pe, fp, deg, offsets, out);
+        case 2: return launch_rows_f32<1, false>(ctx, pb, pe, mode, fp, deg, offsets, out);
+        case 3: return launch_rows_f32<1, true>(ctx, pb, pe, mode, fp, deg, offsets, out);
+        case 4: return launch_rows_f32<2, false>(ctx, pb, pe, mode, fp, deg, offsets, out);
+        case 5: return launch_rows_f32<2, true>(ctx, pb, pe, mode, fp, deg, offsets, out);
+        case 6: return launch_rows_f32<3, false>(ctx, pb, pe, mode, fp, deg, offsets, out);
+        default: return launch_rows_f32<3, true>(ctx, pb, pe, mode, fp, deg, offsets, out);
     }
 }
 
@@ -635,11 +646,16 @@ int cnn_grid_rows(cnnb200_ctx *ctx, ll pb, ll pe, int *deg) {
         FilterParams fp;
         CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
         if (ctx->use_filter && filter_params(ctx, &fp))
-            CNN_TRY(launch_rows_f32_any(ctx, pb, pe, fp, deg, goff, ctx->b_tmp0.as<int>() - g0));
+            CNN_TRY(launch_rows_f32_any(ctx, pb, pe, 2, fp, deg, goff, ctx->b_tmp0.as<int>() - g0));
         else
             CNN_TRY(launch_rows_any(ctx, pb, pe, 2, deg, goff, ctx->b_tmp0.as<int>() - g0));
     } else {
-        CNN_TRY(launch_rows_any(ctx, pb, pe, 0, deg, nullptr, nullptr));
+        FilterParams fp;
+        CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
+        if (ctx->use_filter && filter_params(ctx, &fp))
+            CNN_TRY(launch_rows_f32_any(ctx, pb, pe, 0, fp, deg, nullptr, nullptr));
+        else
+            CNN_TRY(launch_rows_any(ctx, pb, pe, 0, deg, nullptr, nullptr));
     }
     return CNNB200_OK;
 }
@@ -658,7 +674,11 @@ int cnn_grid_fill(cnnb200_ctx *ctx, ll pb, ll pe, const ll *row_ptr, int *col_id
         CNN_LAUNCHED(ctx, 1);
         CNN_KERNEL_CHECK();
     } else {
-        CNN_TRY(launch_rows_any(ctx, pb, pe, 1, nullptr, row_ptr, col_idx));
+        FilterParams fp;
+        if (ctx->use_filter && filter_params(ctx, &fp))
+            CNN_TRY(launch_rows_f32_any(ctx, pb, pe, 1, fp, nullptr, row_ptr, col_idx));
+        else
+            CNN_TRY(launch_rows_any(ctx, pb, pe, 1, nullptr, row_ptr, col_idx));
     }
     return CNNB200_OK;
 }

@@ -1,4 +1,5 @@
-"""Quick GPU check: parity on a few sets + C2 stage timings (for kernel iteration)."""
+"""Quick GPU check: parity on a few sets + C2 stage timings (for kernel iteration).
+SWEEP_VAR=<CNNB200_* environment variable> VALUES=a,b,c runs the C2 fit once per value (fresh context each)."""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -28,15 +29,15 @@ xd = torch.from_numpy(x).cuda()
 labd = torch.empty(n, dtype=torch.int64, device="cuda")
 ref = np.load("gpurun_out/c2_labels.npy") if os.path.exists("gpurun_out/c2_labels.npy") and n == 1000000 else None
 VAR = os.environ.get("SWEEP_VAR", "CNNB200_FILTER")
-for edge_pass in os.environ.get("FILTERS", "0,1").split(","):
-    os.environ[VAR] = edge_pass
+for value in os.environ.get("VALUES", "1").split(","):
+    os.environ[VAR] = value
     ctx = _lib.Context(0)
     ctx.set_timing(True)
     for it in range(4):
         ctx.fit_points(xd, r * r, c + 1, c + 2, labd, member_cutoff=10)
         t, launches = ctx.timings()
         if it:
-            print("filter", edge_pass, {k: round(v[0], 3) for k, v in t.items() if v[1]}, "total", round(sum(v[0] for v in t.values()), 3), ctx.stats(), flush=True)
+            print(VAR, value, {k: round(v[0], 3) for k, v in t.items() if v[1]}, "total", round(sum(v[0] for v in t.values()), 3), ctx.stats(), flush=True)
     if ref is None:
         ref = labd.cpu().numpy()
     else:

@@ -188,6 +188,16 @@ def test_filter_kernel_equals_f64_kernel_on_c2_sample(ctx):
     b = ctx2.neighbours_export()
     np.testing.assert_array_equal(a[0], b[0])
     np.testing.assert_array_equal(a[1], b[1])
+    # two-pass form of the filter kernel (count, scan, fill): what very large inputs use
+    os.environ["CNNB200_SINGLE_PASS_MB"] = "0"
+    try:
+        ctx3 = _lib.Context(0)
+    finally:
+        del os.environ["CNNB200_SINGLE_PASS_MB"]
+    ctx3.neighbours_from_points(x, 0.12 ** 2)
+    c = ctx3.neighbours_export()
+    np.testing.assert_array_equal(a[0], c[0])
+    np.testing.assert_array_equal(a[1], c[1])
 
 
 def test_neighbour_search_high_dim_and_odd_sizes(ctx):

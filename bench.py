@@ -202,9 +202,9 @@ def stage_rooflines(timings, steps, n, d, nnz, stats, peak, count_mode=None):
               "coords in (f64 for the exact recheck + float4 cell-local copy) + 4*N degrees out + 4*nnz hits out (gapped rows)",
               "issue slots: ~450 distance tests per point; the compulsory bytes are small (see DESIGN.md 4)"),
         entry("search_fill", ["compact_rows_kernel"], 8 * nnz + 16 * (n + 1), "4*nnz in + 4*nnz out + 16*(N+1) offsets", "HBM"),
-        entry("comp_sample", ["comp_sample_kernel", "comp_union_kernel"], 8 * (n + 1) + 4 * n + 2 * 4 * n + 4 * n,
-              "row_ptr + parents + the sampled edge slots + first-above positions; rows read by the executed CN checks "
-              "are not counted", "memory latency (dependent row look-ups, union-find chains)"),
+        entry("comp_sample", ["comp_sample_kernel"], 8 * (n + 1) + 4 * n + 4 * n,
+              "row_ptr + parents + first-above positions (the accepted edges are linked in place); rows read by the "
+              "executed CN checks are not counted", "memory latency (dependent row look-ups, union-find chains)"),
         entry("comp_edges", ["comp_scan_kernel", "comp_worklist_kernel"],
               2 * nnz + 8 * (n + 1) + 8 * n + 4 * cand + 16 * unsettled,
               "upper half of every core row (about 2*nnz bytes) + row_ptr + parents + first-above positions + one 4-byte "

@@ -56,6 +56,9 @@ SIGNATURES = {
     "cnnb200_sort_by_size": [_P, _P, C.c_int, _I64, _I64, _I64, _P, _I64],
     "cnnb200_fit_points": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int, C.c_int, _I64, _I64, _I64,
                            C.c_int, _I64, _I64, _P, C.POINTER(_I64)],
+    "cnnb200_label_summary": [_P, _P],
+    "cnnb200_host_register": [_P, C.c_size_t],
+    "cnnb200_host_unregister": [_P],
     "cnnb200_stats": [_P, _P, _I64],
     "cnnb200_ctx_set_timing": [_P, C.c_int],
     "cnnb200_timings": [_P, _P, _P, _I64, C.POINTER(_I64), C.c_int],
@@ -369,6 +372,12 @@ class Context:
             -1 if max_clusters is None else int(max_clusters), lp, C.byref(nc)))
         return nc.value
 
+    def label_summary(self):
+        """(clusters kept, members of the largest one, noise points) of the last size-sorted result."""
+        out = np.zeros(3, dtype=np.int64)
+        check(self._lib.cnnb200_label_summary(self._h, out.ctypes.data))
+        return int(out[0]), int(out[1]), int(out[2])
+
     def set_timing(self, enabled: bool):
         check(self._lib.cnnb200_ctx_set_timing(self._h, int(bool(enabled))))
 
@@ -387,6 +396,19 @@ class Context:
         check(self._lib.cnnb200_stats(self._h, s.ctypes.data, 8))
         return {"candidate_edges": int(s[0]), "checks": int(s[1]), "accepted": int(s[2]),
                 "skipped": int(s[3]), "distance_evals": int(s[4]), "rechecks": int(s[5])}
+
+
+def host_register(array) -> bool:
+    """Page-locks a NumPy array in place; False when the driver refuses (then copies stay pageable)."""
+    try:
+        check(load().cnnb200_host_register(array.ctypes.data, array.nbytes))
+        return True
+    except CnnB200Error:
+        return False
+
+
+def host_unregister(ptr: int):
+    load().cnnb200_host_unregister(ptr)
 
 
 _default_ctx = {}

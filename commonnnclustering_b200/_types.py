@@ -199,6 +199,19 @@ class InputDataComponents(InputData):
     def device_or_host_array(self):
         return self._data
 
+    def pin(self) -> bool:
+        """Page-locks the host array in place (once) so that every fit on these coordinates copies them at PCIe
+        speed; nothing is copied or cached, later changes to the array are seen as before.  Released with the object."""
+        if not isinstance(self._data, np.ndarray) or self._data.nbytes == 0:
+            return False
+        if getattr(self, "_pinned", None) is None:
+            import weakref
+
+            self._pinned = _lib.host_register(self._data)
+            if self._pinned:
+                weakref.finalize(self, _lib.host_unregister, self._data.ctypes.data)
+        return self._pinned
+
     def get_component(self, point: int, dimension: int) -> float:
         return float(self._data[point, dimension])
 

@@ -11,6 +11,19 @@ from ._types import InputData, InputDataComponents, Labels
 from .report import Record, Summary
 
 
+def _label_buffer(n: int, pinned: bool):
+    """Zeroed int64 labels; page-locked (torch's caching host allocator) when the fit writes them with one D2H copy."""
+    if pinned and n > 0:
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                return torch.zeros(n, dtype=torch.int64, pin_memory=True).numpy()
+        except Exception:
+            pass
+    return np.zeros(n, order="C", dtype=np.int64)
+
+
 class Bundle:
     """Input data + labels + summary of one clustering and its place in a hierarchy (reference
     ``_bundle.pyx:20-53``): ``children`` maps a cluster label to the Bundle of that cluster's points,
@@ -212,8 +225,12 @@ class Clustering:
         cnn_cutoff -= cnn_offset
         assert cnn_cutoff >= 0
         n = bundle._input_data.n_points
+        # a fresh fit on coordinates with size sorting can keep the labels on the device
+        # between FitterExtBFS.fit and Labels.sort_by_size: one C-ABI call, one D2H copy
+        may_fuse = (sort_by_size and isinstance(self._fitter, FitterB200Fused)
+                    and isinstance(bundle._input_data, InputDataComponents))
         if (bundle._labels is None) or purge or (not bundle._labels.meta.get("frozen", False)):
-            bundle._labels = Labels(np.zeros(n, order="C", dtype=np.int64))
+            bundle._labels = Labels(_label_buffer(n, pinned=may_fuse))
             old_label_set = set()
             current_start = 1
             fresh = True
@@ -223,10 +240,9 @@ class Clustering:
             fresh = False
         cluster_params = self._fitter.make_parameters(radius_cutoff, cnn_cutoff, current_start)
 
-        # a fresh fit on coordinates with size sorting can keep the labels on the device
-        # between FitterExtBFS.fit and Labels.sort_by_size: one C-ABI call, one D2H copy
-        fused = (fresh and sort_by_size and isinstance(self._fitter, FitterB200Fused)
-                 and isinstance(bundle._input_data, InputDataComponents))
+        fused = fresh and may_fuse
+        if fused:
+            bundle._input_data.pin()
         t0 = time.perf_counter()
         if fused:
             n_found = self._fitter.fit_sorted(bundle._input_data, bundle._labels, cluster_params,
@@ -235,11 +251,12 @@ class Clustering:
             self._fitter.fit(bundle._input_data, bundle._labels, cluster_params)
         execution_time = time.perf_counter() - t0 if record_time else None
 
+        if fused:  # the size sort on the device already knows what the record and the parameter table need
+            n_kept, n_largest, n_noise = self._fitter.ctx.label_summary()
+            del n_found
         if info:
             if fused:
-                n_kept = int(bundle._labels.labels.max()) if n else 0
                 params = {k: (radius_cutoff, cnn_cutoff) for k in range(1, n_kept + 1)}
-                del n_found
             else:
                 new_label_set = bundle._labels.to_set()
                 params = {k: (radius_cutoff, cnn_cutoff) for k in new_label_set - old_label_set if k != 0}
@@ -249,13 +266,17 @@ class Clustering:
         if sort_by_size and not fused:
             bundle._labels.sort_by_size(member_cutoff, max_clusters, ctx=getattr(self._fitter, "ctx", None))
         if record:
-            lab = bundle._labels.labels
-            counts = np.bincount(lab) if n else np.zeros(1, dtype=np.int64)
-            n_noise = int(counts[0]) if counts.size else 0
-            rest = counts[1:]
-            rec = Record(n, radius_cutoff, cnn_cutoff, member_cutoff, max_clusters,
-                         int(np.count_nonzero(rest)), (int(rest.max()) if rest.size else 0) / n,
-                         n_noise / n, execution_time)
+            if fused:
+                rec = Record(n, radius_cutoff, cnn_cutoff, member_cutoff, max_clusters, n_kept, n_largest / n,
+                             n_noise / n, execution_time)
+            else:
+                lab = bundle._labels.labels
+                counts = np.bincount(lab) if n else np.zeros(1, dtype=np.int64)
+                n_noise = int(counts[0]) if counts.size else 0
+                rest = counts[1:]
+                rec = Record(n, radius_cutoff, cnn_cutoff, member_cutoff, max_clusters,
+                             int(np.count_nonzero(rest)), (int(rest.max()) if rest.size else 0) / n,
+                             n_noise / n, execution_time)
             if v:
                 print(rec)
             bundle._summary.append(rec)

@@ -100,7 +100,7 @@ extern "C" int cnnb200_ctx_create(int device, cnnb200_ctx **out) {
 }
 
 #define FOR_EACH_BUF(c, F)                                                                          \
-    F(c->b_row_ptr) F(c->b_col_idx) F(c->b_perm) F(c->b_deg) F(c->b_x) F(c->b_bounds) F(c->b_xs) F(c->b_xf) F(c->b_xperm) F(c->b_o_x) F(c->b_o_deg) F(c->b_o_row_ptr) F(c->b_o_col_idx) F(c->b_o_labels) F(c->b_cell_id)   \
+    F(c->b_row_ptr) F(c->b_col_idx) F(c->b_perm) F(c->b_deg) F(c->b_x) F(c->b_lab_summary) F(c->b_bounds) F(c->b_xs) F(c->b_xf) F(c->b_xperm) F(c->b_o_x) F(c->b_o_deg) F(c->b_o_row_ptr) F(c->b_o_col_idx) F(c->b_o_labels) F(c->b_cell_id)   \
     F(c->b_cell_id_sorted) F(c->b_idx) F(c->b_cell_start) F(c->b_bbox) F(c->b_cub) F(c->b_tmp0)     \
     F(c->b_tmp1) F(c->b_tmp2) F(c->b_parent) F(c->b_core) F(c->b_above) F(c->b_edges) F(c->b_worklist) F(c->b_cell_count) F(c->b_minorig) F(c->b_flags)             \
     F(c->b_rank) F(c->b_labels) F(c->b_consider) F(c->b_stats) F(c->b_lab_count) F(c->b_lab_first)  \
@@ -166,6 +166,21 @@ extern "C" int cnnb200_ctx_set_periodic_bounds(cnnb200_ctx *ctx, const double *b
     CNN_CUDA(cudaMemcpyAsync(ctx->b_bounds.p, bounds, sizeof(double) * (size_t)d, cudaMemcpyHostToDevice, ctx->stream));
     CNN_CUDA(cudaStreamSynchronize(ctx->stream));  // the host array may go away
     ctx->n_bounds = d;
+    return CNNB200_OK;
+}
+
+// Page-locks a caller array in place (cudaHostRegister) so that repeated fits on the same coordinates copy at PCIe
+// speed instead of through the driver's pageable staging; nothing is copied or cached.
+extern "C" int cnnb200_host_register(void *ptr, size_t bytes) {
+    if (!ptr || !bytes) CNN_FAIL(CNNB200_E_INVALID, "host_register: bad argument");
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return CNNB200_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); CNN_FAIL(CNNB200_E_CUDA, "host_register: %s", cudaGetErrorString(e)); }
+    return CNNB200_OK;
+}
+extern "C" int cnnb200_host_unregister(void *ptr) {
+    if (!ptr) return CNNB200_OK;
+    if (cudaHostUnregister(ptr) != cudaSuccess) cudaGetLastError();
     return CNNB200_OK;
 }
 

@@ -147,6 +147,9 @@ struct cnnb200_ctx {
     ll stats[ST_N] = {0};
     Buf b_bounds;     // f64 [n_bounds]: periods of the periodic metric
     ll n_bounds = 0;
+    Buf b_lab_summary;
+    bool have_lab_summary = false;
+    ll lab_summary_n = 0;
     ll known_max_label = -1;
     ll tensor_band_cap = 0;  // capacity (pairs) the borderline list of the tensor-core search needed last time  // set by cnnb200_fit_points for the sort_by_size call that follows a fresh fit
 

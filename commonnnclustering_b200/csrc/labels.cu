@@ -176,6 +176,32 @@ __global__ void label_survivor_kernel(const unsigned long long *__restrict__ key
     surv[t] = ok ? 1 : 0;
 }
 
+// what Clustering.fit records about the relabelled result (cluster.pyx:366-390): clusters kept, members of the
+// largest one, noise points -- from the sorted sizes, so that the host needs no pass over the labels
+__global__ void label_summary_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ surv, ll m, ll n,
+                                     int kb, ll *out) {
+    __shared__ ll s_sum[256], s_max[256], s_cnt[256];
+    ll sum = 0, mx = 0, cnt = 0;
+    for (ll t = threadIdx.x; t < m; t += blockDim.x)
+        if (surv[t]) {
+            const ll size = n - (ll)(keys[t] >> kb);
+            sum += size;
+            mx = size > mx ? size : mx;
+            ++cnt;
+        }
+    s_sum[threadIdx.x] = sum; s_max[threadIdx.x] = mx; s_cnt[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+            s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o];
+            s_max[threadIdx.x] = s_max[threadIdx.x] > s_max[threadIdx.x + o] ? s_max[threadIdx.x] : s_max[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = s_cnt[0]; out[1] = s_max[0]; out[2] = n - s_sum[0]; }
+}
+
 __global__ void label_map_kernel(const int *__restrict__ vals, const int *__restrict__ surv,
                                  const int *__restrict__ surv_rank, ll m, ll *map) {
     ll t = blockIdx.x * (ll)blockDim.x + threadIdx.x;
@@ -206,6 +232,8 @@ extern "C" int cnnb200_sort_by_size(cnnb200_ctx *ctx, int64_t *labels, int loc, 
         Span sh(ctx, T_H2D);
         CNN_CUDA(cudaMemcpyAsync(d_labels, labels, sizeof(ll) * (size_t)n, cudaMemcpyHostToDevice, st));
     }
+    ctx->have_lab_summary = false;
+    ctx->lab_summary_n = n;
     std::unique_ptr<Span> sp(new Span(ctx, T_SORT_BY_SIZE));
     // largest label -> table size (known to the caller after a fresh fit: ctx->known_max_label)
     CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
@@ -267,7 +295,10 @@ extern "C" int cnnb200_sort_by_size(cnnb200_ctx *ctx, int64_t *labels, int loc, 
         CNN_CUDA(cudaMemsetAsync(map, 0, sizeof(ll), st));
         label_map_kernel<<<cnn_blocks(m, 256), 256, 0, st>>>(vals2, ctx->b_flags.as<int>(), ctx->b_rank.as<int>(), m, map);
         label_apply_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_labels, n, map, max_label);
-        CNN_LAUNCHED(ctx, 6);
+        CNN_TRY(cnn_ensure(ctx, ctx->b_lab_summary, sizeof(ll) * 4));
+        label_summary_kernel<<<1, 256, 0, st>>>(keys2, ctx->b_flags.as<int>(), m, n, kb, ctx->b_lab_summary.as<ll>());
+        ctx->have_lab_summary = true;
+        CNN_LAUNCHED(ctx, 7);
         CNN_KERNEL_CHECK();
         if (map_out && map_len > 0) {
             ll cnt = map_len < L ? map_len : L;
@@ -289,5 +320,21 @@ extern "C" int cnnb200_sort_by_size(cnnb200_ctx *ctx, int64_t *labels, int loc, 
         CNN_CUDA(cudaStreamSynchronize(st));
         if (*hf) CNN_FAIL(CNNB200_E_INVALID, "sort_by_size: negative labels");
     }
+    return CNNB200_OK;
+}
+
+// (clusters kept, members of the largest cluster, noise points) of the last cnnb200_sort_by_size / cnnb200_fit_points
+extern "C" int cnnb200_label_summary(cnnb200_ctx *ctx, int64_t *out3) {
+    if (!ctx || !out3) CNN_FAIL(CNNB200_E_INVALID, "label_summary: NULL argument");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->have_lab_summary) {  // only noise (or nothing relabelled yet)
+        out3[0] = 0; out3[1] = 0; out3[2] = ctx->lab_summary_n;
+        return CNNB200_OK;
+    }
+    ll *h;
+    CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
+    CNN_CUDA(cudaMemcpyAsync(h, ctx->b_lab_summary.p, sizeof(ll) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    out3[0] = h[0]; out3[1] = h[1]; out3[2] = h[2];
     return CNNB200_OK;
 }

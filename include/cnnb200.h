@@ -251,6 +251,15 @@ int cnnb200_fit_points(cnnb200_ctx *ctx, const double *x, int loc, int64_t n, in
                        int64_t member_cutoff, int64_t max_clusters, int64_t *labels,
                        int64_t *n_clusters_out);
 
+/* (clusters kept, members of the largest cluster, noise points) after the last cnnb200_sort_by_size /
+ * cnnb200_fit_points with size sorting: what Clustering.fit stores in its Record (cluster.pyx:366-390), HOST int64 [3]. */
+int cnnb200_label_summary(cnnb200_ctx *ctx, int64_t *out3);
+
+/* Page-lock / release a caller array in place (no copy is kept): repeated fits on the same coordinates then
+ * transfer at PCIe speed. */
+int cnnb200_host_register(void *ptr, size_t bytes);
+int cnnb200_host_unregister(void *ptr);
+
 /* Counters of the last fit / search, for measurement (all optional, HOST):
  *   stats[0] candidate edges (i<j, both core)      stats[1] CN checks executed
  *   stats[2] edges accepted by a check             stats[3] edges skipped (already connected)

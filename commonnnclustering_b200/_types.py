@@ -156,6 +156,18 @@ class Labels:
             bundle._children = processed
 
 
+def _pin_arrays(owner, arrays) -> bool:
+    """cudaHostRegister on each (non-empty) array; released when `owner` is collected."""
+    import weakref
+
+    ok = False
+    for a in arrays:
+        if isinstance(a, np.ndarray) and a.nbytes and _lib.host_register(a):
+            weakref.finalize(owner, _lib.host_unregister, a.ctypes.data)
+            ok = True
+    return ok
+
+
 # ---- InputData ------------------------------------------------------------------------------------
 class InputData:
     """Role marker (reference ABC ``InputData``, ``_types.pyx:305-436``)."""
@@ -269,6 +281,12 @@ class InputDataNeighbourhoods(InputData):
     def get_neighbour(self, point: int, member: int) -> int:
         return int(self._data[point, member])
 
+    def pin(self) -> bool:
+        """Page-locks the padded matrix and the counts in place, once (see InputDataComponents.pin)."""
+        if getattr(self, "_pinned", None) is None:
+            self._pinned = _pin_arrays(self, [self._data, self._n_neighbours])
+        return self._pinned
+
     def to_csr(self):
         """(row_ptr int64 [n+1], col_idx int64 [nnz]) of the valid entries."""
         row_ptr = np.zeros(self.n_points + 1, dtype=P_AINDEX)
@@ -291,6 +309,12 @@ class InputDataNeighbourhoodsCSR(InputData):
         if meta is not None:
             _meta.update(meta)
         self.meta = _meta
+
+    def pin(self) -> bool:
+        """Page-locks host CSR arrays in place, once (see InputDataComponents.pin); device tensors need nothing."""
+        if getattr(self, "_pinned", None) is None:
+            self._pinned = _pin_arrays(self, [a for a in (self.row_ptr, self.col_idx) if isinstance(a, np.ndarray)])
+        return self._pinned
 
     def to_csr(self):
         rp, ci = self.row_ptr, self.col_idx
@@ -475,6 +499,7 @@ class NeighboursGetterLookup(NeighboursGetter):
 
     def get_all(self, input_data, cluster_params=None, ctx=None) -> Neighbourhoods:
         ctx = ctx or _lib.default_context()
+        input_data.pin()
         if isinstance(input_data, InputDataNeighbourhoodsCSR):
             ctx.neighbours_from_csr(input_data.row_ptr, input_data.col_idx,
                                     borrow=hasattr(input_data.col_idx, "is_cuda"))

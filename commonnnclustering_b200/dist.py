@@ -82,6 +82,7 @@ class ShardedFit:
         self.device = torch.device("cuda", ctx.device)
         ctx.set_stream(torch.cuda.current_stream(self.device))  # collectives are ordered against this stream
         self.last = {}
+        self._registered = {}
 
     # -- neighbourhoods from coordinates, rows sharded ---------------------------------------------
     def neighbours_from_points(self, x, radius_cutoff, metric="euclidean_r", exchange=False):
@@ -128,6 +129,12 @@ class ShardedFit:
         ctx, G = self.ctx, self.world
         n = row_ptr_host.shape[0] - 1
         nnz = int(row_ptr_host[-1])
+        from . import _lib
+
+        for a in (row_ptr_host, col_idx_host):   # page-lock in place, once per array: uploads at PCIe speed
+            key = (a.ctypes.data, a.nbytes)
+            if key not in self._registered:
+                self._registered[key] = _lib.host_register(a)
         # balance by entries
         targets = (np.arange(G + 1, dtype=np.float64) * nnz / G).astype(np.int64)
         bounds = np.searchsorted(row_ptr_host, targets, side="left").astype(np.int64)

@@ -49,12 +49,18 @@ if world == 1:
         times.append(time.perf_counter() - t0)
     lab = lab_d.cpu().numpy()
     out.update(device_resident_fit_ms=1e3 * min(times[1:]), points_per_s=n / min(times[1:]), stats=ctx.stats())
-    # host-resident input: H2D of the CSR inside the timed region
+    # host-resident input: H2D of the CSR inside the timed region (pageable first, then page-locked in place)
+    def host_fit():
+        t0 = time.perf_counter()
+        ctx.neighbours_from_csr(rp, ci32)
+        ctx.fit(c + 1, c + 2, 1, lab, None)
+        ctx.sort_by_size(lab, mc)
+        return 1e3 * (time.perf_counter() - t0)
+    out["host_resident_fit_ms_pageable"] = host_fit()
     t0 = time.perf_counter()
-    ctx.neighbours_from_csr(rp, ci32)
-    ctx.fit(c + 1, c + 2, 1, lab, None)
-    ctx.sort_by_size(lab, mc)
-    out["host_resident_fit_ms"] = 1e3 * (time.perf_counter() - t0)
+    _lib.host_register(rp); _lib.host_register(ci32); _lib.host_register(lab)
+    out["host_register_ms_once"] = 1e3 * (time.perf_counter() - t0)
+    out["host_resident_fit_ms"] = min(host_fit(), host_fit())
     out["host_equals_device"] = bool(np.array_equal(lab, lab_d.cpu().numpy()))
     if os.environ.get("ORACLE", "1") != "0":
         from oracle import port

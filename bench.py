@@ -181,7 +181,7 @@ def ncu_traffic():
         return json.load(fp).get("kernels", {})
 
 
-def stage_rooflines(timings, steps, n, d, nnz, stats, peak, count_mode=None):
+def stage_rooflines(timings, steps, n, d, nnz, stats, peak, count_mode=None, world=1):
     """Algorithmic bytes per launch (SURVEY.md 8d / DESIGN.md) over the measured mean duration."""
     traffic = ncu_traffic()
 
@@ -215,8 +215,10 @@ def stage_rooflines(timings, steps, n, d, nnz, stats, peak, count_mode=None):
         ms, nb, edges = count_mode
         tr = traffic.get("cn_count_kernel", {}).get("dram_bytes")
         out.append({"kernel": "cn_count_kernel", "stage": "cn_count (count mode: every candidate edge, no early exit; not part "
-                    "of the timed fit step)", "bound": "hbm", "achieved": nb / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": nb / (ms * 1e-3) / 1e9 / peak, "traffic": tr, "ms_per_launch": ms, "algorithmic_bytes": nb,
+                    "of the timed fit step)" + (f"; rows sharded over {world} GPUs, all bytes over the slowest rank's time, "
+                                                f"peak = {world} x one GPU" if world > 1 else ""),
+                    "bound": "hbm", "achieved": nb / (ms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                    "frac": nb / (ms * 1e-3) / 1e9 / (peak * world), "traffic": tr, "ms_per_launch": ms, "algorithmic_bytes": nb,
                     "limited_by": "issue slots (one shared-memory probe per streamed entry)", "cn_checks_per_s": edges / (ms * 1e-3),
                     "note": "no-reuse model of SURVEY 8d: 4*sum over candidate edges of (deg_i + deg_j) + 8 B per edge; the rows "
                             "are in fact served from L1/L2 (N(i) sits in a shared-memory bitmap), so `traffic` is close to the "
@@ -224,8 +226,9 @@ def stage_rooflines(timings, steps, n, d, nnz, stats, peak, count_mode=None):
     return [e for e in out if e]
 
 
-def count_mode_bytes(ctx, n_member_cutoff):
-    """SURVEY 8d's algorithmic bytes of count mode for the CSR the context holds (computed on the device)."""
+def count_mode_bytes(ctx, n_member_cutoff, rows=None):
+    """SURVEY 8d's algorithmic bytes of count mode for the CSR the context holds (computed on the device); `rows`
+    restricts the sum to the candidate edges of a row block."""
     import torch
 
     from commonnnclustering_b200 import dist as cdist
@@ -240,8 +243,9 @@ def count_mode_bytes(ctx, n_member_cutoff):
     total = 0
     edges = 0
     step = 1 << 17  # rows per slab keeps the temporaries small
-    for b in range(0, n, step):
-        e = min(n, b + step)
+    r0, r1 = (0, n) if rows is None else rows
+    for b in range(r0, r1, step):
+        e = min(r1, b + step)
         s0, s1 = int(rp[b]), int(rp[e])
         rows = torch.repeat_interleave(torch.arange(b, e, device=dev), deg[b:e])
         cols = ci[s0:s1].long()
@@ -356,6 +360,33 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     assert np.array_equal(lh_np, lab_dev), "host-buffer and device-buffer paths disagree"
 
+    # ---- count mode (SimilarityChecker._get for every candidate edge): the intersection kernel on its own -------
+    # every rank counts the candidate edges of its own row block (the rows it needs are in its halo CSR); the job's
+    # rate is all bytes over the slowest rank's time
+    step_device()
+    rows = None if runner is None else cdist.block_of(runner.last["bounds"], rank)
+    nb_count, n_edges = count_mode_bytes(ctx, nmc, rows)
+    _, nnz_local, _ = ctx.neighbours_info()
+    counts = torch.empty(max(nnz_local, 1), dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        ctx.cn_count(nmc, counts, rows=rows)
+    barrier()
+    ctx.set_timing(True)
+    ctx.timings(reset=True)
+    reps = 5
+    for i in range(reps):
+        flush.fill_(i)
+        ctx.cn_count(nmc, counts, rows=rows)
+    t_count, _ = ctx.timings(reset=True)
+    ctx.set_timing(False)
+    agg = torch.tensor([float(nb_count), float(n_edges)], dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([t_count["cn_count"][0] / reps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(agg)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    count_mode = (float(tmax.item()), float(agg[0].item()), float(agg[1].item()))
+    del counts
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -375,26 +406,7 @@ def run_b200(args):
                "fitter_points_per_s": n / cl.summary[-1].execution_time}
         assert np.array_equal(cl.labels, lab_dev)
 
-    # ---- count mode (SimilarityChecker._get for every candidate edge): the intersection kernel on its own -------
-    count_mode = None
-    if world == 1:
-        ctx.fit_points(xd, r2, nmc, sim, labd, member_cutoff=w["member_cutoff"])
-        nb_count, n_edges = count_mode_bytes(ctx, nmc)
-        counts = torch.empty(nnz, dtype=torch.int32, device="cuda")
-        for _ in range(2):
-            ctx.cn_count(nmc, counts)
-        ctx.set_timing(True)
-        ctx.timings(reset=True)
-        reps = 5
-        for i in range(reps):
-            flush.fill_(i)
-            ctx.cn_count(nmc, counts)
-        t_count, _ = ctx.timings(reset=True)
-        ctx.set_timing(False)
-        count_mode = (t_count["cn_count"][0] / reps, nb_count, n_edges)
-        del counts
-
-    roofs = stage_rooflines(timings, args.steps, n, d, nnz, stats, peak, count_mode)
+    roofs = stage_rooflines(timings, args.steps, n, d, nnz, stats, peak, count_mode, world)
     fit_roofs = [e for e in roofs if not e["stage"].startswith("cn_count")]
     top = max(fit_roofs, key=lambda e: e["ms_per_launch"]) if fit_roofs else None
     stage_ms = {k: v[0] / args.steps for k, v in timings.items() if v[1]}

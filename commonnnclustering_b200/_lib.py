@@ -43,6 +43,7 @@ SIGNATURES = {
     "cnnb200_neighbours_export": [_P, _P, _P, C.c_int],
     "cnnb200_neighbours_device_view": [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)],
     "cnnb200_cn_count": [_P, _I64, _P, C.c_int, C.POINTER(_I64)],
+    "cnnb200_cn_count_rows": [_P, _I64, _I64, _I64, _P, C.c_int, C.POINTER(_I64)],
     "cnnb200_fit": [_P, _I64, _I64, _I64, _P, _P, C.c_int, C.POINTER(_I64)],
     "cnnb200_components_begin": [_P, _I64, _I64, _P, C.c_int],
     "cnnb200_components_edges": [_P, _I64, _I64],
@@ -267,14 +268,16 @@ class Context:
         return a.value, b.value, c.value
 
     # -- similarity ---------------------------------------------------------------------------
-    def cn_count(self, n_member_cutoff, out=None):
-        """uint32 common-neighbour count per CSR slot (internal CSR order); 0xFFFFFFFF = not an edge."""
-        _, nnz, _ = self.neighbours_info()
+    def cn_count(self, n_member_cutoff, out=None, rows=None):
+        """uint32 common-neighbour count per CSR slot (internal CSR order); 0xFFFFFFFF = not an edge.
+        ``rows=(begin, end)`` restricts the pass to a row block (row-sharded runs)."""
+        n, nnz, _ = self.neighbours_info()
         if out is None:
             out = np.empty(max(nnz, 1), dtype=np.uint32)
         p, loc = _ptr_loc(out)
         ne = _I64()
-        check(self._lib.cnnb200_cn_count(self._h, int(n_member_cutoff), p, loc, C.byref(ne)))
+        b, e = (0, n) if rows is None else rows
+        check(self._lib.cnnb200_cn_count_rows(self._h, int(n_member_cutoff), int(b), int(e), p, loc, C.byref(ne)))
         return out[:nnz], ne.value
 
     # -- components -----------------------------------------------------------------------------

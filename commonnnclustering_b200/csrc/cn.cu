@@ -631,7 +631,7 @@ __global__ void comp_merge_kernel(const int *__restrict__ others, ll n, ll count
 #define CNW_BATCH 4
 
 __global__ void __launch_bounds__(WIN_WARPS * 32)
-cn_count_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll n, ll n_member_cutoff,
+cn_count_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll row_begin, ll n, ll n_member_cutoff,
                 unsigned *__restrict__ counts, unsigned long long *stats, unsigned long long *row_counter) {
     __shared__ unsigned win_all[WIN_WARPS][WIN_BITS / 32];
     const unsigned full = 0xffffffffu;
@@ -645,9 +645,9 @@ cn_count_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx,
     unsigned long long n_edges = 0, n_fallback = 0;
     for (;;) {
         ll i0 = 0;
-        if (lane == 0) i0 = (ll)atomicAdd(row_counter, (unsigned long long)CNW_BATCH);
+        if (lane == 0) i0 = row_begin + (ll)atomicAdd(row_counter, (unsigned long long)CNW_BATCH);
         i0 = __shfl_sync(full, i0, 0);
-        if (i0 >= n) break;
+        if (i0 >= n) break;  // n = end of the row range
         const ll i1 = i0 + CNW_BATCH < n ? i0 + CNW_BATCH : n;
         for (ll i = i0; i < i1; ++i) {
             const ll b = row_ptr[i];
@@ -877,11 +877,20 @@ extern "C" int cnnb200_components_merge(cnnb200_ctx *ctx, const int32_t *others,
 
 extern "C" int cnnb200_cn_count(cnnb200_ctx *ctx, int64_t n_member_cutoff, uint32_t *counts, int loc,
                                 int64_t *n_edges_out) {
+    if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "cn_count: NULL argument");
+    if (!ctx->have_nb) CNN_FAIL(CNNB200_E_STATE, "cn_count: no neighbourhoods held by this context");
+    return cnnb200_cn_count_rows(ctx, n_member_cutoff, 0, ctx->n, counts, loc, n_edges_out);
+}
+
+extern "C" int cnnb200_cn_count_rows(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_t row_begin, int64_t row_end,
+                                     uint32_t *counts, int loc, int64_t *n_edges_out) {
     if (!ctx || !counts) CNN_FAIL(CNNB200_E_INVALID, "cn_count: NULL argument");
     if (!ctx->have_nb) CNN_FAIL(CNNB200_E_STATE, "cn_count: no neighbourhoods held by this context");
+    if (row_begin < 0 || row_end > ctx->n || row_begin > row_end) CNN_FAIL(CNNB200_E_INVALID, "cn_count: bad row range");
     CNN_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    ll n = ctx->n, nnz = ctx->nnz;
+    ll nnz = ctx->nnz;
+    const ll rows = row_end - row_begin;
     CNN_TRY(cnn_ensure(ctx, ctx->b_stats, sizeof(unsigned long long) * ST_N));
     CNN_CUDA(cudaMemsetAsync(ctx->b_stats.p, 0, sizeof(unsigned long long) * ST_N, st));
     unsigned *d_counts = counts;
@@ -892,13 +901,13 @@ extern "C" int cnnb200_cn_count(cnnb200_ctx *ctx, int64_t n_member_cutoff, uint3
     // persistent grid: as many CTAs as fit (32 KB of window bitmaps each), rows handed out dynamically
     static const int cn_ctas = resident_ctas(cn_count_kernel, WIN_WARPS * 32);
     int blocks = ctx->sm_count * cn_ctas;
-    ll want = (n + WIN_WARPS * CNW_BATCH - 1) / (WIN_WARPS * CNW_BATCH);
+    ll want = (rows + WIN_WARPS * CNW_BATCH - 1) / (WIN_WARPS * CNW_BATCH);
     if (blocks > want) blocks = (int)want;
     if (blocks < 1) blocks = 1;
     unsigned long long *row_counter = (unsigned long long *)ctx->b_stats.p + ST_N - 1;
     {
         Span sp(ctx, T_CN_COUNT);
-        cn_count_kernel<<<blocks, WIN_WARPS * 32, 0, st>>>(ctx->row_ptr, ctx->col_idx, n, n_member_cutoff, d_counts,
+        cn_count_kernel<<<blocks, WIN_WARPS * 32, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, n_member_cutoff, d_counts,
                                                           (unsigned long long *)ctx->b_stats.p, row_counter);
         CNN_LAUNCHED(ctx, 1);
     }

@@ -159,6 +159,10 @@ int cnnb200_neighbours_device_view(cnnb200_ctx *ctx, const int64_t **row_ptr,
  * ------------------------------------------------------------------------------------- */
 int cnnb200_cn_count(cnnb200_ctx *ctx, int64_t n_member_cutoff, uint32_t *counts, int loc,
                      int64_t *n_edges_out);
+/* The same for the rows [row_begin, row_end) only (the slots of the other rows are left untouched): one rank's share
+ * of a row-sharded run -- the rows of its block and of every neighbour of them must be held (halo construction). */
+int cnnb200_cn_count_rows(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_t row_begin, int64_t row_end,
+                          uint32_t *counts, int loc, int64_t *n_edges_out);
 
 /* ---------------------------------------------------------------------------------------
  * Density-connected components.  Replaces FitterExtBFS._fit (_fit.pyx:408-491) including its

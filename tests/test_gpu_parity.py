@@ -287,6 +287,16 @@ def test_common_neighbour_counts_equal_oracle(ctx):
     for k in pick:
         i, j = rows[k], ci[k]
         assert counts[k] == port.count_common(ci[rp[i]:rp[i + 1]], ci[rp[j]:rp[j + 1]])
+    # a row block only (row-sharded runs): the block's slots equal the full pass, the others are left alone
+    import torch
+
+    part = torch.full((ci.shape[0],), 7, dtype=torch.int32, device="cuda")
+    b, e = 700, 1900
+    _, n_block = ctx.cn_count(cutoff, part, rows=(b, e))
+    part = part.cpu().numpy().view(np.uint32)
+    in_block = (rows >= b) & (rows < e)
+    np.testing.assert_array_equal(part[in_block], counts[in_block])
+    assert (part[~in_block] == 7).all() and n_block == int((is_edge & in_block).sum())
     # long lists (reference benchmark case equal_c50: identical lists, docsrc/benchmark/bm_similarity.ipynb)
     chk = _types.SimilarityCheckerCommonNN()
     a = np.arange(20000)

@@ -898,6 +898,19 @@ extern "C" int cnnb200_cn_count_rows(cnnb200_ctx *ctx, int64_t n_member_cutoff, 
         CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(unsigned) * (size_t)nnz));
         d_counts = ctx->b_tmp0.as<unsigned>();
     }
+    bool packed = false;
+    CNN_TRY(cnn_pack_rows(ctx, &packed));
+    if (packed) {
+        CNN_CUDA(cudaMemsetAsync(ctx->b_stats.p, 0, sizeof(unsigned long long) * ST_N, st));
+        CNN_TRY(cnn_count_packed(ctx, n_member_cutoff, row_begin, row_end, d_counts));
+        if (loc == CNNB200_HOST)
+            CNN_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof(unsigned) * (size_t)nnz, cudaMemcpyDeviceToHost, st));
+        if (loc == CNNB200_HOST || n_edges_out) {
+            CNN_TRY(fetch_stats(ctx));
+            if (n_edges_out) *n_edges_out = ctx->stats[ST_EDGES];
+        }
+        return CNNB200_OK;
+    }
     // persistent grid: as many CTAs as fit (32 KB of window bitmaps each), rows handed out dynamically
     static const int cn_ctas = resident_ctas(cn_count_kernel, WIN_WARPS * 32);
     int blocks = ctx->sm_count * cn_ctas;

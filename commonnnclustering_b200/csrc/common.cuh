@@ -129,6 +129,11 @@ struct cnnb200_ctx {
     ll o_m = 0, o_nnz = 0;
     Buf b_o_x, b_o_deg, b_o_row_ptr, b_o_col_idx, b_o_labels;
 
+    // ---- bit-packed rows (packed.cu): valid while packed_version == nb_version --------------------------------------
+    ll nb_version = 0, packed_version = -1, packed_words = 0;
+    bool use_packed = true;  // CNNB200_PACKED=0: per-entry kernels only
+    Buf b_wrows, b_wcnt;
+
     // ---- components ----------------------------------------------------------------------
     bool have_comp = false;
     ll n_member_cutoff = 0, similarity_cutoff = 0;
@@ -202,5 +207,7 @@ int cnn_grid_fill(cnnb200_ctx *ctx, ll pb, ll pe, const ll *row_ptr, int *col_id
 int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric);
 int cnn_dense_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric,
                      int method);
+int cnn_pack_rows(cnnb200_ctx *ctx, bool *usable_out);
+int cnn_count_packed(cnnb200_ctx *ctx, ll n_member_cutoff, ll row_begin, ll row_end, unsigned *d_counts);
 int cnn_scan_deg_to_row_ptr(cnnb200_ctx *ctx, const int32_t *deg, ll n, ll *row_ptr, ll *nnz_out,
                             ll *max_deg_out);

@@ -84,6 +84,7 @@ static int finish_csr(cnnb200_ctx *ctx, ll n, ll nnz, ll max_deg, const ll *row_
     ctx->col_idx = col_idx;
     ctx->perm = nullptr;
     ctx->have_nb = true;
+    ++ctx->nb_version;
     ctx->have_comp = false;
     return CNNB200_OK;
 }

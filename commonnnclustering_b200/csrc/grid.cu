@@ -824,6 +824,7 @@ extern "C" int cnnb200_neighbours_adopt(cnnb200_ctx *ctx, const int64_t *row_ptr
     ctx->col_idx = col_idx;
     ctx->perm = grid_perm ? ctx->b_perm.as<int>() : nullptr;
     ctx->have_nb = true;
+    ++ctx->nb_version;
     ctx->have_comp = false;
     ctx->have_points = false;
     ctx->have_other = false;

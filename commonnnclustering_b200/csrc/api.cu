@@ -93,6 +93,7 @@ extern "C" int cnnb200_ctx_create(int device, cnnb200_ctx **out) {
     if (const char *e = getenv("CNNB200_FUSED_UNION")) ctx->fuse_union = atoi(e) != 0;
     if (const char *e = getenv("CNNB200_FILTER")) ctx->use_filter = atoi(e) != 0;
     if (const char *e = getenv("CNNB200_PACKED")) ctx->use_packed = atoi(e) != 0;
+    if (const char *e = getenv("CNNB200_PACK_FIT")) ctx->pack_in_fit = atoi(e) != 0;
     if (const char *e = getenv("CNNB200_TENSOR_REORDER")) ctx->tensor_reorder = atoi(e) != 0;
     if (const char *e = getenv("CNNB200_TENSOR_PAIR_CAP")) ctx->tensor_band_cap = atoll(e);  // initial pair-list capacity (tests)
     if (const char *e = getenv("CNNB200_SINGLE_PASS_MB")) ctx->single_pass_limit = (ll)atoll(e) << 20;

@@ -132,6 +132,8 @@ struct cnnb200_ctx {
     // ---- bit-packed rows (packed.cu): valid while packed_version == nb_version --------------------------------------
     ll nb_version = 0, packed_version = -1, packed_words = 0;
     bool use_packed = true;  // CNNB200_PACKED=0: per-entry kernels only
+    bool pack_in_fit = false; // CNNB200_PACK_FIT=1: the fit's edge passes run on packed rows (measured slower on C2: packing costs 0.73 ms)
+    bool comp_packed = false;
     Buf b_wrows, b_wcnt;
 
     // ---- components ----------------------------------------------------------------------
@@ -208,6 +210,7 @@ int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radi
 int cnn_dense_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric,
                      int method);
 int cnn_pack_rows(cnnb200_ctx *ctx, bool *usable_out);
+int cnn_worklist_packed(cnnb200_ctx *ctx, const int2 *worklist, const unsigned long long *wl_count, int cutoff, int *parent);
 int cnn_count_packed(cnnb200_ctx *ctx, ll n_member_cutoff, ll row_begin, ll row_end, unsigned *d_counts);
 int cnn_scan_deg_to_row_ptr(cnnb200_ctx *ctx, const int32_t *deg, ll n, ll *row_ptr, ll *nnz_out,
                             ll *max_deg_out);

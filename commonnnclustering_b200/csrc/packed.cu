@@ -7,6 +7,7 @@
 // same shared-memory window of N(i), which is now simply the row's words stored at (word index - first word index).
 // Inputs whose rows do not compress (scattered indices) keep the per-entry kernels of cn.cu.
 #include "common.cuh"
+#include "uf.cuh"
 
 #define PK_WORDS (65536 / 32)  // window words per warp (8 KB): same index span as the per-entry window
 #define PK_WARPS 4
@@ -224,6 +225,94 @@ cn_count_packed_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ c
         if (n_edges) atomicAdd(stats + ST_EDGES, n_edges);
         if (n_fallback) atomicAdd(stats + ST_FALLBACK, n_fallback);
     }
+}
+
+// ---- work-list pass on packed rows (same contract as comp_worklist_kernel in cn.cu) ----------------------------------
+__global__ void __launch_bounds__(PK_WARPS * 32)
+comp_worklist_packed_kernel(const ll *__restrict__ row_ptr, const int2 *__restrict__ wrows, const int *__restrict__ wcnt,
+                            const int2 *__restrict__ worklist, const unsigned long long *__restrict__ wl_count, int cutoff,
+                            int *parent, unsigned long long *stats) {
+    __shared__ unsigned win_all[PK_WARPS][PK_WORDS];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    PkWin w;
+    w.words = win_all[threadIdx.x >> 5];
+    w.first = 0;
+    w.span = 0;
+    for (int t = lane; t < PK_WORDS; t += 32) w.words[t] = 0;
+    __syncwarp();
+    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    const ll count = (ll)*wl_count;
+    unsigned long long n_checks = 0, n_acc = 0, n_skip = 0;
+    for (ll e0 = warp * 32; e0 < count; e0 += nwarps * 32) {
+        const ll e = e0 + lane;
+        const bool valid = e < count;
+        const int2 ed = valid ? worklist[e] : make_int2(0, 0);
+        const int ri = valid ? uf_find(parent, ed.x) : 0;
+        const int rj = valid ? uf_find(parent, ed.y) : 0;
+        const bool need = valid && ri != rj;
+        const ll bi = need ? row_ptr[ed.x] : 0, bj = need ? row_ptr[ed.y] : 0;
+        const int mi = need ? (int)(row_ptr[ed.x + 1] - bi) : 0, mj = need ? (int)(row_ptr[ed.y + 1] - bj) : 0;
+        int acc = need && cutoff <= 0 ? 1 : 0;
+        const bool coop = need && cutoff > 0 && mi >= cutoff && mj >= cutoff;
+        const int wi = coop ? wcnt[ed.x] : 0, wj = coop ? wcnt[ed.y] : 0;
+        unsigned work = __ballot_sync(full, coop);
+        const unsigned nd = __ballot_sync(full, need);
+        n_skip += __popc(__ballot_sync(full, valid)) - __popc(nd);
+        n_checks += __popc(nd);
+        int cur_x = -1, cur_w = 0;
+        const int2 *cur_row = nullptr;
+        auto consume = [&](const PkFetch &f) {
+            const int x = __shfl_sync(full, ed.x, f.src);
+            if (x != cur_x) {  // the scan emits the work list row by row: the window is rebuilt only when i changes
+                if (cur_x >= 0) pk_clear(w, cur_row, cur_w, lane);
+                cur_x = x;
+                cur_row = wrows + __shfl_sync(full, bi, f.src);
+                cur_w = __shfl_sync(full, wi, f.src);
+                pk_set(w, cur_row, cur_w, lane);
+            }
+            const int c = w.span ? pk_count(f, lane, w) : pk_common_search(cur_row, cur_w, f.rj, f.wj, lane);
+            if (lane == f.src) acc = c >= cutoff;
+        };
+        PkFetch f0, f1, f2;
+        pk_fetch(f0, work, wrows, bj, wj, lane);
+        pk_fetch(f1, work, wrows, bj, wj, lane);
+        for (;;) {
+            if (f0.src < 0) break;
+            pk_fetch(f2, work, wrows, bj, wj, lane);
+            consume(f0);
+            if (f1.src < 0) break;
+            pk_fetch(f0, work, wrows, bj, wj, lane);
+            consume(f1);
+            if (f2.src < 0) break;
+            pk_fetch(f1, work, wrows, bj, wj, lane);
+            consume(f2);
+        }
+        if (cur_x >= 0) pk_clear(w, cur_row, cur_w, lane);
+        if (acc) uf_union(parent, ri, rj);
+        n_acc += __popc(__ballot_sync(full, acc != 0));
+    }
+    if (lane == 0) {
+        if (n_checks) atomicAdd(stats + ST_CHECKS, n_checks);
+        if (n_acc) atomicAdd(stats + ST_ACCEPTED, n_acc);
+        if (n_skip) atomicAdd(stats + ST_SKIPPED, n_skip);
+    }
+}
+
+int cnn_worklist_packed(cnnb200_ctx *ctx, const int2 *worklist, const unsigned long long *wl_count, int cutoff, int *parent) {
+    static int ctas = 0;
+    if (!ctas) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, comp_worklist_packed_kernel, PK_WARPS * 32, 0) != cudaSuccess || ctas < 1) {
+            cudaGetLastError();
+            ctas = 1;
+        }
+    }
+    comp_worklist_packed_kernel<<<ctx->sm_count * ctas, PK_WARPS * 32, 0, ctx->stream>>>(
+        ctx->row_ptr, ctx->b_wrows.as<int2>(), ctx->b_wcnt.as<int>(), worklist, wl_count, cutoff, parent,
+        (unsigned long long *)ctx->b_stats.p);
+    CNN_KERNEL_CHECK();
+    return CNNB200_OK;
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------------

@@ -48,6 +48,6 @@ cnt = torch.empty(nnz, dtype=torch.int32, device="cuda")
 for it in range(3):
     _, ne = ctx.cn_count(c + 1, cnt)
     t, _l = ctx.timings()
-    print("cn_count ms", round(t["cn_count"][0], 3), "edges", ne, flush=True)
+    print("cn_count ms", round(t["cn_count"][0], 3), "pack ms", round(t["ingest"][0], 3), "edges", ne, flush=True)
 lab = labd.cpu().numpy()
 print("ALL OK" if ok else "FAILURES")

@@ -39,6 +39,8 @@ SIGNATURES = {
     "cnnb200_neighbours_adopt": [_P, _P, _P, _I64, _I64, _I64, C.c_int],
     "cnnb200_neighbours_from_csr": [_P, _P, _P, C.c_int, C.c_int, C.c_int, _I64, _I64],
     "cnnb200_neighbours_from_padded": [_P, _P, _P, C.c_int, _I64, _I64],
+    "cnnb200_neighbours_from_distances": [_P, _P, C.c_int, _I64, C.c_double],
+    "cnnb200_neighbours_sort_rows": [_P, C.POINTER(C.c_int)],
     "cnnb200_neighbours_info": [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)],
     "cnnb200_neighbours_export": [_P, _P, _P, C.c_int],
     "cnnb200_neighbours_device_view": [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)],
@@ -248,6 +250,21 @@ class Context:
             raise ValueError("padded and counts must live in the same memory space")
         n, max_deg = padded.shape
         check(self._lib.cnnb200_neighbours_from_padded(self._h, pp, cp, loc, n, max_deg))
+
+    def neighbours_from_distances(self, dist, radius_cutoff):
+        """Neighbourhoods from a precomputed f64 [n, n] distance matrix (``dist[i, j] <= radius_cutoff``)."""
+        if len(dist.shape) != 2 or dist.shape[0] != dist.shape[1]:
+            raise ValueError("the distance matrix must be square")
+        if "float64" not in str(dist.dtype):
+            raise ValueError("the distance matrix must be float64")
+        dp, loc = _ptr_loc(dist)
+        check(self._lib.cnnb200_neighbours_from_distances(self._h, dp, loc, dist.shape[0], float(radius_cutoff)))
+
+    def neighbours_sort_rows(self) -> bool:
+        """Sorts the held rows ascending when they are not; True when a sort was needed."""
+        flag = C.c_int(0)
+        check(self._lib.cnnb200_neighbours_sort_rows(self._h, C.byref(flag)))
+        return bool(flag.value)
 
     def neighbours_info(self):
         n, nnz, md = _I64(), _I64(), _I64()

@@ -410,6 +410,19 @@ class MetricEuclideanPeriodicReduced(Metric):
         return total
 
 
+class MetricPrecomputed(Metric):
+    """The input data ARE the distances: ``distance(a, b) = data[a, b]``; radius unchanged.
+    Reference: ``MetricExtPrecomputed``, ``_types.pyx:2108-2127`` (recipe key ``precomputed``, the
+    ``distances`` recipe)."""
+    name = "precomputed"
+
+    def adjust_radius(self, radius_cutoff: float) -> float:
+        return float(radius_cutoff)
+
+    def calc_distance(self, index_a: int, index_b: int, input_data) -> float:
+        return float(input_data.to_components_array()[index_a, index_b])
+
+
 class DistanceGetterMetric:
     """Reference: ``DistanceGetterExtMetric``, ``_types.pyx:1966-2017`` (pure indirection)."""
 
@@ -465,6 +478,13 @@ class NeighboursGetterRadius(NeighboursGetter):
 
     def get_all(self, input_data, cluster_params, ctx=None) -> Neighbourhoods:
         ctx = ctx or _lib.default_context()
+        if isinstance(self.metric, MetricPrecomputed):
+            # one thresholding pass over the N x N matrix (``cnnb200_neighbours_from_distances``); a host matrix is
+            # page-locked in place once so that every further fit (parameter scans) streams it at PCIe speed
+            if hasattr(input_data, "pin"):
+                input_data.pin()
+            ctx.neighbours_from_distances(input_data.device_or_host_array, cluster_params.radius_cutoff)
+            return Neighbourhoods(ctx)
         self.prepare(ctx)
         ctx.neighbours_from_points(input_data.device_or_host_array, cluster_params.radius_cutoff,
                                    metric=self.metric.name, method=self.method)
@@ -489,12 +509,13 @@ class NeighboursGetterTensor(NeighboursGetterRadius):
 class NeighboursGetterLookup(NeighboursGetter):
     """Precomputed neighbourhoods.  Bulk replacement of ``NeighboursGetterExtLookup``
     (``_types.pyx:1791-1832``): uploads the padded matrix or CSR once and converts it to int32 CSR.
-    Rows must be ascending (the reference's ``sorted_neighbourhoods`` recipe, ``recipes.py:349-357``)."""
+    ``is_sorted=True`` (the reference's ``sorted_neighbourhoods`` recipe, ``recipes.py:349-357``) promises
+    ascending rows; with ``is_sorted=False`` (the ``neighbourhoods`` recipe, ``recipes.py:340-348``, the
+    reference's default for the getter, ``_types.pyx:1794``) the rows are checked on the device and sorted
+    there when needed -- the labels do not depend on the order inside a list."""
 
-    def __init__(self, is_sorted: bool = True, is_selfcounting: bool = True):
-        if not is_sorted:
-            raise ValueError("the B200 lookup getter needs ascending neighbour lists (is_sorted=True)")
-        self.is_sorted = True
+    def __init__(self, is_sorted: bool = False, is_selfcounting: bool = True):
+        self.is_sorted = bool(is_sorted)
         self.is_selfcounting = bool(is_selfcounting)
 
     def get_all(self, input_data, cluster_params=None, ctx=None) -> Neighbourhoods:
@@ -507,6 +528,8 @@ class NeighboursGetterLookup(NeighboursGetter):
             ctx.neighbours_from_padded(input_data.padded, input_data.n_neighbours)
         else:
             raise TypeError("NeighboursGetterLookup needs InputDataNeighbourhoods or InputDataNeighbourhoodsCSR")
+        if not self.is_sorted:
+            ctx.neighbours_sort_rows()
         return Neighbourhoods(ctx)
 
 

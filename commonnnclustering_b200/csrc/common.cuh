@@ -209,6 +209,7 @@ int cnn_grid_fill(cnnb200_ctx *ctx, ll pb, ll pe, const ll *row_ptr, int *col_id
 int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric);
 int cnn_dense_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric,
                      int method);
+int cnn_finish_csr(cnnb200_ctx *ctx, ll n, ll nnz, ll max_deg, const ll *row_ptr, const int *col_idx);
 int cnn_pack_rows(cnnb200_ctx *ctx, bool *usable_out);
 int cnn_worklist_packed(cnnb200_ctx *ctx, const int2 *worklist, const unsigned long long *wl_count, int cutoff, int *parent);
 int cnn_count_packed(cnnb200_ctx *ctx, ll n_member_cutoff, ll row_begin, ll row_end, unsigned *d_counts);

@@ -76,7 +76,7 @@ __global__ void padded_rows_kernel(const ll *__restrict__ padded, ll row0, ll ro
     if (bad) *flag = 1;
 }
 
-static int finish_csr(cnnb200_ctx *ctx, ll n, ll nnz, ll max_deg, const ll *row_ptr, const int *col_idx) {
+int cnn_finish_csr(cnnb200_ctx *ctx, ll n, ll nnz, ll max_deg, const ll *row_ptr, const int *col_idx) {
     ctx->n = n;
     ctx->nnz = nnz;
     ctx->max_deg = max_deg;
@@ -165,7 +165,7 @@ extern "C" int cnnb200_neighbours_from_csr(cnnb200_ctx *ctx, const int64_t *row_
     CNN_CUDA(cudaMemcpyAsync(h, flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CNN_CUDA(cudaStreamSynchronize(st));
     if (h[0]) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_csr: row_ptr not monotone or an index outside [0, n)");
-    return finish_csr(ctx, n, nnz, h[1], d_row_ptr, d_col);
+    return cnn_finish_csr(ctx, n, nnz, h[1], d_row_ptr, d_col);
 }
 
 extern "C" int cnnb200_neighbours_from_padded(cnnb200_ctx *ctx, const int64_t *padded, const int64_t *counts,
@@ -221,7 +221,7 @@ extern "C" int cnnb200_neighbours_from_padded(cnnb200_ctx *ctx, const int64_t *p
     }
     CNN_TRY(read_flag(ctx, flag, &bad));
     if (bad) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_padded: a neighbour index is outside [0, n)");
-    return finish_csr(ctx, n, nnz, md, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
+    return cnn_finish_csr(ctx, n, nnz, md, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
 }
 
 // ---- export in the caller's index space ----------------------------------------------------------

@@ -72,6 +72,7 @@ COMPONENT_NAME_TYPE_MAP = {
     },
     "distance_getter": {"metric": _types.DistanceGetterMetric},
     "metric": {
+        "precomputed": _types.MetricPrecomputed,
         "euclidean": _types.MetricEuclidean,
         "euclidean_r": _types.MetricEuclideanReduced,
         "euclidean_reduced": _types.MetricEuclideanReduced,
@@ -113,6 +114,25 @@ REGISTERED_RECIPES = {
         "predictor.checker": "commonnn_b200",
         "predictor.ngetter.dgetter": "metric",
         "predictor.ngetter.dgetter.metric": "euclidean_r",
+    },
+    "distances": {   # reference recipes.py:329-339: the input is an N x N distance matrix
+        "input_data": "components_b200",
+        "preparation_hook": "points_from_parts",
+        "fitter": "b200_staged",
+        "fitter.ngetter": "radius_b200",
+        "fitter.checker": "commonnn_b200",
+        "fitter.ngetter.dgetter": "metric",
+        "fitter.ngetter.dgetter.metric": "precomputed",
+    },
+    "neighbourhoods": {   # reference recipes.py:340-348: neighbour lists in any order
+        "input_data": "neighbourhoods_b200",
+        "preparation_hook": "neighbourhoods",
+        "fitter": "b200_staged",
+        "fitter.ngetter": ("lookup", (), {"is_sorted": False}),
+        "fitter.checker": "commonnn_b200",
+        "predictor": "b200",
+        "predictor.ngetter": ("lookup", (), {"is_sorted": False}),
+        "predictor.checker": "commonnn_b200",
     },
     "sorted_neighbourhoods": {
         "input_data": "neighbourhoods_b200",

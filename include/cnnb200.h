@@ -136,6 +136,21 @@ int cnnb200_neighbours_from_csr(cnnb200_ctx *ctx, const int64_t *row_ptr, const 
 int cnnb200_neighbours_from_padded(cnnb200_ctx *ctx, const int64_t *padded,
                                    const int64_t *counts, int loc, int64_t n, int64_t max_deg);
 
+/* Neighbourhoods from a precomputed distance matrix, f64 [n, n] row-major, HOST or DEVICE:
+ * j is a neighbour of i when dist[i*n + j] <= radius_cutoff (NaN never passes; the diagonal decides
+ * whether a point counts itself).  Replaces NeighboursGetterExtBruteForce._get (_types.pyx:1692-1710)
+ * over MetricExtPrecomputed._calc_distance (_types.pyx:2108-2127), i.e. the reference's "distances"
+ * recipe (recipes.py:329-339), for all rows at once.  The matrix is read once. */
+int cnnb200_neighbours_from_distances(cnnb200_ctx *ctx, const double *dist, int loc, int64_t n,
+                                      double radius_cutoff);
+
+/* Brings the rows of the held neighbourhood structure into ascending order when they are not
+ * (the reference's "neighbourhoods" recipe, recipes.py:340-348, takes lists in any order:
+ * NeighboursGetterExtLookup with is_sorted=False, _types.pyx:1791-1804).  A borrowed col_idx is left
+ * untouched (the sorted copy lives in the context).  *sorted_out (optional) = 1 when a sort was needed.
+ * Limit: nnz < 2^31-1 for unsorted input. */
+int cnnb200_neighbours_sort_rows(cnnb200_ctx *ctx, int *sorted_out);
+
 /* Sizes of the neighbourhood structure currently held. */
 int cnnb200_neighbours_info(cnnb200_ctx *ctx, int64_t *n, int64_t *nnz, int64_t *max_deg);
 

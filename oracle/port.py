@@ -270,3 +270,28 @@ def fit_points_periodic(x, r: float, c: int, bounds, member_cutoff=None, max_clu
     if sort:
         sort_by_size(labels, member_cutoff, max_clusters)
     return labels
+
+
+def neighbours_from_distances(dist, radius_cutoff: float):
+    """CSR of {j: dist[i, j] <= radius_cutoff}, rows ascending: NeighboursGetterExtBruteForce._get
+    (_types.pyx:1692-1710) over MetricExtPrecomputed._calc_distance (_types.pyx:2108-2127) -- the metric
+    returns ``input_data[i, j]`` and leaves the radius unchanged (``_adjust_radius``, :2126-2127)."""
+    dist = np.ascontiguousarray(dist, dtype=np.float64)
+    n = dist.shape[0]
+    assert dist.shape == (n, n)
+    with np.errstate(invalid="ignore"):
+        hit = dist <= float(radius_cutoff)
+    row_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(hit.sum(axis=1), out=row_ptr[1:])
+    col_idx = np.nonzero(hit)[1].astype(np.int64)
+    return row_ptr, col_idx
+
+
+def fit_distances(dist, r: float, c: int, member_cutoff=None, max_clusters=None, sort=True):
+    """Clustering.fit with the "distances" recipe (recipes.py:329-339; self-counting brute-force getter)."""
+    p = make_parameters(r, c, metric=None)
+    row_ptr, col_idx = neighbours_from_distances(dist, p["radius_cutoff"])
+    labels = fit_bfs(row_ptr, col_idx, p["n_member_cutoff"], p["similarity_cutoff"], 1)
+    if sort:
+        sort_by_size(labels, member_cutoff, max_clusters)
+    return labels

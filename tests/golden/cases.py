@@ -93,3 +93,53 @@ CASES = {
     "c1_full": dict(data=lambda: datasets.blobs_2d(10_000), fit=dict(r=0.3, c=10)),
     "c1_r019_c37": dict(data=lambda: datasets.blobs_2d(10_000), fit=dict(r=0.19, c=37)),
 }
+
+
+# ---- the reference's other input recipes: "distances" (N x N matrix, MetricExtPrecomputed) and
+# "neighbourhoods" (neighbour lists in ANY order) ------------------------------------------------------
+def cityblock_matrix(x):
+    """Manhattan distances: not a metric the coordinate path offers, so only the matrix route can produce these labels."""
+    x = np.asarray(x, dtype=np.float64)
+    return np.ascontiguousarray(np.abs(x[:, None, :] - x[None, :, :]).sum(axis=2))
+
+
+def euclid_matrix_with_holes(x, seed=11):
+    """Euclidean distances with NaN / inf entries (never neighbours), kept symmetric: the device path settles each
+    candidate edge once from its lower end and therefore needs ``j in N(i) <=> i in N(j)``."""
+    x = np.asarray(x, dtype=np.float64)
+    dm = np.sqrt(((x[:, None, :] - x[None, :, :]) ** 2).sum(axis=2))
+    rng = np.random.default_rng(seed)
+    n = dm.shape[0]
+    i, j = rng.integers(0, n, 4000), rng.integers(0, n, 4000)
+    dm[i[:2500], j[:2500]] = np.nan
+    dm[j[:2500], i[:2500]] = np.nan
+    dm[i[2500:], j[2500:]] = np.inf
+    dm[j[2500:], i[2500:]] = np.inf
+    return np.ascontiguousarray(dm)
+
+
+def shuffled_neighbour_lists(x, r, seed=5):
+    """Neighbour lists (self included) of a point set, every list in random order."""
+    x = np.asarray(x, dtype=np.float64)
+    d2 = ((x[:, None, :] - x[None, :, :]) ** 2).sum(axis=2)
+    rng = np.random.default_rng(seed)
+    out = []
+    for row in d2 <= r * r:
+        nb = np.nonzero(row)[0]
+        rng.shuffle(nb)
+        out.append(nb.astype(np.int64))
+    return out
+
+
+RECIPE_CASES = {
+    "dist_cityblock_blobs800": dict(recipe="distances", data=lambda: cityblock_matrix(datasets.blobs_2d(800)),
+                                    fit=dict(r=0.15, c=8)),
+    "dist_holes_md1000": dict(recipe="distances", data=lambda: euclid_matrix_with_holes(datasets.md_like_3d(1000)),
+                              fit=dict(r=0.6, c=5, member_cutoff=5)),
+    "dist_odd_n1031": dict(recipe="distances", data=lambda: cityblock_matrix(gauss(1031, 3, 9)),
+                           fit=dict(r=0.9, c=6)),
+    "nbh_unsorted_md2000": dict(recipe="neighbourhoods", data=lambda: shuffled_neighbour_lists(datasets.md_like_3d(2000), 0.45),
+                                fit=dict(r=0.45, c=6, member_cutoff=5)),
+    "nbh_unsorted_blobs1200": dict(recipe="neighbourhoods", data=lambda: shuffled_neighbour_lists(datasets.blobs_2d(1200), 0.12),
+                                   fit=dict(r=0.12, c=10)),
+}

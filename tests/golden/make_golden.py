@@ -8,6 +8,7 @@ Run in the build container (needs /root/reference and oracle/_ref built by oracl
 Outputs (committed):
   ref_labels.npz      label arrays produced by the reference's own ``Clustering.fit`` for the cases
                       listed in ``cases.py`` (inputs are regenerated from seeds, never stored)
+  ref_labels_recipes.npz  the same for ``cases.RECIPE_CASES`` ("distances" and "neighbourhoods" recipes)
   records_sample.json a distilled sample of the reference's vendored parameter-scan records
                       (docsrc/benchmark/records/*.json): n_clusters / ratio_largest / ratio_noise
                       for (data set, r, c) cells whose data can be regenerated from code
@@ -41,6 +42,19 @@ def main():
         out[name] = labels.astype(np.int32)
         print(f"{name:28s} n={x.shape[0]:6d} clusters={int(labels.max()):4d} noise={(labels == 0).mean():.3f}")
     np.savez_compressed(os.path.join(HERE, "ref_labels.npz"), **out)
+
+    # the "distances" and "neighbourhoods" recipes of the reference (recipes.py:329-348)
+    out = {}
+    mod = ref.module()
+    for name, case in cases.RECIPE_CASES.items():
+        data = case["data"]()
+        kw = dict(case["fit"])
+        cl = mod.Clustering(data, recipe=case["recipe"])
+        cl.fit(kw.pop("r"), kw.pop("c"), v=False, **kw)
+        labels = np.array(cl.labels, dtype=np.int64)
+        out[name] = labels.astype(np.int32)
+        print(f"{name:28s} n={labels.shape[0]:6d} clusters={int(labels.max()):4d} noise={(labels == 0).mean():.3f}")
+    np.savez_compressed(os.path.join(HERE, "ref_labels_recipes.npz"), **out)
 
     # vendored scan records: keep a deterministic sample per reproducible set
     sample = {}

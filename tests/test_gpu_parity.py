@@ -226,6 +226,81 @@ def test_lookup_recipes_equal_oracle():
         np.testing.assert_array_equal(cl.labels, want)
 
 
+GOLD_RECIPES = np.load(os.path.join(HERE, "golden", "ref_labels_recipes.npz"))
+
+
+@pytest.mark.parametrize("name", list(cases.RECIPE_CASES))
+def test_other_recipes_equal_reference_golden(name):
+    """"distances" (N x N matrix through ``cnnb200_neighbours_from_distances``) and "neighbourhoods" (lists in any
+    order, sorted on the device by ``cnnb200_neighbours_sort_rows``) through ``Clustering`` with the reference's own
+    recipe names, against labels the reference produced."""
+    case = cases.RECIPE_CASES[name]
+    data = case["data"]()
+    kw = dict(case["fit"])
+    cl = fit_via_api(data, kw.pop("r"), kw.pop("c"), recipe=case["recipe"], **kw)
+    np.testing.assert_array_equal(cl.labels, GOLD_RECIPES[name].astype(np.int64))
+
+
+def test_distance_matrix_neighbour_sets(ctx):
+    # sets equal the oracle's thresholding, for host and device matrices, odd sizes, NaN/inf entries, r on a value
+    import torch
+
+    rng = np.random.default_rng(3)
+    for n in (1, 31, 33, 1024, 1025, 2500):
+        dm = rng.random((n, n))
+        dm = np.minimum(dm, dm.T)
+        np.fill_diagonal(dm, 0.0)
+        if n > 40:
+            dm[5, 7] = dm[7, 5] = np.nan
+            dm[1, 2] = dm[2, 1] = np.inf
+            dm[3, 4] = dm[4, 3] = -np.inf
+        r = float(dm[n // 2, n // 3]) if n > 1 else 0.0   # an entry exactly ON the cutoff: "<=" keeps it
+        rp, ci = port.neighbours_from_distances(dm, r)
+        for arr in (dm, torch.from_numpy(dm).cuda()):
+            ctx.neighbours_from_distances(arr, r)
+            got_rp, got_ci = ctx.neighbours_export()
+            np.testing.assert_array_equal(got_rp, rp)
+            np.testing.assert_array_equal(got_ci, ci)
+    with pytest.raises(ValueError):
+        ctx.neighbours_from_distances(np.zeros((3, 4)), 1.0)
+    with pytest.raises(ValueError):
+        ctx.neighbours_from_distances(np.zeros((3, 3), dtype=np.float32), 1.0)
+
+
+def test_sort_rows_on_arrival(ctx):
+    # unsorted CSR / padded input: sorted once on the device; sorted input is left alone; a borrowed device CSR is
+    # never written to
+    import torch
+
+    x = datasets.md_like_3d(4000)
+    rp, ci = port.neighbours(x, 0.4 ** 2)
+    want = port.fit_csr(rp, ci, 6, member_cutoff=5)
+    rng = np.random.default_rng(0)
+    sh = ci.copy()
+    for i in range(x.shape[0]):
+        rng.shuffle(sh[rp[i]:rp[i + 1]])
+    ctx.neighbours_from_csr(rp, ci)
+    assert ctx.neighbours_sort_rows() is False
+    ctx.neighbours_from_csr(rp, sh)
+    assert ctx.neighbours_sort_rows() is True
+    got_rp, got_ci = ctx.neighbours_export()
+    np.testing.assert_array_equal(got_ci, ci)
+    lab = np.zeros(x.shape[0], dtype=np.int64)
+    ctx.fit(6 + 1, 6 + 2, 1, lab)
+    ctx.sort_by_size(lab, member_cutoff=5)
+    np.testing.assert_array_equal(lab, want)
+    d_rp, d_sh = torch.from_numpy(rp).cuda(), torch.from_numpy(sh.astype(np.int32)).cuda()
+    keep = d_sh.clone()
+    ctx.neighbours_from_csr(d_rp, d_sh, borrow=True)
+    assert ctx.neighbours_sort_rows() is True
+    assert torch.equal(d_sh, keep)
+    np.testing.assert_array_equal(ctx.neighbours_export()[1], ci)
+    # through the API: list of shuffled lists, the reference's default lookup getter (is_sorted=False)
+    nb = [sh[rp[i]:rp[i + 1]] for i in range(x.shape[0])]
+    cl = fit_via_api(nb, 0.4, 6, recipe="neighbourhoods", member_cutoff=5)
+    np.testing.assert_array_equal(cl.labels, want)
+
+
 def test_lookup_without_selfcounting(ctx):
     # lists without the point itself: n_member_cutoff = c, similarity_cutoff = c (_fit.pyx:143-151)
     x = datasets.blobs_2d(2000)

@@ -95,6 +95,31 @@ def test_port_equals_reference_golden(name):
     np.testing.assert_array_equal(got, GOLD[name].astype(np.int64))
 
 
+GOLD_RECIPES = np.load(os.path.join(HERE, "golden", "ref_labels_recipes.npz"))
+
+
+def _lists_to_csr(lists):
+    rows = [np.sort(np.asarray(a, dtype=np.int64)) for a in lists]
+    row_ptr = np.zeros(len(rows) + 1, dtype=np.int64)
+    np.cumsum([len(a) for a in rows], out=row_ptr[1:])
+    return row_ptr, np.concatenate(rows)
+
+
+@pytest.mark.parametrize("name", list(cases.RECIPE_CASES))
+def test_port_equals_reference_golden_other_recipes(name):
+    """The reference's "distances" recipe (thresholded N x N matrix) and "neighbourhoods" recipe (lists in any
+    order: the labels only depend on the sets) against labels the reference itself produced."""
+    case = cases.RECIPE_CASES[name]
+    data = case["data"]()
+    kw = dict(case["fit"])
+    r, c = kw.pop("r"), kw.pop("c")
+    if case["recipe"] == "distances":
+        got = port.fit_distances(data, r, c, **kw)
+    else:
+        got = port.fit_csr(*_lists_to_csr(data), c, **kw)
+    np.testing.assert_array_equal(got, GOLD_RECIPES[name].astype(np.int64))
+
+
 def test_grid_and_brute_neighbour_sets_agree():
     for x, r in [(cases.lattice(600, 2, 3), 0.25), (cases.datasets.md_like_3d(3000), 0.5), (cases.lattice(200, 1, 5), 0.125)]:
         a = port.neighbours(x, r * r, method="brute")

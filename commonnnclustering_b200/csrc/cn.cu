@@ -66,6 +66,19 @@ __device__ __forceinline__ int lane_check(const int *__restrict__ a, int na, con
     if (cutoff <= 0) return 1;
     if (na < cutoff || nb < cutoff) return 0;
     int ia = 0, ib = 0, count = 0;
+    if (na > 192 || nb > 192) {
+        // long lists (C1: 10^3 entries per row): start the merge where the index ranges begin to overlap --
+        // one binary search instead of a walk of dependent loads through the non-overlapping head
+        const int a0 = a[0], b0 = b[0];
+        const int *s = a0 < b0 ? a : b;
+        const int target = a0 < b0 ? b0 : a0;
+        int l = 0, h = a0 < b0 ? na : nb;
+        while (l < h) {
+            const int mid = (l + h) >> 1;
+            if (s[mid] < target) l = mid + 1; else h = mid;
+        }
+        if (a0 < b0) ia = l; else ib = l;
+    }
     while (ia < na && ib < nb) {
         const int va = a[ia], vb = b[ib];
         count += va == vb ? 1 : 0;
@@ -309,7 +322,7 @@ __device__ __forceinline__ void fetch_next(RowFetch &f, unsigned &todo, const in
 __global__ void __launch_bounds__(256)
 comp_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll row_begin, ll row_end,
                  const int *__restrict__ above, const int *__restrict__ parent, int2 *__restrict__ worklist,
-                 unsigned long long *wl_count, unsigned long long *stats) {
+                 unsigned long long *wl_count, unsigned long long *stats, int tile_rows) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -317,9 +330,11 @@ comp_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx
     ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     unsigned long long n_edges = 0, n_need = 0;
     constexpr int R = 8;  // chunks in flight per warp
-    for (ll i0 = row_begin + warp * 32; i0 < row_end; i0 += nwarps * 32) {
+    // tile_rows (<= 32) rows per warp tile: fewer when the rows are long, so that few long rows (C1: 10^4 rows of
+    // 10^3 entries) still spread over all SMs
+    for (ll i0 = row_begin + warp * tile_rows; i0 < row_end; i0 += nwarps * tile_rows) {
         const ll il = i0 + lane;
-        const bool lv = il < row_end;
+        const bool lv = il < row_end && lane < tile_rows;
         // independent loads (no branch on the root): one memory round trip for the whole tile header
         const int rl = lv ? parent[il] : -1;
         const ll e_raw = lv ? row_ptr[il + 1] : 0, b_raw = lv ? row_ptr[il] : 0;
@@ -787,10 +802,13 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         CNN_TRY(cnn_ensure(ctx, ctx->b_worklist, sizeof(int2) * (size_t)cap_edges));
         unsigned long long *wl_count = stats + ST_N - 1;
         CNN_CUDA(cudaMemsetAsync(wl_count, 0, sizeof(unsigned long long), st));
-        int sblocks = (int)((rows + 255) / 256);
+        int tile_rows = 32;  // about 8k entries per warp tile
+        const ll mean_deg = ctx->nnz / (ctx->n > 0 ? ctx->n : 1);
+        while (tile_rows > 1 && mean_deg * tile_rows > 8192) tile_rows >>= 1;
+        int sblocks = (int)((rows + 8 * tile_rows - 1) / (8 * tile_rows));
         if (sblocks > ctx->sm_count * 32) sblocks = ctx->sm_count * 32;
         comp_scan_kernel<<<sblocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, above, parent,
-                                                  ctx->b_worklist.as<int2>(), wl_count, stats);
+                                                  ctx->b_worklist.as<int2>(), wl_count, stats, tile_rows);
         if (ctx->comp_packed) {
             CNN_TRY(cnn_worklist_packed(ctx, ctx->b_worklist.as<int2>(), wl_count, cutoff, parent));
         } else {

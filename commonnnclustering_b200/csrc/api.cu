@@ -106,7 +106,8 @@ extern "C" int cnnb200_ctx_create(int device, cnnb200_ctx **out) {
     F(c->b_cell_id_sorted) F(c->b_idx) F(c->b_cell_start) F(c->b_bbox) F(c->b_cub) F(c->b_tmp0)     \
     F(c->b_tmp1) F(c->b_tmp2) F(c->b_parent) F(c->b_core) F(c->b_above) F(c->b_edges) F(c->b_worklist) F(c->b_cell_count) F(c->b_minorig) F(c->b_flags)             \
     F(c->b_rank) F(c->b_labels) F(c->b_consider) F(c->b_stats) F(c->b_lab_count) F(c->b_lab_first)  \
-    F(c->b_lab_keys) F(c->b_lab_keys2) F(c->b_lab_vals) F(c->b_lab_vals2) F(c->b_lab_map)
+    F(c->b_lab_keys) F(c->b_lab_keys2) F(c->b_lab_vals) F(c->b_lab_vals2) F(c->b_lab_map) \
+    F(c->b_pg_x) F(c->b_pg_orig) F(c->b_pg_xq) F(c->b_pg_perm) F(c->b_pg_deg) F(c->b_pg_img) F(c->b_pg_row_ptr) F(c->b_pg_col)
 
 extern "C" int cnnb200_ctx_release(cnnb200_ctx *ctx) {
     if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");
@@ -168,6 +169,7 @@ extern "C" int cnnb200_ctx_set_periodic_bounds(cnnb200_ctx *ctx, const double *b
     CNN_CUDA(cudaMemcpyAsync(ctx->b_bounds.p, bounds, sizeof(double) * (size_t)d, cudaMemcpyHostToDevice, ctx->stream));
     CNN_CUDA(cudaStreamSynchronize(ctx->stream));  // the host array may go away
     ctx->n_bounds = d;
+    for (int k = 0; k < 3; ++k) ctx->bounds_h[k] = k < d ? bounds[k] : 0.0;
     return CNNB200_OK;
 }
 
@@ -262,9 +264,13 @@ extern "C" int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x,
     if (metric != CNNB200_METRIC_EUCLIDEAN_REDUCED && metric != CNNB200_METRIC_EUCLIDEAN &&
         metric != CNNB200_METRIC_EUCLIDEAN_PERIODIC_REDUCED)
         CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_points: unknown metric %d", metric);
-    if (metric == CNNB200_METRIC_EUCLIDEAN_PERIODIC_REDUCED) {
-        if (method != 0 && method != 2) CNN_FAIL(CNNB200_E_INVALID, "the periodic metric is served by the tiled method only");
-        method = 2;
+    const bool periodic = metric == CNNB200_METRIC_EUCLIDEAN_PERIODIC_REDUCED;
+    if (periodic) {
+        if (method == 3) CNN_FAIL(CNNB200_E_INVALID, "the periodic metric is served by the grid (d <= 3) and tiled methods");
+        if (ctx->n_bounds != d)
+            CNN_FAIL(CNNB200_E_STATE, "periodic metric: set %lld bounds with cnnb200_ctx_set_periodic_bounds first", (long long)d);
+        // cell list on the image-augmented set from a few thousand points on; the all-pairs kernel below that
+        if (method == 0) method = (d <= 3 && n >= 4096) ? 1 : 2;
     }
     if (!(radius_cutoff >= 0.0)) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_points: radius_cutoff must be >= 0");
     if (method == 0) method = d <= 3 ? 1 : 2;
@@ -282,7 +288,13 @@ extern "C" int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x,
                                  cudaMemcpyHostToDevice, ctx->stream));
         d_x = ctx->b_x.as<double>();
     }
-    if (method == 1)
+    if (periodic && method == 1) {
+        bool served = false;
+        CNN_TRY(cnn_grid_search_periodic(ctx, d_x, n, d, radius_cutoff, &served));
+        if (!served) method = 2;  // a period shorter than two radii: images would overlap, the all-pairs kernel decides
+    }
+    if (periodic && method == 1) {
+    } else if (method == 1)
         CNN_TRY(cnn_grid_search(ctx, d_x, n, d, radius_cutoff, metric));
     else
         CNN_TRY(cnn_dense_search(ctx, d_x, n, d, radius_cutoff, metric, method));
@@ -290,7 +302,7 @@ extern "C" int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x,
     ++ctx->nb_version;
     ctx->have_other = false;
     ctx->have_points = true;  // prediction for other points needs the coordinates, the cutoff and the metric again
-    ctx->pts_grid = method == 1;
+    ctx->pts_grid = method == 1 && !periodic;
     ctx->pts_x = d_x;
     ctx->pts_d = d;
     ctx->pts_rc = radius_cutoff;

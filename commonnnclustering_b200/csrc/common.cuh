@@ -154,6 +154,8 @@ struct cnnb200_ctx {
     ll stats[ST_N] = {0};
     Buf b_bounds;     // f64 [n_bounds]: periods of the periodic metric
     ll n_bounds = 0;
+    double bounds_h[3] = {0, 0, 0};  // host copy of the first three (periodic cell list, periodic.cu)
+    Buf b_pg_x, b_pg_orig, b_pg_xq, b_pg_perm, b_pg_deg, b_pg_img, b_pg_row_ptr, b_pg_col;  // periodic cell list: augmented set + results
     Buf b_lab_summary;
     bool have_lab_summary = false;
     ll lab_summary_n = 0;
@@ -207,6 +209,7 @@ int cnn_grid_build(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radiu
 int cnn_grid_rows(cnnb200_ctx *ctx, ll pb, ll pe, int *deg);
 int cnn_grid_fill(cnnb200_ctx *ctx, ll pb, ll pe, const ll *row_ptr, int *col_idx);
 int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric);
+int cnn_grid_search_periodic(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, bool *served);
 int cnn_dense_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric,
                      int method);
 int cnn_finish_csr(cnnb200_ctx *ctx, ll n, ll nnz, ll max_deg, const ll *row_ptr, const int *col_idx);

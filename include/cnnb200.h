@@ -44,7 +44,10 @@ extern "C" {
 #define CNNB200_METRIC_EUCLIDEAN_REDUCED 0
 #define CNNB200_METRIC_EUCLIDEAN 1
 /* MetricExtEuclideanPeriodicReduced (_types.pyx:2290-2348, "euclidean_periodic_r"): per-dimension period `bounds[k]`
- * (0 = not periodic), set with cnnb200_ctx_set_periodic_bounds; the tiled all-pairs method only. */
+ * (0 = not periodic), set with cnnb200_ctx_set_periodic_bounds.  Methods: grid (d <= 3: the cell list on the point set
+ * augmented by its periodic images as a filter, then the reference's arithmetic on the original coordinates; needs every
+ * period >= two radii, else the request falls through to tiled) and tiled (all pairs, any d); auto = grid from 4096
+ * points on when d <= 3. */
 #define CNNB200_METRIC_EUCLIDEAN_PERIODIC_REDUCED 2
 
 #define CNNB200_OK 0

@@ -10,5 +10,6 @@ ncu) ncu --set full --clock-control none --import-source on --profile-from-start
 ncu_grid) COUNT=0 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:grid_rows -o gpurun_out/prof_grid -f python scripts/ncu_c2.py > gpurun_out/ncu_grid.log 2>&1; tail -2 gpurun_out/ncu_grid.log;;
 launches) ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python scripts/ncu_c2.py > gpurun_out/ncu_launches.log 2>&1; tail -2 gpurun_out/ncu_launches.log;;
 distmat) python scripts/distmat_bench.py > gpurun_out/distmat.json 2> gpurun_out/distmat.err; tail -3 gpurun_out/distmat.err; cut -c1-1500 gpurun_out/distmat.json;;
+periodic) python scripts/periodic_bench.py > gpurun_out/periodic.json 2> gpurun_out/periodic.err; tail -3 gpurun_out/periodic.err; cut -c1-2500 gpurun_out/periodic.json;;
 esac
 done

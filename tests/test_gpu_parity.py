@@ -674,6 +674,47 @@ def test_predict_equals_reference():
 
 
 # ---- periodic metric -----------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["dihedral2d", "mixed3d_many_periods", "ring1d", "ring1d_long_rows", "lattice3d_ties",
+                                  "short_period"])
+def test_periodic_cell_list_neighbour_sets_are_exact(ctx, name):
+    """The periodic cell list (images as a filter + the reference's arithmetic on the original coordinates) against the
+    oracle's brute force under MetricExtEuclideanPeriodicReduced: identical rows, for coordinates outside [0, L),
+    negative ones, a non-periodic dimension, distances exactly on the cutoff across the boundary, and a period too
+    short for the image construction (falls through to the all-pairs kernel)."""
+    rng = np.random.default_rng(17)
+    n = 6000
+    if name == "dihedral2d":      # angles in [-pi, pi), as MD dihedrals come
+        x = np.c_[rng.vonmises(2.9, 1.5, n), rng.vonmises(-3.0, 2.0, n)]
+        bounds, r = np.array([2 * np.pi, 2 * np.pi]), 0.12
+    elif name == "mixed3d_many_periods":   # y is not periodic; x and z spill over several periods on both sides
+        x = np.c_[rng.random(n) * 50.0 - 20.0, rng.standard_normal(n), rng.random(n) * 21.0 - 7.0]
+        bounds, r = np.array([10.0, 0.0, 7.0]), 0.6
+    elif name == "ring1d":
+        x = (rng.random((n, 1)) * 3.0) - 1.0
+        bounds, r = np.array([1.0]), 0.004
+    elif name == "ring1d_long_rows":   # 2400 neighbours per point: rows with images beyond the shared-memory staging
+        x = (rng.random((n, 1)) * 3.0) - 1.0
+        bounds, r = np.array([1.0]), 0.2
+    elif name == "lattice3d_ties":  # lattice spacing 1/8, period 3, r = 3/8: many pairs exactly ON the cutoff, also across faces
+        x = rng.integers(0, 24, (n, 3)) / 8.0 + rng.integers(-2, 3, (n, 3)) * 3.0
+        bounds, r = np.array([3.0, 3.0, 3.0]), 0.375
+    else:                          # period 0.5 < 2 r: served by the all-pairs kernel
+        x = rng.random((n, 2))
+        bounds, r = np.array([0.5, 1.0]), 0.26
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    ctx.set_periodic_bounds(bounds)
+    want_rp, want_ci = port.neighbours_periodic(x, r * r, bounds)
+    for method in ("auto", "grid", "tiled"):
+        ctx.neighbours_from_points(x, r * r, metric="euclidean_periodic_r", method=method)
+        rp, ci = ctx.neighbours_export()
+        np.testing.assert_array_equal(rp, want_rp)
+        np.testing.assert_array_equal(ci, want_ci)
+    # and the labels through the API
+    cl = cluster.Clustering(x, fitter__ngetter__dgetter__metric=(_types.MetricEuclideanPeriodicReduced, (bounds,), {}))
+    cl.fit(r, 4, member_cutoff=3, v=False)
+    np.testing.assert_array_equal(cl.labels, port.fit_points_periodic(x, r, 4, bounds, member_cutoff=3))
+
+
 def test_periodic_metric_equals_oracle_and_reference(ctx):
     rng = np.random.default_rng(3)
     bounds = np.array([2 * np.pi, 0.0, 2 * np.pi])
@@ -689,7 +730,7 @@ def test_periodic_metric_equals_oracle_and_reference(ctx):
     cl.fit(0.35, 8, member_cutoff=5, v=False)
     np.testing.assert_array_equal(cl.labels, port.fit_points_periodic(x, 0.35, 8, bounds, member_cutoff=5))
     with pytest.raises(ValueError):
-        ctx.neighbours_from_points(x, 0.1, metric="euclidean_periodic_r", method="grid")
+        ctx.neighbours_from_points(x, 0.1, metric="euclidean_periodic_r", method="tensor")
     from oracle import ref
 
     if ref.available():

@@ -24,22 +24,39 @@ pack_rows_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     unsigned long long n_words = 0;
-    for (ll i = warp; i < n; i += nwarps) {
-        const ll b = row_ptr[i];
-        const int m = (int)(row_ptr[i + 1] - b);
+    // the bounds and the first chunk of the warp's NEXT row are fetched while the current one is being packed
+    ll i = warp;
+    ll b = i < n ? row_ptr[i] : 0;
+    int m = i < n ? (int)(row_ptr[i + 1] - b) : 0;
+    int v_first = lane < m ? col_idx[b + lane] : 0;
+    for (; i < n; i += nwarps) {
+        const ll i_next = i + nwarps;
+        ll b_next = 0;
+        int m_next = 0, v_next = 0;
+        if (i_next < n) {
+            b_next = row_ptr[i_next];
+            m_next = (int)(row_ptr[i_next + 1] - b_next);
+            v_next = lane < m_next ? col_idx[b_next + lane] : 0;
+        }
         int2 *out = wrows + b;
         int wc = 0, ckey = -1;
         unsigned cmask = 0;
         for (int k0 = 0; k0 < m; k0 += 32) {
             const int k = k0 + lane;
             const bool valid = k < m;
-            const int v = valid ? col_idx[b + k] : 0;
+            const int v = k0 == 0 ? v_first : (valid ? col_idx[b + k] : 0);
             const int key = valid ? (v >> 5) : -2 - lane;  // invalid lanes never match anything
             const unsigned bit = valid ? 1u << (v & 31) : 0u;
             const int prev = __shfl_up_sync(full, key, 1);
             const bool leader = valid && (lane == 0 || key != prev);
             const unsigned leaders = __ballot_sync(full, leader);
-            const unsigned peers = __match_any_sync(full, key);
+            // the lanes of my word: from the last leader at or below me to the lane before the next leader (keys are
+            // ascending, so a word is a run of lanes; padding lanes carry bit 0 and may ride along with the last run)
+            const unsigned le = leaders & (full >> (31 - lane));
+            const int start = 31 - __clz(le);
+            const unsigned above = lane == 31 ? 0u : leaders & (full << (lane + 1));
+            const int end = above ? __ffs(above) - 2 : 31;
+            const unsigned peers = (full >> (31 - end)) & (full << start);
             const unsigned gmask = __reduce_or_sync(peers, bit);
             const int first_key = __shfl_sync(full, key, 0);
             const bool merge = ckey == first_key;
@@ -63,6 +80,9 @@ pack_rows_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx
         }
         if (lane == 0) wcnt[i] = wc;
         n_words += wc;
+        b = b_next;
+        m = m_next;
+        v_first = v_next;
     }
     if (lane == 0 && n_words) atomicAdd(total, n_words);
 }

@@ -128,30 +128,39 @@ __global__ void col_mean_kernel(const double *__restrict__ x, ll n, int d, doubl
 
 // A'[i] = [hi | hi | lo | 0..], B'[i] = [hi | lo | hi | 0..] (bf16, row length kt), norm[i] = |x_i - mean|^2;
 // padding rows (i >= n) are zero with an infinite norm so that they never come near the cutoff.
-__global__ void split_kernel(const double *__restrict__ x, const double *__restrict__ mean, ll n, ll n_pad, int d,
-                             int kt, __nv_bfloat16 *A, __nv_bfloat16 *B, float *norm, int *maxnorm_bits) {
-    ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
-    if (i >= n_pad) return;
-    __nv_bfloat16 *a = A + i * kt, *b = B + i * kt;
+// One warp per row: lanes stride over the dimensions, so the f64 row comes in as one coalesced read and every bf16
+// segment goes out as contiguous 2-byte stores (a thread per row wrote 2 bytes at a stride of one row: 1.1 ms on C3).
+__global__ void __launch_bounds__(256)
+split_kernel(const double *__restrict__ x, const double *__restrict__ mean, ll n, ll n_pad, int d,
+             int kt, __nv_bfloat16 *A, __nv_bfloat16 *B, float *norm, int *maxnorm_bits) {
+    const int lane = threadIdx.x & 31;
+    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
-    if (i >= n) {
-        for (int k = 0; k < kt; ++k) { a[k] = zero; b[k] = zero; }
-        norm[i] = INFINITY;
-        return;
+    for (ll i = warp; i < n_pad; i += nwarps) {
+        __nv_bfloat16 *a = A + i * kt, *b = B + i * kt;
+        if (i >= n) {
+            for (int k = lane; k < kt; k += 32) { a[k] = zero; b[k] = zero; }
+            if (lane == 0) norm[i] = INFINITY;
+            continue;
+        }
+        double s = 0;
+        for (int k = lane; k < d; k += 32) {
+            const double xc = x[i * d + k] - mean[k];
+            s += xc * xc;
+            const __nv_bfloat16 hi = __float2bfloat16_rn((float)xc);
+            const __nv_bfloat16 lo = __float2bfloat16_rn((float)(xc - (double)__bfloat162float(hi)));
+            a[k] = hi; a[d + k] = hi; a[2 * d + k] = lo;
+            b[k] = hi; b[d + k] = lo; b[2 * d + k] = hi;
+        }
+        for (int k = 3 * d + lane; k < kt; k += 32) { a[k] = zero; b[k] = zero; }
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            const float sf = (float)s;
+            norm[i] = sf;
+            atomicMax(maxnorm_bits, __float_as_int(sf));
+        }
     }
-    double s = 0;
-    for (int k = 0; k < d; ++k) {
-        double xc = x[i * d + k] - mean[k];
-        s += xc * xc;
-        __nv_bfloat16 hi = __float2bfloat16_rn((float)xc);
-        __nv_bfloat16 lo = __float2bfloat16_rn((float)(xc - (double)__bfloat162float(hi)));
-        a[k] = hi; a[d + k] = hi; a[2 * d + k] = lo;
-        b[k] = hi; b[d + k] = lo; b[2 * d + k] = hi;
-    }
-    for (int k = 3 * d; k < kt; ++k) { a[k] = zero; b[k] = zero; }
-    float sf = (float)s;
-    norm[i] = sf;
-    atomicMax(maxnorm_bits, __float_as_int(sf));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -178,35 +187,46 @@ __device__ __noinline__ bool exact_within(const double *__restrict__ x, int d, l
 // is produced in the sorted index space together with perm[] (sorted position -> caller index), as in the grid path.
 #define N_PIVOTS 64
 
-// one warp per point: lanes stride over the dimensions (coalesced row reads), pivots sit in shared memory as floats
+// one warp per point: the row comes in with one coalesced read (lanes stride over the dimensions); each lane then owns
+// two pivots (n_piv <= 64) and walks the dimensions, the point's coordinate broadcast by a shuffle, the pivots in shared
+// memory as floats [d][n_piv] -- no reduction per pivot, one arg-min at the end
 __global__ void __launch_bounds__(256)
 pivot_assign_kernel(const double *__restrict__ x, ll n, int d, int n_piv, unsigned long long *keys, int *idx) {
-    extern __shared__ float piv[];  // [n_piv][d]
+    extern __shared__ float piv[];  // [d][n_piv]
+    const unsigned full = 0xffffffffu;
     for (int t = threadIdx.x; t < n_piv * d; t += blockDim.x) {
         const int p = t / d, k = t - p * d;
-        piv[t] = (float)x[(ll)((double)p * (double)n / (double)n_piv) * d + k];
+        piv[k * n_piv + p] = (float)x[(ll)((double)p * (double)n / (double)n_piv) * d + k];
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    const bool has0 = lane < n_piv, has1 = lane + 32 < n_piv;
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     for (ll i = warp; i < n; i += nwarps) {
         float xi[3];  // d <= 85 < 96: at most 3 coordinates per lane
 #pragma unroll
         for (int u = 0; u < 3; ++u) xi[u] = lane + 32 * u < d ? (float)x[i * d + lane + 32 * u] : 0.f;
-        float best = INFINITY;
-        int arg = 0;
-        for (int p = 0; p < n_piv; ++p) {
-            float s = 0.f;
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int u = 0; u < 3; ++u)
-                if (lane + 32 * u < d) {
-                    const float t = xi[u] - piv[p * d + lane + 32 * u];
-                    s = fmaf(t, t, s);
-                }
+        for (int u = 0; u < 3; ++u) {
+            const int kn = d - 32 * u < 32 ? d - 32 * u : 32;
+            for (int kk = 0; kk < kn; ++kk) {
+                const float xv = __shfl_sync(full, xi[u], kk);
+                const float *row = piv + (32 * u + kk) * n_piv;
+                const float t0 = xv - (has0 ? row[lane] : 0.f), t1 = xv - (has1 ? row[lane + 32] : 0.f);
+                s0 = fmaf(t0, t0, s0);
+                s1 = fmaf(t1, t1, s1);
+            }
+        }
+        float best = has0 ? s0 : INFINITY;
+        int arg = lane;
+        if (has1 && s1 < best) { best = s1; arg = lane + 32; }
 #pragma unroll
-            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (s < best) { best = s; arg = p; }
+        for (int o = 16; o; o >>= 1) {
+            const float ob = __shfl_xor_sync(full, best, o);
+            const int oa = __shfl_xor_sync(full, arg, o);
+            if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
         }
         if (lane == 0) {
             keys[i] = ((unsigned long long)arg << 32) | (unsigned long long)__float_as_uint(best);  // best >= 0: bits are ordered
@@ -234,7 +254,7 @@ __global__ void tile_ball_kernel(const double *__restrict__ x, ll n, int d, doub
         double s = 0.0;
         for (int r = 0; r < rows; ++r) s += x[(r0 + r) * d + k];
         c[k] = s / rows;
-        centre[T * d + k] = c[k];
+        centre[(ll)k * gridDim.x + T] = c[k];  // [d][n_tiles]: tile_skip_kernel reads 32 consecutive tiles per dimension
     }
     __syncthreads();
     double dist = 0.0;
@@ -255,19 +275,22 @@ __global__ void tile_ball_kernel(const double *__restrict__ x, ll n, int d, doub
     if (threadIdx.x == 0) radius[T] = rmax[0] * (1.0 + 1e-12) + 1e-300;
 }
 
-// bit J of row I set <=> tile pair (I, J) can be skipped; one warp per 32 column tiles
+// bit J of row I set <=> tile pair (I, J) can be skipped; one warp per 32 column tiles.  Only the words at or above the
+// diagonal are ever read (TileIter starts at the word of I0), the others are left alone.
 __global__ void tile_skip_kernel(const double *__restrict__ centre, const double *__restrict__ radius, ll n_tiles, int d,
                                  int words, double r_true, unsigned *skip) {
     const ll gw = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (gw >= n_tiles * words) return;
     const ll I = gw / words;
-    const ll J = (gw - I * words) * 32 + lane;
+    const ll wJ = gw - I * words;
+    if (wJ * 32 + 31 < (I & ~1ll)) return;  // below the diagonal of the CTA's first row tile (I0 = I & ~1)
+    const ll J = wJ * 32 + lane;
     bool sk = false;
     if (J < n_tiles) {
         double s = 0.0;
         for (int k = 0; k < d; ++k) {
-            const double t = centre[I * d + k] - centre[J * d + k];
+            const double t = centre[(ll)k * n_tiles + I] - centre[(ll)k * n_tiles + J];
             s += t * t;
         }
         // any i in I, j in J: |x_i - x_j| >= |c_I - c_J| - rho_I - rho_J
@@ -508,51 +531,107 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
 }
 
-// borderline pairs are decided exactly (rejected ones get i = -1); every surviving pair adds one to both degrees
+// borderline pairs are decided exactly (rejected ones get i = -1 and are counted: the degrees and row offsets follow
+// from the sorted keys afterwards -- two atomics per pair on the degree array cost more than the whole exact test).
+// Only ~1 pair in 6 of the list is borderline, so a thread per pair would run the 2 x d-element row walk with a few
+// live lanes per warp and fetch every 32-byte sector for 8 of its bytes.  Instead the warp collects its borderline
+// pairs by ballot and evaluates them four at a time, 8 lanes per pair: a lane loads 8 consecutive coordinates of both
+// rows (whole sectors) and forms its 8 squared differences; the sum is then accumulated in the reference's order
+// (_types.pyx:2253-2267: left to right, no FMA) by passing the running value from lane to lane of the group.
 template <bool SQRT>
-__global__ void pair_resolve_kernel(const double *__restrict__ x, int d, int2 *__restrict__ pairs, ll count, double rc,
-                                    int *deg, unsigned long long *n_band) {
-    ll k = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+pair_resolve_kernel(const double *__restrict__ x, int d, int2 *__restrict__ pairs, ll count, double rc,
+                    unsigned long long *n_band, unsigned long long *n_rejected) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 3, gl = lane & 7;
+    const ll k = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    int2 pr = make_int2(-1, -1);
     bool band = false;
     if (k < count) {
-        int2 pr = pairs[k];
+        pr = pairs[k];
         band = ((unsigned)pr.y & BAND_FLAG) != 0;
-        bool ok = true;
-        if (band) {
-            pr.y = (int)((unsigned)pr.y & ~BAND_FLAG);
-            ok = exact_within<SQRT>(x, d, pr.x, pr.y, rc);
-            pairs[k] = ok ? pr : make_int2(-1, -1);
+        pr.y = (int)((unsigned)pr.y & ~BAND_FLAG);
+    }
+    unsigned todo = __ballot_sync(full, band);
+    if (lane == 0 && todo) atomicAdd(n_band, (unsigned long long)__popc(todo));
+    bool ok = k < count;
+    while (todo) {
+        int src[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            src[q] = todo ? __ffs(todo) - 1 : -1;
+            todo &= todo - 1;  // no-op at 0
         }
-        if (ok) {
-            atomicAdd(deg + pr.x, 1);
-            atomicAdd(deg + pr.y, 1);
+        const int mine = g == 0 ? src[0] : g == 1 ? src[1] : g == 2 ? src[2] : src[3];
+        const int from = mine < 0 ? 0 : mine;
+        const ll pi = __shfl_sync(full, pr.x, from), pj = __shfl_sync(full, pr.y, from);
+        const double *a = x + pi * d, *b = x + pj * d;
+        double sum = 0.0;
+        for (int k0 = 0; k0 < d; k0 += 64) {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int kk = k0 + gl * 8 + u;
+                double df = 0.0;
+                if (mine >= 0 && kk < d) df = __dsub_rn(a[kk], b[kk]);
+                t[u] = __dmul_rn(df, df);  // +0.0 past the end: adding it changes nothing
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                if (gl == r) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) sum = __dadd_rn(sum, t[u]);
+                }
+                sum = __shfl_sync(full, sum, (lane & ~7) | r);
+            }
+        }
+        if (SQRT) sum = __dsqrt_rn(sum);
+        const bool within = sum <= rc;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool wq = __shfl_sync(full, within, q * 8);
+            if (lane == src[q]) ok = wq;
         }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, band);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_band, (unsigned long long)__popc(m));
+    if (band) pairs[k] = ok ? pr : make_int2(-1, -1);
+    const unsigned rej = __ballot_sync(full, band && !ok);
+    if (lane == 0 && rej) atomicAdd(n_rejected, (unsigned long long)__popc(rej));
 }
 
-// Both directed entries of every surviving pair and the self entry of every row as 64-bit keys (row : column);
-// rejected pairs become all-ones keys that sort behind everything.  After one radix sort the low words of the first
-// nnz keys ARE col_idx (rows ascending, columns ascending within a row).
-__global__ void pair_keys_kernel(const int2 *__restrict__ pairs, ll count, ll n, unsigned long long *__restrict__ keys) {
+// Both directed entries of every surviving pair and the self entry of every row as keys (row << bits | column) with
+// 2^bits > n; rejected pairs get row n and sort behind everything.  After one radix sort over 2 * bits key bits (5
+// passes instead of 7 for N = 2*10^5) the low parts of the first nnz keys ARE col_idx (rows ascending, columns
+// ascending within a row).
+__global__ void pair_keys_kernel(const int2 *__restrict__ pairs, ll count, ll n, int bits, unsigned long long *__restrict__ keys) {
     ll k = blockIdx.x * (ll)blockDim.x + threadIdx.x;
-    if (k < n) keys[2 * count + k] = ((unsigned long long)k << 32) | (unsigned long long)k;
+    if (k < n) keys[2 * count + k] = ((unsigned long long)k << bits) | (unsigned long long)k;
     if (k >= count) return;
     const int2 pr = pairs[k];
     const bool ok = pr.x >= 0;
-    keys[2 * k] = ok ? ((unsigned long long)(unsigned)pr.x << 32) | (unsigned)pr.y : ~0ull;
-    keys[2 * k + 1] = ok ? ((unsigned long long)(unsigned)pr.y << 32) | (unsigned)pr.x : ~0ull;
+    const unsigned long long dead = (unsigned long long)n << bits;
+    keys[2 * k] = ok ? ((unsigned long long)(unsigned)pr.x << bits) | (unsigned)pr.y : dead;
+    keys[2 * k + 1] = ok ? ((unsigned long long)(unsigned)pr.y << bits) | (unsigned)pr.x : dead;
 }
 
-__global__ void keys_to_cols_kernel(const unsigned long long *__restrict__ keys, ll nnz, int *__restrict__ col_idx) {
+// low words of the sorted keys = col_idx; the first key of every row gives row_ptr (every row holds its self entry,
+// so no row is empty)
+__global__ void keys_to_cols_kernel(const unsigned long long *__restrict__ keys, ll nnz, ll n, int bits,
+                                    int *__restrict__ col_idx, ll *__restrict__ row_ptr) {
     ll k = blockIdx.x * (ll)blockDim.x + threadIdx.x;
-    if (k < nnz) col_idx[k] = (int)(unsigned)(keys[k] & 0xffffffffull);
+    if (k >= nnz) return;
+    const unsigned long long key = keys[k];
+    col_idx[k] = (int)(unsigned)(key & ((1ull << bits) - 1ull));
+    const unsigned row = (unsigned)(key >> bits);
+    if (k == 0 || row != (unsigned)(keys[k - 1] >> bits)) row_ptr[row] = k;
+    if (k == nnz - 1) row_ptr[n] = nnz;
 }
 
-__global__ void fill_ones_kernel(int *a, ll n, ll n_total) {
-    ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
-    if (i < n_total) a[i] = i < n ? 1 : 0;
+__global__ void max_degree_kernel(const ll *__restrict__ row_ptr, ll n, int *out) {
+    ll r = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    int dg = r < n ? (int)(row_ptr[r + 1] - row_ptr[r]) : 0;
+    for (int o = 16; o; o >>= 1) dg = max(dg, __shfl_xor_sync(0xffffffffu, dg, o));
+    if ((threadIdx.x & 31) == 0 && dg) atomicMax(out, dg);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -650,7 +729,7 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
         CNN_CUDA(cudaMemsetAsync(maxbits, 0, sizeof(int), st));
         CNN_CUDA(cudaMemsetAsync(ctx->b_stats.p, 0, sizeof(unsigned long long) * ST_N, st));
         col_mean_kernel<<<(int)d, 256, 0, st>>>(d_x, n, (int)d, mean);
-        split_kernel<<<cnn_blocks(n_pad, 128), 128, 0, st>>>(d_x, mean, n, n_pad, (int)d, kt, A, B, norm, maxbits);
+        split_kernel<<<cnn_blocks(n_pad, 8) < ctx->sm_count * 32 ? cnn_blocks(n_pad, 8) : ctx->sm_count * 32, 256, 0, st>>>(d_x, mean, n, n_pad, (int)d, kt, A, B, norm, maxbits);
         CNN_LAUNCHED(ctx, 2);
         CNN_KERNEL_CHECK();
     }
@@ -669,9 +748,11 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     CNN_TRY(make_map(&mapA, A, n_pad, kt));
     CNN_TRY(make_map(&mapB, B, n_pad, kt));
 
-    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 128));
     unsigned long long *pair_count = (unsigned long long *)(ctx->b_tmp2.as<char>() + 48);
     unsigned long long *band_count = pair_count + 1;
+    unsigned long long *rej_count = pair_count + 2;
+    int *d_max_deg = (int *)(pair_count + 3);
 
     TensorParams P;
     memset(&P, 0, sizeof(P));
@@ -718,26 +799,27 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     }
     ctx->tensor_band_cap = pair_cap;
 
-    // ---- degrees: self + both ends of every pair that survives the exact test of the borderline ones ----------
-    int *deg = ctx->b_deg.as<int>();
+    // ---- borderline pairs decided exactly; the survivors are counted, not yet attributed to rows ------------------------
+    CNN_CUDA(cudaMemsetAsync(rej_count, 0, 2 * sizeof(unsigned long long), st));  // + d_max_deg
     {
         Span sp(ctx, T_SCAN);
-        fill_ones_kernel<<<cnn_blocks(n + 1, 256), 256, 0, st>>>(deg, n, n + 1);
         if (n_pairs > 0) {
             if (sq)
                 pair_resolve_kernel<true><<<cnn_blocks(n_pairs, 256), 256, 0, st>>>(d_x, (int)d, P.pairs, n_pairs, radius_cutoff,
-                                                                                deg, band_count);
+                                                                                band_count, rej_count);
             else
                 pair_resolve_kernel<false><<<cnn_blocks(n_pairs, 256), 256, 0, st>>>(d_x, (int)d, P.pairs, n_pairs, radius_cutoff,
-                                                                                 deg, band_count);
+                                                                                 band_count, rej_count);
         }
-        CNN_LAUNCHED(ctx, 2);
+        CNN_LAUNCHED(ctx, 1);
         CNN_KERNEL_CHECK();
     }
-    ll nnz = 0, max_deg = 0;
-    CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, deg, n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
+    CNN_CUDA(cudaMemcpyAsync(hb, band_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaStreamSynchronize(st));
+    const ll n_band = (ll)hb[0], n_rej = (ll)hb[1];
+    const ll nnz = 2 * (n_pairs - n_rej) + n;
     if (nnz >= (1ll << 31) - 1) CNN_FAIL(CNNB200_E_RANGE, "tensor search: more than 2^31 neighbour entries");
-    // ---- (row : column) keys of both directions + self, one radix sort, low words = col_idx -----------------------
+    // ---- (row : column) keys of both directions + self, one radix sort: low words = col_idx, row changes = row_ptr ------
     CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
     const ll n_keys = 2 * n_pairs + n;
     if (n_keys >= (1ll << 31) - 1) CNN_FAIL(CNNB200_E_RANGE, "tensor search: more than 2^31 sort keys");
@@ -746,22 +828,25 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     {
         Span sp(ctx, T_SEARCH_FILL);
         const ll work = n_pairs > n ? n_pairs : n;
-        pair_keys_kernel<<<cnn_blocks(work, 256), 256, 0, st>>>(P.pairs, n_pairs, n, keys);
         int bits = 1;
-        while ((1ll << bits) < n) ++bits;
+        while ((1ll << bits) <= n) ++bits;  // 2^bits > n: row n (rejected pairs) fits as well
+        pair_keys_kernel<<<cnn_blocks(work, 256), 256, 0, st>>>(P.pairs, n_pairs, n, bits, keys);
         size_t need = 0;
         CNN_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, need, keys, keys2, (int)n_keys, 0, 64, st));
         CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
         size_t cap = ctx->b_cub.cap;
-        // columns occupy bits [0, bits), rows bits [32, 32 + bits): the bits in between are zero for every valid key
-        // and one for the rejected ones, which therefore still end up last when bit 32 + bits is included
-        CNN_CUDA(cub::DeviceRadixSort::SortKeys(ctx->b_cub.p, cap, keys, keys2, (int)n_keys, 0, 32 + bits + 1, st));
-        keys_to_cols_kernel<<<cnn_blocks(nnz, 256), 256, 0, st>>>(keys2, nnz, ctx->b_col_idx.as<int>());
-        CNN_LAUNCHED(ctx, 2);
+        CNN_CUDA(cub::DeviceRadixSort::SortKeys(ctx->b_cub.p, cap, keys, keys2, (int)n_keys, 0, 2 * bits, st));
+        keys_to_cols_kernel<<<cnn_blocks(nnz, 256), 256, 0, st>>>(keys2, nnz, n, bits, ctx->b_col_idx.as<int>(),
+                                                                  ctx->b_row_ptr.as<ll>());
+        max_degree_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(ctx->b_row_ptr.as<ll>(), n, d_max_deg);
+        CNN_LAUNCHED(ctx, 3);
         CNN_KERNEL_CHECK();
     }
-    CNN_CUDA(cudaMemcpyAsync(hb, band_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    int *hmax = (int *)(hb + 4);
+    CNN_CUDA(cudaMemcpyAsync(hmax, d_max_deg, sizeof(int), cudaMemcpyDeviceToHost, st));
     CNN_CUDA(cudaStreamSynchronize(st));
+    const ll max_deg = hmax[0];
+    hb[0] = (unsigned long long)n_band;
     ctx->stats[ST_RECHECK] = (ll)hb[0];
     ctx->stats[ST_DIST] = n * (n - 1) / 2;
     ctx->n = n;

@@ -179,27 +179,27 @@ __global__ void label_survivor_kernel(const unsigned long long *__restrict__ key
 // what Clustering.fit records about the relabelled result (cluster.pyx:366-390): clusters kept, members of the
 // largest one, noise points -- from the sorted sizes, so that the host needs no pass over the labels
 __global__ void label_summary_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ surv, ll m, ll n,
-                                     int kb, ll *out) {
-    __shared__ ll s_sum[256], s_max[256], s_cnt[256];
+                                     int kb, unsigned long long *out) {
+    // out[0] += clusters kept, out[1] = max size, out[2] += members of kept clusters (noise = n - out[2], on the host)
     ll sum = 0, mx = 0, cnt = 0;
-    for (ll t = threadIdx.x; t < m; t += blockDim.x)
+    for (ll t = blockIdx.x * (ll)blockDim.x + threadIdx.x; t < m; t += (ll)gridDim.x * blockDim.x)
         if (surv[t]) {
             const ll size = n - (ll)(keys[t] >> kb);
             sum += size;
             mx = size > mx ? size : mx;
             ++cnt;
         }
-    s_sum[threadIdx.x] = sum; s_max[threadIdx.x] = mx; s_cnt[threadIdx.x] = cnt;
-    __syncthreads();
-    for (int o = 128; o; o >>= 1) {
-        if ((int)threadIdx.x < o) {
-            s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
-            s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o];
-            s_max[threadIdx.x] = s_max[threadIdx.x] > s_max[threadIdx.x + o] ? s_max[threadIdx.x] : s_max[threadIdx.x + o];
-        }
-        __syncthreads();
+    for (int o = 16; o; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        const ll om = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = om > mx ? om : mx;
     }
-    if (threadIdx.x == 0) { out[0] = s_cnt[0]; out[1] = s_max[0]; out[2] = n - s_sum[0]; }
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicAdd(out + 0, (unsigned long long)cnt);
+        atomicMax(out + 1, (unsigned long long)mx);
+        atomicAdd(out + 2, (unsigned long long)sum);
+    }
 }
 
 __global__ void label_map_kernel(const int *__restrict__ vals, const int *__restrict__ surv,
@@ -296,7 +296,9 @@ extern "C" int cnnb200_sort_by_size(cnnb200_ctx *ctx, int64_t *labels, int loc, 
         label_map_kernel<<<cnn_blocks(m, 256), 256, 0, st>>>(vals2, ctx->b_flags.as<int>(), ctx->b_rank.as<int>(), m, map);
         label_apply_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_labels, n, map, max_label);
         CNN_TRY(cnn_ensure(ctx, ctx->b_lab_summary, sizeof(ll) * 4));
-        label_summary_kernel<<<1, 256, 0, st>>>(keys2, ctx->b_flags.as<int>(), m, n, kb, ctx->b_lab_summary.as<ll>());
+        CNN_CUDA(cudaMemsetAsync(ctx->b_lab_summary.p, 0, sizeof(ll) * 4, st));
+        label_summary_kernel<<<cnn_blocks(m, 256) < 64 ? cnn_blocks(m, 256) : 64, 256, 0, st>>>(
+            keys2, ctx->b_flags.as<int>(), m, n, kb, ctx->b_lab_summary.as<unsigned long long>());
         ctx->have_lab_summary = true;
         CNN_LAUNCHED(ctx, 7);
         CNN_KERNEL_CHECK();
@@ -335,6 +337,6 @@ extern "C" int cnnb200_label_summary(cnnb200_ctx *ctx, int64_t *out3) {
     CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
     CNN_CUDA(cudaMemcpyAsync(h, ctx->b_lab_summary.p, sizeof(ll) * 3, cudaMemcpyDeviceToHost, ctx->stream));
     CNN_CUDA(cudaStreamSynchronize(ctx->stream));
-    out3[0] = h[0]; out3[1] = h[1]; out3[2] = h[2];
+    out3[0] = h[0]; out3[1] = h[1]; out3[2] = ctx->lab_summary_n - h[2];
     return CNNB200_OK;
 }

@@ -441,7 +441,11 @@ comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col
         // software pipeline over the edges of `work`
         int cur_x = -1, cur_m = 0;
         const int *cur_row = nullptr;
+        // an accepted edge settles every other edge of the batch between the same two trees (a row's upper neighbours
+        // mostly sit in a few trees): those are dropped without a check
+        bool dead = false;
         auto consume = [&](const RowFetch &f) {
+            if (__shfl_sync(full, dead, f.src)) return;
             const int x = __shfl_sync(full, ed.x, f.src);
             if (x != cur_x) {
                 if (cur_x >= 0) win_clear(w, cur_row, cur_m, lane);
@@ -454,6 +458,10 @@ comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col
             if (w.span) ok = row_count(f.buf, f.rj, f.mj, lane, w) >= cutoff;
             else ok = warp_common<true>(cur_row, cur_m, f.rj, f.mj, cutoff, lane);
             if (lane == f.src) acc = ok;
+            if (ok) {
+                const int ra = __shfl_sync(full, ri, f.src), rb = __shfl_sync(full, rj, f.src);
+                if (lane != f.src && need && ((ri == ra && rj == rb) || (ri == rb && rj == ra))) dead = true;
+            }
         };
         RowFetch f0, f1, f2;
         fetch_next(f0, work, col_idx, bj, mj, true, lane);
@@ -472,6 +480,9 @@ comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col
         if (cur_x >= 0) win_clear(w, cur_row, cur_m, lane);
         if (acc) uf_union(parent, ri, rj);
         n_acc += __popc(__ballot_sync(full, acc != 0));
+        const int n_dead = __popc(__ballot_sync(full, dead && acc == 0));
+        n_checks -= n_dead;
+        n_skip += n_dead;
     }
     if (lane == 0) {
         if (n_checks) atomicAdd(stats + ST_CHECKS, n_checks);

@@ -517,10 +517,10 @@ __device__ __forceinline__ bool count_accepts(unsigned cnt, unsigned cutoff) {
 __global__ void __launch_bounds__(256)
 counts_sample_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, const unsigned *__restrict__ counts,
                      ll n, unsigned cutoff, const int *__restrict__ parent, int *__restrict__ edge_out,
-                     int *__restrict__ above) {
+                     int *__restrict__ above, int n_samples) {
     ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int j_out = -1;
+    int j_out = -1, j_last = -1;
     if (parent[i] >= 0) {
         const ll rb = row_ptr[i];
         const int m = (int)(row_ptr[i + 1] - rb);
@@ -530,12 +530,19 @@ counts_sample_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col
             if (col_idx[rb + mid] <= (int)i) l = mid + 1; else h = mid;
         }
         above[i] = l;
+        int k_first = m;
         for (int k = l; k < m; ++k) {
             const int j = col_idx[rb + k];
-            if (parent[j] >= 0 && count_accepts(counts[rb + k], cutoff)) { j_out = j; break; }
+            if (parent[j] >= 0 && count_accepts(counts[rb + k], cutoff)) { j_out = j; k_first = k; break; }
+        }
+        // second sample: the LAST accepted entry of the row (the far end of the neighbourhood in the cell-sorted order)
+        for (int k = m - 1; n_samples > 1 && k > k_first; --k) {
+            const int j = col_idx[rb + k];
+            if (parent[j] >= 0 && count_accepts(counts[rb + k], cutoff)) { j_last = j; break; }
         }
     }
-    edge_out[i] = j_out;
+    edge_out[2 * i] = j_out;
+    edge_out[2 * i + 1] = j_last;
 }
 
 __global__ void __launch_bounds__(256)
@@ -546,7 +553,7 @@ counts_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_i
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     unsigned long long n_edges = 0, n_acc = 0, n_looked = 0;
-    constexpr int R = 4;
+    constexpr int R = 8;
     for (ll i0 = warp * 32; i0 < n; i0 += nwarps * 32) {
         const ll il = i0 + lane;
         const int rl = il < n ? ld_parent(parent, (int)il) : -1;
@@ -566,19 +573,19 @@ counts_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_i
         const int total = __shfl_sync(full, incl, 31);
         for (int t0 = 0; t0 < total; t0 += R) {
             int rr[R], r_i[R], jv[R], pjv[R];
-            ll kv[R];
+            unsigned cv[R];  // the counts travel with the columns (same index, coalesced): no dependent load later
 #pragma unroll
             for (int u = 0; u < R; ++u) {
                 const int t = t0 + u;
                 rr[u] = -1;
                 jv[u] = -1;
-                kv[u] = 0;
+                cv[u] = 0xffffffffu;
                 if (t < total) {
                     const int r = __popc(__ballot_sync(full, incl <= t));
                     rr[u] = r;
                     r_i[u] = __shfl_sync(full, rl, r);
                     const ll k = __shfl_sync(full, bl, r) + 32 * (t - __shfl_sync(full, excl, r)) + lane;
-                    if (k < __shfl_sync(full, el, r)) { jv[u] = col_idx[k]; kv[u] = k; }
+                    if (k < __shfl_sync(full, el, r)) { jv[u] = col_idx[k]; cv[u] = counts[k]; }
                 }
             }
 #pragma unroll
@@ -591,7 +598,7 @@ counts_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_i
                 const bool look = cand && pjv[u] != r_i[u];
                 bool acc = false;
                 if (look) {
-                    acc = count_accepts(counts[kv[u]], cutoff);
+                    acc = count_accepts(cv[u], cutoff);
                     if (acc) uf_union(parent, (int)i0 + rr[u], jv[u]);
                 }
                 n_edges += __popc(__ballot_sync(full, cand));
@@ -849,12 +856,12 @@ extern "C" int cnnb200_components_from_counts(cnnb200_ctx *ctx, const uint32_t *
     unsigned long long *stats = (unsigned long long *)ctx->b_stats.p;
     int *parent = ctx->b_parent.as<int>();
     CNN_TRY(cnn_ensure(ctx, ctx->b_above, sizeof(int) * (size_t)n));
-    CNN_TRY(cnn_ensure(ctx, ctx->b_edges, sizeof(int) * (size_t)n));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_edges, sizeof(int) * (size_t)n * 2));
     {
         Span sp(ctx, T_COMP_SAMPLE);
         counts_sample_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, counts, n, cutoff, parent,
-                                                                 ctx->b_edges.as<int>(), ctx->b_above.as<int>());
-        comp_union_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(ctx->b_edges.as<int>(), 0, n, 1, parent);
+                                                                 ctx->b_edges.as<int>(), ctx->b_above.as<int>(), ctx->n_samples);
+        comp_union_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(ctx->b_edges.as<int>(), 0, n, 2, parent);
     }
     {
         Span sp(ctx, T_COMP_FLATTEN);

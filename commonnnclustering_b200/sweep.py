@@ -45,7 +45,7 @@ def fit_sweep(x, radius_cutoffs, cnn_cutoffs, member_cutoff=None, max_clusters=N
     n_r, n_c = len(radius_cutoffs), len(cnn_cutoffs)
     if return_labels:
         if labels_out is None:  # pinned: 8 bytes x N per cell come back over PCIe
-            labels_out = torch.empty((n_r, n_c, n), dtype=torch.int64).pin_memory().numpy()
+            labels_out = torch.empty((n_r, n_c, n), dtype=torch.int64, pin_memory=True).numpy()
         assert labels_out.shape == (n_r, n_c, n) and labels_out.dtype == np.int64
     lab_dev = torch.empty(n, dtype=torch.int64, device=dev)
     summary = Summary()
@@ -64,13 +64,12 @@ def fit_sweep(x, radius_cutoffs, cnn_cutoffs, member_cutoff=None, max_clusters=N
             ctx.components_from_counts(counts)
             ctx.components_labels(1, lab_dev, fresh=True)
             ctx.sort_by_size(lab_dev, member_cutoff, max_clusters)
-            hist = torch.bincount(lab_dev)
             if return_labels:
-                torch.from_numpy(labels_out[ir, ic]).copy_(lab_dev)
-            hist = hist.cpu().numpy()
-            rest = hist[1:]
-            summary.append(Record(n, r, c, member_cutoff, max_clusters, int(np.count_nonzero(rest)),
-                                  (int(rest.max()) if rest.size else 0) / n, int(hist[0]) / n,
+                torch.from_numpy(labels_out[ir, ic]).copy_(lab_dev, non_blocking=True)
+            # the record's three numbers come out of the device-side size sort: no pass over the labels
+            n_kept, n_largest, n_noise = ctx.label_summary()
+            summary.append(Record(n, r, c, member_cutoff, max_clusters, n_kept, n_largest / n, n_noise / n,
                                   t_shared + time.perf_counter() - t0))
         del counts
+    torch.cuda.synchronize(dev)  # the last label copies
     return (labels_out if return_labels else None), summary

@@ -30,6 +30,10 @@ t0 = time.perf_counter()
 _, _ = sweep.fit_sweep(xd, RS, CS, MC, ctx=ctx, return_labels=False)
 torch.cuda.synchronize()
 t_sweep_nolabels = time.perf_counter() - t0
+t0 = time.perf_counter()
+_, _ = sweep.fit_sweep(xd, RS, CS, MC, ctx=ctx, labels_out=labels)     # caller's (page-locked) label array reused
+torch.cuda.synchronize()
+t_sweep_prealloc = time.perf_counter() - t0
 
 # the same 64 cells as independent fits (radius search and early-exit checks repeated per cell)
 single = torch.empty(n, dtype=torch.int64, device="cuda")
@@ -62,6 +66,7 @@ print(json.dumps({
     "workload": f"C5: 8x8 sweep on MD-like 3-D N={n}, member_cutoff={MC}; isolate (r=0.100, c=2), recluster children >= 1000 "
                 "points at (0.063, 20), reel",
     "cells": len(RS) * len(CS), "sweep_s": t_sweep, "sweep_s_without_label_copies": t_sweep_nolabels,
+    "sweep_s_labels_into_preallocated_array": t_sweep_prealloc,
     "independent_fits_s": t_fits, "cells_equal_to_independent_fits": equal,
     "point_fits_per_s_sweep": len(RS) * len(CS) * n / t_sweep, "point_fits_per_s_independent": len(RS) * len(CS) * n / t_fits,
     "hierarchy_s": t_hier, "children": n_children, "children_reclustered": n_reclustered,

@@ -1,7 +1,7 @@
 """Distance-matrix input ("distances" recipe): the thresholding kernel against the HBM roofline, the whole fit from a
 device-resident and from a host matrix, and the oracle's thresholding + BFS on the host beside it.
 
-    python scripts/distmat_bench.py [N] > gpurun_out/distmat.json
+    python tests/checks/distmat_bench.py [N] > gpurun_out/distmat.json
 
 The matrix holds the Euclidean distances of the C2 generator's first N points (N = 40000: 12.8 GB, larger than L2)."""
 import json
@@ -9,7 +9,7 @@ import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 
@@ -23,8 +23,8 @@ xd = torch.from_numpy(x).cuda()
 dm = torch.cdist(xd, xd)                      # f64 [n, n] on the device (input preparation, not timed)
 dm = torch.minimum(dm, dm.T).contiguous()     # exactly symmetric
 torch.cuda.synchronize()
-peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))).get("hbm_gbs", 6554.2) \
-    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6554.2
+peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "..", "MEASURED_PEAKS.json"))).get("hbm_gbs", 6554.2) \
+    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "..", "MEASURED_PEAKS.json")) else 6554.2
 
 ctx = _lib.Context(0)
 lab = torch.zeros(n, dtype=torch.int64, device="cuda")

@@ -1,6 +1,6 @@
 """First contact with the GPU: parity on small sets, then C2 timing by stage."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from commonnnclustering_b200 import _lib, datasets
 from oracle import port

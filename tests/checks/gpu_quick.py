@@ -1,7 +1,7 @@
 """Quick GPU check: parity on a few sets + C2 stage timings (for kernel iteration).
 SWEEP_VAR=<CNNB200_* environment variable> VALUES=a,b,c runs the C2 fit once per value (fresh context each)."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from commonnnclustering_b200 import _lib, datasets

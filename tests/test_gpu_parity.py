@@ -267,6 +267,36 @@ def test_distance_matrix_neighbour_sets(ctx):
         ctx.neighbours_from_distances(np.zeros((3, 3), dtype=np.float32), 1.0)
 
 
+def test_new_input_paths_edge_cases(ctx):
+    # distance matrix with no neighbours at all (not even the diagonal), a negative radius, a single point
+    dm = np.full((40, 40), np.inf)
+    ctx.neighbours_from_distances(dm, 1.0)
+    assert ctx.neighbours_info()[:2] == (40, 0)
+    assert ctx.neighbours_sort_rows() is False
+    lab = np.ones(40, dtype=np.int64)
+    ctx.fit(1, 2, 1, lab)
+    assert not lab.any()
+    ctx.neighbours_from_distances(np.zeros((40, 40)), -1.0)
+    assert ctx.neighbours_info()[1] == 0
+    ctx.neighbours_from_distances(np.zeros((1, 1)), 0.0)
+    assert ctx.neighbours_info()[:2] == (1, 1)
+    with pytest.raises(ValueError):
+        ctx.neighbours_from_distances(np.zeros((2, 2)), float("nan"))
+    # periodic cell list asked for explicitly on a handful of points, on duplicates, and with r = 0
+    rng = np.random.default_rng(1)
+    for n, r in ((1, 0.1), (7, 0.2), (50, 0.0), (300, 0.15)):
+        x = np.ascontiguousarray(rng.random((n, 2)) * 3.0 - 1.0)
+        if n == 50:
+            x[25:] = x[:25]          # exact duplicates: distance 0 <= 0
+        bounds = np.array([1.0, 1.5])
+        ctx.set_periodic_bounds(bounds)
+        want = port.neighbours_periodic(x, r * r, bounds)
+        ctx.neighbours_from_points(x, r * r, metric="euclidean_periodic_r", method="grid")
+        got = ctx.neighbours_export()
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+
+
 def test_sort_rows_on_arrival(ctx):
     # unsorted CSR / padded input: sorted once on the device; sorted input is left alone; a borrowed device CSR is
     # never written to

@@ -425,8 +425,10 @@ def run_b200(args):
         "config": {"workload": w["name"], "l2_flush_between_steps": True, "parallelism": f"row-sharded x{world}",
                    "n_points": n, "n_dim": d, "nnz": nnz, "max_degree": max_deg},
         "e2e": {"value": n * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes),
-                "d2h_bytes_per_step": int(n * 8), "ms_per_step": 1e3 * e2e_s / args.steps,
-                "call": "cnnb200_fit_points (C-ABI, pinned host buffers)"},
+                "d2h_bytes_per_step": int(n * 8) * world, "ms_per_step": 1e3 * e2e_s / args.steps,
+                "call": "cnnb200_fit_points (C-ABI, pinned host buffers)" if world == 1 else
+                        "dist.ShardedFit.fit_points over the C-ABI, pinned host buffers: every rank uploads 1/G of the "
+                        "coordinates, NCCL all-gather over NVLink, every rank reads the full labels back"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": ({k: top[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")} | {

@@ -172,8 +172,30 @@ class ShardedFit:
             torch.from_numpy(labels).copy_(lab_dev)  # D2H (synchronises)
         return n_clusters
 
+    def upload_points(self, x):
+        """Host coordinates (every rank sees the same array) -> replicated device copy.  Each rank uploads only its
+        1/G of the rows over its own PCIe link and the slices are all-gathered over NVLink: G concurrent uploads of
+        the whole array compete for the host's memory bandwidth (C2 on 8 GPUs: 2.96 ms end to end that way)."""
+        from . import _lib
+
+        G, n, d = self.world, x.shape[0], x.shape[1]
+        key = (x.ctypes.data, x.nbytes)
+        if key not in self._registered:          # page-locked in place, once per array
+            self._registered[key] = _lib.host_register(x)
+        rows = (n + G - 1) // G
+        xd = torch.empty((rows * G, d), dtype=torch.float64, device=self.device)
+        r0 = min(self.rank * rows, n)
+        r1 = min(r0 + rows, n)
+        if r1 > r0:
+            xd[r0:r1].copy_(torch.from_numpy(x[r0:r1]), non_blocking=True)
+        mine = xd[self.rank * rows:(self.rank + 1) * rows]
+        dist.all_gather_into_tensor(xd, mine, group=self.group)    # in place: `mine` is this rank's slice of `xd`
+        return xd[:n]
+
     def fit_points(self, x, radius_cutoff, n_member_cutoff, similarity_cutoff, labels, current_start=1,
                    metric="euclidean_r", sort_by_size=True, member_cutoff=None, max_clusters=None, exchange=False, **_):
+        if isinstance(x, np.ndarray) and self.world > 1 and x.flags.c_contiguous and x.dtype == np.float64:
+            x = self.upload_points(x)
         bounds = self.neighbours_from_points(x, radius_cutoff, metric, exchange=exchange)
         return self.fit(bounds, n_member_cutoff, similarity_cutoff, labels, current_start, sort_by_size,
                         member_cutoff, max_clusters)

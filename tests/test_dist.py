@@ -97,7 +97,7 @@ def test_sharded_plumbing_gloo_world2():
 def test_sharded_fit_two_gpus_equals_single_gpu():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    script = os.path.join(ROOT, "scripts", "dist_check.py")
+    script = os.path.join(ROOT, "tests", "checks", "dist_check.py")
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", "29777", script],
                          capture_output=True, text=True, cwd=ROOT, timeout=900)

@@ -47,6 +47,26 @@ def test_builder_default_recipe():
     assert isinstance(f._neighbours_getter, _types.NeighboursGetterLookup) and f._neighbours_getter.is_selfcounting
 
 
+def test_builder_reference_recipes():
+    """All four registered recipes of the reference (recipes.py:316-358) build under their own names, with the
+    parameters the reference's fitters would derive (_fit.pyx:129-161)."""
+    for name in ("coordinates", "distances", "neighbourhoods", "sorted_neighbourhoods"):
+        assert name in recipes.REGISTERED_RECIPES
+    f = recipes.Builder("distances").make_component("fitter")
+    assert isinstance(f._neighbours_getter.metric, _types.MetricPrecomputed)
+    p = f.make_parameters(0.3, 5, 1)     # precomputed metric: radius unchanged; self-counting getter
+    assert (p.radius_cutoff, p.similarity_cutoff, p.n_member_cutoff) == (0.3, 7, 6)
+    dm = _types.InputDataComponents(np.array([[0.0, 2.0], [2.0, 0.0]]))
+    assert _types.MetricPrecomputed().calc_distance(0, 1, dm) == 2.0
+    f = recipes.Builder("neighbourhoods").make_component("fitter")
+    assert isinstance(f._neighbours_getter, _types.NeighboursGetterLookup) and not f._neighbours_getter.is_sorted
+    f = recipes.Builder("sorted_neighbourhoods").make_component("fitter")
+    assert f._neighbours_getter.is_sorted
+    assert _types.NeighboursGetterLookup().is_sorted is False      # the reference's default (_types.pyx:1794)
+    p = f.make_parameters(0.3, 5, 1)     # no metric: radius unchanged
+    assert (p.radius_cutoff, p.similarity_cutoff, p.n_member_cutoff) == (0.3, 7, 6)
+
+
 def test_prepare_points_from_parts():
     # reference test/unit/test_hooks.py
     (a,), kw = recipes.prepare_points_from_parts([[0, 0], [1, 1]])

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(GF_WARPS * 32, 4)
 grid_rows_f32_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, ll n,
                      const int *__restrict__ cell_sorted, const int *__restrict__ cell_start, GridDesc g, double rc,
                      FilterParams fp, int *__restrict__ deg, const ll *__restrict__ goff, int *__restrict__ out,
-                     ll p_begin, ll p_end, unsigned long long *stats) {
+                     ll p_begin, ll p_end, unsigned long long *stats, int qpw) {
     __shared__ float4 s_q[GF_WARPS][32];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -249,9 +249,11 @@ grid_rows_f32_kernel(const double *__restrict__ xs, const float4 *__restrict__ x
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     unsigned long long n_recheck = 0;
-    for (ll p0 = p_begin + warp * 32; p0 < p_end; p0 += nwarps * 32) {
+    // qpw (<= 32) queries per warp tile: fewer when there are few points with long candidate lists (C1: 10^4 points,
+    // 10^3 neighbours each), so that the tiles still cover all SMs
+    for (ll p0 = p_begin + warp * qpw; p0 < p_end; p0 += nwarps * qpw) {
         const ll p = p0 + lane;
-        const bool pvalid = p < p_end;
+        const bool pvalid = lane < qpw && p < p_end;
         const int cid = pvalid ? cell_sorted[p] : -1;
         const int my_row = pvalid ? cid / g.dims[0] : -1, my_cx = pvalid ? cid - my_row * g.dims[0] : 0;
         const float4 my4 = pvalid ? xf[p] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -467,14 +469,17 @@ static bool filter_params(const cnnb200_ctx *ctx, FilterParams *fp) {
 
 template <int D, bool SQRT>
 static int launch_rows_f32(cnnb200_ctx *ctx, ll pb, ll pe, int mode, FilterParams fp, int *deg, const ll *offsets, int *out) {
-    int blocks = (int)((pe - pb + GF_WARPS * 32 - 1) / (GF_WARPS * 32));
+    int qpw = 32;
+    while (qpw > 8 && (pe - pb) / qpw < (ll)ctx->sm_count * 16) qpw >>= 1;
+    if (const char *e = getenv("CNNB200_QPW")) qpw = atoi(e) >= 1 && atoi(e) <= 32 ? atoi(e) : qpw;
+    int blocks = (int)((pe - pb + GF_WARPS * qpw - 1) / (GF_WARPS * qpw));
     int cap = ctx->sm_count * 48;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     unsigned long long *recheck = (unsigned long long *)(ctx->b_tmp2.as<char>() + 40);
     CNN_CUDA(cudaMemsetAsync(recheck, 0, sizeof(unsigned long long), ctx->stream));
 #define GF_ARGS ctx->b_xs.as<double>(), ctx->b_xf.as<float4>(), ctx->grid_n, ctx->b_cell_id_sorted.as<int>(),      \
-                ctx->b_cell_start.as<int>(), ctx->grid, ctx->grid_rc, fp, deg, offsets, out, pb, pe, recheck
+                ctx->b_cell_start.as<int>(), ctx->grid, ctx->grid_rc, fp, deg, offsets, out, pb, pe, recheck, qpw
     if (mode == 0) grid_rows_f32_kernel<D, SQRT, 0><<<blocks, GF_WARPS * 32, 0, ctx->stream>>>(GF_ARGS);
     else if (mode == 1) grid_rows_f32_kernel<D, SQRT, 1><<<blocks, GF_WARPS * 32, 0, ctx->stream>>>(GF_ARGS);
     else grid_rows_f32_kernel<D, SQRT, 2><<<blocks, GF_WARPS * 32, 0, ctx->stream>>>(GF_ARGS);

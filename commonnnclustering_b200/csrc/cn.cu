@@ -128,15 +128,16 @@ __global__ void __launch_bounds__(256)
 comp_sample_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll row_begin, ll row_end,
                    int cutoff, int n_samples, int *parent, int *__restrict__ edge_out,
                    int *__restrict__ above, unsigned long long *stats, int fuse_union,
-                   const int2 *__restrict__ wrows, const int *__restrict__ wcnt) {
+                   const int2 *__restrict__ wrows, const int *__restrict__ wcnt, int rpw) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     unsigned long long n_checks = 0, n_acc = 0;
-    for (ll i0 = row_begin + warp * 32; i0 < row_end; i0 += nwarps * 32) {
+    // rpw (<= 32) rows per warp tile: fewer when the rows are few and long, so that every SM still gets tiles
+    for (ll i0 = row_begin + warp * rpw; i0 < row_end; i0 += nwarps * rpw) {
         const ll i = i0 + lane;
-        const bool valid = i < row_end;
+        const bool valid = lane < rpw && i < row_end;
         const bool core_i = valid && parent[i] >= 0;
         const ll rb = valid ? row_ptr[i] : 0;
         const int m = valid ? (int)(row_ptr[i + 1] - rb) : 0;
@@ -796,12 +797,14 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         Span sp(ctx, T_COMP_SAMPLE);
         ll slots = rows * ns;
         CNN_TRY(cnn_ensure(ctx, ctx->b_edges, sizeof(int) * (size_t)slots));
-        int sblocks = (int)((rows + 255) / 256);
+        int rpw = 32;
+        while (rpw > 8 && rows / rpw < (ll)ctx->sm_count * 16) rpw >>= 1;
+        int sblocks = (int)((rows + 8 * rpw - 1) / (8 * rpw));
         if (sblocks > ctx->sm_count * 32) sblocks = ctx->sm_count * 32;
         comp_sample_kernel<<<sblocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, cutoff, ns, parent,
                                                     ctx->b_edges.as<int>(), above, stats, ctx->fuse_union ? 1 : 0,
                                                     ctx->comp_packed ? ctx->b_wrows.as<int2>() : nullptr,
-                                                    ctx->comp_packed ? ctx->b_wcnt.as<int>() : nullptr);
+                                                    ctx->comp_packed ? ctx->b_wcnt.as<int>() : nullptr, rpw);
         if (!ctx->fuse_union)
             comp_union_kernel<<<cnn_blocks(rows, 256), 256, 0, st>>>(ctx->b_edges.as<int>(), row_begin, rows, ns, parent);
         CNN_LAUNCHED(ctx, ctx->fuse_union ? 1 : 2);

@@ -15,8 +15,8 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--fmad=false",          # distances must round exactly like the reference (no FMA contraction)
-    "-shared",
 ]
+OBJ = os.path.join(HERE, "build")
 
 
 def sources():
@@ -31,15 +31,30 @@ def stale() -> bool:
     return any(os.path.getmtime(p) > t for p in deps)
 
 
+def _headers():
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """One object per translation unit (only the stale ones are recompiled, in parallel), then one link."""
     if not force and not stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    os.makedirs(OBJ, exist_ok=True)
+    base = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += sources() + ["-o", LIB]
-    subprocess.run(cmd, check=True)
+        base += ["-Xptxas", "-v"]
+    t_hdr = max(os.path.getmtime(p) for p in _headers() + [__file__])
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or verbose or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), t_hdr):
+            jobs.append((src, subprocess.Popen(base + ["-c", src, "-o", obj])))
+    failed = [src for src, p in jobs if p.wait() != 0]
+    if failed:
+        raise RuntimeError("nvcc failed for " + ", ".join(os.path.basename(f) for f in failed))
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", LIB], check=True)
     return LIB
 
 

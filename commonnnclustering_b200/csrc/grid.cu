@@ -209,149 +209,289 @@ grid_rows_kernel(const double *__restrict__ xs, ll n, const int *__restrict__ ce
     }
 }
 
-// ---- K2, fp32 filter form (the default single-pass kernel) ------------------------------------------------
-// Same tiles as above (warp = 32 consecutive cell-sorted points).  A GROUP is a run of lanes whose points lie in
-// the same x-row of cells and at most GF_XSPAN cells apart; its candidate list is the union of the 3^D windows of
+// ---- K2, fp32 filter form (the default) ------------------------------------------------------------------
+// Same tiles as above (a warp = up to 32 consecutive cell-sorted points).  A GROUP is a run of lanes whose points lie
+// in the same x-row of cells and at most GF_XSPAN cells apart; its candidate list is the union of the 3^D windows of
 // its cells (still 3^(D-1) contiguous index runs), so that neighbouring sparse cells are served as one well-filled
-// group.  Every lane of the group owns ONE query; the candidates of a run go through shared memory 32 at a time
-// (one coalesced float4 per lane: cell-local fp32 coordinates) and come back as broadcasts; a lane appends its
-// hits to its own (gapped) row -- candidates ascend, so rows come out sorted.  No votes, no ranking.
-//   * The test is an fp32 FILTER with a proven error bound: d2 <= R - eps is a neighbour, d2 > R + eps is not, and
-//     the (rare) pairs in between are decided by the reference's own f64 expression on the original coordinates
-//     (`within`), so the neighbour sets are exactly those of the f64 kernel.  A lane tracks the smallest |d2 - R| it
-//     meets in a chunk and, if that lies inside the band, redoes its chunk with the exact test for the borderline
-//     candidates (the row must stay ascending) -- no branch per candidate in the fast loop.
-//   * fp32 is accurate enough because all coordinates are relative to a nearby cell origin (|value| < 16h):
-//     every coordinate difference carries an error below delta = h * 2^-18, hence
-//     |d2_fp32 - d2| <= 2*sqrt(3)*delta*sqrt(d2) + 3*delta^2 + 2^-22*d2 < eps = h*r*2^-16 + h^2*2^-34 + R*2^-21.
-// Per candidate the loop issues ~13 instructions for up to 32 distance tests (one LDS.128, 8 FP32, compare, store)
-// instead of ~47 per 32 tests (3 LDG.64, 9 FP64, ballot ranking, scattered store) in the f64 form.
+// group.  Every lane of the group owns ONE query; the candidates of a run go through shared memory 32 at a time (one
+// coalesced float4 per lane) and come back as broadcasts.
+//
+// Three kernels share the group structure (gf_next_group), so nothing about it is stored:
+//   grid_plan_kernel   words of hit masks every tile will write (-> prefix = the tile's offset in the mask buffer)
+//   grid_mask_kernel   the distance tests: per (query, 32-candidate chunk) ONE 32-bit hit mask, written as a coalesced
+//                      row of `gp` words per chunk (gp = group size rounded up to a power of two), plus deg[]
+//   grid_expand_kernel after the degree scan: masks -> ascending column indices, whole rows at a time through a
+//                      shared-memory row buffer, so that every store instruction writes 32 consecutive words
+// The hits therefore reach HBM once (4*nnz bytes, coalesced) plus ~100 bytes of masks per point, instead of 4-byte
+// scattered stores into gapped rows that a compaction pass had to read back (round 1: 1.15 GB of traffic, now ~0.5).
+//
+// The test is an fp32 FILTER with a proven error bound, in the expanded form |c|^2 - 2 q.c <= R - |q|^2 (3 FMA per
+// pair instead of 6 operations): coordinates are taken relative to the CENTRE of the group's candidate box (|x| <= 3.5h,
+// |y|,|z| <= 1.5h with h the cell edge), so the cancellation error stays below 2^-14 h^2 (derivation in DESIGN.md);
+// pairs with |t| <= band (t = computed w - T) are decided by the reference's own f64 expression on the original
+// coordinates (`within`), so the neighbour sets are exactly those of the f64 kernel.  A lane tracks the smallest |t|
+// it meets in a chunk and, if that lies inside the band, redoes the chunk with the exact test for those pairs.
+// Per candidate the loop issues 7 instructions for up to 32 tests: LDS.128, 3 FFMA, FADD, FMNMX, SHF (sign bit -> mask).
 #define GF_WARPS 8
 #define GF_XSPAN 3            // a group spans at most GF_XSPAN + 1 cells along x
 
 struct FilterParams {
-    float t_lo, t_hi;  // definite hit: d2 <= t_lo; definite miss: d2 > t_hi
-    float r2, band;    // |d2 - r2| <= band for every d2 in (t_lo, t_hi] (computed in fp32, rounded outwards)
+    float r2;      // R (squared radius) rounded to fp32
+    float band;    // |t| <= band: the pair is decided by the exact f64 test
+    double R;      // the threshold centre in f64 (per-lane T = fl32(R - |q|^2))
 };
 
-// MODE as for grid_rows_kernel: 0 = count pass (deg[] only), 1 = fill pass (rows at goff[] = row_ptr[]),
-// 2 = single pass into gapped rows (hits at goff[], deg[] from the same pass)
-template <int D, bool SQRT, int MODE>
+struct GfGroup {
+    int a, gsz, lg;            // first lane, number of lanes, log2 of the mask row width gp
+    int nruns, nch;            // candidate runs, chunks of 32 candidates over all runs
+    int cx0, cx1, cy, cz;      // candidate cells along x; the queries' cell row
+    bool use_b;                // the run straddles a period boundary of lattice A: take x from lattice B
+    int rs, re;                // per lane (lane < nruns): bounds of run `lane`
+    int ry, rz;                // per lane: cell row of run `lane`
+};
+
+// next group of the tile: the run of lanes, starting at the first open one, whose points lie in the same x-row of cells
+// and at most GF_XSPAN cells apart (a query also meets candidates outside its own window; the test is exact, that only
+// costs time).  Warp-uniform except rs/re/ry/rz.
+template <int D>
+__device__ __forceinline__ void gf_next_group(unsigned &todo, int cid, int my_row, int my_cx, const GridDesc &g,
+                                              const int *__restrict__ cell_start, int lane, GfGroup &G) {
+    const unsigned full = 0xffffffffu;
+    G.a = __ffs(todo) - 1;
+    const int c = __shfl_sync(full, cid, G.a);
+    const int row_a = c / g.dims[0], cx = c - row_a * g.dims[0];
+    const unsigned grp = __ballot_sync(full, my_row == row_a && my_cx - cx <= GF_XSPAN) & todo;
+    todo &= ~grp;
+    G.gsz = __popc(grp);
+    G.lg = G.gsz <= 1 ? 0 : 32 - __clz(G.gsz - 1);
+    const int cx_max = __shfl_sync(full, my_cx, G.a + G.gsz - 1);
+    G.cy = row_a % g.dims[1];
+    G.cz = row_a / g.dims[1];
+    G.cx0 = max(cx - 1, 0);
+    G.cx1 = min(cx_max + 1, g.dims[0] - 1);
+    const int y0 = D > 1 ? max(G.cy - 1, 0) : 0, y1 = D > 1 ? min(G.cy + 1, g.dims[1] - 1) : 0;
+    const int z0 = D > 2 ? max(G.cz - 1, 0) : 0, z1 = D > 2 ? min(G.cz + 1, g.dims[2] - 1) : 0;
+    G.use_b = (G.cx0 >> 4) != (G.cx1 >> 4);
+    const int ny = y1 - y0 + 1;
+    G.nruns = ny * (z1 - z0 + 1);
+    G.rs = G.re = 0;
+    G.ry = G.cy;
+    G.rz = G.cz;
+    if (lane < G.nruns) {
+        G.ry = y0 + lane % ny;
+        G.rz = z0 + lane / ny;
+        const int cb = (G.rz * g.dims[1] + G.ry) * g.dims[0];
+        G.rs = cell_start[cb + G.cx0];
+        G.re = cell_start[cb + G.cx1 + 1];
+    }
+    G.nch = __reduce_add_sync(full, (unsigned)((G.re - G.rs + 31) >> 5));
+}
+
+__device__ __forceinline__ void gf_tile_header(const int *__restrict__ cell_sorted, const GridDesc &g, ll p, bool pvalid,
+                                               int &cid, int &my_row, int &my_cx) {
+    cid = pvalid ? cell_sorted[p] : -1;
+    my_row = pvalid ? cid / g.dims[0] : -1;
+    my_cx = pvalid ? cid - my_row * g.dims[0] : 0;
+}
+
+// words of hit masks per tile (tile t = points [p_begin + t*qpw, +qpw))
+template <int D>
+__global__ void __launch_bounds__(256)
+grid_plan_kernel(const int *__restrict__ cell_sorted, const int *__restrict__ cell_start, GridDesc g, ll p_begin, ll p_end,
+                 int qpw, ll n_tiles, int *__restrict__ tile_words) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const ll t = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    if (t > n_tiles) return;
+    if (t == n_tiles) { if (lane == 0) tile_words[t] = 0; return; }
+    const ll p = p_begin + t * qpw + lane;
+    const bool pvalid = lane < qpw && p < p_end;
+    int cid, my_row, my_cx;
+    gf_tile_header(cell_sorted, g, p, pvalid, cid, my_row, my_cx);
+    unsigned todo = __ballot_sync(full, pvalid);
+    int words = 0;
+    while (todo) {
+        GfGroup G;
+        gf_next_group<D>(todo, cid, my_row, my_cx, g, cell_start, lane, G);
+        words += G.nch << G.lg;
+    }
+    if (lane == 0) tile_words[t] = words;
+}
+
+template <int D, bool SQRT>
 __global__ void __launch_bounds__(GF_WARPS * 32, 4)
-grid_rows_f32_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, ll n,
-                     const int *__restrict__ cell_sorted, const int *__restrict__ cell_start, GridDesc g, double rc,
-                     FilterParams fp, int *__restrict__ deg, const ll *__restrict__ goff, int *__restrict__ out,
-                     ll p_begin, ll p_end, unsigned long long *stats, int qpw) {
+grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, ll n, const int *__restrict__ cell_sorted,
+                 const int *__restrict__ cell_start, GridDesc g, double rc, FilterParams fp, int *__restrict__ deg,
+                 const ll *__restrict__ tile_off, unsigned *__restrict__ masks, ll p_begin, ll p_end, ll n_tiles,
+                 unsigned long long *stats, int qpw) {
     __shared__ float4 s_q[GF_WARPS][32];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float4 *qf = s_q[wid];
-    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
-    ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
-    unsigned long long n_recheck = 0;
-    // qpw (<= 32) queries per warp tile: fewer when there are few points with long candidate lists (C1: 10^4 points,
-    // 10^3 neighbours each), so that the tiles still cover all SMs
-    for (ll p0 = p_begin + warp * qpw; p0 < p_end; p0 += nwarps * qpw) {
-        const ll p = p0 + lane;
+    const ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    unsigned n_recheck = 0;
+    const float hh = 0.5f * (float)g.h;
+    for (ll t = warp; t < n_tiles; t += nwarps) {
+        const ll p = p_begin + t * qpw + lane;
         const bool pvalid = lane < qpw && p < p_end;
-        const int cid = pvalid ? cell_sorted[p] : -1;
-        const int my_row = pvalid ? cid / g.dims[0] : -1, my_cx = pvalid ? cid - my_row * g.dims[0] : 0;
+        int cid, my_row, my_cx;
+        gf_tile_header(cell_sorted, g, p, pvalid, cid, my_row, my_cx);
         const float4 my4 = pvalid ? xf[p] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const ll my_base = (MODE != 0 && pvalid) ? goff[p] : 0;
+        ll woff = tile_off[t];
         unsigned todo = __ballot_sync(full, pvalid);
         while (todo) {
-            // next group: the run of lanes, starting at the first open one, whose points lie in the same x-row
-            // of cells and at most GF_XSPAN cells apart.  They share one candidate list, the union of their
-            // 3^D windows (a query also meets candidates outside its own window; the distance test is exact,
-            // so that only costs time) -- neighbouring sparse cells are served as ONE well-filled group.
-            const int a = __ffs(todo) - 1;
-            const int c = __shfl_sync(full, cid, a);
-            const int row_a = c / g.dims[0], cx = c - row_a * g.dims[0];
-            const unsigned grp = __ballot_sync(full, my_row == row_a && my_cx - cx <= GF_XSPAN) & todo;
-            todo &= ~grp;
-            const int gsz = __popc(grp);
-            const int jme = lane - a;  // my query slot when I belong to the group
-            const bool mine = jme >= 0 && jme < gsz;
-            const int cx_max = __shfl_sync(full, my_cx, a + gsz - 1);
-            const int cy = row_a % g.dims[1];
-            const int cz = row_a / g.dims[1];
-            const int x0 = max(cx - 1, 0), x1 = min(cx_max + 1, g.dims[0] - 1);
-            const int y0 = D > 1 ? max(cy - 1, 0) : 0, y1 = D > 1 ? min(cy + 1, g.dims[1] - 1) : 0;
-            const int z0 = D > 2 ? max(cz - 1, 0) : 0, z1 = D > 2 ? min(cz + 1, g.dims[2] - 1) : 0;
-            const bool use_b = (x0 >> 4) != (x1 >> 4);  // the run straddles a period boundary of lattice A
-            // run bounds: one run per lane, fetched together
-            const int ny = y1 - y0 + 1, nruns = ny * (z1 - z0 + 1);
-            int rs = 0, re = 0;
+            GfGroup G;
+            gf_next_group<D>(todo, cid, my_row, my_cx, g, cell_start, lane, G);
+            const int jme = lane - G.a;  // my query slot when I belong to the group
+            const bool mine = jme >= 0 && jme < G.gsz;
+            const int gp = 1 << G.lg;
+            // shifts that move cell-local coordinates to the centre of the group's candidate box
+            const int lat = G.use_b ? ((G.cx0 + 8) & ~15) - 8 : (G.cx0 & ~15);
+            const double xc = __dadd_rn(cell_origin(g.lo[0], g.h, G.cx0), __dmul_rn(0.5 * (double)(G.cx1 - G.cx0 + 1), g.h));
+            const float shx = (float)__dsub_rn(cell_origin(g.lo[0], g.h, lat), xc);
             float shy = 0.f, shz = 0.f;
-            if (lane < nruns) {
-                const int ry = y0 + lane % ny, rz = z0 + lane / ny;
-                const int cb = (rz * g.dims[1] + ry) * g.dims[0];
-                rs = cell_start[cb + x0];
-                re = cell_start[cb + x1 + 1];
-                // candidate coordinates of this run, moved to the query cell's origin
-                if (D > 1) shy = (float)__dsub_rn(cell_origin(g.lo[1], g.h, ry), cell_origin(g.lo[1], g.h, cy));
-                if (D > 2) shz = (float)__dsub_rn(cell_origin(g.lo[2], g.h, rz), cell_origin(g.lo[2], g.h, cz));
+            if (lane < G.nruns) {
+                if (D > 1) shy = (float)__dsub_rn(__dsub_rn(cell_origin(g.lo[1], g.h, G.ry), cell_origin(g.lo[1], g.h, G.cy)), 0.5 * g.h);
+                if (D > 2) shz = (float)__dsub_rn(__dsub_rn(cell_origin(g.lo[2], g.h, G.rz), cell_origin(g.lo[2], g.h, G.cz)), 0.5 * g.h);
             }
+            // my query relative to the same centre; lanes outside the group carry a query that never hits and is
+            // never borderline (q = 0, T = -1e30: t = |c|^2 + 1e30)
+            const float qx = (G.use_b ? my4.y : my4.x) + shx;
+            const float qy = D > 1 ? my4.z - hh : 0.f, qz = D > 2 ? my4.w - hh : 0.f;
+            const float q2x = mine ? -2.f * qx : 0.f, q2y = mine ? -2.f * qy : 0.f, q2z = mine ? -2.f * qz : 0.f;
+            const double qn = __dadd_rn(__dadd_rn(__dmul_rn((double)qx, (double)qx), __dmul_rn((double)qy, (double)qy)),
+                                        __dmul_rn((double)qz, (double)qz));
+            const float T = mine ? (float)__dsub_rn(fp.R, qn) : -1e30f;
             int cnt = 0;
-            // ---- big group: one query per lane; the chunk's candidates go through shared memory and
-            // are read back as broadcasts.  No votes, no ranking: a lane appends to its own row.
-            // lanes outside the group carry a query parked far away: it never hits and never is borderline
-            const float qx = mine ? (use_b ? my4.y : my4.x) : 1e30f, qy = my4.z, qz = my4.w;
-            int *const orow = out + my_base;
-            for (int r = 0; r < nruns; ++r) {
-                const int s = __shfl_sync(full, rs, r), e = __shfl_sync(full, re, r);
+            for (int r = 0; r < G.nruns; ++r) {
+                const int s = __shfl_sync(full, G.rs, r), e = __shfl_sync(full, G.re, r);
                 const float sy = __shfl_sync(full, shy, r), sz = __shfl_sync(full, shz, r);
                 float4 c4 = s + lane < e ? xf[s + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int q0 = s; q0 < e; q0 += 32) {
                     __syncwarp();
-                    qf[lane] = make_float4(use_b ? c4.y : c4.x, c4.z + sy, c4.w + sz, 0.f);
+                    {
+                        const float cx = (G.use_b ? c4.y : c4.x) + shx, cy = D > 1 ? c4.z + sy : 0.f, cz = D > 2 ? c4.w + sz : 0.f;
+                        qf[lane] = make_float4(cx, cy, cz, fmaf(cz, cz, fmaf(cy, cy, cx * cx)));
+                    }
                     __syncwarp();
                     if (q0 + 32 + lane < e) c4 = xf[q0 + 32 + lane];  // next chunk's candidates, in flight during this one
                     const int nc = min(32, e - q0);
-                    const int cnt0 = cnt;
-                    float near = INFINITY;  // smallest |d2 - R| this lane meets in the chunk
-#pragma unroll 4
+                    unsigned m = 0;
+                    float near = INFINITY;  // smallest |t| this lane meets in the chunk
+#pragma unroll 8
                     for (int tq = 0; tq < nc; ++tq) {
                         const float4 cv = qf[tq];
-                        const float dx = qx - cv.x;
-                        float s2 = dx * dx;
-                        if (D > 1) { const float dy = qy - cv.y; s2 = fmaf(dy, dy, s2); }
-                        if (D > 2) { const float dz = qz - cv.z; s2 = fmaf(dz, dz, s2); }
-                        near = fminf(near, fabsf(s2 - fp.r2));
-                        if (s2 <= fp.t_lo) {
-                            if (MODE != 0) orow[cnt] = q0 + tq;
-                            ++cnt;
-                        }
+                        const float w = fmaf(q2z, cv.z, fmaf(q2y, cv.y, fmaf(q2x, cv.x, cv.w)));
+                        const float tt = w - T;
+                        near = fminf(near, fabsf(tt));
+                        m = __funnelshift_l(__float_as_uint(tt), m, 1);  // sign bit of t: candidate tq ends up at bit nc-1-tq
                     }
+                    m = __brev(m) >> (32 - nc);
                     if (near <= fp.band) {
-                        // rare: a pair of this lane is borderline.  Redo the lane's chunk, deciding such pairs
-                        // with the reference's own f64 test (the row must stay ascending, hence the redo).
-                        cnt = cnt0;
+                        // rare: a pair of this lane is borderline -- decide it with the reference's own f64 test
                         for (int tq = 0; tq < nc; ++tq) {
                             const float4 cv = qf[tq];
-                            const float dx = qx - cv.x;
-                            float s2 = dx * dx;
-                            if (D > 1) { const float dy = qy - cv.y; s2 = fmaf(dy, dy, s2); }
-                            if (D > 2) { const float dz = qz - cv.z; s2 = fmaf(dz, dz, s2); }
-                            bool hit = s2 <= fp.t_lo;
-                            if (s2 > fp.t_lo && s2 <= fp.t_hi) {
-                                hit = within<D, SQRT>(xs[p], D > 1 ? xs[n + p] : 0.0, D > 2 ? xs[2 * n + p] : 0.0, xs, n,
-                                                      q0 + tq, rc);
+                            const float w = fmaf(q2z, cv.z, fmaf(q2y, cv.y, fmaf(q2x, cv.x, cv.w)));
+                            const float tt = w - T;
+                            if (fabsf(tt) <= fp.band) {
+                                const bool hit = within<D, SQRT>(xs[p], D > 1 ? xs[n + p] : 0.0, D > 2 ? xs[2 * n + p] : 0.0, xs, n,
+                                                                 q0 + tq, rc);
+                                m = (m & ~(1u << tq)) | ((hit ? 1u : 0u) << tq);
                                 ++n_recheck;
-                            }
-                            if (hit) {
-                                if (MODE != 0) orow[cnt] = q0 + tq;
-                                ++cnt;
                             }
                         }
                     }
+                    if (mine) masks[woff + jme] = m;
+                    woff += gp;
+                    cnt += __popc(m);
                 }
             }
-            if (MODE != 1 && mine) deg[p] = cnt;
+            if (mine) deg[p] = cnt;
         }
     }
-    n_recheck = __reduce_add_sync(full, (unsigned)n_recheck);
-    if (lane == 0 && n_recheck) atomicAdd(stats, n_recheck);
+    n_recheck = __reduce_add_sync(full, n_recheck);
+    if (lane == 0 && n_recheck) atomicAdd(stats, (unsigned long long)n_recheck);
+}
+
+// masks -> column indices.  One warp per tile; per group the mask rows are taken 32 chunks at a time through shared
+// memory (lane = chunk), every query row of the group is then expanded by the whole warp: popcount prefix over the
+// chunks, set bits -> indices into the row buffer, the row buffer -> col_idx with 32 consecutive words per store.
+#define GX_WARPS 4
+template <int D>
+__global__ void __launch_bounds__(GX_WARPS * 32)
+grid_expand_kernel(const int *__restrict__ cell_sorted, const int *__restrict__ cell_start, GridDesc g, ll p_begin, ll p_end,
+                   int qpw, ll n_tiles, const ll *__restrict__ tile_off, const unsigned *__restrict__ masks,
+                   const ll *__restrict__ row_ptr, int *__restrict__ col_idx) {
+    __shared__ unsigned s_slab[GX_WARPS][32 * 33];
+    __shared__ int s_buf[GX_WARPS][1024];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned *slab = s_slab[wid];
+    int *buf = s_buf[wid];
+    const ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    for (ll t = warp; t < n_tiles; t += nwarps) {
+        const ll p0 = p_begin + t * qpw;
+        const ll p = p0 + lane;
+        const bool pvalid = lane < qpw && p < p_end;
+        int cid, my_row, my_cx;
+        gf_tile_header(cell_sorted, g, p, pvalid, cid, my_row, my_cx);
+        ll rowpos = pvalid ? row_ptr[p] : 0;  // where my row's next entry goes
+        ll woff = tile_off[t];
+        unsigned todo = __ballot_sync(full, pvalid);
+        while (todo) {
+            GfGroup G;
+            gf_next_group<D>(todo, cid, my_row, my_cx, g, cell_start, lane, G);
+            const int gp = 1 << G.lg;
+            // chunk prefix over the runs (lane r < nruns owns run r)
+            const int nchr = (G.re - G.rs + 31) >> 5;
+            int incl = nchr;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const int v = __shfl_up_sync(full, incl, o);
+                if (lane >= o) incl += v;
+            }
+            for (int c0 = 0; c0 < G.nch; c0 += 32) {
+                const int nslab = min(32, G.nch - c0);
+                __syncwarp();
+                // slab of mask rows: contiguous in global memory, [chunk][query] -> slab[chunk * 33 + query]
+                const unsigned *src = masks + woff + ((ll)c0 << G.lg);
+                for (int w = lane; w < (nslab << G.lg); w += 32) slab[(w >> G.lg) * 33 + (w & (gp - 1))] = src[w];
+                // my chunk (lane = chunk): which run, first candidate index
+                const int ci = c0 + lane;
+                int run = 0;
+                for (int r = 0; r < G.nruns; ++r) run += ci >= __shfl_sync(full, incl, r) ? 1 : 0;
+                run = min(run, G.nruns - 1);
+                const int r_incl = __shfl_sync(full, incl, run), r_nch = __shfl_sync(full, nchr, run);
+                const int qb = __shfl_sync(full, G.rs, run) + 32 * (ci - (r_incl - r_nch));
+                __syncwarp();
+                for (int j = 0; j < G.gsz; ++j) {
+                    unsigned m = lane < nslab ? slab[lane * 33 + j] : 0u;
+                    const int c = __popc(m);
+                    int pos = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(full, pos, o);
+                        if (lane >= o) pos += v;
+                    }
+                    const int total = __shfl_sync(full, pos, 31);
+                    pos -= c;
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        buf[pos++] = qb + b;
+                    }
+                    const ll base = __shfl_sync(full, rowpos, G.a + j);
+                    __syncwarp();
+                    for (int k = lane; k < total; k += 32) col_idx[base + k] = buf[k];
+                    __syncwarp();
+                    if (lane == G.a + j) rowpos += total;
+                }
+            }
+            woff += (ll)G.nch << G.lg;
+        }
+    }
 }
 
 // cap[p] = size of the candidate list of point p (all points of the 3^D cells around its cell)
@@ -447,59 +587,101 @@ static int launch_rows(cnnb200_ctx *ctx, ll pb, ll pe, int mode, int *deg, const
     return CNNB200_OK;
 }
 
-// thresholds of the fp32 filter (see grid_rows_f32_kernel); false when fp32 cannot represent the problem
+// thresholds of the fp32 filter (see grid_mask_kernel); false when fp32 cannot represent the problem
 static bool filter_params(const cnnb200_ctx *ctx, FilterParams *fp) {
     const double h = ctx->grid.h;
     if (!(h > 1e-12 && h < 1e12)) return false;
     const double R = ctx->grid_metric == CNNB200_METRIC_EUCLIDEAN ? ctx->grid_rc * ctx->grid_rc : ctx->grid_rc;
     const double r = sqrt(R);
-    const double eps = ldexp(h * r, -16) + ldexp(h * h, -34) + ldexp(R, -21);
-    const double lo = R - eps, hi = R + eps;
-    float flo = (float)lo, fhi = (float)hi;
-    if ((double)flo > lo) flo = nextafterf(flo, -INFINITY);
-    if ((double)fhi < hi) fhi = nextafterf(fhi, INFINITY);
-    if (!isfinite(flo) || !isfinite(fhi)) return false;
-    fp->t_lo = flo;
-    fp->t_hi = fhi;
+    // coordinate differences carry delta <= h 2^-18 (cell-local fp32 copies and their shifts): 2 sqrt(3) delta sqrt(d2) +
+    // 3 delta^2 near the cutoff; the expanded form adds the roundings of |c|^2, of the three FMAs, of T = R - |q|^2
+    // and of t = w - T: below 2^-14 h^2 for |q|, |c| <= 5 h (exactness of the fp32 filter)
+    const double eps = ldexp(h * r, -16) + ldexp(h * h, -34) + ldexp(R, -21) + ldexp(h * h, -14);
+    fp->R = R;
     fp->r2 = (float)R;
-    const double half = fmax((double)fp->r2 - (double)flo, (double)fhi - (double)fp->r2);
-    fp->band = nextafterf((float)(half * (1.0 + ldexp(1.0, -20))), INFINITY);
-    return true;
+    fp->band = nextafterf((float)(eps * (1.0 + ldexp(1.0, -20))), INFINITY);
+    return isfinite(fp->band) && isfinite(fp->r2);
 }
 
-template <int D, bool SQRT>
-static int launch_rows_f32(cnnb200_ctx *ctx, ll pb, ll pe, int mode, FilterParams fp, int *deg, const ll *offsets, int *out) {
+static int mask_tiles(const cnnb200_ctx *ctx, ll pb, ll pe, int *qpw_out, ll *n_tiles) {
+    // fewer queries per warp tile when there are few points with long candidate lists (C1: 10^4 points, 10^3
+    // neighbours each), so that the tiles still cover all SMs
     int qpw = 32;
     while (qpw > 8 && (pe - pb) / qpw < (ll)ctx->sm_count * 16) qpw >>= 1;
     if (const char *e = getenv("CNNB200_QPW")) qpw = atoi(e) >= 1 && atoi(e) <= 32 ? atoi(e) : qpw;
-    int blocks = (int)((pe - pb + GF_WARPS * qpw - 1) / (GF_WARPS * qpw));
-    int cap = ctx->sm_count * 48;
+    *qpw_out = qpw;
+    *n_tiles = (pe - pb + qpw - 1) / qpw;
+    return CNNB200_OK;
+}
+
+static int scan_int_to_ll(cnnb200_ctx *ctx, const int *in, ll *out, ll count);
+
+// plan + mask pass on the row block [pb, pe): deg[] and the hit masks (b_masks at b_tile_off[])
+template <int D, bool SQRT>
+static int launch_mask(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg) {
+    cudaStream_t st = ctx->stream;
+    int qpw;
+    ll n_tiles;
+    mask_tiles(ctx, pb, pe, &qpw, &n_tiles);
+    const int *cs = ctx->b_cell_id_sorted.as<int>(), *cst = ctx->b_cell_start.as<int>();
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tile_words, sizeof(int) * (size_t)(n_tiles + 1)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tile_off, sizeof(ll) * (size_t)(n_tiles + 1)));
+    grid_plan_kernel<D><<<cnn_blocks((n_tiles + 1) * 32, 256), 256, 0, st>>>(cs, cst, ctx->grid, pb, pe, qpw, n_tiles,
+                                                                             ctx->b_tile_words.as<int>());
+    CNN_LAUNCHED(ctx, 1);
+    CNN_KERNEL_CHECK();
+    CNN_TRY(scan_int_to_ll(ctx, ctx->b_tile_words.as<int>(), ctx->b_tile_off.as<ll>(), n_tiles + 1));
+    ll *h;
+    CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
+    CNN_CUDA(cudaMemcpyAsync(h, ctx->b_tile_off.as<ll>() + n_tiles, sizeof(ll), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaStreamSynchronize(st));
+    const ll words = h[0];
+    ctx->stats[ST_DIST] = words * 32;
+    CNN_TRY(cnn_ensure(ctx, ctx->b_masks, sizeof(unsigned) * (size_t)words));
+    ll blocks = (n_tiles + GF_WARPS - 1) / GF_WARPS;
+    const ll cap = (ll)ctx->sm_count * 48;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     unsigned long long *recheck = (unsigned long long *)(ctx->b_tmp2.as<char>() + 40);
-    CNN_CUDA(cudaMemsetAsync(recheck, 0, sizeof(unsigned long long), ctx->stream));
-#define GF_ARGS ctx->b_xs.as<double>(), ctx->b_xf.as<float4>(), ctx->grid_n, ctx->b_cell_id_sorted.as<int>(),      \
-                ctx->b_cell_start.as<int>(), ctx->grid, ctx->grid_rc, fp, deg, offsets, out, pb, pe, recheck, qpw
-    if (mode == 0) grid_rows_f32_kernel<D, SQRT, 0><<<blocks, GF_WARPS * 32, 0, ctx->stream>>>(GF_ARGS);
-    else if (mode == 1) grid_rows_f32_kernel<D, SQRT, 1><<<blocks, GF_WARPS * 32, 0, ctx->stream>>>(GF_ARGS);
-    else grid_rows_f32_kernel<D, SQRT, 2><<<blocks, GF_WARPS * 32, 0, ctx->stream>>>(GF_ARGS);
-#undef GF_ARGS
+    CNN_CUDA(cudaMemsetAsync(recheck, 0, sizeof(unsigned long long), st));
+    grid_mask_kernel<D, SQRT><<<(int)blocks, GF_WARPS * 32, 0, st>>>(
+        ctx->b_xs.as<double>(), ctx->b_xf.as<float4>(), ctx->grid_n, cs, cst, ctx->grid, ctx->grid_rc, fp, deg,
+        ctx->b_tile_off.as<ll>(), ctx->b_masks.as<unsigned>(), pb, pe, n_tiles, recheck, qpw);
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     ctx->grid_recheck_pending = true;
     return CNNB200_OK;
 }
 
-static int launch_rows_f32_any(cnnb200_ctx *ctx, ll pb, ll pe, int mode, FilterParams fp, int *deg, const ll *offsets, int *out) {
+static int launch_mask_any(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg) {
     bool sq = ctx->grid_metric == CNNB200_METRIC_EUCLIDEAN;
     switch (ctx->grid.d * 2 + (sq ? 1 : 0)) {
-        case 2: return launch_rows_f32<1, false>(ctx, pb, pe, mode, fp, deg, offsets, out);
-        case 3: return launch_rows_f32<1, true>(ctx, pb, pe, mode, fp, deg, offsets, out);
-        case 4: return launch_rows_f32<2, false>(ctx, pb, pe, mode, fp, deg, offsets, out);
-        case 5: return launch_rows_f32<2, true>(ctx, pb, pe, mode, fp, deg, offsets, out);
-        case 6: return launch_rows_f32<3, false>(ctx, pb, pe, mode, fp, deg, offsets, out);
-        default: return launch_rows_f32<3, true>(ctx, pb, pe, mode, fp, deg, offsets, out);
+        case 2: return launch_mask<1, false>(ctx, pb, pe, fp, deg);
+        case 3: return launch_mask<1, true>(ctx, pb, pe, fp, deg);
+        case 4: return launch_mask<2, false>(ctx, pb, pe, fp, deg);
+        case 5: return launch_mask<2, true>(ctx, pb, pe, fp, deg);
+        case 6: return launch_mask<3, false>(ctx, pb, pe, fp, deg);
+        default: return launch_mask<3, true>(ctx, pb, pe, fp, deg);
     }
+}
+
+static int launch_expand(cnnb200_ctx *ctx, ll pb, ll pe, const ll *row_ptr, int *col_idx) {
+    int qpw;
+    ll n_tiles;
+    mask_tiles(ctx, pb, pe, &qpw, &n_tiles);
+    ll blocks = (n_tiles + GX_WARPS - 1) / GX_WARPS;
+    const ll cap = (ll)ctx->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+#define GX_ARGS ctx->b_cell_id_sorted.as<int>(), ctx->b_cell_start.as<int>(), ctx->grid, pb, pe, qpw, n_tiles,           \
+                ctx->b_tile_off.as<ll>(), ctx->b_masks.as<unsigned>(), row_ptr, col_idx
+    if (ctx->grid.d == 1) grid_expand_kernel<1><<<(int)blocks, GX_WARPS * 32, 0, ctx->stream>>>(GX_ARGS);
+    else if (ctx->grid.d == 2) grid_expand_kernel<2><<<(int)blocks, GX_WARPS * 32, 0, ctx->stream>>>(GX_ARGS);
+    else grid_expand_kernel<3><<<(int)blocks, GX_WARPS * 32, 0, ctx->stream>>>(GX_ARGS);
+#undef GX_ARGS
+    CNN_LAUNCHED(ctx, 1);
+    CNN_KERNEL_CHECK();
+    return CNNB200_OK;
 }
 
 static int launch_rows_any(cnnb200_ctx *ctx, ll pb, ll pe, int mode, int *deg, const ll *offsets, int *out) {
@@ -523,8 +705,28 @@ static int scan_int_to_ll(cnnb200_ctx *ctx, const int *in, ll *out, ll count) {
     return CNNB200_OK;
 }
 
+// candidate-list sizes (the cell ids in input order are dead after the sort: reuse that buffer) and their prefix =
+// offsets of the gapped rows of the f64 form / the work measure used to balance row blocks
+int cnn_grid_cap(cnnb200_ctx *ctx) {
+    if (ctx->have_cap) return CNNB200_OK;
+    cudaStream_t st = ctx->stream;
+    const ll n = ctx->grid_n;
+    const GridDesc &g = ctx->grid;
+    int *capv = ctx->b_cell_id.as<int>();
+    int nb1 = cnn_blocks(n + 1, 256);
+    const int *cs = ctx->b_cell_id_sorted.as<int>(), *cst = ctx->b_cell_start.as<int>();
+    if (g.d == 1) grid_cap_kernel<1><<<nb1, 256, 0, st>>>(n, cs, cst, g, capv);
+    else if (g.d == 2) grid_cap_kernel<2><<<nb1, 256, 0, st>>>(n, cs, cst, g, capv);
+    else grid_cap_kernel<3><<<nb1, 256, 0, st>>>(n, cs, cst, g, capv);
+    CNN_LAUNCHED(ctx, 1);
+    CNN_KERNEL_CHECK();
+    CNN_TRY(scan_int_to_ll(ctx, capv, ctx->b_tmp1.as<ll>(), n + 1));
+    ctx->have_cap = true;
+    return CNNB200_OK;
+}
+
 // ---- K1: grid geometry, sort by cell, candidate-list prefix --------------------------------------
-int cnn_grid_build(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric) {
+int cnn_grid_build(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric, bool want_cap) {
     cudaStream_t st = ctx->stream;
     ctx->have_grid = false;
     Span sp_build(ctx, T_GRID_BUILD);
@@ -609,29 +811,35 @@ int cnn_grid_build(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radiu
     gather_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_x, ctx->b_perm.as<int>(), ctx->b_cell_id_sorted.as<int>(), n, g,
                                                         ctx->b_xs.as<double>(), ctx->b_xf.as<float4>());
     CNN_LAUNCHED(ctx, 1);
-    // candidate-list sizes (the cell ids in input order are dead after the sort: reuse that buffer)
-    // and their prefix = offsets of the gapped rows / the work measure used to balance row blocks
-    int *capv = ctx->b_cell_id.as<int>();
-    int nb1 = cnn_blocks(n + 1, 256);
-    const int *cs = ctx->b_cell_id_sorted.as<int>(), *cst = ctx->b_cell_start.as<int>();
-    if (d == 1) grid_cap_kernel<1><<<nb1, 256, 0, st>>>(n, cs, cst, g, capv);
-    else if (d == 2) grid_cap_kernel<2><<<nb1, 256, 0, st>>>(n, cs, cst, g, capv);
-    else grid_cap_kernel<3><<<nb1, 256, 0, st>>>(n, cs, cst, g, capv);
-    CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
-    CNN_TRY(scan_int_to_ll(ctx, capv, ctx->b_tmp1.as<ll>(), n + 1));
     ctx->grid = g;
     ctx->grid_n = n;
     ctx->grid_rc = radius_cutoff;
     ctx->grid_metric = metric;
+    ctx->have_cap = false;
+    FilterParams fp;
+    ctx->grid_filter = ctx->use_filter && filter_params(ctx, &fp);
+    if (want_cap || !ctx->grid_filter) CNN_TRY(cnn_grid_cap(ctx));
     ctx->have_grid = true;
     ctx->perm = ctx->b_perm.as<int>();
     return CNNB200_OK;
 }
 
-// ---- K2 on a row block [pb, pe) of the cell-sorted points: degrees (and, single pass, the hits) -------
+// ---- K2 on a row block [pb, pe) of the cell-sorted points: degrees + what the fill needs (hit masks, or the
+// gapped hits of the f64 form) ----------------------------------------------------------------------------------
 int cnn_grid_rows(cnnb200_ctx *ctx, ll pb, ll pe, int *deg) {
     cudaStream_t st = ctx->stream;
+    ctx->blk_begin = pb;
+    ctx->blk_end = pe;
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
+    FilterParams fp;
+    if (ctx->grid_filter && filter_params(ctx, &fp)) {
+        Span sp(ctx, T_SEARCH_COUNT);
+        ctx->blk_masks = true;
+        return launch_mask_any(ctx, pb, pe, fp, deg);
+    }
+    ctx->blk_masks = false;
+    CNN_TRY(cnn_grid_cap(ctx));
     ll *h;
     CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
     const ll *goff = ctx->b_tmp1.as<ll>();
@@ -639,8 +847,6 @@ int cnn_grid_rows(cnnb200_ctx *ctx, ll pb, ll pe, int *deg) {
     CNN_CUDA(cudaMemcpyAsync(h + 1, goff + pe, sizeof(ll), cudaMemcpyDeviceToHost, st));
     CNN_CUDA(cudaStreamSynchronize(st));
     const ll g0 = h[0], gapped = h[1] - h[0];
-    ctx->blk_begin = pb;
-    ctx->blk_end = pe;
     ctx->blk_goff0 = g0;
     ctx->blk_single = ctx->single_pass_limit > 0 && gapped * 4 <= ctx->single_pass_limit;
     ctx->stats[ST_DIST] = gapped;
@@ -648,19 +854,9 @@ int cnn_grid_rows(cnnb200_ctx *ctx, ll pb, ll pe, int *deg) {
     if (ctx->blk_single) {
         CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(int) * (size_t)gapped));
         // row p writes at gapped[goff[p] - g0 ...]: shift the base pointer instead of the offsets
-        FilterParams fp;
-        CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
-        if (ctx->use_filter && filter_params(ctx, &fp))
-            CNN_TRY(launch_rows_f32_any(ctx, pb, pe, 2, fp, deg, goff, ctx->b_tmp0.as<int>() - g0));
-        else
-            CNN_TRY(launch_rows_any(ctx, pb, pe, 2, deg, goff, ctx->b_tmp0.as<int>() - g0));
+        CNN_TRY(launch_rows_any(ctx, pb, pe, 2, deg, goff, ctx->b_tmp0.as<int>() - g0));
     } else {
-        FilterParams fp;
-        CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
-        if (ctx->use_filter && filter_params(ctx, &fp))
-            CNN_TRY(launch_rows_f32_any(ctx, pb, pe, 0, fp, deg, nullptr, nullptr));
-        else
-            CNN_TRY(launch_rows_any(ctx, pb, pe, 0, deg, nullptr, nullptr));
+        CNN_TRY(launch_rows_any(ctx, pb, pe, 0, deg, nullptr, nullptr));
     }
     return CNNB200_OK;
 }
@@ -670,6 +866,7 @@ int cnn_grid_fill(cnnb200_ctx *ctx, ll pb, ll pe, const ll *row_ptr, int *col_id
     if (pb != ctx->blk_begin || pe != ctx->blk_end)
         CNN_FAIL(CNNB200_E_STATE, "grid fill: row block differs from the one the degrees were computed for");
     Span sp(ctx, T_SEARCH_FILL);
+    if (ctx->blk_masks) return launch_expand(ctx, pb, pe, row_ptr, col_idx);
     if (ctx->blk_single) {
         int blocks = (int)((pe - pb + 7) / 8);
         if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
@@ -679,18 +876,14 @@ int cnn_grid_fill(cnnb200_ctx *ctx, ll pb, ll pe, const ll *row_ptr, int *col_id
         CNN_LAUNCHED(ctx, 1);
         CNN_KERNEL_CHECK();
     } else {
-        FilterParams fp;
-        if (ctx->use_filter && filter_params(ctx, &fp))
-            CNN_TRY(launch_rows_f32_any(ctx, pb, pe, 1, fp, nullptr, row_ptr, col_idx));
-        else
-            CNN_TRY(launch_rows_any(ctx, pb, pe, 1, nullptr, row_ptr, col_idx));
+        CNN_TRY(launch_rows_any(ctx, pb, pe, 1, nullptr, row_ptr, col_idx));
     }
     return CNNB200_OK;
 }
 
 int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric) {
     cudaStream_t st = ctx->stream;
-    CNN_TRY(cnn_grid_build(ctx, d_x, n, d, radius_cutoff, metric));
+    CNN_TRY(cnn_grid_build(ctx, d_x, n, d, radius_cutoff, metric, false));
     CNN_TRY(cnn_ensure(ctx, ctx->b_deg, sizeof(int) * (size_t)(n + 1)));
     CNN_TRY(cnn_ensure(ctx, ctx->b_row_ptr, sizeof(ll) * (size_t)(n + 1)));
     CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>() + n, 0, sizeof(int), st));
@@ -746,7 +939,7 @@ extern "C" int cnnb200_grid_begin(cnnb200_ctx *ctx, const double *x, int loc, in
         CNN_CUDA(cudaMemcpyAsync(ctx->b_x.p, x, sizeof(double) * (size_t)n * (size_t)d, cudaMemcpyHostToDevice, ctx->stream));
         d_x = ctx->b_x.as<double>();
     }
-    return cnn_grid_build(ctx, d_x, n, d, radius_cutoff, metric);
+    return cnn_grid_build(ctx, d_x, n, d, radius_cutoff, metric, true);
 }
 
 extern "C" int cnnb200_grid_balance(cnnb200_ctx *ctx, int parts, int64_t *bounds) {

@@ -223,6 +223,51 @@ __global__ void comp_union_kernel(const int *__restrict__ edge_out, ll row_begin
     }
 }
 
+// Second sampling round, on flattened parents: the first round leaves chains of consecutive rows (trees that follow
+// the x-rows of cells); what joins them are edges to rows far away in the index order.  Trying such an edge from
+// EVERY row of a chain repeats the same union hundreds of times in dense regions (C2: 0.67 M checks for 0.03 M
+// unions), so only every `stride`-th row of a tree (counted from its root) tries, and only when the far neighbour
+// sits in another tree: the LAST entry of the row (the highest cell row of its window) and the entry a quarter into
+// the upper part (the next cell row of the same layer).
+__global__ void __launch_bounds__(256)
+comp_sample_far_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll row_begin, ll row_end,
+                       int cutoff, int stride, int *parent, const int *__restrict__ above, unsigned long long *stats) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const ll i = row_begin + blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    const int ri = i < row_end ? ld_parent(parent, (int)i) : -1;
+    const bool sel = ri >= 0 && ((int)i - ri) % stride == 0;
+    unsigned n_checks = 0, n_acc = 0;
+    if (__any_sync(full, sel)) {
+        const ll rb = sel ? row_ptr[i] : 0;
+        const int m = sel ? (int)(row_ptr[i + 1] - rb) : 0;
+        const int l = sel ? above[i] : 0;
+        int jprev = -1;
+#pragma unroll
+        for (int smp = 0; smp < 2; ++smp) {
+            int j = -1;
+            if (sel && l < m) j = col_idx[rb + (smp == 0 ? m - 1 : l + ((m - l) >> 2))];
+            if (j == jprev) j = -1;
+            jprev = j;
+            const int rj = j >= 0 ? ld_parent(parent, j) : -1;
+            const bool ok = rj >= 0 && rj != ri;
+            const ll jb = ok ? row_ptr[j] : 0;
+            const int mj = ok ? (int)(row_ptr[j + 1] - jb) : 0;
+            int acc = 0;
+            if (ok) acc = lane_check(col_idx + rb, m, col_idx + jb, mj, cutoff);
+            if (acc) uf_union(parent, (int)i, j);
+            n_checks += ok ? 1 : 0;
+            n_acc += acc ? 1 : 0;
+        }
+    }
+    n_checks = __reduce_add_sync(full, n_checks);
+    n_acc = __reduce_add_sync(full, n_acc);
+    if (lane == 0 && n_checks) {
+        atomicAdd(stats + ST_CHECKS, (unsigned long long)n_checks);
+        if (n_acc) atomicAdd(stats + ST_ACCEPTED, (unsigned long long)n_acc);
+    }
+}
+
 __global__ void comp_compress_kernel(int *parent, ll n) {
     ll p = blockIdx.x * (ll)blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -410,8 +455,8 @@ comp_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx
 // N(j) are already in flight.
 __global__ void __launch_bounds__(WIN_WARPS * 32)
 comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, const int2 *__restrict__ worklist,
-                     const unsigned long long *__restrict__ wl_count, int cutoff, int *parent,
-                     unsigned long long *stats) {
+                     const unsigned long long *__restrict__ wl_count, unsigned long long *chunk_counter, int chunk,
+                     int cutoff, int *parent, unsigned long long *stats) {
     __shared__ unsigned win_all[WIN_WARPS][WIN_BITS / 32];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -421,11 +466,19 @@ comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col
     w.span = 0;
     for (int t = lane; t < WIN_BITS / 32; t += 32) w.bits[t] = 0;
     __syncwarp();
-    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
-    ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     const ll count = (ll)*wl_count;
     unsigned long long n_checks = 0, n_acc = 0, n_skip = 0;
-    for (ll e0 = warp * 32; e0 < count; e0 += nwarps * 32) {
+    // A warp takes `chunk` consecutive batches of 32 edges at a time (handed out in list order by a counter) and works
+    // through them one after the other with fresh finds per batch.  The scan emits the list row by row, so the many
+    // edges between the same two trees sit next to each other: taken by ONE warp in sequence, the first accepted edge
+    // settles the rest (two finds each); spread over concurrently running warps they would all be evaluated.
+    for (;;) {
+        ll c0 = 0;
+        if (lane == 0) c0 = (ll)atomicAdd(chunk_counter, 1ull);
+        c0 = __shfl_sync(full, c0, 0) * chunk * 32;
+        if (c0 >= count) break;
+        const ll c1 = c0 + (ll)chunk * 32 < count ? c0 + (ll)chunk * 32 : count;
+    for (ll e0 = c0; e0 < c1; e0 += 32) {
         const ll e = e0 + lane;
         const bool valid = e < count;
         const int2 ed = valid ? worklist[e] : make_int2(0, 0);
@@ -484,6 +537,7 @@ comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col
         const int n_dead = __popc(__ballot_sync(full, dead && acc == 0));
         n_checks -= n_dead;
         n_skip += n_dead;
+    }
     }
     if (lane == 0) {
         if (n_checks) atomicAdd(stats + ST_CHECKS, n_checks);
@@ -816,13 +870,23 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         Span sp(ctx, T_COMP_FLATTEN);
         comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(parent, ctx->n);
     }
+    if (ns > 0 && ctx->far_stride > 0 && !ctx->comp_packed) {
+        {
+            Span sp(ctx, T_COMP_SAMPLE);
+            comp_sample_far_kernel<<<cnn_blocks(rows, 256), 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, cutoff,
+                                                                          ctx->far_stride, parent, above, stats);
+        }
+        Span sp(ctx, T_COMP_FLATTEN);
+        comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(parent, ctx->n);
+        CNN_LAUNCHED(ctx, 2);
+    }
     {
         Span sp(ctx, T_COMP_EDGES);
         // work list: at most one entry per CSR entry of the row block (candidate edges are the entries j > i)
         ll cap_edges = ctx->nnz + 64;
         CNN_TRY(cnn_ensure(ctx, ctx->b_worklist, sizeof(int2) * (size_t)cap_edges));
-        unsigned long long *wl_count = stats + ST_N - 1;
-        CNN_CUDA(cudaMemsetAsync(wl_count, 0, sizeof(unsigned long long), st));
+        unsigned long long *wl_count = stats + ST_WL_COUNT;  // + ST_COUNTER right behind it
+        CNN_CUDA(cudaMemsetAsync(wl_count, 0, 2 * sizeof(unsigned long long), st));
         int tile_rows = 32;  // about 8k entries per warp tile
         const ll mean_deg = ctx->nnz / (ctx->n > 0 ? ctx->n : 1);
         while (tile_rows > 1 && mean_deg * tile_rows > 8192) tile_rows >>= 1;
@@ -835,7 +899,8 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         } else {
             static const int wl_ctas = resident_ctas(comp_worklist_kernel, WIN_WARPS * 32);
             comp_worklist_kernel<<<ctx->sm_count * wl_ctas, WIN_WARPS * 32, 0, st>>>(
-                ctx->row_ptr, ctx->col_idx, ctx->b_worklist.as<int2>(), wl_count, cutoff, parent, stats);
+                ctx->row_ptr, ctx->col_idx, ctx->b_worklist.as<int2>(), wl_count, stats + ST_COUNTER, ctx->wl_chunk, cutoff,
+                parent, stats);
         }
         CNN_LAUNCHED(ctx, 2);
     }
@@ -950,7 +1015,7 @@ extern "C" int cnnb200_cn_count_rows(cnnb200_ctx *ctx, int64_t n_member_cutoff, 
     ll want = (rows + WIN_WARPS * CNW_BATCH - 1) / (WIN_WARPS * CNW_BATCH);
     if (blocks > want) blocks = (int)want;
     if (blocks < 1) blocks = 1;
-    unsigned long long *row_counter = (unsigned long long *)ctx->b_stats.p + ST_N - 1;
+    unsigned long long *row_counter = (unsigned long long *)ctx->b_stats.p + ST_COUNTER;
     {
         Span sp(ctx, T_CN_COUNT);
         cn_count_kernel<<<blocks, WIN_WARPS * 32, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, n_member_cutoff, d_counts,

@@ -56,7 +56,9 @@ enum StatSlot {
     ST_DIST = 4,
     ST_RECHECK = 5,
     ST_FALLBACK = 6,  // count mode: rows whose index window did not fit the shared-memory bitmap
-    ST_N = 8
+    ST_WL_COUNT = 8,  // device-side counters that live next to the statistics: work-list length,
+    ST_COUNTER = 9,   // dynamic work distribution (rows / work-list chunks handed out so far)
+    ST_N = 10
 };
 
 // timing slots (cnnb200_timings): device time of the stages of the path, by CUDA events
@@ -88,7 +90,9 @@ struct cnnb200_ctx {
     int sm_count = 148;
     ll single_pass_limit = 32ll << 30;  // bytes of gapped scratch the single-pass search may use (0 = two-pass)
     bool fuse_union = true;  // sampling pass links its accepted edges itself (CNNB200_FUSED_UNION=0: separate kernel)
-    int n_samples = 2;  // edges per core row tried by the sampling pass (tunable: CNNB200_SAMPLES)
+    int n_samples = 1;  // edges per core row tried by the first sampling round (tunable: CNNB200_SAMPLES)
+    int far_stride = 8; // second round: every far_stride-th row of a tree tries two far neighbours (0: off; CNNB200_FAR_STRIDE)
+    int wl_chunk = 16;  // work-list batches of 32 edges a warp takes at a time (CNNB200_WL_CHUNK)
 
     // ---- neighbourhood structure (internal index space) -------------------------------
     bool have_nb = false;

@@ -318,8 +318,8 @@ grid_plan_kernel(const int *__restrict__ cell_sorted, const int *__restrict__ ce
     if (lane == 0) tile_words[t] = words;
 }
 
-template <int D, bool SQRT>
-__global__ void __launch_bounds__(GF_WARPS * 32, 4)
+template <int D, bool SQRT, int MINB>
+__global__ void __launch_bounds__(GF_WARPS * 32, MINB)
 grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, ll n, const int *__restrict__ cell_sorted,
                  const int *__restrict__ cell_start, GridDesc g, double rc, FilterParams fp, int *__restrict__ deg,
                  const ll *__restrict__ tile_off, unsigned *__restrict__ masks, ll p_begin, ll p_end, ll n_tiles,
@@ -338,7 +338,7 @@ grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, l
         int cid, my_row, my_cx;
         gf_tile_header(cell_sorted, g, p, pvalid, cid, my_row, my_cx);
         const float4 my4 = pvalid ? xf[p] : make_float4(0.f, 0.f, 0.f, 0.f);
-        ll woff = tile_off[t];
+        unsigned *mw = masks + tile_off[t];
         unsigned todo = __ballot_sync(full, pvalid);
         while (todo) {
             GfGroup G;
@@ -367,7 +367,8 @@ grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, l
             for (int r = 0; r < G.nruns; ++r) {
                 const int s = __shfl_sync(full, G.rs, r), e = __shfl_sync(full, G.re, r);
                 const float sy = __shfl_sync(full, shy, r), sz = __shfl_sync(full, shz, r);
-                float4 c4 = s + lane < e ? xf[s + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 *cp = xf + s + lane;
+                float4 c4 = s + lane < e ? *cp : make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int q0 = s; q0 < e; q0 += 32) {
                     __syncwarp();
                     {
@@ -375,7 +376,8 @@ grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, l
                         qf[lane] = make_float4(cx, cy, cz, fmaf(cz, cz, fmaf(cy, cy, cx * cx)));
                     }
                     __syncwarp();
-                    if (q0 + 32 + lane < e) c4 = xf[q0 + 32 + lane];  // next chunk's candidates, in flight during this one
+                    cp += 32;
+                    if (q0 + 32 + lane < e) c4 = *cp;  // next chunk's candidates, in flight during this one
                     const int nc = min(32, e - q0);
                     unsigned m = 0;
                     float near = INFINITY;  // smallest |t| this lane meets in the chunk
@@ -402,8 +404,8 @@ grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, l
                             }
                         }
                     }
-                    if (mine) masks[woff + jme] = m;
-                    woff += gp;
+                    if (mine) mw[jme] = m;
+                    mw += gp;
                     cnt += __popc(m);
                 }
             }
@@ -414,83 +416,74 @@ grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, l
     if (lane == 0 && n_recheck) atomicAdd(stats, (unsigned long long)n_recheck);
 }
 
-// masks -> column indices.  One warp per tile; per group the mask rows are taken 32 chunks at a time through shared
-// memory (lane = chunk), every query row of the group is then expanded by the whole warp: popcount prefix over the
-// chunks, set bits -> indices into the row buffer, the row buffer -> col_idx with 32 consecutive words per store.
+// masks -> column indices.  One warp per tile, one query row per lane: a lane walks the mask words of its row in chunk
+// order (the words of a chunk are contiguous over the lanes of the group: coalesced loads) and turns set bits into
+// indices in a shared-memory stage of GX_STAGE slots per row; when a row's stage would overflow (and at the end of the
+// tile) the whole warp writes the staged part of every row to col_idx, 32 consecutive words per store instruction.
+// Stage layout: row-major with a pad of one word (reads of one row by 32 lanes are conflict-free).
 #define GX_WARPS 4
+#define GX_STAGE 64
 template <int D>
 __global__ void __launch_bounds__(GX_WARPS * 32)
 grid_expand_kernel(const int *__restrict__ cell_sorted, const int *__restrict__ cell_start, GridDesc g, ll p_begin, ll p_end,
                    int qpw, ll n_tiles, const ll *__restrict__ tile_off, const unsigned *__restrict__ masks,
                    const ll *__restrict__ row_ptr, int *__restrict__ col_idx) {
-    __shared__ unsigned s_slab[GX_WARPS][32 * 33];
-    __shared__ int s_buf[GX_WARPS][1024];
+    __shared__ int s_stage[GX_WARPS][32 * (GX_STAGE + 1)];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned *slab = s_slab[wid];
-    int *buf = s_buf[wid];
+    int *stage = s_stage[wid];
+    int *mine_stage = stage + lane * (GX_STAGE + 1);
     const ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     for (ll t = warp; t < n_tiles; t += nwarps) {
-        const ll p0 = p_begin + t * qpw;
-        const ll p = p0 + lane;
+        const ll p = p_begin + t * qpw + lane;
         const bool pvalid = lane < qpw && p < p_end;
         int cid, my_row, my_cx;
         gf_tile_header(cell_sorted, g, p, pvalid, cid, my_row, my_cx);
         ll rowpos = pvalid ? row_ptr[p] : 0;  // where my row's next entry goes
-        ll woff = tile_off[t];
+        int cnt = 0;                          // staged entries of my row
+        auto flush = [&]() {
+            __syncwarp();
+            unsigned has = __ballot_sync(full, cnt > 0);
+            while (has) {
+                const int j = __ffs(has) - 1;
+                has &= has - 1;
+                const int c = __shfl_sync(full, cnt, j);
+                const ll base = __shfl_sync(full, rowpos, j);
+                const int *src = stage + j * (GX_STAGE + 1);
+                for (int k = lane; k < c; k += 32) col_idx[base + k] = src[k];
+            }
+            rowpos += cnt;
+            cnt = 0;
+            __syncwarp();
+        };
+        const unsigned *mw = masks + tile_off[t];
         unsigned todo = __ballot_sync(full, pvalid);
         while (todo) {
             GfGroup G;
             gf_next_group<D>(todo, cid, my_row, my_cx, g, cell_start, lane, G);
+            const int jme = lane - G.a;
+            const bool mine = jme >= 0 && jme < G.gsz;
             const int gp = 1 << G.lg;
-            // chunk prefix over the runs (lane r < nruns owns run r)
-            const int nchr = (G.re - G.rs + 31) >> 5;
-            int incl = nchr;
-#pragma unroll
-            for (int o = 1; o < 16; o <<= 1) {
-                const int v = __shfl_up_sync(full, incl, o);
-                if (lane >= o) incl += v;
-            }
-            for (int c0 = 0; c0 < G.nch; c0 += 32) {
-                const int nslab = min(32, G.nch - c0);
-                __syncwarp();
-                // slab of mask rows: contiguous in global memory, [chunk][query] -> slab[chunk * 33 + query]
-                const unsigned *src = masks + woff + ((ll)c0 << G.lg);
-                for (int w = lane; w < (nslab << G.lg); w += 32) slab[(w >> G.lg) * 33 + (w & (gp - 1))] = src[w];
-                // my chunk (lane = chunk): which run, first candidate index
-                const int ci = c0 + lane;
-                int run = 0;
-                for (int r = 0; r < G.nruns; ++r) run += ci >= __shfl_sync(full, incl, r) ? 1 : 0;
-                run = min(run, G.nruns - 1);
-                const int r_incl = __shfl_sync(full, incl, run), r_nch = __shfl_sync(full, nchr, run);
-                const int qb = __shfl_sync(full, G.rs, run) + 32 * (ci - (r_incl - r_nch));
-                __syncwarp();
-                for (int j = 0; j < G.gsz; ++j) {
-                    unsigned m = lane < nslab ? slab[lane * 33 + j] : 0u;
-                    const int c = __popc(m);
-                    int pos = c;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int v = __shfl_up_sync(full, pos, o);
-                        if (lane >= o) pos += v;
-                    }
-                    const int total = __shfl_sync(full, pos, 31);
-                    pos -= c;
+            int left = G.nch;  // chunks of the group still to come; the next chunk's word is fetched one step ahead
+            unsigned m_next = (mine && left > 0) ? mw[jme] : 0u;
+            for (int r = 0; r < G.nruns; ++r) {
+                const int s = __shfl_sync(full, G.rs, r), e = __shfl_sync(full, G.re, r);
+                for (int q0 = s; q0 < e; q0 += 32) {
+                    unsigned m = m_next;
+                    mw += gp;
+                    --left;
+                    m_next = (mine && left > 0) ? mw[jme] : 0u;
+                    if (__any_sync(full, cnt + __popc(m) > GX_STAGE)) flush();
                     while (m) {
                         const int b = __ffs(m) - 1;
                         m &= m - 1;
-                        buf[pos++] = qb + b;
+                        mine_stage[cnt++] = q0 + b;
                     }
-                    const ll base = __shfl_sync(full, rowpos, G.a + j);
-                    __syncwarp();
-                    for (int k = lane; k < total; k += 32) col_idx[base + k] = buf[k];
-                    __syncwarp();
-                    if (lane == G.a + j) rowpos += total;
                 }
             }
-            woff += (ll)G.nch << G.lg;
         }
+        flush();
     }
 }
 
@@ -644,9 +637,13 @@ static int launch_mask(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg
     if (blocks < 1) blocks = 1;
     unsigned long long *recheck = (unsigned long long *)(ctx->b_tmp2.as<char>() + 40);
     CNN_CUDA(cudaMemsetAsync(recheck, 0, sizeof(unsigned long long), st));
-    grid_mask_kernel<D, SQRT><<<(int)blocks, GF_WARPS * 32, 0, st>>>(
-        ctx->b_xs.as<double>(), ctx->b_xf.as<float4>(), ctx->grid_n, cs, cst, ctx->grid, ctx->grid_rc, fp, deg,
-        ctx->b_tile_off.as<ll>(), ctx->b_masks.as<unsigned>(), pb, pe, n_tiles, recheck, qpw);
+    static const int minb = getenv("CNNB200_MASK_MINB") ? atoi(getenv("CNNB200_MASK_MINB")) : 4;
+#define GM_ARGS ctx->b_xs.as<double>(), ctx->b_xf.as<float4>(), ctx->grid_n, cs, cst, ctx->grid, ctx->grid_rc, fp, deg,     \
+                ctx->b_tile_off.as<ll>(), ctx->b_masks.as<unsigned>(), pb, pe, n_tiles, recheck, qpw
+    if (minb == 3) grid_mask_kernel<D, SQRT, 3><<<(int)blocks, GF_WARPS * 32, 0, st>>>(GM_ARGS);
+    else if (minb == 2) grid_mask_kernel<D, SQRT, 2><<<(int)blocks, GF_WARPS * 32, 0, st>>>(GM_ARGS);
+    else grid_mask_kernel<D, SQRT, 4><<<(int)blocks, GF_WARPS * 32, 0, st>>>(GM_ARGS);
+#undef GM_ARGS
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     ctx->grid_recheck_pending = true;

@@ -385,7 +385,7 @@ int cnn_count_packed(cnnb200_ctx *ctx, ll n_member_cutoff, ll row_begin, ll row_
     Span sp(ctx, T_CN_COUNT);
     cn_count_packed_kernel<<<blocks, PK_WARPS * 32, 0, st>>>(ctx->row_ptr, ctx->col_idx, ctx->b_wrows.as<int2>(),
                                                             ctx->b_wcnt.as<int>(), row_begin, row_end, n_member_cutoff, d_counts,
-                                                            stats, stats + ST_N - 1);
+                                                            stats, stats + ST_COUNTER);
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     return CNNB200_OK;

@@ -353,7 +353,7 @@ extern "C" int cnnb200_predict(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_
         CNN_CUDA(cudaMemcpyAsync(ok, label_ok, (size_t)(max_label + 1), cudaMemcpyHostToDevice, st));
     }
     CNN_TRY(cnn_ensure(ctx, ctx->b_stats, sizeof(unsigned long long) * ST_N));
-    unsigned long long *row_counter = (unsigned long long *)ctx->b_stats.p + ST_N - 1;
+    unsigned long long *row_counter = (unsigned long long *)ctx->b_stats.p + ST_COUNTER;
     CNN_CUDA(cudaMemsetAsync(row_counter, 0, sizeof(unsigned long long), st));
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, predict_kernel, PW_WARPS * 32, 0) != cudaSuccess || per_sm < 1) {

@@ -415,7 +415,9 @@ class Context:
         s = np.zeros(8, dtype=np.int64)
         check(self._lib.cnnb200_stats(self._h, s.ctypes.data, 8))
         return {"candidate_edges": int(s[0]), "checks": int(s[1]), "accepted": int(s[2]),
-                "skipped": int(s[3]), "distance_evals": int(s[4]), "rechecks": int(s[5])}
+                "skipped": int(s[3]), "distance_evals": int(s[4]), "rechecks": int(s[5]),
+                "window_fallbacks": int(s[6]), "search_method": {0: None, 1: "grid", 2: "tiled", 3: "tensor"}.get(int(s[7]) & 15),
+                "count_packed": bool(int(s[7]) & 16)}
 
 
 def host_register(array) -> bool:

@@ -275,7 +275,10 @@ extern "C" int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x,
         if (method == 0) method = (d <= 3 && n >= 4096) ? 1 : 2;
     }
     if (!(radius_cutoff >= 0.0)) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_points: radius_cutoff must be >= 0");
-    if (method == 0) method = d <= 3 ? 1 : 2;
+    // auto: cell list up to three dimensions; above that the tcgen05 filter + f64 recheck (the same neighbour sets as
+    // the f64 all-pairs kernel, NeighboursGetterExtBruteForce._get for any D) from a few thousand points on
+    const bool automatic = method == 0;
+    if (method == 0) method = d <= 3 ? 1 : ((d <= 85 && n >= 4096) ? 3 : 2);
     if (method == 1 && d > 3) CNN_FAIL(CNNB200_E_INVALID, "grid method needs d <= 3 (got %lld)", (ll)d);
     if (method < 1 || method > 3) CNN_FAIL(CNNB200_E_INVALID, "unknown method %d", method);
     CNN_CUDA(cudaSetDevice(ctx->device));
@@ -298,9 +301,16 @@ extern "C" int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x,
     if (periodic && method == 1) {
     } else if (method == 1)
         CNN_TRY(cnn_grid_search(ctx, d_x, n, d, radius_cutoff, metric));
-    else
-        CNN_TRY(cnn_dense_search(ctx, d_x, n, d, radius_cutoff, metric, method));
+    else {
+        int rc = cnn_dense_search(ctx, d_x, n, d, radius_cutoff, metric, method);
+        if (rc == CNNB200_E_RANGE && automatic && method == 3) {  // more pairs than the pair list can index: exact kernel
+            method = 2;
+            rc = cnn_dense_search(ctx, d_x, n, d, radius_cutoff, metric, method);
+        }
+        CNN_TRY(rc);
+    }
     ctx->have_nb = true;
+    ctx->stats[ST_PATH] = (ctx->stats[ST_PATH] & ~15ll) | method;
     ++ctx->nb_version;
     ctx->have_other = false;
     ctx->have_points = true;  // prediction for other points needs the coordinates, the cutoff and the metric again
@@ -320,26 +330,48 @@ extern "C" int cnnb200_fit_points(cnnb200_ctx *ctx, const double *x, int loc, in
                                   int64_t *n_clusters_out) {
     if (!labels) CNN_FAIL(CNNB200_E_INVALID, "fit_points: labels is NULL");
     CNN_TRY(cnnb200_neighbours_from_points(ctx, x, loc, n, d, radius_cutoff, metric, method, nullptr));
+    static const bool fused_labels = !getenv("CNNB200_FUSED_LABELS") || atoi(getenv("CNNB200_FUSED_LABELS")) != 0;
     if (!sort_by_size)
         return cnnb200_fit(ctx, n_member_cutoff, similarity_cutoff, current_start, labels, nullptr, loc,
                            n_clusters_out);
-    // keep the labels on the device between the fit and the relabel: one D2H at the end
+    // a fresh fit followed by sort_by_size: the labels stay on the device, numbering and size sort collapse into one
+    // ranking of the components (cnn_labels_fused), one D2H copy and ONE synchronisation at the end
     CNN_TRY(cnn_ensure(ctx, ctx->b_labels, sizeof(ll) * (size_t)n));
     int64_t *d_labels = loc == CNNB200_HOST ? (int64_t *)ctx->b_labels.p : labels;
-    if (loc == CNNB200_HOST) CNN_CUDA(cudaMemsetAsync(d_labels, 0, sizeof(ll) * (size_t)n, ctx->stream));
     CNN_TRY(cnnb200_components_begin(ctx, n_member_cutoff, similarity_cutoff, nullptr, CNNB200_DEVICE));
     CNN_TRY(cnnb200_components_edges(ctx, 0, n));
-    int64_t n_clusters = 0;  // asking for it also refreshes the counters behind cnnb200_stats
-    CNN_TRY(cnnb200_components_labels(ctx, current_start, d_labels, CNNB200_DEVICE, /*fresh=*/1, &n_clusters));
-    if (n_clusters_out) *n_clusters_out = n_clusters;
-    ctx->known_max_label = n_clusters > 0 ? current_start + n_clusters - 1 : 0;  // fresh fit: no reduce, no sync
-    CNN_TRY(cnnb200_sort_by_size(ctx, d_labels, CNNB200_DEVICE, n, member_cutoff, max_clusters, nullptr, 0));
+    unsigned long long *counters = nullptr;
+    CNN_TRY(cnn_labels_fused(ctx, member_cutoff, max_clusters, d_labels, &counters));
+    unsigned long long *h;
+    CNN_TRY(cnn_pinned(ctx, 128, (void **)&h));
     if (loc == CNNB200_HOST) {
-        {
-            Span sp(ctx, T_D2H);
-            CNN_CUDA(cudaMemcpyAsync(labels, d_labels, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-        }
-        CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        Span sp(ctx, T_D2H);
+        CNN_CUDA(cudaMemcpyAsync(labels, d_labels, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    CNN_CUDA(cudaMemcpyAsync(h, counters, sizeof(ll) * 6, cudaMemcpyDeviceToHost, ctx->stream));
+    CNN_CUDA(cudaMemcpyAsync(h + 8, ctx->b_stats.p, sizeof(ll) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 4; ++k) ctx->stats[k] = (ll)h[8 + k];
+    const int64_t n_clusters = (int64_t)h[0];
+    if (n_clusters_out) *n_clusters_out = n_clusters;
+    if (h[2] || !fused_labels) {
+        // more surviving clusters than one CTA ranks: the general chain (numbering, then the size sort over all labels)
+        if (loc == CNNB200_HOST) CNN_CUDA(cudaMemsetAsync(d_labels, 0, sizeof(ll) * (size_t)n, ctx->stream));
+        int64_t nc2 = 0;
+        CNN_TRY(cnnb200_components_labels(ctx, current_start, d_labels, CNNB200_DEVICE, /*fresh=*/1, &nc2));
+        ctx->known_max_label = nc2 > 0 ? current_start + nc2 - 1 : 0;
+        CNN_TRY(cnnb200_sort_by_size(ctx, d_labels, CNNB200_DEVICE, n, member_cutoff, max_clusters, nullptr, 0));
+        if (loc == CNNB200_HOST) {
+            CNN_CUDA(cudaMemcpyAsync(labels, d_labels, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+            CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        return CNNB200_OK;
+    }
+    ctx->have_lab_summary = true;
+    ctx->lab_summary_n = n;
+    ctx->lab_summary_host[0] = (ll)h[3];
+    ctx->lab_summary_host[1] = (ll)h[4];
+    ctx->lab_summary_host[2] = n - (ll)h[5];
+    ctx->lab_summary_cached = true;
     return CNNB200_OK;
 }

@@ -228,44 +228,39 @@ __global__ void comp_union_kernel(const int *__restrict__ edge_out, ll row_begin
 // EVERY row of a chain repeats the same union hundreds of times in dense regions (C2: 0.67 M checks for 0.03 M
 // unions), so only every `stride`-th row of a tree (counted from its root) tries, and only when the far neighbour
 // sits in another tree: the LAST entry of the row (the highest cell row of its window) and the entry a quarter into
-// the upper part (the next cell row of the same layer).
+// the upper part (the next cell row of the same layer).  The edges go to the work list and are evaluated by
+// comp_worklist_kernel (whole-warp intersections: the two rows of such an edge overlap only partly and are not in L1,
+// a per-lane merge would walk them with one dependent global load per step).
 __global__ void __launch_bounds__(256)
-comp_sample_far_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll row_begin, ll row_end,
-                       int cutoff, int stride, int *parent, const int *__restrict__ above, unsigned long long *stats) {
+comp_far_emit_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll row_begin, ll row_end, int stride,
+                     const int *__restrict__ parent, const int *__restrict__ above, int2 *__restrict__ worklist,
+                     unsigned long long *wl_count) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const ll i = row_begin + blockIdx.x * (ll)blockDim.x + threadIdx.x;
-    const int ri = i < row_end ? ld_parent(parent, (int)i) : -1;
+    const int ri = i < row_end ? parent[i] : -1;
     const bool sel = ri >= 0 && ((int)i - ri) % stride == 0;
-    unsigned n_checks = 0, n_acc = 0;
-    if (__any_sync(full, sel)) {
-        const ll rb = sel ? row_ptr[i] : 0;
-        const int m = sel ? (int)(row_ptr[i + 1] - rb) : 0;
-        const int l = sel ? above[i] : 0;
-        int jprev = -1;
-#pragma unroll
-        for (int smp = 0; smp < 2; ++smp) {
-            int j = -1;
-            if (sel && l < m) j = col_idx[rb + (smp == 0 ? m - 1 : l + ((m - l) >> 2))];
-            if (j == jprev) j = -1;
-            jprev = j;
-            const int rj = j >= 0 ? ld_parent(parent, j) : -1;
-            const bool ok = rj >= 0 && rj != ri;
-            const ll jb = ok ? row_ptr[j] : 0;
-            const int mj = ok ? (int)(row_ptr[j + 1] - jb) : 0;
-            int acc = 0;
-            if (ok) acc = lane_check(col_idx + rb, m, col_idx + jb, mj, cutoff);
-            if (acc) uf_union(parent, (int)i, j);
-            n_checks += ok ? 1 : 0;
-            n_acc += acc ? 1 : 0;
-        }
+    if (!__any_sync(full, sel)) return;
+    const ll rb = sel ? row_ptr[i] : 0;
+    const int m = sel ? (int)(row_ptr[i + 1] - rb) : 0;
+    const int l = sel ? above[i] : 0;
+    int j0 = -1, j1 = -1;
+    if (sel && l < m) {
+        j0 = col_idx[rb + m - 1];
+        j1 = col_idx[rb + l + ((m - l) >> 2)];
+        if (j1 == j0) j1 = -1;
     }
-    n_checks = __reduce_add_sync(full, n_checks);
-    n_acc = __reduce_add_sync(full, n_acc);
-    if (lane == 0 && n_checks) {
-        atomicAdd(stats + ST_CHECKS, (unsigned long long)n_checks);
-        if (n_acc) atomicAdd(stats + ST_ACCEPTED, (unsigned long long)n_acc);
-    }
+    const int r0 = j0 >= 0 ? parent[j0] : -1, r1 = j1 >= 0 ? parent[j1] : -1;
+    const bool e0 = r0 >= 0 && r0 != ri, e1 = r1 >= 0 && r1 != ri && r1 != r0;
+    const unsigned b0 = __ballot_sync(full, e0), b1 = __ballot_sync(full, e1);
+    const int tot = __popc(b0) + __popc(b1);
+    if (!tot) return;
+    unsigned long long pos = 0;
+    if (lane == 0) pos = atomicAdd(wl_count, (unsigned long long)tot);
+    pos = __shfl_sync(full, pos, 0);
+    if (e0) worklist[pos + __popc(b0 & lt)] = make_int2((int)i, j0);
+    if (e1) worklist[pos + __popc(b0) + __popc(b1 & lt)] = make_int2((int)i, j1);
 }
 
 __global__ void comp_compress_kernel(int *parent, ll n) {
@@ -467,6 +462,10 @@ comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col
     for (int t = lane; t < WIN_BITS / 32; t += 32) w.bits[t] = 0;
     __syncwarp();
     const ll count = (ll)*wl_count;
+    {   // short lists: at least four chunks per warp
+        const ll per_warp = count / (((ll)gridDim.x * blockDim.x >> 5) * 32 * 4);
+        chunk = per_warp < 1 ? 1 : (per_warp < chunk ? (int)per_warp : chunk);
+    }
     unsigned long long n_checks = 0, n_acc = 0, n_skip = 0;
     // A warp takes `chunk` consecutive batches of 32 edges at a time (handed out in list order by a counter) and works
     // through them one after the other with fresh finds per batch.  The scan emits the list row by row, so the many
@@ -870,22 +869,27 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         Span sp(ctx, T_COMP_FLATTEN);
         comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(parent, ctx->n);
     }
+    ll cap_edges = ctx->nnz + 64;  // work list: at most one entry per CSR entry of the row block
+    CNN_TRY(cnn_ensure(ctx, ctx->b_worklist, sizeof(int2) * (size_t)cap_edges));
+    unsigned long long *wl_count = stats + ST_WL_COUNT;  // + ST_COUNTER right behind it
+    static const int wl_ctas = resident_ctas(comp_worklist_kernel, WIN_WARPS * 32);
     if (ns > 0 && ctx->far_stride > 0 && !ctx->comp_packed) {
         {
             Span sp(ctx, T_COMP_SAMPLE);
-            comp_sample_far_kernel<<<cnn_blocks(rows, 256), 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, cutoff,
-                                                                          ctx->far_stride, parent, above, stats);
+            CNN_CUDA(cudaMemsetAsync(wl_count, 0, 2 * sizeof(unsigned long long), st));
+            comp_far_emit_kernel<<<cnn_blocks(rows, 256), 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end,
+                                                                        ctx->far_stride, parent, above,
+                                                                        ctx->b_worklist.as<int2>(), wl_count);
+            comp_worklist_kernel<<<ctx->sm_count * wl_ctas, WIN_WARPS * 32, 0, st>>>(
+                ctx->row_ptr, ctx->col_idx, ctx->b_worklist.as<int2>(), wl_count, stats + ST_COUNTER, ctx->wl_chunk, cutoff,
+                parent, stats);
         }
         Span sp(ctx, T_COMP_FLATTEN);
         comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(parent, ctx->n);
-        CNN_LAUNCHED(ctx, 2);
+        CNN_LAUNCHED(ctx, 3);
     }
     {
         Span sp(ctx, T_COMP_EDGES);
-        // work list: at most one entry per CSR entry of the row block (candidate edges are the entries j > i)
-        ll cap_edges = ctx->nnz + 64;
-        CNN_TRY(cnn_ensure(ctx, ctx->b_worklist, sizeof(int2) * (size_t)cap_edges));
-        unsigned long long *wl_count = stats + ST_WL_COUNT;  // + ST_COUNTER right behind it
         CNN_CUDA(cudaMemsetAsync(wl_count, 0, 2 * sizeof(unsigned long long), st));
         int tile_rows = 32;  // about 8k entries per warp tile
         const ll mean_deg = ctx->nnz / (ctx->n > 0 ? ctx->n : 1);
@@ -897,7 +901,6 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         if (ctx->comp_packed) {
             CNN_TRY(cnn_worklist_packed(ctx, ctx->b_worklist.as<int2>(), wl_count, cutoff, parent));
         } else {
-            static const int wl_ctas = resident_ctas(comp_worklist_kernel, WIN_WARPS * 32);
             comp_worklist_kernel<<<ctx->sm_count * wl_ctas, WIN_WARPS * 32, 0, st>>>(
                 ctx->row_ptr, ctx->col_idx, ctx->b_worklist.as<int2>(), wl_count, stats + ST_COUNTER, ctx->wl_chunk, cutoff,
                 parent, stats);
@@ -998,6 +1001,7 @@ extern "C" int cnnb200_cn_count_rows(cnnb200_ctx *ctx, int64_t n_member_cutoff, 
     }
     bool packed = false;
     CNN_TRY(cnn_pack_rows(ctx, &packed));
+    ctx->stats[ST_PATH] = (ctx->stats[ST_PATH] & ~16ll) | (packed ? 16 : 0);
     if (packed) {
         CNN_CUDA(cudaMemsetAsync(ctx->b_stats.p, 0, sizeof(unsigned long long) * ST_N, st));
         CNN_TRY(cnn_count_packed(ctx, n_member_cutoff, row_begin, row_end, d_counts));

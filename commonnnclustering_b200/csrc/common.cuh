@@ -56,6 +56,7 @@ enum StatSlot {
     ST_DIST = 4,
     ST_RECHECK = 5,
     ST_FALLBACK = 6,  // count mode: rows whose index window did not fit the shared-memory bitmap
+    ST_PATH = 7,      // which kernels served the last calls: bits 0-3 search method (1 grid, 2 tiled f64, 3 tensor), bit 4 packed count mode
     ST_WL_COUNT = 8,  // device-side counters that live next to the statistics: work-list length,
     ST_COUNTER = 9,   // dynamic work distribution (rows / work-list chunks handed out so far)
     ST_N = 10
@@ -163,7 +164,8 @@ struct cnnb200_ctx {
     double bounds_h[3] = {0, 0, 0};  // host copy of the first three (periodic cell list, periodic.cu)
     Buf b_pg_x, b_pg_orig, b_pg_xq, b_pg_perm, b_pg_deg, b_pg_img, b_pg_row_ptr, b_pg_col;  // periodic cell list: augmented set + results
     Buf b_lab_summary;
-    bool have_lab_summary = false;
+    bool have_lab_summary = false, lab_summary_cached = false;  // cached: the three numbers already sit in lab_summary_host
+    ll lab_summary_host[3] = {0, 0, 0};
     ll lab_summary_n = 0;
     ll known_max_label = -1;
     ll tensor_band_cap = 0;  // capacity (pairs) the borderline list of the tensor-core search needed last time  // set by cnnb200_fit_points for the sort_by_size call that follows a fresh fit
@@ -219,6 +221,7 @@ int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radi
 int cnn_grid_search_periodic(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, bool *served);
 int cnn_dense_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric,
                      int method);
+int cnn_labels_fused(cnnb200_ctx *ctx, ll member_cutoff, ll max_clusters, ll *d_labels, unsigned long long **counters_out);
 int cnn_finish_csr(cnnb200_ctx *ctx, ll n, ll nnz, ll max_deg, const ll *row_ptr, const int *col_idx);
 int cnn_pack_rows(cnnb200_ctx *ctx, bool *usable_out);
 int cnn_worklist_packed(cnnb200_ctx *ctx, const int2 *worklist, const unsigned long long *wl_count, int cutoff, int *parent);

@@ -417,10 +417,11 @@ grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, l
 }
 
 // masks -> column indices.  One warp per tile, one query row per lane: a lane walks the mask words of its row in chunk
-// order (the words of a chunk are contiguous over the lanes of the group: coalesced loads) and turns set bits into
-// indices in a shared-memory stage of GX_STAGE slots per row; when a row's stage would overflow (and at the end of the
-// tile) the whole warp writes the staged part of every row to col_idx, 32 consecutive words per store instruction.
-// Stage layout: row-major with a pad of one word (reads of one row by 32 lanes are conflict-free).
+// order (the words of a chunk are contiguous over the lanes of the group: coalesced loads, the next word fetched one
+// step ahead) and turns set bits into indices in a shared-memory stage of 64 slots per row.  After every chunk the
+// rows that hold 32 entries or more are written out by the whole warp -- full 128-byte store instructions -- and the
+// rest at the end of the tile.  Stage layout: row-major with a pad of one word (the 32 lanes reading one row hit 32
+// banks).  Row positions are kept as 32-bit offsets from the tile's first row.
 #define GX_WARPS 4
 #define GX_STAGE 64
 template <int D>
@@ -436,25 +437,29 @@ grid_expand_kernel(const int *__restrict__ cell_sorted, const int *__restrict__ 
     const ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     for (ll t = warp; t < n_tiles; t += nwarps) {
-        const ll p = p_begin + t * qpw + lane;
+        const ll p0 = p_begin + t * qpw;
+        const ll p = p0 + lane;
         const bool pvalid = lane < qpw && p < p_end;
         int cid, my_row, my_cx;
         gf_tile_header(cell_sorted, g, p, pvalid, cid, my_row, my_cx);
-        ll rowpos = pvalid ? row_ptr[p] : 0;  // where my row's next entry goes
-        int cnt = 0;                          // staged entries of my row
-        auto flush = [&]() {
+        const ll tile_base = row_ptr[p0];
+        int *out = col_idx + tile_base;
+        int rowpos = pvalid ? (int)(row_ptr[p] - tile_base) : 0;  // where my row's next entry goes, from the tile's base
+        int cnt = 0;                                               // staged entries of my row
+        // writes the staged entries of the rows in `rows` (all of them: a row is emptied by a flush)
+        auto flush = [&](unsigned rows) {
             __syncwarp();
-            unsigned has = __ballot_sync(full, cnt > 0);
-            while (has) {
-                const int j = __ffs(has) - 1;
-                has &= has - 1;
-                const int c = __shfl_sync(full, cnt, j);
-                const ll base = __shfl_sync(full, rowpos, j);
+            const int mycnt = cnt;
+            if ((rows >> lane) & 1u) { rowpos += cnt; cnt = 0; }
+            while (rows) {
+                const int j = __ffs(rows) - 1;
+                rows &= rows - 1;
+                const int c = __shfl_sync(full, mycnt, j);
+                const int base = __shfl_sync(full, rowpos, j) - c;
                 const int *src = stage + j * (GX_STAGE + 1);
-                for (int k = lane; k < c; k += 32) col_idx[base + k] = src[k];
+                out[base + lane] = src[lane];  // c >= 32 whenever a flush is triggered inside the tile
+                if (lane + 32 < c) out[base + lane + 32] = src[lane + 32];
             }
-            rowpos += cnt;
-            cnt = 0;
             __syncwarp();
         };
         const unsigned *mw = masks + tile_off[t];
@@ -474,16 +479,27 @@ grid_expand_kernel(const int *__restrict__ cell_sorted, const int *__restrict__ 
                     mw += gp;
                     --left;
                     m_next = (mine && left > 0) ? mw[jme] : 0u;
-                    if (__any_sync(full, cnt + __popc(m) > GX_STAGE)) flush();
                     while (m) {
                         const int b = __ffs(m) - 1;
                         m &= m - 1;
                         mine_stage[cnt++] = q0 + b;
                     }
+                    const unsigned rdy = __ballot_sync(full, cnt >= 32);
+                    if (rdy) flush(rdy);
                 }
             }
         }
-        flush();
+        // the remainders (fewer than 32 entries per row)
+        __syncwarp();
+        unsigned rows = __ballot_sync(full, cnt > 0);
+        while (rows) {
+            const int j = __ffs(rows) - 1;
+            rows &= rows - 1;
+            const int c = __shfl_sync(full, cnt, j);
+            const int base = __shfl_sync(full, rowpos, j);
+            if (lane < c) out[base + lane] = stage[j * (GX_STAGE + 1) + lane];
+        }
+        __syncwarp();
     }
 }
 
@@ -637,7 +653,7 @@ static int launch_mask(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg
     if (blocks < 1) blocks = 1;
     unsigned long long *recheck = (unsigned long long *)(ctx->b_tmp2.as<char>() + 40);
     CNN_CUDA(cudaMemsetAsync(recheck, 0, sizeof(unsigned long long), st));
-    static const int minb = getenv("CNNB200_MASK_MINB") ? atoi(getenv("CNNB200_MASK_MINB")) : 4;
+    static const int minb = getenv("CNNB200_MASK_MINB") ? atoi(getenv("CNNB200_MASK_MINB")) : 3;
 #define GM_ARGS ctx->b_xs.as<double>(), ctx->b_xf.as<float4>(), ctx->grid_n, cs, cst, ctx->grid, ctx->grid_rc, fp, deg,     \
                 ctx->b_tile_off.as<ll>(), ctx->b_masks.as<unsigned>(), pb, pe, n_tiles, recheck, qpw
     if (minb == 3) grid_mask_kernel<D, SQRT, 3><<<(int)blocks, GF_WARPS * 32, 0, st>>>(GM_ARGS);

@@ -233,6 +233,7 @@ extern "C" int cnnb200_sort_by_size(cnnb200_ctx *ctx, int64_t *labels, int loc, 
         CNN_CUDA(cudaMemcpyAsync(d_labels, labels, sizeof(ll) * (size_t)n, cudaMemcpyHostToDevice, st));
     }
     ctx->have_lab_summary = false;
+    ctx->lab_summary_cached = false;
     ctx->lab_summary_n = n;
     std::unique_ptr<Span> sp(new Span(ctx, T_SORT_BY_SIZE));
     // largest label -> table size (known to the caller after a fresh fit: ctx->known_max_label)
@@ -333,10 +334,158 @@ extern "C" int cnnb200_label_summary(cnnb200_ctx *ctx, int64_t *out3) {
         out3[0] = 0; out3[1] = 0; out3[2] = ctx->lab_summary_n;
         return CNNB200_OK;
     }
+    if (ctx->lab_summary_cached) {  // cnnb200_fit_points read them with its final synchronisation
+        for (int k = 0; k < 3; ++k) out3[k] = ctx->lab_summary_host[k];
+        return CNNB200_OK;
+    }
     ll *h;
     CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
     CNN_CUDA(cudaMemcpyAsync(h, ctx->b_lab_summary.p, sizeof(ll) * 3, cudaMemcpyDeviceToHost, ctx->stream));
     CNN_CUDA(cudaStreamSynchronize(ctx->stream));
     out3[0] = h[0]; out3[1] = h[1]; out3[2] = ctx->lab_summary_n - h[2];
+    return CNNB200_OK;
+}
+
+// ---- fresh fit + sort_by_size in one go (cnnb200_fit_points) ------------------------------------------------------
+// After a fresh fit every label comes from this fit, so FitterExtBFS's numbering followed by Labels.sort_by_size
+// (_fit.pyx:434-491, _types.pyx:212-286) collapses to: rank the components by (size descending, smallest member index
+// ascending -- the first occurrence of the BFS label), drop those below member_cutoff / beyond max_clusters, number the
+// rest 1, 2, ...  Components below member_cutoff never influence the rank of the others (they sort behind every
+// survivor), so only the survivors are sorted: a few hundred keys on C2 instead of 48 751, in ONE CTA.
+//   fused_sizes_kernel    size and smallest caller index per root (warp-aggregated atomics)
+//   fused_roots_kernel    roots -> compact list of survivor keys (size : min index), counts all components
+//   fused_rank_kernel     one CTA: bitonic sort of up to FUSED_MAX_KEYS keys in shared memory, rank -> root_label[],
+//                         summary (clusters kept, largest, members kept); more keys: flag, the caller falls back
+//   fused_write_kernel    labels[perm[p]] = root_label[parent[p]]
+#define FUSED_MAX_KEYS 4096
+
+__global__ void fused_sizes_kernel(const int *__restrict__ parent, const int *__restrict__ perm, ll n, int *size, int *minorig) {
+    ll p = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    const int r = p < n ? parent[p] : -1;
+    const bool active = r >= 0;
+    const unsigned am = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    const unsigned peers = __match_any_sync(am, r);
+    const int mn = __reduce_min_sync(peers, perm ? perm[p] : (int)p);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+        atomicAdd(size + r, __popc(peers));
+        atomicMin(minorig + r, mn);
+    }
+}
+
+// counters: [0] components, [1] survivor keys, [2] overflow flag, [3] kept, [4] largest, [5] members kept
+__global__ void fused_roots_kernel(const int *__restrict__ parent, const int *__restrict__ size, const int *__restrict__ minorig,
+                                   ll n, int kb, ll member_cutoff, unsigned long long *keys, int *vals, int *root_label,
+                                   unsigned long long *counters) {
+    ll p = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    const bool root = p < n && parent[p] == (int)p;
+    const int sz = root ? size[p] : 0;
+    const bool surv = root && sz >= member_cutoff;
+    const unsigned rm = __ballot_sync(0xffffffffu, root), sm = __ballot_sync(0xffffffffu, surv);
+    const int lane = threadIdx.x & 31;
+    if (!rm) return;
+    unsigned long long base = 0;
+    if (lane == 0) {
+        atomicAdd(counters + 0, (unsigned long long)__popc(rm));
+        if (sm) base = atomicAdd(counters + 1, (unsigned long long)__popc(sm));
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (root) root_label[p] = 0;
+    if (surv) {
+        const unsigned long long k = base + __popc(sm & ((1u << lane) - 1u));
+        if (k < FUSED_MAX_KEYS) {
+            keys[k] = ((unsigned long long)(n - sz) << kb) | (unsigned long long)minorig[p];
+            vals[k] = (int)p;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+fused_rank_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ vals, ll n, int kb, ll max_clusters,
+                  int *root_label, unsigned long long *counters) {
+    __shared__ unsigned long long s_key[FUSED_MAX_KEYS];
+    __shared__ int s_val[FUSED_MAX_KEYS];
+    const ll m = (ll)counters[1];
+    if (m > FUSED_MAX_KEYS) {
+        if (threadIdx.x == 0) counters[2] = 1;
+        return;
+    }
+    int np2 = 1;
+    while (np2 < m) np2 <<= 1;
+    for (int t = threadIdx.x; t < np2; t += blockDim.x) {
+        s_key[t] = t < m ? keys[t] : ~0ull;
+        s_val[t] = t < m ? vals[t] : -1;
+    }
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < np2; t += blockDim.x) {
+                const int u = t ^ j;
+                if (u > t) {
+                    const bool up = (t & k) == 0;
+                    const unsigned long long a = s_key[t], b = s_key[u];
+                    if ((a > b) == up) {
+                        s_key[t] = b; s_key[u] = a;
+                        const int v = s_val[t]; s_val[t] = s_val[u]; s_val[u] = v;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    // keys are distinct (the smallest member index is): ascending keys = size descending, ties by first occurrence
+    const ll kept = max_clusters >= 0 && max_clusters < m ? max_clusters : m;
+    unsigned long long members = 0;
+    for (int t = threadIdx.x; t < m; t += blockDim.x) {
+        root_label[s_val[t]] = t < kept ? t + 1 : 0;
+        if (t < kept) members += (unsigned long long)(n - (ll)(s_key[t] >> kb));
+    }
+    for (int o = 16; o; o >>= 1) members += __shfl_xor_sync(0xffffffffu, members, o);
+    if ((threadIdx.x & 31) == 0 && members) atomicAdd(counters + 5, members);
+    if (threadIdx.x == 0) {
+        counters[3] = (unsigned long long)kept;
+        counters[4] = kept > 0 ? (unsigned long long)(n - (ll)(s_key[0] >> kb)) : 0ull;
+    }
+}
+
+__global__ void fused_write_kernel(const int *__restrict__ parent, const int *__restrict__ perm, const int *__restrict__ root_label,
+                                   ll n, ll *labels) {
+    ll p = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int r = parent[p];
+    labels[perm ? perm[p] : p] = r >= 0 ? (ll)root_label[r] : 0;
+}
+
+// Enqueues the four kernels; `counters_out` (device, 6 words) is read by the caller together with its final
+// synchronisation: [0] number of components = clusters the BFS would have numbered, [2] != 0: more survivors than one
+// CTA sorts -- the caller repeats with cnnb200_components_labels + cnnb200_sort_by_size.
+int cnn_labels_fused(cnnb200_ctx *ctx, ll member_cutoff, ll max_clusters, ll *d_labels, unsigned long long **counters_out) {
+    cudaStream_t st = ctx->stream;
+    const ll n = ctx->n;
+    if (member_cutoff < 0) member_cutoff = 2;  // None -> 2 (_types.pyx:235-237)
+    const int *parent = ctx->b_parent.as<int>();
+    Span sp(ctx, T_LABELS);
+    CNN_TRY(cnn_ensure(ctx, ctx->b_minorig, sizeof(int) * (size_t)n));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_lab_count, sizeof(int) * (size_t)n));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_rank, sizeof(int) * (size_t)(n + 1)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_lab_keys, sizeof(ll) * FUSED_MAX_KEYS));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_lab_vals, sizeof(int) * FUSED_MAX_KEYS));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_lab_summary, sizeof(ll) * 8));
+    int *size = ctx->b_lab_count.as<int>(), *minorig = ctx->b_minorig.as<int>(), *root_label = ctx->b_rank.as<int>();
+    unsigned long long *counters = ctx->b_lab_summary.as<unsigned long long>();
+    CNN_CUDA(cudaMemsetAsync(size, 0, sizeof(int) * (size_t)n, st));
+    CNN_CUDA(cudaMemsetAsync(minorig, 0x7f, sizeof(int) * (size_t)n, st));
+    CNN_CUDA(cudaMemsetAsync(counters, 0, sizeof(ll) * 8, st));
+    int kb = 1;
+    while ((1ll << kb) <= n) ++kb;
+    const int nb = cnn_blocks(n, 256);
+    fused_sizes_kernel<<<nb, 256, 0, st>>>(parent, ctx->perm, n, size, minorig);
+    fused_roots_kernel<<<nb, 256, 0, st>>>(parent, size, minorig, n, kb, member_cutoff, ctx->b_lab_keys.as<unsigned long long>(),
+                                           ctx->b_lab_vals.as<int>(), root_label, counters);
+    fused_rank_kernel<<<1, 1024, 0, st>>>(ctx->b_lab_keys.as<unsigned long long>(), ctx->b_lab_vals.as<int>(), n, kb, max_clusters,
+                                          root_label, counters);
+    fused_write_kernel<<<nb, 256, 0, st>>>(parent, ctx->perm, root_label, n, d_labels);
+    CNN_LAUNCHED(ctx, 4);
+    CNN_KERNEL_CHECK();
+    *counters_out = counters;
     return CNNB200_OK;
 }

@@ -286,7 +286,10 @@ int cnnb200_host_unregister(void *ptr);
  *   stats[0] candidate edges (i<j, both core)      stats[1] CN checks executed
  *   stats[2] edges accepted by a check             stats[3] edges skipped (already connected)
  *   stats[4] distance evaluations (neighbour search, count pass)
- *   stats[5] pairs re-checked in f64 (tensor-core filter path) */
+ *   stats[5] pairs re-checked in f64 (fp32 / tensor-core filter paths)
+ *   stats[6] count mode: rows whose index window did not fit the shared-memory bitmap
+ *   stats[7] which kernels served the last calls: bits 0-3 = method of the last cnnb200_neighbours_from_points
+ *            (1 cell list, 2 tiled f64, 3 tcgen05 filter), bit 4 = the last count-mode pass ran on bit-packed rows */
 int cnnb200_stats(cnnb200_ctx *ctx, int64_t *stats, int64_t len);
 
 /* Stage timing by CUDA events on the context's stream (off by default).  cnnb200_timings

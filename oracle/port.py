@@ -40,6 +40,9 @@ def lib():
             f.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_double, C.c_int, _i64p, _i64p]
         L.cnn_oracle_neighbours_brute_count.restype = None
         L.cnn_oracle_neighbours_brute_fill.restype = None
+        L.cnn_oracle_neighbours_upper.restype = None
+        L.cnn_oracle_neighbours_upper.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p]
         L.cnn_oracle_neighbours_periodic_count.restype = None
         L.cnn_oracle_neighbours_periodic_count.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_double, _f64p, _i64p]
         L.cnn_oracle_neighbours_periodic_fill.restype = None
@@ -99,6 +102,31 @@ def neighbours(x, radius_cutoff: float, metric: str = "euclidean_r", method: str
     rc = fil(x, n, d, float(radius_cutoff), m, row_ptr, col_idx)
     assert not rc, rc
     return row_ptr, col_idx[: int(row_ptr[-1])]
+
+
+def neighbours_large(x, radius_cutoff: float, metric: str = "euclidean_r"):
+    """The brute-force neighbour sets for any dimension at sizes where two full N^2 passes are too slow (C3, N = 2e5,
+    D = 64): every unordered pair once, the sum abandoned as soon as it exceeds the cutoff (exact, see
+    ``cnn_oracle_neighbours_upper``), then mirrored.  Same CSR as ``neighbours(..., method="brute")``."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n, d = x.shape
+    L = lib()
+    m = METRICS[metric]
+    up_deg = np.zeros(n, dtype=np.int64)
+    L.cnn_oracle_neighbours_upper(x, n, d, float(radius_cutoff), m, up_deg.ctypes.data, None, None)
+    up_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(up_deg, out=up_ptr[1:])
+    up_idx = np.empty(max(int(up_ptr[-1]), 1), dtype=np.int64)
+    L.cnn_oracle_neighbours_upper(x, n, d, float(radius_cutoff), m, None, up_ptr.ctypes.data, up_idx.ctypes.data)
+    up_idx = up_idx[: int(up_ptr[-1])]
+    rows = np.repeat(np.arange(n, dtype=np.int64), up_deg)
+    # both directions of every pair plus the diagonal (dist(i, i) = 0 <= cutoff for any cutoff >= 0)
+    r_all = np.concatenate([rows, up_idx, np.arange(n, dtype=np.int64)])
+    c_all = np.concatenate([up_idx, rows, np.arange(n, dtype=np.int64)])
+    order = np.lexsort((c_all, r_all))
+    row_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(r_all, minlength=n), out=row_ptr[1:])
+    return row_ptr, np.ascontiguousarray(c_all[order])
 
 
 def check(a, b, c: int, kind: str = "sorted") -> bool:

@@ -774,3 +774,28 @@ def test_periodic_metric_equals_oracle_and_reference(ctx):
         ours = cluster.Clustering(x[:1200], fitter__ngetter__dgetter__metric=(_types.MetricEuclideanPeriodicReduced, (bounds,), {}))
         ours.fit(0.45, 6, member_cutoff=5, v=False)
         np.testing.assert_array_equal(ours.labels, np.array(rcl.labels))
+
+
+@pytest.mark.gpu
+def test_fused_numbering_and_size_sort(ctx):
+    """cnnb200_fit_points ranks the components in one CTA when few survive member_cutoff and falls back to the
+    general chain (numbering + sort_by_size over all labels) otherwise; both equal the oracle."""
+    # 10 000 clusters of two points each: more survivors than one CTA ranks -> fallback
+    base = np.arange(10_000, dtype=np.float64)[:, None] * 10.0
+    x = np.concatenate([base, base + 0.1]).reshape(-1, 1)
+    rng = np.random.default_rng(5)
+    x = np.ascontiguousarray(x[rng.permutation(x.shape[0])])
+    want = port.fit_points(x, 0.5, 0, member_cutoff=None)
+    got = np.zeros(x.shape[0], dtype=np.int64)
+    nc = ctx.fit_points(x, 0.25, 1, 2, got)
+    assert nc == 10_000 and np.array_equal(got, want) and got.max() == 10_000
+    # ties in size are broken by first occurrence; max_clusters and member_cutoff cut the tail
+    x = datasets.md_like_3d(60_000)
+    for mc, mx in [(None, None), (10, None), (5, 7), (1, 3), (50, 1)]:
+        want = port.fit_points(x, 0.2, 5, member_cutoff=mc, max_clusters=mx)
+        got = np.zeros(x.shape[0], dtype=np.int64)
+        ctx.fit_points(x, 0.04, 6, 7, got, member_cutoff=mc, max_clusters=mx)
+        assert np.array_equal(got, want), (mc, mx)
+        kept, largest, noise = ctx.label_summary()
+        cnt = np.bincount(want)
+        assert (kept, largest, noise) == (len(cnt) - 1, int(cnt[1:].max()) if len(cnt) > 1 else 0, int(cnt[0]))

@@ -53,6 +53,9 @@ SIGNATURES = {
     "cnnb200_components_parents": [_P, C.POINTER(_P)],
     "cnnb200_components_merge": [_P, _P, _I64],
     "cnnb200_components_labels": [_P, _I64, _P, C.c_int, C.c_int, C.POINTER(_I64)],
+    "cnnb200_fit_sharded_begin": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int, _I64, _I64, C.c_int, C.c_int, _P,
+                                  C.POINTER(_P)],
+    "cnnb200_fit_sharded_end": [_P, _P, _I64, C.c_int, _I64, _I64, _I64, _P, C.c_int, C.POINTER(_I64)],
     "cnnb200_neighbours_other_from_points": [_P, _P, C.c_int, _I64, _I64, C.POINTER(_I64)],
     "cnnb200_neighbours_other_from_csr": [_P, _P, _P, C.c_int, _I64, _I64],
     "cnnb200_predict": [_P, _I64, _I64, _P, _P, _I64, _P, _P, C.c_int],
@@ -279,6 +282,17 @@ class Context:
         check(self._lib.cnnb200_neighbours_export(self._h, row_ptr.ctypes.data, col_idx.ctypes.data, HOST))
         return row_ptr, col_idx[:nnz]
 
+    def neighbours_export_device(self):
+        """The same CSR (caller's index space, rows ascending) as CUDA tensors: row_ptr int64 [n+1], col_idx int32 [nnz]."""
+        import torch
+
+        n, nnz, _ = self.neighbours_info()
+        dev = torch.device("cuda", self.device)
+        row_ptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        col64 = torch.empty(max(nnz, 1), dtype=torch.int64, device=dev)
+        check(self._lib.cnnb200_neighbours_export(self._h, row_ptr.data_ptr(), col64.data_ptr(), DEVICE))
+        return row_ptr, col64[:nnz].to(torch.int32)
+
     def neighbours_device_view(self):
         a, b, c = _P(), _P(), _P()
         check(self._lib.cnnb200_neighbours_device_view(self._h, C.byref(a), C.byref(b), C.byref(c)))
@@ -331,6 +345,31 @@ class Context:
         if loc != DEVICE:
             raise ValueError("foreign parent arrays must be device tensors")
         check(self._lib.cnnb200_components_merge(self._h, p, int(count)))
+
+    def fit_sharded_begin(self, x, radius_cutoff, n_member_cutoff, similarity_cutoff, rank, world, metric="euclidean_r"):
+        """-> (block bounds int64 [world + 1], device pointer of this rank's int32 [n] parent array)."""
+        p, loc = _ptr_loc(x)
+        n, d = x.shape
+        bounds = np.zeros(world + 1, dtype=np.int64)
+        parents = _P()
+        check(self._lib.cnnb200_fit_sharded_begin(self._h, p, loc, n, d, float(radius_cutoff), METRIC_IDS[metric],
+                                                  int(n_member_cutoff), int(similarity_cutoff), int(rank), int(world),
+                                                  bounds.ctypes.data, C.byref(parents)))
+        return bounds, parents.value
+
+    def fit_sharded_end(self, others, world, labels, sort_by_size=True, current_start=1, member_cutoff=None,
+                        max_clusters=None):
+        """``labels`` None: merge only (this rank's caller does not want the labels)."""
+        op, loc = _ptr_loc(others)
+        if loc != DEVICE:
+            raise ValueError("the gathered parent arrays must be a device tensor")
+        lp, lloc = _ptr_loc(labels)
+        nc = _I64()
+        check(self._lib.cnnb200_fit_sharded_end(
+            self._h, op, int(world), int(bool(sort_by_size)), int(current_start),
+            -1 if member_cutoff is None else int(member_cutoff), -1 if max_clusters is None else int(max_clusters),
+            lp, lloc, C.byref(nc)))
+        return nc.value
 
     def components_labels(self, current_start, labels, fresh=True):
         lp, loc = _ptr_loc(labels)

@@ -198,7 +198,7 @@ class Clustering:
 
         g = self._fitter._neighbours_getter
         labels, summary = sweep.fit_sweep(self._bundle._input_data.device_or_host_array, radius_cutoffs, cnn_cutoffs,
-                                          member_cutoff, max_clusters, metric=g.metric.name, ctx=self._fitter.ctx,
+                                          member_cutoff, max_clusters, metric=g.metric, ctx=self._fitter.ctx,
                                           return_labels=return_labels)
         for rec in summary:
             self._bundle._summary.append(rec)

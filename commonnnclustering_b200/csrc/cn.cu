@@ -1035,3 +1035,66 @@ extern "C" int cnnb200_cn_count_rows(cnnb200_ctx *ctx, int64_t n_member_cutoff, 
     }
     return CNNB200_OK;
 }
+
+// Second half of the row-sharded fit: `others` = the parent arrays of all ranks ([world, n] int32, all-gathered by the
+// caller; this rank's own slice included or not -- a union with oneself is a no-op).  Rows another rank knows to be
+// core become singleton trees here too, the forests are merged (hooking towards the smaller root makes the result
+// the same on every rank), then the components are ranked and the labels written: labels == NULL skips the labels
+// (ranks whose caller does not want them), loc = HOST copies them back.
+extern "C" int cnnb200_fit_sharded_end(cnnb200_ctx *ctx, const int32_t *others, int64_t world, int sort_by_size,
+                                       int64_t current_start, int64_t member_cutoff, int64_t max_clusters,
+                                       int64_t *labels, int loc, int64_t *n_clusters_out) {
+    if (!ctx || !others) CNN_FAIL(CNNB200_E_INVALID, "fit_sharded_end: NULL argument");
+    if (!ctx->have_comp) CNN_FAIL(CNNB200_E_STATE, "fit_sharded_end: call fit_sharded_begin first");
+    CNN_TRY(cnnb200_components_merge(ctx, others, world));
+    const ll n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    if (!labels) {
+        if (n_clusters_out) *n_clusters_out = -1;
+        return CNNB200_OK;
+    }
+    if (!sort_by_size) {
+        if (loc == CNNB200_HOST) {  // fresh labels: nothing to upload
+            CNN_TRY(cnn_ensure(ctx, ctx->b_labels, sizeof(ll) * (size_t)n));
+            CNN_CUDA(cudaMemsetAsync(ctx->b_labels.p, 0, sizeof(ll) * (size_t)n, st));
+            CNN_TRY(cnnb200_components_labels(ctx, current_start, ctx->b_labels.as<ll>(), CNNB200_DEVICE, 1, n_clusters_out));
+            CNN_CUDA(cudaMemcpyAsync(labels, ctx->b_labels.p, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            CNN_CUDA(cudaStreamSynchronize(st));
+            return CNNB200_OK;
+        }
+        return cnnb200_components_labels(ctx, current_start, labels, loc, 1, n_clusters_out);
+    }
+    CNN_TRY(cnn_ensure(ctx, ctx->b_labels, sizeof(ll) * (size_t)n));
+    ll *d_labels = loc == CNNB200_HOST ? ctx->b_labels.as<ll>() : labels;
+    unsigned long long *counters = nullptr;
+    CNN_TRY(cnn_labels_fused(ctx, member_cutoff, max_clusters, d_labels, &counters));
+    unsigned long long *h;
+    CNN_TRY(cnn_pinned(ctx, 128, (void **)&h));
+    if (loc == CNNB200_HOST) {
+        Span sp(ctx, T_D2H);
+        CNN_CUDA(cudaMemcpyAsync(labels, d_labels, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    }
+    CNN_CUDA(cudaMemcpyAsync(h, counters, sizeof(ll) * 6, cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaMemcpyAsync(h + 8, ctx->b_stats.p, sizeof(ll) * 4, cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < 4; ++k) ctx->stats[k] = (ll)h[8 + k];
+    if (n_clusters_out) *n_clusters_out = (int64_t)h[0];
+    if (h[2]) {  // more surviving clusters than one CTA ranks: the general chain
+        int64_t nc2 = 0;
+        CNN_TRY(cnnb200_components_labels(ctx, current_start, d_labels, CNNB200_DEVICE, 1, &nc2));
+        ctx->known_max_label = nc2 > 0 ? current_start + nc2 - 1 : 0;
+        CNN_TRY(cnnb200_sort_by_size(ctx, d_labels, CNNB200_DEVICE, n, member_cutoff, max_clusters, nullptr, 0));
+        if (loc == CNNB200_HOST) {
+            CNN_CUDA(cudaMemcpyAsync(labels, d_labels, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            CNN_CUDA(cudaStreamSynchronize(st));
+        }
+        return CNNB200_OK;
+    }
+    ctx->have_lab_summary = true;
+    ctx->lab_summary_n = n;
+    ctx->lab_summary_host[0] = (ll)h[3];
+    ctx->lab_summary_host[1] = (ll)h[4];
+    ctx->lab_summary_host[2] = n - (ll)h[5];
+    ctx->lab_summary_cached = true;
+    return CNNB200_OK;
+}

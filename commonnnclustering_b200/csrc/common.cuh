@@ -112,6 +112,9 @@ struct cnnb200_ctx {
     ll blk_begin = 0, blk_end = 0, blk_goff0 = 0;
     bool blk_single = false, blk_masks = false;
     bool have_cap = false, grid_filter = false;  // candidate-list prefix computed / the fp32 filter serves this grid
+    bool mask_words_pending = false;             // the mask pass ran before the host knew how many words it needs
+    ll mask_words_needed = 0;
+    const ll *mask_total = nullptr;              // device: total words of the last plan
     Buf b_tile_words, b_tile_off, b_masks;       // fp32 filter: words of hit masks per warp tile, their prefix, the masks
     Buf b_cell_count;
 
@@ -215,7 +218,7 @@ static inline int cnn_blocks(ll work_items, int per_block) {
 // --- stage entry points implemented across the .cu files ----------------------------------
 int cnn_grid_build(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric, bool want_cap);
 int cnn_grid_cap(cnnb200_ctx *ctx);
-int cnn_grid_rows(cnnb200_ctx *ctx, ll pb, ll pe, int *deg);
+int cnn_grid_rows(cnnb200_ctx *ctx, ll pb, ll pe, int *deg, bool speculative);
 int cnn_grid_fill(cnnb200_ctx *ctx, ll pb, ll pe, const ll *row_ptr, int *col_idx);
 int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric);
 int cnn_grid_search_periodic(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, bool *served);

@@ -323,8 +323,9 @@ __global__ void __launch_bounds__(GF_WARPS * 32, MINB)
 grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, ll n, const int *__restrict__ cell_sorted,
                  const int *__restrict__ cell_start, GridDesc g, double rc, FilterParams fp, int *__restrict__ deg,
                  const ll *__restrict__ tile_off, unsigned *__restrict__ masks, ll p_begin, ll p_end, ll n_tiles,
-                 unsigned long long *stats, int qpw) {
+                 unsigned long long *stats, int qpw, ll cap_words) {
     __shared__ float4 s_q[GF_WARPS][32];
+    if (tile_off[n_tiles] > cap_words) return;  // launched before the host knew the size: it re-launches after growing
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float4 *qf = s_q[wid];
@@ -563,7 +564,13 @@ int cnn_scan_deg_to_row_ptr(cnnb200_ctx *ctx, const int32_t *deg, ll n, ll *row_
     CNN_CUDA(cudaMemcpyAsync((char *)h + 8, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (ctx->grid_recheck_pending)  // pairs the fp32 filter handed to the exact test (counter next to d_max)
         CNN_CUDA(cudaMemcpyAsync((char *)h + 16, ctx->b_tmp2.as<char>() + 40, sizeof(ll), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->mask_words_pending)
+        CNN_CUDA(cudaMemcpyAsync((char *)h + 24, ctx->mask_total, sizeof(ll), cudaMemcpyDeviceToHost, ctx->stream));
     CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->mask_words_pending) {
+        ctx->mask_words_needed = *(ll *)((char *)h + 24);
+        ctx->stats[ST_DIST] = ctx->mask_words_needed * 32;
+    }
     if (ctx->grid_recheck_pending) {
         ctx->stats[ST_RECHECK] = *(ll *)((char *)h + 16);
         ctx->grid_recheck_pending = false;
@@ -627,7 +634,7 @@ static int scan_int_to_ll(cnnb200_ctx *ctx, const int *in, ll *out, ll count);
 
 // plan + mask pass on the row block [pb, pe): deg[] and the hit masks (b_masks at b_tile_off[])
 template <int D, bool SQRT>
-static int launch_mask(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg) {
+static int launch_mask(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg, bool speculative) {
     cudaStream_t st = ctx->stream;
     int qpw;
     ll n_tiles;
@@ -640,13 +647,21 @@ static int launch_mask(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     CNN_TRY(scan_int_to_ll(ctx, ctx->b_tile_words.as<int>(), ctx->b_tile_off.as<ll>(), n_tiles + 1));
-    ll *h;
-    CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
-    CNN_CUDA(cudaMemcpyAsync(h, ctx->b_tile_off.as<ll>() + n_tiles, sizeof(ll), cudaMemcpyDeviceToHost, st));
-    CNN_CUDA(cudaStreamSynchronize(st));
-    const ll words = h[0];
-    ctx->stats[ST_DIST] = words * 32;
-    CNN_TRY(cnn_ensure(ctx, ctx->b_masks, sizeof(unsigned) * (size_t)words));
+    ctx->mask_total = ctx->b_tile_off.as<ll>() + n_tiles;
+    if (speculative && ctx->b_masks.cap > 0) {
+        // warm context: launch with the capacity at hand; the total travels to the host with the degree scan's
+        // synchronisation (cnn_scan_deg_to_row_ptr) and cnn_grid_check_masks repeats the pass if it did not fit
+        ctx->mask_words_pending = true;
+    } else {
+        ll *h;
+        CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
+        CNN_CUDA(cudaMemcpyAsync(h, ctx->mask_total, sizeof(ll), cudaMemcpyDeviceToHost, st));
+        CNN_CUDA(cudaStreamSynchronize(st));
+        const ll words = h[0];
+        ctx->stats[ST_DIST] = words * 32;
+        ctx->mask_words_pending = false;
+        CNN_TRY(cnn_ensure(ctx, ctx->b_masks, sizeof(unsigned) * (size_t)words));
+    }
     ll blocks = (n_tiles + GF_WARPS - 1) / GF_WARPS;
     const ll cap = (ll)ctx->sm_count * 48;
     if (blocks > cap) blocks = cap;
@@ -655,7 +670,8 @@ static int launch_mask(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg
     CNN_CUDA(cudaMemsetAsync(recheck, 0, sizeof(unsigned long long), st));
     static const int minb = getenv("CNNB200_MASK_MINB") ? atoi(getenv("CNNB200_MASK_MINB")) : 3;
 #define GM_ARGS ctx->b_xs.as<double>(), ctx->b_xf.as<float4>(), ctx->grid_n, cs, cst, ctx->grid, ctx->grid_rc, fp, deg,     \
-                ctx->b_tile_off.as<ll>(), ctx->b_masks.as<unsigned>(), pb, pe, n_tiles, recheck, qpw
+                ctx->b_tile_off.as<ll>(), ctx->b_masks.as<unsigned>(), pb, pe, n_tiles, recheck, qpw,                 \
+                (ll)(ctx->b_masks.cap / sizeof(unsigned))
     if (minb == 3) grid_mask_kernel<D, SQRT, 3><<<(int)blocks, GF_WARPS * 32, 0, st>>>(GM_ARGS);
     else if (minb == 2) grid_mask_kernel<D, SQRT, 2><<<(int)blocks, GF_WARPS * 32, 0, st>>>(GM_ARGS);
     else grid_mask_kernel<D, SQRT, 4><<<(int)blocks, GF_WARPS * 32, 0, st>>>(GM_ARGS);
@@ -666,15 +682,15 @@ static int launch_mask(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg
     return CNNB200_OK;
 }
 
-static int launch_mask_any(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg) {
+static int launch_mask_any(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg, bool speculative) {
     bool sq = ctx->grid_metric == CNNB200_METRIC_EUCLIDEAN;
     switch (ctx->grid.d * 2 + (sq ? 1 : 0)) {
-        case 2: return launch_mask<1, false>(ctx, pb, pe, fp, deg);
-        case 3: return launch_mask<1, true>(ctx, pb, pe, fp, deg);
-        case 4: return launch_mask<2, false>(ctx, pb, pe, fp, deg);
-        case 5: return launch_mask<2, true>(ctx, pb, pe, fp, deg);
-        case 6: return launch_mask<3, false>(ctx, pb, pe, fp, deg);
-        default: return launch_mask<3, true>(ctx, pb, pe, fp, deg);
+        case 2: return launch_mask<1, false>(ctx, pb, pe, fp, deg, speculative);
+        case 3: return launch_mask<1, true>(ctx, pb, pe, fp, deg, speculative);
+        case 4: return launch_mask<2, false>(ctx, pb, pe, fp, deg, speculative);
+        case 5: return launch_mask<2, true>(ctx, pb, pe, fp, deg, speculative);
+        case 6: return launch_mask<3, false>(ctx, pb, pe, fp, deg, speculative);
+        default: return launch_mask<3, true>(ctx, pb, pe, fp, deg, speculative);
     }
 }
 
@@ -840,7 +856,7 @@ int cnn_grid_build(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radiu
 
 // ---- K2 on a row block [pb, pe) of the cell-sorted points: degrees + what the fill needs (hit masks, or the
 // gapped hits of the f64 form) ----------------------------------------------------------------------------------
-int cnn_grid_rows(cnnb200_ctx *ctx, ll pb, ll pe, int *deg) {
+int cnn_grid_rows(cnnb200_ctx *ctx, ll pb, ll pe, int *deg, bool speculative) {
     cudaStream_t st = ctx->stream;
     ctx->blk_begin = pb;
     ctx->blk_end = pe;
@@ -849,7 +865,7 @@ int cnn_grid_rows(cnnb200_ctx *ctx, ll pb, ll pe, int *deg) {
     if (ctx->grid_filter && filter_params(ctx, &fp)) {
         Span sp(ctx, T_SEARCH_COUNT);
         ctx->blk_masks = true;
-        return launch_mask_any(ctx, pb, pe, fp, deg);
+        return launch_mask_any(ctx, pb, pe, fp, deg, speculative);
     }
     ctx->blk_masks = false;
     CNN_TRY(cnn_grid_cap(ctx));
@@ -900,9 +916,16 @@ int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radi
     CNN_TRY(cnn_ensure(ctx, ctx->b_deg, sizeof(int) * (size_t)(n + 1)));
     CNN_TRY(cnn_ensure(ctx, ctx->b_row_ptr, sizeof(ll) * (size_t)(n + 1)));
     CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>() + n, 0, sizeof(int), st));
-    CNN_TRY(cnn_grid_rows(ctx, 0, n, ctx->b_deg.as<int>()));
+    CNN_TRY(cnn_grid_rows(ctx, 0, n, ctx->b_deg.as<int>(), true));
     ll nnz = 0, max_deg = 0;
     CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
+    if (ctx->mask_words_pending) {
+        ctx->mask_words_pending = false;
+        if ((size_t)ctx->mask_words_needed * sizeof(unsigned) > ctx->b_masks.cap) {  // the masks did not fit: grow, repeat
+            CNN_TRY(cnn_grid_rows(ctx, 0, n, ctx->b_deg.as<int>(), false));
+            CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
+        }
+    }
     CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
     CNN_TRY(cnn_grid_fill(ctx, 0, n, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>()));
     ctx->n = n;
@@ -1012,7 +1035,7 @@ extern "C" int cnnb200_grid_degrees(cnnb200_ctx *ctx, int64_t row_begin, int64_t
     if (row_begin < 0 || row_end > ctx->grid_n || row_begin > row_end)
         CNN_FAIL(CNNB200_E_INVALID, "grid_degrees: bad row range");
     CNN_CUDA(cudaSetDevice(ctx->device));
-    return cnn_grid_rows(ctx, row_begin, row_end, deg);
+    return cnn_grid_rows(ctx, row_begin, row_end, deg, false);
 }
 
 extern "C" int cnnb200_grid_fill(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end, const int64_t *row_ptr,
@@ -1039,5 +1062,111 @@ extern "C" int cnnb200_neighbours_adopt(cnnb200_ctx *ctx, const int64_t *row_ptr
     ctx->have_comp = false;
     ctx->have_points = false;
     ctx->have_other = false;
+    return CNNB200_OK;
+}
+
+// ---- the row-sharded fit on coordinates as TWO calls per rank ---------------------------------------------------------
+// begin:  cell sort (replicated), row blocks balanced by candidate pairs, this rank's block + halo searched, the
+//         candidate edges of the block settled on a private parent array.  Three host synchronisations (bounding box,
+//         block/halo bounds, nnz), no library kernels other than CUB, nothing in Python between the stages.
+// (the caller all-gathers the parent arrays: cnnb200_components_parents)
+// end:    cnnb200_fit_sharded_end (cn.cu): merge, ranking of the components, labels.
+__global__ void block_ranges_kernel(const ll *__restrict__ goff, const int *__restrict__ cell_sorted,
+                                    const int *__restrict__ cell_start, GridDesc g, ll n, int parts, int rank, ll *out) {
+    // out[0 .. parts] = block bounds; out[parts + 1], out[parts + 2] = halo of block `rank`
+    __shared__ ll s_bounds[1026];
+    for (int k = threadIdx.x; k <= parts; k += blockDim.x) {
+        ll b;
+        if (k == 0) b = 0;
+        else if (k == parts) b = n;
+        else {
+            const ll total = goff[n];
+            const ll target = (ll)((double)total * k / parts);
+            ll lo = 0, hi = n;
+            while (lo < hi) {
+                ll mid = (lo + hi) >> 1;
+                if (goff[mid] < target) lo = mid + 1; else hi = mid;
+            }
+            lo = (lo + 16) / 32 * 32;
+            b = lo > n ? n : lo;
+        }
+        s_bounds[k] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k <= parts; ++k)
+            if (s_bounds[k] < s_bounds[k - 1]) s_bounds[k] = s_bounds[k - 1];
+        for (int k = 0; k <= parts; ++k) out[k] = s_bounds[k];
+        const ll rb = s_bounds[rank], re = s_bounds[rank + 1];
+        ll lo = rb, hi = re;
+        if (re > rb) {
+            // cell ids are x-fastest: the window of cell id c lies within [c - reach, c + reach]
+            const ll ncell = (ll)g.dims[0] * g.dims[1] * g.dims[2];
+            const ll reach = (g.d > 2 ? (ll)g.dims[0] * g.dims[1] : 0) + (g.d > 1 ? g.dims[0] : 0) + 1;
+            ll c_lo = (ll)cell_sorted[rb] - reach, c_hi = (ll)cell_sorted[re - 1] + reach + 1;
+            if (c_lo < 0) c_lo = 0;
+            if (c_hi > ncell) c_hi = ncell;
+            const ll a = cell_start[c_lo], b = cell_start[c_hi];
+            lo = a < rb ? a : rb;
+            hi = b > re ? b : re;
+        }
+        out[parts + 1] = lo;
+        out[parts + 2] = hi;
+    }
+}
+
+extern "C" int cnnb200_fit_sharded_begin(cnnb200_ctx *ctx, const double *x, int loc, int64_t n, int64_t d,
+                                         double radius_cutoff, int metric, int64_t n_member_cutoff,
+                                         int64_t similarity_cutoff, int rank, int world, int64_t *bounds,
+                                         int32_t **parents) {
+    if (!ctx || !x || !bounds || !parents) CNN_FAIL(CNNB200_E_INVALID, "fit_sharded_begin: NULL argument");
+    if (world < 1 || world > 1024 || rank < 0 || rank >= world) CNN_FAIL(CNNB200_E_INVALID, "fit_sharded_begin: bad rank / world");
+    CNN_TRY(cnnb200_grid_begin(ctx, x, loc, n, d, radius_cutoff, metric));
+    cudaStream_t st = ctx->stream;
+    // block bounds and this rank's halo, computed on the device, one small copy back
+    CNN_TRY(cnn_ensure(ctx, ctx->b_bbox, sizeof(ll) * (size_t)(world + 3)));
+    block_ranges_kernel<<<1, 256, 0, st>>>(ctx->b_tmp1.as<ll>(), ctx->b_cell_id_sorted.as<int>(), ctx->b_cell_start.as<int>(),
+                                           ctx->grid, n, world, rank, ctx->b_bbox.as<ll>());
+    CNN_LAUNCHED(ctx, 1);
+    CNN_KERNEL_CHECK();
+    ll *h;
+    CNN_TRY(cnn_pinned(ctx, sizeof(ll) * (size_t)(world + 3), (void **)&h));
+    CNN_CUDA(cudaMemcpyAsync(h, ctx->b_bbox.p, sizeof(ll) * (size_t)(world + 3), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k <= world; ++k) bounds[k] = h[k];
+    const ll rb = h[rank], re = h[rank + 1], lo = h[world + 1], hi = h[world + 2];
+    // rows [lo, hi): degrees (row-indexed, zero elsewhere), offsets, entries
+    CNN_TRY(cnn_ensure(ctx, ctx->b_deg, sizeof(int) * (size_t)(n + 1)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_row_ptr, sizeof(ll) * (size_t)(n + 1)));
+    CNN_CUDA(cudaMemsetAsync(ctx->b_deg.p, 0, sizeof(int) * (size_t)(n + 1), st));
+    ll nnz = 0, max_deg = 0;
+    if (hi > lo) {
+        CNN_TRY(cnn_grid_rows(ctx, lo, hi, ctx->b_deg.as<int>(), true));
+        CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
+        if (ctx->mask_words_pending) {
+            ctx->mask_words_pending = false;
+            if ((size_t)ctx->mask_words_needed * sizeof(unsigned) > ctx->b_masks.cap) {
+                CNN_TRY(cnn_grid_rows(ctx, lo, hi, ctx->b_deg.as<int>(), false));
+                CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));
+            }
+        }
+        CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
+        CNN_TRY(cnn_grid_fill(ctx, lo, hi, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>()));
+    } else {
+        CNN_CUDA(cudaMemsetAsync(ctx->b_row_ptr.p, 0, sizeof(ll) * (size_t)(n + 1), st));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, 16));
+    }
+    ctx->n = n;
+    ctx->nnz = nnz;
+    ctx->max_deg = max_deg;
+    ctx->row_ptr = ctx->b_row_ptr.as<ll>();
+    ctx->col_idx = ctx->b_col_idx.as<int>();
+    ctx->perm = ctx->b_perm.as<int>();
+    ctx->have_nb = true;
+    ++ctx->nb_version;
+    ctx->stats[ST_PATH] = (ctx->stats[ST_PATH] & ~15ll) | 1;
+    CNN_TRY(cnnb200_components_begin(ctx, n_member_cutoff, similarity_cutoff, nullptr, CNNB200_DEVICE));
+    if (re > rb) CNN_TRY(cnnb200_components_edges(ctx, rb, re));
+    *parents = ctx->b_parent.as<int>();
     return CNNB200_OK;
 }

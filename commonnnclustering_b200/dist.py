@@ -123,54 +123,79 @@ class ShardedFit:
         return bounds
 
     # -- neighbourhoods from a precomputed CSR: each rank uploads only its row block ------------------
-    def neighbours_from_csr_host(self, row_ptr_host, col_idx_host):
-        """row_ptr int64 [n+1] / col_idx int32|int64 [nnz] in host memory (every rank sees the arrays,
-        e.g. memory-mapped; each rank reads and uploads only its own rows)."""
-        ctx, G = self.ctx, self.world
+    def upload_csr_block(self, row_ptr_host, col_idx_host):
+        """Host CSR (row_ptr int64 [n+1], col_idx int32 [nnz]; every rank sees the arrays, e.g. memory-mapped) ->
+        this rank's rows in HBM: its slice of ``row_ptr`` and of ``col_idx``, each copied straight into its place in
+        the full-size device buffers (the exchange fills the rest).  Row blocks are balanced by entries; the arrays
+        are page-locked in place once, so the G uploads run concurrently at PCIe speed, 1/G of the bytes each."""
+        G = self.world
         n = row_ptr_host.shape[0] - 1
         nnz = int(row_ptr_host[-1])
         from . import _lib
 
-        for a in (row_ptr_host, col_idx_host):   # page-lock in place, once per array: uploads at PCIe speed
+        for a in (row_ptr_host, col_idx_host):
             key = (a.ctypes.data, a.nbytes)
             if key not in self._registered:
                 self._registered[key] = _lib.host_register(a)
-        # balance by entries
-        targets = (np.arange(G + 1, dtype=np.float64) * nnz / G).astype(np.int64)
-        bounds = np.searchsorted(row_ptr_host, targets, side="left").astype(np.int64)
-        bounds[0], bounds[-1] = 0, n
-        bounds = np.maximum.accumulate(bounds)
-        slice_bounds = row_ptr_host[bounds]
-        s, e = int(slice_bounds[self.rank]), int(slice_bounds[self.rank + 1])
-        row_ptr = torch.from_numpy(np.ascontiguousarray(row_ptr_host)).to(self.device)
-        col_idx = torch.empty(max(nnz, 1), dtype=torch.int32, device=self.device)[:nnz]
-        mine = torch.from_numpy(np.ascontiguousarray(col_idx_host[s:e]))
-        col_idx[s:e].copy_(mine.to(self.device, non_blocking=True).to(torch.int32))
-        exchange_slices(col_idx, slice_bounds, self.group)
-        max_deg = int(np.diff(row_ptr_host).max()) if n else 0
-        ctx.neighbours_adopt(row_ptr, col_idx, max_deg, grid_perm=False)
-        self.last = dict(bounds=bounds, slice_bounds=slice_bounds, nnz=nnz)
+        key = (row_ptr_host.ctypes.data, n, nnz, G)
+        plan = getattr(self, "_csr_plan", None)
+        if plan is None or plan[0] != key:     # bounds depend on the offsets only: computed once per structure
+            targets = (np.arange(G + 1, dtype=np.float64) * nnz / G).astype(np.int64)
+            bounds = np.searchsorted(row_ptr_host, targets, side="left").astype(np.int64)
+            bounds[0], bounds[-1] = 0, n
+            bounds = np.maximum.accumulate(bounds)
+            slice_bounds = row_ptr_host[bounds].astype(np.int64)
+            row_ptr = torch.empty(n + 1, dtype=torch.int64, device=self.device)
+            col_idx = torch.empty(max(nnz, 1), dtype=torch.int32, device=self.device)[:nnz]
+            plan = self._csr_plan = (key, bounds, slice_bounds, row_ptr, col_idx)
+        _, bounds, slice_bounds, row_ptr, col_idx = plan
+        b, e = block_of(bounds, self.rank)
+        s, t = int(slice_bounds[self.rank]), int(slice_bounds[self.rank + 1])
+        hi = e + 1 if self.rank == G - 1 else e     # the last rank also owns row_ptr[n]
+        row_ptr[b:hi].copy_(torch.from_numpy(row_ptr_host[b:hi]), non_blocking=True)
+        if col_idx_host.dtype == np.int32:
+            col_idx[s:t].copy_(torch.from_numpy(col_idx_host[s:t]), non_blocking=True)
+        else:
+            col_idx[s:t].copy_(torch.from_numpy(np.ascontiguousarray(col_idx_host[s:t])).to(self.device, non_blocking=True))
+        return dict(n=n, nnz=nnz, bounds=bounds, slice_bounds=slice_bounds, row_ptr=row_ptr, col_idx=col_idx)
+
+    def exchange_csr(self, blk):
+        """Exchange 1 of SURVEY 8e on rows that already sit in HBM: the slices of ``row_ptr`` and ``col_idx`` are
+        broadcast from their owners into every rank's full-size buffers (NCCL over NVLink); the gathered CSR is
+        adopted.  Returns the row-block bounds."""
+        G, bounds = self.world, blk["bounds"]
+        rb = np.array(bounds, dtype=np.int64)
+        rb[-1] += 1
+        exchange_slices(blk["row_ptr"], rb, self.group)
+        exchange_slices(blk["col_idx"], blk["slice_bounds"], self.group)
+        self.ctx.neighbours_adopt(blk["row_ptr"], blk["col_idx"], -1, grid_perm=False)
+        self.last = dict(bounds=bounds, slice_bounds=blk["slice_bounds"], nnz=blk["nnz"])
         return bounds
+
+    def neighbours_from_csr_host(self, row_ptr_host, col_idx_host):
+        return self.exchange_csr(self.upload_csr_block(row_ptr_host, col_idx_host))
 
     # -- components on the gathered CSR, rows sharded ----------------------------------------------------
     def fit(self, bounds, n_member_cutoff, similarity_cutoff, labels, current_start=1, sort_by_size=True,
             member_cutoff=None, max_clusters=None):
+        """Components of the adopted (gathered) CSR: every rank settles the candidate edges of its row block,
+        all-gather of the parent arrays, merge + ranking + labels (``cnnb200_fit_sharded_end``); ``labels`` may be
+        ``None`` on ranks whose caller does not want them."""
         ctx = self.ctx
         n = int(bounds[-1])
         b, e = block_of(bounds, self.rank)
         ctx.components_begin(n_member_cutoff, similarity_cutoff)
         ctx.components_edges(b, e)
-        parents = tensor_from_ptr(ctx.components_parents_ptr(), (n,), "<i4", self.device)
-        gathered = gather_parents(parents, self.group)
-        ctx.components_merge(gathered, self.world)
-        on_host = isinstance(labels, np.ndarray)
-        lab_dev = torch.zeros(n, dtype=torch.int64, device=self.device) if on_host else labels.zero_()
-        n_clusters = ctx.components_labels(current_start, lab_dev, fresh=True)
-        if sort_by_size:
-            ctx.sort_by_size(lab_dev, member_cutoff, max_clusters)
-        if on_host:
-            torch.from_numpy(labels).copy_(lab_dev)  # D2H (synchronises)
-        return n_clusters
+        pptr = ctx.components_parents_ptr()
+        key = (pptr, n)
+        if getattr(self, "_parents_key", None) != key:
+            self._parents_key, self._parents = key, tensor_from_ptr(pptr, (n,), "<i4", self.device)
+        gathered = self._gather_buffer(n)
+        if gathered.is_cuda:
+            dist.all_gather_into_tensor(gathered, self._parents, group=self.group)
+        else:
+            dist.all_gather(list(gathered.unbind(0)), self._parents, group=self.group)
+        return ctx.fit_sharded_end(gathered, self.world, labels, sort_by_size, current_start, member_cutoff, max_clusters)
 
     def upload_points(self, x):
         """Host coordinates (every rank sees the same array) -> replicated device copy.  Each rank uploads only its
@@ -192,10 +217,32 @@ class ShardedFit:
         dist.all_gather_into_tensor(xd, mine, group=self.group)    # in place: `mine` is this rank's slice of `xd`
         return xd[:n]
 
+    def _gather_buffer(self, n):
+        buf = getattr(self, "_gathered", None)
+        if buf is None or buf.shape[1] != n:
+            buf = self._gathered = torch.empty((self.world, n), dtype=torch.int32, device=self.device)
+        return buf
+
     def fit_points(self, x, radius_cutoff, n_member_cutoff, similarity_cutoff, labels, current_start=1,
                    metric="euclidean_r", sort_by_size=True, member_cutoff=None, max_clusters=None, exchange=False, **_):
+        """The whole row-sharded fit: two C calls per rank (``cnnb200_fit_sharded_begin`` / ``_end``) with ONE
+        collective between them, the all-gather of the parent arrays.  ``labels`` may be ``None`` on ranks whose
+        caller does not want them (they only take part in the merge); ``exchange=True`` runs the CSR all-gather
+        layout of the precomputed-neighbourhood path on coordinates instead (kept for comparison)."""
         if isinstance(x, np.ndarray) and self.world > 1 and x.flags.c_contiguous and x.dtype == np.float64:
             x = self.upload_points(x)
-        bounds = self.neighbours_from_points(x, radius_cutoff, metric, exchange=exchange)
-        return self.fit(bounds, n_member_cutoff, similarity_cutoff, labels, current_start, sort_by_size,
-                        member_cutoff, max_clusters)
+        if exchange:
+            bounds = self.neighbours_from_points(x, radius_cutoff, metric, exchange=True)
+            return self.fit(bounds, n_member_cutoff, similarity_cutoff, labels, current_start, sort_by_size,
+                            member_cutoff, max_clusters)
+        ctx = self.ctx
+        n = x.shape[0]
+        bounds, pptr = ctx.fit_sharded_begin(x, radius_cutoff, n_member_cutoff, similarity_cutoff, self.rank, self.world,
+                                             metric)
+        key = (pptr, n)
+        if getattr(self, "_parents_key", None) != key:
+            self._parents_key, self._parents = key, tensor_from_ptr(pptr, (n,), "<i4", self.device)
+        gathered = self._gather_buffer(n)
+        dist.all_gather_into_tensor(gathered, self._parents, group=self.group)
+        self.last = dict(bounds=bounds)
+        return ctx.fit_sharded_end(gathered, self.world, labels, sort_by_size, current_start, member_cutoff, max_clusters)

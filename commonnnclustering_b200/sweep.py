@@ -33,8 +33,20 @@ def fit_sweep(x, radius_cutoffs, cnn_cutoffs, member_cutoff=None, max_clusters=N
     """
     import torch
 
+    from . import _types
+
     if ctx is None:
         ctx = _lib.default_context()
+    # the metric decides how a radius becomes the cutoff the search compares with (`adjust_radius`) and may carry
+    # state the context needs (periods); a name stands for the metric without state
+    if isinstance(metric, str):
+        if metric not in ("euclidean_r", "euclidean"):
+            raise ValueError(f"fit_sweep: pass a Metric object for {metric!r} (it carries state), or use euclidean / euclidean_r")
+        metric = _types.MetricEuclideanReduced() if metric == "euclidean_r" else _types.MetricEuclidean()
+    if isinstance(metric, _types.MetricPrecomputed):
+        raise ValueError("fit_sweep works on coordinates: a distance matrix has no radius search to share between cells")
+    if isinstance(metric, _types.MetricEuclideanPeriodicReduced):
+        ctx.set_periodic_bounds(metric.bounds)
     dev = torch.device("cuda", ctx.device)
     xd = x if hasattr(x, "is_cuda") else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
     xd = xd.to(dev)
@@ -52,8 +64,7 @@ def fit_sweep(x, radius_cutoffs, cnn_cutoffs, member_cutoff=None, max_clusters=N
     c_min = min(cnn_cutoffs)
     for ir, r in enumerate(radius_cutoffs):
         t0 = time.perf_counter()
-        rc = r * r if metric == "euclidean_r" else r
-        nnz = ctx.neighbours_from_points(xd, rc, metric=metric)
+        nnz = ctx.neighbours_from_points(xd, metric.adjust_radius(r), metric=metric.name)
         counts = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
         ctx.cn_count(c_min + 1, counts)          # self-counting neighbourhoods: member cutoff c + 1
         torch.cuda.synchronize(dev)

@@ -226,6 +226,26 @@ int cnnb200_components_labels(cnnb200_ctx *ctx, int64_t current_start, int64_t *
                               int fresh, int64_t *n_clusters_out);
 
 /* ---------------------------------------------------------------------------------------
+ * The row-sharded fit on coordinates (d <= 3) as two calls per rank with ONE collective between them
+ * (replaces FitterExtBFS._fit, _fit.pyx:408-491, plus Labels.sort_by_size,
+ * _types.pyx:212-286, for one process per GPU):
+ *   fit_sharded_begin  cell sort (replicated), row blocks bounds[0..world] (HOST out) balanced by candidate
+ *                      pairs, block `rank` plus its halo searched, the block's candidate edges settled on a
+ *                      private parent array; *parents = DEVICE int32 [n] to all-gather.
+ *   (all-gather of the parent arrays: [world, n] int32)
+ *   fit_sharded_end    merge of the forests (identical on every rank), then -- where `labels` is not NULL --
+ *                      the ranking of the components and the labels (sort_by_size != 0: size-sorted as
+ *                      cnnb200_fit_points delivers them; 0: numbered from current_start as the BFS does).
+ * ------------------------------------------------------------------------------------- */
+int cnnb200_fit_sharded_begin(cnnb200_ctx *ctx, const double *x, int loc, int64_t n, int64_t d,
+                              double radius_cutoff, int metric, int64_t n_member_cutoff,
+                              int64_t similarity_cutoff, int rank, int world, int64_t *bounds,
+                              int32_t **parents);
+int cnnb200_fit_sharded_end(cnnb200_ctx *ctx, const int32_t *others, int64_t world, int sort_by_size,
+                            int64_t current_start, int64_t member_cutoff, int64_t max_clusters,
+                            int64_t *labels, int loc, int64_t *n_clusters_out);
+
+/* ---------------------------------------------------------------------------------------
  * Prediction for points OUTSIDE the clustered set.  Replaces PredictorFirstmatch.predict
  * (_fit.pyx:1231-1291) with NeighboursGetterExtBruteForce._get_other (_types.pyx:1712-1731) or
  * NeighboursGetterExtLookup._get_other (:1819-1832).

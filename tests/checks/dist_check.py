@@ -22,9 +22,22 @@ for n, r, c, mc in [(20000, 0.25, 10, None), (300000, 0.13, 20, 10)]:
     x = datasets.md_like_3d(n)
     lab = np.empty(n, dtype=np.int64)
     sf.fit_points(x, r * r, c + 1, c + 2, lab, member_cutoff=mc)
+    # device-resident coordinates and labels; labels only on rank 0 (the other ranks take part in the merge only)
+    xd = torch.from_numpy(x).cuda()
+    lab_d = torch.full((n,), -7, dtype=torch.int64, device="cuda") if rank == 0 else None
+    sf.fit_points(xd, r * r, c + 1, c + 2, lab_d, member_cutoff=mc)
+    # unsorted numbering (FitterExtBFS's own labels)
+    lab_u = np.empty(n, dtype=np.int64)
+    sf.fit_points(x, r * r, c + 1, c + 2, lab_u, sort_by_size=False)
+    single_u = np.empty(n, dtype=np.int64)
+    c0 = _lib.Context(local)
+    c0.neighbours_from_points(x, r * r)
+    c0.fit(c + 1, c + 2, 1, single_u, None)
     single = np.empty(n, dtype=np.int64)
     _lib.Context(local).fit_points(x, r * r, c + 1, c + 2, single, member_cutoff=mc)
-    same = np.array_equal(lab, single)
+    same = np.array_equal(lab, single) and np.array_equal(lab_u, single_u)
+    if rank == 0:
+        same &= np.array_equal(lab_d.cpu().numpy(), single)
     lab_x = np.empty(n, dtype=np.int64)
     sf.fit_points(x, r * r, c + 1, c + 2, lab_x, member_cutoff=mc, exchange=True)   # CSR all-gather layout
     same &= np.array_equal(lab_x, single)

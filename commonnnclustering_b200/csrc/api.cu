@@ -104,7 +104,7 @@ extern "C" int cnnb200_ctx_create(int device, cnnb200_ctx **out) {
 }
 
 #define FOR_EACH_BUF(c, F)                                                                          \
-    F(c->b_row_ptr) F(c->b_col_idx) F(c->b_perm) F(c->b_deg) F(c->b_x) F(c->b_wrows) F(c->b_wcnt) F(c->b_lab_summary) F(c->b_bounds) F(c->b_xs) F(c->b_xf) F(c->b_xperm) F(c->b_o_x) F(c->b_o_deg) F(c->b_o_row_ptr) F(c->b_o_col_idx) F(c->b_o_labels) F(c->b_cell_id)   \
+    F(c->b_row_ptr) F(c->b_col_idx) F(c->b_col_spare) F(c->b_o_col_sorted) F(c->b_perm) F(c->b_deg) F(c->b_x) F(c->b_wrows) F(c->b_wcnt) F(c->b_lab_summary) F(c->b_bounds) F(c->b_xs) F(c->b_xf) F(c->b_xperm) F(c->b_o_x) F(c->b_o_deg) F(c->b_o_row_ptr) F(c->b_o_col_idx) F(c->b_o_labels) F(c->b_cell_id)   \
     F(c->b_cell_id_sorted) F(c->b_idx) F(c->b_cell_start) F(c->b_bbox) F(c->b_cub) F(c->b_tmp0)     \
     F(c->b_tmp1) F(c->b_tmp2) F(c->b_parent) F(c->b_core) F(c->b_above) F(c->b_edges) F(c->b_worklist) F(c->b_cell_count) F(c->b_minorig) F(c->b_flags)             \
     F(c->b_rank) F(c->b_labels) F(c->b_consider) F(c->b_stats) F(c->b_lab_count) F(c->b_lab_first)  \

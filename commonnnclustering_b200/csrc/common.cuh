@@ -101,7 +101,7 @@ struct cnnb200_ctx {
     const ll *row_ptr = nullptr;       // [n+1]  (points into b_row_ptr or borrowed memory)
     const int32_t *col_idx = nullptr;  // [nnz]
     const int32_t *perm = nullptr;     // [n] internal -> caller index; nullptr = identity
-    Buf b_row_ptr, b_col_idx, b_perm, b_deg;
+    Buf b_row_ptr, b_col_idx, b_col_spare, b_perm, b_deg;
 
     // ---- uniform grid of the last cnn_grid_build + the row block being searched ---------------
     bool have_grid = false;
@@ -137,7 +137,8 @@ struct cnnb200_ctx {
     int pts_metric = 0;
     bool have_other = false;
     ll o_m = 0, o_nnz = 0;
-    Buf b_o_x, b_o_deg, b_o_row_ptr, b_o_col_idx, b_o_labels;
+    Buf b_o_x, b_o_deg, b_o_row_ptr, b_o_col_idx, b_o_col_sorted, b_o_labels;
+    const int *o_col_orig = nullptr;  // the predictand lists in the order they were given (first-match order), when they had to be sorted
 
     // ---- bit-packed rows (packed.cu): valid while packed_version == nb_version --------------------------------------
     ll nb_version = 0, packed_version = -1, packed_words = 0;
@@ -225,6 +226,9 @@ int cnn_grid_search_periodic(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, do
 int cnn_dense_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric,
                      int method);
 int cnn_labels_fused(cnnb200_ctx *ctx, ll member_cutoff, ll max_clusters, ll *d_labels, unsigned long long **counters_out);
+int cnn_sort_csr_rows(cnnb200_ctx *ctx, const ll *row_ptr, const int *col, ll n, ll nnz, Buf &out);
+int cnn_csr_rows_unsorted(cnnb200_ctx *ctx, const ll *row_ptr, const int *col, ll n, int *unsorted);
+int cnn_ensure_sorted_rows(cnnb200_ctx *ctx, bool known_unsorted, int *sorted_out);
 int cnn_finish_csr(cnnb200_ctx *ctx, ll n, ll nnz, ll max_deg, const ll *row_ptr, const int *col_idx);
 int cnn_pack_rows(cnnb200_ctx *ctx, bool *usable_out);
 int cnn_worklist_packed(cnnb200_ctx *ctx, const int2 *worklist, const unsigned long long *wl_count, int cutoff, int *parent);

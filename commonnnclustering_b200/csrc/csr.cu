@@ -38,6 +38,26 @@ __global__ void range_check_kernel(const int *__restrict__ in, ll m, ll n, int *
     if (bad) *flag = 1;
 }
 
+// warp per row: indices inside [0, n) (flag[0]) and rows ascending (flag[2]); one read of col_idx for both.  Rows whose
+// bounds are not monotone are skipped here (deg_from_row_ptr_kernel reports them).
+__global__ void rows_check_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col, ll n, ll nnz, int *flag) {
+    const int lane = threadIdx.x & 31;
+    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    bool bad = false, unsorted = false;
+    for (ll r = warp; r < n; r += nwarps) {
+        const ll b = row_ptr[r], e = row_ptr[r + 1];
+        if (b < 0 || e > nnz || b > e) continue;
+        for (ll k = b + lane; k < e; k += 32) {
+            const int v = col[k];
+            bad |= v < 0 || v >= n;
+            if (k + 1 < e) unsorted |= v > col[k + 1];
+        }
+    }
+    if (bad) flag[0] = 1;
+    if (unsorted) flag[2] = 1;
+}
+
 __global__ void deg_from_row_ptr_kernel(const ll *__restrict__ row_ptr, ll n, int *deg, int *flag) {
     ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
     if (i > n) return;
@@ -119,18 +139,16 @@ extern "C" int cnnb200_neighbours_from_csr(cnnb200_ctx *ctx, const int64_t *row_
     const int *d_col;
     CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
     int *flag = ctx->b_tmp2.as<int>();
-    CNN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    CNN_CUDA(cudaMemsetAsync(flag, 0, 4 * sizeof(int), st));
     if (loc == CNNB200_DEVICE && borrow && idx_bytes == 4) {
         d_row_ptr = (const ll *)row_ptr;
         d_col = (const int *)col_idx;
-        range_check_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_col, nnz, n, flag);
     } else {
         CNN_TRY(cnn_ensure(ctx, ctx->b_row_ptr, sizeof(ll) * (size_t)(n + 1)));
         CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
         CNN_CUDA(cudaMemcpyAsync(ctx->b_row_ptr.p, row_ptr, sizeof(ll) * (size_t)(n + 1), kind, st));
         if (idx_bytes == 4) {
             CNN_CUDA(cudaMemcpyAsync(ctx->b_col_idx.p, col_idx, sizeof(int) * (size_t)nnz, kind, st));
-            range_check_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->b_col_idx.as<int>(), nnz, n, flag);
         } else {
             // stage int64 indices in chunks and narrow them on the device
             const ll chunk = 32ll << 20;  // 32 Mi entries = 256 MB
@@ -151,9 +169,14 @@ extern "C" int cnnb200_neighbours_from_csr(cnnb200_ctx *ctx, const int64_t *row_
         d_col = ctx->b_col_idx.as<int>();
     }
     CNN_KERNEL_CHECK();
-    // degrees (for max_deg and a monotonicity check of row_ptr)
+    // degrees (for max_deg and a monotonicity check of row_ptr), then index range + ascending rows in one pass
     CNN_TRY(cnn_ensure(ctx, ctx->b_deg, sizeof(int) * (size_t)(n + 1)));
     deg_from_row_ptr_kernel<<<cnn_blocks(n + 1, 256), 256, 0, st>>>(d_row_ptr, n, ctx->b_deg.as<int>(), flag);
+    {
+        ll blocks = (n + 7) / 8;
+        if (blocks > (ll)ctx->sm_count * 32) blocks = (ll)ctx->sm_count * 32;
+        rows_check_kernel<<<(int)blocks, 256, 0, st>>>(d_row_ptr, d_col, n, nnz, flag);
+    }
     CNN_KERNEL_CHECK();
     size_t need = 0;
     CNN_CUDA(cub::DeviceReduce::Max(nullptr, need, ctx->b_deg.as<int>(), flag + 1, (int)(n + 1), st));
@@ -162,10 +185,13 @@ extern "C" int cnnb200_neighbours_from_csr(cnnb200_ctx *ctx, const int64_t *row_
     CNN_CUDA(cub::DeviceReduce::Max(ctx->b_cub.p, cap, ctx->b_deg.as<int>(), flag + 1, (int)(n + 1), st));
     int *h;
     CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
-    CNN_CUDA(cudaMemcpyAsync(h, flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaMemcpyAsync(h, flag, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CNN_CUDA(cudaStreamSynchronize(st));
     if (h[0]) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_csr: row_ptr not monotone or an index outside [0, n)");
-    return cnn_finish_csr(ctx, n, nnz, h[1], d_row_ptr, d_col);
+    const bool unsorted = h[2] != 0;
+    CNN_TRY(cnn_finish_csr(ctx, n, nnz, h[1], d_row_ptr, d_col));
+    if (unsorted) CNN_TRY(cnn_ensure_sorted_rows(ctx, true, nullptr));  // lists in any order: sorted on arrival
+    return CNNB200_OK;
 }
 
 extern "C" int cnnb200_neighbours_from_padded(cnnb200_ctx *ctx, const int64_t *padded, const int64_t *counts,
@@ -221,7 +247,8 @@ extern "C" int cnnb200_neighbours_from_padded(cnnb200_ctx *ctx, const int64_t *p
     }
     CNN_TRY(read_flag(ctx, flag, &bad));
     if (bad) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_padded: a neighbour index is outside [0, n)");
-    return cnn_finish_csr(ctx, n, nnz, md, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
+    CNN_TRY(cnn_finish_csr(ctx, n, nnz, md, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>()));
+    return cnn_ensure_sorted_rows(ctx, false, nullptr);  // lists in any order: sorted on arrival
 }
 
 // ---- export in the caller's index space ----------------------------------------------------------

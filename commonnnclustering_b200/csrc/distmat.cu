@@ -181,35 +181,18 @@ __global__ void keys_low_kernel(const unsigned long long *__restrict__ keys, ll 
     if (k < nnz) col_idx[k] = (int)(unsigned)(keys[k] & 0xffffffffull);
 }
 
-extern "C" int cnnb200_neighbours_sort_rows(cnnb200_ctx *ctx, int *sorted_out) {
-    if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");
-    if (!ctx->have_nb) CNN_FAIL(CNNB200_E_STATE, "neighbours_sort_rows: no neighbourhoods held");
-    CNN_CUDA(cudaSetDevice(ctx->device));
+// Rows of a CSR (device: row_ptr [n+1], col [nnz]) ascending: one radix sort of (row : column) keys, the low words of
+// the sorted keys are the ascending rows.  Writes into `out` (grown as needed; may not alias `col`).
+int cnn_sort_csr_rows(cnnb200_ctx *ctx, const ll *row_ptr, const int *col, ll n, ll nnz, Buf &out) {
     cudaStream_t st = ctx->stream;
-    const ll n = ctx->n, nnz = ctx->nnz;
-    if (sorted_out) *sorted_out = 0;
-    if (nnz < 2) return CNNB200_OK;
-    Span sp(ctx, T_INGEST);
-    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
-    int *flag = ctx->b_tmp2.as<int>();
-    CNN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
-    ll blocks = (n + 7) / 8;
-    if (blocks > (ll)ctx->sm_count * 32) blocks = (ll)ctx->sm_count * 32;
-    rows_unsorted_kernel<<<(int)blocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, n, flag);
-    CNN_LAUNCHED(ctx, 1);
-    CNN_KERNEL_CHECK();
-    int *h;
-    CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
-    CNN_CUDA(cudaMemcpyAsync(h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CNN_CUDA(cudaStreamSynchronize(st));
-    if (!h[0]) return CNNB200_OK;
     if (nnz >= (1ll << 31) - 1)
-        CNN_FAIL(CNNB200_E_RANGE, "neighbours_sort_rows: more than 2^31-2 entries; pass ascending rows");
-    // one radix sort of (row : column) keys; the low words of the sorted keys are the ascending rows
+        CNN_FAIL(CNNB200_E_RANGE, "row sort: more than 2^31-2 entries; pass ascending rows");
     CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(unsigned long long) * (size_t)nnz));
     CNN_TRY(cnn_ensure(ctx, ctx->b_tmp1, sizeof(unsigned long long) * (size_t)nnz));
     unsigned long long *keys = ctx->b_tmp0.as<unsigned long long>(), *keys2 = ctx->b_tmp1.as<unsigned long long>();
-    row_keys_kernel<<<(int)blocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, n, keys);
+    ll blocks = (n + 7) / 8;
+    if (blocks > (ll)ctx->sm_count * 32) blocks = (ll)ctx->sm_count * 32;
+    row_keys_kernel<<<(int)blocks, 256, 0, st>>>(row_ptr, col, n, keys);
     int bits = 1;
     while ((1ll << bits) < n) ++bits;
     size_t need = 0;
@@ -217,14 +200,59 @@ extern "C" int cnnb200_neighbours_sort_rows(cnnb200_ctx *ctx, int *sorted_out) {
     CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
     size_t cap = ctx->b_cub.cap;
     CNN_CUDA(cub::DeviceRadixSort::SortKeys(ctx->b_cub.p, cap, keys, keys2, (int)nnz, 0, 32 + bits, st));
-    if (ctx->col_idx != ctx->b_col_idx.as<int>())  // borrowed caller memory stays untouched
-        CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
-    keys_low_kernel<<<cnn_blocks(nnz, 256), 256, 0, st>>>(keys2, nnz, ctx->b_col_idx.as<int>());
+    CNN_TRY(cnn_ensure(ctx, out, sizeof(int) * (size_t)nnz));
+    keys_low_kernel<<<cnn_blocks(nnz, 256), 256, 0, st>>>(keys2, nnz, out.as<int>());
     CNN_LAUNCHED(ctx, 2);
     CNN_KERNEL_CHECK();
+    return CNNB200_OK;
+}
+
+// 1 in *unsorted when some row of the CSR is not ascending (synchronises)
+int cnn_csr_rows_unsorted(cnnb200_ctx *ctx, const ll *row_ptr, const int *col, ll n, int *unsorted) {
+    cudaStream_t st = ctx->stream;
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
+    int *flag = ctx->b_tmp2.as<int>();
+    CNN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    ll blocks = (n + 7) / 8;
+    if (blocks > (ll)ctx->sm_count * 32) blocks = (ll)ctx->sm_count * 32;
+    rows_unsorted_kernel<<<(int)blocks, 256, 0, st>>>(row_ptr, col, n, flag);
+    CNN_LAUNCHED(ctx, 1);
+    CNN_KERNEL_CHECK();
+    int *h;
+    CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
+    CNN_CUDA(cudaMemcpyAsync(h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaStreamSynchronize(st));
+    *unsorted = h[0];
+    return CNNB200_OK;
+}
+
+// The intersection kernels (cn.cu: shared-memory row window, lower_bound of `above`) REQUIRE ascending rows; every
+// ingest path ends here, so an unsorted list costs a sort instead of an out-of-bounds shared-memory write.
+int cnn_ensure_sorted_rows(cnnb200_ctx *ctx, bool known_unsorted, int *sorted_out) {
+    const ll n = ctx->n, nnz = ctx->nnz;
+    if (sorted_out) *sorted_out = 0;
+    if (nnz < 2) return CNNB200_OK;
+    int unsorted = known_unsorted ? 1 : 0;
+    if (!known_unsorted) CNN_TRY(cnn_csr_rows_unsorted(ctx, ctx->row_ptr, ctx->col_idx, n, &unsorted));
+    if (!unsorted) return CNNB200_OK;
+    if (ctx->col_idx == ctx->b_col_idx.as<int>()) {
+        // sort through the spare buffer and swap (the sort may not run in place)
+        CNN_TRY(cnn_sort_csr_rows(ctx, ctx->row_ptr, ctx->col_idx, n, nnz, ctx->b_col_spare));
+        Buf t = ctx->b_col_idx; ctx->b_col_idx = ctx->b_col_spare; ctx->b_col_spare = t;
+    } else {
+        CNN_TRY(cnn_sort_csr_rows(ctx, ctx->row_ptr, ctx->col_idx, n, nnz, ctx->b_col_idx));  // borrowed memory stays untouched
+    }
     ctx->col_idx = ctx->b_col_idx.as<int>();
     ++ctx->nb_version;
     ctx->have_comp = false;
     if (sorted_out) *sorted_out = 1;
     return CNNB200_OK;
+}
+
+extern "C" int cnnb200_neighbours_sort_rows(cnnb200_ctx *ctx, int *sorted_out) {
+    if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");
+    if (!ctx->have_nb) CNN_FAIL(CNNB200_E_STATE, "neighbours_sort_rows: no neighbourhoods held");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    Span sp(ctx, T_INGEST);
+    return cnn_ensure_sorted_rows(ctx, false, sorted_out);
 }

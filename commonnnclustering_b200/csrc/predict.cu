@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(PW_WARPS * 32)
 predict_kernel(const ll *__restrict__ o_row_ptr, const int *__restrict__ o_col_idx, ll m, const ll *__restrict__ row_ptr,
                const int *__restrict__ col_idx, const int *__restrict__ perm, const ll *__restrict__ labels,
                const uint8_t *__restrict__ label_ok, ll max_label, ll n_member_cutoff, ll similarity_cutoff,
-               ll *__restrict__ other_labels, uint8_t *__restrict__ other_consider, unsigned long long *row_counter) {
+               ll *__restrict__ other_labels, uint8_t *__restrict__ other_consider, unsigned long long *row_counter,
+               const int *__restrict__ o_col_orig) {
     __shared__ unsigned win_all[PW_WARPS][PW_BITS / 32];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -165,9 +166,15 @@ predict_kernel(const ll *__restrict__ o_row_ptr, const int *__restrict__ o_col_i
             }
             __syncwarp();
         }
+        // The reference takes the FIRST matching member in the order of the predictand's list (_fit.pyx:1264-1291).
+        // Lists built here from coordinates are ascending in the internal order: the first match of the reference's
+        // ascending caller-index list is the matching member with the smallest caller index.  Lists the caller gave
+        // (o_col_orig: their original order, when they had to be sorted for the window) are walked in that order and
+        // the first match ends the walk.
+        const int *scan = o_col_orig ? o_col_orig + ob : orow;
         int best = 0x7fffffff;  // smallest caller index among the matching members
         for (int k = 0; k < mo; ++k) {
-            const int mm = orow[k];
+            const int mm = scan[k];
             const int caller = perm ? perm[mm] : mm;
             if (caller >= best) continue;
             const ll lab = labels[caller];
@@ -188,7 +195,10 @@ predict_kernel(const ll *__restrict__ o_row_ptr, const int *__restrict__ o_col_i
                     c = pr_common(orow, mo, mrow, nm, lane);
                 }
             }
-            if ((ll)c >= similarity_cutoff) best = caller;
+            if ((ll)c >= similarity_cutoff) {
+                best = caller;
+                if (o_col_orig || !perm) break;  // list order is the reference's order: the first match decides
+            }
         }
         if (windowed) {
             __syncwarp();
@@ -288,6 +298,7 @@ extern "C" int cnnb200_neighbours_other_from_points(cnnb200_ctx *ctx, const doub
     }
     ctx->o_m = m;
     ctx->o_nnz = nnz;
+    ctx->o_col_orig = nullptr;
     ctx->have_other = true;
     if (nnz_out) *nnz_out = nnz;
     return CNNB200_OK;
@@ -295,7 +306,27 @@ extern "C" int cnnb200_neighbours_other_from_points(cnnb200_ctx *ctx, const doub
 
 __global__ void other_narrow_kernel(const ll *__restrict__ in, ll count, int *__restrict__ out) {
     ll k = blockIdx.x * (ll)blockDim.x + threadIdx.x;
-    if (k < count) out[k] = (int)in[k];
+    if (k < count) out[k] = (in[k] < 0 || in[k] > 0x7fffffffll) ? -1 : (int)in[k];  // out of range: caught by the check
+}
+
+// offsets monotone, first 0, last nnz (flag[0]); indices inside [0, n) (flag[0]); rows ascending (flag[2])
+__global__ void other_check_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col, ll m, ll nnz, ll n, int *flag) {
+    const int lane = threadIdx.x & 31;
+    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    bool bad = false, unsorted = false;
+    if (warp == 0 && lane == 0) bad = row_ptr[0] != 0 || row_ptr[m] != nnz;
+    for (ll r = warp; r < m; r += nwarps) {
+        const ll b = row_ptr[r], e = row_ptr[r + 1];
+        if (b < 0 || e > nnz || b > e) { bad = true; continue; }
+        for (ll k = b + lane; k < e; k += 32) {
+            const int v = col[k];
+            bad |= v < 0 || v >= n;
+            if (k + 1 < e) unsorted |= v > col[k + 1];
+        }
+    }
+    if (bad) flag[0] = 1;
+    if (unsorted) flag[2] = 1;
 }
 
 extern "C" int cnnb200_neighbours_other_from_csr(cnnb200_ctx *ctx, const int64_t *row_ptr, const int64_t *col_idx, int loc,
@@ -316,6 +347,28 @@ extern "C" int cnnb200_neighbours_other_from_csr(cnnb200_ctx *ctx, const int64_t
         other_narrow_kernel<<<cnn_blocks(nnz, 256), 256, 0, st>>>(ctx->b_tmp0.as<ll>(), nnz, ctx->b_o_col_idx.as<int>());
         CNN_LAUNCHED(ctx, 1);
         CNN_KERNEL_CHECK();
+    }
+    // the lists index the clustered set: offsets monotone and ending at nnz, indices inside [0, n); the kernel's window
+    // needs ascending rows -- lists in any order (NeighboursGetterExtLookup with is_sorted = False) are sorted into a
+    // second array and the original order is kept for the first-match walk
+    ctx->o_col_orig = nullptr;
+    if (m > 0) {
+        CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
+        int *flag = ctx->b_tmp2.as<int>();
+        CNN_CUDA(cudaMemsetAsync(flag, 0, 4 * sizeof(int), st));
+        other_check_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->b_o_row_ptr.as<ll>(), ctx->b_o_col_idx.as<int>(), m, nnz, ctx->n,
+                                                             flag);
+        CNN_LAUNCHED(ctx, 1);
+        CNN_KERNEL_CHECK();
+        int *h;
+        CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
+        CNN_CUDA(cudaMemcpyAsync(h, flag, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CNN_CUDA(cudaStreamSynchronize(st));
+        if (h[0]) CNN_FAIL(CNNB200_E_INVALID, "neighbours_other_from_csr: row_ptr not monotone / not ending at nnz, or an index outside [0, n)");
+        if (h[2]) {
+            CNN_TRY(cnn_sort_csr_rows(ctx, ctx->b_o_row_ptr.as<ll>(), ctx->b_o_col_idx.as<int>(), m, nnz, ctx->b_o_col_sorted));
+            ctx->o_col_orig = ctx->b_o_col_idx.as<int>();
+        }
     }
     ctx->o_m = m;
     ctx->o_nnz = nnz;
@@ -363,9 +416,10 @@ extern "C" int cnnb200_predict(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_
     ll want = (m + PW_WARPS - 1) / PW_WARPS;
     int blocks = ctx->sm_count * per_sm;
     if (blocks > want) blocks = (int)want;
-    predict_kernel<<<blocks, PW_WARPS * 32, 0, st>>>(ctx->b_o_row_ptr.as<ll>(), ctx->b_o_col_idx.as<int>(), m, ctx->row_ptr,
+    const int *o_sorted = ctx->o_col_orig ? ctx->b_o_col_sorted.as<int>() : ctx->b_o_col_idx.as<int>();
+    predict_kernel<<<blocks, PW_WARPS * 32, 0, st>>>(ctx->b_o_row_ptr.as<ll>(), o_sorted, m, ctx->row_ptr,
                                                     ctx->col_idx, ctx->perm, d_labels, d_ok, max_label, n_member_cutoff,
-                                                    similarity_cutoff, d_ol, d_oc, row_counter);
+                                                    similarity_cutoff, d_ol, d_oc, row_counter, ctx->o_col_orig);
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     if (loc == CNNB200_HOST) {

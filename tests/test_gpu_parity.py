@@ -799,3 +799,95 @@ def test_fused_numbering_and_size_sort(ctx):
         kept, largest, noise = ctx.label_summary()
         cnt = np.bincount(want)
         assert (kept, largest, noise) == (len(cnt) - 1, int(cnt[1:].max()) if len(cnt) > 1 else 0, int(cnt[0]))
+
+
+@pytest.mark.gpu
+def test_predict_with_lists_in_any_order(ctx):
+    """The 'neighbourhoods' recipe hands the predictor lists in ANY order (NeighboursGetterExtLookup, is_sorted = False,
+    recipes.py:340-348): the label comes from the first matching member IN LIST ORDER (_fit.pyx:1264-1291), whatever
+    the order, and malformed lists are rejected instead of read out of bounds."""
+    rng = np.random.default_rng(11)
+    pts = datasets.blobs_2d(1600)
+    x, x_other = np.ascontiguousarray(pts[::2]), np.ascontiguousarray(pts[1::2])
+    r, c = 0.15, 4
+    rp, ci = port.neighbours(x, r * r)
+    orp, oci = port.neighbours_other(x, x_other, r * r)
+    labels = port.fit_points(x, 0.12, 8, member_cutoff=5)
+    # shuffle every list of both sets
+    def shuffled(rp_, ci_):
+        out = ci_.copy()
+        for a, b in zip(rp_[:-1], rp_[1:]):
+            out[a:b] = rng.permutation(out[a:b])
+        return out
+    ci_s, oci_s = shuffled(rp, ci), shuffled(orp, oci)
+    # expected: the reference's loop with set intersections (order-free counts), members walked in list order
+    rows = [set(ci[a:b].tolist()) for a, b in zip(rp[:-1], rp[1:])]
+    want = np.zeros(x_other.shape[0], dtype=np.int64)
+    for p in range(x_other.shape[0]):
+        na = oci_s[orp[p]:orp[p + 1]]
+        if not na.size > c + 1:
+            continue
+        sa = set(na.tolist())
+        for member in na:
+            if labels[member] == 0 or not len(rows[member]) > c + 1:
+                continue
+            if len(sa & rows[member]) >= c + 2:
+                want[p] = labels[member]
+                break
+    ctx.neighbours_from_csr(rp, ci_s)          # sorted on arrival
+    ctx.neighbours_other_from_csr(orp, oci_s)
+    got = np.zeros(x_other.shape[0], dtype=np.int64)
+    consider = np.ones(x_other.shape[0], dtype=np.uint8)
+    label_ok = np.ones(int(labels.max()) + 1, dtype=np.uint8)
+    label_ok[0] = 0
+    ctx.predict(c + 1, c + 2, labels, label_ok, got, consider)
+    np.testing.assert_array_equal(got, want)
+    assert want.max() > 0 and (consider[want > 0] == 0).all()
+    # the first match in list order differs from the smallest index for some point (otherwise the test is vacuous)
+    ctx.neighbours_other_from_csr(orp, oci)
+    got_sorted = np.zeros_like(got)
+    ctx.predict(c + 1, c + 2, labels, label_ok, got_sorted, np.ones_like(consider))
+    assert (got_sorted > 0).sum() == (got > 0).sum()
+    # malformed predictand lists
+    bad = oci.copy()
+    bad[5] = x.shape[0]
+    with pytest.raises(ValueError):
+        ctx.neighbours_other_from_csr(orp, bad)
+    bad_rp = orp.copy()
+    bad_rp[3] = bad_rp[4] + 1
+    with pytest.raises(ValueError):
+        ctx.neighbours_other_from_csr(bad_rp, oci)
+
+
+@pytest.mark.gpu
+def test_unsorted_lists_are_sorted_on_every_ingest_path(ctx):
+    """Ascending rows are a REQUIREMENT of the intersection kernels; no ingest path trusts the caller for it."""
+    rng = np.random.default_rng(3)
+    x = datasets.md_like_3d(4000)
+    rp, ci = port.neighbours(x, 0.3 * 0.3)
+    want = port.fit_csr(rp, ci, 5, member_cutoff=None)
+    ci_s = ci.copy()
+    for a, b in zip(rp[:-1], rp[1:]):
+        ci_s[a:b] = rng.permutation(ci_s[a:b])
+    import torch
+    for form in ("host64", "host32", "device_borrowed"):
+        if form == "host64":
+            ctx.neighbours_from_csr(rp, ci_s)
+        elif form == "host32":
+            ctx.neighbours_from_csr(rp, ci_s.astype(np.int32))
+        else:
+            rp_d, ci_d = torch.from_numpy(rp).cuda(), torch.from_numpy(ci_s.astype(np.int32)).cuda()
+            keep = ci_d.clone()
+            ctx.neighbours_from_csr(rp_d, ci_d, borrow=True)
+        got = np.zeros(x.shape[0], dtype=np.int64)
+        ctx.fit(6, 7, 1, got, None)
+        ctx.sort_by_size(got, None)
+        assert np.array_equal(got, want), form
+        if form == "device_borrowed":
+            assert torch.equal(ci_d, keep)     # the caller's buffer is not modified
+    padded, counts = port.csr_to_padded(rp, ci_s)
+    ctx.neighbours_from_padded(padded, counts)
+    got = np.zeros(x.shape[0], dtype=np.int64)
+    ctx.fit(6, 7, 1, got, None)
+    ctx.sort_by_size(got, None)
+    assert np.array_equal(got, want)

@@ -102,6 +102,105 @@ class FitterB200Fused(FitterB200):
         return n_clusters
 
 
+class HierarchicalFitter:
+    """Role marker (reference ABC ``HierarchicalFitter``, ``_fit.pyx:86-126``).  Its ``make_parameters`` has the same
+    body as ``Fitter.make_parameters`` and looks at ``self._neighbours_getter`` -- an attribute
+    ``HierarchicalFitterRepeat`` does not have, so for that class NEITHER the radius is adjusted NOR are the cutoffs
+    raised for self-counting neighbourhoods: the wrapped fitter receives ``(r, c, c, c, start)`` as they were given.
+    Kept as it is (bit-exact parity)."""
+
+    make_parameters = Fitter.make_parameters
+
+
+class HierarchicalFitterRepeat(HierarchicalFitter):
+    """A hierarchy from repeated flat fits on the ROOT data with a sequence of ``(radius_cutoff, cnn_cutoff)`` pairs
+    (reference ``HierarchicalFitterRepeat``, ``_fit.pyx:1018-1184``): after every step each cluster of the previous
+    step ("terminal" bundle) receives the current labels of its members as its own label array and is isolated into
+    children, which become the terminal bundles of the next step.
+
+    The per-step fit runs on the device; so does the grouping of the points by (previous label, current label)
+    (``cnnb200_labels_group``: two radix sorts instead of the reference's per-point ``parent_labels_map`` loop and
+    one ``Labels.mapping`` pass per parent), after which every bundle is a few NumPy slices."""
+
+    def __init__(self, fitter=None):
+        self._fitter = fitter if fitter is not None else FitterB200()
+
+    def __str__(self):
+        return f"{type(self).__name__}(fitter={self._fitter})"
+
+    @classmethod
+    def get_builder_kwargs(cls):
+        return [("fitter", None)]
+
+    def fit(self, bundle, **kwargs):
+        self._fit(bundle, kwargs["radius_cutoff"], kwargs["cnn_cutoff"], kwargs.get("member_cutoff"),
+                  kwargs.get("max_clusters"), kwargs.get("cnn_offset"), kwargs.get("sort_by_size", True),
+                  kwargs.get("info", True), kwargs.get("v", True))
+
+    def _fit(self, bundle, radius_cutoff, cnn_cutoff, member_cutoff=None, max_clusters=None, cnn_offset=None,
+             sort_by_size=True, info=True, v=True):
+        import weakref
+        from collections.abc import Iterable
+
+        from .cluster import Bundle
+
+        radius_cutoff = [float(x) for x in (radius_cutoff if isinstance(radius_cutoff, Iterable) else [radius_cutoff])]
+        cnn_cutoff = [int(x) for x in (cnn_cutoff if isinstance(cnn_cutoff, Iterable) else [cnn_cutoff])]
+        if len(radius_cutoff) == 1:
+            radius_cutoff *= len(cnn_cutoff)
+        if len(cnn_cutoff) == 1:
+            cnn_cutoff *= len(radius_cutoff)
+        n_steps = len(radius_cutoff)
+        assert n_steps == len(cnn_cutoff)
+        if cnn_offset is None:
+            cnn_offset = 0
+        ctx = self._fitter.ctx
+        n_points = bundle._input_data.n_points
+        previous = np.ones(n_points, dtype=np.int64)
+        terminal = {1: bundle}
+        for step in range(n_steps):
+            if v:
+                print(f"Running step {step:<5} (r = {radius_cutoff[step]}, c = {cnn_cutoff[step]})")
+            current = Labels(np.zeros(n_points, order="C", dtype=np.int64))
+            cluster_params = self.make_parameters(radius_cutoff[step], cnn_cutoff[step] - cnn_offset, 1)
+            self._fitter.fit(bundle._input_data, current, cluster_params)
+            if sort_by_size:
+                current.sort_by_size(member_cutoff, max_clusters, ctx=ctx)
+            cur = current.labels
+            # all (parent, child) groups of the step at once; points of parent 0 (noise of the previous step) drop out
+            order, rank = ctx.labels_group(previous, cur)
+            p_sorted, c_sorted = previous[order], cur[order]
+            first = int(np.searchsorted(p_sorted, 1, side="left"))
+            new_terminal = {}
+            p_starts = first + np.flatnonzero(np.r_[True, p_sorted[first + 1:] != p_sorted[first:-1]]) if first < n_points \
+                else np.zeros(0, dtype=np.int64)
+            p_ends = np.r_[p_starts[1:], n_points]
+            for ps, pe in zip(p_starts.tolist(), p_ends.tolist()):
+                p_label = int(p_sorted[ps])
+                parent = terminal[p_label]
+                lab = np.empty(pe - ps, dtype=np.int64)
+                lab[rank[ps:pe]] = c_sorted[ps:pe]        # the current labels of the parent's members in point order
+                parent._labels = Labels(lab)
+                if info:
+                    params = {int(k): (radius_cutoff[step], cnn_cutoff[step]) for k in np.unique(lab).tolist() if k != 0}
+                    parent._labels.meta.update({"params": params, "reference": weakref.proxy(parent), "origin": "fit"})
+                # Bundle.isolate(isolate_input_data=False) from the same sort: children in order of first occurrence
+                parent._children = {}
+                cs = ps + np.flatnonzero(np.r_[True, c_sorted[ps + 1:pe] != c_sorted[ps:pe - 1]])
+                ce = np.r_[cs[1:], pe]
+                groups = [(int(rank[a]), a, b) for a, b in zip(cs.tolist(), ce.tolist()) if c_sorted[a] != 0]
+                for _, a, b in sorted(groups):
+                    c_label = int(c_sorted[a])
+                    child = Bundle(parent=parent, alias=f"{parent.alias} - {c_label}")
+                    child.parent_indices = rank[a:b].astype(np.intp)      # ascending: the sorts are stable
+                    child.root_indices = child.parent_indices if parent.root_indices is None \
+                        else parent.root_indices[child.parent_indices]
+                    parent._children[c_label] = child
+                    new_terminal[c_label] = child
+            terminal = new_terminal
+            previous = cur
+
+
 class Predictor:
     """Role marker (reference ABC ``Predictor``, ``_fit.pyx:164-216``)."""
 

@@ -41,6 +41,7 @@ SIGNATURES = {
     "cnnb200_neighbours_from_padded": [_P, _P, _P, C.c_int, _I64, _I64],
     "cnnb200_neighbours_from_distances": [_P, _P, C.c_int, _I64, C.c_double],
     "cnnb200_neighbours_sort_rows": [_P, C.POINTER(C.c_int)],
+    "cnnb200_neighbours_asymmetry": [_P, C.POINTER(_I64)],
     "cnnb200_neighbours_info": [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)],
     "cnnb200_neighbours_export": [_P, _P, _P, C.c_int],
     "cnnb200_neighbours_device_view": [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)],
@@ -63,6 +64,7 @@ SIGNATURES = {
     "cnnb200_fit_points": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int, C.c_int, _I64, _I64, _I64,
                            C.c_int, _I64, _I64, _P, C.POINTER(_I64)],
     "cnnb200_label_summary": [_P, _P],
+    "cnnb200_labels_group": [_P, _P, _P, C.c_int, _I64, _P, _P],
     "cnnb200_host_register": [_P, C.c_size_t],
     "cnnb200_host_unregister": [_P],
     "cnnb200_stats": [_P, _P, _I64],
@@ -269,6 +271,12 @@ class Context:
         check(self._lib.cnnb200_neighbours_sort_rows(self._h, C.byref(flag)))
         return bool(flag.value)
 
+    def neighbours_asymmetry(self) -> int:
+        """Number of entries (i, j) of the held neighbourhoods whose mirror (j, i) is missing."""
+        k = _I64()
+        check(self._lib.cnnb200_neighbours_asymmetry(self._h, C.byref(k)))
+        return k.value
+
     def neighbours_info(self):
         n, nnz, md = _I64(), _I64(), _I64()
         check(self._lib.cnnb200_neighbours_info(self._h, C.byref(n), C.byref(nnz), C.byref(md)))
@@ -430,6 +438,18 @@ class Context:
             -1 if member_cutoff is None else int(member_cutoff),
             -1 if max_clusters is None else int(max_clusters), lp, C.byref(nc)))
         return nc.value
+
+    def labels_group(self, prev, cur):
+        """(order, rank) int64 [n]: points sorted by (prev, cur, index) and their position among the points with the
+        same previous label (``cnnb200_labels_group``)."""
+        prev = np.ascontiguousarray(prev, dtype=np.int64)
+        cur = np.ascontiguousarray(cur, dtype=np.int64)
+        n = prev.shape[0]
+        order = np.empty(n, dtype=np.int64)
+        rank = np.empty(n, dtype=np.int64)
+        check(self._lib.cnnb200_labels_group(self._h, prev.ctypes.data, cur.ctypes.data, HOST, n, order.ctypes.data,
+                                             rank.ctypes.data))
+        return order, rank
 
     def label_summary(self):
         """(clusters kept, members of the largest one, noise points) of the last size-sorted result."""

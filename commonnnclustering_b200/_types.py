@@ -228,9 +228,17 @@ class InputDataComponents(InputData):
         return float(self._data[point, dimension])
 
     def get_subset(self, indices):
-        idx = np.asarray(indices)
+        """The points ``indices`` (ascending) as a new input data object; the part lengths ``meta["edges"]`` follow
+        the points (what the reference's ``Bundle.isolate`` computes for a child, ``_bundle.pyx:321-350``)."""
+        idx = np.asarray(indices, dtype=np.int64)
         sub = self._data[idx] if isinstance(self._data, np.ndarray) else self._data[idx.tolist()]
-        return type(self)(sub)
+        meta = {}
+        edges = self.meta.get("edges", None)
+        if edges:
+            bounds = np.cumsum(np.asarray(edges, dtype=np.int64))
+            part = np.searchsorted(bounds, idx, side="right")
+            meta["edges"] = np.bincount(part, minlength=len(edges))[:len(edges)].astype(int).tolist()
+        return type(self)(sub, meta=meta)
 
     def by_parts(self):
         """Yield the parts delimited by ``meta["edges"]`` (``_types.pyx:1089-1109``)."""
@@ -294,6 +302,17 @@ class InputDataNeighbourhoods(InputData):
         mask = np.arange(self._data.shape[1])[None, :] < self._n_neighbours[:, None]
         return row_ptr, np.ascontiguousarray(self._data[mask])
 
+    def get_subset(self, indices):
+        """The neighbourhoods of the points ``indices`` restricted to those points, members renumbered to their
+        position in the subset.  (The reference keeps the old member numbers and drops the counts,
+        ``_types.pyx:1199-1217`` -- SURVEY 8f notes the defect; child reclustering needs the renumbered form.)"""
+        row_ptr, col_idx = _subset_csr(*self.to_csr(), np.asarray(indices, dtype=np.int64), self.n_points)
+        counts = np.diff(row_ptr)
+        padded = np.zeros((counts.shape[0], max(int(counts.max()) if counts.size else 0, 1)), dtype=P_AINDEX)
+        rows = np.repeat(np.arange(counts.shape[0]), counts)
+        padded[rows, np.arange(col_idx.shape[0]) - np.repeat(row_ptr[:-1], counts)] = col_idx
+        return type(self)(padded, counts)
+
 
 class InputDataNeighbourhoodsCSR(InputData):
     """Precomputed neighbourhoods in CSR form (row_ptr int64 ``[n+1]``, col_idx int32/int64
@@ -321,6 +340,26 @@ class InputDataNeighbourhoodsCSR(InputData):
         if hasattr(rp, "is_cuda"):
             rp, ci = rp.cpu().numpy(), ci.cpu().numpy()
         return np.ascontiguousarray(rp, dtype=P_AINDEX), np.ascontiguousarray(ci, dtype=P_AINDEX)
+
+    def get_subset(self, indices):
+        """Rows of ``indices`` restricted to those points, members renumbered to their position in the subset."""
+        return type(self)(*_subset_csr(*self.to_csr(), np.asarray(indices, dtype=np.int64), self.n_points))
+
+
+def _subset_csr(row_ptr, col_idx, indices, n_points):
+    """CSR of the sub-graph on ``indices`` (ascending, unique): rows of those points, members outside dropped, the
+    rest renumbered; vectorised."""
+    new_id = np.full(n_points, -1, dtype=np.int64)
+    new_id[indices] = np.arange(indices.shape[0])
+    counts = (row_ptr[1:] - row_ptr[:-1])[indices]
+    starts = row_ptr[:-1][indices]
+    flat = np.repeat(starts - (np.cumsum(counts) - counts), counts) + np.arange(int(counts.sum()))
+    members = new_id[col_idx[flat]]
+    keep = members >= 0
+    rows = np.repeat(np.arange(indices.shape[0]), counts)[keep]
+    sub_ptr = np.zeros(indices.shape[0] + 1, dtype=np.int64)
+    np.cumsum(np.bincount(rows, minlength=indices.shape[0]), out=sub_ptr[1:])
+    return sub_ptr, np.ascontiguousarray(members[keep])
 
 
 class Neighbourhoods:
@@ -512,11 +551,17 @@ class NeighboursGetterLookup(NeighboursGetter):
     ``is_sorted=True`` (the reference's ``sorted_neighbourhoods`` recipe, ``recipes.py:349-357``) promises
     ascending rows; with ``is_sorted=False`` (the ``neighbourhoods`` recipe, ``recipes.py:340-348``, the
     reference's default for the getter, ``_types.pyx:1794``) the rows are checked on the device and sorted
-    there when needed -- the labels do not depend on the order inside a list."""
+    there when needed -- the labels do not depend on the order inside a list.
 
-    def __init__(self, is_sorted: bool = False, is_selfcounting: bool = True):
+    The lists must be SYMMETRIC (``j in N(i)`` exactly when ``i in N(j)``), as radius neighbourhoods are: candidate
+    edges are read as the entries ``j > i`` of row ``i``, and the union-find that replaces the reference's BFS equals
+    it only on an undirected graph.  kNN-style lists violate this; ``check_symmetric=True`` counts
+    the one-sided entries on the device (``cnnb200_neighbours_asymmetry``) and raises when there are any."""
+
+    def __init__(self, is_sorted: bool = False, is_selfcounting: bool = True, check_symmetric: bool = False):
         self.is_sorted = bool(is_sorted)
         self.is_selfcounting = bool(is_selfcounting)
+        self.check_symmetric = bool(check_symmetric)
 
     def get_all(self, input_data, cluster_params=None, ctx=None) -> Neighbourhoods:
         ctx = ctx or _lib.default_context()
@@ -530,6 +575,10 @@ class NeighboursGetterLookup(NeighboursGetter):
             raise TypeError("NeighboursGetterLookup needs InputDataNeighbourhoods or InputDataNeighbourhoodsCSR")
         if not self.is_sorted:
             ctx.neighbours_sort_rows()
+        if self.check_symmetric:
+            one_sided = ctx.neighbours_asymmetry()
+            if one_sided:
+                raise ValueError(f"neighbourhoods are not symmetric: {one_sided} entries (i, j) without (j, i)")
         return Neighbourhoods(ctx)
 
 

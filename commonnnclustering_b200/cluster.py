@@ -6,7 +6,7 @@ import weakref
 import numpy as np
 
 from . import recipes
-from ._fit import Fitter, FitterB200Fused, Predictor
+from ._fit import Fitter, FitterB200Fused, HierarchicalFitter, Predictor
 from ._types import InputData, InputDataComponents, Labels
 from .report import Record, Summary
 
@@ -76,11 +76,14 @@ class Bundle:
 class Clustering:
     """``Clustering(data).fit(radius_cutoff, cnn_cutoff, member_cutoff)`` on a B200."""
 
-    def __init__(self, data=None, *, fitter=None, predictor=None, recipe=None, **recipe_kwargs):
+    def __init__(self, data=None, *, fitter=None, hierarchical_fitter=None, predictor=None, recipe=None, **recipe_kwargs):
         builder = recipes.Builder(recipe, **recipe_kwargs)
+        self._hierarchical_fitter = hierarchical_fitter if isinstance(hierarchical_fitter, HierarchicalFitter) else None
+        if hierarchical_fitter is not None and self._hierarchical_fitter is None:
+            builder.set("hierarchical_fitter", hierarchical_fitter)
         self._predictor = predictor if isinstance(predictor, Predictor) else None
         if predictor is not None and self._predictor is None:
-            builder.recipe["predictor"] = predictor
+            builder.set("predictor", predictor)
         if data is None:
             self._bundle = None
         elif isinstance(data, Bundle):
@@ -93,12 +96,15 @@ class Clustering:
             self._fitter = fitter
         else:
             if fitter is not None:
-                builder.recipe["fitter"] = fitter
+                builder.set("fitter", fitter)
             f = builder.make_component("fitter")
             self._fitter = None if f is object else f
         if self._predictor is None:
             pr = builder.make_component("predictor")
             self._predictor = None if pr is object else pr
+        if self._hierarchical_fitter is None:
+            hf = builder.make_component("hierarchical_fitter")
+            self._hierarchical_fitter = None if hf is object else hf
 
     @property
     def root(self):
@@ -130,6 +136,20 @@ class Clustering:
     def isolate(self, purge: bool = True, isolate_input_data: bool = True, bundle=None) -> None:
         """Reference ``Clustering.isolate`` (``cluster.pyx:394-413``)."""
         (bundle if bundle is not None else self._bundle).isolate(purge, isolate_input_data)
+
+    def fit_hierarchical(self, purge=True, bundle=None, **fitter_kwargs) -> None:
+        """Reference ``Clustering.fit_hierarchical`` (``cluster.pyx:394-411``): the keyword arguments are those of the
+        hierarchical fitter (``radius_cutoff`` / ``cnn_cutoff`` sequences, ``member_cutoff``, ``max_clusters``,
+        ``cnn_offset``, ``sort_by_size``, ``info``, ``v`` for ``HierarchicalFitterRepeat``)."""
+        if bundle is None:
+            bundle = self._bundle
+        if purge or bundle._children is None:
+            bundle._children = {}
+        if self._hierarchical_fitter is None:   # default: repeated flat fits with this clustering's fitter
+            from ._fit import HierarchicalFitterRepeat
+
+            self._hierarchical_fitter = HierarchicalFitterRepeat(self._fitter)
+        self._hierarchical_fitter.fit(bundle, **fitter_kwargs)
 
     def reel(self, depth=None, bundle=None) -> None:
         """Wrap up the label assignments of lower hierarchy levels (reference ``cluster.pyx:502-558``):

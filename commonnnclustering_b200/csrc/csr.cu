@@ -323,3 +323,47 @@ extern "C" int cnnb200_neighbours_export(cnnb200_ctx *ctx, int64_t *row_ptr, int
     CNN_CUDA(cudaStreamSynchronize(st));
     return CNNB200_OK;
 }
+
+// ---- symmetry of the lists (debug / validation aid) ------------------------------------------------------------------
+__global__ void asymmetry_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col, ll n, unsigned long long *count) {
+    const int lane = threadIdx.x & 31;
+    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    unsigned missing = 0;
+    for (ll i = warp; i < n; i += nwarps) {
+        const ll b = row_ptr[i], e = row_ptr[i + 1];
+        for (ll k = b + lane; k < e; k += 32) {
+            const int j = col[k];
+            ll lo = row_ptr[j], hi = row_ptr[j + 1];
+            while (lo < hi) {  // rows are ascending: lower bound of i in row j
+                const ll mid = (lo + hi) >> 1;
+                if (col[mid] < (int)i) lo = mid + 1; else hi = mid;
+            }
+            if (!(lo < row_ptr[j + 1] && col[lo] == (int)i)) ++missing;
+        }
+    }
+    missing = __reduce_add_sync(0xffffffffu, missing);
+    if (lane == 0 && missing) atomicAdd(count, (unsigned long long)missing);
+}
+
+extern "C" int cnnb200_neighbours_asymmetry(cnnb200_ctx *ctx, int64_t *one_sided_out) {
+    if (!ctx || !one_sided_out) CNN_FAIL(CNNB200_E_INVALID, "neighbours_asymmetry: NULL argument");
+    if (!ctx->have_nb) CNN_FAIL(CNNB200_E_STATE, "neighbours_asymmetry: no neighbourhoods held by this context");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
+    unsigned long long *cnt = ctx->b_tmp2.as<unsigned long long>() + 4;
+    CNN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
+    ll blocks = (ctx->n + 7) / 8;
+    if (blocks > (ll)ctx->sm_count * 32) blocks = (ll)ctx->sm_count * 32;
+    if (blocks < 1) blocks = 1;
+    asymmetry_kernel<<<(int)blocks, 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, ctx->n, cnt);
+    CNN_LAUNCHED(ctx, 1);
+    CNN_KERNEL_CHECK();
+    ll *h;
+    CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
+    CNN_CUDA(cudaMemcpyAsync(h, cnt, sizeof(ll), cudaMemcpyDeviceToHost, st));
+    CNN_CUDA(cudaStreamSynchronize(st));
+    *one_sided_out = h[0];
+    return CNNB200_OK;
+}

@@ -489,3 +489,105 @@ int cnn_labels_fused(cnnb200_ctx *ctx, ll member_cutoff, ll max_clusters, ll *d_
     *counters_out = counters;
     return CNNB200_OK;
 }
+
+// ---- (previous label, current label) grouping for the hierarchy driver --------------------------------------------------
+// HierarchicalFitterRepeat._fit (_fit.pyx:1110-1184) walks all points once per step to collect, for every cluster of
+// the previous step, the current labels of its members in point order (`parent_labels_map`), and Bundle.isolate then
+// groups each of those lists by label.  Both groupings for ALL parents at once:
+//   order[k]  point indices sorted by (previous label, current label, index)      -- two stable radix sorts
+//   rank[k]   position of point order[k] among the points with the same previous label, in index order
+// so that the members of (parent p, child c) are one contiguous slice of `order`, their places in the parent's own
+// label array are the same slice of `rank`, and the parent's label array is cur[order] scattered through rank.
+__global__ void group_keys_kernel(const ll *__restrict__ prev, const ll *__restrict__ cur, ll n, unsigned long long *k_prev,
+                                  unsigned long long *k_both, int *idx, int *flag) {
+    ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ll p = prev[i], c = cur[i];
+    if (p < 0 || c < 0 || p > 0x7fffffffll || c > 0x7fffffffll) *flag = 1;
+    k_prev[i] = (unsigned long long)p;
+    k_both[i] = ((unsigned long long)p << 32) | (unsigned long long)(unsigned)c;
+    idx[i] = (int)i;
+}
+
+// sorted by previous label (stable): rank = position - first position of the label's run
+__global__ void group_rank_kernel(const unsigned long long *__restrict__ k_sorted, const int *__restrict__ idx_sorted, ll n,
+                                  int *run_start, int *rank_of_point) {
+    ll k = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    // first position of my run: binary search for the lower bound of my key
+    const unsigned long long key = k_sorted[k];
+    ll lo = 0, hi = k;
+    while (lo < hi) {
+        const ll mid = (lo + hi) >> 1;
+        if (k_sorted[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    rank_of_point[idx_sorted[k]] = (int)(k - lo);
+    (void)run_start;
+}
+
+__global__ void group_out_kernel(const int *__restrict__ idx_sorted, const int *__restrict__ rank_of_point, ll n, ll *order,
+                                 ll *rank) {
+    ll k = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int i = idx_sorted[k];
+    order[k] = i;
+    rank[k] = rank_of_point[i];
+}
+
+extern "C" int cnnb200_labels_group(cnnb200_ctx *ctx, const int64_t *prev, const int64_t *cur, int loc, int64_t n,
+                                    int64_t *order, int64_t *rank) {
+    if (!ctx || !prev || !cur || !order || !rank) CNN_FAIL(CNNB200_E_INVALID, "labels_group: NULL argument");
+    if (n < 0 || n >= (1ll << 31) - 1) CNN_FAIL(CNNB200_E_RANGE, "labels_group: n out of range");
+    if (n == 0) return CNNB200_OK;
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t b8 = sizeof(ll) * (size_t)n;
+    const ll *d_prev = prev, *d_cur = cur;
+    ll *d_order = order, *d_rank = rank;
+    if (loc == CNNB200_HOST) {
+        CNN_TRY(cnn_ensure(ctx, ctx->b_labels, b8));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_lab_map, b8));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_o_labels, 2 * b8));
+        CNN_CUDA(cudaMemcpyAsync(ctx->b_labels.p, prev, b8, cudaMemcpyHostToDevice, st));
+        CNN_CUDA(cudaMemcpyAsync(ctx->b_lab_map.p, cur, b8, cudaMemcpyHostToDevice, st));
+        d_prev = ctx->b_labels.as<ll>();
+        d_cur = ctx->b_lab_map.as<ll>();
+        d_order = ctx->b_o_labels.as<ll>();
+        d_rank = d_order + n;
+    }
+    CNN_TRY(cnn_ensure(ctx, ctx->b_lab_keys, b8));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_lab_keys2, b8));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, b8));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_lab_vals, sizeof(int) * (size_t)n));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_lab_vals2, sizeof(int) * (size_t)n));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_rank, sizeof(int) * (size_t)(n + 1)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 64));
+    unsigned long long *k_prev = ctx->b_lab_keys.as<unsigned long long>(), *k_sorted = ctx->b_lab_keys2.as<unsigned long long>();
+    unsigned long long *k_both = ctx->b_tmp0.as<unsigned long long>();
+    int *idx = ctx->b_lab_vals.as<int>(), *idx_sorted = ctx->b_lab_vals2.as<int>(), *rank_of_point = ctx->b_rank.as<int>();
+    int *flag = ctx->b_tmp2.as<int>();
+    CNN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    const int nb = cnn_blocks(n, 256);
+    group_keys_kernel<<<nb, 256, 0, st>>>(d_prev, d_cur, n, k_prev, k_both, idx, flag);
+    size_t need = 0;
+    CNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, k_both, k_sorted, idx, idx_sorted, (int)n, 0, 64, st));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
+    size_t cap = ctx->b_cub.cap;
+    CNN_CUDA(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, cap, k_prev, k_sorted, idx, idx_sorted, (int)n, 0, 32, st));
+    group_rank_kernel<<<nb, 256, 0, st>>>(k_sorted, idx_sorted, n, nullptr, rank_of_point);
+    cap = ctx->b_cub.cap;
+    CNN_CUDA(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, cap, k_both, k_sorted, idx, idx_sorted, (int)n, 0, 64, st));
+    group_out_kernel<<<nb, 256, 0, st>>>(idx_sorted, rank_of_point, n, d_order, d_rank);
+    CNN_LAUNCHED(ctx, 3);
+    CNN_KERNEL_CHECK();
+    int *h;
+    CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
+    CNN_CUDA(cudaMemcpyAsync(h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (loc == CNNB200_HOST) {
+        CNN_CUDA(cudaMemcpyAsync(order, d_order, b8, cudaMemcpyDeviceToHost, st));
+        CNN_CUDA(cudaMemcpyAsync(rank, d_rank, b8, cudaMemcpyDeviceToHost, st));
+    }
+    CNN_CUDA(cudaStreamSynchronize(st));
+    if (h[0]) CNN_FAIL(CNNB200_E_INVALID, "labels_group: labels must lie in [0, 2^31)");
+    return CNNB200_OK;
+}

@@ -27,6 +27,23 @@ from ._types import MetricEuclidean, MetricEuclideanReduced
 _METRICS = {"euclidean_r": MetricEuclideanReduced, "euclidean": MetricEuclidean}
 
 
+def _padded_view(input_data):
+    """(padded int64 [n, max_deg], counts int64 [n]) of an ``InputDataExtNeighbourhoodsMemoryview`` without touching a
+    row in Python: ``n_neighbours`` is the counts array, and the rows its ``data`` accessor hands out are views into
+    the padded matrix -- the matrix is the 2-D array at the end of the first row's ``base`` chain."""
+    counts = getattr(input_data, "n_neighbours", None)
+    rows = getattr(input_data, "data", None)
+    if counts is None or not rows:
+        return None, None
+    base = rows[0]
+    while base is not None and not (isinstance(base, np.ndarray) and base.ndim == 2):
+        base = getattr(base, "base", None)
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    if base is None or base.dtype != np.int64 or not base.flags.c_contiguous or base.shape[0] != counts.shape[0]:
+        return None, None
+    return base, counts
+
+
 def make_fitter_type(ref_types, ref_fit):
     """Builds the plug-in fitter class against an imported reference (its ABC and parameter type)."""
 
@@ -63,12 +80,18 @@ def make_fitter_type(ref_types, ref_fit):
                 x = np.ascontiguousarray(input_data.to_components_array(), dtype=np.float64)
                 ctx.neighbours_from_points(x, cluster_params.radius_cutoff, metric=self.metric.name, method=self.method)
             elif input_data.meta.get("access_neighbours", False):
-                rows = input_data.data  # list of index arrays (the reference's accessor)
-                counts = np.fromiter((len(r) for r in rows), dtype=np.int64, count=len(rows))
-                row_ptr = np.zeros(len(rows) + 1, dtype=np.int64)
-                np.cumsum(counts, out=row_ptr[1:])
-                col = np.concatenate(rows).astype(np.int64) if row_ptr[-1] else np.zeros(0, dtype=np.int64)
-                ctx.neighbours_from_csr(row_ptr, col)
+                padded, counts = _padded_view(input_data)
+                if padded is not None:
+                    # the reference's own zero-padded int64 matrix (_types.pyx:1159-1184), ingested as it is
+                    ctx.neighbours_from_padded(padded, counts)
+                else:                    # any other container: its row accessor, one concatenation
+                    rows = input_data.data
+                    counts = np.fromiter((len(r) for r in rows), dtype=np.int64, count=len(rows))
+                    row_ptr = np.zeros(len(rows) + 1, dtype=np.int64)
+                    np.cumsum(counts, out=row_ptr[1:])
+                    col = np.concatenate(rows).astype(np.int64) if row_ptr[-1] else np.zeros(0, dtype=np.int64)
+                    ctx.neighbours_from_csr(row_ptr, col)
+                # lists in any order are sorted by the ingest (the labels do not depend on the order within a list)
             else:
                 raise TypeError("FitterB200Plugin needs coordinates or neighbourhoods as input data")
             lab = labels.labels          # NumPy view on the reference's buffer: written in place

@@ -1,5 +1,6 @@
 """Recipes: string keys -> component types, as in the reference's ``recipes.py`` (registry
-``recipes.py:316-445``, ``Builder`` :182-313), for the component set of the B200 fit path."""
+``recipes.py:316-445``), and a builder that assembles components from them (a recipe tree; the reference's builder,
+``recipes.py:182-313``, defines the key grammar it accepts) -- for the component set of the B200 fit path."""
 import numpy as np
 
 from . import _fit, _types
@@ -87,13 +88,14 @@ COMPONENT_NAME_TYPE_MAP = {
     },
     "fitter": {"b200": _fit.FitterB200Fused, "b200_staged": _fit.FitterB200, "bfs": _fit.FitterB200Fused},
     "predictor": {"b200": _fit.PredictorB200, "firstmatch": _fit.PredictorB200},
+    "hierarchical_fitter": {"repeat": _fit.HierarchicalFitterRepeat},
 }
 
 COMPONENT_ALT_KW_MAP = {
     "input": "input_data", "data": "input_data", "n": "neighbours", "na": "neighbours",
     "nb": "neighbour_neighbours", "getter": "neighbours_getter", "ogetter": "neighbours_getter_other",
     "ngetter": "neighbours_getter", "ongetter": "neighbours_getter_other", "dgetter": "distance_getter",
-    "checker": "similarity_checker", "q": "queue", "prep": "preparation_hook",
+    "checker": "similarity_checker", "q": "queue", "prep": "preparation_hook", "hfitter": "hierarchical_fitter",
 }
 
 # component keywords that share the type table of another keyword (reference ``recipes.py``, COMPONENT_KW_TYPE_ALIAS_MAP)
@@ -158,79 +160,122 @@ def get_registered_recipe(key):
     return dict(REGISTERED_RECIPES[key.lower()])
 
 
+class _Node:
+    """One component of a recipe: how to make it (``details``) and the recipe entries below it."""
+    __slots__ = ("details", "present", "below")
+
+    def __init__(self):
+        self.details = None
+        self.present = False
+        self.below = {}
+
+
 class Builder:
-    """Assembles components from a recipe.  Reference: ``recipes.Builder``, ``recipes.py:182-313``
-    (same key grammar: dotted paths, ``__`` as separator in keyword arguments, short aliases)."""
+    """Assembles components from a recipe (the role of the reference's ``recipes.Builder``, ``recipes.py:182-313``,
+    with the same key grammar: dotted paths such as ``fitter.ngetter.dgetter.metric``, ``__`` instead of the dot in
+    keyword arguments, the short aliases of ``COMPONENT_ALT_KW_MAP``; an entry is a registered name, a type, a
+    ``(type-or-name, args, kwargs)`` triple or ``None``).
+
+    The flat recipe is turned into a TREE once -- one node per component, children keyed by the constructor keyword
+    they fill -- and a component is made by walking its subtree: each type says through ``get_builder_kwargs()`` which
+    keywords it takes and which sibling keyword may stand in (``neighbours_getter_other`` falls back to
+    ``neighbours_getter``)."""
 
     default_recipe = "coordinates"
 
     def __init__(self, recipe=None, **kwargs):
         if recipe is None:
             recipe = self.default_recipe
-        if isinstance(recipe, str):
-            recipe = get_registered_recipe(recipe)
-        recipe = dict(recipe)
-        recipe.update(kwargs)
-        recipe = {k.replace("__", "."): v for k, v in recipe.items()}
-        self.recipe = {
-            ".".join(COMPONENT_ALT_KW_MAP.get(kw, kw) for kw in k.split(".")): v for k, v in recipe.items()
-        }
+        entries = dict(get_registered_recipe(recipe) if isinstance(recipe, str) else recipe)
+        entries.update(kwargs)
+        self._root = _Node()
+        for key, details in entries.items():
+            self.set(key, details)
 
-    def make_component(self, component_kw, alternative=None, prev_kw=None):
-        prev_kw = prev_kw or []
-        full_kw = ".".join([*prev_kw, component_kw])
-        if alternative is not None:
-            alternative = full_kw.rsplit(".", 1)[0] + f".{alternative}"
-        if full_kw in self.recipe:
-            details = self.recipe[full_kw]
-        elif alternative is not None and alternative in self.recipe:
-            details = self.recipe[alternative]
-        else:
-            return object
-        if details is None:
-            return None
+    @staticmethod
+    def _path(key):
+        return [COMPONENT_ALT_KW_MAP.get(part, part) for part in key.replace("__", ".").split(".")]
+
+    def set(self, key, details):
+        """Adds or replaces one recipe entry (``key`` in any spelling the grammar allows)."""
+        node = self._root
+        for part in self._path(key):
+            node = node.below.setdefault(part, _Node())
+        node.details, node.present = details, True
+
+    @property
+    def recipe(self):
+        """The normalised flat form (full keywords, dots) -- what the reference's builder keeps as ``recipe``."""
+        flat = {}
+
+        def walk(node, prefix):
+            for kw, sub in node.below.items():
+                path = prefix + [kw]
+                if sub.present:
+                    flat[".".join(path)] = sub.details
+                walk(sub, path)
+
+        walk(self._root, [])
+        return flat
+
+    @staticmethod
+    def _resolve(table_kw, details):
+        """-> (callable, args, kwargs) for an entry of the type table ``table_kw``."""
+        table = COMPONENT_NAME_TYPE_MAP.get(COMPONENT_KW_TYPE_ALIAS_MAP.get(table_kw, table_kw), {})
         args, kwargs = (), {}
-        type_kw = COMPONENT_KW_TYPE_ALIAS_MAP.get(component_kw, component_kw)
-        if isinstance(details, str):
-            ctype = COMPONENT_NAME_TYPE_MAP[type_kw][details]
-        elif isinstance(details, tuple):
-            ctype, args, kwargs = details
+        if isinstance(details, tuple):
+            details, args, kwargs = details
             kwargs = dict(kwargs)
-            if isinstance(ctype, str):
-                ctype = COMPONENT_NAME_TYPE_MAP[type_kw][ctype]
-        else:
-            ctype = details
-        if hasattr(ctype, "get_builder_kwargs"):
-            for kw, alt in ctype.get_builder_kwargs():
-                comp = self.make_component(kw, alt, prev_kw=full_kw.split("."))
-                if comp is not object:
-                    kwargs[kw] = comp
+        if isinstance(details, str):
+            details = table[details]
+        return details, tuple(args), kwargs
+
+    def _construct(self, kw, node, scope):
+        if node.details is None:
+            return None
+        ctype, args, kwargs = self._resolve(kw, node.details)
+        for sub_kw, stand_in in (ctype.get_builder_kwargs() if hasattr(ctype, "get_builder_kwargs") else ()):
+            sub = node.below.get(sub_kw)
+            if (sub is None or not sub.present) and stand_in is not None:
+                sub = node.below.get(stand_in)
+            if sub is not None and sub.present:
+                kwargs[sub_kw] = self._construct(sub_kw, sub, node)
         return ctype(*args, **kwargs)
 
+    def make_component(self, component_kw, alternative=None, prev_kw=None):
+        """The component registered under ``component_kw`` (below ``prev_kw``, a list of keywords, when given), or the
+        sentinel ``object`` when the recipe has no entry for it -- ``None`` is a legal component."""
+        node = self._root
+        for part in prev_kw or ():
+            node = node.below.get(part)
+            if node is None:
+                return object
+        found = node.below.get(COMPONENT_ALT_KW_MAP.get(component_kw, component_kw))
+        if (found is None or not found.present) and alternative is not None:
+            found = node.below.get(alternative)
+        if found is None or not found.present:
+            return object
+        return self._construct(component_kw, found, node)
+
     def make_input_data(self, data, preparation_hook=None, details=None):
-        if preparation_hook is None:
-            preparation_hook = self.recipe.get("preparation_hook", prepare_pass)
-        if isinstance(preparation_hook, str):
-            preparation_hook = COMPONENT_NAME_TYPE_MAP["preparation_hook"][preparation_hook]
+        """Runs the preparation hook on ``data`` and hands the result to the input-data type of the recipe."""
+        hook = preparation_hook
+        if hook is None:
+            hook_node = self._root.below.get("preparation_hook")
+            hook = hook_node.details if hook_node is not None and hook_node.present else prepare_pass
+        if isinstance(hook, str):
+            hook = COMPONENT_NAME_TYPE_MAP["preparation_hook"][hook]
         if details is None:
-            try:
-                details = self.recipe["input_data"]
-            except KeyError:
+            data_node = self._root.below.get("input_data")
+            if data_node is None or not data_node.present:
                 raise LookupError("Input data type details not found")
-        args, kwargs = (), {}
-        if isinstance(details, str):
-            ctype = COMPONENT_NAME_TYPE_MAP["input_data"][details]
-        elif isinstance(details, tuple):
-            ctype, args, kwargs = details
-            kwargs = dict(kwargs)
-            if isinstance(ctype, str):
-                ctype = COMPONENT_NAME_TYPE_MAP["input_data"][ctype]
-        else:
-            ctype = details
-        data_args, data_kwargs = preparation_hook(data)
+            details = data_node.details
+        ctype, args, kwargs = self._resolve("input_data", details)
+        data_args, data_kwargs = hook(data)
         if ctype is _types.InputDataNeighbourhoodsCSR and len(data_args) == 1:
-            data_args = tuple(data_args[0])
-        data_kwargs.setdefault("meta", {})
-        data_kwargs["meta"].update(kwargs.get("meta", {}))
+            data_args = tuple(data_args[0])          # (row_ptr, col_idx) handed over as one pair
+        meta = dict(data_kwargs.get("meta") or {})
+        meta.update(kwargs.get("meta", {}))
         kwargs.update(data_kwargs)
+        kwargs["meta"] = meta
         return ctype(*data_args, *args, **kwargs)

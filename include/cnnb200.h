@@ -155,6 +155,10 @@ int cnnb200_neighbours_from_distances(cnnb200_ctx *ctx, const double *dist, int 
 int cnnb200_neighbours_sort_rows(cnnb200_ctx *ctx, int *sorted_out);
 
 /* Sizes of the neighbourhood structure currently held. */
+/* Number of entries (i, j) whose mirror (j, i) is missing.  The component pass reads candidate edges as the entries
+ * j > i of row i, which equals the reference's BFS (_fit.pyx:434-491) only for SYMMETRIC lists -- radius
+ * neighbourhoods are; for lists of other origin (kNN) this is the check to run first. */
+int cnnb200_neighbours_asymmetry(cnnb200_ctx *ctx, int64_t *one_sided_out);
 int cnnb200_neighbours_info(cnnb200_ctx *ctx, int64_t *n, int64_t *nnz, int64_t *max_deg);
 
 /* Copies the neighbourhoods out in the CALLER's index space, rows ascending:
@@ -296,6 +300,16 @@ int cnnb200_fit_points(cnnb200_ctx *ctx, const double *x, int loc, int64_t n, in
 /* (clusters kept, members of the largest cluster, noise points) after the last cnnb200_sort_by_size /
  * cnnb200_fit_points with size sorting: what Clustering.fit stores in its Record (cluster.pyx:366-390), HOST int64 [3]. */
 int cnnb200_label_summary(cnnb200_ctx *ctx, int64_t *out3);
+
+/* Grouping of the points by (previous label, current label) for the hierarchy driver: replaces the per-point
+ * loop of HierarchicalFitterRepeat._fit (_fit.pyx:1150-1160, `parent_labels_map`) and the per-parent grouping of
+ * Bundle.isolate (_bundle.pyx:275-352) for ALL parents of a step at once.
+ *   order[k]  point indices sorted by (prev, cur, index)
+ *   rank[k]   position of point order[k] among the points with the same previous label, in index order
+ * The members of (parent p, child c) are one contiguous slice of order; the same slice of rank gives their places in
+ * the parent's own label array.  prev / cur / order / rank: int64 [n], all in `loc`. */
+int cnnb200_labels_group(cnnb200_ctx *ctx, const int64_t *prev, const int64_t *cur, int loc, int64_t n,
+                         int64_t *order, int64_t *rank);
 
 /* Page-lock / release a caller array in place (no copy is kept): repeated fits on the same coordinates then
  * transfer at PCIe speed. */

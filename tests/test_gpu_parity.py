@@ -311,8 +311,8 @@ def test_sort_rows_on_arrival(ctx):
         rng.shuffle(sh[rp[i]:rp[i + 1]])
     ctx.neighbours_from_csr(rp, ci)
     assert ctx.neighbours_sort_rows() is False
-    ctx.neighbours_from_csr(rp, sh)
-    assert ctx.neighbours_sort_rows() is True
+    ctx.neighbours_from_csr(rp, sh)                      # lists in any order are sorted by the ingest itself
+    assert ctx.neighbours_sort_rows() is False
     got_rp, got_ci = ctx.neighbours_export()
     np.testing.assert_array_equal(got_ci, ci)
     lab = np.zeros(x.shape[0], dtype=np.int64)
@@ -322,7 +322,7 @@ def test_sort_rows_on_arrival(ctx):
     d_rp, d_sh = torch.from_numpy(rp).cuda(), torch.from_numpy(sh.astype(np.int32)).cuda()
     keep = d_sh.clone()
     ctx.neighbours_from_csr(d_rp, d_sh, borrow=True)
-    assert ctx.neighbours_sort_rows() is True
+    assert ctx.neighbours_sort_rows() is False
     assert torch.equal(d_sh, keep)
     np.testing.assert_array_equal(ctx.neighbours_export()[1], ci)
     # through the API: list of shuffled lists, the reference's default lookup getter (is_sorted=False)
@@ -891,3 +891,84 @@ def test_unsorted_lists_are_sorted_on_every_ingest_path(ctx):
     ctx.fit(6, 7, 1, got, None)
     ctx.sort_by_size(got, None)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_hierarchical_repeat_equals_reference(ctx):
+    """Clustering.fit_hierarchical with HierarchicalFitterRepeat against the reference's own
+    (_fit.pyx:1018-1184, cluster.pyx:394-411): the same tree -- label array, children and reference indices of every
+    bundle."""
+    from oracle import ref
+
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rmod = ref.module()
+    x = datasets.blobs_2d(1500)
+    kw = dict(radius_cutoff=[0.5, 0.25, 0.12, 0.08], cnn_cutoff=[5, 8, 8, 10], member_cutoff=5, v=False)
+    theirs = rmod.Clustering(
+        x, hierarchical_fitter="repeat", hierarchical_fitter__fitter="bfs", hierarchical_fitter__fitter__ngetter="brute_force",
+        hierarchical_fitter__fitter__na="vuset", hierarchical_fitter__fitter__nb="vuset",
+        hierarchical_fitter__fitter__checker="switch", hierarchical_fitter__fitter__queue="fifo",
+        hierarchical_fitter__fitter__ngetter__dgetter="metric", hierarchical_fitter__fitter__ngetter__dgetter__metric="euclidean_r")
+    theirs.fit_hierarchical(**kw)
+    ours = cluster.Clustering(x, hierarchical_fitter="repeat", hierarchical_fitter__fitter="b200_staged",
+                              hierarchical_fitter__fitter__ngetter="radius_b200",
+                              hierarchical_fitter__fitter__ngetter__dgetter="metric",
+                              hierarchical_fitter__fitter__ngetter__dgetter__metric="euclidean_r")
+    ours._hierarchical_fitter._fitter._ctx = ctx
+    ours.fit_hierarchical(**kw)
+    nodes = [0]
+
+    def same(a, b):
+        nodes[0] += 1
+        la = None if a._labels is None else np.asarray(a._labels.labels)
+        lb = None if b._labels is None else np.asarray(b._labels.labels)
+        assert (la is None) == (lb is None)
+        if la is not None:
+            np.testing.assert_array_equal(la, lb)
+        ca, cb = a._children or {}, b._children or {}
+        assert list(ca) == list(cb)
+        for k in ca:
+            np.testing.assert_array_equal(ca[k].parent_indices, np.asarray(cb[k]._reference_indices.parent))
+            np.testing.assert_array_equal(ca[k].root_indices, np.asarray(cb[k]._reference_indices.root))
+            same(ca[k], cb[k])
+
+    same(ours._bundle, theirs._bundle)
+    assert nodes[0] > 5
+    # the default hierarchical fitter wraps the clustering's own fitter; sequences may be given as scalars
+    cl = cluster.Clustering(x)
+    cl.fitter._ctx = ctx
+    cl.fit_hierarchical(radius_cutoff=0.25, cnn_cutoff=[8, 20], member_cutoff=5, v=False)
+    assert cl.root._children and cl.root._labels is not None
+    # the device grouping primitive on its own: order and rank against NumPy
+    rng = np.random.default_rng(2)
+    prev, cur = rng.integers(0, 7, 5000), rng.integers(0, 9, 5000)
+    order, rank = ctx.labels_group(prev, cur)
+    np.testing.assert_array_equal(order, np.lexsort((np.arange(5000), cur, prev)))
+    want_rank = np.empty(5000, dtype=np.int64)
+    for p in range(7):
+        idx = np.flatnonzero(prev == p)
+        want_rank[idx] = np.arange(idx.size)
+    np.testing.assert_array_equal(rank, want_rank[order])
+
+
+@pytest.mark.gpu
+def test_symmetry_check_of_precomputed_lists(ctx):
+    x = datasets.md_like_3d(3000)
+    rp, ci = port.neighbours(x, 0.3 ** 2)
+    ctx.neighbours_from_csr(rp, ci)
+    assert ctx.neighbours_asymmetry() == 0
+    # kNN-style lists: drop the last entry of every row with more than three entries
+    keep = np.ones(ci.shape[0], dtype=bool)
+    keep[(rp[1:] - 1)[np.diff(rp) > 3]] = False
+    rp2 = np.zeros_like(rp)
+    np.cumsum(np.add.reduceat(keep.astype(np.int64), rp[:-1]), out=rp2[1:])
+    ci2 = ci[keep]
+    ctx.neighbours_from_csr(rp2, ci2)
+    rows = np.repeat(np.arange(x.shape[0]), np.diff(rp2))
+    have = set(zip(rows.tolist(), ci2.tolist()))
+    want = sum((j, i) not in have for i, j in have)
+    assert want > 0 and ctx.neighbours_asymmetry() == want
+    g = _types.NeighboursGetterLookup(is_sorted=True, check_symmetric=True)
+    with pytest.raises(ValueError):
+        g.get_all(_types.InputDataNeighbourhoodsCSR(rp2, ci2), ctx=ctx)

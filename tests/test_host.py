@@ -171,3 +171,27 @@ def test_isolate_and_reel_equal_reference():
     theirs.reel()
     np.testing.assert_array_equal(ours.labels, theirs.labels)
     assert ours.root._labels.meta["params"] == theirs.root._labels.meta["params"]
+
+
+def test_get_subset_of_every_input_type():
+    """Bundle.isolate relies on get_subset: coordinates carry their part lengths along, neighbourhood inputs are
+    restricted to the subset and renumbered (_bundle.pyx:321-350, _types.pyx:1199-1217)."""
+    from commonnnclustering_b200 import _types
+
+    x = np.arange(20, dtype=np.float64).reshape(10, 2)
+    comp = _types.InputDataComponents(x, meta={"edges": [4, 3, 3]})
+    sub = comp.get_subset([0, 1, 5, 9])
+    assert sub.meta["edges"] == [2, 1, 1] and np.array_equal(sub.to_components_array(), x[[0, 1, 5, 9]])
+    rp = np.array([0, 3, 5, 8, 10, 12], dtype=np.int64)
+    ci = np.array([0, 1, 2, 0, 1, 0, 2, 4, 3, 4, 2, 4], dtype=np.int64)
+    idx = np.array([0, 2, 4])
+    want_rows = [[0, 1], [0, 1, 2], [1, 2]]            # members {0, 2, 4} renumbered to 0, 1, 2
+    csr = _types.InputDataNeighbourhoodsCSR(rp, ci).get_subset(idx)
+    got_rp, got_ci = csr.to_csr()
+    assert [got_ci[a:b].tolist() for a, b in zip(got_rp[:-1], got_rp[1:])] == want_rows
+    padded = np.zeros((5, 3), dtype=np.int64)
+    counts = np.diff(rp)
+    for i in range(5):
+        padded[i, :counts[i]] = ci[rp[i]:rp[i + 1]]
+    nb = _types.InputDataNeighbourhoods(padded, counts).get_subset(idx)
+    assert [row.tolist() for row in nb.data] == want_rows and nb.n_neighbours.tolist() == [2, 3, 2]

@@ -60,3 +60,32 @@ def test_reference_clustering_runs_on_the_gpu_fitter():
         cl.fit(0.2, 3, v=False, sort_by_size=False)
         outs.append(np.asarray(cl.labels).copy())
     np.testing.assert_array_equal(outs[0], outs[1])
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_reference_neighbourhood_recipes_run_on_the_gpu_fitter():
+    """`sorted_neighbourhoods_b200`: the reference's own input type and preparation hook (padded int64 matrix), the GPU
+    fitter; lists in ascending order and in any order, against the reference's two neighbourhood recipes."""
+    from commonnnclustering_b200 import datasets, plugin
+    from oracle import port
+
+    mod = ref.module()
+    plugin.register()
+    rng = np.random.default_rng(4)
+    for x, r, c, kw in [(datasets.blobs_2d(2500), 0.1, 10, {"member_cutoff": 5}),
+                        (datasets.md_like_3d(3000), 0.4, 5, {})]:
+        rp, ci = port.neighbours(x, r * r)
+        nb = [ci[a:b] for a, b in zip(rp[:-1], rp[1:])]
+        shuffled = [rng.permutation(row) for row in nb]
+        cpu = mod.Clustering(nb, recipe="sorted_neighbourhoods")
+        cpu.fit(r, c, v=False, **kw)
+        cpu_any = mod.Clustering(shuffled, recipe="neighbourhoods")
+        cpu_any.fit(r, c, v=False, **kw)
+        np.testing.assert_array_equal(np.asarray(cpu_any.labels), np.asarray(cpu.labels))
+        for lists in (nb, shuffled):
+            gpu = mod.Clustering(lists, recipe="sorted_neighbourhoods_b200")
+            gpu.fit(r, c, v=False, **kw)
+            np.testing.assert_array_equal(np.asarray(gpu.labels), np.asarray(cpu.labels))
+        padded, counts = plugin._padded_view(gpu._bundle._input_data)
+        assert padded is not None and padded.shape[0] == len(nb) and int(counts.sum()) == int(rp[-1])

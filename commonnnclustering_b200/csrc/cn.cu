@@ -284,15 +284,16 @@ __global__ void comp_compress_kernel(int *parent, ll n) {
 #define WIN_PF 5        // chunks (of 32 entries) prefetched per streamed row
 
 struct RowWin {
-    unsigned *bits;  // WIN_BITS / 32 words owned by the warp; all zero between rows
+    unsigned *bits;  // cap / 32 words owned by the warp; all zero between rows
     int first;
     unsigned span;  // 0: no window
+    unsigned cap = WIN_BITS;  // window bits available to the warp
 };
 
 __device__ __forceinline__ void win_set(RowWin &w, const int *__restrict__ row, int m, int lane) {
     w.first = row[0];
     const unsigned span = (unsigned)(row[m - 1] - w.first) + 1u;
-    w.span = span <= (unsigned)WIN_BITS ? span : 0u;
+    w.span = span <= w.cap ? span : 0u;
     if (w.span)
         for (int k = lane; k < m; k += 32) {
             const unsigned idx = (unsigned)(row[k] - w.first);
@@ -448,18 +449,20 @@ comp_scan_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx
 // shared-memory window of row i -- the scan emits the work list row by row, so consecutive entries
 // mostly share i and the window is rebuilt only when i changes -- while the entries of the next
 // N(j) are already in flight.
-__global__ void __launch_bounds__(WIN_WARPS * 32)
+template <int WBITS, int MINB>
+__global__ void __launch_bounds__(WIN_WARPS * 32, MINB)
 comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, const int2 *__restrict__ worklist,
                      const unsigned long long *__restrict__ wl_count, unsigned long long *chunk_counter, int chunk,
                      int cutoff, int *parent, unsigned long long *stats) {
-    __shared__ unsigned win_all[WIN_WARPS][WIN_BITS / 32];
+    __shared__ unsigned win_all[WIN_WARPS][WBITS / 32];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     RowWin w;
     w.bits = win_all[threadIdx.x >> 5];
     w.first = 0;
     w.span = 0;
-    for (int t = lane; t < WIN_BITS / 32; t += 32) w.bits[t] = 0;
+    w.cap = WBITS;
+    for (int t = lane; t < WBITS / 32; t += 32) w.bits[t] = 0;
     __syncwarp();
     const ll count = (ll)*wl_count;
     {   // short lists: at least four chunks per warp
@@ -872,7 +875,20 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
     ll cap_edges = ctx->nnz + 64;  // work list: at most one entry per CSR entry of the row block
     CNN_TRY(cnn_ensure(ctx, ctx->b_worklist, sizeof(int2) * (size_t)cap_edges));
     unsigned long long *wl_count = stats + ST_WL_COUNT;  // + ST_COUNTER right behind it
-    static const int wl_ctas = resident_ctas(comp_worklist_kernel, WIN_WARPS * 32);
+    // work-list kernel variant: window bits per warp / resident CTAs per SM asked for (CNNB200_WL_VARIANT: 0 = 64 Ki bits,
+    // 1 = 32 Ki bits and 8 CTAs per SM -- more warps in flight, rows spanning more than 32 Ki indices take the
+    // binary-search path)
+    static const int wl_variant = getenv("CNNB200_WL_VARIANT") ? atoi(getenv("CNNB200_WL_VARIANT")) : 0;
+    static const int wl_ctas = wl_variant == 1 ? resident_ctas(comp_worklist_kernel<32768, 8>, WIN_WARPS * 32)
+                                               : resident_ctas(comp_worklist_kernel<WIN_BITS, 6>, WIN_WARPS * 32);
+    auto launch_worklist = [&](int chunk_) {
+        if (wl_variant == 1)
+            comp_worklist_kernel<32768, 8><<<ctx->sm_count * wl_ctas, WIN_WARPS * 32, 0, st>>>(
+                ctx->row_ptr, ctx->col_idx, ctx->b_worklist.as<int2>(), wl_count, stats + ST_COUNTER, chunk_, cutoff, parent, stats);
+        else
+            comp_worklist_kernel<WIN_BITS, 6><<<ctx->sm_count * wl_ctas, WIN_WARPS * 32, 0, st>>>(
+                ctx->row_ptr, ctx->col_idx, ctx->b_worklist.as<int2>(), wl_count, stats + ST_COUNTER, chunk_, cutoff, parent, stats);
+    };
     if (ns > 0 && ctx->far_stride > 0 && !ctx->comp_packed) {
         {
             Span sp(ctx, T_COMP_SAMPLE);
@@ -880,9 +896,7 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
             comp_far_emit_kernel<<<cnn_blocks(rows, 256), 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end,
                                                                         ctx->far_stride, parent, above,
                                                                         ctx->b_worklist.as<int2>(), wl_count);
-            comp_worklist_kernel<<<ctx->sm_count * wl_ctas, WIN_WARPS * 32, 0, st>>>(
-                ctx->row_ptr, ctx->col_idx, ctx->b_worklist.as<int2>(), wl_count, stats + ST_COUNTER, ctx->wl_chunk, cutoff,
-                parent, stats);
+            launch_worklist(ctx->wl_chunk);
         }
         Span sp(ctx, T_COMP_FLATTEN);
         comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(parent, ctx->n);
@@ -901,9 +915,7 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         if (ctx->comp_packed) {
             CNN_TRY(cnn_worklist_packed(ctx, ctx->b_worklist.as<int2>(), wl_count, cutoff, parent));
         } else {
-            comp_worklist_kernel<<<ctx->sm_count * wl_ctas, WIN_WARPS * 32, 0, st>>>(
-                ctx->row_ptr, ctx->col_idx, ctx->b_worklist.as<int2>(), wl_count, stats + ST_COUNTER, ctx->wl_chunk, cutoff,
-                parent, stats);
+            launch_worklist(ctx->wl_chunk);
         }
         CNN_LAUNCHED(ctx, 2);
     }

@@ -259,8 +259,10 @@ comp_far_emit_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col
     unsigned long long pos = 0;
     if (lane == 0) pos = atomicAdd(wl_count, (unsigned long long)tot);
     pos = __shfl_sync(full, pos, 0);
-    if (e0) worklist[pos + __popc(b0 & lt)] = make_int2((int)i, j0);
-    if (e1) worklist[pos + __popc(b0) + __popc(b1 & lt)] = make_int2((int)i, j1);
+    // the two edges of a row next to each other: the work-list kernel builds the row's window once for both
+    const unsigned long long mine = pos + __popc(b0 & lt) + __popc(b1 & lt);
+    if (e0) worklist[mine] = make_int2((int)i, j0);
+    if (e1) worklist[mine + (e0 ? 1 : 0)] = make_int2((int)i, j1);
 }
 
 __global__ void comp_compress_kernel(int *parent, ll n) {
@@ -310,6 +312,8 @@ __device__ __forceinline__ void win_clear(RowWin &w, const int *__restrict__ row
     __syncwarp();
 }
 
+__device__ __forceinline__ bool win_ready(const RowWin &w) { return w.span != 0; }
+
 // 1 when v is an entry of the windowed row.  v = -1 (padding) never is: first >= 0 puts it out of range.
 __device__ __forceinline__ int win_probe(const RowWin &w, int v) {
     const unsigned idx = (unsigned)(v - w.first);
@@ -324,7 +328,10 @@ __device__ __forceinline__ void row_prefetch(int (&buf)[WIN_PF], const int *__re
     }
 }
 
-// |windowed row ∩ N(j)|, N(j)'s first WIN_PF chunks already in registers
+// |windowed row ∩ N(j)|, N(j)'s first WIN_PF chunks already in registers.  (Measured and dropped, r2: keeping a row
+// WITHOUT index locality as a sorted array in the window words and probing it by binary search in shared memory --
+// on C4 the global-memory search of warp_common, which shrinks its range as it goes and stops early, is faster:
+// 9.5 ms against 11.2 ms per fit.)
 __device__ __forceinline__ int row_count(const int (&buf)[WIN_PF], const int *__restrict__ rj, int mj, int lane,
                                          const RowWin &w) {
     int c = 0;
@@ -511,7 +518,7 @@ comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col
                 win_set(w, cur_row, cur_m, lane);
             }
             int ok;
-            if (w.span) ok = row_count(f.buf, f.rj, f.mj, lane, w) >= cutoff;
+            if (win_ready(w)) ok = row_count(f.buf, f.rj, f.mj, lane, w) >= cutoff;
             else ok = warp_common<true>(cur_row, cur_m, f.rj, f.mj, cutoff, lane);
             if (lane == f.src) acc = ok;
             if (ok) {
@@ -734,7 +741,7 @@ cn_count_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx,
                 continue;
             }
             win_set(w, row, m, lane);
-            if (!w.span) ++n_fallback;
+            if (!win_ready(w)) ++n_fallback;
             for (int k0 = 0; k0 < m; k0 += 32) {
                 const int k = k0 + lane;
                 const int j = k < m ? row[k] : -1;
@@ -744,7 +751,7 @@ cn_count_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx,
                 unsigned todo = __ballot_sync(full, valid && mj > n_member_cutoff);
                 unsigned out = 0xffffffffu;
                 n_edges += __popc(todo);
-                const bool windowed = w.span != 0;
+                const bool windowed = win_ready(w);
                 auto consume = [&](const RowFetch &f) {
                     const int c = windowed ? row_count(f.buf, f.rj, f.mj, lane, w)
                                            : warp_common<false>(row, m, f.rj, f.mj, 0, lane);
@@ -801,6 +808,7 @@ int cnn_fetch_comp_stats(cnnb200_ctx *ctx) { return fetch_stats(ctx); }
 extern "C" int cnnb200_components_begin(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_t similarity_cutoff,
                                         const uint8_t *consider, int loc) {
     if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");
+
     if (!ctx->have_nb) CNN_FAIL(CNNB200_E_STATE, "components: no neighbourhoods held by this context");
     if (n_member_cutoff < 0 || similarity_cutoff < 0)
         CNN_FAIL(CNNB200_E_INVALID, "components: cutoffs must be >= 0");

@@ -58,6 +58,35 @@ __global__ void rows_check_kernel(const ll *__restrict__ row_ptr, const int *__r
     if (unsorted) flag[2] = 1;
 }
 
+// The same checks with one THREAD per row, for short rows (a warp per row spends most of its time waiting for two
+// dependent loads per 50 entries): offsets monotone (flag[0]), indices inside [0, n) (flag[0]), rows ascending (flag[2]),
+// largest degree (flag[1]).  Consecutive threads walk consecutive rows, so the sectors they touch are shared through L1.
+__global__ void __launch_bounds__(256)
+rows_check_short_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col, ll n, ll nnz, int *flag) {
+    const ll r = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    bool bad = false, unsorted = false;
+    int deg = 0;
+    if (r < n) {
+        const ll b = row_ptr[r], e = row_ptr[r + 1];
+        if (b < 0 || e > nnz || b > e || e - b > 0x7fffffffll) {
+            bad = true;
+        } else {
+            deg = (int)(e - b);
+            int prev = -1;
+            for (ll k = b; k < e; ++k) {
+                const int v = col[k];
+                bad |= v < 0 || v >= n;
+                unsorted |= v < prev;
+                prev = v;
+            }
+        }
+    }
+    deg = __reduce_max_sync(0xffffffffu, deg);
+    if ((threadIdx.x & 31) == 0 && deg > 0) atomicMax(flag + 1, deg);
+    if (bad) flag[0] = 1;
+    if (unsorted) flag[2] = 1;
+}
+
 __global__ void deg_from_row_ptr_kernel(const ll *__restrict__ row_ptr, ll n, int *deg, int *flag) {
     ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
     if (i > n) return;
@@ -169,20 +198,27 @@ extern "C" int cnnb200_neighbours_from_csr(cnnb200_ctx *ctx, const int64_t *row_
         d_col = ctx->b_col_idx.as<int>();
     }
     CNN_KERNEL_CHECK();
-    // degrees (for max_deg and a monotonicity check of row_ptr), then index range + ascending rows in one pass
-    CNN_TRY(cnn_ensure(ctx, ctx->b_deg, sizeof(int) * (size_t)(n + 1)));
-    deg_from_row_ptr_kernel<<<cnn_blocks(n + 1, 256), 256, 0, st>>>(d_row_ptr, n, ctx->b_deg.as<int>(), flag);
-    {
-        ll blocks = (n + 7) / 8;
-        if (blocks > (ll)ctx->sm_count * 32) blocks = (ll)ctx->sm_count * 32;
-        rows_check_kernel<<<(int)blocks, 256, 0, st>>>(d_row_ptr, d_col, n, nnz, flag);
+    if (nnz / n < 96) {
+        // short rows: offsets, index range, ascending order and the largest degree in ONE pass, a thread per row
+        rows_check_short_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_row_ptr, d_col, n, nnz, flag);
+        CNN_LAUNCHED(ctx, 1);
+        CNN_KERNEL_CHECK();
+    } else {
+        // degrees (for max_deg and a monotonicity check of row_ptr), then index range + ascending rows, a warp per row
+        CNN_TRY(cnn_ensure(ctx, ctx->b_deg, sizeof(int) * (size_t)(n + 1)));
+        deg_from_row_ptr_kernel<<<cnn_blocks(n + 1, 256), 256, 0, st>>>(d_row_ptr, n, ctx->b_deg.as<int>(), flag);
+        {
+            ll blocks = (n + 7) / 8;
+            if (blocks > (ll)ctx->sm_count * 32) blocks = (ll)ctx->sm_count * 32;
+            rows_check_kernel<<<(int)blocks, 256, 0, st>>>(d_row_ptr, d_col, n, nnz, flag);
+        }
+        CNN_KERNEL_CHECK();
+        size_t need = 0;
+        CNN_CUDA(cub::DeviceReduce::Max(nullptr, need, ctx->b_deg.as<int>(), flag + 1, (int)(n + 1), st));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
+        size_t cap = ctx->b_cub.cap;
+        CNN_CUDA(cub::DeviceReduce::Max(ctx->b_cub.p, cap, ctx->b_deg.as<int>(), flag + 1, (int)(n + 1), st));
     }
-    CNN_KERNEL_CHECK();
-    size_t need = 0;
-    CNN_CUDA(cub::DeviceReduce::Max(nullptr, need, ctx->b_deg.as<int>(), flag + 1, (int)(n + 1), st));
-    CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
-    size_t cap = ctx->b_cub.cap;
-    CNN_CUDA(cub::DeviceReduce::Max(ctx->b_cub.p, cap, ctx->b_deg.as<int>(), flag + 1, (int)(n + 1), st));
     int *h;
     CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
     CNN_CUDA(cudaMemcpyAsync(h, flag, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));

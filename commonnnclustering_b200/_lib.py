@@ -50,6 +50,7 @@ SIGNATURES = {
     "cnnb200_fit": [_P, _I64, _I64, _I64, _P, _P, C.c_int, C.POINTER(_I64)],
     "cnnb200_components_begin": [_P, _I64, _I64, _P, C.c_int],
     "cnnb200_components_edges": [_P, _I64, _I64],
+    "cnnb200_components_phase": [_P, _I64, _I64, C.c_int],
     "cnnb200_components_from_counts": [_P, _P],
     "cnnb200_components_parents": [_P, C.POINTER(_P)],
     "cnnb200_components_merge": [_P, _P, _I64],
@@ -336,6 +337,9 @@ class Context:
 
     def components_edges(self, row_begin, row_end):
         check(self._lib.cnnb200_components_edges(self._h, int(row_begin), int(row_end)))
+
+    def components_phase(self, row_begin, row_end, phase):
+        check(self._lib.cnnb200_components_phase(self._h, int(row_begin), int(row_end), int(phase)))
 
     def components_from_counts(self, counts):
         p, loc = _ptr_loc(counts)

@@ -841,7 +841,10 @@ extern "C" int cnnb200_components_begin(cnnb200_ctx *ctx, int64_t n_member_cutof
     return CNNB200_OK;
 }
 
-extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end) {
+// phases: 1 = the sampling rounds (first entry above every row; far entries from every k-th row of a tree),
+//         2 = the scan of all candidate edges + the work list.  A row-sharded run may exchange and merge the forests
+//         between the two, so that the scan sees what the other ranks' samples already joined.
+static int components_pass(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end, int phases) {
     if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");
     if (!ctx->have_comp) CNN_FAIL(CNNB200_E_STATE, "components_edges: call components_begin first");
     if (row_begin < 0 || row_end > ctx->n || row_begin > row_end)
@@ -857,7 +860,8 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
     int *parent = ctx->b_parent.as<int>();
     CNN_TRY(cnn_ensure(ctx, ctx->b_above, sizeof(int) * (size_t)ctx->n));
     int *above = ctx->b_above.as<int>();
-    if (ns > 0) {
+    if (!(phases & 1)) {
+    } else if (ns > 0) {
         Span sp(ctx, T_COMP_SAMPLE);
         ll slots = rows * ns;
         CNN_TRY(cnn_ensure(ctx, ctx->b_edges, sizeof(int) * (size_t)slots));
@@ -876,7 +880,7 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         comp_above_kernel<<<cnn_blocks(rows, 256), 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end, above);
         CNN_LAUNCHED(ctx, 1);
     }
-    {
+    if (phases & 1) {
         Span sp(ctx, T_COMP_FLATTEN);
         comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(parent, ctx->n);
     }
@@ -897,7 +901,7 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
             comp_worklist_kernel<WIN_BITS, 6><<<ctx->sm_count * wl_ctas, WIN_WARPS * 32, 0, st>>>(
                 ctx->row_ptr, ctx->col_idx, ctx->b_worklist.as<int2>(), wl_count, stats + ST_COUNTER, chunk_, cutoff, parent, stats);
     };
-    if (ns > 0 && ctx->far_stride > 0 && !ctx->comp_packed) {
+    if ((phases & 1) && ns > 0 && ctx->far_stride > 0 && !ctx->comp_packed) {
         {
             Span sp(ctx, T_COMP_SAMPLE);
             CNN_CUDA(cudaMemsetAsync(wl_count, 0, 2 * sizeof(unsigned long long), st));
@@ -910,7 +914,7 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(parent, ctx->n);
         CNN_LAUNCHED(ctx, 3);
     }
-    {
+    if (phases & 2) {
         Span sp(ctx, T_COMP_EDGES);
         CNN_CUDA(cudaMemsetAsync(wl_count, 0, 2 * sizeof(unsigned long long), st));
         int tile_rows = 32;  // about 8k entries per warp tile
@@ -927,13 +931,22 @@ extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int
         }
         CNN_LAUNCHED(ctx, 2);
     }
-    {
+    if (phases & 2) {
         Span sp(ctx, T_COMP_FLATTEN);
         comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(parent, ctx->n);
     }
     CNN_LAUNCHED(ctx, 2);
     CNN_KERNEL_CHECK();
     return CNNB200_OK;
+}
+
+extern "C" int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end) {
+    return components_pass(ctx, row_begin, row_end, 3);
+}
+
+extern "C" int cnnb200_components_phase(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end, int phase) {
+    if (phase != 1 && phase != 2) CNN_FAIL(CNNB200_E_INVALID, "components_phase: phase must be 1 (sampling rounds) or 2 (scan + work list)");
+    return components_pass(ctx, row_begin, row_end, phase);
 }
 
 extern "C" int cnnb200_components_from_counts(cnnb200_ctx *ctx, const uint32_t *counts) {

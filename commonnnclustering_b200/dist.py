@@ -125,9 +125,10 @@ class ShardedFit:
     # -- neighbourhoods from a precomputed CSR: each rank uploads only its row block ------------------
     def upload_csr_block(self, row_ptr_host, col_idx_host):
         """Host CSR (row_ptr int64 [n+1], col_idx int32 [nnz]; every rank sees the arrays, e.g. memory-mapped) ->
-        this rank's rows in HBM: its slice of ``row_ptr`` and of ``col_idx``, each copied straight into its place in
-        the full-size device buffers (the exchange fills the rest).  Row blocks are balanced by entries; the arrays
-        are page-locked in place once, so the G uploads run concurrently at PCIe speed, 1/G of the bytes each."""
+        1/G of the bytes in HBM on every rank.  Both arrays are cut into G EQUAL flat chunks (a chunk need not end at a
+        row: the upload and the exchange move bytes, only the component pass works on row blocks), so the exchange is
+        one in-place ``all_gather_into_tensor`` per array.  The arrays are page-locked in place once; the G uploads run
+        concurrently, each over its own PCIe link."""
         G = self.world
         n = row_ptr_host.shape[0] - 1
         nnz = int(row_ptr_host[-1])
@@ -143,34 +144,37 @@ class ShardedFit:
             targets = (np.arange(G + 1, dtype=np.float64) * nnz / G).astype(np.int64)
             bounds = np.searchsorted(row_ptr_host, targets, side="left").astype(np.int64)
             bounds[0], bounds[-1] = 0, n
-            bounds = np.maximum.accumulate(bounds)
-            slice_bounds = row_ptr_host[bounds].astype(np.int64)
-            row_ptr = torch.empty(n + 1, dtype=torch.int64, device=self.device)
-            col_idx = torch.empty(max(nnz, 1), dtype=torch.int32, device=self.device)[:nnz]
-            plan = self._csr_plan = (key, bounds, slice_bounds, row_ptr, col_idx)
-        _, bounds, slice_bounds, row_ptr, col_idx = plan
-        b, e = block_of(bounds, self.rank)
-        s, t = int(slice_bounds[self.rank]), int(slice_bounds[self.rank + 1])
-        hi = e + 1 if self.rank == G - 1 else e     # the last rank also owns row_ptr[n]
-        row_ptr[b:hi].copy_(torch.from_numpy(row_ptr_host[b:hi]), non_blocking=True)
-        if col_idx_host.dtype == np.int32:
-            col_idx[s:t].copy_(torch.from_numpy(col_idx_host[s:t]), non_blocking=True)
-        else:
-            col_idx[s:t].copy_(torch.from_numpy(np.ascontiguousarray(col_idx_host[s:t])).to(self.device, non_blocking=True))
-        return dict(n=n, nnz=nnz, bounds=bounds, slice_bounds=slice_bounds, row_ptr=row_ptr, col_idx=col_idx)
+            bounds = np.maximum.accumulate(bounds)                     # row blocks balanced by entries
+            chunk_r, chunk_c = -(-(n + 1) // G), -(-max(nnz, 1) // G)  # flat chunks of the two arrays
+            row_ptr = torch.empty(G * chunk_r, dtype=torch.int64, device=self.device)
+            col_idx = torch.empty(G * chunk_c, dtype=torch.int32, device=self.device)
+            plan = self._csr_plan = (key, bounds, chunk_r, chunk_c, row_ptr, col_idx)
+        _, bounds, chunk_r, chunk_c, row_ptr, col_idx = plan
+        g = self.rank
+        a, b = g * chunk_r, min((g + 1) * chunk_r, n + 1)
+        if b > a:
+            row_ptr[a:b].copy_(torch.from_numpy(row_ptr_host[a:b]), non_blocking=True)
+        a, b = g * chunk_c, min((g + 1) * chunk_c, nnz)
+        if b > a:
+            if col_idx_host.dtype == np.int32:
+                col_idx[a:b].copy_(torch.from_numpy(col_idx_host[a:b]), non_blocking=True)
+            else:
+                col_idx[a:b].copy_(torch.from_numpy(np.ascontiguousarray(col_idx_host[a:b])).to(self.device, non_blocking=True))
+        return dict(n=n, nnz=nnz, bounds=bounds, chunk_r=chunk_r, chunk_c=chunk_c, row_ptr=row_ptr, col_idx=col_idx)
 
     def exchange_csr(self, blk):
-        """Exchange 1 of SURVEY 8e on rows that already sit in HBM: the slices of ``row_ptr`` and ``col_idx`` are
-        broadcast from their owners into every rank's full-size buffers (NCCL over NVLink); the gathered CSR is
-        adopted.  Returns the row-block bounds."""
-        G, bounds = self.world, blk["bounds"]
-        rb = np.array(bounds, dtype=np.int64)
-        rb[-1] += 1
-        exchange_slices(blk["row_ptr"], rb, self.group)
-        exchange_slices(blk["col_idx"], blk["slice_bounds"], self.group)
-        self.ctx.neighbours_adopt(blk["row_ptr"], blk["col_idx"], -1, grid_perm=False)
-        self.last = dict(bounds=bounds, slice_bounds=blk["slice_bounds"], nnz=blk["nnz"])
-        return bounds
+        """Exchange 1 of SURVEY 8e on bytes that already sit in HBM: all-gather of the G equal chunks of ``row_ptr``
+        and of ``col_idx`` (in place, NCCL over NVLink); the gathered CSR is adopted.  Returns the row-block bounds."""
+        g = self.rank
+        for full, chunk in ((blk["row_ptr"], blk["chunk_r"]), (blk["col_idx"], blk["chunk_c"])):
+            mine = full[g * chunk:(g + 1) * chunk]
+            if full.is_cuda:
+                dist.all_gather_into_tensor(full, mine, group=self.group)
+            else:
+                dist.all_gather(list(full.view(self.world, chunk).unbind(0)), mine.clone(), group=self.group)
+        self.ctx.neighbours_adopt(blk["row_ptr"][:blk["n"] + 1], blk["col_idx"][:blk["nnz"]], -1, grid_perm=False)
+        self.last = dict(bounds=blk["bounds"], nnz=blk["nnz"], two_phase=True)
+        return blk["bounds"]
 
     def neighbours_from_csr_host(self, row_ptr_host, col_idx_host):
         return self.exchange_csr(self.upload_csr_block(row_ptr_host, col_idx_host))
@@ -185,16 +189,28 @@ class ShardedFit:
         n = int(bounds[-1])
         b, e = block_of(bounds, self.rank)
         ctx.components_begin(n_member_cutoff, similarity_cutoff)
-        ctx.components_edges(b, e)
         pptr = ctx.components_parents_ptr()
         key = (pptr, n)
         if getattr(self, "_parents_key", None) != key:
             self._parents_key, self._parents = key, tensor_from_ptr(pptr, (n,), "<i4", self.device)
         gathered = self._gather_buffer(n)
-        if gathered.is_cuda:
-            dist.all_gather_into_tensor(gathered, self._parents, group=self.group)
+
+        def gather():
+            if gathered.is_cuda:
+                dist.all_gather_into_tensor(gathered, self._parents, group=self.group)
+            else:
+                dist.all_gather(list(gathered.unbind(0)), self._parents, group=self.group)
+
+        if self.last.get("two_phase") and self.world > 1:
+            # lists without index locality: most candidate edges cross the row blocks, so the forests of the sampling
+            # rounds are exchanged and merged BEFORE the scan -- each rank then skips what any rank already joined
+            ctx.components_phase(b, e, 1)
+            gather()
+            ctx.components_merge(gathered, self.world)
+            ctx.components_phase(b, e, 2)
         else:
-            dist.all_gather(list(gathered.unbind(0)), self._parents, group=self.group)
+            ctx.components_edges(b, e)
+        gather()
         return ctx.fit_sharded_end(gathered, self.world, labels, sort_by_size, current_start, member_cutoff, max_clusters)
 
     def upload_points(self, x):

@@ -213,6 +213,12 @@ int cnnb200_fit(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_t similarity_cu
 int cnnb200_components_begin(cnnb200_ctx *ctx, int64_t n_member_cutoff,
                              int64_t similarity_cutoff, const uint8_t *consider, int loc);
 int cnnb200_components_edges(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end);
+/* The two halves of components_edges on their own: phase 1 = the sampling rounds (every row tries its first entry
+ * above it, every k-th row of a tree two far entries), phase 2 = the scan of all candidate edges of the rows + the
+ * work list.  A row-sharded run on lists WITHOUT index locality (precomputed neighbourhoods in the caller's order:
+ * most candidate edges cross the row blocks) all-gathers and merges the forests between the two
+ * (cnnb200_components_merge), so that each rank's scan skips what any rank's samples already joined. */
+int cnnb200_components_phase(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end, int phase);
 /* Parameter sweeps (the reference's scan loop calls Clustering.fit once per (radius_cutoff, cnn_cutoff)
  * cell, docsrc/benchmark/scans.ipynb; HierarchicalFitterRepeat._fit does the same per step,
  * _fit.pyx:1058-1187).  For one radius the counts of cnnb200_cn_count answer EVERY cnn_cutoff:

@@ -408,14 +408,12 @@ def run_b200(args):
         if runner is None:
             def step_device():
                 ctx.neighbours_from_csr(rp_d, ci_d, borrow=True)
-                ctx.fit(nmc, sim, 1, labd.zero_(), None)
-                ctx.sort_by_size(labd, w["member_cutoff"])
+                ctx.fit_sorted(nmc, sim, labd, member_cutoff=w["member_cutoff"])
 
             def step_host():
                 ctx.neighbours_from_csr(rp_np, ci_np)
-                ctx.fit(nmc, sim, 1, lh_np, None)
-                ctx.sort_by_size(lh_np, w["member_cutoff"])
-            e2e_call = "cnnb200_neighbours_from_csr + cnnb200_fit + cnnb200_sort_by_size (C-ABI, page-locked host CSR)"
+                ctx.fit_sorted(nmc, sim, lh_np, member_cutoff=w["member_cutoff"])
+            e2e_call = "cnnb200_neighbours_from_csr + cnnb200_fit_sorted (C-ABI, page-locked host CSR)"
         else:
             del rp_d, ci_d
             torch.cuda.empty_cache()

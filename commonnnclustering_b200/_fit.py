@@ -83,20 +83,26 @@ class FitterB200(Fitter):
 
 
 class FitterB200Fused(FitterB200):
-    """Same result as ``FitterB200`` followed by ``Labels.sort_by_size`` but as ONE C-ABI call
-    (``cnnb200_fit_points``) that keeps the labels on the device between the two steps.  Used by
-    ``Clustering.fit`` for fresh fits on coordinates."""
+    """Same result as ``FitterB200`` followed by ``Labels.sort_by_size`` but as ONE C-ABI call that keeps the labels on
+    the device between the two steps (``cnnb200_fit_points`` on coordinates, ``cnnb200_fit_sorted`` on neighbourhoods
+    that were ingested first).  Used by ``Clustering.fit`` for fresh fits with size sorting."""
 
-    def fit_sorted(self, input_data: InputDataComponents, labels: Labels, cluster_params: ClusterParameters,
-                   member_cutoff=None, max_clusters=None) -> int:
+    def fit_sorted(self, input_data, labels: Labels, cluster_params: ClusterParameters, member_cutoff=None,
+                   max_clusters=None) -> int:
         ctx = self.ctx
         g = self._neighbours_getter
-        g.prepare(ctx)
-        n_clusters = ctx.fit_points(
-            input_data.device_or_host_array, cluster_params.radius_cutoff, cluster_params.n_member_cutoff,
-            cluster_params.similarity_cutoff, labels.labels, cluster_params.current_start,
-            metric=g.metric.name, method=g.method, sort_by_size=True,
-            member_cutoff=member_cutoff, max_clusters=max_clusters)
+        if isinstance(input_data, InputDataComponents) and isinstance(g, NeighboursGetterRadius) \
+                and g.metric.name in _lib.METRIC_IDS:
+            g.prepare(ctx)
+            n_clusters = ctx.fit_points(
+                input_data.device_or_host_array, cluster_params.radius_cutoff, cluster_params.n_member_cutoff,
+                cluster_params.similarity_cutoff, labels.labels, cluster_params.current_start,
+                metric=g.metric.name, method=g.method, sort_by_size=True,
+                member_cutoff=member_cutoff, max_clusters=max_clusters)
+        else:
+            self.last_neighbourhoods = g.get_all(input_data, cluster_params, ctx)
+            n_clusters = ctx.fit_sorted(cluster_params.n_member_cutoff, cluster_params.similarity_cutoff, labels.labels,
+                                        cluster_params.current_start, member_cutoff, max_clusters)
         labels.consider[:] = 0
         labels.meta["b200"] = dict(ctx.stats(), n_points=int(labels.labels.shape[0]))
         return n_clusters

@@ -64,6 +64,7 @@ SIGNATURES = {
     "cnnb200_sort_by_size": [_P, _P, C.c_int, _I64, _I64, _I64, _P, _I64],
     "cnnb200_fit_points": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int, C.c_int, _I64, _I64, _I64,
                            C.c_int, _I64, _I64, _P, C.POINTER(_I64)],
+    "cnnb200_fit_sorted": [_P, _I64, _I64, _I64, _I64, _I64, _P, C.c_int, C.POINTER(_I64)],
     "cnnb200_label_summary": [_P, _P],
     "cnnb200_labels_group": [_P, _P, _P, C.c_int, _I64, _P, _P],
     "cnnb200_host_register": [_P, C.c_size_t],
@@ -454,6 +455,15 @@ class Context:
         check(self._lib.cnnb200_labels_group(self._h, prev.ctypes.data, cur.ctypes.data, HOST, n, order.ctypes.data,
                                              rank.ctypes.data))
         return order, rank
+
+    def fit_sorted(self, n_member_cutoff, similarity_cutoff, labels, current_start=1, member_cutoff=None, max_clusters=None):
+        """Fresh fit on the held neighbourhoods + sort_by_size in one call; returns the number of clusters found."""
+        lp, loc = _ptr_loc(labels)
+        nc = _I64()
+        check(self._lib.cnnb200_fit_sorted(self._h, int(n_member_cutoff), int(similarity_cutoff), int(current_start),
+                                           -1 if member_cutoff is None else int(member_cutoff),
+                                           -1 if max_clusters is None else int(max_clusters), lp, loc, C.byref(nc)))
+        return nc.value
 
     def label_summary(self):
         """(clusters kept, members of the largest one, noise points) of the last size-sorted result."""

@@ -247,8 +247,7 @@ class Clustering:
         n = bundle._input_data.n_points
         # a fresh fit on coordinates with size sorting can keep the labels on the device
         # between FitterExtBFS.fit and Labels.sort_by_size: one C-ABI call, one D2H copy
-        may_fuse = (sort_by_size and isinstance(self._fitter, FitterB200Fused)
-                    and isinstance(bundle._input_data, InputDataComponents))
+        may_fuse = sort_by_size and isinstance(self._fitter, FitterB200Fused)
         if (bundle._labels is None) or purge or (not bundle._labels.meta.get("frozen", False)):
             bundle._labels = Labels(_label_buffer(n, pinned=may_fuse))
             old_label_set = set()
@@ -261,7 +260,7 @@ class Clustering:
         cluster_params = self._fitter.make_parameters(radius_cutoff, cnn_cutoff, current_start)
 
         fused = fresh and may_fuse
-        if fused:
+        if fused and hasattr(bundle._input_data, "pin"):
             bundle._input_data.pin()
         t0 = time.perf_counter()
         if fused:

@@ -330,12 +330,24 @@ extern "C" int cnnb200_fit_points(cnnb200_ctx *ctx, const double *x, int loc, in
                                   int64_t *n_clusters_out) {
     if (!labels) CNN_FAIL(CNNB200_E_INVALID, "fit_points: labels is NULL");
     CNN_TRY(cnnb200_neighbours_from_points(ctx, x, loc, n, d, radius_cutoff, metric, method, nullptr));
-    static const bool fused_labels = !getenv("CNNB200_FUSED_LABELS") || atoi(getenv("CNNB200_FUSED_LABELS")) != 0;
     if (!sort_by_size)
         return cnnb200_fit(ctx, n_member_cutoff, similarity_cutoff, current_start, labels, nullptr, loc,
                            n_clusters_out);
-    // a fresh fit followed by sort_by_size: the labels stay on the device, numbering and size sort collapse into one
-    // ranking of the components (cnn_labels_fused), one D2H copy and ONE synchronisation at the end
+    return cnnb200_fit_sorted(ctx, n_member_cutoff, similarity_cutoff, current_start, member_cutoff, max_clusters, labels, loc,
+                              n_clusters_out);
+}
+
+// A fresh fit on the neighbourhoods the context holds (whatever built them) followed by sort_by_size: the labels stay
+// on the device, numbering and size sort collapse into one ranking of the components (cnn_labels_fused), one D2H copy
+// and ONE synchronisation at the end.
+extern "C" int cnnb200_fit_sorted(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_t similarity_cutoff, int64_t current_start,
+                                  int64_t member_cutoff, int64_t max_clusters, int64_t *labels, int loc,
+                                  int64_t *n_clusters_out) {
+    if (!ctx || !labels) CNN_FAIL(CNNB200_E_INVALID, "fit_sorted: NULL argument");
+    if (!ctx->have_nb) CNN_FAIL(CNNB200_E_STATE, "fit_sorted: no neighbourhoods held by this context");
+    static const bool fused_labels = !getenv("CNNB200_FUSED_LABELS") || atoi(getenv("CNNB200_FUSED_LABELS")) != 0;
+    const ll n = ctx->n;
+    CNN_CUDA(cudaSetDevice(ctx->device));
     CNN_TRY(cnn_ensure(ctx, ctx->b_labels, sizeof(ll) * (size_t)n));
     int64_t *d_labels = loc == CNNB200_HOST ? (int64_t *)ctx->b_labels.p : labels;
     CNN_TRY(cnnb200_components_begin(ctx, n_member_cutoff, similarity_cutoff, nullptr, CNNB200_DEVICE));

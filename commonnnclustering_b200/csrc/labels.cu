@@ -357,7 +357,7 @@ extern "C" int cnnb200_label_summary(cnnb200_ctx *ctx, int64_t *out3) {
 //   fused_rank_kernel     one CTA: bitonic sort of up to FUSED_MAX_KEYS keys in shared memory, rank -> root_label[],
 //                         summary (clusters kept, largest, members kept); more keys: flag, the caller falls back
 //   fused_write_kernel    labels[perm[p]] = root_label[parent[p]]
-#define FUSED_MAX_KEYS 4096
+#define FUSED_MAX_KEYS 16384   // 12 bytes of (dynamic) shared memory per key: 192 KB
 
 __global__ void fused_sizes_kernel(const int *__restrict__ parent, const int *__restrict__ perm, ll n, int *size, int *minorig) {
     ll p = blockIdx.x * (ll)blockDim.x + threadIdx.x;
@@ -403,8 +403,9 @@ __global__ void fused_roots_kernel(const int *__restrict__ parent, const int *__
 __global__ void __launch_bounds__(1024)
 fused_rank_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ vals, ll n, int kb, ll max_clusters,
                   int *root_label, unsigned long long *counters) {
-    __shared__ unsigned long long s_key[FUSED_MAX_KEYS];
-    __shared__ int s_val[FUSED_MAX_KEYS];
+    extern __shared__ unsigned long long s_fused[];
+    unsigned long long *s_key = s_fused;
+    int *s_val = (int *)(s_fused + FUSED_MAX_KEYS);
     const ll m = (ll)counters[1];
     if (m > FUSED_MAX_KEYS) {
         if (threadIdx.x == 0) counters[2] = 1;
@@ -481,8 +482,11 @@ int cnn_labels_fused(cnnb200_ctx *ctx, ll member_cutoff, ll max_clusters, ll *d_
     fused_sizes_kernel<<<nb, 256, 0, st>>>(parent, ctx->perm, n, size, minorig);
     fused_roots_kernel<<<nb, 256, 0, st>>>(parent, size, minorig, n, kb, member_cutoff, ctx->b_lab_keys.as<unsigned long long>(),
                                            ctx->b_lab_vals.as<int>(), root_label, counters);
-    fused_rank_kernel<<<1, 1024, 0, st>>>(ctx->b_lab_keys.as<unsigned long long>(), ctx->b_lab_vals.as<int>(), n, kb, max_clusters,
-                                          root_label, counters);
+    static const bool smem_ok = cudaFuncSetAttribute(fused_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     FUSED_MAX_KEYS * 12) == cudaSuccess;
+    if (!smem_ok) CNN_FAIL(CNNB200_E_CUDA, "fused ranking: cannot opt in to %d bytes of shared memory", FUSED_MAX_KEYS * 12);
+    fused_rank_kernel<<<1, 1024, FUSED_MAX_KEYS * 12, st>>>(ctx->b_lab_keys.as<unsigned long long>(), ctx->b_lab_vals.as<int>(), n, kb,
+                                                           max_clusters, root_label, counters);
     fused_write_kernel<<<nb, 256, 0, st>>>(parent, ctx->perm, root_label, n, d_labels);
     CNN_LAUNCHED(ctx, 4);
     CNN_KERNEL_CHECK();

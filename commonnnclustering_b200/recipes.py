@@ -120,7 +120,7 @@ REGISTERED_RECIPES = {
     "distances": {   # reference recipes.py:329-339: the input is an N x N distance matrix
         "input_data": "components_b200",
         "preparation_hook": "points_from_parts",
-        "fitter": "b200_staged",
+        "fitter": "b200",
         "fitter.ngetter": "radius_b200",
         "fitter.checker": "commonnn_b200",
         "fitter.ngetter.dgetter": "metric",
@@ -129,7 +129,7 @@ REGISTERED_RECIPES = {
     "neighbourhoods": {   # reference recipes.py:340-348: neighbour lists in any order
         "input_data": "neighbourhoods_b200",
         "preparation_hook": "neighbourhoods",
-        "fitter": "b200_staged",
+        "fitter": "b200",
         "fitter.ngetter": ("lookup", (), {"is_sorted": False}),
         "fitter.checker": "commonnn_b200",
         "predictor": "b200",
@@ -139,7 +139,7 @@ REGISTERED_RECIPES = {
     "sorted_neighbourhoods": {
         "input_data": "neighbourhoods_b200",
         "preparation_hook": "neighbourhoods",
-        "fitter": "b200_staged",
+        "fitter": "b200",
         "fitter.ngetter": ("lookup", (), {"is_sorted": True}),
         "fitter.checker": "commonnn_b200",
         "predictor": "b200",
@@ -149,7 +149,7 @@ REGISTERED_RECIPES = {
     "neighbourhoods_csr": {
         "input_data": "neighbourhoods_csr",
         "preparation_hook": "pass",
-        "fitter": "b200_staged",
+        "fitter": "b200",
         "fitter.ngetter": ("lookup", (), {"is_sorted": True}),
         "fitter.checker": "commonnn_b200",
     },

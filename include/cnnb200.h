@@ -302,6 +302,11 @@ int cnnb200_fit_points(cnnb200_ctx *ctx, const double *x, int loc, int64_t n, in
                        int64_t similarity_cutoff, int64_t current_start, int sort_by_size,
                        int64_t member_cutoff, int64_t max_clusters, int64_t *labels,
                        int64_t *n_clusters_out);
+/* The same for the neighbourhoods the context already holds (cnnb200_neighbours_from_csr / _from_padded /
+ * _from_distances / _from_points): FitterExtBFS.fit on fresh labels + Labels.sort_by_size as one call. */
+int cnnb200_fit_sorted(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_t similarity_cutoff, int64_t current_start,
+                       int64_t member_cutoff, int64_t max_clusters, int64_t *labels, int loc,
+                       int64_t *n_clusters_out);
 
 /* (clusters kept, members of the largest cluster, noise points) after the last cnnb200_sort_by_size /
  * cnnb200_fit_points with size sorting: what Clustering.fit stores in its Record (cluster.pyx:366-390), HOST int64 [3]. */

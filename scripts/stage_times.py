@@ -40,8 +40,7 @@ def child(name):
         class _Fit:
             def fit_points(self, *_a, **_k):
                 ctx.neighbours_from_csr(rp_d, ci_d, borrow=True)
-                ctx.fit(c + 1, c + 2, 1, lab.zero_(), None)
-                ctx.sort_by_size(lab, p["member_cutoff"])
+                ctx.fit_sorted(c + 1, c + 2, lab, member_cutoff=p["member_cutoff"])
         fitter = _Fit()
     else:
         fitter = ctx

@@ -780,15 +780,20 @@ def test_periodic_metric_equals_oracle_and_reference(ctx):
 def test_fused_numbering_and_size_sort(ctx):
     """cnnb200_fit_points ranks the components in one CTA when few survive member_cutoff and falls back to the
     general chain (numbering + sort_by_size over all labels) otherwise; both equal the oracle."""
-    # 10 000 clusters of two points each: more survivors than one CTA ranks -> fallback
-    base = np.arange(10_000, dtype=np.float64)[:, None] * 10.0
+    # 20 000 clusters of two points each: more survivors than one CTA ranks -> fallback
+    base = np.arange(20_000, dtype=np.float64)[:, None] * 10.0
     x = np.concatenate([base, base + 0.1]).reshape(-1, 1)
     rng = np.random.default_rng(5)
     x = np.ascontiguousarray(x[rng.permutation(x.shape[0])])
     want = port.fit_points(x, 0.5, 0, member_cutoff=None)
     got = np.zeros(x.shape[0], dtype=np.int64)
     nc = ctx.fit_points(x, 0.25, 1, 2, got)
-    assert nc == 10_000 and np.array_equal(got, want) and got.max() == 10_000
+    assert nc == 20_000 and np.array_equal(got, want) and got.max() == 20_000
+    # 6 000 such clusters: ranked by the one CTA (ties in size broken by first occurrence)
+    x6 = np.ascontiguousarray(x[np.isin((x[:, 0] // 10).astype(np.int64), np.arange(6000))])
+    want = port.fit_points(x6, 0.5, 0, member_cutoff=None)
+    got = np.zeros(x6.shape[0], dtype=np.int64)
+    assert ctx.fit_points(x6, 0.25, 1, 2, got) == 6000 and np.array_equal(got, want)
     # ties in size are broken by first occurrence; max_clusters and member_cutoff cut the tail
     x = datasets.md_like_3d(60_000)
     for mc, mx in [(None, None), (10, None), (5, 7), (1, 3), (50, 1)]:

@@ -243,10 +243,11 @@ struct FilterParams {
 
 struct GfGroup {
     int a, gsz, lg;            // first lane, number of lanes, log2 of the mask row width gp
-    int nruns, nch;            // candidate runs, chunks of 32 candidates over all runs
+    int nruns, total, nch;     // candidate runs, candidates over all runs, chunks of 32 of the CONCATENATED runs
     int cx0, cx1, cy, cz;      // candidate cells along x; the queries' cell row
     bool use_b;                // the run straddles a period boundary of lattice A: take x from lattice B
-    int rs, re;                // per lane (lane < nruns): bounds of run `lane`
+    int incl, off;             // per lane (lane < nruns): candidates up to and including run `lane`; index of the
+                               // run's first candidate minus its position in the concatenation (index = off + position)
     int ry, rz;                // per lane: cell row of run `lane`
 };
 
@@ -274,17 +275,38 @@ __device__ __forceinline__ void gf_next_group(unsigned &todo, int cid, int my_ro
     G.use_b = (G.cx0 >> 4) != (G.cx1 >> 4);
     const int ny = y1 - y0 + 1;
     G.nruns = ny * (z1 - z0 + 1);
-    G.rs = G.re = 0;
+    int rs = 0, len = 0;
     G.ry = G.cy;
     G.rz = G.cz;
     if (lane < G.nruns) {
         G.ry = y0 + lane % ny;
         G.rz = z0 + lane / ny;
         const int cb = (G.rz * g.dims[1] + G.ry) * g.dims[0];
-        G.rs = cell_start[cb + G.cx0];
-        G.re = cell_start[cb + G.cx1 + 1];
+        rs = cell_start[cb + G.cx0];
+        len = cell_start[cb + G.cx1 + 1] - rs;
     }
-    G.nch = __reduce_add_sync(full, (unsigned)((G.re - G.rs + 31) >> 5));
+    // the runs are walked as ONE sequence, 32 candidates per chunk whatever run they come from: a sparse group's nine
+    // short runs make one chunk instead of nine
+    G.incl = len;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int v = __shfl_up_sync(full, G.incl, o);
+        if (lane >= o) G.incl += v;
+    }
+    G.off = rs - (G.incl - len);
+    G.total = __shfl_sync(full, G.incl, G.nruns - 1);
+    G.nch = (G.total + 31) >> 5;
+}
+
+// Position v of the concatenated candidate list -> the run it lies in.  `run` only moves forward from chunk to chunk;
+// all lanes take part (the shuffles inside are warp-wide), lanes with valid == false do not move.
+__device__ __forceinline__ void gf_locate(const GfGroup &G, int v, bool valid, int &run) {
+    for (;;) {
+        const int nxt = __shfl_sync(0xffffffffu, G.incl, run);
+        const bool adv = valid && v >= nxt && run < G.nruns - 1;
+        if (!__any_sync(0xffffffffu, adv)) break;
+        run += adv ? 1 : 0;
+    }
 }
 
 __device__ __forceinline__ void gf_tile_header(const int *__restrict__ cell_sorted, const GridDesc &g, ll p, bool pvalid,
@@ -325,10 +347,12 @@ grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, l
                  const ll *__restrict__ tile_off, unsigned *__restrict__ masks, ll p_begin, ll p_end, ll n_tiles,
                  unsigned long long *stats, int qpw, ll cap_words) {
     __shared__ float4 s_q[GF_WARPS][32];
+    __shared__ int s_i[GF_WARPS][32];
     if (tile_off[n_tiles] > cap_words) return;  // launched before the host knew the size: it re-launches after growing
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float4 *qf = s_q[wid];
+    int *qi = s_i[wid];  // candidate indices of the staged chunk (the exact recheck needs them)
     const ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     unsigned n_recheck = 0;
@@ -365,50 +389,58 @@ grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, l
                                         __dmul_rn((double)qz, (double)qz));
             const float T = mine ? (float)__dsub_rn(fp.R, qn) : -1e30f;
             int cnt = 0;
-            for (int r = 0; r < G.nruns; ++r) {
-                const int s = __shfl_sync(full, G.rs, r), e = __shfl_sync(full, G.re, r);
-                const float sy = __shfl_sync(full, shy, r), sz = __shfl_sync(full, shz, r);
-                const float4 *cp = xf + s + lane;
-                float4 c4 = s + lane < e ? *cp : make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int q0 = s; q0 < e; q0 += 32) {
-                    __syncwarp();
-                    {
-                        const float cx = (G.use_b ? c4.y : c4.x) + shx, cy = D > 1 ? c4.z + sy : 0.f, cz = D > 2 ? c4.w + sz : 0.f;
-                        qf[lane] = make_float4(cx, cy, cz, fmaf(cz, cz, fmaf(cy, cy, cx * cx)));
-                    }
-                    __syncwarp();
-                    cp += 32;
-                    if (q0 + 32 + lane < e) c4 = *cp;  // next chunk's candidates, in flight during this one
-                    const int nc = min(32, e - q0);
-                    unsigned m = 0;
-                    float near = INFINITY;  // smallest |t| this lane meets in the chunk
+            // candidates of chunk 0 (position v = lane of the concatenated runs), fetched one chunk ahead from then on
+            int run = 0;
+            gf_locate(G, lane, lane < G.total, run);
+            int idx = __shfl_sync(full, G.off, run) + lane;
+            float sy = __shfl_sync(full, shy, run), sz = __shfl_sync(full, shz, run);
+            float4 c4 = lane < G.total ? xf[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int v0 = 0; v0 < G.total; v0 += 32) {
+                __syncwarp();
+                {
+                    const float cx = (G.use_b ? c4.y : c4.x) + shx, cy = D > 1 ? c4.z + sy : 0.f, cz = D > 2 ? c4.w + sz : 0.f;
+                    qf[lane] = make_float4(cx, cy, cz, fmaf(cz, cz, fmaf(cy, cy, cx * cx)));
+                    qi[lane] = idx;
+                }
+                __syncwarp();
+                {   // next chunk's candidates, in flight during this one
+                    const int vn = v0 + 32 + lane;
+                    const bool valid = vn < G.total;
+                    gf_locate(G, vn, valid, run);
+                    idx = __shfl_sync(full, G.off, run) + vn;
+                    sy = __shfl_sync(full, shy, run);
+                    sz = __shfl_sync(full, shz, run);
+                    if (valid) c4 = xf[idx];
+                }
+                const int nc = min(32, G.total - v0);
+                unsigned m = 0;
+                float near = INFINITY;  // smallest |t| this lane meets in the chunk
 #pragma unroll 8
+                for (int tq = 0; tq < nc; ++tq) {
+                    const float4 cv = qf[tq];
+                    const float w = fmaf(q2z, cv.z, fmaf(q2y, cv.y, fmaf(q2x, cv.x, cv.w)));
+                    const float tt = w - T;
+                    near = fminf(near, fabsf(tt));
+                    m = __funnelshift_l(__float_as_uint(tt), m, 1);  // sign bit of t: candidate tq ends up at bit nc-1-tq
+                }
+                m = __brev(m) >> (32 - nc);
+                if (near <= fp.band) {
+                    // rare: a pair of this lane is borderline -- decide it with the reference's own f64 test
                     for (int tq = 0; tq < nc; ++tq) {
                         const float4 cv = qf[tq];
                         const float w = fmaf(q2z, cv.z, fmaf(q2y, cv.y, fmaf(q2x, cv.x, cv.w)));
                         const float tt = w - T;
-                        near = fminf(near, fabsf(tt));
-                        m = __funnelshift_l(__float_as_uint(tt), m, 1);  // sign bit of t: candidate tq ends up at bit nc-1-tq
-                    }
-                    m = __brev(m) >> (32 - nc);
-                    if (near <= fp.band) {
-                        // rare: a pair of this lane is borderline -- decide it with the reference's own f64 test
-                        for (int tq = 0; tq < nc; ++tq) {
-                            const float4 cv = qf[tq];
-                            const float w = fmaf(q2z, cv.z, fmaf(q2y, cv.y, fmaf(q2x, cv.x, cv.w)));
-                            const float tt = w - T;
-                            if (fabsf(tt) <= fp.band) {
-                                const bool hit = within<D, SQRT>(xs[p], D > 1 ? xs[n + p] : 0.0, D > 2 ? xs[2 * n + p] : 0.0, xs, n,
-                                                                 q0 + tq, rc);
-                                m = (m & ~(1u << tq)) | ((hit ? 1u : 0u) << tq);
-                                ++n_recheck;
-                            }
+                        if (fabsf(tt) <= fp.band) {
+                            const bool hit = within<D, SQRT>(xs[p], D > 1 ? xs[n + p] : 0.0, D > 2 ? xs[2 * n + p] : 0.0, xs, n,
+                                                             qi[tq], rc);
+                            m = (m & ~(1u << tq)) | ((hit ? 1u : 0u) << tq);
+                            ++n_recheck;
                         }
                     }
-                    if (mine) mw[jme] = m;
-                    mw += gp;
-                    cnt += __popc(m);
                 }
+                if (mine) mw[jme] = m;
+                mw += gp;
+                cnt += __popc(m);
             }
             if (mine) deg[p] = cnt;
         }
@@ -431,9 +463,11 @@ grid_expand_kernel(const int *__restrict__ cell_sorted, const int *__restrict__ 
                    int qpw, ll n_tiles, const ll *__restrict__ tile_off, const unsigned *__restrict__ masks,
                    const ll *__restrict__ row_ptr, int *__restrict__ col_idx) {
     __shared__ int s_stage[GX_WARPS][32 * (GX_STAGE + 1)];
+    __shared__ int s_cand[GX_WARPS][32];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int *stage = s_stage[wid];
+    int *cand = s_cand[wid];
     int *mine_stage = stage + lane * (GX_STAGE + 1);
     const ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
@@ -473,21 +507,25 @@ grid_expand_kernel(const int *__restrict__ cell_sorted, const int *__restrict__ 
             const int gp = 1 << G.lg;
             int left = G.nch;  // chunks of the group still to come; the next chunk's word is fetched one step ahead
             unsigned m_next = (mine && left > 0) ? mw[jme] : 0u;
-            for (int r = 0; r < G.nruns; ++r) {
-                const int s = __shfl_sync(full, G.rs, r), e = __shfl_sync(full, G.re, r);
-                for (int q0 = s; q0 < e; q0 += 32) {
-                    unsigned m = m_next;
-                    mw += gp;
-                    --left;
-                    m_next = (mine && left > 0) ? mw[jme] : 0u;
-                    while (m) {
-                        const int b = __ffs(m) - 1;
-                        m &= m - 1;
-                        mine_stage[cnt++] = q0 + b;
-                    }
-                    const unsigned rdy = __ballot_sync(full, cnt >= 32);
-                    if (rdy) flush(rdy);
+            int run = 0;
+            for (int v0 = 0; v0 < G.total; v0 += 32) {
+                // candidate index of every position of the chunk (lane = position), through shared memory
+                const int v = v0 + lane;
+                gf_locate(G, v, v < G.total, run);
+                __syncwarp();
+                cand[lane] = __shfl_sync(full, G.off, run) + v;
+                __syncwarp();
+                unsigned m = m_next;
+                mw += gp;
+                --left;
+                m_next = (mine && left > 0) ? mw[jme] : 0u;
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    mine_stage[cnt++] = cand[b];
                 }
+                const unsigned rdy = __ballot_sync(full, cnt >= 32);
+                if (rdy) flush(rdy);
             }
         }
         // the remainders (fewer than 32 entries per row)

@@ -234,7 +234,7 @@ __global__ void comp_union_kernel(const int *__restrict__ edge_out, ll row_begin
 __global__ void __launch_bounds__(256)
 comp_far_emit_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, ll row_begin, ll row_end, int stride,
                      const int *__restrict__ parent, const int *__restrict__ above, int2 *__restrict__ worklist,
-                     unsigned long long *wl_count) {
+                     unsigned long long *wl_count, int n_far) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -248,7 +248,7 @@ comp_far_emit_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col
     int j0 = -1, j1 = -1;
     if (sel && l < m) {
         j0 = col_idx[rb + m - 1];
-        j1 = col_idx[rb + l + ((m - l) >> 2)];
+        if (n_far > 1) j1 = col_idx[rb + l + ((m - l) >> 2)];
         if (j1 == j0) j1 = -1;
     }
     const int r0 = j0 >= 0 ? parent[j0] : -1, r1 = j1 >= 0 ? parent[j1] : -1;
@@ -907,7 +907,7 @@ static int components_pass(cnnb200_ctx *ctx, int64_t row_begin, int64_t row_end,
             CNN_CUDA(cudaMemsetAsync(wl_count, 0, 2 * sizeof(unsigned long long), st));
             comp_far_emit_kernel<<<cnn_blocks(rows, 256), 256, 0, st>>>(ctx->row_ptr, ctx->col_idx, row_begin, row_end,
                                                                         ctx->far_stride, parent, above,
-                                                                        ctx->b_worklist.as<int2>(), wl_count);
+                                                                        ctx->b_worklist.as<int2>(), wl_count, ctx->n_far);
             launch_worklist(ctx->wl_chunk);
         }
         Span sp(ctx, T_COMP_FLATTEN);

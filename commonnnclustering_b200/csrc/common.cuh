@@ -93,6 +93,7 @@ struct cnnb200_ctx {
     bool fuse_union = true;  // sampling pass links its accepted edges itself (CNNB200_FUSED_UNION=0: separate kernel)
     int n_samples = 1;  // edges per core row tried by the first sampling round (tunable: CNNB200_SAMPLES)
     int far_stride = 8; // second round: every far_stride-th row of a tree tries two far neighbours (0: off; CNNB200_FAR_STRIDE)
+    int n_far = 2;      // far entries such a row tries: the last one and the one a quarter into the upper part (CNNB200_FAR_SAMPLES)
     int wl_chunk = 16;  // work-list batches of 32 edges a warp takes at a time (CNNB200_WL_CHUNK)
 
     // ---- neighbourhood structure (internal index space) -------------------------------

@@ -111,19 +111,33 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---------------------------------------------------------------------------------------------------
 // operand preparation
 // ---------------------------------------------------------------------------------------------------
-__global__ void col_mean_kernel(const double *__restrict__ x, ll n, int d, double *mean) {
-    // one block per dimension
-    int k = blockIdx.x;
-    double s = 0;
-    for (ll i = threadIdx.x; i < n; i += blockDim.x) s += x[i * d + k];
-    __shared__ double sh[256];
-    sh[threadIdx.x] = s;
+// column sums with whole rows read coalesced (a warp per row, lanes over the dimensions; a block per dimension read
+// x with a stride of one row: 16x the bytes, 0.15 ms on C3), then mean = sum / n.  The order of the atomic adds
+// is not fixed; the mean only centres the data (any centre gives the same neighbour sets: the filter's band is
+// derived from the centred norms and every borderline pair is decided in f64 on the original coordinates).
+#define CM_MAXD 128
+__global__ void __launch_bounds__(256)
+col_sum_kernel(const double *__restrict__ x, ll n, int d, double *sum) {
+    __shared__ double sh[8][CM_MAXD];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double acc[CM_MAXD / 32] = {0.0, 0.0, 0.0, 0.0};
+    const ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5, nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    for (ll i = warp; i < n; i += nwarps)
+#pragma unroll
+        for (int u = 0; u < CM_MAXD / 32; ++u)
+            if (lane + 32 * u < d) acc[u] += x[i * d + lane + 32 * u];
+#pragma unroll
+    for (int u = 0; u < CM_MAXD / 32; ++u) sh[w][lane + 32 * u] = acc[u];
     __syncthreads();
-    for (int o = 128; o; o >>= 1) {
-        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-        __syncthreads();
+    if ((int)threadIdx.x < d) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
+        atomicAdd(sum + threadIdx.x, t);
     }
-    if (threadIdx.x == 0) mean[k] = sh[0] / (double)n;
+}
+
+__global__ void col_mean_kernel(double *mean, int d, ll n) {
+    if ((int)threadIdx.x < d) mean[threadIdx.x] /= (double)n;
 }
 
 // A'[i] = [hi | hi | lo | 0..], B'[i] = [hi | lo | hi | 0..] (bf16, row length kt), norm[i] = |x_i - mean|^2;
@@ -728,7 +742,9 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
         Span sp(ctx, T_GRID_BUILD);
         CNN_CUDA(cudaMemsetAsync(maxbits, 0, sizeof(int), st));
         CNN_CUDA(cudaMemsetAsync(ctx->b_stats.p, 0, sizeof(unsigned long long) * ST_N, st));
-        col_mean_kernel<<<(int)d, 256, 0, st>>>(d_x, n, (int)d, mean);
+        CNN_CUDA(cudaMemsetAsync(mean, 0, sizeof(double) * (size_t)d, st));
+        col_sum_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(d_x, n, (int)d, mean);
+        col_mean_kernel<<<1, CM_MAXD, 0, st>>>(mean, (int)d, n);
         split_kernel<<<cnn_blocks(n_pad, 8) < ctx->sm_count * 32 ? cnn_blocks(n_pad, 8) : ctx->sm_count * 32, 256, 0, st>>>(d_x, mean, n, n_pad, (int)d, kt, A, B, norm, maxbits);
         CNN_LAUNCHED(ctx, 2);
         CNN_KERNEL_CHECK();

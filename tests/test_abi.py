@@ -51,6 +51,27 @@ def test_sass_is_sm100a():
     assert "sm_100a" in out
 
 
+def test_sass_shows_the_tcgen05_tma_path():
+    """The tiled distance kernel really is tcgen05 / TMEM / TMA code (and the committed summary matches the library):
+    UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = cp.async.bulk.tensor."""
+    import importlib.util
+
+    from commonnnclustering_b200 import build
+
+    build.build()
+    spec = importlib.util.spec_from_file_location("sass_summary", os.path.join(ROOT, "scripts", "sass_summary.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    total, per_kernel, arch = mod.counts()
+    assert arch == ["sm_100a"]
+    assert total["UTCHMMA"] >= 8 and total["LDTM"] >= 4 and total["UTMALDG"] >= 8 and total["SYNCS"] >= 8
+    tensor = [v for k, v in per_kernel.items() if "tensor_pairs_kernel" in k]
+    assert tensor and tensor[0].get("UTCHMMA", 0) >= 8 and tensor[0].get("LDTM", 0) >= 4 and tensor[0].get("UTMALDG", 0) >= 8
+    committed = open(os.path.join(ROOT, "profiles", "sass_summary.txt")).read()
+    for m in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert re.search(rf"^{m}\s+{total[m]}\b", committed, flags=re.M), m
+
+
 def test_product_never_imports_the_oracle():
     # the package, the public header and the measurement scripts: only tests/ (incl. tests/checks/), smoke() and
     # bench.py's cpu_baseline / reference legs may touch oracle/

@@ -350,8 +350,13 @@ struct TileIter {
 // ---------------------------------------------------------------------------------------------------
 #define NSB 3   // barrier slots reserved for the shared-memory stages of the B operand (2 are used; 1 for 4-atom tiles)
 #define NST 4   // TMEM accumulator stages of 128 columns (MMA <-> epilogue): the whole 512-column TMEM
-#define PAIR_BUF 16     // pairs a thread collects before it reserves space in the global list
-#define EPI_WARPS 8     // epilogue warps: two per TMEM lane quarter, 64 columns of a tile each
+#ifndef CNN_EPI_WARPS
+#define CNN_EPI_WARPS 8   // measured r2 on C3: 16 warps 3.64 ms, 8 warps 3.48 ms
+#endif
+#define EPI_WARPS CNN_EPI_WARPS  // epilogue warps: 8 = one per (row tile, TMEM lane quarter), all 128 columns each;
+                                 // 16 = two per (row tile, lane quarter), 64 columns each (more warps to hide the
+                                 // tcgen05.ld / shared-memory latency of an epilogue that, not the MMA, bounds the kernel)
+#define PAIR_BUF (128 / EPI_WARPS)  // pairs a thread collects before it reserves space in the global list
 #define NUM_THREADS ((2 + EPI_WARPS) * 32)
 #define BAND_FLAG 0x80000000u
 
@@ -401,7 +406,7 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (warp == 0 && lane == 0) {
         mbar_init(a_full, 1);
         for (int s = 0; s < nsb; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < NST; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 128); }
+        for (int s = 0; s < NST; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 16 * EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -466,7 +471,8 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         // ===== epilogue: TMEM -> registers -> classify -> emit pairs =====
         const int ew = warp - 2;             // 0 .. EPI_WARPS-1
         const int q = warp & 3;              // TMEM lane quarter this warp may access
-        const int rt = ew >> 2;              // which of the CTA's two row tiles
+        const int rt = (ew >> 2) & 1;        // which of the CTA's two row tiles
+        const int ch = ew >> 3;              // 16 epilogue warps: which 64 columns of the tile (0 with 8 warps)
         const int row = q * 32 + lane;       // accumulator row = TMEM lane
         float *ncw = ncs + ew * 2 * TT;
         int *mybuf = pbuf + (ew * 32 + lane) * PAIR_BUF;
@@ -498,12 +504,12 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * TT);
 #pragma unroll
-            for (int hp = 0; hp < 2; ++hp) {  // 64 columns at a time: two tcgen05.ld in flight
+            for (int hp = EPI_WARPS == 16 ? ch : 0; hp < (EPI_WARPS == 16 ? ch + 1 : 2); ++hp) {  // 64 columns at a time: two tcgen05.ld in flight
                 float va[32], vb[32];
                 tmem_ld32(taddr + hp * 64, va);
                 tmem_ld32(taddr + hp * 64 + 32, vb);
                 tmem_ld_wait();
-                if (hp == 1) {  // the whole accumulator stage is in registers: hand it back to the MMA warp
+                if (EPI_WARPS == 16 || hp == 1) {  // this warp's part of the accumulator stage is in registers: hand it back
                     tc_fence_before();
                     mbar_arrive(t_empty + ts);
                 }

@@ -55,6 +55,7 @@ SIGNATURES = {
     "cnnb200_components_parents": [_P, C.POINTER(_P)],
     "cnnb200_components_merge": [_P, _P, _I64],
     "cnnb200_components_labels": [_P, _I64, _P, C.c_int, C.c_int, C.POINTER(_I64)],
+    "cnnb200_components_labels_sorted": [_P, _I64, _I64, _I64, _P, C.c_int, C.POINTER(_I64)],
     "cnnb200_fit_sharded_begin": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int, _I64, _I64, C.c_int, C.c_int, _P,
                                   C.POINTER(_P)],
     "cnnb200_fit_sharded_end": [_P, _P, _I64, C.c_int, _I64, _I64, _I64, _P, C.c_int, C.POINTER(_I64)],
@@ -388,6 +389,16 @@ class Context:
         lp, loc = _ptr_loc(labels)
         nc = _I64()
         check(self._lib.cnnb200_components_labels(self._h, int(current_start), lp, loc, int(bool(fresh)), C.byref(nc)))
+        return nc.value
+
+    def components_labels_sorted(self, labels, current_start=1, member_cutoff=None, max_clusters=None):
+        """Fresh labels of the finished forest, size-sorted (= components_labels + sort_by_size); returns the number
+        of clusters before the size sort."""
+        lp, loc = _ptr_loc(labels)
+        nc = _I64()
+        check(self._lib.cnnb200_components_labels_sorted(
+            self._h, int(current_start), -1 if member_cutoff is None else int(member_cutoff),
+            -1 if max_clusters is None else int(max_clusters), lp, loc, C.byref(nc)))
         return nc.value
 
     # -- prediction ---------------------------------------------------------------------------------

@@ -110,7 +110,7 @@ extern "C" int cnnb200_ctx_create(int device, cnnb200_ctx **out) {
     F(c->b_tmp1) F(c->b_tmp2) F(c->b_parent) F(c->b_core) F(c->b_above) F(c->b_edges) F(c->b_worklist) F(c->b_cell_count) F(c->b_minorig) F(c->b_flags)             \
     F(c->b_rank) F(c->b_labels) F(c->b_consider) F(c->b_stats) F(c->b_lab_count) F(c->b_lab_first)  \
     F(c->b_lab_keys) F(c->b_lab_keys2) F(c->b_lab_vals) F(c->b_lab_vals2) F(c->b_lab_map) \
-    F(c->b_tile_words) F(c->b_tile_off) F(c->b_masks) F(c->b_pg_x) F(c->b_pg_orig) F(c->b_pg_xq) F(c->b_pg_perm) F(c->b_pg_deg) F(c->b_pg_img) F(c->b_pg_row_ptr) F(c->b_pg_col)
+    F(c->b_tile_off) F(c->b_masks) F(c->b_pg_x) F(c->b_pg_orig) F(c->b_pg_xq) F(c->b_pg_perm) F(c->b_pg_deg) F(c->b_pg_img) F(c->b_pg_row_ptr) F(c->b_pg_col)
 
 extern "C" int cnnb200_ctx_release(cnnb200_ctx *ctx) {
     if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");
@@ -324,35 +324,14 @@ extern "C" int cnnb200_neighbours_from_points(cnnb200_ctx *ctx, const double *x,
     return CNNB200_OK;
 }
 
-extern "C" int cnnb200_fit_points(cnnb200_ctx *ctx, const double *x, int loc, int64_t n, int64_t d,
-                                  double radius_cutoff, int metric, int method, int64_t n_member_cutoff,
-                                  int64_t similarity_cutoff, int64_t current_start, int sort_by_size,
-                                  int64_t member_cutoff, int64_t max_clusters, int64_t *labels,
-                                  int64_t *n_clusters_out) {
-    if (!labels) CNN_FAIL(CNNB200_E_INVALID, "fit_points: labels is NULL");
-    CNN_TRY(cnnb200_neighbours_from_points(ctx, x, loc, n, d, radius_cutoff, metric, method, nullptr));
-    if (!sort_by_size)
-        return cnnb200_fit(ctx, n_member_cutoff, similarity_cutoff, current_start, labels, nullptr, loc,
-                           n_clusters_out);
-    return cnnb200_fit_sorted(ctx, n_member_cutoff, similarity_cutoff, current_start, member_cutoff, max_clusters, labels, loc,
-                              n_clusters_out);
-}
-
-// A fresh fit on the neighbourhoods the context holds (whatever built them) followed by sort_by_size: the labels stay
-// on the device, numbering and size sort collapse into one ranking of the components (cnn_labels_fused), one D2H copy
-// and ONE synchronisation at the end.
-extern "C" int cnnb200_fit_sorted(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_t similarity_cutoff, int64_t current_start,
-                                  int64_t member_cutoff, int64_t max_clusters, int64_t *labels, int loc,
-                                  int64_t *n_clusters_out) {
-    if (!ctx || !labels) CNN_FAIL(CNNB200_E_INVALID, "fit_sorted: NULL argument");
-    if (!ctx->have_nb) CNN_FAIL(CNNB200_E_STATE, "fit_sorted: no neighbourhoods held by this context");
+// Ranking of the components + labels for a forest that is complete (after cnnb200_components_edges /
+// _from_counts / _merge) when every label comes from this fit: cnn_labels_fused, one D2H copy and ONE synchronisation;
+// the general chain (numbering, then the size sort over all labels) when more clusters survive than one CTA ranks.
+// `labels` is the caller's array (host or device), `d_labels` the device array the kernels write.
+int cnn_labels_sorted(cnnb200_ctx *ctx, int64_t current_start, int64_t member_cutoff, int64_t max_clusters, int64_t *labels,
+                      int64_t *d_labels, int loc, int64_t *n_clusters_out) {
     static const bool fused_labels = !getenv("CNNB200_FUSED_LABELS") || atoi(getenv("CNNB200_FUSED_LABELS")) != 0;
     const ll n = ctx->n;
-    CNN_CUDA(cudaSetDevice(ctx->device));
-    CNN_TRY(cnn_ensure(ctx, ctx->b_labels, sizeof(ll) * (size_t)n));
-    int64_t *d_labels = loc == CNNB200_HOST ? (int64_t *)ctx->b_labels.p : labels;
-    CNN_TRY(cnnb200_components_begin(ctx, n_member_cutoff, similarity_cutoff, nullptr, CNNB200_DEVICE));
-    CNN_TRY(cnnb200_components_edges(ctx, 0, n));
     unsigned long long *counters = nullptr;
     CNN_TRY(cnn_labels_fused(ctx, member_cutoff, max_clusters, d_labels, &counters));
     unsigned long long *h;
@@ -387,4 +366,45 @@ extern "C" int cnnb200_fit_sorted(cnnb200_ctx *ctx, int64_t n_member_cutoff, int
     ctx->lab_summary_host[2] = n - (ll)h[5];
     ctx->lab_summary_cached = true;
     return CNNB200_OK;
+}
+
+extern "C" int cnnb200_components_labels_sorted(cnnb200_ctx *ctx, int64_t current_start, int64_t member_cutoff,
+                                                int64_t max_clusters, int64_t *labels, int loc, int64_t *n_clusters_out) {
+    if (!ctx || !labels) CNN_FAIL(CNNB200_E_INVALID, "components_labels_sorted: NULL argument");
+    if (!ctx->have_comp) CNN_FAIL(CNNB200_E_STATE, "components_labels_sorted: call components_begin first");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_labels, sizeof(ll) * (size_t)ctx->n));
+    int64_t *d_labels = loc == CNNB200_HOST ? (int64_t *)ctx->b_labels.p : labels;
+    return cnn_labels_sorted(ctx, current_start, member_cutoff, max_clusters, labels, d_labels, loc, n_clusters_out);
+}
+
+extern "C" int cnnb200_fit_points(cnnb200_ctx *ctx, const double *x, int loc, int64_t n, int64_t d,
+                                  double radius_cutoff, int metric, int method, int64_t n_member_cutoff,
+                                  int64_t similarity_cutoff, int64_t current_start, int sort_by_size,
+                                  int64_t member_cutoff, int64_t max_clusters, int64_t *labels,
+                                  int64_t *n_clusters_out) {
+    if (!labels) CNN_FAIL(CNNB200_E_INVALID, "fit_points: labels is NULL");
+    CNN_TRY(cnnb200_neighbours_from_points(ctx, x, loc, n, d, radius_cutoff, metric, method, nullptr));
+    if (!sort_by_size)
+        return cnnb200_fit(ctx, n_member_cutoff, similarity_cutoff, current_start, labels, nullptr, loc,
+                           n_clusters_out);
+    return cnnb200_fit_sorted(ctx, n_member_cutoff, similarity_cutoff, current_start, member_cutoff, max_clusters, labels, loc,
+                              n_clusters_out);
+}
+
+// A fresh fit on the neighbourhoods the context holds (whatever built them) followed by sort_by_size: the labels stay
+// on the device, numbering and size sort collapse into one ranking of the components (cnn_labels_fused), one D2H copy
+// and ONE synchronisation at the end.
+extern "C" int cnnb200_fit_sorted(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_t similarity_cutoff, int64_t current_start,
+                                  int64_t member_cutoff, int64_t max_clusters, int64_t *labels, int loc,
+                                  int64_t *n_clusters_out) {
+    if (!ctx || !labels) CNN_FAIL(CNNB200_E_INVALID, "fit_sorted: NULL argument");
+    if (!ctx->have_nb) CNN_FAIL(CNNB200_E_STATE, "fit_sorted: no neighbourhoods held by this context");
+    const ll n = ctx->n;
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_labels, sizeof(ll) * (size_t)n));
+    int64_t *d_labels = loc == CNNB200_HOST ? (int64_t *)ctx->b_labels.p : labels;
+    CNN_TRY(cnnb200_components_begin(ctx, n_member_cutoff, similarity_cutoff, nullptr, CNNB200_DEVICE));
+    CNN_TRY(cnnb200_components_edges(ctx, 0, n));
+    return cnn_labels_sorted(ctx, current_start, member_cutoff, max_clusters, labels, d_labels, loc, n_clusters_out);
 }

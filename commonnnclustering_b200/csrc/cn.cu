@@ -1099,35 +1099,5 @@ extern "C" int cnnb200_fit_sharded_end(cnnb200_ctx *ctx, const int32_t *others, 
     }
     CNN_TRY(cnn_ensure(ctx, ctx->b_labels, sizeof(ll) * (size_t)n));
     ll *d_labels = loc == CNNB200_HOST ? ctx->b_labels.as<ll>() : labels;
-    unsigned long long *counters = nullptr;
-    CNN_TRY(cnn_labels_fused(ctx, member_cutoff, max_clusters, d_labels, &counters));
-    unsigned long long *h;
-    CNN_TRY(cnn_pinned(ctx, 128, (void **)&h));
-    if (loc == CNNB200_HOST) {
-        Span sp(ctx, T_D2H);
-        CNN_CUDA(cudaMemcpyAsync(labels, d_labels, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    }
-    CNN_CUDA(cudaMemcpyAsync(h, counters, sizeof(ll) * 6, cudaMemcpyDeviceToHost, st));
-    CNN_CUDA(cudaMemcpyAsync(h + 8, ctx->b_stats.p, sizeof(ll) * 4, cudaMemcpyDeviceToHost, st));
-    CNN_CUDA(cudaStreamSynchronize(st));
-    for (int k = 0; k < 4; ++k) ctx->stats[k] = (ll)h[8 + k];
-    if (n_clusters_out) *n_clusters_out = (int64_t)h[0];
-    if (h[2]) {  // more surviving clusters than one CTA ranks: the general chain
-        int64_t nc2 = 0;
-        CNN_TRY(cnnb200_components_labels(ctx, current_start, d_labels, CNNB200_DEVICE, 1, &nc2));
-        ctx->known_max_label = nc2 > 0 ? current_start + nc2 - 1 : 0;
-        CNN_TRY(cnnb200_sort_by_size(ctx, d_labels, CNNB200_DEVICE, n, member_cutoff, max_clusters, nullptr, 0));
-        if (loc == CNNB200_HOST) {
-            CNN_CUDA(cudaMemcpyAsync(labels, d_labels, sizeof(ll) * (size_t)n, cudaMemcpyDeviceToHost, st));
-            CNN_CUDA(cudaStreamSynchronize(st));
-        }
-        return CNNB200_OK;
-    }
-    ctx->have_lab_summary = true;
-    ctx->lab_summary_n = n;
-    ctx->lab_summary_host[0] = (ll)h[3];
-    ctx->lab_summary_host[1] = (ll)h[4];
-    ctx->lab_summary_host[2] = n - (ll)h[5];
-    ctx->lab_summary_cached = true;
-    return CNNB200_OK;
+    return cnn_labels_sorted(ctx, current_start, member_cutoff, max_clusters, labels, d_labels, loc, n_clusters_out);
 }

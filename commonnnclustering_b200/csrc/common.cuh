@@ -116,7 +116,7 @@ struct cnnb200_ctx {
     bool mask_words_pending = false;             // the mask pass ran before the host knew how many words it needs
     ll mask_words_needed = 0;
     const ll *mask_total = nullptr;              // device: total words of the last plan
-    Buf b_tile_words, b_tile_off, b_masks;       // fp32 filter: words of hit masks per warp tile, their prefix, the masks
+    Buf b_tile_off, b_masks;       // fp32 filter: offset of every warp tile's hit masks, the masks
     Buf b_cell_count;
 
     // ---- neighbour search scratch ------------------------------------------------------
@@ -226,6 +226,8 @@ int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radi
 int cnn_grid_search_periodic(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, bool *served);
 int cnn_dense_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radius_cutoff, int metric,
                      int method);
+int cnn_labels_sorted(cnnb200_ctx *ctx, int64_t current_start, int64_t member_cutoff, int64_t max_clusters, int64_t *labels,
+                      int64_t *d_labels, int loc, int64_t *n_clusters_out);
 int cnn_labels_fused(cnnb200_ctx *ctx, ll member_cutoff, ll max_clusters, ll *d_labels, unsigned long long **counters_out);
 int cnn_sort_csr_rows(cnnb200_ctx *ctx, const ll *row_ptr, const int *col, ll n, ll nnz, Buf &out);
 int cnn_csr_rows_unsorted(cnnb200_ctx *ctx, const ll *row_ptr, const int *col, ll n, int *unsorted);

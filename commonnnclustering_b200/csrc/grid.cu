@@ -216,10 +216,10 @@ grid_rows_kernel(const double *__restrict__ xs, ll n, const int *__restrict__ ce
 // group.  Every lane of the group owns ONE query; the candidates of a run go through shared memory 32 at a time (one
 // coalesced float4 per lane) and come back as broadcasts.
 //
-// Three kernels share the group structure (gf_next_group), so nothing about it is stored:
-//   grid_plan_kernel   words of hit masks every tile will write (-> prefix = the tile's offset in the mask buffer)
+// Two kernels share the group structure (gf_next_group), so nothing about it is stored:
 //   grid_mask_kernel   the distance tests: per (query, 32-candidate chunk) ONE 32-bit hit mask, written as a coalesced
-//                      row of `gp` words per chunk (gp = group size rounded up to a power of two), plus deg[]
+//                      row of `gp` words per chunk (gp = group size rounded up to a power of two), plus deg[]; a tile
+//                      reserves its words from a running counter and leaves the offset in tile_off[]
 //   grid_expand_kernel after the degree scan: masks -> ascending column indices, whole rows at a time through a
 //                      shared-memory row buffer, so that every store instruction writes 32 consecutive words
 // The hits therefore reach HBM once (4*nnz bytes, coalesced) plus ~100 bytes of masks per point, instead of 4-byte
@@ -316,39 +316,14 @@ __device__ __forceinline__ void gf_tile_header(const int *__restrict__ cell_sort
     my_cx = pvalid ? cid - my_row * g.dims[0] : 0;
 }
 
-// words of hit masks per tile (tile t = points [p_begin + t*qpw, +qpw))
-template <int D>
-__global__ void __launch_bounds__(256)
-grid_plan_kernel(const int *__restrict__ cell_sorted, const int *__restrict__ cell_start, GridDesc g, ll p_begin, ll p_end,
-                 int qpw, ll n_tiles, int *__restrict__ tile_words) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const ll t = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
-    if (t > n_tiles) return;
-    if (t == n_tiles) { if (lane == 0) tile_words[t] = 0; return; }
-    const ll p = p_begin + t * qpw + lane;
-    const bool pvalid = lane < qpw && p < p_end;
-    int cid, my_row, my_cx;
-    gf_tile_header(cell_sorted, g, p, pvalid, cid, my_row, my_cx);
-    unsigned todo = __ballot_sync(full, pvalid);
-    int words = 0;
-    while (todo) {
-        GfGroup G;
-        gf_next_group<D>(todo, cid, my_row, my_cx, g, cell_start, lane, G);
-        words += G.nch << G.lg;
-    }
-    if (lane == 0) tile_words[t] = words;
-}
-
 template <int D, bool SQRT, int MINB>
 __global__ void __launch_bounds__(GF_WARPS * 32, MINB)
 grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, ll n, const int *__restrict__ cell_sorted,
                  const int *__restrict__ cell_start, GridDesc g, double rc, FilterParams fp, int *__restrict__ deg,
-                 const ll *__restrict__ tile_off, unsigned *__restrict__ masks, ll p_begin, ll p_end, ll n_tiles,
-                 unsigned long long *stats, int qpw, ll cap_words) {
+                 ll *__restrict__ tile_off, unsigned *__restrict__ masks, ll p_begin, ll p_end, ll n_tiles,
+                 unsigned long long *stats, int qpw, ll cap_words, unsigned long long *bump) {
     __shared__ float4 s_q[GF_WARPS][32];
     __shared__ int s_i[GF_WARPS][32];
-    if (tile_off[n_tiles] > cap_words) return;  // launched before the host knew the size: it re-launches after growing
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float4 *qf = s_q[wid];
@@ -363,8 +338,26 @@ grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, l
         int cid, my_row, my_cx;
         gf_tile_header(cell_sorted, g, p, pvalid, cid, my_row, my_cx);
         const float4 my4 = pvalid ? xf[p] : make_float4(0.f, 0.f, 0.f, 0.f);
-        unsigned *mw = masks + tile_off[t];
         unsigned todo = __ballot_sync(full, pvalid);
+        // the tile's mask words are reserved from a running counter (their number follows from the group structure
+        // alone); the offset is left in tile_off[] for the expand pass.  A tile that does not fit the buffer is
+        // skipped -- the counter still ends at the total, and the host repeats the pass with a larger buffer.
+        unsigned *mw;
+        {
+            unsigned td = todo;
+            int words = 0;
+            while (td) {
+                GfGroup G;
+                gf_next_group<D>(td, cid, my_row, my_cx, g, cell_start, lane, G);
+                words += G.nch << G.lg;
+            }
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(bump, (unsigned long long)words);
+            base = __shfl_sync(full, base, 0);
+            if (lane == 0) tile_off[t] = (ll)base;
+            if ((ll)base + words > cap_words) continue;
+            mw = masks + base;
+        }
         while (todo) {
             GfGroup G;
             gf_next_group<D>(todo, cid, my_row, my_cx, g, cell_start, lane, G);
@@ -668,9 +661,10 @@ static int mask_tiles(const cnnb200_ctx *ctx, ll pb, ll pe, int *qpw_out, ll *n_
     return CNNB200_OK;
 }
 
-static int scan_int_to_ll(cnnb200_ctx *ctx, const int *in, ll *out, ll count);
-
-// plan + mask pass on the row block [pb, pe): deg[] and the hit masks (b_masks at b_tile_off[])
+// mask pass on the row block [pb, pe): deg[] and the hit masks (b_masks at b_tile_off[]).  speculative: launched with
+// the buffer at hand, the number of words it asked for travels to the host with the degree scan's synchronisation
+// (cnn_scan_deg_to_row_ptr) and the caller repeats the pass non-speculatively when it did not fit; otherwise the
+// pass is repeated here until it fits.
 template <int D, bool SQRT>
 static int launch_mask(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg, bool speculative) {
     cudaStream_t st = ctx->stream;
@@ -678,46 +672,44 @@ static int launch_mask(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg
     ll n_tiles;
     mask_tiles(ctx, pb, pe, &qpw, &n_tiles);
     const int *cs = ctx->b_cell_id_sorted.as<int>(), *cst = ctx->b_cell_start.as<int>();
-    CNN_TRY(cnn_ensure(ctx, ctx->b_tile_words, sizeof(int) * (size_t)(n_tiles + 1)));
     CNN_TRY(cnn_ensure(ctx, ctx->b_tile_off, sizeof(ll) * (size_t)(n_tiles + 1)));
-    grid_plan_kernel<D><<<cnn_blocks((n_tiles + 1) * 32, 256), 256, 0, st>>>(cs, cst, ctx->grid, pb, pe, qpw, n_tiles,
-                                                                             ctx->b_tile_words.as<int>());
-    CNN_LAUNCHED(ctx, 1);
-    CNN_KERNEL_CHECK();
-    CNN_TRY(scan_int_to_ll(ctx, ctx->b_tile_words.as<int>(), ctx->b_tile_off.as<ll>(), n_tiles + 1));
-    ctx->mask_total = ctx->b_tile_off.as<ll>() + n_tiles;
-    if (speculative && ctx->b_masks.cap > 0) {
-        // warm context: launch with the capacity at hand; the total travels to the host with the degree scan's
-        // synchronisation (cnn_scan_deg_to_row_ptr) and cnn_grid_check_masks repeats the pass if it did not fit
-        ctx->mask_words_pending = true;
-    } else {
-        ll *h;
-        CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
-        CNN_CUDA(cudaMemcpyAsync(h, ctx->mask_total, sizeof(ll), cudaMemcpyDeviceToHost, st));
-        CNN_CUDA(cudaStreamSynchronize(st));
-        const ll words = h[0];
-        ctx->stats[ST_DIST] = words * 32;
-        ctx->mask_words_pending = false;
-        CNN_TRY(cnn_ensure(ctx, ctx->b_masks, sizeof(unsigned) * (size_t)words));
-    }
+    if (ctx->b_masks.cap == 0)  // first guess: 32 words per point (C2 needs 21; sparse sets less)
+        CNN_TRY(cnn_ensure(ctx, ctx->b_masks, sizeof(unsigned) * (size_t)((pe - pb) * 32 + (1 << 16))));
     ll blocks = (n_tiles + GF_WARPS - 1) / GF_WARPS;
     const ll cap = (ll)ctx->sm_count * 48;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     unsigned long long *recheck = (unsigned long long *)(ctx->b_tmp2.as<char>() + 40);
-    CNN_CUDA(cudaMemsetAsync(recheck, 0, sizeof(unsigned long long), st));
+    unsigned long long *bump = (unsigned long long *)(ctx->b_tmp2.as<char>() + 48);
     static const int minb = getenv("CNNB200_MASK_MINB") ? atoi(getenv("CNNB200_MASK_MINB")) : 3;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        CNN_CUDA(cudaMemsetAsync(recheck, 0, 2 * sizeof(unsigned long long), st));  // recheck counter + bump
 #define GM_ARGS ctx->b_xs.as<double>(), ctx->b_xf.as<float4>(), ctx->grid_n, cs, cst, ctx->grid, ctx->grid_rc, fp, deg,     \
                 ctx->b_tile_off.as<ll>(), ctx->b_masks.as<unsigned>(), pb, pe, n_tiles, recheck, qpw,                 \
-                (ll)(ctx->b_masks.cap / sizeof(unsigned))
-    if (minb == 3) grid_mask_kernel<D, SQRT, 3><<<(int)blocks, GF_WARPS * 32, 0, st>>>(GM_ARGS);
-    else if (minb == 2) grid_mask_kernel<D, SQRT, 2><<<(int)blocks, GF_WARPS * 32, 0, st>>>(GM_ARGS);
-    else grid_mask_kernel<D, SQRT, 4><<<(int)blocks, GF_WARPS * 32, 0, st>>>(GM_ARGS);
+                (ll)(ctx->b_masks.cap / sizeof(unsigned)), bump
+        if (minb == 4) grid_mask_kernel<D, SQRT, 4><<<(int)blocks, GF_WARPS * 32, 0, st>>>(GM_ARGS);
+        else if (minb == 2) grid_mask_kernel<D, SQRT, 2><<<(int)blocks, GF_WARPS * 32, 0, st>>>(GM_ARGS);
+        else grid_mask_kernel<D, SQRT, 3><<<(int)blocks, GF_WARPS * 32, 0, st>>>(GM_ARGS);
 #undef GM_ARGS
-    CNN_LAUNCHED(ctx, 1);
-    CNN_KERNEL_CHECK();
-    ctx->grid_recheck_pending = true;
-    return CNNB200_OK;
+        CNN_LAUNCHED(ctx, 1);
+        CNN_KERNEL_CHECK();
+        ctx->grid_recheck_pending = true;
+        ctx->mask_total = (const ll *)bump;
+        if (speculative) {
+            ctx->mask_words_pending = true;
+            return CNNB200_OK;
+        }
+        ll *h;
+        CNN_TRY(cnn_pinned(ctx, 64, (void **)&h));
+        CNN_CUDA(cudaMemcpyAsync(h, bump, sizeof(ll), cudaMemcpyDeviceToHost, st));
+        CNN_CUDA(cudaStreamSynchronize(st));
+        const ll words = h[0];
+        ctx->stats[ST_DIST] = words * 32;
+        ctx->mask_words_pending = false;
+        if ((size_t)words * sizeof(unsigned) <= ctx->b_masks.cap) return CNNB200_OK;
+        CNN_TRY(cnn_ensure(ctx, ctx->b_masks, sizeof(unsigned) * (size_t)words));
+    }
+    CNN_FAIL(CNNB200_E_STATE, "cell-list search: the hit masks did not fit after two regrowths");
 }
 
 static int launch_mask_any(cnnb200_ctx *ctx, ll pb, ll pe, FilterParams fp, int *deg, bool speculative) {

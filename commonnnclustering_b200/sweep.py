@@ -73,8 +73,7 @@ def fit_sweep(x, radius_cutoffs, cnn_cutoffs, member_cutoff=None, max_clusters=N
             t0 = time.perf_counter()
             ctx.components_begin(c + 1, c + 2)   # FitterExtInterface.make_parameters, _fit.pyx:129-161
             ctx.components_from_counts(counts)
-            ctx.components_labels(1, lab_dev, fresh=True)
-            ctx.sort_by_size(lab_dev, member_cutoff, max_clusters)
+            ctx.components_labels_sorted(lab_dev, 1, member_cutoff, max_clusters)   # numbering + size sort as one ranking
             if return_labels:
                 torch.from_numpy(labels_out[ir, ic]).copy_(lab_dev, non_blocking=True)
             # the record's three numbers come out of the device-side size sort: no pass over the labels

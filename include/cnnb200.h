@@ -234,6 +234,11 @@ int cnnb200_components_parents(cnnb200_ctx *ctx, int32_t **parents);
 int cnnb200_components_merge(cnnb200_ctx *ctx, const int32_t *others, int64_t count);
 int cnnb200_components_labels(cnnb200_ctx *ctx, int64_t current_start, int64_t *labels, int loc,
                               int fresh, int64_t *n_clusters_out);
+/* components_labels on fresh labels followed by Labels.sort_by_size (_types.pyx:212-286) as ONE ranking of the
+ * components (sizes, smallest members, the survivors of member_cutoff sorted by one CTA); what a cell of a parameter
+ * scan and the end of a row-sharded fit call.  n_clusters_out: clusters before the size sort. */
+int cnnb200_components_labels_sorted(cnnb200_ctx *ctx, int64_t current_start, int64_t member_cutoff,
+                                     int64_t max_clusters, int64_t *labels, int loc, int64_t *n_clusters_out);
 
 /* ---------------------------------------------------------------------------------------
  * The row-sharded fit on coordinates (d <= 3) as two calls per rank with ONE collective between them

@@ -67,7 +67,7 @@ def workload(name, n_override=None):
     if name == "c5":
         n = n_override or 1_000_000
         return dict(key="c5", name=f"C5: 8x8 (radius_cutoff, cnn_cutoff) sweep on MD-like 3-D N={n}, member_cutoff=10; "
-                                   "one step = all 64 cells (BASELINE configs[4])",
+                                   "one step = all 64 cells + isolate / child reclustering / reel of the softest cell (BASELINE configs[4])",
                     make=lambda: datasets.md_like_3d(n), n=n, d=3, radii=list(datasets.C5_RADII), cnn=list(datasets.C5_CNN),
                     r=0.063, c=20, member_cutoff=10)
     raise SystemExit(f"unknown workload {name}")
@@ -442,13 +442,33 @@ def run_b200(args):
         lab_all = torch.empty((len(radii), len(cnn), n), dtype=torch.int64).pin_memory().numpy()
         h2d, d2h = int(x.nbytes), int(cells * n * 8)
 
+        hcl = cluster.Clustering(x)
+        hcl.fitter._ctx = ctx
+        soft = torch.empty(n, dtype=torch.int64, device="cuda")
+
+        def hierarchy(labels_softest):
+            """isolate the clusters of the softest cell (r = 0.100, c = 2), recluster every child with >= 1000 points
+            at (0.063, 20), reel."""
+            hcl.labels = labels_softest
+            hcl.isolate()
+            for child in hcl.root._children.values():
+                if child._input_data.n_points >= 1000:
+                    hcl.fit(0.063, 20, member_cutoff=w["member_cutoff"], v=False, bundle=child)
+            hcl.reel()
+            return hcl.labels
+
         def step_device():
             sweep.fit_sweep(xd, radii, cnn, w["member_cutoff"], ctx=ctx, return_labels=False)
+            # the softest cell once more for its labels (the sweep above keeps none): one fit, one 8 MB copy
+            ctx.fit_points(xd, radii[-1] ** 2, cnn[0] + 1, cnn[0] + 2, soft, member_cutoff=w["member_cutoff"])
+            extra["clusters_after_reel"] = int(hierarchy(soft.cpu().numpy()).max())
 
         def step_host():
             sweep.fit_sweep(x, radii, cnn, w["member_cutoff"], ctx=ctx, labels_out=lab_all)
+            hierarchy(lab_all[len(radii) - 1, 0].copy())
         e2e_call = ("sweep.fit_sweep (one radius search + one count-mode pass per radius, components per cell over the C-ABI), "
-                    "coordinates from the host, all 64 label arrays copied into a page-locked host array")
+                    "coordinates from the host, all 64 label arrays copied into a page-locked host array; then "
+                    "Clustering.isolate on the softest cell, Clustering.fit on every child with >= 1000 points, Clustering.reel")
         units = cells * n
         steps = min(steps, 5)
         labd = None

@@ -5,7 +5,7 @@ import weakref
 
 import numpy as np
 
-from . import recipes
+from . import _lib, recipes
 from ._fit import Fitter, FitterB200Fused, HierarchicalFitter, Predictor
 from ._types import InputData, InputDataComponents, Labels
 from .report import Record, Summary
@@ -43,14 +43,18 @@ class Bundle:
     children = property(lambda self: self._children)
     parent = property(lambda self: self._parent)
 
-    def isolate(self, purge: bool = True, isolate_input_data: bool = True) -> None:
+    def isolate(self, purge: bool = True, isolate_input_data: bool = True, ctx=None) -> None:
         """Child bundles from the cluster labels (reference ``_bundle.pyx:275-352``): one child per
         label != 0 holding the indices of its members (ascending) and, optionally, that subset of the
-        input data.  The member lists come from one stable argsort instead of a Python loop."""
+        input data.  The member lists come from one stable sort by label instead of a Python loop -- on the
+        device (``cnnb200_labels_group``) when a context is given and the set is large."""
         if purge or self._children is None:
             self._children = {}
         lab = self._labels.labels
-        order = np.argsort(lab, kind="stable")
+        if ctx is not None and lab.shape[0] >= 100_000 and lab.size and lab.min() >= 0:
+            order, _ = ctx.labels_group(lab, np.zeros(lab.shape[0], dtype=np.int64))
+        else:
+            order = np.argsort(lab, kind="stable")
         sorted_lab = lab[order]
         starts = np.flatnonzero(np.r_[True, sorted_lab[1:] != sorted_lab[:-1]])
         ends = np.r_[starts[1:], sorted_lab.shape[0]]
@@ -135,7 +139,14 @@ class Clustering:
 
     def isolate(self, purge: bool = True, isolate_input_data: bool = True, bundle=None) -> None:
         """Reference ``Clustering.isolate`` (``cluster.pyx:394-413``)."""
-        (bundle if bundle is not None else self._bundle).isolate(purge, isolate_input_data)
+        target = bundle if bundle is not None else self._bundle
+        ctx = None
+        if target._labels is not None and target._labels.labels.shape[0] >= 100_000 and self._fitter is not None:
+            try:          # large sets: the grouping by label runs on the device
+                ctx = getattr(self._fitter, "ctx", None)
+            except _lib.CnnB200Error:
+                ctx = None    # no device here: the NumPy grouping (isolate is host logic and must not need one)
+        target.isolate(purge, isolate_input_data, ctx=ctx)
 
     def fit_hierarchical(self, purge=True, bundle=None, **fitter_kwargs) -> None:
         """Reference ``Clustering.fit_hierarchical`` (``cluster.pyx:394-411``): the keyword arguments are those of the

@@ -60,6 +60,23 @@ def exchange_slices(col_idx, slice_bounds, group=None):
         w.wait()
 
 
+def chunk_of(total, world):
+    """Length of the equal flat chunks an array of ``total`` elements is cut into for ``world`` ranks."""
+    return -(-max(int(total), 1) // world)
+
+
+def allgather_chunks(full, chunk, group=None):
+    """``full`` [world * chunk] holds the caller's chunk ``[rank * chunk, (rank + 1) * chunk)`` -> all chunks, in place
+    (NCCL: ``all_gather_into_tensor`` on a view of the buffer itself; gloo: per-chunk views)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = full[rank * chunk:(rank + 1) * chunk]
+    if full.is_cuda:
+        dist.all_gather_into_tensor(full, mine, group=group)
+    else:
+        dist.all_gather(list(full.view(world, chunk).unbind(0)), mine.clone(), group=group)
+
+
 def gather_parents(parents, group=None):
     """parents int32 [n] of this rank -> int32 [G, n] of all ranks."""
     world = dist.get_world_size(group)
@@ -145,7 +162,7 @@ class ShardedFit:
             bounds = np.searchsorted(row_ptr_host, targets, side="left").astype(np.int64)
             bounds[0], bounds[-1] = 0, n
             bounds = np.maximum.accumulate(bounds)                     # row blocks balanced by entries
-            chunk_r, chunk_c = -(-(n + 1) // G), -(-max(nnz, 1) // G)  # flat chunks of the two arrays
+            chunk_r, chunk_c = chunk_of(n + 1, G), chunk_of(nnz, G)       # flat chunks of the two arrays
             row_ptr = torch.empty(G * chunk_r, dtype=torch.int64, device=self.device)
             col_idx = torch.empty(G * chunk_c, dtype=torch.int32, device=self.device)
             plan = self._csr_plan = (key, bounds, chunk_r, chunk_c, row_ptr, col_idx)
@@ -165,13 +182,8 @@ class ShardedFit:
     def exchange_csr(self, blk):
         """Exchange 1 of SURVEY 8e on bytes that already sit in HBM: all-gather of the G equal chunks of ``row_ptr``
         and of ``col_idx`` (in place, NCCL over NVLink); the gathered CSR is adopted.  Returns the row-block bounds."""
-        g = self.rank
-        for full, chunk in ((blk["row_ptr"], blk["chunk_r"]), (blk["col_idx"], blk["chunk_c"])):
-            mine = full[g * chunk:(g + 1) * chunk]
-            if full.is_cuda:
-                dist.all_gather_into_tensor(full, mine, group=self.group)
-            else:
-                dist.all_gather(list(full.view(self.world, chunk).unbind(0)), mine.clone(), group=self.group)
+        allgather_chunks(blk["row_ptr"], blk["chunk_r"], self.group)
+        allgather_chunks(blk["col_idx"], blk["chunk_c"], self.group)
         self.ctx.neighbours_adopt(blk["row_ptr"][:blk["n"] + 1], blk["col_idx"][:blk["nnz"]], -1, grid_perm=False)
         self.last = dict(bounds=blk["bounds"], nnz=blk["nnz"], two_phase=True)
         return blk["bounds"]

@@ -57,6 +57,14 @@ def _worker(rank, world, port, out):
         col[sb[rank]:sb[rank + 1]] = torch.from_numpy(ci[sb[rank]:sb[rank + 1]].astype(np.int32))
         cdist.exchange_slices(col, sb)
         assert np.array_equal(col.numpy(), ci)
+        # exchange 1, equal-chunk form (the precomputed-CSR path): flat chunks that ignore row boundaries, gathered in place
+        for arr in (rp, ci.astype(np.int32)):
+            chunk = cdist.chunk_of(arr.shape[0], world)
+            full = torch.full((world * chunk,), -9, dtype=torch.from_numpy(arr).dtype)
+            a, b2 = rank * chunk, min((rank + 1) * chunk, arr.shape[0])
+            full[a:b2] = torch.from_numpy(arr[a:b2])
+            cdist.allgather_chunks(full, chunk)
+            assert np.array_equal(full[:arr.shape[0]].numpy(), arr)
         # per-rank components on the own row block only (NumPy stand-in for K5/K6)
         core = np.diff(rp) > c + 1
         parent = np.where(core, np.arange(n), -1).astype(np.int32)

@@ -699,7 +699,9 @@ __global__ void comp_merge_kernel(const int *__restrict__ others, ll n, ll count
     for (; t < n * count; t += stride) {
         int i = (int)(t % n);
         int o = others[t];
-        if (o >= 0 && o != i) uf_union(parent, i, o);
+        // most entries say what this rank's forest says already (identical after an earlier merge, or the rank's own
+        // slice): one comparison instead of two finds
+        if (o >= 0 && o != i && o != ld_parent(parent, i)) uf_union(parent, i, o);
     }
 }
 

@@ -63,6 +63,12 @@ __device__ __forceinline__ int cell_coord(double v, double lo, double h, int dim
     return min(max(c, 0), dim - 1);
 }
 
+// ORDERED: idx[i] = i for the stable radix sort that follows (the cell-sorted order is then a function of the data
+// alone -- what the ranks of a row-sharded run need to agree on); otherwise idx[i] = the point's arrival slot in its
+// cell, and scatter_kernel places it at cell_start[cell] + slot: a counting sort, no radix passes.  The order inside
+// a cell then depends on the schedule; neighbour sets, intersections and labels do not (rows are ascending in
+// whatever internal order there is, only the numbering maps back through perm[]).
+template <bool ORDERED>
 __global__ void cell_id_kernel(const double *__restrict__ x, ll n, GridDesc g, int *cell_id, int *idx,
                                int *cell_count) {
     ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
@@ -71,8 +77,8 @@ __global__ void cell_id_kernel(const double *__restrict__ x, ll n, GridDesc g, i
     for (int k = 0; k < g.d; ++k) c[k] = cell_coord(x[i * g.d + k], g.lo[k], g.h, g.dims[k]);
     int cid = (c[2] * g.dims[1] + c[1]) * g.dims[0] + c[0];
     cell_id[i] = cid;
-    idx[i] = (int)i;
-    atomicAdd(&cell_count[cid], 1);
+    const int slot = atomicAdd(&cell_count[cid], 1);
+    idx[i] = ORDERED ? (int)i : slot;
 }
 
 // Origin of cell index c along one axis.  The SAME expression is used wherever a cell-local
@@ -100,6 +106,35 @@ __global__ void gather_kernel(const double *__restrict__ x, const int *__restric
     }
     if (!xf) return;
     const int c = cell_sorted[p];
+    const int cx = c % g.dims[0];
+    const int t = c / g.dims[0];
+    const int cy = t % g.dims[1];
+    const int cz = t / g.dims[1];
+    float4 f;
+    f.x = (float)__dsub_rn(v[0], cell_origin(g.lo[0], g.h, cx & ~15));
+    f.y = (float)__dsub_rn(v[0], cell_origin(g.lo[0], g.h, ((cx + 8) & ~15) - 8));
+    f.z = d > 1 ? (float)__dsub_rn(v[1], cell_origin(g.lo[1], g.h, cy)) : 0.f;
+    f.w = d > 2 ? (float)__dsub_rn(v[2], cell_origin(g.lo[2], g.h, cz)) : 0.f;
+    xf[p] = f;
+}
+
+// counting-sort form of the same: thread i (caller order, coalesced reads of x) writes point i to its place
+__global__ void scatter_kernel(const double *__restrict__ x, const int *__restrict__ cell_id, const int *__restrict__ slot,
+                               const int *__restrict__ cell_start, ll n, GridDesc g, int *__restrict__ perm,
+                               int *__restrict__ cell_sorted, double *xs, float4 *xf) {
+    ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = g.d;
+    const int c = cell_id[i];
+    const ll p = (ll)cell_start[c] + slot[i];
+    perm[p] = (int)i;
+    cell_sorted[p] = c;
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int k = 0; k < d; ++k) {
+        v[k] = x[i * d + k];
+        xs[k * n + p] = v[k];
+    }
+    if (!xf) return;
     const int cx = c % g.dims[0];
     const int t = c / g.dims[0];
     const int cy = t % g.dims[1];
@@ -846,29 +881,43 @@ int cnn_grid_build(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radiu
     CNN_TRY(cnn_ensure(ctx, ctx->b_tmp1, sizeof(ll) * (size_t)(n + 1)));
     int *cell_count = ctx->b_cell_count.as<int>();
     CNN_CUDA(cudaMemsetAsync(cell_count, 0, sizeof(int) * (size_t)(ncell + 1), st));
-    cell_id_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_x, n, g, ctx->b_cell_id.as<int>(),
-                                                         ctx->b_idx.as<int>(), cell_count);
+    // a row-sharded run (want_cap) needs an order every rank reproduces: stable radix sort by cell; a single GPU takes
+    // the counting sort (CNNB200_ORDERED_SORT=1 forces the radix sort)
+    static const bool force_ordered = getenv("CNNB200_ORDERED_SORT") && atoi(getenv("CNNB200_ORDERED_SORT")) != 0;
+    const bool ordered = want_cap || force_ordered;
+    if (ordered)
+        cell_id_kernel<true><<<cnn_blocks(n, 256), 256, 0, st>>>(d_x, n, g, ctx->b_cell_id.as<int>(), ctx->b_idx.as<int>(), cell_count);
+    else
+        cell_id_kernel<false><<<cnn_blocks(n, 256), 256, 0, st>>>(d_x, n, g, ctx->b_cell_id.as<int>(), ctx->b_idx.as<int>(), cell_count);
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
+    CNN_TRY(cnn_ensure(ctx, ctx->b_xf, sizeof(float4) * (size_t)n));
+    size_t need_sort = 0, need_scan = 0;
     int bits = 1;
     while ((1ll << bits) < ncell) ++bits;
-    size_t need_sort = 0, need_scan = 0;
-    CNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need_sort, ctx->b_cell_id.as<int>(),
-                                             ctx->b_cell_id_sorted.as<int>(), ctx->b_idx.as<int>(),
-                                             ctx->b_perm.as<int>(), (int)n, 0, bits, st));
+    if (ordered)
+        CNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need_sort, ctx->b_cell_id.as<int>(),
+                                                 ctx->b_cell_id_sorted.as<int>(), ctx->b_idx.as<int>(),
+                                                 ctx->b_perm.as<int>(), (int)n, 0, bits, st));
     CNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need_scan, cell_count, ctx->b_cell_start.as<int>(),
                                            (int)(ncell + 1), st));
     CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need_sort > need_scan ? need_sort : need_scan));
     size_t cap = ctx->b_cub.cap;
-    CNN_CUDA(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, cap, ctx->b_cell_id.as<int>(),
-                                             ctx->b_cell_id_sorted.as<int>(), ctx->b_idx.as<int>(),
-                                             ctx->b_perm.as<int>(), (int)n, 0, bits, st));
+    if (ordered)
+        CNN_CUDA(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, cap, ctx->b_cell_id.as<int>(),
+                                                 ctx->b_cell_id_sorted.as<int>(), ctx->b_idx.as<int>(),
+                                                 ctx->b_perm.as<int>(), (int)n, 0, bits, st));
     cap = ctx->b_cub.cap;
     CNN_CUDA(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, cap, cell_count, ctx->b_cell_start.as<int>(),
                                            (int)(ncell + 1), st));
-    CNN_TRY(cnn_ensure(ctx, ctx->b_xf, sizeof(float4) * (size_t)n));
-    gather_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_x, ctx->b_perm.as<int>(), ctx->b_cell_id_sorted.as<int>(), n, g,
-                                                        ctx->b_xs.as<double>(), ctx->b_xf.as<float4>());
+    if (ordered)
+        gather_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_x, ctx->b_perm.as<int>(), ctx->b_cell_id_sorted.as<int>(), n, g,
+                                                            ctx->b_xs.as<double>(), ctx->b_xf.as<float4>());
+    else
+        scatter_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(d_x, ctx->b_cell_id.as<int>(), ctx->b_idx.as<int>(),
+                                                             ctx->b_cell_start.as<int>(), n, g, ctx->b_perm.as<int>(),
+                                                             ctx->b_cell_id_sorted.as<int>(), ctx->b_xs.as<double>(),
+                                                             ctx->b_xf.as<float4>());
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     ctx->grid = g;

@@ -214,8 +214,8 @@ class InputDataComponents(InputData):
     def pin(self) -> bool:
         """Page-locks the host array in place (once) so that every fit on these coordinates copies them at PCIe
         speed; nothing is copied or cached, later changes to the array are seen as before.  Released with the object."""
-        if not isinstance(self._data, np.ndarray) or self._data.nbytes == 0:
-            return False
+        if not isinstance(self._data, np.ndarray) or self._data.nbytes < (1 << 20):
+            return False   # below a megabyte the registration costs more than the pageable copy it saves
         if getattr(self, "_pinned", None) is None:
             import weakref
 

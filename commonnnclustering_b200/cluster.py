@@ -178,14 +178,34 @@ class Clustering:
                 depth -= 1
             parent._labels.meta["origin"] = "reel"
             parent_labels = parent._labels.labels
+            # the reference asks for the parent's largest label before every child (an O(n) pass per child); kept exact
+            # with a histogram that follows the assignments: a child's points are ALL points of its label, so the label
+            # leaves the parent when the child's labels are written over it
+            counts = np.bincount(parent_labels[parent_labels >= 0]).astype(np.int64) if parent_labels.size else np.zeros(1, np.int64)
+            negative = bool(parent_labels.size and parent_labels.min() < 0)
+            top = counts.shape[0] - 1
             for label, child in parent._children.items():
                 if child._labels is None:
                     continue
                 if depth is None or depth > 0:
                     _reel(child, depth)
-                n_clusters = int(parent_labels.max())
+                if negative:
+                    n_clusters = int(parent_labels.max())
+                else:
+                    while top > 0 and counts[top] == 0:
+                        top -= 1
+                    n_clusters = top
                 child_labels = child._labels.labels
-                parent_labels[child.parent_indices] = np.where(child_labels == 0, 0, child_labels + n_clusters)
+                new = np.where(child_labels == 0, 0, child_labels + n_clusters)
+                if not negative:
+                    old_vals = parent_labels[child.parent_indices]
+                    counts -= np.bincount(old_vals, minlength=counts.shape[0])
+                    add = np.bincount(new)
+                    if add.shape[0] > counts.shape[0]:
+                        counts = np.concatenate([counts, np.zeros(add.shape[0] - counts.shape[0], np.int64)])
+                    counts[:add.shape[0]] += add
+                    top = max(top, add.shape[0] - 1)
+                parent_labels[child.parent_indices] = new
                 params_parent = parent._labels.meta.setdefault("params", {})
                 params_parent.pop(label, None)
                 for old_label, p in child._labels.meta.get("params", {}).items():

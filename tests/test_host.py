@@ -195,3 +195,38 @@ def test_get_subset_of_every_input_type():
         padded[i, :counts[i]] = ci[rp[i]:rp[i + 1]]
     nb = _types.InputDataNeighbourhoods(padded, counts).get_subset(idx)
     assert [row.tolist() for row in nb.data] == want_rows and nb.n_neighbours.tolist() == [2, 3, 2]
+
+
+def test_reel_running_maximum_equals_the_per_child_pass():
+    """reel shifts every child's labels by the parent's CURRENT largest label (cluster.pyx:502-558 takes a max over the
+    parent per child); the histogram that replaces those passes must give the same labels, also when a child is all
+    noise (the parent's largest label then disappears) and over two levels."""
+    from commonnnclustering_b200 import cluster
+    from commonnnclustering_b200._types import Labels
+
+    rng = np.random.default_rng(8)
+
+    def naive(parent_labels, children):
+        out = parent_labels.copy()
+        for label, (idx, child_labels) in children.items():
+            n_clusters = int(out.max())
+            out[idx] = np.where(child_labels == 0, 0, child_labels + n_clusters)
+        return out
+
+    for trial in range(20):
+        n = 400
+        lab = rng.integers(0, 7, n)
+        x = rng.random((n, 2))
+        cl = cluster.Clustering(x)
+        cl.labels = lab.copy()
+        cl.isolate()
+        children = {}
+        for label, child in cl.root._children.items():
+            m = child.parent_indices.shape[0]
+            kind = rng.integers(0, 3)
+            cl_lab = np.zeros(m, dtype=np.int64) if kind == 0 else rng.integers(0, 1 + rng.integers(1, 5), m)
+            child._labels = Labels(cl_lab.copy())
+            children[label] = (child.parent_indices, cl_lab)
+        want = naive(lab.astype(np.int64), children)
+        cl.reel()
+        np.testing.assert_array_equal(cl.labels, want)

@@ -47,6 +47,7 @@ SIGNATURES = {
     "cnnb200_neighbours_device_view": [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)],
     "cnnb200_cn_count": [_P, _I64, _P, C.c_int, C.POINTER(_I64)],
     "cnnb200_cn_count_rows": [_P, _I64, _I64, _I64, _P, C.c_int, C.POINTER(_I64)],
+    "cnnb200_cn_check_pairs": [_P, _P, _I64, _I64, _P, C.c_int],
     "cnnb200_fit": [_P, _I64, _I64, _I64, _P, _P, C.c_int, C.POINTER(_I64)],
     "cnnb200_components_begin": [_P, _I64, _I64, _P, C.c_int],
     "cnnb200_components_edges": [_P, _I64, _I64],
@@ -321,6 +322,15 @@ class Context:
         b, e = (0, n) if rows is None else rows
         check(self._lib.cnnb200_cn_count_rows(self._h, int(n_member_cutoff), int(b), int(e), p, loc, C.byref(ne)))
         return out[:nnz], ne.value
+
+    def cn_check_pairs(self, pairs, similarity_cutoff):
+        """Early-exit check of ``pairs`` (int32 [k, 2], internal row indices) -> uint8 [k]: bit 0 = per-lane merge,
+        bit 1 = whole-warp window form; both say |N(i) ∩ N(j)| >= similarity_cutoff."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        out = np.zeros(pairs.shape[0], dtype=np.uint8)
+        check(self._lib.cnnb200_cn_check_pairs(self._h, pairs.ctypes.data, pairs.shape[0], int(similarity_cutoff),
+                                               out.ctypes.data, HOST))
+        return out
 
     # -- components -----------------------------------------------------------------------------
     def fit(self, n_member_cutoff, similarity_cutoff, current_start, labels, consider=None):

@@ -622,7 +622,22 @@ class SimilarityCheckerCommonNN(SimilarityChecker):
         return int(counts[0])
 
     def check(self, neighbours_a, neighbours_b, cluster_params, ctx=None) -> bool:
+        """``SimilarityChecker.check`` of the reference for two index lists, answered by the EARLY-EXIT kernels the fit
+        uses (per-lane merge and whole-warp window form must agree), not by the count."""
         c = cluster_params.similarity_cutoff
         if c == 0:
             return True  # _types.pyx:2589-2590
-        return self.get(neighbours_a, neighbours_b, cluster_params, ctx) >= c
+        ctx = ctx or _lib.default_context()
+        a = np.unique(np.asarray(neighbours_a, dtype=np.int64))
+        b = np.unique(np.asarray(neighbours_b, dtype=np.int64))
+        if a.size == 0 or b.size == 0:
+            return False
+        both = np.unique(np.concatenate([a, b]))
+        rows = [np.searchsorted(both, a), np.searchsorted(both, b)] + [np.empty(0, np.int64)] * max(both.size - 2, 0)
+        row_ptr = np.zeros(len(rows) + 1, dtype=np.int64)
+        np.cumsum([len(r) for r in rows], out=row_ptr[1:])
+        ctx.neighbours_from_csr(row_ptr, np.concatenate(rows).astype(np.int64))
+        bits = int(ctx.cn_check_pairs([[0, 1]], c)[0])
+        if bits not in (0, 3):
+            raise RuntimeError("the two early-exit forms of the common-neighbour check disagree")
+        return bits == 3

@@ -1103,3 +1103,83 @@ extern "C" int cnnb200_fit_sharded_end(cnnb200_ctx *ctx, const int32_t *others, 
     ll *d_labels = loc == CNNB200_HOST ? ctx->b_labels.as<ll>() : labels;
     return cnn_labels_sorted(ctx, current_start, member_cutoff, max_clusters, labels, d_labels, loc, n_clusters_out);
 }
+
+// ---- the early-exit checks on arbitrary pairs (SimilarityChecker.check in bulk; also what the tests pin) ---------------
+// out[k] bit 0: lane_check (the per-lane two-pointer merge of the sampling round, SimilarityCheckerExtScreensorted._check,
+// _types.pyx:2654-2706); bit 1: the whole-warp form of the work list (row window of N(i), N(j) streamed through it, or
+// warp_common<true> when the row has no window).  Both must equal |N(i) ∩ N(j)| >= cutoff (cutoff 0: always true).
+__global__ void __launch_bounds__(WIN_WARPS * 32)
+cn_check_pairs_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col_idx, const int2 *__restrict__ pairs,
+                      ll n_pairs, int cutoff, uint8_t *__restrict__ out) {
+    __shared__ unsigned win_all[WIN_WARPS][WIN_BITS / 32];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    RowWin w;
+    w.bits = win_all[threadIdx.x >> 5];
+    w.first = 0;
+    w.span = 0;
+    for (int t = lane; t < WIN_BITS / 32; t += 32) w.bits[t] = 0;
+    __syncwarp();
+    const ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5, nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    for (ll k0 = warp * 32; k0 < n_pairs; k0 += nwarps * 32) {
+        const ll k = k0 + lane;
+        const bool valid = k < n_pairs;
+        const int2 pr = valid ? pairs[k] : make_int2(0, 0);
+        const ll bi = row_ptr[pr.x], bj = row_ptr[pr.y];
+        const int mi = (int)(row_ptr[pr.x + 1] - bi), mj = (int)(row_ptr[pr.y + 1] - bj);
+        int res = valid ? lane_check(col_idx + bi, mi, col_idx + bj, mj, cutoff) : 0;
+        for (int src = 0; src < 32; ++src) {
+            if (k0 + src >= n_pairs) break;
+            const int *ri = col_idx + __shfl_sync(full, bi, src), *rj = col_idx + __shfl_sync(full, bj, src);
+            const int ni = __shfl_sync(full, mi, src), nj = __shfl_sync(full, mj, src);
+            int ok;
+            if (cutoff <= 0) ok = 1;
+            else if (ni < cutoff || nj < cutoff) ok = 0;
+            else {
+                win_set(w, ri, ni, lane);
+                if (w.span) {
+                    int buf[WIN_PF];
+                    row_prefetch(buf, rj, nj, lane);
+                    ok = row_count(buf, rj, nj, lane, w) >= cutoff;
+                } else {
+                    ok = warp_common<true>(ri, ni, rj, nj, cutoff, lane);
+                }
+                win_clear(w, ri, ni, lane);
+            }
+            if (lane == src) res |= ok ? 2 : 0;
+        }
+        if (valid) out[k] = (uint8_t)res;
+    }
+}
+
+extern "C" int cnnb200_cn_check_pairs(cnnb200_ctx *ctx, const int32_t *pairs, int64_t n_pairs, int64_t similarity_cutoff,
+                                      uint8_t *out, int loc) {
+    if (!ctx || (!pairs && n_pairs > 0) || (!out && n_pairs > 0)) CNN_FAIL(CNNB200_E_INVALID, "cn_check_pairs: NULL argument");
+    if (!ctx->have_nb) CNN_FAIL(CNNB200_E_STATE, "cn_check_pairs: no neighbourhoods held by this context");
+    if (n_pairs < 0 || similarity_cutoff < 0) CNN_FAIL(CNNB200_E_INVALID, "cn_check_pairs: negative argument");
+    if (n_pairs == 0) return CNNB200_OK;
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int2 *d_pairs = (const int2 *)pairs;
+    uint8_t *d_out = out;
+    if (loc == CNNB200_HOST) {
+        for (ll k = 0; k < 2 * n_pairs; ++k)
+            if (pairs[k] < 0 || pairs[k] >= ctx->n) CNN_FAIL(CNNB200_E_INVALID, "cn_check_pairs: index outside [0, n)");
+        CNN_TRY(cnn_ensure(ctx, ctx->b_edges, sizeof(int2) * (size_t)n_pairs));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_flags, (size_t)n_pairs + 64));
+        CNN_CUDA(cudaMemcpyAsync(ctx->b_edges.p, pairs, sizeof(int2) * (size_t)n_pairs, cudaMemcpyHostToDevice, st));
+        d_pairs = ctx->b_edges.as<int2>();
+        d_out = ctx->b_flags.as<uint8_t>();
+    }
+    const int cutoff = similarity_cutoff > 0x7fffffffll ? 0x7fffffff : (int)similarity_cutoff;
+    ll blocks = (n_pairs + WIN_WARPS * 32 - 1) / (WIN_WARPS * 32);
+    if (blocks > (ll)ctx->sm_count * 8) blocks = (ll)ctx->sm_count * 8;
+    cn_check_pairs_kernel<<<(int)blocks, WIN_WARPS * 32, 0, st>>>(ctx->row_ptr, ctx->col_idx, d_pairs, n_pairs, cutoff, d_out);
+    CNN_LAUNCHED(ctx, 1);
+    CNN_KERNEL_CHECK();
+    if (loc == CNNB200_HOST) {
+        CNN_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+        CNN_CUDA(cudaStreamSynchronize(st));
+    }
+    return CNNB200_OK;
+}

@@ -185,6 +185,12 @@ int cnnb200_cn_count(cnnb200_ctx *ctx, int64_t n_member_cutoff, uint32_t *counts
  * of a row-sharded run -- the rows of its block and of every neighbour of them must be held (halo construction). */
 int cnnb200_cn_count_rows(cnnb200_ctx *ctx, int64_t n_member_cutoff, int64_t row_begin, int64_t row_end,
                           uint32_t *counts, int loc, int64_t *n_edges_out);
+/* SimilarityChecker._check (early exit) for arbitrary pairs of rows of the held neighbourhoods, in the INTERNAL index
+ * space: pairs int32 [n_pairs][2], out uint8 [n_pairs].  Bit 0 = the per-lane two-pointer merge the sampling round
+ * uses (SimilarityCheckerExtScreensorted._check, _types.pyx:2654-2706), bit 1 = the whole-warp window form of the work
+ * list; both equal |N(i) ∩ N(j)| >= similarity_cutoff (0: always true, _types.pyx:2589-2590). */
+int cnnb200_cn_check_pairs(cnnb200_ctx *ctx, const int32_t *pairs, int64_t n_pairs, int64_t similarity_cutoff,
+                           uint8_t *out, int loc);
 
 /* ---------------------------------------------------------------------------------------
  * Density-connected components.  Replaces FitterExtBFS._fit (_fit.pyx:408-491) including its

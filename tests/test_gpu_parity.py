@@ -977,3 +977,37 @@ def test_symmetry_check_of_precomputed_lists(ctx):
     g = _types.NeighboursGetterLookup(is_sorted=True, check_symmetric=True)
     with pytest.raises(ValueError):
         g.get_all(_types.InputDataNeighbourhoodsCSR(rp2, ci2), ctx=ctx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["local", "long_rows", "no_locality"])
+def test_early_exit_checks_equal_oracle(ctx, kind):
+    """The two early-exit forms of SimilarityChecker._check that the fit runs -- the per-lane merge of the sampling
+    round (with its skip-ahead for long lists) and the whole-warp window form of the work list (bitmap window, or the
+    global binary search when a row has no index locality) -- on arbitrary pairs against |N(i) ∩ N(j)| >= c."""
+    rng = np.random.default_rng(21)
+    if kind == "long_rows":
+        x, r = datasets.blobs_2d(3000), 0.35        # hundreds of entries per row
+    else:
+        x, r = datasets.md_like_3d(6000), 0.45
+    if kind == "no_locality":
+        x = np.ascontiguousarray(x[rng.permutation(x.shape[0])])   # rows span the whole index range: no window
+        x = np.concatenate([x, x + 100.0, x + 200.0, x + 300.0, x + 400.0, x + 500.0, x + 600.0, x + 700.0, x + 800.0,
+                            x + 900.0, x + 1000.0, x + 1100.0])     # 72 000 points: spans beyond the 65 536-bit window
+        x = np.ascontiguousarray(x[rng.permutation(x.shape[0])])
+    rp, ci = port.neighbours(x, r * r)
+    n = x.shape[0]
+    ctx.neighbours_from_csr(rp, ci)
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    pick = rng.choice(ci.shape[0], size=3000, replace=False)
+    pairs = np.concatenate([np.stack([rows[pick], ci[pick]], 1),                       # neighbours
+                            rng.integers(0, n, (500, 2))]).astype(np.int32)              # arbitrary rows
+    want_cnt = np.array([np.intersect1d(ci[rp[i]:rp[i + 1]], ci[rp[j]:rp[j + 1]], assume_unique=True).size
+                         for i, j in pairs])
+    if kind == "long_rows":
+        assert np.diff(rp).max() > 400
+    for c in (0, 1, 3, 12, 40, 200):
+        got = ctx.cn_check_pairs(pairs, c)
+        want = (want_cnt >= c) | (c == 0)
+        np.testing.assert_array_equal(got & 1, want.astype(np.uint8), err_msg=f"per-lane merge, c={c}")
+        np.testing.assert_array_equal(got >> 1, want.astype(np.uint8), err_msg=f"window form, c={c}")

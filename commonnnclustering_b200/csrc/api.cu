@@ -98,7 +98,7 @@ extern "C" int cnnb200_ctx_create(int device, cnnb200_ctx **out) {
     if (const char *e = getenv("CNNB200_PACKED")) ctx->use_packed = atoi(e) != 0;
     if (const char *e = getenv("CNNB200_PACK_FIT")) ctx->pack_in_fit = atoi(e) != 0;
     if (const char *e = getenv("CNNB200_TENSOR_REORDER")) ctx->tensor_reorder = atoi(e) != 0;
-    if (const char *e = getenv("CNNB200_TENSOR_PAIR_CAP")) ctx->tensor_band_cap = atoll(e);  // initial pair-list capacity (tests)
+    if (const char *e = getenv("CNNB200_TENSOR_PAIR_CAP")) ctx->tensor_band_cap = atoll(e);  // initial slab capacity of the tensor-core search (tests)
     if (const char *e = getenv("CNNB200_SINGLE_PASS_MB")) ctx->single_pass_limit = (ll)atoll(e) << 20;
     *out = ctx;
     return CNNB200_OK;
@@ -110,7 +110,7 @@ extern "C" int cnnb200_ctx_create(int device, cnnb200_ctx **out) {
     F(c->b_tmp1) F(c->b_tmp2) F(c->b_parent) F(c->b_core) F(c->b_above) F(c->b_edges) F(c->b_worklist) F(c->b_cell_count) F(c->b_minorig) F(c->b_flags)             \
     F(c->b_rank) F(c->b_labels) F(c->b_consider) F(c->b_stats) F(c->b_lab_count) F(c->b_lab_first)  \
     F(c->b_lab_keys) F(c->b_lab_keys2) F(c->b_lab_vals) F(c->b_lab_vals2) F(c->b_lab_map) \
-    F(c->b_tile_off) F(c->b_masks) F(c->b_pg_x) F(c->b_pg_orig) F(c->b_pg_xq) F(c->b_pg_perm) F(c->b_pg_deg) F(c->b_pg_img) F(c->b_pg_row_ptr) F(c->b_pg_col)
+    F(c->b_tile_off) F(c->b_masks) F(c->b_pg_x) F(c->b_pg_orig) F(c->b_pg_xq) F(c->b_pg_perm) F(c->b_pg_deg) F(c->b_pg_img) F(c->b_pg_row_ptr) F(c->b_pg_col) F(c->b_tslab) F(c->b_tband) F(c->b_tdir)
 
 extern "C" int cnnb200_ctx_release(cnnb200_ctx *ctx) {
     if (!ctx) CNN_FAIL(CNNB200_E_INVALID, "ctx is NULL");

@@ -173,7 +173,8 @@ struct cnnb200_ctx {
     ll lab_summary_host[3] = {0, 0, 0};
     ll lab_summary_n = 0;
     ll known_max_label = -1;
-    ll tensor_band_cap = 0;  // capacity (pairs) the borderline list of the tensor-core search needed last time  // set by cnnb200_fit_points for the sort_by_size call that follows a fresh fit
+    ll tensor_band_cap = 0;  // capacity (slabs) the hit bitmaps of the tensor-core search needed last time
+    Buf b_tslab, b_tband, b_tdir;  // tensor-core search: hit slabs, borderline slabs, the two slab directories
 
     // ---- measurement ---------------------------------------------------------------------------
     bool timing = false;

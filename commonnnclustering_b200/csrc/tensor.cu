@@ -5,34 +5,35 @@
 // Bulk replacement of NeighboursGetterExtBruteForce._get (reference _types.pyx:1692-1710) with
 // MetricExtEuclideanReduced / MetricExtEuclidean (_types.pyx:2253-2267, :2173-2187).  The
 // reference evaluates N^2 distances in f64, one virtual call each; here the N^2 part is a dense
-// contraction d2(i,j) = |x_i|^2 + |x_j|^2 - 2 x_i.x_j and runs as a bf16 GEMM:
+// contraction d2(i,j) = |x_i|^2 + |x_j|^2 - 2 x_i.x_j and runs as an fp16 GEMM:
 //
-//   * the (mean-centred) coordinates are split x = hi + lo into two bf16 parts; the three
-//     products hi.hi + hi.lo + lo.hi are ONE MMA chain over the concatenated K axis
-//     A' = [hi | hi | lo], B' = [hi | lo | hi] (K = 3 D, fp32 accumulation in TMEM);
+//   * the (mean-centred, power-of-two scaled) coordinates are split x = hi + lo into two fp16
+//     parts; the three products lo.hi + hi.lo + hi.hi are ONE MMA chain over the concatenated K
+//     axis A' = [lo | hi | hi], B' = [hi | lo | hi] (K = 3 D, fp32 accumulation in TMEM);
 //   * the epilogue reads the accumulator tile with tcgen05.ld, forms d2~ and classifies:
-//       d2~ <= R - eps  -> neighbour,   d2~ > R + eps -> not a neighbour,
-//       otherwise       -> the pair is re-evaluated right there with the reference's own f64
-//                          expression (sequential sum, no FMA, sqrt for the non-reduced metric);
-//     eps is a bound on |d2~ - d2| derived from the largest norm, so the neighbour
-//     SETS are exactly the reference's;
-//   * a CTA owns 128 rows and walks over all 128-column tiles in ascending order, so each CSR
-//     row is emitted ascending (count pass -> scan -> fill pass, as for the other producers).
+//       d2~ <= R - eps  -> neighbour,   d2~ > R + eps -> not a neighbour,   otherwise borderline;
+//     the result leaves the SM as hit BITMAPS (32 rows x 128 columns per warp and tile, only where
+//     there is a hit), borderline bits in a second bitmap;
+//   * borderline pairs are decided by tile_resolve_kernel with the reference's own f64 expression
+//     (sequential sum, no FMA, sqrt for the non-reduced metric); eps is a bound on |d2~ - d2|
+//     derived from the largest norm, so the neighbour SETS are exactly the reference's;
+//   * the CSR follows from the bitmaps by position (tile_rows_kernel: popcount -> scan -> expand):
+//     rows come out ascending with no pair list and no sort.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one
-// elected lane) + TMEM allocation, warps 2-5 = epilogue (one TMEM lane quarter each).
-// Pipelines: smem B stages full/empty (TMA <-> MMA), TMEM accumulator stages full/empty
-// (MMA <-> epilogue), two stages each.
+// Warp roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one
+// elected lane) + TMEM allocation, warps 2-9 = epilogue (two row tiles x four TMEM lane quarters).
+// Pipelines: smem B stages full/empty (TMA <-> MMA), four TMEM accumulator stages full/empty
+// (MMA <-> epilogue).
 #include <cub/cub.cuh>
 #include <cuda.h>
 #include <string.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "common.cuh"
 
 #define TT 128            // tile edge (rows of A' = UMMA M, rows of B' = UMMA N)
-#define KATOM 64          // bf16 elements per 128-byte swizzle atom
+#define KATOM 64          // 16-bit elements per 128-byte swizzle atom
 #define ATOM_BYTES (TT * 128)
 #define MAX_ATOMS 4
 
@@ -74,7 +75,7 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 in, f32 accumulate (kind::f16)
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 in, f32 accumulate (kind::f16)
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -111,48 +112,99 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---------------------------------------------------------------------------------------------------
 // operand preparation
 // ---------------------------------------------------------------------------------------------------
-// column sums with whole rows read coalesced (a warp per row, lanes over the dimensions; a block per dimension read
-// x with a stride of one row: 16x the bytes, 0.15 ms on C3), then mean = sum / n.  The order of the atomic adds
-// is not fixed; the mean only centres the data (any centre gives the same neighbour sets: the filter's band is
-// derived from the centred norms and every borderline pair is decided in f64 on the original coordinates).
+// Column sums, minima and maxima with whole rows read coalesced (a warp per row, lanes over the dimensions).  The
+// order of the atomic adds is not fixed; the mean only centres the data (any centre gives the same neighbour sets:
+// the filter's band is derived from the centred norms and every borderline pair is decided in f64 on the original
+// coordinates).  Minima / maxima travel as order-preserving 64-bit codes so that atomicMin / atomicMax apply.
 #define CM_MAXD 128
+__device__ __forceinline__ unsigned long long f64_code(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_decode(unsigned long long c) {
+    return __longlong_as_double((long long)((c >> 63) ? (c & 0x7fffffffffffffffull) : ~c));
+}
+
 __global__ void __launch_bounds__(256)
-col_sum_kernel(const double *__restrict__ x, ll n, int d, double *sum) {
+col_sum_kernel(const double *__restrict__ x, ll n, int d, double *sum, unsigned long long *mm /*[2][CM_MAXD]*/) {
     __shared__ double sh[8][CM_MAXD];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double acc[CM_MAXD / 32] = {0.0, 0.0, 0.0, 0.0};
+    double lo[CM_MAXD / 32], hi[CM_MAXD / 32];
+#pragma unroll
+    for (int u = 0; u < CM_MAXD / 32; ++u) { lo[u] = INFINITY; hi[u] = -INFINITY; }
     const ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5, nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
     for (ll i = warp; i < n; i += nwarps)
 #pragma unroll
         for (int u = 0; u < CM_MAXD / 32; ++u)
-            if (lane + 32 * u < d) acc[u] += x[i * d + lane + 32 * u];
+            if (lane + 32 * u < d) {
+                const double v = x[i * d + lane + 32 * u];
+                acc[u] += v;
+                lo[u] = fmin(lo[u], v);
+                hi[u] = fmax(hi[u], v);
+            }
+    for (int pass = 0; pass < 3; ++pass) {
+        __syncthreads();
 #pragma unroll
-    for (int u = 0; u < CM_MAXD / 32; ++u) sh[w][lane + 32 * u] = acc[u];
-    __syncthreads();
-    if ((int)threadIdx.x < d) {
-        double t = 0.0;
-        for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
-        atomicAdd(sum + threadIdx.x, t);
+        for (int u = 0; u < CM_MAXD / 32; ++u) sh[w][lane + 32 * u] = pass == 0 ? acc[u] : pass == 1 ? lo[u] : hi[u];
+        __syncthreads();
+        if ((int)threadIdx.x < d) {
+            double t = sh[0][threadIdx.x];
+            for (int k = 1; k < 8; ++k) {
+                const double o = sh[k][threadIdx.x];
+                t = pass == 0 ? t + o : pass == 1 ? fmin(t, o) : fmax(t, o);
+            }
+            if (pass == 0) atomicAdd(sum + threadIdx.x, t);
+            else if (pass == 1) atomicMin(mm + threadIdx.x, f64_code(t));
+            else atomicMax(mm + CM_MAXD + threadIdx.x, f64_code(t));
+        }
     }
 }
 
-__global__ void col_mean_kernel(double *mean, int d, ll n) {
-    if ((int)threadIdx.x < d) mean[threadIdx.x] /= (double)n;
+// mean[k] = sum[k] / n and the power of two that brings the largest centred coordinate into (2^13, 2^14]: fp16 keeps
+// 11 significant bits down to 2^-14, so after the scaling every coordinate within 2^-27 of the largest one still
+// splits into two normal halves (smaller ones lose relative, not absolute, precision: DESIGN.md)
+__global__ void col_mean_kernel(double *mean, const unsigned long long *mm, int d, ll n, int *scale_e) {
+    __shared__ double dev[CM_MAXD];
+    double v = 0.0;
+    if ((int)threadIdx.x < d) {
+        const double m = mean[threadIdx.x] / (double)n;
+        mean[threadIdx.x] = m;
+        v = fmax(f64_decode(mm[CM_MAXD + threadIdx.x]) - m, m - f64_decode(mm[threadIdx.x]));
+    }
+    dev[threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mx = 0.0;
+        for (int k = 0; k < d; ++k) mx = fmax(mx, dev[k]);
+        int e = 0;
+        if (mx > 0.0 && isfinite(mx)) {
+            int ex;
+            frexp(mx, &ex);  // mx = f * 2^ex, 0.5 <= f < 1
+            e = 14 - ex;
+        }
+        *scale_e = e;
+    }
 }
 
-// A'[i] = [hi | hi | lo | 0..], B'[i] = [hi | lo | hi | 0..] (bf16, row length kt), norm[i] = |x_i - mean|^2;
-// padding rows (i >= n) are zero with an infinite norm so that they never come near the cutoff.
-// One warp per row: lanes stride over the dimensions, so the f64 row comes in as one coalesced read and every bf16
-// segment goes out as contiguous 2-byte stores (a thread per row wrote 2 bytes at a stride of one row: 1.1 ms on C3).
+// X = 2^e (x - mean) split into two fp16 parts, X = hi + lo + delta with |lo| <= 2^-11 |X|, |delta| <= 2^-22 |X|
+// (+ 2^-25 absolute where a part is subnormal).  A'[i] = [lo | hi | hi | 0..], B'[i] = [hi | lo | hi | 0..] (row
+// length kt): the MMA chain over the concatenated K axis accumulates lo.hi + hi.lo FIRST, while the accumulator is
+// still 2^-10 of its final size, and hi.hi last -- the roundings of the fp32 accumulation scale with what is being
+// added to.  norm[i] = |X_i|^2 (f64 sum, rounded once); padding rows (i >= n) are zero with an infinite norm so
+// that they never come near the cutoff.
+// One warp per row: lanes stride over the dimensions, so the f64 row comes in as one coalesced read and every fp16
+// segment goes out as contiguous 2-byte stores.
 __global__ void __launch_bounds__(256)
-split_kernel(const double *__restrict__ x, const double *__restrict__ mean, ll n, ll n_pad, int d,
-             int kt, __nv_bfloat16 *A, __nv_bfloat16 *B, float *norm, int *maxnorm_bits) {
+split_kernel(const double *__restrict__ x, const double *__restrict__ mean, const int *__restrict__ scale_e, ll n,
+             ll n_pad, int d, int kt, __half *A, __half *B, float *norm, int *maxnorm_bits) {
     const int lane = threadIdx.x & 31;
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
-    const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+    const __half zero = __float2half_rn(0.f);
+    const int e = *scale_e;
     for (ll i = warp; i < n_pad; i += nwarps) {
-        __nv_bfloat16 *a = A + i * kt, *b = B + i * kt;
+        __half *a = A + i * kt, *b = B + i * kt;
         if (i >= n) {
             for (int k = lane; k < kt; k += 32) { a[k] = zero; b[k] = zero; }
             if (lane == 0) norm[i] = INFINITY;
@@ -160,11 +212,11 @@ split_kernel(const double *__restrict__ x, const double *__restrict__ mean, ll n
         }
         double s = 0;
         for (int k = lane; k < d; k += 32) {
-            const double xc = x[i * d + k] - mean[k];
-            s += xc * xc;
-            const __nv_bfloat16 hi = __float2bfloat16_rn((float)xc);
-            const __nv_bfloat16 lo = __float2bfloat16_rn((float)(xc - (double)__bfloat162float(hi)));
-            a[k] = hi; a[d + k] = hi; a[2 * d + k] = lo;
+            const double X = scalbn(x[i * d + k] - mean[k], e);
+            s += X * X;
+            const __half hi = __double2half(X);
+            const __half lo = __double2half(X - (double)__half2float(hi));
+            a[k] = lo; a[d + k] = hi; a[2 * d + k] = hi;
             b[k] = hi; b[d + k] = lo; b[2 * d + k] = hi;
         }
         for (int k = 3 * d + lane; k < kt; k += 32) { a[k] = zero; b[k] = zero; }
@@ -172,24 +224,26 @@ split_kernel(const double *__restrict__ x, const double *__restrict__ mean, ll n
         if (lane == 0) {
             const float sf = (float)s;
             norm[i] = sf;
-            atomicMax(maxnorm_bits, __float_as_int(sf));
+            atomicMax(maxnorm_bits, __float_as_int(sf));  // NaN sorts above +inf: caught by the set-up kernel
         }
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// exact f64 distance, the reference's expression (_types.pyx:2253-2267)
-// ---------------------------------------------------------------------------------------------------
-template <bool SQRT>
-__device__ __noinline__ bool exact_within(const double *__restrict__ x, int d, ll i, ll j, double rc) {
-    const double *a = x + i * d, *b = x + j * d;
-    double s = 0.0;
-    for (int k = 0; k < d; ++k) {
-        double t = __dsub_rn(a[k], b[k]);
-        s = __dadd_rn(s, __dmul_rn(t, t));
-    }
-    if (SQRT) s = __dsqrt_rn(s);
-    return s <= rc;
+// thresholds of the filter in the scaled units of the operands: thr[0] = R_s - eps, thr[1] = R_s + eps (rounded
+// away from R_s, clamped to finite values so that an infinite column norm never meets an infinite threshold)
+__global__ void tensor_setup_kernel(const int *maxnorm_bits, const int *scale_e, double R, double coef, float *thr, int *bad) {
+    const float mf = __int_as_float(*maxnorm_bits);
+    if (!isfinite(mf)) { *bad = 1; thr[0] = -INFINITY; thr[1] = -INFINITY; return; }
+    *bad = 0;
+    const double M = (double)mf * (1.0 + ldexp(1.0, -20));
+    const double Rs = scalbn(R, 2 * *scale_e);
+    const double eps = M * coef + Rs * ldexp(1.0, -22) + 1e-300;
+    float lo = (float)(Rs - eps), hi = (float)(Rs + eps);
+    lo = nextafterf(lo, -INFINITY);
+    hi = nextafterf(hi, INFINITY);
+    const float big = 3.0e38f;
+    thr[0] = fminf(fmaxf(lo, -big), big);
+    thr[1] = fminf(fmaxf(hi, -big), big);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -350,45 +404,75 @@ struct TileIter {
 // ---------------------------------------------------------------------------------------------------
 #define NSB 3   // barrier slots reserved for the shared-memory stages of the B operand (2 are used; 1 for 4-atom tiles)
 #define NST 4   // TMEM accumulator stages of 128 columns (MMA <-> epilogue): the whole 512-column TMEM
-#ifndef CNN_EPI_WARPS
-#define CNN_EPI_WARPS 8   // measured r2 on C3: 16 warps 3.64 ms, 8 warps 3.48 ms
-#endif
-#define EPI_WARPS CNN_EPI_WARPS  // epilogue warps: 8 = one per (row tile, TMEM lane quarter), all 128 columns each;
-                                 // 16 = two per (row tile, lane quarter), 64 columns each (more warps to hide the
-                                 // tcgen05.ld / shared-memory latency of an epilogue that, not the MMA, bounds the kernel)
-#define PAIR_BUF (128 / EPI_WARPS)  // pairs a thread collects before it reserves space in the global list
+#define EPI_WARPS 8   // epilogue warps: one per (row tile, TMEM lane quarter), all 128 columns each
 #define NUM_THREADS ((2 + EPI_WARPS) * 32)
 #define BAND_FLAG 0x80000000u
+#define SLAB_POOL 16  // slab slots a warp reserves at a time
 
+// Output of the tile pass: hit BITMAPS.  The unit is a *slab*: the 32 rows of one TMEM lane quarter (row quarter
+// g = 4 I + q of row tile I) against the 128 columns of column tile J, one uint4 per row (bit c of word w = column
+// 32 w + c), 512 bytes written by one warp with one coalesced store.  Only slabs that hold a hit exist; they are
+// found through two directories, dir[g][J] and its transpose dirT[J][g] (slot + 1, bit 31 = the slab has
+// borderline pairs, whose bits sit in the parallel array bslabs).  Bits are kept for i < j only.
+// Everything downstream is positional: the row of i is {bits of column i in the slabs above it} (ascending row
+// quarters: ascending j < i), i itself, {bits of row i} (ascending column tiles) -- no pair list, no sort.
 struct TensorParams {
-    const float *norm;    // [n_pad]
+    const float *norm;    // [n_pad] |X|^2 in the scaled units of the operands
+    const float *thr;     // device: {R_s - eps, R_s + eps}
     ll n, n_tiles;
     int atoms, nsb;
-    float r2_lo, r2_hi;   // R - eps, R + eps in squared-distance units
     const unsigned *skip; // [n_tiles][words] tile pairs that cannot hold a neighbour pair (nullptr: visit all)
     int words;
-    int2 *pairs;          // out: (i, j) with i < j; j carries BAND_FLAG when the pair is inside the +-eps band
-    unsigned long long *pair_count;  // running length of `pairs` (may exceed pair_cap: then nothing is stored)
-    ll pair_cap;
+    uint4 *slabs, *bslabs;      // [slab_cap][32]
+    unsigned *dir, *dirT;       // [4 n_tiles][n_tiles], [n_tiles][4 n_tiles]
+    unsigned *slab_count;       // slots handed out (may exceed slab_cap: then the pass is repeated)
+    unsigned slab_cap;
 };
+
+// 32 accumulator elements of one row against their column norms.  w = |X_j|^2 - 2 X_i.X_j is formed in place and its
+// minimum tracked (1.5 instructions per element); only when some row of the warp comes within reach of the cutoff are
+// the two sign masks collected (4 more): bit c of mh <=> w_c <= thr_hi (neighbour or borderline), of ml <=> w_c <=
+// thr_lo (neighbour for certain).  Two independent shift chains per mask.
+__device__ __forceinline__ void classify32(float (&v)[32], const float *nc, float thr_hi, float thr_lo, unsigned &mh,
+                                           unsigned &ml) {
+    float mn = INFINITY;
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 n4 = reinterpret_cast<const float4 *>(nc)[c4];
+        v[4 * c4 + 0] = fmaf(-2.f, v[4 * c4 + 0], n4.x);
+        v[4 * c4 + 1] = fmaf(-2.f, v[4 * c4 + 1], n4.y);
+        v[4 * c4 + 2] = fmaf(-2.f, v[4 * c4 + 2], n4.z);
+        v[4 * c4 + 3] = fmaf(-2.f, v[4 * c4 + 3], n4.w);
+        mn = fminf(mn, fminf(v[4 * c4 + 0], v[4 * c4 + 1]));
+        mn = fminf(mn, fminf(v[4 * c4 + 2], v[4 * c4 + 3]));
+    }
+    mh = 0;
+    ml = 0;
+    if (__any_sync(0xffffffffu, mn <= thr_hi)) {
+        unsigned ha = 0, hb = 0, la = 0, lb = 0;  // sign bit set <=> w > thr
+#pragma unroll
+        for (int k = 15; k >= 0; --k) {
+            ha = __funnelshift_l(__float_as_uint(thr_hi - v[16 + k]), ha, 1);
+            hb = __funnelshift_l(__float_as_uint(thr_hi - v[k]), hb, 1);
+            la = __funnelshift_l(__float_as_uint(thr_lo - v[16 + k]), la, 1);
+            lb = __funnelshift_l(__float_as_uint(thr_lo - v[k]), lb, 1);
+        }
+        mh = ~((ha << 16) | hb);
+        ml = ~((la << 16) | lb);
+    }
+}
 
 // SINGLE pass over the upper triangle of the tile grid.  CTA c owns the TWO adjacent row tiles 2c and 2c+1 (256 rows,
 // both A tiles stay in shared memory) and walks the column tiles J >= 2c: every B tile that comes in by TMA feeds two
-// MMA groups, which halves the L2 -> shared-memory traffic per flop (a 128-row CTA needs ~12 TB/s of B tiles to keep
-// the tensor pipe busy at K = 192).  CTAs are launched in order of decreasing work.
-// The epilogue (warps 2-5: row tile 2c, warps 6-9: row tile 2c+1, one TMEM lane quarter each) classifies every
-// accumulator element -- d2~ <= R - eps: neighbours, d2~ > R + eps: not, otherwise borderline -- and only EMITS pairs
-// (i < j) into a global list (per-thread buffers of PAIR_BUF pairs, one atomic per flush).  Borderline pairs are
-// decided afterwards by pair_resolve_kernel with the reference's own f64 expression, fully parallel, instead of
-// stalling an epilogue warp (and, through it, the MMA pipeline) for ~1 us each; degrees, row offsets and the two
-// directed entries of every pair follow from the list, and one radix sort puts everything in CSR order.  Nothing
-// depends on the order in which tiles are visited.
+// MMA groups, which halves the L2 -> shared-memory traffic per flop.  CTAs are launched in order of decreasing work.
+// Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocation, warps 2-5 = epilogue of row tile 2c, warps 6-9 of row
+// tile 2c+1 (one TMEM lane quarter each).  Nothing depends on the order in which tiles are visited.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+tensor_tiles_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const TensorParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: 2 A tiles | nsb B stages | barriers | tmem slot | per-warp column norms | per-thread pair buffers
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // carve: 2 A tiles | nsb B stages | barriers | tmem slot | per-warp column norms
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the address space
     const int atoms = P.atoms, nsb = P.nsb;
     const uint32_t tile_bytes = (uint32_t)atoms * ATOM_BYTES;
     uint8_t *sA = smem;
@@ -397,7 +481,6 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     uint64_t *a_full = bars, *full = bars + 2, *empty = full + NSB, *t_full = empty + NSB, *t_empty = t_full + NST;
     uint32_t *tmem_slot = (uint32_t *)(t_empty + NST);
     float *ncs = (float *)(bars + 20);                  // [EPI_WARPS][2][TT], 16-byte aligned
-    int *pbuf = (int *)(ncs + EPI_WARPS * 2 * TT);      // [EPI_WARPS * 32][PAIR_BUF]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const ll n_tiles = P.n_tiles;
@@ -406,7 +489,7 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (warp == 0 && lane == 0) {
         mbar_init(a_full, 1);
         for (int s = 0; s < nsb; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < NST; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 16 * EPI_WARPS); }
+        for (int s = 0; s < NST; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -440,8 +523,8 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            // instruction descriptor: D f32, A/B bf16, both K-major, N = 128, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(TT >> 4) << 24);
+            // instruction descriptor: D f32, A/B fp16 (format 0), both K-major, N = 128, M = 128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(TT >> 4) << 24);
             const uint32_t a_addr = smem_u32(sA);
             mbar_wait(a_full, 0);
             ll t = 0;
@@ -451,14 +534,14 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 const int s = (int)(t % nsb);
                 mbar_wait(full + s, (uint32_t)((t / nsb) & 1));          // TMA has landed this B tile
                 const uint32_t b_addr = smem_u32(sB + s * tile_bytes);
-                // the tile (I0 + 1, I0) below the diagonal is computed too (its pairs are dropped by the epilogue):
+                // the tile (I0 + 1, I0) below the diagonal is computed too (its bits are dropped by the epilogue):
                 // every accumulator stage is then used on every second step and the phases stay in lock step
                 for (int rt = 0; rt < 2; ++rt) {
                     const int ts = (int)((t & 1) << 1) | rt;
                     mbar_wait(t_empty + ts, (uint32_t)((t >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)ts * TT;
-                    for (int k = 0; k < atoms * 4; ++k) {  // UMMA K = 16 bf16 = 32 bytes inside the swizzle atom
+                    for (int k = 0; k < atoms * 4; ++k) {  // UMMA K = 16 halves = 32 bytes inside the swizzle atom
                         const uint32_t off = (uint32_t)(k >> 2) * ATOM_BYTES + (uint32_t)(k & 3) * 32;
                         tc_mma(d_tmem, umma_desc(a_addr + rt * tile_bytes + off), umma_desc(b_addr + off), idesc, k > 0);
                     }
@@ -468,26 +551,21 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> classify -> emit pairs =====
+        // ===== epilogue: TMEM -> registers -> classify -> hit bitmaps =====
+        const unsigned fullm = 0xffffffffu;
         const int ew = warp - 2;             // 0 .. EPI_WARPS-1
         const int q = warp & 3;              // TMEM lane quarter this warp may access
         const int rt = (ew >> 2) & 1;        // which of the CTA's two row tiles
-        const int ch = ew >> 3;              // 16 epilogue warps: which 64 columns of the tile (0 with 8 warps)
         const int row = q * 32 + lane;       // accumulator row = TMEM lane
         float *ncw = ncs + ew * 2 * TT;
-        int *mybuf = pbuf + (ew * 32 + lane) * PAIR_BUF;
-        int n_buf = 0;
-        const ll gi = (I0 + rt) * TT + row;
+        const ll It = I0 + rt;
+        const ll gi = It * TT + row;
+        const ll g = It * 4 + q;             // row quarter
         const bool live = gi < P.n;
         const float nr = live ? P.norm[gi] : 0.f;
         // d2~ = nr + nc - 2 acc <= thr   <=>   w = nc - 2 acc <= thr - nr ; dead rows never pass
-        const float thr_hi = live ? P.r2_hi - nr : -INFINITY, thr_lo = live ? P.r2_lo - nr : -INFINITY;
-        auto flush = [&]() {
-            const ll pos = (ll)atomicAdd(P.pair_count, (unsigned long long)n_buf);
-            if (pos + n_buf <= P.pair_cap)
-                for (int k = 0; k < n_buf; ++k) P.pairs[pos + k] = make_int2((int)gi, mybuf[k]);
-            n_buf = 0;
-        };
+        const float thr_hi = live ? P.thr[1] - nr : -INFINITY, thr_lo = live ? P.thr[0] - nr : -INFINITY;
+        unsigned pool_next = 0, pool_end = 0;
         TileIter it;
         it.init(P.skip, I0, n_tiles, P.words);
         ll j = it.next();
@@ -503,46 +581,52 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             mbar_wait(t_full + ts, (uint32_t)((t >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * TT);
+            unsigned hi[4], lo[4];
 #pragma unroll
-            for (int hp = EPI_WARPS == 16 ? ch : 0; hp < (EPI_WARPS == 16 ? ch + 1 : 2); ++hp) {  // 64 columns at a time: two tcgen05.ld in flight
+            for (int hp = 0; hp < 2; ++hp) {  // 64 columns at a time: two tcgen05.ld in flight
                 float va[32], vb[32];
                 tmem_ld32(taddr + hp * 64, va);
                 tmem_ld32(taddr + hp * 64 + 32, vb);
                 tmem_ld_wait();
-                if (EPI_WARPS == 16 || hp == 1) {  // this warp's part of the accumulator stage is in registers: hand it back
+                if (hp == 1) {  // this warp's part of the accumulator stage is in registers: hand it back
                     tc_fence_before();
                     mbar_arrive(t_empty + ts);
                 }
+                classify32(va, nc + hp * 64, thr_hi, thr_lo, hi[2 * hp], lo[2 * hp]);
+                classify32(vb, nc + hp * 64 + 32, thr_hi, thr_lo, hi[2 * hp + 1], lo[2 * hp + 1]);
+            }
+            if (j <= It) {  // diagonal tile: only columns above the row are kept; the tile below the diagonal: nothing
 #pragma unroll
-                for (int chunk = 0; chunk < 2; ++chunk) {
-                    const float *cur = chunk ? vb : va;
-                    const int cbase = hp * 64 + chunk * 32;
-                    // two bit masks per lane, element c at bit 31 - c: funnel-shift the sign of (thr - w) in
-                    unsigned m_hi = 0, m_lo = 0;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float w = fmaf(-2.f, cur[c], nc[cbase + c]);
-                        m_hi = __funnelshift_l(__float_as_uint(thr_hi - w), m_hi, 1);
-                        m_lo = __funnelshift_l(__float_as_uint(thr_lo - w), m_lo, 1);
-                    }
-                    m_hi = ~m_hi;  // bit set <=> w <= thr (the difference is never NaN: norms are finite or +inf)
-                    m_lo = ~m_lo;
-                    if (!live) m_hi = 0;
-                    const int col0 = (int)(j * TT) + cbase;
-                    while (m_hi) {
-                        const int c = __clz(m_hi);
-                        const unsigned bit = 0x80000000u >> c;
-                        m_hi &= ~bit;
-                        const int gj = col0 + c;
-                        if (gj <= (int)gi) continue;  // diagonal and sub-diagonal tiles: only j > i is emitted
-                        mybuf[n_buf++] = (m_lo & bit) ? gj : (int)((unsigned)gj | BAND_FLAG);
-                        if (n_buf == PAIR_BUF) flush();
+                for (int w = 0; w < 4; ++w) {
+                    unsigned keep = 0;
+                    if (j == It) keep = w < q ? 0u : (w > q ? 0xffffffffu : (lane == 31 ? 0u : (0xfffffffeu << lane)));
+                    hi[w] &= keep;
+                    lo[w] &= keep;
+                }
+            }
+            const unsigned any = hi[0] | hi[1] | hi[2] | hi[3];
+            if (__any_sync(fullm, any != 0)) {
+                if (pool_next == pool_end) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(P.slab_count, (unsigned)SLAB_POOL);
+                    pool_next = __shfl_sync(fullm, base, 0);
+                    pool_end = pool_next + SLAB_POOL;
+                }
+                const unsigned slot = pool_next++;
+                if (slot < P.slab_cap) {
+                    const uint4 bd = make_uint4(hi[0] & ~lo[0], hi[1] & ~lo[1], hi[2] & ~lo[2], hi[3] & ~lo[3]);
+                    const bool band = __any_sync(fullm, (bd.x | bd.y | bd.z | bd.w) != 0);
+                    P.slabs[(size_t)slot * 32 + lane] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    if (band) P.bslabs[(size_t)slot * 32 + lane] = bd;
+                    if (lane == 0) {
+                        const unsigned v = (slot + 1) | (band ? BAND_FLAG : 0u);
+                        P.dir[g * n_tiles + j] = v;
+                        P.dirT[j * (4 * n_tiles) + g] = v;
                     }
                 }
             }
             j = j_next;
         }
-        if (n_buf) flush();
     }
     tc_fence_before();
     __syncthreads();
@@ -551,107 +635,194 @@ tensor_pairs_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
 }
 
-// borderline pairs are decided exactly (rejected ones get i = -1 and are counted: the degrees and row offsets follow
-// from the sorted keys afterwards -- two atomics per pair on the degree array cost more than the whole exact test).
-// Only ~1 pair in 6 of the list is borderline, so a thread per pair would run the 2 x d-element row walk with a few
-// live lanes per warp and fetch every 32-byte sector for 8 of its bytes.  Instead the warp collects its borderline
-// pairs by ballot and evaluates them four at a time, 8 lanes per pair: a lane loads 8 consecutive coordinates of both
-// rows (whole sectors) and forms its 8 squared differences; the sum is then accumulated in the reference's order
-// (_types.pyx:2253-2267: left to right, no FMA) by passing the running value from lane to lane of the group.
+// ---------------------------------------------------------------------------------------------------
+// borderline pairs, decided with the reference's own f64 expression (_types.pyx:2253-2267)
+// ---------------------------------------------------------------------------------------------------
+// A warp takes 32 consecutive directory entries and, for every slab flagged as holding borderline pairs, one row per
+// lane: each lane pops the lowest borderline bit of its row, the warp evaluates the pending pairs four at a time, 8
+// lanes per pair -- a lane loads 8 consecutive coordinates of both rows (whole sectors) and forms its 8 squared
+// differences; the sum is then accumulated in the reference's order (left to right, no FMA) by passing the running
+// value from lane to lane of the group.  A rejected pair loses its bit in the hit slab; the lane owns its row, so
+// the slab is rewritten with plain stores.
 template <bool SQRT>
 __global__ void __launch_bounds__(256)
-pair_resolve_kernel(const double *__restrict__ x, int d, int2 *__restrict__ pairs, ll count, double rc,
-                    unsigned long long *n_band, unsigned long long *n_rejected) {
+tile_resolve_kernel(const double *__restrict__ x, int d, const unsigned *__restrict__ dir, ll n_entries, ll n_tiles,
+                    uint4 *slabs, const uint4 *__restrict__ bslabs, double rc, unsigned long long *n_band,
+                    unsigned long long *n_rejected) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int g = lane >> 3, gl = lane & 7;
-    const ll k = blockIdx.x * (ll)blockDim.x + threadIdx.x;
-    int2 pr = make_int2(-1, -1);
-    bool band = false;
-    if (k < count) {
-        pr = pairs[k];
-        band = ((unsigned)pr.y & BAND_FLAG) != 0;
-        pr.y = (int)((unsigned)pr.y & ~BAND_FLAG);
-    }
-    unsigned todo = __ballot_sync(full, band);
-    if (lane == 0 && todo) atomicAdd(n_band, (unsigned long long)__popc(todo));
-    bool ok = k < count;
-    while (todo) {
-        int src[4];
+    const int grp = lane >> 3, gl = lane & 7;
+    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    unsigned long long my_band = 0, my_rej = 0;
+    for (ll e0 = ((blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5) * 32; e0 < n_entries; e0 += nwarps * 32) {
+        const ll e = e0 + lane;
+        const unsigned v = e < n_entries ? dir[e] : 0u;
+        unsigned need = __ballot_sync(full, (v & BAND_FLAG) != 0);
+        while (need) {
+            const int b = __ffs(need) - 1;
+            need &= need - 1;
+            const unsigned slot = (__shfl_sync(full, v, b) & ~BAND_FLAG) - 1u;
+            const ll ee = e0 + b;
+            const ll g = ee / n_tiles, J = ee - g * n_tiles;
+            const ll pi_mine = g * 32 + lane;
+            uint4 bd = bslabs[(size_t)slot * 32 + lane];
+            uint4 rj = make_uint4(0u, 0u, 0u, 0u);
+            my_band += __popc(bd.x) + __popc(bd.y) + __popc(bd.z) + __popc(bd.w);
+            for (;;) {
+                // this lane's next pending pair
+                int w = -1, bit = 0;
+                if (bd.x) { w = 0; bit = __ffs(bd.x) - 1; bd.x &= bd.x - 1; }
+                else if (bd.y) { w = 1; bit = __ffs(bd.y) - 1; bd.y &= bd.y - 1; }
+                else if (bd.z) { w = 2; bit = __ffs(bd.z) - 1; bd.z &= bd.z - 1; }
+                else if (bd.w) { w = 3; bit = __ffs(bd.w) - 1; bd.w &= bd.w - 1; }
+                unsigned todo = __ballot_sync(full, w >= 0);
+                if (!todo) break;
+                const ll pj_mine = J * TT + 32 * w + bit;
+                bool ok = true;
+                while (todo) {
+                    int src[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            src[q] = todo ? __ffs(todo) - 1 : -1;
-            todo &= todo - 1;  // no-op at 0
-        }
-        const int mine = g == 0 ? src[0] : g == 1 ? src[1] : g == 2 ? src[2] : src[3];
-        const int from = mine < 0 ? 0 : mine;
-        const ll pi = __shfl_sync(full, pr.x, from), pj = __shfl_sync(full, pr.y, from);
-        const double *a = x + pi * d, *b = x + pj * d;
-        double sum = 0.0;
-        for (int k0 = 0; k0 < d; k0 += 64) {
-            double t[8];
+                    for (int k = 0; k < 4; ++k) {
+                        src[k] = todo ? __ffs(todo) - 1 : -1;
+                        todo &= todo - 1;  // no-op at 0
+                    }
+                    const int mine = grp == 0 ? src[0] : grp == 1 ? src[1] : grp == 2 ? src[2] : src[3];
+                    const int from = mine < 0 ? 0 : mine;
+                    const ll pi = __shfl_sync(full, pi_mine, from), pj = __shfl_sync(full, pj_mine, from);
+                    const double *a = x + pi * d, *bb = x + pj * d;
+                    double sum = 0.0;
+                    for (int k0 = 0; k0 < d; k0 += 64) {
+                        double t[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int kk = k0 + gl * 8 + u;
-                double df = 0.0;
-                if (mine >= 0 && kk < d) df = __dsub_rn(a[kk], b[kk]);
-                t[u] = __dmul_rn(df, df);  // +0.0 past the end: adding it changes nothing
-            }
+                        for (int u = 0; u < 8; ++u) {
+                            const int kk = k0 + gl * 8 + u;
+                            double df = 0.0;
+                            if (mine >= 0 && kk < d) df = __dsub_rn(a[kk], bb[kk]);
+                            t[u] = __dmul_rn(df, df);  // +0.0 past the end: adding it changes nothing
+                        }
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                if (gl == r) {
+                        for (int r = 0; r < 8; ++r) {
+                            if (gl == r) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) sum = __dadd_rn(sum, t[u]);
+                                for (int u = 0; u < 8; ++u) sum = __dadd_rn(sum, t[u]);
+                            }
+                            sum = __shfl_sync(full, sum, (lane & ~7) | r);
+                        }
+                    }
+                    if (SQRT) sum = __dsqrt_rn(sum);
+                    const bool within = sum <= rc;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const bool wq = __shfl_sync(full, within, k * 8);
+                        if (lane == src[k]) ok = wq;
+                    }
                 }
-                sum = __shfl_sync(full, sum, (lane & ~7) | r);
+                if (w >= 0 && !ok) {
+                    const unsigned m = 1u << bit;
+                    if (w == 0) rj.x |= m; else if (w == 1) rj.y |= m; else if (w == 2) rj.z |= m; else rj.w |= m;
+                    ++my_rej;
+                }
+            }
+            if (rj.x | rj.y | rj.z | rj.w) {
+                uint4 h = slabs[(size_t)slot * 32 + lane];
+                h.x &= ~rj.x; h.y &= ~rj.y; h.z &= ~rj.z; h.w &= ~rj.w;
+                slabs[(size_t)slot * 32 + lane] = h;
             }
         }
-        if (SQRT) sum = __dsqrt_rn(sum);
-        const bool within = sum <= rc;
+    }
+    for (int o = 16; o; o >>= 1) {
+        my_band += __shfl_xor_sync(full, my_band, o);
+        my_rej += __shfl_xor_sync(full, my_rej, o);
+    }
+    if (lane == 0 && my_band) atomicAdd(n_band, my_band);
+    if (lane == 0 && my_rej) atomicAdd(n_rejected, my_rej);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bitmaps -> CSR
+// ---------------------------------------------------------------------------------------------------
+// lane l holds row l of a 32 x 32 bit block (bit c = column c); afterwards lane c holds column c (bit l = row l)
+__device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
+    const unsigned full = 0xffffffffu;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const bool wq = __shfl_sync(full, within, q * 8);
-            if (lane == src[q]) ok = wq;
+    for (int k = 16; k; k >>= 1) {
+        // m: bits whose index has bit k clear
+        const unsigned m = k == 16 ? 0x0000ffffu : k == 8 ? 0x00ff00ffu : k == 4 ? 0x0f0f0f0fu : k == 2 ? 0x33333333u : 0x55555555u;
+        const unsigned y = __shfl_xor_sync(full, x, k);
+        x = (lane & k) ? ((x & ~m) | ((y & ~m) >> k)) : ((x & m) | ((y & m) << k));
+    }
+    return x;
+}
+
+// One CTA per row tile T, one warp per row quarter, one row per lane.  FILL = false: degrees; true: the rows, written
+// in ascending order: entries below the diagonal from the columns of the slabs above (dirT[T][.], row quarters
+// ascending), the row itself, entries above the diagonal from the row's own slabs (dir[g][.], column tiles ascending).
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+tile_rows_kernel(const unsigned *__restrict__ dir, const unsigned *__restrict__ dirT, const uint4 *__restrict__ slabs,
+                 ll n, ll n_tiles, int *__restrict__ deg, const ll *__restrict__ row_ptr, int *__restrict__ col_idx) {
+    const unsigned full = 0xffffffffu;
+    const ll T = blockIdx.x;
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ll g = T * 4 + q, r = g * 32 + lane, G = 4 * n_tiles;
+    int cnt = 0;
+    int *out = nullptr;
+    if (FILL && r < n) out = col_idx + row_ptr[r];
+    const unsigned *dt = dirT + T * G;
+    for (ll g0 = 0; g0 <= g; g0 += 32) {
+        const ll gp = g0 + lane;
+        const unsigned v = gp <= g ? dt[gp] : 0u;
+        unsigned nz = __ballot_sync(full, v != 0u);
+        while (nz) {
+            const int b = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const unsigned slot = (__shfl_sync(full, v, b) & ~BAND_FLAG) - 1u;
+            unsigned xw = reinterpret_cast<const unsigned *>(slabs + (size_t)slot * 32 + lane)[q];
+            xw = transpose32(xw, lane);  // bit l: row l of quarter g0 + b has column r
+            if (FILL) {
+                const int base = (int)((g0 + b) * 32);
+                while (xw) {
+                    const int bit = __ffs(xw) - 1;
+                    xw &= xw - 1;
+                    out[cnt++] = base + bit;
+                }
+            } else {
+                cnt += __popc(xw);
+            }
         }
     }
-    if (band) pairs[k] = ok ? pr : make_int2(-1, -1);
-    const unsigned rej = __ballot_sync(full, band && !ok);
-    if (lane == 0 && rej) atomicAdd(n_rejected, (unsigned long long)__popc(rej));
-}
-
-// Both directed entries of every surviving pair and the self entry of every row as keys (row << bits | column) with
-// 2^bits > n; rejected pairs get row n and sort behind everything.  After one radix sort over 2 * bits key bits (5
-// passes instead of 7 for N = 2*10^5) the low parts of the first nnz keys ARE col_idx (rows ascending, columns
-// ascending within a row).
-__global__ void pair_keys_kernel(const int2 *__restrict__ pairs, ll count, ll n, int bits, unsigned long long *__restrict__ keys) {
-    ll k = blockIdx.x * (ll)blockDim.x + threadIdx.x;
-    if (k < n) keys[2 * count + k] = ((unsigned long long)k << bits) | (unsigned long long)k;
-    if (k >= count) return;
-    const int2 pr = pairs[k];
-    const bool ok = pr.x >= 0;
-    const unsigned long long dead = (unsigned long long)n << bits;
-    keys[2 * k] = ok ? ((unsigned long long)(unsigned)pr.x << bits) | (unsigned)pr.y : dead;
-    keys[2 * k + 1] = ok ? ((unsigned long long)(unsigned)pr.y << bits) | (unsigned)pr.x : dead;
-}
-
-// low words of the sorted keys = col_idx; the first key of every row gives row_ptr (every row holds its self entry,
-// so no row is empty)
-__global__ void keys_to_cols_kernel(const unsigned long long *__restrict__ keys, ll nnz, ll n, int bits,
-                                    int *__restrict__ col_idx, ll *__restrict__ row_ptr) {
-    ll k = blockIdx.x * (ll)blockDim.x + threadIdx.x;
-    if (k >= nnz) return;
-    const unsigned long long key = keys[k];
-    col_idx[k] = (int)(unsigned)(key & ((1ull << bits) - 1ull));
-    const unsigned row = (unsigned)(key >> bits);
-    if (k == 0 || row != (unsigned)(keys[k - 1] >> bits)) row_ptr[row] = k;
-    if (k == nnz - 1) row_ptr[n] = nnz;
-}
-
-__global__ void max_degree_kernel(const ll *__restrict__ row_ptr, ll n, int *out) {
-    ll r = blockIdx.x * (ll)blockDim.x + threadIdx.x;
-    int dg = r < n ? (int)(row_ptr[r + 1] - row_ptr[r]) : 0;
-    for (int o = 16; o; o >>= 1) dg = max(dg, __shfl_xor_sync(0xffffffffu, dg, o));
-    if ((threadIdx.x & 31) == 0 && dg) atomicMax(out, dg);
+    if (r < n) {
+        if (FILL) out[cnt] = (int)r;
+        ++cnt;
+    }
+    const unsigned *dr = dir + g * n_tiles;
+    for (ll J0 = T & ~31ll; J0 < n_tiles; J0 += 32) {
+        const ll J = J0 + lane;
+        const unsigned v = (J >= T && J < n_tiles) ? dr[J] : 0u;
+        unsigned nz = __ballot_sync(full, v != 0u);
+        while (nz) {
+            const int b = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const unsigned slot = (__shfl_sync(full, v, b) & ~BAND_FLAG) - 1u;
+            const uint4 m = slabs[(size_t)slot * 32 + lane];
+            if (FILL) {
+                const int base = (int)((J0 + b) * TT);
+                unsigned wds[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    unsigned xw = wds[w];
+                    while (xw) {
+                        const int bit = __ffs(xw) - 1;
+                        xw &= xw - 1;
+                        out[cnt++] = base + 32 * w + bit;
+                    }
+                }
+            } else {
+                cnt += __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);
+            }
+        }
+    }
+    if (!FILL && r <= n) deg[r] = r < n ? cnt : 0;  // deg[n] = 0: the scan then leaves nnz in row_ptr[n]
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -680,7 +851,7 @@ static int make_map(CUtensorMap *map, void *base, ll n_pad, int kt) {
     cuuint64_t strides[1] = {(cuuint64_t)kt * 2};
     cuuint32_t box[2] = {KATOM, TT};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) CNN_FAIL(CNNB200_E_CUDA, "tensor search: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -695,6 +866,8 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
                  MAX_ATOMS * KATOM / 3, (long long)d);
     const int kt = atoms * KATOM;
     const ll n_tiles = (n + TT - 1) / TT, n_pad = n_tiles * TT;
+    if (n_tiles > 16384)  // the two slab directories take 32 n_tiles^2 bytes
+        CNN_FAIL(CNNB200_E_RANGE, "tensor search serves up to %d points (got %lld); use the tiled method", 16384 * TT, (long long)n);
     const bool sq = metric == CNNB200_METRIC_EUCLIDEAN;
     const double R = sq ? radius_cutoff * radius_cutoff : radius_cutoff;
 
@@ -734,142 +907,127 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     }
 
     // ---- operands -----------------------------------------------------------------------------
-    CNN_TRY(cnn_ensure(ctx, ctx->b_xs, sizeof(__nv_bfloat16) * (size_t)n_pad * kt * 2));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_xs, sizeof(__half) * (size_t)n_pad * kt * 2));
     CNN_TRY(cnn_ensure(ctx, ctx->b_tmp1, sizeof(float) * (size_t)n_pad));
-    CNN_TRY(cnn_ensure(ctx, ctx->b_bbox, sizeof(double) * (size_t)(d + 2)));
-    CNN_TRY(cnn_ensure(ctx, ctx->b_deg, sizeof(int) * (size_t)(n + 1)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_bbox, sizeof(double) * (size_t)(CM_MAXD + 2 * CM_MAXD + 16)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_deg, sizeof(int) * (size_t)(n_pad + 1)));
     CNN_TRY(cnn_ensure(ctx, ctx->b_row_ptr, sizeof(ll) * (size_t)(n + 1)));
     CNN_TRY(cnn_ensure(ctx, ctx->b_stats, sizeof(unsigned long long) * ST_N));
-    __nv_bfloat16 *A = ctx->b_xs.as<__nv_bfloat16>(), *B = A + (size_t)n_pad * kt;
+    __half *A = ctx->b_xs.as<__half>(), *B = A + (size_t)n_pad * kt;
     float *norm = ctx->b_tmp1.as<float>();
     double *mean = ctx->b_bbox.as<double>();
-    int *maxbits = (int *)(mean + d);
+    unsigned long long *mm = (unsigned long long *)(mean + CM_MAXD);  // [2][CM_MAXD] codes of the column minima / maxima
+    int *maxbits = (int *)(mm + 2 * CM_MAXD);
+    int *scale_e = maxbits + 1, *bad = maxbits + 2;
+    float *thr = (float *)(maxbits + 4);
+    unsigned *slab_count = (unsigned *)(maxbits + 6);
+    unsigned long long *band_count = (unsigned long long *)(maxbits + 8), *rej_count = band_count + 1;
+
+    // |d2~ - d2| in units of the largest squared norm M ("Exactness of the tensor-core filter"):
+    //   6.1 * 2^-22                      the products the split drops (lo.lo) and the residuals of the halves;
+    //   68 * 2^-23 * (n_hh * 1.002 + n_small * 2^-10.9)
+    //                                    fp32 accumulation in the tensor core: per K = 16 instruction 17 addends, each
+    //                                    off by at most one ulp of the largest magnitude in play -- M for the
+    //                                    instructions that hold hi.hi products (and the zero padding behind them),
+    //                                    2^-10.9 M before that --, twice for 2 x_i.x_j, and a factor 2 of head-room;
+    //   2^-20                            the norms rounded to f32, the roundings of nc - 2 acc and thr - nr.
+    const int n_instr = atoms * 4, n_small = (int)(2 * d / 16), n_hh = n_instr - n_small;
+    const double coef = 6.1 * ldexp(1.0, -22) + 68.0 * ldexp(1.0, -23) * (n_hh * 1.002 + n_small * 5.3e-4) + ldexp(1.0, -20);
     {
         Span sp(ctx, T_GRID_BUILD);
-        CNN_CUDA(cudaMemsetAsync(maxbits, 0, sizeof(int), st));
         CNN_CUDA(cudaMemsetAsync(ctx->b_stats.p, 0, sizeof(unsigned long long) * ST_N, st));
-        CNN_CUDA(cudaMemsetAsync(mean, 0, sizeof(double) * (size_t)d, st));
-        col_sum_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(d_x, n, (int)d, mean);
-        col_mean_kernel<<<1, CM_MAXD, 0, st>>>(mean, (int)d, n);
-        split_kernel<<<cnn_blocks(n_pad, 8) < ctx->sm_count * 32 ? cnn_blocks(n_pad, 8) : ctx->sm_count * 32, 256, 0, st>>>(d_x, mean, n, n_pad, (int)d, kt, A, B, norm, maxbits);
-        CNN_LAUNCHED(ctx, 2);
+        CNN_CUDA(cudaMemsetAsync(mean, 0, sizeof(double) * (size_t)(CM_MAXD + 2 * CM_MAXD + 16), st));
+        CNN_CUDA(cudaMemsetAsync(mm, 0xff, sizeof(unsigned long long) * CM_MAXD, st));  // minima start at the largest code
+        col_sum_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(d_x, n, (int)d, mean, mm);
+        col_mean_kernel<<<1, CM_MAXD, 0, st>>>(mean, mm, (int)d, n, scale_e);
+        split_kernel<<<cnn_blocks(n_pad, 8) < ctx->sm_count * 32 ? cnn_blocks(n_pad, 8) : ctx->sm_count * 32, 256, 0, st>>>(
+            d_x, mean, scale_e, n, n_pad, (int)d, kt, A, B, norm, maxbits);
+        tensor_setup_kernel<<<1, 1, 0, st>>>(maxbits, scale_e, R, coef, thr, bad);
+        CNN_LAUNCHED(ctx, 4);
         CNN_KERNEL_CHECK();
     }
-    float *hm;
-    CNN_TRY(cnn_pinned(ctx, 64, (void **)&hm));
-    CNN_CUDA(cudaMemcpyAsync(hm, maxbits, sizeof(float), cudaMemcpyDeviceToHost, st));
-    CNN_CUDA(cudaStreamSynchronize(st));
-    const double maxnorm = hm[0];
-    if (!isfinite(maxnorm)) CNN_FAIL(CNNB200_E_INVALID, "neighbour search: coordinates contain NaN or infinity");
-    // |d2~ - d2| <= 2 * maxnorm * (2^-15 [bf16 split: dropped lo.lo and residuals] + K * 2^-22 [fp32
-    // accumulation in the tensor core]) + 2^-20 * maxnorm [norms rounded to f32, the f32 roundings of
-    // nc - 2 acc and of t - nr in the epilogue]; see DESIGN.md
-    const double eps = 2.0 * maxnorm * (ldexp(1.0, -15) + (double)kt * ldexp(1.0, -22)) + ldexp(maxnorm, -20) + 1e-30;
 
     CUtensorMap mapA, mapB;
     CNN_TRY(make_map(&mapA, A, n_pad, kt));
     CNN_TRY(make_map(&mapB, B, n_pad, kt));
 
-    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp2, 128));
-    unsigned long long *pair_count = (unsigned long long *)(ctx->b_tmp2.as<char>() + 48);
-    unsigned long long *band_count = pair_count + 1;
-    unsigned long long *rej_count = pair_count + 2;
-    int *d_max_deg = (int *)(pair_count + 3);
+    const size_t dir_entries = (size_t)4 * n_tiles * n_tiles;
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tdir, sizeof(unsigned) * 2 * dir_entries));
+    unsigned *dir = ctx->b_tdir.as<unsigned>(), *dirT = dir + dir_entries;
 
     TensorParams P;
     memset(&P, 0, sizeof(P));
     P.norm = norm;
+    P.thr = thr;
     P.n = n;
     P.n_tiles = n_tiles;
     P.atoms = atoms;
     P.nsb = atoms >= 4 ? 1 : 2;  // 2 A tiles + nsb B tiles must fit 227 KB
-    P.r2_lo = (float)(R - eps);
-    P.r2_hi = (float)(R + eps);
-    // keep the f32 thresholds on the safe side of the f64 ones
-    P.r2_lo = nextafterf(P.r2_lo, -INFINITY);
-    P.r2_hi = nextafterf(P.r2_hi, INFINITY);
-    P.pair_count = pair_count;
     P.skip = skip;
     P.words = words;
+    P.dir = dir;
+    P.dirT = dirT;
+    P.slab_count = slab_count;
 
     const size_t smem = (size_t)(2 + P.nsb) * atoms * ATOM_BYTES + 1024 /*alignment*/ + 20 * 8 +
-                        EPI_WARPS * 2 * TT * sizeof(float) + EPI_WARPS * 32 * PAIR_BUF * sizeof(int) + 64;
-    CNN_CUDA(cudaFuncSetAttribute(tensor_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        EPI_WARPS * 2 * TT * sizeof(float) + 64;
+    CNN_CUDA(cudaFuncSetAttribute(tensor_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
-    // ---- the pass over the upper triangle (rerun once with a larger list should the pairs not fit) ------------
-    ll n_pairs = 0;
-    ll pair_cap = ctx->tensor_band_cap > 0 ? ctx->tensor_band_cap : (128 * n > (1ll << 20) ? 128 * n : (1ll << 20));
-    unsigned long long *hb;
-    CNN_TRY(cnn_pinned(ctx, 64, (void **)&hb));
+    // ---- the pass over the upper triangle, the exact decisions, the degrees (all of it repeated once with more
+    //      room should the slabs not fit: the host learns that together with nnz) -------------------------------------
+    ll slab_cap = ctx->tensor_band_cap > 0 ? ctx->tensor_band_cap : (64 * n_tiles > 4096 ? 64 * n_tiles : 4096);
+    unsigned *hb;
+    CNN_TRY(cnn_pinned(ctx, 256, (void **)&hb));
+    hb += 32;  // the first 128 bytes belong to cnn_scan_deg_to_row_ptr
+    ll nnz = 0, max_deg = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        CNN_TRY(cnn_ensure(ctx, ctx->b_worklist, sizeof(int2) * (size_t)pair_cap));
-        P.pairs = ctx->b_worklist.as<int2>();
-        P.pair_cap = pair_cap;
-        CNN_CUDA(cudaMemsetAsync(pair_count, 0, 2 * sizeof(unsigned long long), st));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_tslab, sizeof(uint4) * 32 * (size_t)slab_cap));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_tband, sizeof(uint4) * 32 * (size_t)slab_cap));
+        P.slabs = ctx->b_tslab.as<uint4>();
+        P.bslabs = ctx->b_tband.as<uint4>();
+        P.slab_cap = (unsigned)slab_cap;
+        CNN_CUDA(cudaMemsetAsync(dir, 0, sizeof(unsigned) * 2 * dir_entries, st));
+        CNN_CUDA(cudaMemsetAsync(slab_count, 0, 2 * sizeof(unsigned) + 2 * sizeof(unsigned long long), st));
+        CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>() + n, 0, sizeof(int), st));
         {
             Span sp(ctx, T_SEARCH_COUNT);
-            tensor_pairs_kernel<<<(int)((n_tiles + 1) / 2), NUM_THREADS, smem, st>>>(mapA, mapB, P);
+            tensor_tiles_kernel<<<(int)((n_tiles + 1) / 2), NUM_THREADS, smem, st>>>(mapA, mapB, P);
             CNN_LAUNCHED(ctx, 1);
             CNN_KERNEL_CHECK();
         }
-        CNN_CUDA(cudaMemcpyAsync(hb, pair_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CNN_CUDA(cudaStreamSynchronize(st));
-        n_pairs = (ll)hb[0];
-        if (n_pairs <= pair_cap) break;
-        if (attempt == 1) CNN_FAIL(CNNB200_E_STATE, "tensor search: pair list overflowed twice");
-        pair_cap = n_pairs + n_pairs / 16 + 1024;
-    }
-    ctx->tensor_band_cap = pair_cap;
-
-    // ---- borderline pairs decided exactly; the survivors are counted, not yet attributed to rows ------------------------
-    CNN_CUDA(cudaMemsetAsync(rej_count, 0, 2 * sizeof(unsigned long long), st));  // + d_max_deg
-    {
-        Span sp(ctx, T_SCAN);
-        if (n_pairs > 0) {
+        {
+            Span sp(ctx, T_SCAN);
+            const int rb = ctx->sm_count * 8;
             if (sq)
-                pair_resolve_kernel<true><<<cnn_blocks(n_pairs, 256), 256, 0, st>>>(d_x, (int)d, P.pairs, n_pairs, radius_cutoff,
-                                                                                band_count, rej_count);
+                tile_resolve_kernel<true><<<rb, 256, 0, st>>>(d_x, (int)d, dir, (ll)dir_entries, n_tiles, P.slabs, P.bslabs,
+                                                              radius_cutoff, band_count, rej_count);
             else
-                pair_resolve_kernel<false><<<cnn_blocks(n_pairs, 256), 256, 0, st>>>(d_x, (int)d, P.pairs, n_pairs, radius_cutoff,
-                                                                                 band_count, rej_count);
+                tile_resolve_kernel<false><<<rb, 256, 0, st>>>(d_x, (int)d, dir, (ll)dir_entries, n_tiles, P.slabs, P.bslabs,
+                                                               radius_cutoff, band_count, rej_count);
+            tile_rows_kernel<false><<<(int)n_tiles, 128, 0, st>>>(dir, dirT, P.slabs, n, n_tiles, ctx->b_deg.as<int>(), nullptr, nullptr);
+            CNN_LAUNCHED(ctx, 2);
+            CNN_KERNEL_CHECK();
         }
+        CNN_CUDA(cudaMemcpyAsync(hb, bad, 4 * sizeof(int) + 2 * sizeof(unsigned) + 2 * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, st));
+        CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, ctx->b_deg.as<int>(), n, ctx->b_row_ptr.as<ll>(), &nnz, &max_deg));  // synchronises
+        if (((int *)hb)[0]) CNN_FAIL(CNNB200_E_INVALID, "neighbour search: coordinates contain NaN or infinity");
+        const ll used = (ll)hb[4];
+        if (used <= slab_cap) break;
+        if (attempt == 1) CNN_FAIL(CNNB200_E_STATE, "tensor search: slab store overflowed twice");
+        slab_cap = used + used / 16 + 1024;
+    }
+    ctx->tensor_band_cap = slab_cap;
+    if (nnz >= (1ll << 31) - 1) CNN_FAIL(CNNB200_E_RANGE, "tensor search: more than 2^31 neighbour entries");
+    CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
+    {
+        Span sp(ctx, T_SEARCH_FILL);
+        tile_rows_kernel<true><<<(int)n_tiles, 128, 0, st>>>(dir, dirT, P.slabs, n, n_tiles, nullptr, ctx->b_row_ptr.as<ll>(),
+                                                             ctx->b_col_idx.as<int>());
         CNN_LAUNCHED(ctx, 1);
         CNN_KERNEL_CHECK();
     }
-    CNN_CUDA(cudaMemcpyAsync(hb, band_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CNN_CUDA(cudaStreamSynchronize(st));
-    const ll n_band = (ll)hb[0], n_rej = (ll)hb[1];
-    const ll nnz = 2 * (n_pairs - n_rej) + n;
-    if (nnz >= (1ll << 31) - 1) CNN_FAIL(CNNB200_E_RANGE, "tensor search: more than 2^31 neighbour entries");
-    // ---- (row : column) keys of both directions + self, one radix sort: low words = col_idx, row changes = row_ptr ------
-    CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
-    const ll n_keys = 2 * n_pairs + n;
-    if (n_keys >= (1ll << 31) - 1) CNN_FAIL(CNNB200_E_RANGE, "tensor search: more than 2^31 sort keys");
-    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(unsigned long long) * (size_t)n_keys * 2));
-    unsigned long long *keys = ctx->b_tmp0.as<unsigned long long>(), *keys2 = keys + n_keys;
-    {
-        Span sp(ctx, T_SEARCH_FILL);
-        const ll work = n_pairs > n ? n_pairs : n;
-        int bits = 1;
-        while ((1ll << bits) <= n) ++bits;  // 2^bits > n: row n (rejected pairs) fits as well
-        pair_keys_kernel<<<cnn_blocks(work, 256), 256, 0, st>>>(P.pairs, n_pairs, n, bits, keys);
-        size_t need = 0;
-        CNN_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, need, keys, keys2, (int)n_keys, 0, 64, st));
-        CNN_TRY(cnn_ensure(ctx, ctx->b_cub, need));
-        size_t cap = ctx->b_cub.cap;
-        CNN_CUDA(cub::DeviceRadixSort::SortKeys(ctx->b_cub.p, cap, keys, keys2, (int)n_keys, 0, 2 * bits, st));
-        keys_to_cols_kernel<<<cnn_blocks(nnz, 256), 256, 0, st>>>(keys2, nnz, n, bits, ctx->b_col_idx.as<int>(),
-                                                                  ctx->b_row_ptr.as<ll>());
-        max_degree_kernel<<<cnn_blocks(n, 256), 256, 0, st>>>(ctx->b_row_ptr.as<ll>(), n, d_max_deg);
-        CNN_LAUNCHED(ctx, 3);
-        CNN_KERNEL_CHECK();
-    }
-    int *hmax = (int *)(hb + 4);
-    CNN_CUDA(cudaMemcpyAsync(hmax, d_max_deg, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CNN_CUDA(cudaStreamSynchronize(st));
-    const ll max_deg = hmax[0];
-    hb[0] = (unsigned long long)n_band;
-    ctx->stats[ST_RECHECK] = (ll)hb[0];
+    ctx->stats[ST_RECHECK] = (ll)((unsigned long long *)(hb + 6))[0];
     ctx->stats[ST_DIST] = n * (n - 1) / 2;
     ctx->n = n;
     ctx->nnz = nnz;

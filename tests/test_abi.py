@@ -65,7 +65,7 @@ def test_sass_shows_the_tcgen05_tma_path():
     total, per_kernel, arch = mod.counts()
     assert arch == ["sm_100a"]
     assert total["UTCHMMA"] >= 8 and total["LDTM"] >= 4 and total["UTMALDG"] >= 8 and total["SYNCS"] >= 8
-    tensor = [v for k, v in per_kernel.items() if "tensor_pairs_kernel" in k]
+    tensor = [v for k, v in per_kernel.items() if "tensor_tiles_kernel" in k]
     assert tensor and tensor[0].get("UTCHMMA", 0) >= 8 and tensor[0].get("LDTM", 0) >= 4 and tensor[0].get("UTMALDG", 0) >= 8
     committed = open(os.path.join(ROOT, "profiles", "sass_summary.txt")).read()
     for m in ("UTCHMMA", "LDTM", "UTMALDG"):

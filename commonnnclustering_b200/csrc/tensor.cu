@@ -311,41 +311,74 @@ __global__ void gather_rows_kernel(const double *__restrict__ x, const int *__re
     out[t] = x[(ll)perm[p] * d + k];
 }
 
-// one block per tile: centre (mean of its live rows) and radius (largest distance of a row to the centre, rounded up)
-__global__ void tile_ball_kernel(const double *__restrict__ x, ll n, int d, double *centre, double *radius) {
-    __shared__ double c[128];
+// One block per tile: bounding ball(s) of its live rows -- centre (mean) and radius (largest distance of a row to the
+// centre, rounded up).  A tile that straddles two pivot cells holds points of two unrelated regions; one ball around
+// both would reach every other tile (C3: 62 such tiles made 43 % of all tile visits and the longest CTA 7x the
+// average), so the rows from the first change of pivot on get a ball of their own (radius2 < 0: no second ball).
+__global__ void tile_ball_kernel(const double *__restrict__ x, const unsigned long long *__restrict__ keys, ll n, int d,
+                                 double *centre, double *radius, double *centre2, double *radius2) {
+    __shared__ double c[2][128];
     __shared__ double rmax[TT];
+    __shared__ int split;
     const ll T = blockIdx.x;
     const ll r0 = T * TT;
     const int rows = (int)((n - r0) < TT ? (n - r0) : TT);
+    if (threadIdx.x == 0) split = rows;
+    __syncthreads();
+    if ((int)threadIdx.x < rows && (unsigned)(keys[r0 + threadIdx.x] >> 32) != (unsigned)(keys[r0] >> 32)) atomicMin(&split, (int)threadIdx.x);
+    __syncthreads();
+    const int sp = split;
     for (int k = threadIdx.x; k < d; k += blockDim.x) {
-        double s = 0.0;
-        for (int r = 0; r < rows; ++r) s += x[(r0 + r) * d + k];
-        c[k] = s / rows;
-        centre[(ll)k * gridDim.x + T] = c[k];  // [d][n_tiles]: tile_skip_kernel reads 32 consecutive tiles per dimension
+        double s1 = 0.0, s2 = 0.0;
+        for (int r = 0; r < sp; ++r) s1 += x[(r0 + r) * d + k];
+        for (int r = sp; r < rows; ++r) s2 += x[(r0 + r) * d + k];
+        c[0][k] = s1 / sp;
+        c[1][k] = sp < rows ? s2 / (rows - sp) : 0.0;
+        centre[(ll)k * gridDim.x + T] = c[0][k];  // [d][n_tiles]: tile_skip_kernel reads 32 consecutive tiles per dimension
+        centre2[(ll)k * gridDim.x + T] = c[1][k];
     }
     __syncthreads();
+    const int grp = (int)threadIdx.x >= sp ? 1 : 0;
     double dist = 0.0;
     if ((int)threadIdx.x < rows) {
         double s = 0.0;
         for (int k = 0; k < d; ++k) {
-            const double t = x[(r0 + threadIdx.x) * d + k] - c[k];
+            const double t = x[(r0 + threadIdx.x) * d + k] - c[grp][k];
             s += t * t;
         }
         dist = sqrt(s);
     }
-    rmax[threadIdx.x] = dist;
-    __syncthreads();
-    for (int o = TT / 2; o; o >>= 1) {
-        if ((int)threadIdx.x < o) rmax[threadIdx.x] = fmax(rmax[threadIdx.x], rmax[threadIdx.x + o]);
+    for (int pass = 0; pass < 2; ++pass) {
         __syncthreads();
+        rmax[threadIdx.x] = ((int)threadIdx.x < rows && grp == pass) ? dist : 0.0;
+        __syncthreads();
+        for (int o = TT / 2; o; o >>= 1) {
+            if ((int)threadIdx.x < o) rmax[threadIdx.x] = fmax(rmax[threadIdx.x], rmax[threadIdx.x + o]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const double rr = rmax[0] * (1.0 + 1e-12) + 1e-300;
+            if (pass == 0) radius[T] = rr;
+            else radius2[T] = sp < rows ? rr : -1.0;
+        }
     }
-    if (threadIdx.x == 0) radius[T] = rmax[0] * (1.0 + 1e-12) + 1e-300;
+}
+
+__device__ __forceinline__ bool balls_apart(const double *__restrict__ ca, ll a, const double *__restrict__ cb, ll b, ll n_tiles,
+                                            int d, double ra, double rb, double reach) {
+    double s = 0.0;
+    for (int k = 0; k < d; ++k) {
+        const double t = ca[(ll)k * n_tiles + a] - cb[(ll)k * n_tiles + b];
+        s += t * t;
+    }
+    // any i in ball a, j in ball b: |x_i - x_j| >= |c_a - c_b| - rho_a - rho_b
+    return sqrt(s) * (1.0 - 1e-12) - ra - rb > reach;
 }
 
 // bit J of row I set <=> tile pair (I, J) can be skipped; one warp per 32 column tiles.  Only the words at or above the
 // diagonal are ever read (TileIter starts at the word of I0), the others are left alone.
-__global__ void tile_skip_kernel(const double *__restrict__ centre, const double *__restrict__ radius, ll n_tiles, int d,
+__global__ void tile_skip_kernel(const double *__restrict__ centre, const double *__restrict__ radius,
+                                 const double *__restrict__ centre2, const double *__restrict__ radius2, ll n_tiles, int d,
                                  int words, double r_true, unsigned *skip) {
     const ll gw = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -356,13 +389,12 @@ __global__ void tile_skip_kernel(const double *__restrict__ centre, const double
     const ll J = wJ * 32 + lane;
     bool sk = false;
     if (J < n_tiles) {
-        double s = 0.0;
-        for (int k = 0; k < d; ++k) {
-            const double t = centre[(ll)k * n_tiles + I] - centre[(ll)k * n_tiles + J];
-            s += t * t;
-        }
-        // any i in I, j in J: |x_i - x_j| >= |c_I - c_J| - rho_I - rho_J
-        sk = sqrt(s) * (1.0 - 1e-12) - radius[I] - radius[J] > r_true * (1.0 + 1e-9);
+        const double reach = r_true * (1.0 + 1e-9);
+        const double rI2 = radius2[I], rJ2 = radius2[J];
+        sk = balls_apart(centre, I, centre, J, n_tiles, d, radius[I], radius[J], reach);
+        if (sk && rJ2 >= 0.0) sk = balls_apart(centre, I, centre2, J, n_tiles, d, radius[I], rJ2, reach);
+        if (sk && rI2 >= 0.0) sk = balls_apart(centre2, I, centre, J, n_tiles, d, rI2, radius[J], reach);
+        if (sk && rI2 >= 0.0 && rJ2 >= 0.0) sk = balls_apart(centre2, I, centre2, J, n_tiles, d, rI2, rJ2, reach);
     }
     const unsigned m = __ballot_sync(0xffffffffu, sk);
     if (lane == 0) skip[gw] = m;
@@ -425,6 +457,7 @@ struct TensorParams {
     int words;
     uint4 *slabs, *bslabs;      // [slab_cap][32]
     unsigned *dir, *dirT;       // [4 n_tiles][n_tiles], [n_tiles][4 n_tiles]
+    int2 *info;                 // [slab_cap] (row quarter + 1, column tile) of the slabs that hold borderline pairs, else (0, 0)
     unsigned *slab_count;       // slots handed out (may exceed slab_cap: then the pass is repeated)
     unsigned slab_cap;
 };
@@ -622,6 +655,7 @@ tensor_tiles_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         const unsigned v = (slot + 1) | (band ? BAND_FLAG : 0u);
                         P.dir[g * n_tiles + j] = v;
                         P.dirT[j * (4 * n_tiles) + g] = v;
+                        if (band) P.info[slot] = make_int2((int)g + 1, (int)j);
                     }
                 }
             }
@@ -638,96 +672,91 @@ tensor_tiles_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 // ---------------------------------------------------------------------------------------------------
 // borderline pairs, decided with the reference's own f64 expression (_types.pyx:2253-2267)
 // ---------------------------------------------------------------------------------------------------
-// A warp takes 32 consecutive directory entries and, for every slab flagged as holding borderline pairs, one row per
-// lane: each lane pops the lowest borderline bit of its row, the warp evaluates the pending pairs four at a time, 8
-// lanes per pair -- a lane loads 8 consecutive coordinates of both rows (whole sectors) and forms its 8 squared
-// differences; the sum is then accumulated in the reference's order (left to right, no FMA) by passing the running
-// value from lane to lane of the group.  A rejected pair loses its bit in the hit slab; the lane owns its row, so
-// the slab is rewritten with plain stores.
+// A warp per slab that holds borderline pairs (slots are handed out strided, so the dense regions of the tile grid
+// spread over all warps), one row per lane: each lane pops the lowest borderline bit of its row, the warp evaluates the
+// pending pairs four at a time, 8 lanes per pair -- a lane loads 8 consecutive coordinates of both rows (whole
+// sectors) and forms its 8 squared differences; the sum is then accumulated in the reference's order (left to right,
+// no FMA) by passing the running value from lane to lane of the group.  A rejected pair loses its bit in the hit
+// slab; the lane owns its row, so the slab is rewritten with plain stores.
 template <bool SQRT>
 __global__ void __launch_bounds__(256)
-tile_resolve_kernel(const double *__restrict__ x, int d, const unsigned *__restrict__ dir, ll n_entries, ll n_tiles,
-                    uint4 *slabs, const uint4 *__restrict__ bslabs, double rc, unsigned long long *n_band,
+tile_resolve_kernel(const double *__restrict__ x, int d, const int2 *__restrict__ info, const unsigned *__restrict__ slab_count,
+                    unsigned slab_cap, uint4 *slabs, const uint4 *__restrict__ bslabs, double rc, unsigned long long *n_band,
                     unsigned long long *n_rejected) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int grp = lane >> 3, gl = lane & 7;
-    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    const unsigned nwarps = (unsigned)(((ll)gridDim.x * blockDim.x) >> 5);
+    unsigned n_slots = *slab_count;
+    if (n_slots > slab_cap) n_slots = slab_cap;
     unsigned long long my_band = 0, my_rej = 0;
-    for (ll e0 = ((blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5) * 32; e0 < n_entries; e0 += nwarps * 32) {
-        const ll e = e0 + lane;
-        const unsigned v = e < n_entries ? dir[e] : 0u;
-        unsigned need = __ballot_sync(full, (v & BAND_FLAG) != 0);
-        while (need) {
-            const int b = __ffs(need) - 1;
-            need &= need - 1;
-            const unsigned slot = (__shfl_sync(full, v, b) & ~BAND_FLAG) - 1u;
-            const ll ee = e0 + b;
-            const ll g = ee / n_tiles, J = ee - g * n_tiles;
-            const ll pi_mine = g * 32 + lane;
-            uint4 bd = bslabs[(size_t)slot * 32 + lane];
-            uint4 rj = make_uint4(0u, 0u, 0u, 0u);
-            my_band += __popc(bd.x) + __popc(bd.y) + __popc(bd.z) + __popc(bd.w);
-            for (;;) {
-                // this lane's next pending pair
-                int w = -1, bit = 0;
-                if (bd.x) { w = 0; bit = __ffs(bd.x) - 1; bd.x &= bd.x - 1; }
-                else if (bd.y) { w = 1; bit = __ffs(bd.y) - 1; bd.y &= bd.y - 1; }
-                else if (bd.z) { w = 2; bit = __ffs(bd.z) - 1; bd.z &= bd.z - 1; }
-                else if (bd.w) { w = 3; bit = __ffs(bd.w) - 1; bd.w &= bd.w - 1; }
-                unsigned todo = __ballot_sync(full, w >= 0);
-                if (!todo) break;
-                const ll pj_mine = J * TT + 32 * w + bit;
-                bool ok = true;
-                while (todo) {
-                    int src[4];
+    for (unsigned slot = (unsigned)((blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5); slot < n_slots; slot += nwarps) {
+        const int2 inf = info[slot];
+        if (inf.x == 0) continue;
+        const ll g = inf.x - 1, J = inf.y;
+        const ll pi_mine = g * 32 + lane;
+        uint4 bd = bslabs[(size_t)slot * 32 + lane];
+        uint4 rj = make_uint4(0u, 0u, 0u, 0u);
+        my_band += __popc(bd.x) + __popc(bd.y) + __popc(bd.z) + __popc(bd.w);
+        for (;;) {
+            // this lane's next pending pair
+            int w = -1, bit = 0;
+            if (bd.x) { w = 0; bit = __ffs(bd.x) - 1; bd.x &= bd.x - 1; }
+            else if (bd.y) { w = 1; bit = __ffs(bd.y) - 1; bd.y &= bd.y - 1; }
+            else if (bd.z) { w = 2; bit = __ffs(bd.z) - 1; bd.z &= bd.z - 1; }
+            else if (bd.w) { w = 3; bit = __ffs(bd.w) - 1; bd.w &= bd.w - 1; }
+            unsigned todo = __ballot_sync(full, w >= 0);
+            if (!todo) break;
+            const ll pj_mine = J * TT + 32 * w + bit;
+            bool ok = true;
+            while (todo) {
+                int src[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        src[k] = todo ? __ffs(todo) - 1 : -1;
-                        todo &= todo - 1;  // no-op at 0
+                for (int k = 0; k < 4; ++k) {
+                    src[k] = todo ? __ffs(todo) - 1 : -1;
+                    todo &= todo - 1;  // no-op at 0
+                }
+                const int mine = grp == 0 ? src[0] : grp == 1 ? src[1] : grp == 2 ? src[2] : src[3];
+                const int from = mine < 0 ? 0 : mine;
+                const ll pi = __shfl_sync(full, pi_mine, from), pj = __shfl_sync(full, pj_mine, from);
+                const double *a = x + pi * d, *bb = x + pj * d;
+                double sum = 0.0;
+                for (int k0 = 0; k0 < d; k0 += 64) {
+                    double t[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int kk = k0 + gl * 8 + u;
+                        double df = 0.0;
+                        if (mine >= 0 && kk < d) df = __dsub_rn(a[kk], bb[kk]);
+                        t[u] = __dmul_rn(df, df);  // +0.0 past the end: adding it changes nothing
                     }
-                    const int mine = grp == 0 ? src[0] : grp == 1 ? src[1] : grp == 2 ? src[2] : src[3];
-                    const int from = mine < 0 ? 0 : mine;
-                    const ll pi = __shfl_sync(full, pi_mine, from), pj = __shfl_sync(full, pj_mine, from);
-                    const double *a = x + pi * d, *bb = x + pj * d;
-                    double sum = 0.0;
-                    for (int k0 = 0; k0 < d; k0 += 64) {
-                        double t[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int kk = k0 + gl * 8 + u;
-                            double df = 0.0;
-                            if (mine >= 0 && kk < d) df = __dsub_rn(a[kk], bb[kk]);
-                            t[u] = __dmul_rn(df, df);  // +0.0 past the end: adding it changes nothing
+                    for (int r = 0; r < 8; ++r) {
+                        if (gl == r) {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) sum = __dadd_rn(sum, t[u]);
                         }
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            if (gl == r) {
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) sum = __dadd_rn(sum, t[u]);
-                            }
-                            sum = __shfl_sync(full, sum, (lane & ~7) | r);
-                        }
-                    }
-                    if (SQRT) sum = __dsqrt_rn(sum);
-                    const bool within = sum <= rc;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const bool wq = __shfl_sync(full, within, k * 8);
-                        if (lane == src[k]) ok = wq;
+                        sum = __shfl_sync(full, sum, (lane & ~7) | r);
                     }
                 }
-                if (w >= 0 && !ok) {
-                    const unsigned m = 1u << bit;
-                    if (w == 0) rj.x |= m; else if (w == 1) rj.y |= m; else if (w == 2) rj.z |= m; else rj.w |= m;
-                    ++my_rej;
+                if (SQRT) sum = __dsqrt_rn(sum);
+                const bool within = sum <= rc;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool wq = __shfl_sync(full, within, k * 8);
+                    if (lane == src[k]) ok = wq;
                 }
             }
-            if (rj.x | rj.y | rj.z | rj.w) {
-                uint4 h = slabs[(size_t)slot * 32 + lane];
-                h.x &= ~rj.x; h.y &= ~rj.y; h.z &= ~rj.z; h.w &= ~rj.w;
-                slabs[(size_t)slot * 32 + lane] = h;
+            if (w >= 0 && !ok) {
+                const unsigned m = 1u << bit;
+                if (w == 0) rj.x |= m; else if (w == 1) rj.y |= m; else if (w == 2) rj.z |= m; else rj.w |= m;
+                ++my_rej;
             }
+        }
+        if (rj.x | rj.y | rj.z | rj.w) {
+            uint4 h = slabs[(size_t)slot * 32 + lane];
+            h.x &= ~rj.x; h.y &= ~rj.y; h.z &= ~rj.z; h.w &= ~rj.w;
+            slabs[(size_t)slot * 32 + lane] = h;
         }
     }
     for (int o = 16; o; o >>= 1) {
@@ -754,75 +783,114 @@ __device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
     return x;
 }
 
-// One CTA per row tile T, one warp per row quarter, one row per lane.  FILL = false: degrees; true: the rows, written
-// in ascending order: entries below the diagonal from the columns of the slabs above (dirT[T][.], row quarters
-// ascending), the row itself, entries above the diagonal from the row's own slabs (dir[g][.], column tiles ascending).
+// One CTA per row tile T; warps 0-3 walk the part of the rows below the diagonal (one row quarter each, one row per
+// lane): bits of the row's COLUMN in the slabs above it (dirT[T][.], row quarters ascending); warps 4-7 the part above:
+// the row's own slabs (dir[g][.], column tiles ascending).  Four slabs are fetched at a time (the walk is a chain of
+// dependent L2 reads: directory -> slab).  FILL = false: degrees (and the size of the lower part, which tells the
+// second pass where the upper part starts); true: the rows, ascending.
 template <bool FILL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 tile_rows_kernel(const unsigned *__restrict__ dir, const unsigned *__restrict__ dirT, const uint4 *__restrict__ slabs,
-                 ll n, ll n_tiles, int *__restrict__ deg, const ll *__restrict__ row_ptr, int *__restrict__ col_idx) {
+                 ll n, ll n_tiles, int *__restrict__ deg, int *__restrict__ low, const ll *__restrict__ row_ptr,
+                 int *__restrict__ col_idx) {
+    __shared__ int s_low[TT];
     const unsigned full = 0xffffffffu;
     const ll T = blockIdx.x;
-    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, q = warp & 3, lane = threadIdx.x & 31;
+    const bool upper = warp >= 4;
     const ll g = T * 4 + q, r = g * 32 + lane, G = 4 * n_tiles;
     int cnt = 0;
     int *out = nullptr;
-    if (FILL && r < n) out = col_idx + row_ptr[r];
-    const unsigned *dt = dirT + T * G;
-    for (ll g0 = 0; g0 <= g; g0 += 32) {
-        const ll gp = g0 + lane;
-        const unsigned v = gp <= g ? dt[gp] : 0u;
-        unsigned nz = __ballot_sync(full, v != 0u);
-        while (nz) {
-            const int b = __ffs(nz) - 1;
-            nz &= nz - 1;
-            const unsigned slot = (__shfl_sync(full, v, b) & ~BAND_FLAG) - 1u;
-            unsigned xw = reinterpret_cast<const unsigned *>(slabs + (size_t)slot * 32 + lane)[q];
-            xw = transpose32(xw, lane);  // bit l: row l of quarter g0 + b has column r
-            if (FILL) {
-                const int base = (int)((g0 + b) * 32);
-                while (xw) {
-                    const int bit = __ffs(xw) - 1;
-                    xw &= xw - 1;
-                    out[cnt++] = base + bit;
-                }
-            } else {
-                cnt += __popc(xw);
-            }
-        }
-    }
-    if (r < n) {
-        if (FILL) out[cnt] = (int)r;
-        ++cnt;
-    }
-    const unsigned *dr = dir + g * n_tiles;
-    for (ll J0 = T & ~31ll; J0 < n_tiles; J0 += 32) {
-        const ll J = J0 + lane;
-        const unsigned v = (J >= T && J < n_tiles) ? dr[J] : 0u;
-        unsigned nz = __ballot_sync(full, v != 0u);
-        while (nz) {
-            const int b = __ffs(nz) - 1;
-            nz &= nz - 1;
-            const unsigned slot = (__shfl_sync(full, v, b) & ~BAND_FLAG) - 1u;
-            const uint4 m = slabs[(size_t)slot * 32 + lane];
-            if (FILL) {
-                const int base = (int)((J0 + b) * TT);
-                unsigned wds[4] = {m.x, m.y, m.z, m.w};
+    if (FILL && r < n) out = col_idx + row_ptr[r] + (upper ? low[r] : 0);
+    if (!upper) {
+        const unsigned *dt = dirT + T * G;
+        for (ll g0 = 0; g0 <= g; g0 += 32) {
+            const ll gp = g0 + lane;
+            const unsigned v = gp <= g ? dt[gp] : 0u;
+            unsigned nz = __ballot_sync(full, v != 0u);
+            while (nz) {
+                int b[4];
+                unsigned xw[4];
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    unsigned xw = wds[w];
-                    while (xw) {
-                        const int bit = __ffs(xw) - 1;
-                        xw &= xw - 1;
-                        out[cnt++] = base + 32 * w + bit;
+                for (int k = 0; k < 4; ++k) {
+                    b[k] = nz ? __ffs(nz) - 1 : -1;
+                    nz &= nz - 1;  // no-op at 0
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned slot = (__shfl_sync(full, v, b[k] < 0 ? 0 : b[k]) & ~BAND_FLAG) - 1u;
+                    xw[k] = b[k] < 0 ? 0u : reinterpret_cast<const unsigned *>(slabs + (size_t)slot * 32 + lane)[q];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (b[k] < 0) continue;  // warp-uniform
+                    unsigned m = transpose32(xw[k], lane);  // bit l: row l of quarter g0 + b has column r
+                    if (FILL) {
+                        const int base = (int)((g0 + b[k]) * 32);
+                        while (m) {
+                            const int bit = __ffs(m) - 1;
+                            m &= m - 1;
+                            out[cnt++] = base + bit;
+                        }
+                    } else {
+                        cnt += __popc(m);
                     }
                 }
-            } else {
-                cnt += __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);
+            }
+        }
+        if (!FILL) {
+            s_low[q * 32 + lane] = cnt;
+            if (r < n) low[r] = cnt;
+        }
+    } else {
+        if (r < n) {
+            if (FILL) out[0] = (int)r;
+            cnt = 1;
+        }
+        const unsigned *dr = dir + g * n_tiles;
+        for (ll J0 = T & ~31ll; J0 < n_tiles; J0 += 32) {
+            const ll J = J0 + lane;
+            const unsigned v = (J >= T && J < n_tiles) ? dr[J] : 0u;
+            unsigned nz = __ballot_sync(full, v != 0u);
+            while (nz) {
+                int b[4];
+                uint4 m[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    b[k] = nz ? __ffs(nz) - 1 : -1;
+                    nz &= nz - 1;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned slot = (__shfl_sync(full, v, b[k] < 0 ? 0 : b[k]) & ~BAND_FLAG) - 1u;
+                    m[k] = b[k] < 0 ? make_uint4(0u, 0u, 0u, 0u) : slabs[(size_t)slot * 32 + lane];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (b[k] < 0) continue;
+                    if (FILL) {
+                        const int base = (int)((J0 + b[k]) * TT);
+                        const unsigned wds[4] = {m[k].x, m[k].y, m[k].z, m[k].w};
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            unsigned xw = wds[w];
+                            while (xw) {
+                                const int bit = __ffs(xw) - 1;
+                                xw &= xw - 1;
+                                out[cnt++] = base + 32 * w + bit;
+                            }
+                        }
+                    } else {
+                        cnt += __popc(m[k].x) + __popc(m[k].y) + __popc(m[k].z) + __popc(m[k].w);
+                    }
+                }
             }
         }
     }
-    if (!FILL && r <= n) deg[r] = r < n ? cnt : 0;  // deg[n] = 0: the scan then leaves nnz in row_ptr[n]
+    if (!FILL) {
+        __syncthreads();
+        if (upper && r <= n) deg[r] = r < n ? cnt + s_low[q * 32 + lane] : 0;  // deg[n] = 0: the scan leaves nnz in row_ptr[n]
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -894,13 +962,14 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
         gather_rows_kernel<<<cnn_blocks(n * d, 256), 256, 0, st>>>(d_x, ctx->b_perm.as<int>(), n, (int)d, ctx->b_xperm.as<double>());
         d_x = ctx->b_xperm.as<double>();
         // bounding balls of the tiles and the pairs of tiles that are too far apart to matter
-        CNN_TRY(cnn_ensure(ctx, ctx->b_cell_start, sizeof(double) * (size_t)n_tiles * (size_t)(d + 1)));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_cell_start, sizeof(double) * 2 * (size_t)n_tiles * (size_t)(d + 1)));
         CNN_TRY(cnn_ensure(ctx, ctx->b_cell_count, sizeof(unsigned) * (size_t)n_tiles * (size_t)words));
         double *centre = ctx->b_cell_start.as<double>(), *radius = centre + n_tiles * d;
-        tile_ball_kernel<<<(int)n_tiles, TT, 0, st>>>(d_x, n, (int)d, centre, radius);
+        double *centre2 = radius + n_tiles, *radius2 = centre2 + n_tiles * d;
+        tile_ball_kernel<<<(int)n_tiles, TT, 0, st>>>(d_x, pk2, n, (int)d, centre, radius, centre2, radius2);
         const double r_true = sq ? radius_cutoff : sqrt(radius_cutoff);
-        tile_skip_kernel<<<cnn_blocks(n_tiles * words * 32, 256), 256, 0, st>>>(centre, radius, n_tiles, (int)d, words, r_true,
-                                                                               ctx->b_cell_count.as<unsigned>());
+        tile_skip_kernel<<<cnn_blocks(n_tiles * words * 32, 256), 256, 0, st>>>(centre, radius, centre2, radius2, n_tiles, (int)d,
+                                                                               words, r_true, ctx->b_cell_count.as<unsigned>());
         skip = ctx->b_cell_count.as<unsigned>();
         CNN_LAUNCHED(ctx, 4);
         CNN_KERNEL_CHECK();
@@ -975,7 +1044,7 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
 
     // ---- the pass over the upper triangle, the exact decisions, the degrees (all of it repeated once with more
     //      room should the slabs not fit: the host learns that together with nnz) -------------------------------------
-    ll slab_cap = ctx->tensor_band_cap > 0 ? ctx->tensor_band_cap : (64 * n_tiles > 4096 ? 64 * n_tiles : 4096);
+    ll slab_cap = ctx->tensor_band_cap > 0 ? ctx->tensor_band_cap : (256 * n_tiles > 4096 ? 256 * n_tiles : 4096);
     unsigned *hb;
     CNN_TRY(cnn_pinned(ctx, 256, (void **)&hb));
     hb += 32;  // the first 128 bytes belong to cnn_scan_deg_to_row_ptr
@@ -986,6 +1055,10 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
         P.slabs = ctx->b_tslab.as<uint4>();
         P.bslabs = ctx->b_tband.as<uint4>();
         P.slab_cap = (unsigned)slab_cap;
+        CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(int2) * (size_t)slab_cap + sizeof(int) * (size_t)n_pad));
+        P.info = ctx->b_tmp0.as<int2>();
+        int *low = (int *)(P.info + slab_cap);
+        CNN_CUDA(cudaMemsetAsync(P.info, 0, sizeof(int2) * (size_t)slab_cap, st));
         CNN_CUDA(cudaMemsetAsync(dir, 0, sizeof(unsigned) * 2 * dir_entries, st));
         CNN_CUDA(cudaMemsetAsync(slab_count, 0, 2 * sizeof(unsigned) + 2 * sizeof(unsigned long long), st));
         CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>() + n, 0, sizeof(int), st));
@@ -999,12 +1072,13 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
             Span sp(ctx, T_SCAN);
             const int rb = ctx->sm_count * 8;
             if (sq)
-                tile_resolve_kernel<true><<<rb, 256, 0, st>>>(d_x, (int)d, dir, (ll)dir_entries, n_tiles, P.slabs, P.bslabs,
+                tile_resolve_kernel<true><<<rb, 256, 0, st>>>(d_x, (int)d, P.info, slab_count, P.slab_cap, P.slabs, P.bslabs,
                                                               radius_cutoff, band_count, rej_count);
             else
-                tile_resolve_kernel<false><<<rb, 256, 0, st>>>(d_x, (int)d, dir, (ll)dir_entries, n_tiles, P.slabs, P.bslabs,
+                tile_resolve_kernel<false><<<rb, 256, 0, st>>>(d_x, (int)d, P.info, slab_count, P.slab_cap, P.slabs, P.bslabs,
                                                                radius_cutoff, band_count, rej_count);
-            tile_rows_kernel<false><<<(int)n_tiles, 128, 0, st>>>(dir, dirT, P.slabs, n, n_tiles, ctx->b_deg.as<int>(), nullptr, nullptr);
+            tile_rows_kernel<false><<<(int)n_tiles, 256, 0, st>>>(dir, dirT, P.slabs, n, n_tiles, ctx->b_deg.as<int>(), low, nullptr,
+                                                                  nullptr);
             CNN_LAUNCHED(ctx, 2);
             CNN_KERNEL_CHECK();
         }
@@ -1022,7 +1096,8 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
     {
         Span sp(ctx, T_SEARCH_FILL);
-        tile_rows_kernel<true><<<(int)n_tiles, 128, 0, st>>>(dir, dirT, P.slabs, n, n_tiles, nullptr, ctx->b_row_ptr.as<ll>(),
+        tile_rows_kernel<true><<<(int)n_tiles, 256, 0, st>>>(dir, dirT, P.slabs, n, n_tiles, nullptr,
+                                                             (int *)(ctx->b_tmp0.as<int2>() + slab_cap), ctx->b_row_ptr.as<ll>(),
                                                              ctx->b_col_idx.as<int>());
         CNN_LAUNCHED(ctx, 1);
         CNN_KERNEL_CHECK();

@@ -457,7 +457,7 @@ struct TensorParams {
     int words;
     uint4 *slabs, *bslabs;      // [slab_cap][32]
     unsigned *dir, *dirT;       // [4 n_tiles][n_tiles], [n_tiles][4 n_tiles]
-    int2 *info;                 // [slab_cap] (row quarter + 1, column tile) of the slabs that hold borderline pairs, else (0, 0)
+    int2 *info;                 // [slab_cap] (row quarter + 1, column tile | bit 30: holds borderline pairs) of the slabs in use, else (0, 0)
     unsigned *slab_count;       // slots handed out (may exceed slab_cap: then the pass is repeated)
     unsigned slab_cap;
 };
@@ -655,7 +655,7 @@ tensor_tiles_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         const unsigned v = (slot + 1) | (band ? BAND_FLAG : 0u);
                         P.dir[g * n_tiles + j] = v;
                         P.dirT[j * (4 * n_tiles) + g] = v;
-                        if (band) P.info[slot] = make_int2((int)g + 1, (int)j);
+                        P.info[slot] = make_int2((int)g + 1, (int)j | (band ? 0x40000000 : 0));
                     }
                 }
             }
@@ -669,107 +669,6 @@ tensor_tiles_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// borderline pairs, decided with the reference's own f64 expression (_types.pyx:2253-2267)
-// ---------------------------------------------------------------------------------------------------
-// A warp per slab that holds borderline pairs (slots are handed out strided, so the dense regions of the tile grid
-// spread over all warps), one row per lane: each lane pops the lowest borderline bit of its row, the warp evaluates the
-// pending pairs four at a time, 8 lanes per pair -- a lane loads 8 consecutive coordinates of both rows (whole
-// sectors) and forms its 8 squared differences; the sum is then accumulated in the reference's order (left to right,
-// no FMA) by passing the running value from lane to lane of the group.  A rejected pair loses its bit in the hit
-// slab; the lane owns its row, so the slab is rewritten with plain stores.
-template <bool SQRT>
-__global__ void __launch_bounds__(256)
-tile_resolve_kernel(const double *__restrict__ x, int d, const int2 *__restrict__ info, const unsigned *__restrict__ slab_count,
-                    unsigned slab_cap, uint4 *slabs, const uint4 *__restrict__ bslabs, double rc, unsigned long long *n_band,
-                    unsigned long long *n_rejected) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int grp = lane >> 3, gl = lane & 7;
-    const unsigned nwarps = (unsigned)(((ll)gridDim.x * blockDim.x) >> 5);
-    unsigned n_slots = *slab_count;
-    if (n_slots > slab_cap) n_slots = slab_cap;
-    unsigned long long my_band = 0, my_rej = 0;
-    for (unsigned slot = (unsigned)((blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5); slot < n_slots; slot += nwarps) {
-        const int2 inf = info[slot];
-        if (inf.x == 0) continue;
-        const ll g = inf.x - 1, J = inf.y;
-        const ll pi_mine = g * 32 + lane;
-        uint4 bd = bslabs[(size_t)slot * 32 + lane];
-        uint4 rj = make_uint4(0u, 0u, 0u, 0u);
-        my_band += __popc(bd.x) + __popc(bd.y) + __popc(bd.z) + __popc(bd.w);
-        for (;;) {
-            // this lane's next pending pair
-            int w = -1, bit = 0;
-            if (bd.x) { w = 0; bit = __ffs(bd.x) - 1; bd.x &= bd.x - 1; }
-            else if (bd.y) { w = 1; bit = __ffs(bd.y) - 1; bd.y &= bd.y - 1; }
-            else if (bd.z) { w = 2; bit = __ffs(bd.z) - 1; bd.z &= bd.z - 1; }
-            else if (bd.w) { w = 3; bit = __ffs(bd.w) - 1; bd.w &= bd.w - 1; }
-            unsigned todo = __ballot_sync(full, w >= 0);
-            if (!todo) break;
-            const ll pj_mine = J * TT + 32 * w + bit;
-            bool ok = true;
-            while (todo) {
-                int src[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    src[k] = todo ? __ffs(todo) - 1 : -1;
-                    todo &= todo - 1;  // no-op at 0
-                }
-                const int mine = grp == 0 ? src[0] : grp == 1 ? src[1] : grp == 2 ? src[2] : src[3];
-                const int from = mine < 0 ? 0 : mine;
-                const ll pi = __shfl_sync(full, pi_mine, from), pj = __shfl_sync(full, pj_mine, from);
-                const double *a = x + pi * d, *bb = x + pj * d;
-                double sum = 0.0;
-                for (int k0 = 0; k0 < d; k0 += 64) {
-                    double t[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int kk = k0 + gl * 8 + u;
-                        double df = 0.0;
-                        if (mine >= 0 && kk < d) df = __dsub_rn(a[kk], bb[kk]);
-                        t[u] = __dmul_rn(df, df);  // +0.0 past the end: adding it changes nothing
-                    }
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        if (gl == r) {
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) sum = __dadd_rn(sum, t[u]);
-                        }
-                        sum = __shfl_sync(full, sum, (lane & ~7) | r);
-                    }
-                }
-                if (SQRT) sum = __dsqrt_rn(sum);
-                const bool within = sum <= rc;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const bool wq = __shfl_sync(full, within, k * 8);
-                    if (lane == src[k]) ok = wq;
-                }
-            }
-            if (w >= 0 && !ok) {
-                const unsigned m = 1u << bit;
-                if (w == 0) rj.x |= m; else if (w == 1) rj.y |= m; else if (w == 2) rj.z |= m; else rj.w |= m;
-                ++my_rej;
-            }
-        }
-        if (rj.x | rj.y | rj.z | rj.w) {
-            uint4 h = slabs[(size_t)slot * 32 + lane];
-            h.x &= ~rj.x; h.y &= ~rj.y; h.z &= ~rj.z; h.w &= ~rj.w;
-            slabs[(size_t)slot * 32 + lane] = h;
-        }
-    }
-    for (int o = 16; o; o >>= 1) {
-        my_band += __shfl_xor_sync(full, my_band, o);
-        my_rej += __shfl_xor_sync(full, my_rej, o);
-    }
-    if (lane == 0 && my_band) atomicAdd(n_band, my_band);
-    if (lane == 0 && my_rej) atomicAdd(n_rejected, my_rej);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// bitmaps -> CSR
-// ---------------------------------------------------------------------------------------------------
 // lane l holds row l of a 32 x 32 bit block (bit c = column c); afterwards lane c holds column c (bit l = row l)
 __device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
     const unsigned full = 0xffffffffu;
@@ -783,16 +682,127 @@ __device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
     return x;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// borderline pairs, decided with the reference's own f64 expression (_types.pyx:2253-2267)
+// ---------------------------------------------------------------------------------------------------
+// A warp walks the slabs that hold borderline pairs (slots are handed out strided, so the dense regions of the tile grid
+// spread over all warps) and collects their pairs in a list in shared memory; whenever the list is nearly full -- and at
+// the end -- the pairs are evaluated 32 at a time, one per LANE, in the reference's order (left to right, no FMA).  The
+// coordinates pass through shared memory 8 dimensions at a time: the 64 rows of the 32 pairs come in as 64-byte
+// pieces (4 lanes x 16 bytes: whole sectors, every byte used once) and each lane reads its own pair back as
+// [dimension][row] pairs of adjacent doubles.  A rejected pair loses its bit in the hit slab (atomicAnd: the pairs of
+// one row may sit in different lanes).
+// Measured on C3 (10^6 borderline pairs): four pairs at a time with 8 lanes each and the running sum handed from lane
+// to lane 0.57 ms (every DADD of the chain issued for the warp with four lanes active); one pair per lane reading
+// its rows directly 1.26 ms (8 of every 32 bytes fetched used per request, rows evicted from L1 between uses).
+#define RL_CAP 256
+#define RL_WARPS 4
+#define RL_PITCH 66   // doubles per dimension row of the stage: 64 rows + 2 (bank spread of the 4 column groups on store)
+template <bool SQRT>
+__global__ void __launch_bounds__(RL_WARPS * 32)
+tile_resolve_kernel(const double *__restrict__ x, int d, const int2 *__restrict__ info, const unsigned *__restrict__ slab_count,
+                    unsigned slab_cap, unsigned *slab_words, const uint4 *__restrict__ bslabs, double rc,
+                    unsigned long long *n_band, unsigned long long *n_rejected) {
+    __shared__ int4 s_list[RL_WARPS][RL_CAP];
+    __shared__ __align__(16) double s_stage[RL_WARPS][8][RL_PITCH];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int4 *list = s_list[threadIdx.x >> 5];
+    double (*stage)[RL_PITCH] = s_stage[threadIdx.x >> 5];
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned nwarps = (unsigned)(((ll)gridDim.x * blockDim.x) >> 5);
+    unsigned n_slots = *slab_count;
+    if (n_slots > slab_cap) n_slots = slab_cap;
+    unsigned long long my_band = 0, my_rej = 0;
+    int n_list = 0;  // warp-uniform
+    auto drain = [&]() {
+        __syncwarp();
+        for (int p0 = 0; p0 < n_list; p0 += 32) {
+            const bool have = p0 + lane < n_list;
+            int4 e = make_int4(0, 0, 0, 0);
+            if (have) e = list[p0 + lane];
+            // load slot t of this lane: row rr = 8 t + lane / 4 of the 64 (pair rr / 2, its i or j), doubles 2 (lane & 3), + 1
+            const double *src[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int rr = 8 * t + (lane >> 2);
+                const int pi = __shfl_sync(full, e.x, rr >> 1), pj = __shfl_sync(full, e.y, rr >> 1);
+                src[t] = x + (ll)((rr & 1) ? pj : pi) * d + 2 * (lane & 3);
+            }
+            double sum = 0.0;
+            for (int k0 = 0; k0 < d; k0 += 8) {
+                const int kk = k0 + 2 * (lane & 3);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int rr = 8 * t + (lane >> 2);
+                    const double v0 = kk < d ? src[t][k0] : 0.0, v1 = kk + 1 < d ? src[t][k0 + 1] : 0.0;
+                    stage[2 * (lane & 3)][rr] = v0;       // a pair that does not exist reads row 0: harmless
+                    stage[2 * (lane & 3) + 1][rr] = v1;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const double2 ab = *reinterpret_cast<const double2 *>(&stage[k][2 * lane]);
+                    const double t = __dsub_rn(ab.x, ab.y);   // 0 - 0 past the last dimension: adds +0.0
+                    sum = __dadd_rn(sum, __dmul_rn(t, t));
+                }
+                __syncwarp();
+            }
+            if (SQRT) sum = __dsqrt_rn(sum);
+            if (have && !(sum <= rc)) {
+                atomicAnd(slab_words + (unsigned)e.z, ~(1u << e.w));
+                ++my_rej;
+            }
+        }
+        n_list = 0;
+        __syncwarp();
+    };
+    for (unsigned slot = (unsigned)((blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5); slot < n_slots; slot += nwarps) {
+        const int2 inf = info[slot];
+        if (inf.x == 0 || !(inf.y & 0x40000000)) continue;
+        const ll g = inf.x - 1, J = inf.y & 0x3fffffff;
+        uint4 bd = bslabs[(size_t)slot * 32 + lane];
+        my_band += __popc(bd.x) + __popc(bd.y) + __popc(bd.z) + __popc(bd.w);
+        for (;;) {
+            // this lane's next pending pair
+            int w = -1, bit = 0;
+            if (bd.x) { w = 0; bit = __ffs(bd.x) - 1; bd.x &= bd.x - 1; }
+            else if (bd.y) { w = 1; bit = __ffs(bd.y) - 1; bd.y &= bd.y - 1; }
+            else if (bd.z) { w = 2; bit = __ffs(bd.z) - 1; bd.z &= bd.z - 1; }
+            else if (bd.w) { w = 3; bit = __ffs(bd.w) - 1; bd.w &= bd.w - 1; }
+            const unsigned todo = __ballot_sync(full, w >= 0);
+            if (!todo) break;
+            if (n_list + 32 > RL_CAP) drain();
+            if (w >= 0)
+                list[n_list + __popc(todo & lt)] = make_int4((int)(g * 32 + lane), (int)(J * TT + 32 * w + bit),
+                                                            (int)((slot * 32u + (unsigned)lane) * 4u + (unsigned)w), bit);
+            n_list += __popc(todo);
+        }
+    }
+    drain();
+    for (int o = 16; o; o >>= 1) {
+        my_band += __shfl_xor_sync(full, my_band, o);
+        my_rej += __shfl_xor_sync(full, my_rej, o);
+    }
+    if (lane == 0 && my_band) atomicAdd(n_band, my_band);
+    if (lane == 0 && my_rej) atomicAdd(n_rejected, my_rej);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bitmaps -> CSR
+// ---------------------------------------------------------------------------------------------------
 // One CTA per row tile T; warps 0-3 walk the part of the rows below the diagonal (one row quarter each, one row per
-// lane): bits of the row's COLUMN in the slabs above it (dirT[T][.], row quarters ascending); warps 4-7 the part above:
+// lane): bits of the row's COLUMN in the slabs above it (dirT[T][.], row quarters ascending; the first pass transposes
+// word q of such a slab -- 32 rows x the 32 columns of this quarter -- and leaves the result for the second); warps 4-7 the part above:
 // the row's own slabs (dir[g][.], column tiles ascending).  Four slabs are fetched at a time (the walk is a chain of
 // dependent L2 reads: directory -> slab).  FILL = false: degrees (and the size of the lower part, which tells the
 // second pass where the upper part starts); true: the rows, ascending.
+#define RB 8   // slabs fetched at a time
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 tile_rows_kernel(const unsigned *__restrict__ dir, const unsigned *__restrict__ dirT, const uint4 *__restrict__ slabs,
-                 ll n, ll n_tiles, int *__restrict__ deg, int *__restrict__ low, const ll *__restrict__ row_ptr,
-                 int *__restrict__ col_idx) {
+                 unsigned *__restrict__ tslabs, ll n, ll n_tiles, int *__restrict__ deg, int *__restrict__ low,
+                 const ll *__restrict__ row_ptr, int *__restrict__ col_idx) {
     __shared__ int s_low[TT];
     const unsigned full = 0xffffffffu;
     const ll T = blockIdx.x;
@@ -804,27 +814,35 @@ tile_rows_kernel(const unsigned *__restrict__ dir, const unsigned *__restrict__ 
     if (FILL && r < n) out = col_idx + row_ptr[r] + (upper ? low[r] : 0);
     if (!upper) {
         const unsigned *dt = dirT + T * G;
+        unsigned v = lane <= g ? dt[lane] : 0u;
         for (ll g0 = 0; g0 <= g; g0 += 32) {
-            const ll gp = g0 + lane;
-            const unsigned v = gp <= g ? dt[gp] : 0u;
+            const ll gpn = g0 + 32 + lane;
+            const unsigned vn = gpn <= g ? dt[gpn] : 0u;  // the next 32 directory entries are under way while these are served
             unsigned nz = __ballot_sync(full, v != 0u);
             while (nz) {
-                int b[4];
-                unsigned xw[4];
+                int b[RB];
+                unsigned xw[RB], sl[RB];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < RB; ++k) {
                     b[k] = nz ? __ffs(nz) - 1 : -1;
                     nz &= nz - 1;  // no-op at 0
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < RB; ++k) {
                     const unsigned slot = (__shfl_sync(full, v, b[k] < 0 ? 0 : b[k]) & ~BAND_FLAG) - 1u;
-                    xw[k] = b[k] < 0 ? 0u : reinterpret_cast<const unsigned *>(slabs + (size_t)slot * 32 + lane)[q];
+                    sl[k] = slot;
+                    // first pass: word q of the slab's 32 rows; second pass: the transposed block the first pass left behind
+                    xw[k] = b[k] < 0 ? 0u : FILL ? tslabs[(size_t)slot * 128 + q * 32 + lane]
+                                                 : reinterpret_cast<const unsigned *>(slabs + (size_t)slot * 32 + lane)[q];
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < RB; ++k) {
                     if (b[k] < 0) continue;  // warp-uniform
-                    unsigned m = transpose32(xw[k], lane);  // bit l: row l of quarter g0 + b has column r
+                    unsigned m = xw[k];  // bit l: row l of quarter g0 + b has column r
+                    if (!FILL) {
+                        m = transpose32(m, lane);
+                        tslabs[(size_t)sl[k] * 128 + q * 32 + lane] = m;  // every (slab, word) is visited by exactly one warp
+                    }
                     if (FILL) {
                         const int base = (int)((g0 + b[k]) * 32);
                         while (m) {
@@ -837,6 +855,7 @@ tile_rows_kernel(const unsigned *__restrict__ dir, const unsigned *__restrict__ 
                     }
                 }
             }
+            v = vn;
         }
         if (!FILL) {
             s_low[q * 32 + lane] = cnt;
@@ -848,25 +867,27 @@ tile_rows_kernel(const unsigned *__restrict__ dir, const unsigned *__restrict__ 
             cnt = 1;
         }
         const unsigned *dr = dir + g * n_tiles;
-        for (ll J0 = T & ~31ll; J0 < n_tiles; J0 += 32) {
-            const ll J = J0 + lane;
-            const unsigned v = (J >= T && J < n_tiles) ? dr[J] : 0u;
+        const ll Jb = T & ~31ll;
+        unsigned v = (Jb + lane >= T && Jb + lane < n_tiles) ? dr[Jb + lane] : 0u;
+        for (ll J0 = Jb; J0 < n_tiles; J0 += 32) {
+            const ll Jn = J0 + 32 + lane;
+            const unsigned vn = Jn < n_tiles ? dr[Jn] : 0u;
             unsigned nz = __ballot_sync(full, v != 0u);
             while (nz) {
-                int b[4];
-                uint4 m[4];
+                int b[RB];
+                uint4 m[RB];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < RB; ++k) {
                     b[k] = nz ? __ffs(nz) - 1 : -1;
                     nz &= nz - 1;
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < RB; ++k) {
                     const unsigned slot = (__shfl_sync(full, v, b[k] < 0 ? 0 : b[k]) & ~BAND_FLAG) - 1u;
                     m[k] = b[k] < 0 ? make_uint4(0u, 0u, 0u, 0u) : slabs[(size_t)slot * 32 + lane];
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < RB; ++k) {
                     if (b[k] < 0) continue;
                     if (FILL) {
                         const int base = (int)((J0 + b[k]) * TT);
@@ -885,6 +906,7 @@ tile_rows_kernel(const unsigned *__restrict__ dir, const unsigned *__restrict__ 
                     }
                 }
             }
+            v = vn;
         }
     }
     if (!FILL) {
@@ -1051,9 +1073,10 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     ll nnz = 0, max_deg = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         CNN_TRY(cnn_ensure(ctx, ctx->b_tslab, sizeof(uint4) * 32 * (size_t)slab_cap));
-        CNN_TRY(cnn_ensure(ctx, ctx->b_tband, sizeof(uint4) * 32 * (size_t)slab_cap));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_tband, sizeof(uint4) * 32 * 2 * (size_t)slab_cap));  // borderline slabs | transposed hit slabs
         P.slabs = ctx->b_tslab.as<uint4>();
         P.bslabs = ctx->b_tband.as<uint4>();
+        unsigned *tslabs = (unsigned *)(P.bslabs + 32 * (size_t)slab_cap);
         P.slab_cap = (unsigned)slab_cap;
         CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(int2) * (size_t)slab_cap + sizeof(int) * (size_t)n_pad));
         P.info = ctx->b_tmp0.as<int2>();
@@ -1070,15 +1093,15 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
         }
         {
             Span sp(ctx, T_SCAN);
-            const int rb = ctx->sm_count * 8;
+            const int rb = ctx->sm_count * 12;
             if (sq)
-                tile_resolve_kernel<true><<<rb, 256, 0, st>>>(d_x, (int)d, P.info, slab_count, P.slab_cap, P.slabs, P.bslabs,
+                tile_resolve_kernel<true><<<rb, RL_WARPS * 32, 0, st>>>(d_x, (int)d, P.info, slab_count, P.slab_cap, (unsigned *)P.slabs, P.bslabs,
                                                               radius_cutoff, band_count, rej_count);
             else
-                tile_resolve_kernel<false><<<rb, 256, 0, st>>>(d_x, (int)d, P.info, slab_count, P.slab_cap, P.slabs, P.bslabs,
+                tile_resolve_kernel<false><<<rb, RL_WARPS * 32, 0, st>>>(d_x, (int)d, P.info, slab_count, P.slab_cap, (unsigned *)P.slabs, P.bslabs,
                                                                radius_cutoff, band_count, rej_count);
-            tile_rows_kernel<false><<<(int)n_tiles, 256, 0, st>>>(dir, dirT, P.slabs, n, n_tiles, ctx->b_deg.as<int>(), low, nullptr,
-                                                                  nullptr);
+            tile_rows_kernel<false><<<(int)n_tiles, 256, 0, st>>>(dir, dirT, P.slabs, tslabs, n, n_tiles, ctx->b_deg.as<int>(), low,
+                                                                  nullptr, nullptr);
             CNN_LAUNCHED(ctx, 2);
             CNN_KERNEL_CHECK();
         }
@@ -1096,7 +1119,7 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
     {
         Span sp(ctx, T_SEARCH_FILL);
-        tile_rows_kernel<true><<<(int)n_tiles, 256, 0, st>>>(dir, dirT, P.slabs, n, n_tiles, nullptr,
+        tile_rows_kernel<true><<<(int)n_tiles, 256, 0, st>>>(dir, dirT, P.slabs, (unsigned *)(P.bslabs + 32 * (size_t)slab_cap), n, n_tiles, nullptr,
                                                              (int *)(ctx->b_tmp0.as<int2>() + slab_cap), ctx->b_row_ptr.as<ll>(),
                                                              ctx->b_col_idx.as<int>());
         CNN_LAUNCHED(ctx, 1);

@@ -791,6 +791,39 @@ tile_resolve_kernel(const double *__restrict__ x, int d, const int2 *__restrict_
 // ---------------------------------------------------------------------------------------------------
 // bitmaps -> CSR
 // ---------------------------------------------------------------------------------------------------
+// Degrees, slab by slab (a warp per slab, slots strided): the rows of the slab add their popcounts to up[] (entries
+// above the diagonal), its columns -- after the 32 x 32 bit transposes, which are kept for the fill pass -- to low[]
+// (entries below the diagonal).  Atomics on 4-byte counters, no return value, only for non-zero counts.
+__global__ void __launch_bounds__(256)
+slab_count_kernel(const int2 *__restrict__ info, const unsigned *__restrict__ slab_count, unsigned slab_cap,
+                  const uint4 *__restrict__ slabs, unsigned *__restrict__ tslabs, int *__restrict__ up, int *__restrict__ low) {
+    const int lane = threadIdx.x & 31;
+    const unsigned nwarps = (unsigned)(((ll)gridDim.x * blockDim.x) >> 5);
+    unsigned n_slots = *slab_count;
+    if (n_slots > slab_cap) n_slots = slab_cap;
+    for (unsigned slot = (unsigned)((blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5); slot < n_slots; slot += nwarps) {
+        const int2 inf = info[slot];
+        if (inf.x == 0) continue;
+        const ll g = inf.x - 1, J = inf.y & 0x3fffffff;
+        const uint4 h = slabs[(size_t)slot * 32 + lane];
+        const int c = __popc(h.x) + __popc(h.y) + __popc(h.z) + __popc(h.w);
+        if (c) atomicAdd(up + g * 32 + lane, c);
+        unsigned *ts = tslabs + (size_t)slot * 128;
+        const unsigned wds[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const unsigned m = transpose32(wds[w], lane);
+            ts[32 * w + lane] = m;
+            if (m) atomicAdd(low + J * TT + 32 * w + lane, __popc(m));
+        }
+    }
+}
+
+__global__ void deg_sum_kernel(const int *__restrict__ up, const int *__restrict__ low, ll n, int *__restrict__ deg) {
+    const ll r = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (r <= n) deg[r] = r < n ? up[r] + low[r] + 1 : 0;  // deg[n] = 0: the scan leaves nnz in row_ptr[n]
+}
+
 // One CTA per row tile T; warps 0-3 walk the part of the rows below the diagonal (one row quarter each, one row per
 // lane): bits of the row's COLUMN in the slabs above it (dirT[T][.], row quarters ascending; the first pass transposes
 // word q of such a slab -- 32 rows x the 32 columns of this quarter -- and leaves the result for the second); warps 4-7 the part above:
@@ -1078,10 +1111,10 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
         P.bslabs = ctx->b_tband.as<uint4>();
         unsigned *tslabs = (unsigned *)(P.bslabs + 32 * (size_t)slab_cap);
         P.slab_cap = (unsigned)slab_cap;
-        CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(int2) * (size_t)slab_cap + sizeof(int) * (size_t)n_pad));
+        CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(int2) * (size_t)slab_cap + sizeof(int) * 2 * (size_t)n_pad));
         P.info = ctx->b_tmp0.as<int2>();
-        int *low = (int *)(P.info + slab_cap);
-        CNN_CUDA(cudaMemsetAsync(P.info, 0, sizeof(int2) * (size_t)slab_cap, st));
+        int *low = (int *)(P.info + slab_cap), *up = low + n_pad;
+        CNN_CUDA(cudaMemsetAsync(P.info, 0, sizeof(int2) * (size_t)slab_cap + sizeof(int) * 2 * (size_t)n_pad, st));
         CNN_CUDA(cudaMemsetAsync(dir, 0, sizeof(unsigned) * 2 * dir_entries, st));
         CNN_CUDA(cudaMemsetAsync(slab_count, 0, 2 * sizeof(unsigned) + 2 * sizeof(unsigned long long), st));
         CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>() + n, 0, sizeof(int), st));
@@ -1100,9 +1133,9 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
             else
                 tile_resolve_kernel<false><<<rb, RL_WARPS * 32, 0, st>>>(d_x, (int)d, P.info, slab_count, P.slab_cap, (unsigned *)P.slabs, P.bslabs,
                                                                radius_cutoff, band_count, rej_count);
-            tile_rows_kernel<false><<<(int)n_tiles, 256, 0, st>>>(dir, dirT, P.slabs, tslabs, n, n_tiles, ctx->b_deg.as<int>(), low,
-                                                                  nullptr, nullptr);
-            CNN_LAUNCHED(ctx, 2);
+            slab_count_kernel<<<rb, 256, 0, st>>>(P.info, slab_count, P.slab_cap, P.slabs, tslabs, up, low);
+            deg_sum_kernel<<<cnn_blocks(n + 1, 256), 256, 0, st>>>(up, low, n, ctx->b_deg.as<int>());
+            CNN_LAUNCHED(ctx, 3);
             CNN_KERNEL_CHECK();
         }
         CNN_CUDA(cudaMemcpyAsync(hb, bad, 4 * sizeof(int) + 2 * sizeof(unsigned) + 2 * sizeof(unsigned long long),

@@ -107,6 +107,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+// one lane of a converged warp (the others skip the block, nobody diverges for good)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------
@@ -500,13 +510,15 @@ __device__ __forceinline__ void classify32(float (&v)[32], const float *nc, floa
 // MMA groups, which halves the L2 -> shared-memory traffic per flop.  CTAs are launched in order of decreasing work.
 // Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocation, warps 2-5 = epilogue of row tile 2c, warps 6-9 of row
 // tile 2c+1 (one TMEM lane quarter each).  Nothing depends on the order in which tiles are visited.
+template <int ATOMS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tensor_tiles_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const TensorParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: 2 A tiles | nsb B stages | barriers | tmem slot | per-warp column norms
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the address space
-    const int atoms = P.atoms, nsb = P.nsb;
+    constexpr int atoms = ATOMS;
+    const int nsb = P.nsb;
     const uint32_t tile_bytes = (uint32_t)atoms * ATOM_BYTES;
     uint8_t *sA = smem;
     uint8_t *sB = smem + 2 * tile_bytes;
@@ -555,33 +567,44 @@ tensor_tiles_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            // instruction descriptor: D f32, A/B fp16 (format 0), both K-major, N = 128, M = 128
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(TT >> 4) << 24);
-            const uint32_t a_addr = smem_u32(sA);
-            mbar_wait(a_full, 0);
-            ll t = 0;
-            TileIter it;
-            it.init(P.skip, I0, n_tiles, P.words);
-            for (ll j = it.next(); j >= 0; j = it.next(), ++t) {
-                const int s = (int)(t % nsb);
-                mbar_wait(full + s, (uint32_t)((t / nsb) & 1));          // TMA has landed this B tile
-                const uint32_t b_addr = smem_u32(sB + s * tile_bytes);
-                // the tile (I0 + 1, I0) below the diagonal is computed too (its bits are dropped by the epilogue):
-                // every accumulator stage is then used on every second step and the phases stay in lock step
-                for (int rt = 0; rt < 2; ++rt) {
-                    const int ts = (int)((t & 1) << 1) | rt;
-                    mbar_wait(t_empty + ts, (uint32_t)((t >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)ts * TT;
-                    for (int k = 0; k < atoms * 4; ++k) {  // UMMA K = 16 halves = 32 bytes inside the swizzle atom
-                        const uint32_t off = (uint32_t)(k >> 2) * ATOM_BYTES + (uint32_t)(k & 3) * 32;
-                        tc_mma(d_tmem, umma_desc(a_addr + rt * tile_bytes + off), umma_desc(b_addr + off), idesc, k > 0);
+        // The WHOLE warp walks the loop (waits included) and one elected lane issues: addresses, descriptors and the
+        // loop state then live in uniform registers and the 12 tcgen05.mma of a tile go out back to back.  (With
+        // "if (lane == 0)" around the loop the compiler wrapped every MMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+        // sequence, ~23 instructions of one thread each: 160 cycles per MMA against 64 in the tensor pipe -- the tile pass
+        // of C3 took 0.70 ms with an empty epilogue.)
+        // instruction descriptor: D f32, A/B fp16 (format 0), both K-major, N = 128, M = 128
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(TT >> 4) << 24);
+        const uint64_t desc_a0 = umma_desc(smem_u32(sA)), desc_a1 = umma_desc(smem_u32(sA) + tile_bytes);
+        mbar_wait(a_full, 0);
+        ll t = 0;
+        TileIter it;
+        it.init(P.skip, I0, n_tiles, P.words);
+        for (ll j = it.next(); j >= 0; j = it.next(), ++t) {
+            const int s = (int)(t % nsb);
+            mbar_wait(full + s, (uint32_t)((t / nsb) & 1));          // TMA has landed this B tile
+            const uint64_t desc_b = umma_desc(smem_u32(sB + s * tile_bytes));
+            // the tile (I0 + 1, I0) below the diagonal is computed too (its bits are dropped by the epilogue):
+            // every accumulator stage is then used on every second step and the phases stay in lock step
+#pragma unroll
+            for (int rt = 0; rt < 2; ++rt) {
+                const int ts = (int)((t & 1) << 1) | rt;
+                mbar_wait(t_empty + ts, (uint32_t)((t >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)ts * TT;
+                const uint64_t desc_a = rt ? desc_a1 : desc_a0;
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < ATOMS * 4; ++k) {  // UMMA K = 16 halves = 32 bytes inside the swizzle atom
+                        // descriptor address field counts 16-byte units
+                        const uint64_t off = (uint64_t)((k >> 2) * (ATOM_BYTES >> 4) + (k & 3) * 2);
+                        tc_mma(d_tmem, desc_a + off, desc_b + off, idesc, k > 0);
                     }
                     tc_commit(t_full + ts);  // accumulator ready for the epilogue
                 }
-                tc_commit(empty + s);        // smem stage free once these MMAs have read it
+                __syncwarp();
             }
+            if (elect_one()) tc_commit(empty + s);        // smem stage free once these MMAs have read it
+            __syncwarp();
         }
     } else {
         // ===== epilogue: TMEM -> registers -> classify -> hit bitmaps =====
@@ -1095,7 +1118,9 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
 
     const size_t smem = (size_t)(2 + P.nsb) * atoms * ATOM_BYTES + 1024 /*alignment*/ + 20 * 8 +
                         EPI_WARPS * 2 * TT * sizeof(float) + 64;
-    CNN_CUDA(cudaFuncSetAttribute(tensor_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*tiles_kernel)(const CUtensorMap, const CUtensorMap, const TensorParams) =
+        atoms == 1 ? tensor_tiles_kernel<1> : atoms == 2 ? tensor_tiles_kernel<2> : atoms == 3 ? tensor_tiles_kernel<3> : tensor_tiles_kernel<4>;
+    CNN_CUDA(cudaFuncSetAttribute(tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // ---- the pass over the upper triangle, the exact decisions, the degrees (all of it repeated once with more
     //      room should the slabs not fit: the host learns that together with nnz) -------------------------------------
@@ -1120,7 +1145,7 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
         CNN_CUDA(cudaMemsetAsync(ctx->b_deg.as<int>() + n, 0, sizeof(int), st));
         {
             Span sp(ctx, T_SEARCH_COUNT);
-            tensor_tiles_kernel<<<(int)((n_tiles + 1) / 2), NUM_THREADS, smem, st>>>(mapA, mapB, P);
+            tiles_kernel<<<(int)((n_tiles + 1) / 2), NUM_THREADS, smem, st>>>(mapA, mapB, P);
             CNN_LAUNCHED(ctx, 1);
             CNN_KERNEL_CHECK();
         }

@@ -444,7 +444,8 @@ struct TileIter {
 // ---------------------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------------------
-#define NSB 3   // barrier slots reserved for the shared-memory stages of the B operand (2 are used; 1 for 4-atom tiles)
+#define NSB 8   // barrier slots for the shared-memory stages of the B operand; a stage is ONE 64-wide K atom (16 KB) of a
+                // column tile: the loads run two tiles and more ahead of the MMAs (whole-tile stages: only two fit)
 #define NST 4   // TMEM accumulator stages of 128 columns (MMA <-> epilogue): the whole 512-column TMEM
 #define EPI_WARPS 8   // epilogue warps: one per (row tile, TMEM lane quarter), all 128 columns each
 #define NUM_THREADS ((2 + EPI_WARPS) * 32)
@@ -470,6 +471,7 @@ struct TensorParams {
     int2 *info;                 // [slab_cap] (row quarter + 1, column tile | bit 30: holds borderline pairs) of the slabs in use, else (0, 0)
     unsigned *slab_count;       // slots handed out (may exceed slab_cap: then the pass is repeated)
     unsigned slab_cap;
+    int dbg;  // measurement only (CNNB200_TENSOR_DBG): 1 = the epilogue skips the classification, 2 = no MMA is issued
 };
 
 // 32 accumulator elements of one row against their column norms.  w = |X_j|^2 - 2 X_i.X_j is formed in place and its
@@ -515,17 +517,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 tensor_tiles_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const TensorParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: 2 A tiles | nsb B stages | barriers | tmem slot | per-warp column norms
+    // carve: 2 A tiles | nsb B atom stages | barriers | tmem slot | per-warp column norms
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the address space
     constexpr int atoms = ATOMS;
     const int nsb = P.nsb;
     const uint32_t tile_bytes = (uint32_t)atoms * ATOM_BYTES;
     uint8_t *sA = smem;
     uint8_t *sB = smem + 2 * tile_bytes;
-    uint64_t *bars = (uint64_t *)(smem + (2 + nsb) * tile_bytes);
+    uint64_t *bars = (uint64_t *)(smem + 2 * tile_bytes + nsb * ATOM_BYTES);
     uint64_t *a_full = bars, *full = bars + 2, *empty = full + NSB, *t_full = empty + NSB, *t_empty = t_full + NST;
     uint32_t *tmem_slot = (uint32_t *)(t_empty + NST);
-    float *ncs = (float *)(bars + 20);                  // [EPI_WARPS][2][TT], 16-byte aligned
+    float *ncs = (float *)(bars + 32);                  // [EPI_WARPS][2][TT], 16-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const ll n_tiles = P.n_tiles;
@@ -548,23 +550,29 @@ tensor_tiles_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+        // ===== TMA producer (whole warp in the loop, one elected lane issues) =====
+        if (elect_one()) {
             mbar_expect_tx(a_full, 2 * tile_bytes);   // rows past the end of the operand are zero-filled
             for (int rt = 0; rt < 2; ++rt)
                 for (int a = 0; a < atoms; ++a)
                     tma_load_2d(sA + rt * tile_bytes + a * ATOM_BYTES, &mapA, a * KATOM, (int)((I0 + rt) * TT), a_full);
-            ll t = 0;
-            TileIter it;
-            it.init(P.skip, I0, n_tiles, P.words);
-            for (ll j = it.next(); j >= 0; j = it.next(), ++t) {
-                const int s = (int)(t % nsb);
-                mbar_wait(empty + s, (uint32_t)((t / nsb) & 1) ^ 1);
-                mbar_expect_tx(full + s, tile_bytes);
-                for (int a = 0; a < atoms; ++a)
-                    tma_load_2d(sB + s * tile_bytes + a * ATOM_BYTES, &mapB, a * KATOM, (int)(j * TT), full + s);
-            }
         }
+        __syncwarp();
+        int s = 0;
+        uint32_t ph = 1;  // parity of the "empty" phase a fresh barrier passes
+        TileIter it;
+        it.init(P.skip, I0, n_tiles, P.words);
+        for (ll j = it.next(); j >= 0; j = it.next())
+#pragma unroll
+            for (int a = 0; a < ATOMS; ++a) {
+                mbar_wait(empty + s, ph);
+                if (elect_one()) {
+                    mbar_expect_tx(full + s, ATOM_BYTES);
+                    tma_load_2d(sB + s * ATOM_BYTES, &mapB, a * KATOM, (int)(j * TT), full + s);
+                }
+                __syncwarp();
+                if (++s == nsb) { s = 0; ph ^= 1; }
+            }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         // The WHOLE warp walks the loop (waits included) and one elected lane issues: addresses, descriptors and the
@@ -577,34 +585,39 @@ tensor_tiles_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         const uint64_t desc_a0 = umma_desc(smem_u32(sA)), desc_a1 = umma_desc(smem_u32(sA) + tile_bytes);
         mbar_wait(a_full, 0);
         ll t = 0;
+        int s = 0;
+        uint32_t ph = 0;
         TileIter it;
         it.init(P.skip, I0, n_tiles, P.words);
         for (ll j = it.next(); j >= 0; j = it.next(), ++t) {
-            const int s = (int)(t % nsb);
-            mbar_wait(full + s, (uint32_t)((t / nsb) & 1));          // TMA has landed this B tile
-            const uint64_t desc_b = umma_desc(smem_u32(sB + s * tile_bytes));
             // the tile (I0 + 1, I0) below the diagonal is computed too (its bits are dropped by the epilogue):
             // every accumulator stage is then used on every second step and the phases stay in lock step
+            const int ts0 = (int)((t & 1) << 1);
 #pragma unroll
-            for (int rt = 0; rt < 2; ++rt) {
-                const int ts = (int)((t & 1) << 1) | rt;
-                mbar_wait(t_empty + ts, (uint32_t)((t >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
+            for (int a = 0; a < ATOMS; ++a) {
+                mbar_wait(full + s, ph);          // TMA has landed this atom of the B tile
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)ts * TT;
-                const uint64_t desc_a = rt ? desc_a1 : desc_a0;
-                if (elect_one()) {
+                const uint64_t desc_b = umma_desc(smem_u32(sB + s * ATOM_BYTES));
 #pragma unroll
-                    for (int k = 0; k < ATOMS * 4; ++k) {  // UMMA K = 16 halves = 32 bytes inside the swizzle atom
-                        // descriptor address field counts 16-byte units
-                        const uint64_t off = (uint64_t)((k >> 2) * (ATOM_BYTES >> 4) + (k & 3) * 2);
-                        tc_mma(d_tmem, desc_a + off, desc_b + off, idesc, k > 0);
+                for (int rt = 0; rt < 2; ++rt) {
+                    if (a == 0) {
+                        mbar_wait(t_empty + ts0 + rt, (uint32_t)((t >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
+                        tc_fence_after();
                     }
-                    tc_commit(t_full + ts);  // accumulator ready for the epilogue
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(ts0 + rt) * TT;
+                    const uint64_t desc_a = (rt ? desc_a1 : desc_a0) + (uint64_t)(a * (ATOM_BYTES >> 4));  // 16-byte units
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 4 && !(P.dbg & 2); ++k)   // UMMA K = 16 halves = 32 bytes inside the swizzle atom
+                            tc_mma(d_tmem, desc_a + (uint64_t)(k * 2), desc_b + (uint64_t)(k * 2), idesc, a > 0 || k > 0);
+                        if (a == ATOMS - 1) tc_commit(t_full + ts0 + rt);  // accumulator ready for the epilogue
+                    }
+                    __syncwarp();
                 }
+                if (elect_one()) tc_commit(empty + s);        // atom stage free once these MMAs have read it
                 __syncwarp();
+                if (++s == nsb) { s = 0; ph ^= 1; }
             }
-            if (elect_one()) tc_commit(empty + s);        // smem stage free once these MMAs have read it
-            __syncwarp();
         }
     } else {
         // ===== epilogue: TMEM -> registers -> classify -> hit bitmaps =====
@@ -648,6 +661,7 @@ tensor_tiles_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     tc_fence_before();
                     mbar_arrive(t_empty + ts);
                 }
+                if (P.dbg & 1) { hi[2 * hp] = hi[2 * hp + 1] = lo[2 * hp] = lo[2 * hp + 1] = __float_as_uint(va[0] + vb[31]) == 0x12345u; continue; }
                 classify32(va, nc + hp * 64, thr_hi, thr_lo, hi[2 * hp], lo[2 * hp]);
                 classify32(vb, nc + hp * 64 + 32, thr_hi, thr_lo, hi[2 * hp + 1], lo[2 * hp + 1]);
             }
@@ -1109,14 +1123,18 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     P.n = n;
     P.n_tiles = n_tiles;
     P.atoms = atoms;
-    P.nsb = atoms >= 4 ? 1 : 2;  // 2 A tiles + nsb B tiles must fit 227 KB
+    {   // 2 A tiles + nsb atom stages of B + 12 KB of barriers / norms / alignment must fit 227 KB
+        const int room = (227 * 1024 - 12 * 1024 - 2 * atoms * ATOM_BYTES) / ATOM_BYTES;
+        P.nsb = room < NSB ? room : NSB;
+    }
     P.skip = skip;
     P.words = words;
     P.dir = dir;
     P.dirT = dirT;
     P.slab_count = slab_count;
+    P.dbg = getenv("CNNB200_TENSOR_DBG") ? atoi(getenv("CNNB200_TENSOR_DBG")) : 0;
 
-    const size_t smem = (size_t)(2 + P.nsb) * atoms * ATOM_BYTES + 1024 /*alignment*/ + 20 * 8 +
+    const size_t smem = (size_t)(2 * atoms + P.nsb) * ATOM_BYTES + 1024 /*alignment*/ + 32 * 8 +
                         EPI_WARPS * 2 * TT * sizeof(float) + 64;
     void (*tiles_kernel)(const CUtensorMap, const CUtensorMap, const TensorParams) =
         atoms == 1 ? tensor_tiles_kernel<1> : atoms == 2 ? tensor_tiles_kernel<2> : atoms == 3 ? tensor_tiles_kernel<3> : tensor_tiles_kernel<4>;

@@ -270,13 +270,13 @@ def stage_rooflines(w, timings, n, d, nnz, stats, peak, world, words):
             useful = float(d) * n * (n - 1)
             kpad = ((3 * d + 63) // 64) * 64
             issued = float(n) * n * kpad          # upper triangle of 128x128 tiles, hi/lo split: K = 3*D padded to 64
-            out.append({"kernel": "tensor_pairs_kernel", "stage": "search_count", "bound": "tensor",
+            out.append({"kernel": "tensor_tiles_kernel", "stage": "search_count", "bound": "tensor",
                         "achieved": useful / (dur * 1e-3) / 1e12, "peak": peak["tf_sustained"], "unit": "TFLOP/s",
                         "frac": useful / (dur * 1e-3) / 1e12 / peak["tf_sustained"], "traffic": None, "ms_per_launch": dur,
                         "useful_flops": useful, "issued_flops_without_tile_pruning": issued,
                         "issued_tflops_upper_bound": issued / (dur * 1e-3) / 1e12,
-                        "limited_by": "tensor pipe / epilogue (tcgen05.ld + classification)",
-                        "note": "useful = SURVEY 8d's D*N*(N-1) flops (each unordered pair once); the bf16 hi/lo split "
+                        "limited_by": "tensor pipe (MMA-only run of the same tile walk: 0.42 ms on C3) + epilogue",
+                        "note": "useful = SURVEY 8d's D*N*(N-1) flops (each unordered pair once); the fp16 hi/lo split "
                                 "issues 3x that per visited tile; tile pruning skips tiles whose bounding balls are "
                                 "further apart than the radius (data dependent), so the issued figure is an upper bound"})
     if "ingest" in timings and timings["ingest"][1] and w["key"] == "c4":
@@ -608,7 +608,7 @@ def run_b200(args):
         "scaling": "weak" if replicas else "strong", "vs_baseline": None,
         "value_is": "inputs resident in HBM, CUDA events (bench contract); e2e.value is SURVEY 8d's metric: H2D of the inputs, "
                     "all kernels and collectives, D2H of the labels and the final synchronisation inside the timed region",
-        "dtype": {"c3": "bf16 hi/lo split tcgen05 filter, f32 accumulation + exact f64 recheck of borderline pairs / int32 indices "
+        "dtype": {"c3": "fp16 hi/lo split tcgen05 filter, f32 accumulation + exact f64 recheck of borderline pairs / int32 indices "
                         "/ int64 labels"}.get(key, "f64 (fp32 filter + exact f64 recheck of borderline pairs) / int32 indices / "
                                                    "int64 labels") if key != "c4" else "int32 indices / int64 offsets and labels",
         "data": "synthetic",

@@ -205,6 +205,7 @@ __global__ void col_mean_kernel(double *mean, const unsigned long long *mm, int 
 // that they never come near the cutoff.
 // One warp per row: lanes stride over the dimensions, so the f64 row comes in as one coalesced read and every fp16
 // segment goes out as contiguous 2-byte stores.
+template <bool PAIR>
 __global__ void __launch_bounds__(256)
 split_kernel(const double *__restrict__ x, const double *__restrict__ mean, const int *__restrict__ scale_e, ll n,
              ll n_pad, int d, int kt, __half *A, __half *B, float *norm, int *maxnorm_bits) {
@@ -216,20 +217,44 @@ split_kernel(const double *__restrict__ x, const double *__restrict__ mean, cons
     for (ll i = warp; i < n_pad; i += nwarps) {
         __half *a = A + i * kt, *b = B + i * kt;
         if (i >= n) {
-            for (int k = lane; k < kt; k += 32) { a[k] = zero; b[k] = zero; }
+            for (int k = 2 * lane; k < kt; k += 64) {  // kt is a multiple of 64
+                *reinterpret_cast<__half2 *>(a + k) = __halves2half2(zero, zero);
+                *reinterpret_cast<__half2 *>(b + k) = __halves2half2(zero, zero);
+            }
             if (lane == 0) norm[i] = INFINITY;
             continue;
         }
         double s = 0;
-        for (int k = lane; k < d; k += 32) {
-            const double X = scalbn(x[i * d + k] - mean[k], e);
-            s += X * X;
-            const __half hi = __double2half(X);
-            const __half lo = __double2half(X - (double)__half2float(hi));
-            a[k] = lo; a[d + k] = hi; a[2 * d + k] = hi;
-            b[k] = hi; b[d + k] = lo; b[2 * d + k] = hi;
+        if (PAIR) {  // d even: two adjacent dimensions per lane, 4-byte stores (a thread per dimension: 2-byte stores)
+            for (int k = 2 * lane; k < d; k += 64) {
+                const double X0 = scalbn(x[i * d + k] - mean[k], e), X1 = scalbn(x[i * d + k + 1] - mean[k + 1], e);
+                s += X0 * X0;
+                s += X1 * X1;
+                const __half h0 = __double2half(X0), h1 = __double2half(X1);
+                const __half l0 = __double2half(X0 - (double)__half2float(h0)), l1 = __double2half(X1 - (double)__half2float(h1));
+                const __half2 hi = __halves2half2(h0, h1), lo = __halves2half2(l0, l1);
+                *reinterpret_cast<__half2 *>(a + k) = lo;
+                *reinterpret_cast<__half2 *>(a + d + k) = hi;
+                *reinterpret_cast<__half2 *>(a + 2 * d + k) = hi;
+                *reinterpret_cast<__half2 *>(b + k) = hi;
+                *reinterpret_cast<__half2 *>(b + d + k) = lo;
+                *reinterpret_cast<__half2 *>(b + 2 * d + k) = hi;
+            }
+            for (int k = 3 * d + 2 * lane; k < kt; k += 64) {
+                *reinterpret_cast<__half2 *>(a + k) = __halves2half2(zero, zero);
+                *reinterpret_cast<__half2 *>(b + k) = __halves2half2(zero, zero);
+            }
+        } else {
+            for (int k = lane; k < d; k += 32) {
+                const double X = scalbn(x[i * d + k] - mean[k], e);
+                s += X * X;
+                const __half hi = __double2half(X);
+                const __half lo = __double2half(X - (double)__half2float(hi));
+                a[k] = lo; a[d + k] = hi; a[2 * d + k] = hi;
+                b[k] = hi; b[d + k] = lo; b[2 * d + k] = hi;
+            }
+            for (int k = 3 * d + lane; k < kt; k += 32) { a[k] = zero; b[k] = zero; }
         }
-        for (int k = 3 * d + lane; k < kt; k += 32) { a[k] = zero; b[k] = zero; }
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) {
             const float sf = (float)s;
@@ -265,50 +290,80 @@ __global__ void tensor_setup_kernel(const int *maxnorm_bits, const int *scale_e,
 // is produced in the sorted index space together with perm[] (sorted position -> caller index), as in the grid path.
 #define N_PIVOTS 64
 
-// one warp per point: the row comes in with one coalesced read (lanes stride over the dimensions); each lane then owns
-// two pivots (n_piv <= 64) and walks the dimensions, the point's coordinate broadcast by a shuffle, the pivots in shared
-// memory as floats [d][n_piv] -- no reduction per pivot, one arg-min at the end
+// A warp takes FOUR points at a time: the rows come in with coalesced reads (lanes stride over the dimensions); each lane
+// then owns two pivots (n_piv <= 64) and walks the dimensions, the points' coordinates broadcast by shuffles, the pivots in
+// shared memory as floats [d][n_piv].  Only the inner products are accumulated (|x - p|^2 = |x|^2 - 2 x.p + |p|^2: 14
+// instructions per dimension for 4 points x 2 pivots); one arg-min per point at the end.  fp32 is enough: whatever the
+// assignment, the tile pruning works from the bounding balls of the tiles that result.
 __global__ void __launch_bounds__(256)
 pivot_assign_kernel(const double *__restrict__ x, ll n, int d, int n_piv, unsigned long long *keys, int *idx) {
-    extern __shared__ float piv[];  // [d][n_piv]
+    extern __shared__ float piv[];  // [d][n_piv] | [n_piv] squared norms
+    float *pn = piv + (size_t)d * n_piv;
     const unsigned full = 0xffffffffu;
     for (int t = threadIdx.x; t < n_piv * d; t += blockDim.x) {
         const int p = t / d, k = t - p * d;
         piv[k * n_piv + p] = (float)x[(ll)((double)p * (double)n / (double)n_piv) * d + k];
     }
     __syncthreads();
+    for (int p = threadIdx.x; p < n_piv; p += blockDim.x) {
+        float sq = 0.f;
+        for (int k = 0; k < d; ++k) sq = fmaf(piv[k * n_piv + p], piv[k * n_piv + p], sq);
+        pn[p] = sq;
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const bool has0 = lane < n_piv, has1 = lane + 32 < n_piv;
+    const float pn0 = has0 ? pn[lane] : 0.f, pn1 = has1 ? pn[lane + 32] : 0.f;
     ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
     const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
-    for (ll i = warp; i < n; i += nwarps) {
-        float xi[3];  // d <= 85 < 96: at most 3 coordinates per lane
+    for (ll i0 = warp * 4; i0 < n; i0 += nwarps * 4) {
+        float xi[4][3];  // d <= 85 < 96: at most 3 coordinates per lane and point
+        float xx[4];
 #pragma unroll
-        for (int u = 0; u < 3; ++u) xi[u] = lane + 32 * u < d ? (float)x[i * d + lane + 32 * u] : 0.f;
-        float s0 = 0.f, s1 = 0.f;
+        for (int p = 0; p < 4; ++p) {
+            const ll i = i0 + p < n ? i0 + p : n - 1;
+            float sq = 0.f;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                xi[p][u] = lane + 32 * u < d ? (float)x[i * d + lane + 32 * u] : 0.f;
+                sq = fmaf(xi[p][u], xi[p][u], sq);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(full, sq, o);
+            xx[p] = sq;
+        }
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
             const int kn = d - 32 * u < 32 ? d - 32 * u : 32;
             for (int kk = 0; kk < kn; ++kk) {
-                const float xv = __shfl_sync(full, xi[u], kk);
                 const float *row = piv + (32 * u + kk) * n_piv;
-                const float t0 = xv - (has0 ? row[lane] : 0.f), t1 = xv - (has1 ? row[lane + 32] : 0.f);
-                s0 = fmaf(t0, t0, s0);
-                s1 = fmaf(t1, t1, s1);
+                const float r0 = has0 ? row[lane] : 0.f, r1 = has1 ? row[lane + 32] : 0.f;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float xv = __shfl_sync(full, xi[p][u], kk);
+                    s0[p] = fmaf(xv, r0, s0[p]);
+                    s1[p] = fmaf(xv, r1, s1[p]);
+                }
             }
         }
-        float best = has0 ? s0 : INFINITY;
-        int arg = lane;
-        if (has1 && s1 < best) { best = s1; arg = lane + 32; }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            const float ob = __shfl_xor_sync(full, best, o);
-            const int oa = __shfl_xor_sync(full, arg, o);
-            if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
-        }
-        if (lane == 0) {
-            keys[i] = ((unsigned long long)arg << 32) | (unsigned long long)__float_as_uint(best);  // best >= 0: bits are ordered
-            idx[i] = (int)i;
+        for (int p = 0; p < 4; ++p) {
+            float best = has0 ? fmaf(-2.f, s0[p], pn0) : INFINITY;
+            int arg = lane;
+            const float b1 = fmaf(-2.f, s1[p], pn1);
+            if (has1 && b1 < best) { best = b1; arg = lane + 32; }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const float ob = __shfl_xor_sync(full, best, o);
+                const int oa = __shfl_xor_sync(full, arg, o);
+                if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+            }
+            if (lane == 0 && i0 + p < n) {
+                const float dist = fmaxf(best + xx[p], 0.f);  // >= 0: the bits are ordered
+                keys[i0 + p] = ((unsigned long long)arg << 32) | (unsigned long long)__float_as_uint(dist);
+                idx[i0 + p] = (int)(i0 + p);
+            }
         }
     }
 }
@@ -1044,7 +1099,7 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
         CNN_TRY(cnn_ensure(ctx, ctx->b_lab_keys2, sizeof(unsigned long long) * (size_t)n));
         CNN_TRY(cnn_ensure(ctx, ctx->b_xperm, sizeof(double) * (size_t)n * (size_t)d));
         unsigned long long *pk = ctx->b_lab_keys.as<unsigned long long>(), *pk2 = ctx->b_lab_keys2.as<unsigned long long>();
-        pivot_assign_kernel<<<ctx->sm_count * 8, 256, sizeof(float) * (size_t)n_piv * (size_t)d, st>>>(d_x, n, (int)d, n_piv, pk,
+        pivot_assign_kernel<<<ctx->sm_count * 8, 256, sizeof(float) * (size_t)n_piv * (size_t)(d + 1), st>>>(d_x, n, (int)d, n_piv, pk,
                                                                                                       ctx->b_idx.as<int>());
         size_t need = 0;
         CNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, pk, pk2, ctx->b_idx.as<int>(), ctx->b_perm.as<int>(), (int)n, 0, 40, st));
@@ -1101,8 +1156,9 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
         CNN_CUDA(cudaMemsetAsync(mm, 0xff, sizeof(unsigned long long) * CM_MAXD, st));  // minima start at the largest code
         col_sum_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(d_x, n, (int)d, mean, mm);
         col_mean_kernel<<<1, CM_MAXD, 0, st>>>(mean, mm, (int)d, n, scale_e);
-        split_kernel<<<cnn_blocks(n_pad, 8) < ctx->sm_count * 32 ? cnn_blocks(n_pad, 8) : ctx->sm_count * 32, 256, 0, st>>>(
-            d_x, mean, scale_e, n, n_pad, (int)d, kt, A, B, norm, maxbits);
+        const int sb = cnn_blocks(n_pad, 8) < ctx->sm_count * 32 ? cnn_blocks(n_pad, 8) : ctx->sm_count * 32;
+        if (d % 2 == 0) split_kernel<true><<<sb, 256, 0, st>>>(d_x, mean, scale_e, n, n_pad, (int)d, kt, A, B, norm, maxbits);
+        else split_kernel<false><<<sb, 256, 0, st>>>(d_x, mean, scale_e, n, n_pad, (int)d, kt, A, B, norm, maxbits);
         tensor_setup_kernel<<<1, 1, 0, st>>>(maxbits, scale_e, R, coef, thr, bad);
         CNN_LAUNCHED(ctx, 4);
         CNN_KERNEL_CHECK();

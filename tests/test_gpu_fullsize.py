@@ -39,7 +39,7 @@ def test_c3_full_size_equals_oracle_brute_force(ctx):
     cl = cluster.Clustering(x)
     cl.fitter._ctx = ctx
     cl.fit(p["radius_cutoff"], p["cnn_cutoff"], member_cutoff=p["member_cutoff"], v=False)
-    assert ctx.stats()["search_method"] == "tensor"      # tensor_pairs_kernel served the default call
+    assert ctx.stats()["search_method"] == "tensor"      # tensor_tiles_kernel served the default call
     assert np.array_equal(cl.labels, want)
     assert want.max() >= 10
     grp, gci = ctx.neighbours_export()

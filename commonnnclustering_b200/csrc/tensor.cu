@@ -674,6 +674,7 @@ tensor_tiles_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 if (++s == nsb) { s = 0; ph ^= 1; }
             }
         }
+        if (elect_one() && t) atomicAdd(P.slab_count + 1, (unsigned)(2 * t));  // 128 x 128 tiles this CTA put through the MMA
     } else {
         // ===== epilogue: TMEM -> registers -> classify -> hit bitmaps =====
         const unsigned fullm = 0xffffffffu;
@@ -1258,7 +1259,7 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
         CNN_KERNEL_CHECK();
     }
     ctx->stats[ST_RECHECK] = (ll)((unsigned long long *)(hb + 6))[0];
-    ctx->stats[ST_DIST] = n * (n - 1) / 2;
+    ctx->stats[ST_DIST] = (ll)hb[5] * TT * TT;  // pairs in the tiles that were visited (the others were ruled out by the bounding balls)
     ctx->n = n;
     ctx->nnz = nnz;
     ctx->max_deg = max_deg;

@@ -341,7 +341,7 @@ int cnnb200_host_unregister(void *ptr);
 /* Counters of the last fit / search, for measurement (all optional, HOST):
  *   stats[0] candidate edges (i<j, both core)      stats[1] CN checks executed
  *   stats[2] edges accepted by a check             stats[3] edges skipped (already connected)
- *   stats[4] distance evaluations (neighbour search, count pass)
+ *   stats[4] distance evaluations (neighbour search; tcgen05 filter: the pairs of the 128 x 128 tiles that were visited)
  *   stats[5] pairs re-checked in f64 (fp32 / tensor-core filter paths)
  *   stats[6] count mode: rows whose index window did not fit the shared-memory bitmap
  *   stats[7] which kernels served the last calls: bits 0-3 = method of the last cnnb200_neighbours_from_points

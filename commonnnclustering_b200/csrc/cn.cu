@@ -342,6 +342,25 @@ __device__ __forceinline__ int row_count(const int (&buf)[WIN_PF], const int *__
     return __reduce_add_sync(0xffffffffu, c);
 }
 
+// The same as a CHECK (|.| >= cutoff?) with the reference's early exits (SimilarityCheckerExtScreensorted._check,
+// _types.pyx:2654-2706): after the WIN_PF prefetched chunks the answer is often known -- enough common neighbours
+// already (long rows of dense regions overlap almost completely), or too few entries left to get there -- and the
+// rest of N(j), the part that still has to come from memory, is never read.
+__device__ __forceinline__ int row_check(const int (&buf)[WIN_PF], const int *__restrict__ rj, int mj, int lane,
+                                         const RowWin &w, int cutoff) {
+    int c = 0;
+#pragma unroll
+    for (int u = 0; u < WIN_PF; ++u) c += win_probe(w, buf[u]);
+    if (mj <= 32 * WIN_PF) return __reduce_add_sync(0xffffffffu, c) >= cutoff;
+    int total = __reduce_add_sync(0xffffffffu, c);
+    if (total >= cutoff) return 1;
+    if (total + (mj - 32 * WIN_PF) < cutoff) return 0;
+    c = 0;
+#pragma unroll 4
+    for (int t = lane + 32 * WIN_PF; t < mj; t += 32) c += win_probe(w, rj[t]);
+    return total + __reduce_add_sync(0xffffffffu, c) >= cutoff;
+}
+
 // One streamed row in flight: where it is, which lane of the current 32-edge block it belongs to, and
 // its first WIN_PF chunks.  Three of them rotate (fetch two ahead, consume the oldest), so that two
 // memory round trips overlap the probing of one row.
@@ -518,7 +537,7 @@ comp_worklist_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ col
                 win_set(w, cur_row, cur_m, lane);
             }
             int ok;
-            if (win_ready(w)) ok = row_count(f.buf, f.rj, f.mj, lane, w) >= cutoff;
+            if (win_ready(w)) ok = row_check(f.buf, f.rj, f.mj, lane, w, cutoff);
             else ok = warp_common<true>(cur_row, cur_m, f.rj, f.mj, cutoff, lane);
             if (lane == f.src) acc = ok;
             if (ok) {
@@ -1140,7 +1159,7 @@ cn_check_pairs_kernel(const ll *__restrict__ row_ptr, const int *__restrict__ co
                 if (w.span) {
                     int buf[WIN_PF];
                     row_prefetch(buf, rj, nj, lane);
-                    ok = row_count(buf, rj, nj, lane, w) >= cutoff;
+                    ok = row_check(buf, rj, nj, lane, w, cutoff);
                 } else {
                     ok = warp_common<true>(ri, ni, rj, nj, cutoff, lane);
                 }

@@ -40,6 +40,7 @@ SIGNATURES = {
     "cnnb200_neighbours_from_csr": [_P, _P, _P, C.c_int, C.c_int, C.c_int, _I64, _I64],
     "cnnb200_neighbours_from_padded": [_P, _P, _P, C.c_int, _I64, _I64],
     "cnnb200_neighbours_from_distances": [_P, _P, C.c_int, _I64, C.c_double],
+    "cnnb200_neighbours_from_condensed": [_P, _P, C.c_int, _I64, C.c_double],
     "cnnb200_neighbours_sort_rows": [_P, C.POINTER(C.c_int)],
     "cnnb200_neighbours_asymmetry": [_P, C.POINTER(_I64)],
     "cnnb200_neighbours_info": [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)],
@@ -268,6 +269,17 @@ class Context:
             raise ValueError("the distance matrix must be float64")
         dp, loc = _ptr_loc(dist)
         check(self._lib.cnnb200_neighbours_from_distances(self._h, dp, loc, dist.shape[0], float(radius_cutoff)))
+
+    def neighbours_from_condensed(self, dist, n, radius_cutoff):
+        """Neighbourhoods from condensed f64 distances ``[n (n - 1) / 2]`` (row-by-row upper triangle, the layout of
+        ``scipy.spatial.distance.pdist`` and of the reference's ``InputDataExtDistancesLinearMemoryview``)."""
+        n = int(n)
+        if len(dist.shape) != 1 or dist.shape[0] != n * (n - 1) // 2:
+            raise ValueError("condensed distances: expected a vector of n (n - 1) / 2 values")
+        if "float64" not in str(dist.dtype):
+            raise ValueError("the distances must be float64")
+        dp, loc = _ptr_loc(dist) if dist.shape[0] else (None, HOST)
+        check(self._lib.cnnb200_neighbours_from_condensed(self._h, dp, loc, n, float(radius_cutoff)))
 
     def neighbours_sort_rows(self) -> bool:
         """Sorts the held rows ascending when they are not; True when a sort was needed."""

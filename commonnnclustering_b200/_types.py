@@ -212,10 +212,16 @@ class InputDataComponents(InputData):
         return self._data
 
     def pin(self) -> bool:
-        """Page-locks the host array in place (once) so that every fit on these coordinates copies them at PCIe
-        speed; nothing is copied or cached, later changes to the array are seen as before.  Released with the object."""
+        """Page-locks the host array in place so that repeated fits on these coordinates copy them at PCIe speed;
+        nothing is copied or cached, later changes to the array are seen as before.  Released with the object.
+        The FIRST fit copies from pageable memory: registering and releasing 24 MB costs 3-4 ms, more than the one
+        pageable copy it would save -- the children of ``isolate`` are typically fitted once (C5: nine child fits,
+        30 ms of registrations)."""
         if not isinstance(self._data, np.ndarray) or self._data.nbytes < (1 << 20):
-            return False   # below a megabyte the registration costs more than the pageable copy it saves
+            return False   # below a megabyte the registration costs more than the pageable copies it saves
+        self._pin_calls = getattr(self, "_pin_calls", 0) + 1
+        if self._pin_calls < 2:
+            return False
         if getattr(self, "_pinned", None) is None:
             import weakref
 
@@ -253,6 +259,63 @@ class InputDataComponents(InputData):
                 start = end
         else:
             yield from ()
+
+
+class InputDataDistancesLinear(InputData):
+    """Pairwise distances in condensed form: the ``N (N - 1) / 2`` values ``d(a, b)``, ``a < b``, row by row (what
+    ``scipy.spatial.distance.pdist`` returns).  Reference: ``InputDataExtDistancesLinearMemoryview``,
+    ``_types.pyx:1112-1150``; used with ``MetricPrecomputed``.  Half the bytes of the square matrix, read once
+    (``cnnb200_neighbours_from_condensed``)."""
+
+    def __init__(self, data, *, n_points=None, meta=None):
+        if isinstance(data, np.ndarray):
+            data = np.ascontiguousarray(data, dtype=np.float64)
+        if len(data.shape) != 1:
+            raise ValueError("condensed distances are a 1-D sequence")
+        self._data = data
+        # the reference's own expression (_types.pyx:1121-1122)
+        self.n_points = int(0.5 * (np.sqrt(8 * data.shape[0] + 1) + 1)) if n_points is None else int(n_points)
+        if self.n_points * (self.n_points - 1) // 2 != data.shape[0]:
+            raise ValueError(f"{data.shape[0]} values are not the condensed distances of {self.n_points} points")
+        self.n_dim = 0
+        _meta = {"access_distances": True}
+        if meta is not None:
+            _meta.update(meta)
+        self.meta = _meta
+
+    @property
+    def data(self):
+        return self._data if isinstance(self._data, np.ndarray) else self._data.cpu().numpy()
+
+    @property
+    def device_or_host_array(self):
+        return self._data
+
+    def pin(self) -> bool:
+        """Page-locks the host vector in place from the second fit on (see InputDataComponents.pin)."""
+        if not isinstance(self._data, np.ndarray) or self._data.nbytes < (1 << 20):
+            return False
+        self._pin_calls = getattr(self, "_pin_calls", 0) + 1
+        if self._pin_calls < 2:
+            return False
+        if getattr(self, "_pinned", None) is None:
+            self._pinned = _pin_arrays(self, [self._data])
+        return self._pinned
+
+    def get_distance(self, point_a: int, point_b: int) -> float:
+        """``_get_distance`` of the reference (``_types.pyx:1129-1146``)."""
+        if point_a == point_b:
+            return 0.0
+        a, b = (point_b, point_a) if point_a > point_b else (point_a, point_b)
+        return float(self.data[a * (self.n_points - 1) - (a * a - a) // 2 + (b - a - 1)])
+
+    def get_subset(self, indices):
+        """The distances among the points ``indices`` (ascending), again in condensed form."""
+        idx = np.asarray(indices, dtype=np.int64)
+        m = idx.shape[0]
+        ia, ib = np.triu_indices(m, k=1)
+        a, b = idx[ia], idx[ib]
+        return type(self)(self.data[a * (self.n_points - 1) - (a * a - a) // 2 + (b - a - 1)], n_points=m)
 
 
 class InputDataNeighbourhoods(InputData):
@@ -522,7 +585,10 @@ class NeighboursGetterRadius(NeighboursGetter):
             # page-locked in place once so that every further fit (parameter scans) streams it at PCIe speed
             if hasattr(input_data, "pin"):
                 input_data.pin()
-            ctx.neighbours_from_distances(input_data.device_or_host_array, cluster_params.radius_cutoff)
+            if isinstance(input_data, InputDataDistancesLinear):
+                ctx.neighbours_from_condensed(input_data.device_or_host_array, input_data.n_points, cluster_params.radius_cutoff)
+            else:
+                ctx.neighbours_from_distances(input_data.device_or_host_array, cluster_params.radius_cutoff)
             return Neighbourhoods(ctx)
         self.prepare(ctx)
         ctx.neighbours_from_points(input_data.device_or_host_array, cluster_params.radius_cutoff,

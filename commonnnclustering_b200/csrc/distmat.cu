@@ -81,6 +81,27 @@ dist_fill_kernel(const unsigned *__restrict__ mask, ll n, ll words, const ll *__
     }
 }
 
+// degrees -> offsets, masks -> ascending rows, adoption by the context
+static int rows_from_masks(cnnb200_ctx *ctx, const unsigned *mask, int *deg, ll n, ll words) {
+    cudaStream_t st = ctx->stream;
+    ll nnz = 0, md = 0;
+    {
+        Span sp(ctx, T_SCAN);
+        CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, deg, n, ctx->b_row_ptr.as<ll>(), &nnz, &md));
+    }
+    CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)(nnz > 0 ? nnz : 1)));
+    {
+        Span sp(ctx, T_SEARCH_FILL);
+        ll blocks = (n + 7) / 8;
+        if (blocks > (ll)ctx->sm_count * 32) blocks = (ll)ctx->sm_count * 32;
+        dist_fill_kernel<<<(int)blocks, 256, 0, st>>>(mask, n, words, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
+        CNN_LAUNCHED(ctx, 1);
+    }
+    CNN_KERNEL_CHECK();
+    ctx->stats[ST_RECHECK] = 0;
+    return cnn_finish_csr(ctx, n, nnz, md, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
+}
+
 extern "C" int cnnb200_neighbours_from_distances(cnnb200_ctx *ctx, const double *dist, int loc, int64_t n,
                                                  double radius_cutoff) {
     if (!ctx || !dist) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_distances: NULL argument");
@@ -130,23 +151,142 @@ extern "C" int cnnb200_neighbours_from_distances(cnnb200_ctx *ctx, const double 
         }
     }
     CNN_KERNEL_CHECK();
-    ll nnz = 0, md = 0;
-    {
-        Span sp(ctx, T_SCAN);
-        CNN_TRY(cnn_scan_deg_to_row_ptr(ctx, deg, n, ctx->b_row_ptr.as<ll>(), &nnz, &md));
+    ctx->stats[ST_DIST] = n * n;
+    return rows_from_masks(ctx, mask, deg, n, words);
+}
+
+// ---- condensed distances ----------------------------------------------------------------------------------------
+// InputDataExtDistancesLinearMemoryview (_types.pyx:1112-1150) stores the N (N - 1) / 2 distances d(a, b), a < b, row
+// by row: d(a, b) sits at a (N - 1) - a (a - 1) / 2 + (b - a - 1); d(a, a) = 0.  The upper triangle of the bit matrix
+// follows from ONE coalesced pass over the vector (4 N^2 bytes, the compulsory traffic); the lower triangle is its
+// transpose, formed on the bits (N^2 / 8 bytes) by 32 x 32 block transposes.
+
+// one warp per (row, 1024-column block) at or right of the diagonal
+__global__ void __launch_bounds__(256)
+cond_mask_kernel(const double *__restrict__ cond, ll n, ll words, double rc, unsigned *__restrict__ mask) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const ll blocks_per_row = (n + DM_COLS - 1) / DM_COLS;
+    const ll items = n * blocks_per_row;
+    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    for (ll it = warp; it < items; it += nwarps) {
+        const ll r = it / blocks_per_row, blk = it - r * blocks_per_row;
+        const ll w = blk * 32 + lane;
+        if ((blk + 1) * DM_COLS <= r) {  // wholly left of the diagonal: filled by the transposition
+            if (w < words) mask[r * words + w] = 0u;
+            continue;
+        }
+        const double *src = cond + (r * (n - 1) - r * (r - 1) / 2) - r - 1;  // src[c] = d(r, c) for c > r
+        const ll c0 = blk * DM_COLS + lane;
+        unsigned word = 0;
+#pragma unroll
+        for (int k0 = 0; k0 < 32; k0 += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const ll c = c0 + (ll)(k0 + u) * 32;
+                v[u] = c >= n || c < r ? nan : (c == r ? 0.0 : __ldcs(src + c));  // NaN: never a neighbour
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned b = __ballot_sync(full, v[u] <= rc);
+                if (lane == k0 + u) word = b;
+            }
+        }
+        if (w < words) mask[r * words + w] = word;
     }
-    CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)(nnz > 0 ? nnz : 1)));
+}
+
+// lane l holds row l of a 32 x 32 bit block (bit c = column c); afterwards lane c holds column c (bit l = row l)
+__device__ __forceinline__ unsigned bit_transpose32(unsigned x, int lane) {
+#pragma unroll
+    for (int k = 16; k; k >>= 1) {
+        const unsigned m = k == 16 ? 0x0000ffffu : k == 8 ? 0x00ff00ffu : k == 4 ? 0x0f0f0f0fu : k == 2 ? 0x33333333u : 0x55555555u;
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, k);
+        x = (lane & k) ? ((x & ~m) | ((y & ~m) >> k)) : ((x & m) | ((y & m) << k));
+    }
+    return x;
+}
+
+// one warp per 32 x 32 bit block (I, J), J >= I, of the upper triangle: its transpose becomes block (J, I)
+__global__ void __launch_bounds__(256)
+mask_mirror_kernel(unsigned *__restrict__ mask, ll n, ll words) {
+    const int lane = threadIdx.x & 31;
+    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    for (ll it = warp; it < words * words; it += nwarps) {
+        const ll I = it / words, J = it - I * words;
+        if (J < I) continue;
+        const ll r = 32 * I + lane;
+        const unsigned x = r < n ? mask[r * words + J] : 0u;
+        const unsigned t = bit_transpose32(x, lane);
+        if (J == I) {
+            if (r < n) mask[r * words + I] = x | t;
+        } else {
+            const ll rt = 32 * J + lane;
+            if (rt < n) mask[rt * words + I] = t;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mask_degree_kernel(const unsigned *__restrict__ mask, ll n, ll words, int *__restrict__ deg) {
+    const int lane = threadIdx.x & 31;
+    ll warp = (blockIdx.x * (ll)blockDim.x + threadIdx.x) >> 5;
+    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    for (ll r = warp; r < n; r += nwarps) {
+        int c = 0;
+        for (ll w = lane; w < words; w += 32) c += __popc(mask[r * words + w]);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) deg[r] = c;
+    }
+}
+
+extern "C" int cnnb200_neighbours_from_condensed(cnnb200_ctx *ctx, const double *dist, int loc, int64_t n,
+                                                 double radius_cutoff) {
+    if (!ctx || (!dist && n > 1)) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_condensed: NULL argument");
+    if (n < 1) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_condensed: need n >= 1");
+    if (n >= (1ll << 31) - 1) CNN_FAIL(CNNB200_E_RANGE, "neighbours_from_condensed: n must be < 2^31-1");
+    if (radius_cutoff != radius_cutoff) CNN_FAIL(CNNB200_E_INVALID, "neighbours_from_condensed: radius_cutoff is NaN");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->have_nb = false;
+    ctx->have_points = false;
+    ctx->have_other = false;
+    ctx->have_comp = false;
+    const ll words = (n + 31) / 32, len = n * (n - 1) / 2;
+    CNN_TRY(cnn_ensure(ctx, ctx->b_tmp1, sizeof(unsigned) * (size_t)(n * words)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_deg, sizeof(int) * (size_t)(n + 1)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_row_ptr, sizeof(ll) * (size_t)(n + 1)));
+    CNN_CUDA(cudaMemsetAsync(ctx->b_deg.p, 0, sizeof(int) * (size_t)(n + 1), st));
+    unsigned *mask = ctx->b_tmp1.as<unsigned>();
+    int *deg = ctx->b_deg.as<int>();
+    const double *d_cond = dist;
+    if (loc != CNNB200_DEVICE && len > 0) {
+        Span sp(ctx, T_H2D);
+        CNN_TRY(cnn_ensure(ctx, ctx->b_tmp0, sizeof(double) * (size_t)len));
+        CNN_CUDA(cudaMemcpyAsync(ctx->b_tmp0.p, dist, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, st));
+        d_cond = ctx->b_tmp0.as<double>();
+    }
     {
-        Span sp(ctx, T_SEARCH_FILL);
-        ll blocks = (n + 7) / 8;
+        Span sp(ctx, T_SEARCH_COUNT);
+        const ll blocks_per_row = (n + DM_COLS - 1) / DM_COLS;
+        ll blocks = (n * blocks_per_row + 7) / 8;
         if (blocks > (ll)ctx->sm_count * 32) blocks = (ll)ctx->sm_count * 32;
-        dist_fill_kernel<<<(int)blocks, 256, 0, st>>>(mask, n, words, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
-        CNN_LAUNCHED(ctx, 1);
+        cond_mask_kernel<<<(int)blocks, 256, 0, st>>>(d_cond, n, words, radius_cutoff, mask);
+        ll mb = (words * words + 7) / 8;
+        if (mb > (ll)ctx->sm_count * 32) mb = (ll)ctx->sm_count * 32;
+        mask_mirror_kernel<<<(int)mb, 256, 0, st>>>(mask, n, words);
+        ll db = (n + 7) / 8;
+        if (db > (ll)ctx->sm_count * 32) db = (ll)ctx->sm_count * 32;
+        mask_degree_kernel<<<(int)db, 256, 0, st>>>(mask, n, words, deg);
+        CNN_LAUNCHED(ctx, 3);
     }
     CNN_KERNEL_CHECK();
-    ctx->stats[ST_DIST] = n * n;
-    ctx->stats[ST_RECHECK] = 0;
-    return cnn_finish_csr(ctx, n, nnz, md, ctx->b_row_ptr.as<ll>(), ctx->b_col_idx.as<int>());
+    ctx->stats[ST_DIST] = len;
+    return rows_from_masks(ctx, mask, deg, n, words);
 }
 
 // ---- ascending rows ------------------------------------------------------------------------------------------------

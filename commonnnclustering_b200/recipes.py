@@ -57,6 +57,7 @@ COMPONENT_NAME_TYPE_MAP = {
         "neighbourhoods_b200": _types.InputDataNeighbourhoods,
         "neighbourhoods_mview": _types.InputDataNeighbourhoods,
         "neighbourhoods_csr": _types.InputDataNeighbourhoodsCSR,
+        "distances_linear": _types.InputDataDistancesLinear,   # condensed distances (InputDataExtDistancesLinearMemoryview)
     },
     "preparation_hook": {
         "pass": prepare_pass,

@@ -147,6 +147,12 @@ int cnnb200_neighbours_from_padded(cnnb200_ctx *ctx, const int64_t *padded,
 int cnnb200_neighbours_from_distances(cnnb200_ctx *ctx, const double *dist, int loc, int64_t n,
                                       double radius_cutoff);
 
+/* The same from CONDENSED distances: the N (N - 1) / 2 values d(a, b), a < b, row by row (d(a, b) at
+ * a (N - 1) - a (a - 1) / 2 + (b - a - 1), d(a, a) = 0) -- the layout of InputDataExtDistancesLinearMemoryview
+ * (_types.pyx:1112-1150, `_get_distance`).  dist: f64 [n (n - 1) / 2] in `loc` (may be NULL for n = 1); read once. */
+int cnnb200_neighbours_from_condensed(cnnb200_ctx *ctx, const double *dist, int loc, int64_t n,
+                                      double radius_cutoff);
+
 /* Brings the rows of the held neighbourhood structure into ascending order when they are not
  * (the reference's "neighbourhoods" recipe, recipes.py:340-348, takes lists in any order:
  * NeighboursGetterExtLookup with is_sorted=False, _types.pyx:1791-1804).  A borrowed col_idx is left

@@ -65,8 +65,12 @@ def test_sass_shows_the_tcgen05_tma_path():
     total, per_kernel, arch = mod.counts()
     assert arch == ["sm_100a"]
     assert total["UTCHMMA"] >= 8 and total["LDTM"] >= 4 and total["UTMALDG"] >= 8 and total["SYNCS"] >= 8
-    tensor = [v for k, v in per_kernel.items() if "tensor_tiles_kernel" in k]
-    assert tensor and tensor[0].get("UTCHMMA", 0) >= 8 and tensor[0].get("LDTM", 0) >= 4 and tensor[0].get("UTMALDG", 0) >= 8
+    # one instantiation per number of 64-wide K atoms (1 .. 4): 8 MMAs (2 row tiles x 4 K steps) and 3 TMA loads
+    # (2 A tiles + the B stage) per atom, four tcgen05.ld per accumulator tile
+    tensor = sorted((v for k, v in per_kernel.items() if "tensor_tiles_kernel" in k), key=lambda v: v.get("UTCHMMA", 0))
+    assert len(tensor) == 4
+    for atoms, v in enumerate(tensor, start=1):
+        assert v.get("UTCHMMA", 0) == 8 * atoms and v.get("LDTM", 0) >= 4 and v.get("UTMALDG", 0) == 3 * atoms
     committed = open(os.path.join(ROOT, "profiles", "sass_summary.txt")).read()
     for m in ("UTCHMMA", "LDTM", "UTMALDG"):
         assert re.search(rf"^{m}\s+{total[m]}\b", committed, flags=re.M), m

@@ -267,6 +267,51 @@ def test_distance_matrix_neighbour_sets(ctx):
         ctx.neighbours_from_distances(np.zeros((3, 3), dtype=np.float32), 1.0)
 
 
+def test_condensed_distances_equal_square_matrix(ctx):
+    """Condensed distances (``InputDataExtDistancesLinearMemoryview``'s layout, _types.pyx:1112-1150) give the neighbour
+    sets of the square matrix they stand for -- host and device vectors, sizes around the 32 / 1024 block edges, NaN /
+    inf entries, a cutoff ON a value, a negative cutoff -- and the same labels through ``Clustering``."""
+    import torch
+
+    from commonnnclustering_b200 import _types
+
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 31, 33, 64, 1023, 1025, 2500):
+        dm = rng.random((n, n))
+        dm = np.minimum(dm, dm.T)
+        np.fill_diagonal(dm, 0.0)
+        if n > 40:
+            dm[5, 7] = dm[7, 5] = np.nan
+            dm[1, 2] = dm[2, 1] = np.inf
+            dm[3, 40] = dm[40, 3] = -np.inf
+        iu = np.triu_indices(n, k=1)
+        cond = np.ascontiguousarray(dm[iu])
+        r = float(dm[n // 2, n // 3]) if n > 2 else 0.5
+        rp, ci = port.neighbours_from_distances(dm, r)
+        for arr in (cond, torch.from_numpy(cond).cuda()):
+            ctx.neighbours_from_condensed(arr, n, r)
+            got_rp, got_ci = ctx.neighbours_export()
+            np.testing.assert_array_equal(got_rp, rp)
+            np.testing.assert_array_equal(got_ci, ci)
+        ctx.neighbours_from_condensed(cond, n, -1.0)     # d(a, a) = 0 > -1: only the -inf entries pass
+        assert ctx.neighbours_info()[1] == int(port.neighbours_from_distances(dm, -1.0)[0][-1])
+    with pytest.raises(ValueError):
+        ctx.neighbours_from_condensed(np.zeros(4), 4, 1.0)
+    # through the component interface: InputDataDistancesLinear + MetricPrecomputed
+    x = datasets.blobs_2d(1500)
+    dm = np.sqrt(((x[:, None, :] - x[None, :, :]) ** 2).sum(-1))
+    data = _types.InputDataDistancesLinear(np.ascontiguousarray(dm[np.triu_indices(1500, k=1)]))
+    assert data.n_points == 1500 and data.get_distance(7, 3) == dm[3, 7] and data.get_distance(4, 4) == 0.0
+    cl = cluster.Clustering(data, recipe="distances")
+    cl.fit(0.12, 8, v=False)
+    want = cluster.Clustering(dm, recipe="distances")
+    want.fit(0.12, 8, v=False)
+    np.testing.assert_array_equal(cl.labels, want.labels)
+    np.testing.assert_array_equal(cl.labels, port.fit_distances(dm, 0.12, 8))
+    sub = data.get_subset(np.arange(0, 1500, 3))
+    np.testing.assert_array_equal(sub.data, dm[::3, ::3][np.triu_indices(500, k=1)])
+
+
 def test_new_input_paths_edge_cases(ctx):
     # distance matrix with no neighbours at all (not even the diagonal), a negative radius, a single point
     dm = np.full((40, 40), np.inf)

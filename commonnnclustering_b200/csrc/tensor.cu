@@ -1149,7 +1149,8 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     //                                    2^-10.9 M before that --, twice for 2 x_i.x_j, and a factor 2 of head-room;
     //   2^-20                            the norms rounded to f32, the roundings of nc - 2 acc and thr - nr.
     const int n_instr = atoms * 4, n_small = (int)(2 * d / 16), n_hh = n_instr - n_small;
-    const double coef = 6.1 * ldexp(1.0, -22) + 68.0 * ldexp(1.0, -23) * (n_hh * 1.002 + n_small * 5.3e-4) + ldexp(1.0, -20);
+    double coef = 6.1 * ldexp(1.0, -22) + 68.0 * ldexp(1.0, -23) * (n_hh * 1.002 + n_small * 5.3e-4) + ldexp(1.0, -20);
+    if (const char *e = getenv("CNNB200_TENSOR_EPS_SCALE")) coef *= atof(e);  // measurement only: how much head-room the bound has
     {
         Span sp(ctx, T_GRID_BUILD);
         CNN_CUDA(cudaMemsetAsync(ctx->b_stats.p, 0, sizeof(unsigned long long) * ST_N, st));

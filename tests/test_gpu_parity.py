@@ -88,6 +88,38 @@ def test_tensor_core_neighbour_sets_are_exact(ctx):
         ctx.neighbours_from_points(rng.standard_normal((10, 86)), 1.0, method="tensor")  # > 85 dims
 
 
+def test_tensor_core_fp16_split_edge_cases(ctx):
+    """The fp16 hi/lo split of the tensor-core filter: every number of 64-wide K atoms (D = 4 .. 85, odd D: the scalar
+    split kernel), instruction boundaries that cut through the hi.hi block (D % 16 != 0), coordinates scaled by 1e-20 /
+    1e+20 (the power-of-two scaling), one dimension 1e6 times wider than the others (small coordinates become fp16
+    subnormals after the scaling) and a radius far beyond the data (every pair a neighbour)."""
+    rng = np.random.default_rng(77)
+    sets = []
+    for d in (4, 5, 21, 22, 43, 64, 85):
+        x = rng.standard_normal((700 + d, d))
+        r = float(np.sqrt(2.0 * d) * 0.8)
+        sets.append((x, r))
+    x = rng.standard_normal((900, 12))
+    sets += [(x * 1e-20, 3.5e-20), (x * 1e20, 3.5e20), (x + 1e3, 3.5)]
+    wide = rng.standard_normal((800, 10))
+    wide[:, 0] *= 1e6
+    sets.append((wide, 2.5e5))
+    sets.append((rng.standard_normal((300, 7)), 1e3))     # R >> every distance
+    sets.append((np.zeros((200, 9)), 0.0))                # all points identical, r = 0: 0 <= 0
+    for x, r in sets:
+        x = np.ascontiguousarray(x)
+        ctx.neighbours_from_points(x, r * r, metric="euclidean_r", method="tiled")
+        want = ctx.neighbours_export()
+        ctx.neighbours_from_points(x, r * r, metric="euclidean_r", method="tensor")
+        got = ctx.neighbours_export()
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+    x = rng.standard_normal((50, 6))
+    x[7, 3] = np.nan
+    with pytest.raises(ValueError):
+        ctx.neighbours_from_points(x, 1.0, method="tensor")
+
+
 def test_tensor_core_reordered_ties_and_pair_list_regrowth():
     """Pivot-sorted order + tile pruning (n >= 4096) on data full of exact ties, with a pair list that is far too
     small at first (the pass is repeated once with the size it asked for), with and without the reordering."""

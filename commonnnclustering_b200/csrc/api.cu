@@ -93,6 +93,7 @@ extern "C" int cnnb200_ctx_create(int device, cnnb200_ctx **out) {
     if (const char *e = getenv("CNNB200_FAR_STRIDE")) ctx->far_stride = atoi(e);
     if (const char *e = getenv("CNNB200_FAR_SAMPLES")) ctx->n_far = atoi(e);
     if (const char *e = getenv("CNNB200_WL_CHUNK")) ctx->wl_chunk = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char *e = getenv("CNNB200_BALANCE_ROW")) ctx->balance_per_row = atoll(e) >= 0 ? atoll(e) : 0;
     if (const char *e = getenv("CNNB200_FUSED_UNION")) ctx->fuse_union = atoi(e) != 0;
     if (const char *e = getenv("CNNB200_FILTER")) ctx->use_filter = atoi(e) != 0;
     if (const char *e = getenv("CNNB200_PACKED")) ctx->use_packed = atoi(e) != 0;

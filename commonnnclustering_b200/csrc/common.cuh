@@ -95,6 +95,7 @@ struct cnnb200_ctx {
     int far_stride = 8; // second round: every far_stride-th row of a tree tries two far neighbours (0: off; CNNB200_FAR_STRIDE)
     int n_far = 2;      // far entries such a row tries: the last one and the one a quarter into the upper part (CNNB200_FAR_SAMPLES)
     int wl_chunk = 16;  // work-list batches of 32 edges a warp takes at a time (CNNB200_WL_CHUNK)
+    ll balance_per_row = 500;  // row-block balance: cost = candidate pairs + this * rows (CNNB200_BALANCE_ROW)
 
     // ---- neighbourhood structure (internal index space) -------------------------------
     bool have_nb = false;

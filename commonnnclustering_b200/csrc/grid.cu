@@ -1017,18 +1017,21 @@ int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radi
 }
 
 // ---- row-sharded construction (multi-GPU): C-ABI -----------------------------------------------------
-__global__ void balance_kernel(const ll *__restrict__ goff, ll n, int parts, ll *bounds) {
+// The cost of a row block is modelled as (candidate pairs) + per_row * (rows): the search and the component pass both
+// have a part that follows the number of points, not of candidates (C2 on two GPUs, balanced by candidates alone: the
+// rank with 58 % of the points took 0.14 ms longer: 1.55 ms against 1.41 ms).
+__global__ void balance_kernel(const ll *__restrict__ goff, ll n, int parts, ll per_row, ll *bounds) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > parts) return;
     if (k == 0) { bounds[0] = 0; return; }
     if (k == parts) { bounds[parts] = n; return; }
-    // first row whose candidate prefix reaches k/parts of the total, rounded to a multiple of 32 rows
-    const ll total = goff[n];
+    // first row whose cost prefix reaches k/parts of the total, rounded to a multiple of 32 rows
+    const ll total = goff[n] + per_row * n;
     const ll target = (ll)((double)total * k / parts);
     ll lo = 0, hi = n;
     while (lo < hi) {
         ll mid = (lo + hi) >> 1;
-        if (goff[mid] < target) lo = mid + 1; else hi = mid;
+        if (goff[mid] + per_row * mid < target) lo = mid + 1; else hi = mid;
     }
     lo = (lo + 16) / 32 * 32;
     bounds[k] = lo > n ? n : lo;
@@ -1063,7 +1066,7 @@ extern "C" int cnnb200_grid_balance(cnnb200_ctx *ctx, int parts, int64_t *bounds
     CNN_CUDA(cudaSetDevice(ctx->device));
     CNN_TRY(cnn_ensure(ctx, ctx->b_bbox, sizeof(ll) * (size_t)(parts + 1)));
     balance_kernel<<<cnn_blocks(parts + 1, 128), 128, 0, ctx->stream>>>(ctx->b_tmp1.as<ll>(), ctx->grid_n, parts,
-                                                                         ctx->b_bbox.as<ll>());
+                                                                         ctx->balance_per_row, ctx->b_bbox.as<ll>());
     CNN_KERNEL_CHECK();
     ll *h;
     CNN_TRY(cnn_pinned(ctx, sizeof(ll) * (size_t)(parts + 1), (void **)&h));
@@ -1151,7 +1154,8 @@ extern "C" int cnnb200_neighbours_adopt(cnnb200_ctx *ctx, const int64_t *row_ptr
 // (the caller all-gathers the parent arrays: cnnb200_components_parents)
 // end:    cnnb200_fit_sharded_end (cn.cu): merge, ranking of the components, labels.
 __global__ void block_ranges_kernel(const ll *__restrict__ goff, const int *__restrict__ cell_sorted,
-                                    const int *__restrict__ cell_start, GridDesc g, ll n, int parts, int rank, ll *out) {
+                                    const int *__restrict__ cell_start, GridDesc g, ll n, int parts, int rank, ll per_row,
+                                    ll *out) {
     // out[0 .. parts] = block bounds; out[parts + 1], out[parts + 2] = halo of block `rank`
     __shared__ ll s_bounds[1026];
     for (int k = threadIdx.x; k <= parts; k += blockDim.x) {
@@ -1159,12 +1163,12 @@ __global__ void block_ranges_kernel(const ll *__restrict__ goff, const int *__re
         if (k == 0) b = 0;
         else if (k == parts) b = n;
         else {
-            const ll total = goff[n];
+            const ll total = goff[n] + per_row * n;   // cost model: see balance_kernel
             const ll target = (ll)((double)total * k / parts);
             ll lo = 0, hi = n;
             while (lo < hi) {
                 ll mid = (lo + hi) >> 1;
-                if (goff[mid] < target) lo = mid + 1; else hi = mid;
+                if (goff[mid] + per_row * mid < target) lo = mid + 1; else hi = mid;
             }
             lo = (lo + 16) / 32 * 32;
             b = lo > n ? n : lo;
@@ -1205,7 +1209,7 @@ extern "C" int cnnb200_fit_sharded_begin(cnnb200_ctx *ctx, const double *x, int 
     // block bounds and this rank's halo, computed on the device, one small copy back
     CNN_TRY(cnn_ensure(ctx, ctx->b_bbox, sizeof(ll) * (size_t)(world + 3)));
     block_ranges_kernel<<<1, 256, 0, st>>>(ctx->b_tmp1.as<ll>(), ctx->b_cell_id_sorted.as<int>(), ctx->b_cell_start.as<int>(),
-                                           ctx->grid, n, world, rank, ctx->b_bbox.as<ll>());
+                                           ctx->grid, n, world, rank, ctx->balance_per_row, ctx->b_bbox.as<ll>());
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     ll *h;

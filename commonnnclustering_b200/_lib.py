@@ -61,6 +61,8 @@ SIGNATURES = {
     "cnnb200_fit_sharded_begin": [_P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int, _I64, _I64, C.c_int, C.c_int, _P,
                                   C.POINTER(_P)],
     "cnnb200_fit_sharded_end": [_P, _P, _I64, C.c_int, _I64, _I64, _I64, _P, C.c_int, C.POINTER(_I64)],
+    "cnnb200_fit_sharded_ranges": [_P, _I64, _P],
+    "cnnb200_fit_sharded_end_windows": [_P, _P, _I64, _P, _I64, C.c_int, _I64, _I64, _I64, _P, C.c_int, C.POINTER(_I64)],
     "cnnb200_neighbours_other_from_points": [_P, _P, C.c_int, _I64, _I64, C.POINTER(_I64)],
     "cnnb200_neighbours_other_from_csr": [_P, _P, _P, C.c_int, _I64, _I64],
     "cnnb200_predict": [_P, _I64, _I64, _P, _P, _I64, _P, _P, C.c_int],
@@ -403,6 +405,28 @@ class Context:
         nc = _I64()
         check(self._lib.cnnb200_fit_sharded_end(
             self._h, op, int(world), int(bool(sort_by_size)), int(current_start),
+            -1 if member_cutoff is None else int(member_cutoff), -1 if max_clusters is None else int(max_clusters),
+            lp, lloc, C.byref(nc)))
+        return nc.value
+
+    def fit_sharded_ranges(self, world):
+        """-> int64 [world, 2]: the rows [lo, hi) every rank built in the last ``fit_sharded_begin`` (block + halo)."""
+        r = np.zeros((int(world), 2), dtype=np.int64)
+        check(self._lib.cnnb200_fit_sharded_ranges(self._h, int(world), r.ctypes.data))
+        return r
+
+    def fit_sharded_end_windows(self, others, world, starts, length, labels, sort_by_size=True, current_start=1,
+                                member_cutoff=None, max_clusters=None):
+        """``fit_sharded_end`` on the gathered WINDOWS ``[world, length]`` of the parent arrays (window g starts at row
+        ``starts[g]``)."""
+        op, loc = _ptr_loc(others)
+        if loc != DEVICE:
+            raise ValueError("the gathered parent windows must be a device tensor")
+        lp, lloc = _ptr_loc(labels)
+        st = np.ascontiguousarray(starts, dtype=np.int64)
+        nc = _I64()
+        check(self._lib.cnnb200_fit_sharded_end_windows(
+            self._h, op, int(world), st.ctypes.data, int(length), int(bool(sort_by_size)), int(current_start),
             -1 if member_cutoff is None else int(member_cutoff), -1 if max_clusters is None else int(max_clusters),
             lp, lloc, C.byref(nc)))
         return nc.value

@@ -724,6 +724,35 @@ __global__ void comp_merge_kernel(const int *__restrict__ others, ll n, ll count
     }
 }
 
+// The same two steps on WINDOWS of the foreign parent arrays: rank g built the rows [lo_g, hi_g) only (its block plus
+// the halo), everything else in its array is -1 and says nothing -- so the ranks exchange `len` entries from
+// starts[g] on (len = the longest range, starts[g] <= lo_g), G x len instead of G x n values (8 GPUs on C2: 0.19 n).
+__global__ void comp_adopt_core_win_kernel(const int *__restrict__ others, const ll *__restrict__ starts, ll len, ll n,
+                                           ll count, int *parent, uint8_t *core) {
+    ll i = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    if (i >= n || parent[i] >= 0) return;
+    for (ll g = 0; g < count; ++g) {
+        const ll k = i - starts[g];
+        if (k >= 0 && k < len && others[g * len + k] >= 0) {
+            parent[i] = (int)i;
+            core[i] = 1;
+            return;
+        }
+    }
+}
+
+__global__ void comp_merge_win_kernel(const int *__restrict__ others, const ll *__restrict__ starts, ll len, ll count,
+                                      int *parent) {
+    ll t = blockIdx.x * (ll)blockDim.x + threadIdx.x;
+    ll stride = (ll)gridDim.x * blockDim.x;
+    for (; t < len * count; t += stride) {
+        const ll g = t / len;
+        const int i = (int)(starts[g] + (t - g * len));
+        const int o = others[t];
+        if (o >= 0 && o != i && o != ld_parent(parent, i)) uf_union(parent, i, o);
+    }
+}
+
 // ---- count mode -----------------------------------------------------------------------------------
 // |N(i) ∩ N(j)| for every candidate edge (SimilarityChecker._get semantics, no early exit).
 // One warp per row i: N(i) becomes the shared-memory window, every N(j) with j in N(i), j > i is
@@ -1090,6 +1119,9 @@ extern "C" int cnnb200_cn_count_rows(cnnb200_ctx *ctx, int64_t n_member_cutoff, 
     return CNNB200_OK;
 }
 
+static int sharded_finish(cnnb200_ctx *ctx, int sort_by_size, int64_t current_start, int64_t member_cutoff, int64_t max_clusters,
+                          int64_t *labels, int loc, int64_t *n_clusters_out);
+
 // Second half of the row-sharded fit: `others` = the parent arrays of all ranks ([world, n] int32, all-gathered by the
 // caller; this rank's own slice included or not -- a union with oneself is a no-op).  Rows another rank knows to be
 // core become singleton trees here too, the forests are merged (hooking towards the smaller root makes the result
@@ -1101,6 +1133,48 @@ extern "C" int cnnb200_fit_sharded_end(cnnb200_ctx *ctx, const int32_t *others, 
     if (!ctx || !others) CNN_FAIL(CNNB200_E_INVALID, "fit_sharded_end: NULL argument");
     if (!ctx->have_comp) CNN_FAIL(CNNB200_E_STATE, "fit_sharded_end: call fit_sharded_begin first");
     CNN_TRY(cnnb200_components_merge(ctx, others, world));
+    return sharded_finish(ctx, sort_by_size, current_start, member_cutoff, max_clusters, labels, loc, n_clusters_out);
+}
+
+extern "C" int cnnb200_fit_sharded_ranges(cnnb200_ctx *ctx, int64_t world, int64_t *ranges) {
+    if (!ctx || !ranges) CNN_FAIL(CNNB200_E_INVALID, "fit_sharded_ranges: NULL argument");
+    if (!ctx->have_comp || ctx->shard_world != world) CNN_FAIL(CNNB200_E_STATE, "fit_sharded_ranges: call fit_sharded_begin first");
+    for (int64_t r = 0; r < 2 * world; ++r) ranges[r] = ctx->shard_ranges[r];
+    return CNNB200_OK;
+}
+
+extern "C" int cnnb200_fit_sharded_end_windows(cnnb200_ctx *ctx, const int32_t *others, int64_t world, const int64_t *starts,
+                                               int64_t len, int sort_by_size, int64_t current_start, int64_t member_cutoff,
+                                               int64_t max_clusters, int64_t *labels, int loc, int64_t *n_clusters_out) {
+    if (!ctx || !others || !starts) CNN_FAIL(CNNB200_E_INVALID, "fit_sharded_end_windows: NULL argument");
+    if (!ctx->have_comp) CNN_FAIL(CNNB200_E_STATE, "fit_sharded_end_windows: call fit_sharded_begin first");
+    if (world < 1 || world > 1024 || len < 0 || len > ctx->n) CNN_FAIL(CNNB200_E_INVALID, "fit_sharded_end_windows: bad world / len");
+    for (int64_t g = 0; g < world; ++g)
+        if (starts[g] < 0 || starts[g] + len > ctx->n) CNN_FAIL(CNNB200_E_INVALID, "fit_sharded_end_windows: window %lld leaves [0, n)", (long long)g);
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    {
+        Span sp(ctx, T_COMP_FLATTEN);
+        CNN_TRY(cnn_ensure(ctx, ctx->b_bbox, sizeof(ll) * (size_t)(3 * world + 1)));
+        ll *h;
+        CNN_TRY(cnn_pinned(ctx, sizeof(ll) * (size_t)(3 * world + 1), (void **)&h));
+        for (int64_t g = 0; g < world; ++g) h[g] = starts[g];
+        CNN_CUDA(cudaMemcpyAsync(ctx->b_bbox.p, h, sizeof(ll) * (size_t)world, cudaMemcpyHostToDevice, st));
+        const ll *d_starts = ctx->b_bbox.as<ll>();
+        if (len > 0) {
+            comp_adopt_core_win_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(others, d_starts, len, ctx->n, world,
+                                                                               ctx->b_parent.as<int>(), ctx->b_core.as<uint8_t>());
+            comp_merge_win_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(others, d_starts, len, world, ctx->b_parent.as<int>());
+        }
+        comp_compress_kernel<<<cnn_blocks(ctx->n, 256), 256, 0, st>>>(ctx->b_parent.as<int>(), ctx->n);
+        CNN_LAUNCHED(ctx, 3);
+        CNN_KERNEL_CHECK();
+    }
+    return sharded_finish(ctx, sort_by_size, current_start, member_cutoff, max_clusters, labels, loc, n_clusters_out);
+}
+
+static int sharded_finish(cnnb200_ctx *ctx, int sort_by_size, int64_t current_start, int64_t member_cutoff, int64_t max_clusters,
+                          int64_t *labels, int loc, int64_t *n_clusters_out) {
     const ll n = ctx->n;
     cudaStream_t st = ctx->stream;
     if (!labels) {

@@ -95,7 +95,7 @@ struct cnnb200_ctx {
     int far_stride = 8; // second round: every far_stride-th row of a tree tries two far neighbours (0: off; CNNB200_FAR_STRIDE)
     int n_far = 2;      // far entries such a row tries: the last one and the one a quarter into the upper part (CNNB200_FAR_SAMPLES)
     int wl_chunk = 16;  // work-list batches of 32 edges a warp takes at a time (CNNB200_WL_CHUNK)
-    ll balance_per_row = 500;  // row-block balance: cost = candidate pairs + this * rows (CNNB200_BALANCE_ROW)
+    ll balance_per_row = 250;  // row-block balance: cost = candidate pairs + this * rows (CNNB200_BALANCE_ROW)
 
     // ---- neighbourhood structure (internal index space) -------------------------------
     bool have_nb = false;
@@ -174,6 +174,8 @@ struct cnnb200_ctx {
     ll lab_summary_host[3] = {0, 0, 0};
     ll lab_summary_n = 0;
     ll known_max_label = -1;
+    int shard_world = 0;            // row-sharded fit: ranks of the last fit_sharded_begin and the rows each of them built
+    ll shard_ranges[2 * 1024] = {0};  // [lo, hi) per rank (block + halo)
     ll tensor_band_cap = 0;  // capacity (slabs) the hit bitmaps of the tensor-core search needed last time
     Buf b_tslab, b_tband, b_tdir;  // tensor-core search: hit slabs, borderline slabs, the two slab directories
 

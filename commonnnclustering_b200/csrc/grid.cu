@@ -1019,7 +1019,9 @@ int cnn_grid_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double radi
 // ---- row-sharded construction (multi-GPU): C-ABI -----------------------------------------------------
 // The cost of a row block is modelled as (candidate pairs) + per_row * (rows): the search and the component pass both
 // have a part that follows the number of points, not of candidates (C2 on two GPUs, balanced by candidates alone: the
-// rank with 58 % of the points took 0.14 ms longer: 1.55 ms against 1.41 ms).
+// rank with 58 % of the points took 0.14 ms longer: 1.55 ms against 1.41 ms).  per_row = 250 (same-box A/B of bench.py
+// on C2): 8 GPUs 1.12 -> 1.01 ms per fit, 2 GPUs unchanged (1.60 ms; 500 moves too much onto rank 0, which also
+// ranks the components and writes the labels: 1.64 ms).
 __global__ void balance_kernel(const ll *__restrict__ goff, ll n, int parts, ll per_row, ll *bounds) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > parts) return;
@@ -1156,7 +1158,8 @@ extern "C" int cnnb200_neighbours_adopt(cnnb200_ctx *ctx, const int64_t *row_ptr
 __global__ void block_ranges_kernel(const ll *__restrict__ goff, const int *__restrict__ cell_sorted,
                                     const int *__restrict__ cell_start, GridDesc g, ll n, int parts, int rank, ll per_row,
                                     ll *out) {
-    // out[0 .. parts] = block bounds; out[parts + 1], out[parts + 2] = halo of block `rank`
+    // out[0 .. parts] = block bounds; out[parts + 1 + 2 r], out[parts + 2 + 2 r] = block r plus its halo (all ranks: every
+    // rank then knows which window of its parent array each of the others has to send)
     __shared__ ll s_bounds[1026];
     for (int k = threadIdx.x; k <= parts; k += blockDim.x) {
         ll b;
@@ -1180,7 +1183,10 @@ __global__ void block_ranges_kernel(const ll *__restrict__ goff, const int *__re
         for (int k = 1; k <= parts; ++k)
             if (s_bounds[k] < s_bounds[k - 1]) s_bounds[k] = s_bounds[k - 1];
         for (int k = 0; k <= parts; ++k) out[k] = s_bounds[k];
-        const ll rb = s_bounds[rank], re = s_bounds[rank + 1];
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < parts; r += blockDim.x) {
+        const ll rb = s_bounds[r], re = s_bounds[r + 1];
         ll lo = rb, hi = re;
         if (re > rb) {
             // cell ids are x-fastest: the window of cell id c lies within [c - reach, c + reach]
@@ -1193,8 +1199,8 @@ __global__ void block_ranges_kernel(const ll *__restrict__ goff, const int *__re
             lo = a < rb ? a : rb;
             hi = b > re ? b : re;
         }
-        out[parts + 1] = lo;
-        out[parts + 2] = hi;
+        out[parts + 1 + 2 * r] = lo;
+        out[parts + 2 + 2 * r] = hi;
     }
 }
 
@@ -1207,17 +1213,19 @@ extern "C" int cnnb200_fit_sharded_begin(cnnb200_ctx *ctx, const double *x, int 
     CNN_TRY(cnnb200_grid_begin(ctx, x, loc, n, d, radius_cutoff, metric));
     cudaStream_t st = ctx->stream;
     // block bounds and this rank's halo, computed on the device, one small copy back
-    CNN_TRY(cnn_ensure(ctx, ctx->b_bbox, sizeof(ll) * (size_t)(world + 3)));
+    CNN_TRY(cnn_ensure(ctx, ctx->b_bbox, sizeof(ll) * (size_t)(3 * world + 1)));
     block_ranges_kernel<<<1, 256, 0, st>>>(ctx->b_tmp1.as<ll>(), ctx->b_cell_id_sorted.as<int>(), ctx->b_cell_start.as<int>(),
                                            ctx->grid, n, world, rank, ctx->balance_per_row, ctx->b_bbox.as<ll>());
     CNN_LAUNCHED(ctx, 1);
     CNN_KERNEL_CHECK();
     ll *h;
-    CNN_TRY(cnn_pinned(ctx, sizeof(ll) * (size_t)(world + 3), (void **)&h));
-    CNN_CUDA(cudaMemcpyAsync(h, ctx->b_bbox.p, sizeof(ll) * (size_t)(world + 3), cudaMemcpyDeviceToHost, st));
+    CNN_TRY(cnn_pinned(ctx, sizeof(ll) * (size_t)(3 * world + 1), (void **)&h));
+    CNN_CUDA(cudaMemcpyAsync(h, ctx->b_bbox.p, sizeof(ll) * (size_t)(3 * world + 1), cudaMemcpyDeviceToHost, st));
     CNN_CUDA(cudaStreamSynchronize(st));
     for (int k = 0; k <= world; ++k) bounds[k] = h[k];
-    const ll rb = h[rank], re = h[rank + 1], lo = h[world + 1], hi = h[world + 2];
+    const ll rb = h[rank], re = h[rank + 1], lo = h[world + 1 + 2 * rank], hi = h[world + 2 + 2 * rank];
+    ctx->shard_world = world;
+    for (int r = 0; r < 2 * world; ++r) ctx->shard_ranges[r] = h[world + 1 + r];
     // rows [lo, hi): degrees (row-indexed, zero elsewhere), offsets, entries
     CNN_TRY(cnn_ensure(ctx, ctx->b_deg, sizeof(int) * (size_t)(n + 1)));
     CNN_TRY(cnn_ensure(ctx, ctx->b_row_ptr, sizeof(ll) * (size_t)(n + 1)));

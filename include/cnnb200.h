@@ -271,6 +271,16 @@ int cnnb200_fit_sharded_begin(cnnb200_ctx *ctx, const double *x, int loc, int64_
 int cnnb200_fit_sharded_end(cnnb200_ctx *ctx, const int32_t *others, int64_t world, int sort_by_size,
                             int64_t current_start, int64_t member_cutoff, int64_t max_clusters,
                             int64_t *labels, int loc, int64_t *n_clusters_out);
+/* The exchange restricted to what the ranks really built.  Rank r's parent array says something only for the rows
+ * [lo_r, hi_r) of its block plus halo (everything else is -1):
+ *   fit_sharded_ranges       ranges[2 r], ranges[2 r + 1] = lo_r, hi_r of ALL ranks (HOST out, identical on every rank)
+ *                            after fit_sharded_begin; the caller picks len = max (hi_r - lo_r) and
+ *                            starts[r] = min(lo_r, n - len) and all-gathers parents[starts[rank] .. + len).
+ *   fit_sharded_end_windows  as fit_sharded_end with others = [world, len] int32 (DEVICE) and starts (HOST [world]). */
+int cnnb200_fit_sharded_ranges(cnnb200_ctx *ctx, int64_t world, int64_t *ranges);
+int cnnb200_fit_sharded_end_windows(cnnb200_ctx *ctx, const int32_t *others, int64_t world, const int64_t *starts,
+                                    int64_t len, int sort_by_size, int64_t current_start, int64_t member_cutoff,
+                                    int64_t max_clusters, int64_t *labels, int loc, int64_t *n_clusters_out);
 
 /* ---------------------------------------------------------------------------------------
  * Prediction for points OUTSIDE the clustered set.  Replaces PredictorFirstmatch.predict

@@ -22,6 +22,12 @@ for n, r, c, mc in [(20000, 0.25, 10, None), (300000, 0.13, 20, 10)]:
     x = datasets.md_like_3d(n)
     lab = np.empty(n, dtype=np.int64)
     sf.fit_points(x, r * r, c + 1, c + 2, lab, member_cutoff=mc)
+    # the windowed exchange of the parent arrays (cnnb200_fit_sharded_ranges / _end_windows)
+    lab_w = np.empty(n, dtype=np.int64)
+    sf.windows = True
+    sf.fit_points(x, r * r, c + 1, c + 2, lab_w, member_cutoff=mc)
+    sf.windows = False
+    assert np.array_equal(lab_w, lab), "windowed exchange differs"
     # device-resident coordinates and labels; labels only on rank 0 (the other ranks take part in the merge only)
     xd = torch.from_numpy(x).cuda()
     lab_d = torch.full((n,), -7, dtype=torch.int64, device="cuda") if rank == 0 else None

@@ -937,37 +937,35 @@ __global__ void deg_sum_kernel(const int *__restrict__ up, const int *__restrict
     if (r <= n) deg[r] = r < n ? up[r] + low[r] + 1 : 0;  // deg[n] = 0: the scan leaves nnz in row_ptr[n]
 }
 
-// One CTA per row tile T; warps 0-3 walk the part of the rows below the diagonal (one row quarter each, one row per
-// lane): bits of the row's COLUMN in the slabs above it (dirT[T][.], row quarters ascending; the first pass transposes
-// word q of such a slab -- 32 rows x the 32 columns of this quarter -- and leaves the result for the second); warps 4-7 the part above:
-// the row's own slabs (dir[g][.], column tiles ascending).  Four slabs are fetched at a time (the walk is a chain of
-// dependent L2 reads: directory -> slab).  FILL = false: degrees (and the size of the lower part, which tells the
-// second pass where the upper part starts); true: the rows, ascending.
+// One CTA per row tile T; warps 0-3 write the part of the rows below the diagonal (one row quarter each, one row per
+// lane): bits of the row's COLUMN in the transposed slabs above it (dirT[T][.], row quarters ascending, the blocks
+// slab_count_kernel left behind); warps 4-7 the row itself and the part above: the row's own slabs (dir[g][.], column tiles
+// ascending).  Eight slabs are fetched at a time and the next 32 directory entries are under way while these are served (the
+// walk is a chain of dependent L2 reads: directory -> slab).  low[r] (entries below the diagonal, from the count pass)
+// tells the upper warps where their part starts.  Rows come out ascending.
 #define RB 8   // slabs fetched at a time
-template <bool FILL>
 __global__ void __launch_bounds__(256)
 tile_rows_kernel(const unsigned *__restrict__ dir, const unsigned *__restrict__ dirT, const uint4 *__restrict__ slabs,
-                 unsigned *__restrict__ tslabs, ll n, ll n_tiles, int *__restrict__ deg, int *__restrict__ low,
+                 const unsigned *__restrict__ tslabs, ll n, ll n_tiles, const int *__restrict__ low,
                  const ll *__restrict__ row_ptr, int *__restrict__ col_idx) {
-    __shared__ int s_low[TT];
     const unsigned full = 0xffffffffu;
     const ll T = blockIdx.x;
     const int warp = threadIdx.x >> 5, q = warp & 3, lane = threadIdx.x & 31;
     const bool upper = warp >= 4;
     const ll g = T * 4 + q, r = g * 32 + lane, G = 4 * n_tiles;
     int cnt = 0;
-    int *out = nullptr;
-    if (FILL && r < n) out = col_idx + row_ptr[r] + (upper ? low[r] : 0);
+    int *out = nullptr;  // dead rows (r >= n) have no bits anywhere: nothing is ever written through it
+    if (r < n) out = col_idx + row_ptr[r] + (upper ? low[r] : 0);
     if (!upper) {
         const unsigned *dt = dirT + T * G;
         unsigned v = lane <= g ? dt[lane] : 0u;
         for (ll g0 = 0; g0 <= g; g0 += 32) {
             const ll gpn = g0 + 32 + lane;
-            const unsigned vn = gpn <= g ? dt[gpn] : 0u;  // the next 32 directory entries are under way while these are served
+            const unsigned vn = gpn <= g ? dt[gpn] : 0u;
             unsigned nz = __ballot_sync(full, v != 0u);
             while (nz) {
                 int b[RB];
-                unsigned xw[RB], sl[RB];
+                unsigned xw[RB];
 #pragma unroll
                 for (int k = 0; k < RB; ++k) {
                     b[k] = nz ? __ffs(nz) - 1 : -1;
@@ -976,40 +974,25 @@ tile_rows_kernel(const unsigned *__restrict__ dir, const unsigned *__restrict__ 
 #pragma unroll
                 for (int k = 0; k < RB; ++k) {
                     const unsigned slot = (__shfl_sync(full, v, b[k] < 0 ? 0 : b[k]) & ~BAND_FLAG) - 1u;
-                    sl[k] = slot;
-                    // first pass: word q of the slab's 32 rows; second pass: the transposed block the first pass left behind
-                    xw[k] = b[k] < 0 ? 0u : FILL ? tslabs[(size_t)slot * 128 + q * 32 + lane]
-                                                 : reinterpret_cast<const unsigned *>(slabs + (size_t)slot * 32 + lane)[q];
+                    xw[k] = b[k] < 0 ? 0u : tslabs[(size_t)slot * 128 + q * 32 + lane];
                 }
 #pragma unroll
                 for (int k = 0; k < RB; ++k) {
                     if (b[k] < 0) continue;  // warp-uniform
-                    unsigned m = xw[k];  // bit l: row l of quarter g0 + b has column r
-                    if (!FILL) {
-                        m = transpose32(m, lane);
-                        tslabs[(size_t)sl[k] * 128 + q * 32 + lane] = m;  // every (slab, word) is visited by exactly one warp
-                    }
-                    if (FILL) {
-                        const int base = (int)((g0 + b[k]) * 32);
-                        while (m) {
-                            const int bit = __ffs(m) - 1;
-                            m &= m - 1;
-                            out[cnt++] = base + bit;
-                        }
-                    } else {
-                        cnt += __popc(m);
+                    unsigned m = xw[k];      // bit l: row l of quarter g0 + b has column r
+                    const int base = (int)((g0 + b[k]) * 32);
+                    while (m) {
+                        const int bit = __ffs(m) - 1;
+                        m &= m - 1;
+                        out[cnt++] = base + bit;
                     }
                 }
             }
             v = vn;
         }
-        if (!FILL) {
-            s_low[q * 32 + lane] = cnt;
-            if (r < n) low[r] = cnt;
-        }
     } else {
         if (r < n) {
-            if (FILL) out[0] = (int)r;
+            out[0] = (int)r;
             cnt = 1;
         }
         const unsigned *dr = dir + g * n_tiles;
@@ -1035,29 +1018,21 @@ tile_rows_kernel(const unsigned *__restrict__ dir, const unsigned *__restrict__ 
 #pragma unroll
                 for (int k = 0; k < RB; ++k) {
                     if (b[k] < 0) continue;
-                    if (FILL) {
-                        const int base = (int)((J0 + b[k]) * TT);
-                        const unsigned wds[4] = {m[k].x, m[k].y, m[k].z, m[k].w};
+                    const int base = (int)((J0 + b[k]) * TT);
+                    const unsigned wds[4] = {m[k].x, m[k].y, m[k].z, m[k].w};
 #pragma unroll
-                        for (int w = 0; w < 4; ++w) {
-                            unsigned xw = wds[w];
-                            while (xw) {
-                                const int bit = __ffs(xw) - 1;
-                                xw &= xw - 1;
-                                out[cnt++] = base + 32 * w + bit;
-                            }
+                    for (int w = 0; w < 4; ++w) {
+                        unsigned xw = wds[w];
+                        while (xw) {
+                            const int bit = __ffs(xw) - 1;
+                            xw &= xw - 1;
+                            out[cnt++] = base + 32 * w + bit;
                         }
-                    } else {
-                        cnt += __popc(m[k].x) + __popc(m[k].y) + __popc(m[k].z) + __popc(m[k].w);
                     }
                 }
             }
             v = vn;
         }
-    }
-    if (!FILL) {
-        __syncthreads();
-        if (upper && r <= n) deg[r] = r < n ? cnt + s_low[q * 32 + lane] : 0;  // deg[n] = 0: the scan leaves nnz in row_ptr[n]
     }
 }
 
@@ -1275,9 +1250,9 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     CNN_TRY(cnn_ensure(ctx, ctx->b_col_idx, sizeof(int) * (size_t)nnz));
     {
         Span sp(ctx, T_SEARCH_FILL);
-        tile_rows_kernel<true><<<(int)n_tiles, 256, 0, st>>>(dir, dirT, P.slabs, (unsigned *)(P.bslabs + 32 * (size_t)slab_cap), n, n_tiles, nullptr,
-                                                             (int *)(ctx->b_tmp0.as<int2>() + slab_cap), ctx->b_row_ptr.as<ll>(),
-                                                             ctx->b_col_idx.as<int>());
+        tile_rows_kernel<<<(int)n_tiles, 256, 0, st>>>(dir, dirT, P.slabs, (const unsigned *)(P.bslabs + 32 * (size_t)slab_cap), n, n_tiles,
+                                                       (const int *)(ctx->b_tmp0.as<int2>() + slab_cap), ctx->b_row_ptr.as<ll>(),
+                                                       ctx->b_col_idx.as<int>());
         CNN_LAUNCHED(ctx, 1);
         CNN_KERNEL_CHECK();
     }

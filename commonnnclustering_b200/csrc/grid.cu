@@ -290,19 +290,20 @@ struct GfGroup {
 // and at most GF_XSPAN cells apart (a query also meets candidates outside its own window; the test is exact, that only
 // costs time).  Warp-uniform except rs/re/ry/rz.
 template <int D>
-__device__ __forceinline__ void gf_next_group(unsigned &todo, int cid, int my_row, int my_cx, const GridDesc &g,
+__device__ __forceinline__ void gf_next_group(unsigned &todo, int my_cz, int my_row, int my_cx, const GridDesc &g,
                                               const int *__restrict__ cell_start, int lane, GfGroup &G) {
     const unsigned full = 0xffffffffu;
     G.a = __ffs(todo) - 1;
-    const int c = __shfl_sync(full, cid, G.a);
-    const int row_a = c / g.dims[0], cx = c - row_a * g.dims[0];
+    // the cell coordinates of the group's first point come from its lane (gf_tile_header divided once per tile;
+    // dividing here again, per group and per pass, was 5 integer divisions of ~20 instructions each)
+    const int row_a = __shfl_sync(full, my_row, G.a), cx = __shfl_sync(full, my_cx, G.a);
     const unsigned grp = __ballot_sync(full, my_row == row_a && my_cx - cx <= GF_XSPAN) & todo;
     todo &= ~grp;
     G.gsz = __popc(grp);
     G.lg = G.gsz <= 1 ? 0 : 32 - __clz(G.gsz - 1);
     const int cx_max = __shfl_sync(full, my_cx, G.a + G.gsz - 1);
-    G.cy = row_a % g.dims[1];
-    G.cz = row_a / g.dims[1];
+    G.cz = __shfl_sync(full, my_cz, G.a);
+    G.cy = row_a - G.cz * g.dims[1];
     G.cx0 = max(cx - 1, 0);
     G.cx1 = min(cx_max + 1, g.dims[0] - 1);
     const int y0 = D > 1 ? max(G.cy - 1, 0) : 0, y1 = D > 1 ? min(G.cy + 1, g.dims[1] - 1) : 0;
@@ -314,8 +315,9 @@ __device__ __forceinline__ void gf_next_group(unsigned &todo, int cid, int my_ro
     G.ry = G.cy;
     G.rz = G.cz;
     if (lane < G.nruns) {
-        G.ry = y0 + lane % ny;
-        G.rz = z0 + lane / ny;
+        const int qz = ny == 1 ? lane : (ny == 2 ? lane >> 1 : (lane * 11) >> 5);   // lane / ny for lane < 9, ny <= 3
+        G.ry = y0 + lane - qz * ny;
+        G.rz = z0 + qz;
         const int cb = (G.rz * g.dims[1] + G.ry) * g.dims[0];
         rs = cell_start[cb + G.cx0];
         len = cell_start[cb + G.cx1 + 1] - rs;
@@ -345,10 +347,11 @@ __device__ __forceinline__ void gf_locate(const GfGroup &G, int v, bool valid, i
 }
 
 __device__ __forceinline__ void gf_tile_header(const int *__restrict__ cell_sorted, const GridDesc &g, ll p, bool pvalid,
-                                               int &cid, int &my_row, int &my_cx) {
-    cid = pvalid ? cell_sorted[p] : -1;
-    my_row = pvalid ? cid / g.dims[0] : -1;
-    my_cx = pvalid ? cid - my_row * g.dims[0] : 0;
+                                               int &my_cz, int &my_row, int &my_cx) {
+    const int c = pvalid ? cell_sorted[p] : -1;
+    my_row = pvalid ? c / g.dims[0] : -1;
+    my_cx = pvalid ? c - my_row * g.dims[0] : 0;
+    my_cz = pvalid ? my_row / g.dims[1] : 0;   // row = cz * dims[1] + cy
 }
 
 template <int D, bool SQRT, int MINB>
@@ -370,8 +373,8 @@ grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, l
     for (ll t = warp; t < n_tiles; t += nwarps) {
         const ll p = p_begin + t * qpw + lane;
         const bool pvalid = lane < qpw && p < p_end;
-        int cid, my_row, my_cx;
-        gf_tile_header(cell_sorted, g, p, pvalid, cid, my_row, my_cx);
+        int my_cz, my_row, my_cx;
+        gf_tile_header(cell_sorted, g, p, pvalid, my_cz, my_row, my_cx);
         const float4 my4 = pvalid ? xf[p] : make_float4(0.f, 0.f, 0.f, 0.f);
         unsigned todo = __ballot_sync(full, pvalid);
         // the tile's mask words are reserved from a running counter (their number follows from the group structure
@@ -383,7 +386,7 @@ grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, l
             int words = 0;
             while (td) {
                 GfGroup G;
-                gf_next_group<D>(td, cid, my_row, my_cx, g, cell_start, lane, G);
+                gf_next_group<D>(td, my_cz, my_row, my_cx, g, cell_start, lane, G);
                 words += G.nch << G.lg;
             }
             unsigned long long base = 0;
@@ -395,7 +398,7 @@ grid_mask_kernel(const double *__restrict__ xs, const float4 *__restrict__ xf, l
         }
         while (todo) {
             GfGroup G;
-            gf_next_group<D>(todo, cid, my_row, my_cx, g, cell_start, lane, G);
+            gf_next_group<D>(todo, my_cz, my_row, my_cx, g, cell_start, lane, G);
             const int jme = lane - G.a;  // my query slot when I belong to the group
             const bool mine = jme >= 0 && jme < G.gsz;
             const int gp = 1 << G.lg;
@@ -503,8 +506,8 @@ grid_expand_kernel(const int *__restrict__ cell_sorted, const int *__restrict__ 
         const ll p0 = p_begin + t * qpw;
         const ll p = p0 + lane;
         const bool pvalid = lane < qpw && p < p_end;
-        int cid, my_row, my_cx;
-        gf_tile_header(cell_sorted, g, p, pvalid, cid, my_row, my_cx);
+        int my_cz, my_row, my_cx;
+        gf_tile_header(cell_sorted, g, p, pvalid, my_cz, my_row, my_cx);
         const ll tile_base = row_ptr[p0];
         int *out = col_idx + tile_base;
         int rowpos = pvalid ? (int)(row_ptr[p] - tile_base) : 0;  // where my row's next entry goes, from the tile's base
@@ -529,7 +532,7 @@ grid_expand_kernel(const int *__restrict__ cell_sorted, const int *__restrict__ 
         unsigned todo = __ballot_sync(full, pvalid);
         while (todo) {
             GfGroup G;
-            gf_next_group<D>(todo, cid, my_row, my_cx, g, cell_start, lane, G);
+            gf_next_group<D>(todo, my_cz, my_row, my_cx, g, cell_start, lane, G);
             const int jme = lane - G.a;
             const bool mine = jme >= 0 && jme < G.gsz;
             const int gp = 1 << G.lg;

@@ -102,7 +102,9 @@ class ShardedFit:
         ctx.set_stream(torch.cuda.current_stream(self.device))  # collectives are ordered against this stream
         self.last = {}
         self._registered = {}
-        self.windows = os.environ.get("CNNB200_DIST_WINDOWS", "0") == "1"   # exchange windows of the parent arrays
+        # exchange windows of the parent arrays instead of whole arrays (fit_points): pays from 8 ranks on
+        env = os.environ.get("CNNB200_DIST_WINDOWS")
+        self.windows = (env == "1") if env is not None else self.world >= 8
 
     # -- neighbourhoods from coordinates, rows sharded ---------------------------------------------
     def neighbours_from_points(self, x, radius_cutoff, metric="euclidean_r", exchange=False):
@@ -285,10 +287,11 @@ class ShardedFit:
             dist.all_gather_into_tensor(gathered, self._parents, group=self.group)
             self.last = dict(bounds=bounds)
             return ctx.fit_sharded_end(gathered, self.world, labels, sort_by_size, current_start, member_cutoff, max_clusters)
-        # windows=True: a rank's parent array says something only for the rows it built (block + halo), so the ranks may
-        # exchange windows of the longest such range instead of whole arrays (8 GPUs on C2: 0.19 n per rank).  Measured on
-        # C2: no gain -- 1.147 against 1.121 ms per fit on 8 GPUs, 1.634 against 1.595 ms on 2: the 4 MB arrays travel in
-        # the latency of the collective either way and the merge kernel is not what the last phase spends its time on.
+        # windows=True: a rank's parent array says something only for the rows it built (block + halo), so the ranks
+        # exchange windows of the longest such range instead of whole arrays (8 GPUs on C2: 0.19 n per rank).  Same-box
+        # A/B of bench.py on C2: 8 GPUs 1.00 / 1.02 ms against 1.10 ms per fit (merge + flatten 0.087 -> 0.064 ms, time
+        # outside any stage 0.24 -> 0.17 ms); 2 GPUs 1.63 against 1.60 ms (the windows are 0.6 n there and the extra
+        # host work between the two C calls costs more than the bytes) -- hence the default: from 8 ranks on.
         ranges = ctx.fit_sharded_ranges(self.world)
         plan = getattr(self, "_win_plan", None)
         if plan is None or plan[0] != key or not np.array_equal(plan[1], ranges):   # repeated fits: nothing to redo

@@ -79,6 +79,15 @@ def allgather_chunks(full, chunk, group=None):
         dist.all_gather(list(full.view(world, chunk).unbind(0)), mine.clone(), group=group)
 
 
+def plan_windows(ranges, n):
+    """ranges int64 [world, 2]: the rows [lo, hi) every rank built -> (length, starts): the ranks exchange
+    ``parents[starts[r] : starts[r] + length]``; every window covers its rank's range and stays inside [0, n)."""
+    ranges = np.asarray(ranges, dtype=np.int64)
+    length = max(int((ranges[:, 1] - ranges[:, 0]).max()), 1)
+    starts = np.maximum(np.minimum(ranges[:, 0], n - length), 0)
+    return length, starts
+
+
 def gather_parents(parents, group=None):
     """parents int32 [n] of this rank -> int32 [G, n] of all ranks."""
     world = dist.get_world_size(group)
@@ -295,8 +304,7 @@ class ShardedFit:
         ranges = ctx.fit_sharded_ranges(self.world)
         plan = getattr(self, "_win_plan", None)
         if plan is None or plan[0] != key or not np.array_equal(plan[1], ranges):   # repeated fits: nothing to redo
-            length = max(int((ranges[:, 1] - ranges[:, 0]).max()), 1)
-            starts = np.maximum(np.minimum(ranges[:, 0], n - length), 0)
+            length, starts = plan_windows(ranges, n)
             gathered = self._gather_buffer(n) if length == n else self._window_buffer(length)
             s0 = int(starts[self.rank])
             plan = self._win_plan = (key, ranges, length, starts, gathered, self._parents[s0:s0 + length])

@@ -230,3 +230,45 @@ def test_reel_running_maximum_equals_the_per_child_pass():
         want = naive(lab.astype(np.int64), children)
         cl.reel()
         np.testing.assert_array_equal(cl.labels, want)
+
+
+def test_condensed_distances_input_type():
+    """InputDataDistancesLinear mirrors InputDataExtDistancesLinearMemoryview (_types.pyx:1112-1150): n_points from the
+    vector length, `_get_distance`'s index arithmetic, subsets again condensed; registered under "distances_linear"."""
+    rng = np.random.default_rng(4)
+    n = 23
+    dm = rng.random((n, n))
+    dm = np.minimum(dm, dm.T)
+    np.fill_diagonal(dm, 0.0)
+    cond = dm[np.triu_indices(n, k=1)]
+    data = _types.InputDataDistancesLinear(cond)
+    assert data.n_points == n and data.meta["access_distances"] and data.data.shape == (n * (n - 1) // 2,)
+    for a, b in ((0, 1), (5, 3), (22, 0), (21, 22), (7, 7)):
+        assert data.get_distance(a, b) == dm[a, b]
+    idx = np.array([1, 4, 5, 19, 22])
+    sub = data.get_subset(idx)
+    assert sub.n_points == 5 and np.array_equal(sub.data, dm[np.ix_(idx, idx)][np.triu_indices(5, k=1)])
+    assert _types.InputDataDistancesLinear(np.zeros(0)).n_points == 1     # one point: no pairs
+    with pytest.raises(ValueError):
+        _types.InputDataDistancesLinear(np.zeros(4))                      # not a triangular number
+    with pytest.raises(ValueError):
+        _types.InputDataDistancesLinear(np.zeros((3, 3)))
+    assert recipes.COMPONENT_NAME_TYPE_MAP["input_data"]["distances_linear"] is _types.InputDataDistancesLinear
+    # pinning starts with the second fit (a child of isolate is usually fitted once)
+    big = _types.InputDataComponents(np.zeros((50_000, 3)))
+    assert big.pin() is False and big._pin_calls == 1
+
+
+def test_window_plan_of_the_sharded_exchange():
+    """dist.plan_windows: every rank's window covers the rows it built, all windows have one length and stay in [0, n)."""
+    from commonnnclustering_b200 import dist as cdist
+
+    n = 1000
+    ranges = np.array([[0, 300], [250, 520], [480, 790], [760, 1000]])
+    length, starts = cdist.plan_windows(ranges, n)
+    assert length == 310 and starts.tolist() == [0, 250, 480, 690]
+    assert np.all(starts <= ranges[:, 0]) and np.all(starts + length >= ranges[:, 1]) and np.all(starts + length <= n)
+    length, starts = cdist.plan_windows(np.array([[0, 0], [0, 1000]]), n)      # an empty block next to a full one
+    assert length == n and starts.tolist() == [0, 0]
+    length, starts = cdist.plan_windows(np.array([[5, 5], [9, 9]]), 10)        # nothing built anywhere
+    assert length == 1 and np.all(starts + length <= 10)

@@ -88,6 +88,44 @@ def _worker(rank, world, port, out):
         labels[roots >= 0] = np.searchsorted(uniq, roots[roots >= 0]) + 1
         want = oracle.fit_points(x, r, c, sort=False)
         assert np.array_equal(labels, want)
+        # the windowed form of exchange 2 (dist.plan_windows; cnnb200_fit_sharded_ranges / _end_windows on the device): a
+        # rank that built only its block and the rows its lists refer to knows nothing outside that range
+        xs = x[np.argsort(x[:, 0], kind="stable")]             # index locality, as after the cell sort
+        rp, ci = oracle.neighbours(xs, r * r)
+        core = np.diff(rp) > c + 1
+        touched = np.unique(np.concatenate([np.arange(b, e), ci[rp[b]:rp[e]]]))
+        lo, hi = int(touched.min()), int(touched.max()) + 1
+        parent = np.full(n, -1, dtype=np.int32)
+        parent[lo:hi] = np.where(core[lo:hi], np.arange(lo, hi), -1)
+        for i in range(b, e):
+            if not core[i]:
+                continue
+            ni = ci[rp[i]:rp[i + 1]]
+            for j in ni[ni > i]:
+                if core[j] and oracle.check(ni, ci[rp[j]:rp[j + 1]], c + 2):
+                    _union_min(parent, i, int(j))
+        mine = torch.tensor([lo, hi], dtype=torch.int64)
+        ranges = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(ranges, mine)
+        ranges = torch.stack(ranges).numpy()
+        length, starts = cdist.plan_windows(ranges, n)
+        assert length < n and np.all(starts <= ranges[:, 0]) and np.all(starts + length >= ranges[:, 1])
+        wins = [torch.zeros(length, dtype=torch.int32) for _ in range(world)]
+        dist.all_gather(wins, torch.from_numpy(parent[starts[rank]:starts[rank] + length].copy()))
+        for g in range(world):                                  # rows another rank knows to be core become singleton trees
+            w = wins[g].numpy()
+            idx = starts[g] + np.flatnonzero(w >= 0)
+            fresh = idx[parent[idx] < 0]
+            parent[fresh] = fresh
+        for g in range(world):
+            w = wins[g].numpy()
+            for k in np.flatnonzero(w >= 0):
+                _union_min(parent, int(starts[g] + k), int(w[k]))
+        roots = np.array([_find(parent, i) if parent[i] >= 0 else -1 for i in range(n)])
+        uniq = np.unique(roots[roots >= 0])
+        labels = np.zeros(n, dtype=np.int64)
+        labels[roots >= 0] = np.searchsorted(uniq, roots[roots >= 0]) + 1
+        assert np.array_equal(labels, oracle.fit_points(xs, r, c, sort=False))
         out[rank] = True
     finally:
         dist.destroy_process_group()

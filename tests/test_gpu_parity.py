@@ -669,6 +669,26 @@ def test_sweep_cells_equal_oracle(ctx):
             assert abs(rec.ratio_noise - float((want == 0).mean())) < 1e-15
 
 
+def test_sweep_with_the_periodic_metric_equals_the_oracle(ctx):
+    """fit_sweep takes the metric OBJECT: the periodic metric squares the radius (`adjust_radius`) and brings its bounds
+    along (a sweep with metric.name only searched with the unsquared radius and stale bounds)."""
+    from commonnnclustering_b200 import _types, sweep
+
+    rng = np.random.default_rng(12)
+    bounds = [2.0, 3.0]
+    x = np.ascontiguousarray(rng.random((4000, 2)) * np.array(bounds))
+    x[:1500] = x[:1500] * 0.15 + np.array([1.9, 2.9])       # a dense patch that wraps around both boundaries
+    metric = _types.MetricEuclideanPeriodicReduced(bounds)
+    rs, cs = [0.05, 0.08], [2, 8]
+    labels, summary = sweep.fit_sweep(x, rs, cs, member_cutoff=4, metric=metric, ctx=ctx)
+    for ir, r in enumerate(rs):
+        for ic, c in enumerate(cs):
+            want = port.fit_points_periodic(x, r, c, bounds, member_cutoff=4)
+            np.testing.assert_array_equal(labels[ir, ic], want, err_msg=f"cell r={r} c={c}")
+    with pytest.raises(ValueError):
+        sweep.fit_sweep(x, rs, cs, metric="euclidean_periodic_r", ctx=ctx)   # a name cannot carry the bounds
+
+
 def test_sweep_3d_equals_one_fit_per_cell(ctx):
     from commonnnclustering_b200 import sweep
 

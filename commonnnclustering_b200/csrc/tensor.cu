@@ -1203,6 +1203,8 @@ int cnn_tensor_search(cnnb200_ctx *ctx, const double *d_x, ll n, ll d, double ra
     hb += 32;  // the first 128 bytes belong to cnn_scan_deg_to_row_ptr
     ll nnz = 0, max_deg = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
+        if (slab_cap > (1ll << 24))  // word offsets into the slab store travel as 32-bit values (tile_resolve_kernel)
+            CNN_FAIL(CNNB200_E_RANGE, "tensor search: more than 2^24 hit slabs (%lld); use the tiled method", (long long)slab_cap);
         CNN_TRY(cnn_ensure(ctx, ctx->b_tslab, sizeof(uint4) * 32 * (size_t)slab_cap));
         CNN_TRY(cnn_ensure(ctx, ctx->b_tband, sizeof(uint4) * 32 * 2 * (size_t)slab_cap));  // borderline slabs | transposed hit slabs
         P.slabs = ctx->b_tslab.as<uint4>();

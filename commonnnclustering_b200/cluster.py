@@ -2,6 +2,7 @@
 (``cluster.pyx:102-147`` construction, ``:256-392`` ``fit``, ``:155-177`` ``labels``)."""
 import time
 import weakref
+from collections.abc import Iterable, MutableMapping, MutableSequence
 
 import numpy as np
 
@@ -24,24 +25,127 @@ def _label_buffer(n: int, pinned: bool):
     return np.zeros(n, order="C", dtype=np.int64)
 
 
+def _label_path(label):
+    """A child address as a list of integers: 3, [1, 1, 2] and "1.1.2" are all accepted (reference ``get_child``,
+    ``_bundle.pyx:174-218``)."""
+    if isinstance(label, str):
+        label = label.split(".")
+    if isinstance(label, Iterable):
+        return [int(part) for part in label]
+    return [int(label)]
+
+
 class Bundle:
     """Input data + labels + summary of one clustering and its place in a hierarchy (reference
-    ``_bundle.pyx:20-53``): ``children`` maps a cluster label to the Bundle of that cluster's points,
+    ``_bundle.pyx:20-273``): ``children`` maps a cluster label to the Bundle of that cluster's points,
     ``parent_indices`` / ``root_indices`` say where a child's points sit in its parent / the root
-    (``ReferenceIndices``, ``_types.pyx:289-305``)."""
+    (``ReferenceIndices``, ``_types.pyx:289-305``).  As in the reference the public ``labels`` / ``input_data`` hand out
+    the ARRAYS (``Labels.labels``, ``InputData.data``); the objects themselves are ``_labels`` / ``_input_data``."""
 
-    def __init__(self, input_data=None, labels=None, summary=None, parent=None, alias=""):
-        self._input_data = input_data
-        self._labels = labels
-        self._summary = summary if summary is not None else Summary()
-        self._children = None
+    def __init__(self, input_data=None, labels=None, summary=None, parent=None, alias=None, children=None, meta=None,
+                 hierarchy_level=0):
+        self.input_data = input_data
+        self.labels = labels
+        self.summary = summary
+        self.children = children
         self._parent = parent
-        self.alias = alias
+        self.alias = "root" if alias is None else str(alias)
+        self.hierarchy_level = parent.hierarchy_level + 1 if parent is not None else hierarchy_level
+        self.meta = meta if meta is not None else {}
         self.parent_indices = None
         self.root_indices = None
 
-    children = property(lambda self: self._children)
     parent = property(lambda self: self._parent)
+
+    @property
+    def labels(self):
+        return None if self._labels is None else self._labels.labels
+
+    @labels.setter
+    def labels(self, value):
+        if value is not None and not isinstance(value, Labels):
+            value = Labels.from_sequence(value)
+        self._labels = value
+
+    @property
+    def input_data(self):
+        return None if self._input_data is None else self._input_data.data
+
+    @input_data.setter
+    def input_data(self, value):
+        if value is not None and not isinstance(value, InputData):
+            raise TypeError(f"Can't use object of type {type(value).__name__} as input data. "
+                            f"Expected type {InputData.__name__}.")
+        self._input_data = value
+
+    @property
+    def children(self):
+        return self._children
+
+    @children.setter
+    def children(self, value):
+        if value is None:
+            value = {}
+        if not isinstance(value, MutableMapping):
+            raise TypeError("Expected a mutable mapping")
+        self._children = value
+
+    @property
+    def summary(self):
+        return self._summary
+
+    @summary.setter
+    def summary(self, value):
+        if value is None:
+            value = Summary()
+        if not isinstance(value, MutableSequence):
+            raise TypeError("Expected a mutable sequence")
+        self._summary = value
+
+    @property
+    def hierarchy_level(self):
+        return self._hierarchy_level
+
+    @hierarchy_level.setter
+    def hierarchy_level(self, value):
+        self._hierarchy_level = int(value)
+
+    def info(self) -> str:
+        """The reference's short description (``_bundle.pyx:148-172``)."""
+        meta = self._input_data.meta if self._input_data is not None else {}
+        kinds = [kind for kind, flag in (("coordinates", "access_coords"), ("distances", "access_distances"),
+                                         ("neighbours", "access_neighbours")) if meta.get(flag, False)]
+        lines = {"alias": repr(self.alias), "hierarchy_level": self._hierarchy_level,
+                 "access": ", ".join(kinds or ["unknown"]),
+                 "points": self._input_data.n_points if self._input_data is not None else None,
+                 "children": len(self._children)}
+        return "\n".join(f"{k}: {v}" for k, v in lines.items())
+
+    def get_child(self, label):
+        """The child with this label; a list or a dotted string walks down the hierarchy."""
+        node = self
+        for step in _label_path(label):
+            try:
+                node = node._children[step]
+            except KeyError:
+                raise KeyError(f"Clustering {node.alias!r} has no child with label {step}") from None
+        return node
+
+    def add_child(self, label, bundle=None):
+        """Attach ``bundle`` (a new empty one by default) under the address ``label``; an existing child is replaced."""
+        *above, last = _label_path(label)
+        parent = self.get_child(above) if above else self
+        if bundle is None:
+            bundle = type(self)(parent=parent)
+        if not isinstance(bundle, Bundle):
+            raise TypeError("Expected a Bundle")
+        parent._children[last] = bundle
+
+    def __getitem__(self, key):
+        return self.get_child(key)
+
+    def __setitem__(self, key, value):
+        self.add_child(key, value)
 
     def isolate(self, purge: bool = True, isolate_input_data: bool = True, ctx=None) -> None:
         """Child bundles from the cluster labels (reference ``_bundle.pyx:275-352``): one child per
@@ -71,10 +175,6 @@ class Bundle:
             if isolate_input_data:
                 child._input_data = self._input_data.get_subset(parent_indices)
             self._children[label] = child
-
-    input_data = property(lambda self: self._input_data)
-    labels = property(lambda self: self._labels)
-    summary = property(lambda self: self._summary)
 
 
 class Clustering:
@@ -127,7 +227,9 @@ class Clustering:
 
     @labels.setter
     def labels(self, value):
-        self._bundle._labels = value if isinstance(value, Labels) else Labels.from_sequence(value)
+        if self._bundle is None:
+            raise ValueError("Can't set labels because there is no root bundle")
+        self._bundle.labels = value
 
     @property
     def summary(self):
@@ -136,6 +238,22 @@ class Clustering:
     @property
     def children(self):
         return self._bundle._children
+
+    def __str__(self):
+        parts = {"input_data": self._bundle._input_data if self._bundle is not None else None, "fitter": self._fitter,
+                 "hfitter": self._hierarchical_fitter, "predictor": self._predictor}
+        return f"{type(self).__name__}({', '.join(f'{k}={v}' for k, v in parts.items())})"
+
+    def __getitem__(self, value):
+        """``clustering[3]``, ``clustering["1.1.2"]``: a bundle further down the hierarchy (``cluster.pyx:227-228``)."""
+        return self._bundle.get_child(value)
+
+    def _fit(self, cluster_params, bundle=None) -> None:
+        """Low-level fit (reference ``cluster.pyx:230-254``): the parameters go to the fitter as they are, the labels
+        are not initialised."""
+        if bundle is None:
+            bundle = self._bundle
+        self._fitter.fit(bundle._input_data, bundle._labels, cluster_params)
 
     def isolate(self, purge: bool = True, isolate_input_data: bool = True, bundle=None) -> None:
         """Reference ``Clustering.isolate`` (``cluster.pyx:394-413``)."""

@@ -41,7 +41,7 @@ def test_clustering_fit_equals_reference_golden(name):
     cl = fit_via_api(x, kw.pop("r"), kw.pop("c"), **kw)
     np.testing.assert_array_equal(cl.labels, GOLD[name].astype(np.int64))
     assert cl.labels.dtype == np.int64
-    assert not cl.root.labels.consider.any()  # consider[:] = 0 after a fit (_fit.pyx:434-437)
+    assert not cl.root._labels.consider.any()  # consider[:] = 0 after a fit (_fit.pyx:434-437)
 
 
 @pytest.mark.parametrize("name", ["blobs1500_r010_c20", "md5000_r04_c5", "lattice3d", "lattice1d", "blobs1500_euclid"])
@@ -152,7 +152,7 @@ def test_readme_doctest():
     rec = cl.summary[-1]
     assert (rec.n_points, rec.n_clusters, rec.cnn_cutoff) == (12, 2, 1)
     assert abs(rec.ratio_noise - 4 / 12) < 1e-15 and rec.execution_time > 0
-    assert cl.root.labels.meta["params"] == {1: (1.5, 1), 2: (1.5, 1)}
+    assert cl.root._labels.meta["params"] == {1: (1.5, 1), 2: (1.5, 1)}
 
 
 # ---- neighbour sets ------------------------------------------------------------------------------------
@@ -506,8 +506,8 @@ def test_frozen_labels_through_clustering_api():
     cl = cluster.Clustering(x)
     cl.fit(0.1, 10, v=False)
     first = cl.labels.copy()
-    cl.root.labels.meta["frozen"] = True
-    cl.root.labels.consider[:] = (first == 0).astype(np.uint8)  # recluster the noise, keep the rest
+    cl.root._labels.meta["frozen"] = True
+    cl.root._labels.consider[:] = (first == 0).astype(np.uint8)  # recluster the noise, keep the rest
     cl.fit(0.2, 3, v=False, sort_by_size=False)
     rp, ci = port.neighbours(x, 0.2 ** 2)
     want = port.fit_bfs(rp, ci, 4, 5, current_start=int(first.max()) + 1, labels=first.copy(),

@@ -1,0 +1,159 @@
+"""Host logic of `Clustering.fit` / `fit_hierarchical` / `isolate` / `reel` without a GPU: the device is replaced by a
+stand-in that answers the SAME context contract from the oracle (test infrastructure) and NumPy, so what runs here is
+the package's own Python -- `cluster.Clustering`, `Labels.sort_by_size`'s bookkeeping, `_fit.HierarchicalFitterRepeat` --
+and its result is compared with the reference itself (`oracle/_ref`; cluster.pyx:256-413, :502-558, _fit.pyx:1018-1184).
+The GPU twins of these tests (tests/test_gpu_parity.py::test_hierarchical_repeat_equals_reference, ...) run the same
+comparisons with the real context."""
+import numpy as np
+import pytest
+
+from commonnnclustering_b200 import _fit, _types, cluster, datasets
+from oracle import port, ref
+
+needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+class OracleContext:
+    """The two context calls the host logic makes around a staged fit, answered on the CPU."""
+
+    def sort_by_size(self, labels, member_cutoff=None, max_clusters=None, return_map=False, max_label=None):
+        old = labels.copy()
+        port.sort_by_size(labels, member_cutoff, max_clusters)      # in place, like cnnb200_sort_by_size
+        if not return_map:
+            return None
+        reassign = np.zeros((int(old.max()) if max_label is None else max_label) + 1, dtype=np.int64)
+        reassign[old] = labels
+        return reassign
+
+    def labels_group(self, prev, cur):
+        n = prev.shape[0]
+        order = np.lexsort((np.arange(n), cur, prev))
+        rank = np.empty(n, dtype=np.int64)
+        for p in np.unique(prev):
+            idx = np.flatnonzero(prev == p)
+            rank[idx] = np.arange(idx.size)
+        return order.astype(np.int64), rank[order]
+
+
+class OracleFitter(_fit.Fitter):
+    """`FitterB200`'s contract (`make_parameters` of the role, `fit` in place, `ctx`) on the oracle's BFS."""
+
+    def __init__(self):
+        self._neighbours_getter = _types.NeighboursGetterRadius()
+        self.ctx = OracleContext()
+
+    def fit(self, input_data, labels, cluster_params):
+        x = input_data.to_components_array()
+        row_ptr, col_idx = port.neighbours(x, cluster_params.radius_cutoff, method="brute")
+        port.fit_bfs(row_ptr, col_idx, cluster_params.n_member_cutoff, cluster_params.similarity_cutoff,
+                     cluster_params.current_start, labels=labels.labels, consider=labels.consider)
+
+
+REF_KW = dict(fitter="bfs", fitter__ngetter="brute_force", fitter__na="vuset", fitter__nb="vuset", fitter__checker="switch",
+              fitter__queue="fifo", fitter__ngetter__dgetter="metric", fitter__ngetter__dgetter__metric="euclidean_r")
+
+
+def reference_clustering(rmod, x, prefix="", **extra):
+    """The reference's Clustering on a COPY of its default recipe: keyword arguments would be merged into the
+    registered recipe itself (recipes.py:193-194) and leak into every later construction in the process."""
+    from cnnclustering import recipes as rrecipes
+
+    recipe = dict(rrecipes.get_registered_recipe("coordinates"))
+    recipe.update({prefix + k: v for k, v in REF_KW.items()})
+    recipe.update(extra)
+    return rmod.Clustering(x, recipe=recipe)
+
+
+def same_tree(a, b, count):
+    count[0] += 1
+    la = None if a._labels is None else np.asarray(a._labels.labels)
+    lb = None if b._labels is None else np.asarray(b._labels.labels)
+    assert (la is None) == (lb is None)
+    if la is not None:
+        np.testing.assert_array_equal(la, lb)
+    ca, cb = a._children or {}, b._children or {}
+    assert list(ca) == list(cb)
+    for k in ca:
+        np.testing.assert_array_equal(ca[k].parent_indices, np.asarray(cb[k]._reference_indices.parent))
+        np.testing.assert_array_equal(ca[k].root_indices, np.asarray(cb[k]._reference_indices.root))
+        same_tree(ca[k], cb[k], count)
+
+
+@needs_ref
+def test_fit_records_and_frozen_labels_equal_reference():
+    rmod = ref.module()
+    x = datasets.blobs_2d(1200)
+    ours = cluster.Clustering(x, fitter=OracleFitter())
+    theirs = reference_clustering(rmod, x)
+    for cl in (ours, theirs):
+        cl.fit(0.3, 10, member_cutoff=5, v=False)
+    np.testing.assert_array_equal(ours.labels, np.asarray(theirs.labels))
+    a, b = ours.summary[-1], theirs.summary[-1]
+    for field in ("n_points", "radius_cutoff", "cnn_cutoff", "member_cutoff", "max_clusters", "n_clusters", "ratio_largest",
+                  "ratio_noise"):
+        assert getattr(a, field) == getattr(b, field), field
+    assert ours._bundle._labels.meta["params"] == theirs._bundle._labels.meta["params"]
+    # a second fit on frozen labels: only the noise is reclustered, new clusters are numbered after the old ones
+    for cl in (ours, theirs):
+        cl._bundle._labels.meta["frozen"] = True
+        cl.fit(0.45, 3, v=False, sort_by_size=False)
+    np.testing.assert_array_equal(ours.labels, np.asarray(theirs.labels))
+    assert ours._bundle._labels.meta["params"] == theirs._bundle._labels.meta["params"]
+    assert ours.summary[-1].n_clusters == theirs.summary[-1].n_clusters
+
+
+@needs_ref
+def test_hierarchical_repeat_host_logic_equals_reference():
+    rmod = ref.module()
+    x = datasets.blobs_2d(1500)
+    kw = dict(radius_cutoff=[0.5, 0.25, 0.12, 0.08], cnn_cutoff=[5, 8, 8, 10], member_cutoff=5, v=False)
+    theirs = reference_clustering(rmod, x, prefix="hierarchical_fitter__", hierarchical_fitter="repeat")
+    theirs.fit_hierarchical(**kw)
+    ours = cluster.Clustering(x, fitter=OracleFitter(), hierarchical_fitter=_fit.HierarchicalFitterRepeat(OracleFitter()))
+    ours.fit_hierarchical(**kw)
+    count = [0]
+    same_tree(ours._bundle, theirs._bundle, count)
+    assert count[0] > 5
+    # parameters recorded per cluster (info=True) follow the reference's, level by level
+    def params(b):
+        return None if b._labels is None else b._labels.meta.get("params")
+    assert params(ours._bundle) == params(theirs._bundle)
+    for k, child in (ours._bundle._children or {}).items():
+        assert params(child) == params(theirs._bundle._children[k])
+    # reel: the tree folded back into one label array
+    ours.reel()
+    theirs.reel()
+    np.testing.assert_array_equal(ours.labels, np.asarray(theirs.labels))
+
+
+@needs_ref
+def test_isolate_recluster_reel_host_logic_equals_reference():
+    rmod = ref.module()
+    x = datasets.blobs_2d(1500)
+    ours = cluster.Clustering(x, fitter=OracleFitter())
+    theirs = reference_clustering(rmod, x)
+    for cl in (ours, theirs):
+        cl.fit(0.45, 5, member_cutoff=5, v=False)
+        cl.isolate()
+    assert list(ours.children) == list(theirs.children)
+    for k in ours.children:
+        for cl in (ours, theirs):
+            cl.fit(0.2, 8, member_cutoff=5, v=False, bundle=cl.children[k])
+        np.testing.assert_array_equal(ours.children[k].labels, np.asarray(theirs.children[k].labels))
+    ours.reel()
+    theirs.reel()
+    np.testing.assert_array_equal(ours.labels, np.asarray(theirs.labels))
+    assert ours._bundle._labels.meta["params"] == theirs._bundle._labels.meta["params"]
+
+
+def test_stand_in_context_follows_the_device_contract():
+    """labels_group: order by (prev, cur, index), rank within the previous cluster; sort_by_size: map old -> new."""
+    ctx = OracleContext()
+    prev = np.array([1, 2, 1, 0, 2, 1], dtype=np.int64)
+    cur = np.array([2, 1, 1, 3, 1, 2], dtype=np.int64)
+    order, rank = ctx.labels_group(prev, cur)
+    assert order.tolist() == [3, 2, 0, 5, 1, 4]
+    assert rank.tolist() == [0, 1, 0, 2, 0, 1]
+    lab = np.array([3, 3, 1, 2, 2, 2, 0], dtype=np.int64)
+    reassign = ctx.sort_by_size(lab, 1, None, return_map=True, max_label=3)
+    assert lab.tolist() == [2, 2, 3, 1, 1, 1, 0] and reassign.tolist() == [0, 3, 1, 2]

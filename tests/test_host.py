@@ -84,7 +84,7 @@ def test_prepare_neighbourhoods_padding():
 
 def test_clustering_construction():
     c = cluster.Clustering(datasets.README_POINTS)
-    assert c.root.input_data.n_points == 12 and c.labels is None
+    assert c.root._input_data.n_points == 12 and c.labels is None
     assert isinstance(c.fitter, _fit.Fitter)
     with pytest.raises(TypeError):
         c.fitter = object()
@@ -134,7 +134,7 @@ def test_isolate_and_reel_known_answer():
     assert list(cl.root.children) == [2, 1, 3]
     assert cl.root.children[1].parent_indices.tolist() == [2, 4, 6, 10]
     assert cl.root.children[2].parent_indices.tolist() == [0, 1, 5, 11]
-    np.testing.assert_array_equal(cl.root.children[3].input_data.data, x[[8, 9]])
+    np.testing.assert_array_equal(cl.root.children[3].input_data, x[[8, 9]])
     cl.reel()
     # child 2 first (labels + 3), then child 1 (labels + current max 5); child 3 has no labels
     assert cl.labels.tolist() == [0, 4, 6, 0, 6, 4, 0, 0, 3, 3, 7, 5]

@@ -1,52 +1,31 @@
 """Host logic of `Clustering.fit` / `fit_hierarchical` / `isolate` / `reel` without a GPU: the device is replaced by a
-stand-in that answers the SAME context contract from the oracle (test infrastructure) and NumPy, so what runs here is
-the package's own Python -- `cluster.Clustering`, `Labels.sort_by_size`'s bookkeeping, `_fit.HierarchicalFitterRepeat` --
+stand-in that answers the SAME context contract from the oracle (tests/standin.py), so what runs here is the package's
+own Python -- `cluster.Clustering`, `FitterB200`, `Labels.sort_by_size`'s bookkeeping, `_fit.HierarchicalFitterRepeat` --
 and its result is compared with the reference itself (`oracle/_ref`; cluster.pyx:256-413, :502-558, _fit.pyx:1018-1184).
 The GPU twins of these tests (tests/test_gpu_parity.py::test_hierarchical_repeat_equals_reference, ...) run the same
 comparisons with the real context."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
-from commonnnclustering_b200 import _fit, _types, cluster, datasets
-from oracle import port, ref
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from standin import StandInContext  # noqa: E402
+
+from commonnnclustering_b200 import _fit, cluster, datasets  # noqa: E402
+from oracle import ref  # noqa: E402
 
 needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
 
 
-class OracleContext:
-    """The two context calls the host logic makes around a staged fit, answered on the CPU."""
-
-    def sort_by_size(self, labels, member_cutoff=None, max_clusters=None, return_map=False, max_label=None):
-        old = labels.copy()
-        port.sort_by_size(labels, member_cutoff, max_clusters)      # in place, like cnnb200_sort_by_size
-        if not return_map:
-            return None
-        reassign = np.zeros((int(old.max()) if max_label is None else max_label) + 1, dtype=np.int64)
-        reassign[old] = labels
-        return reassign
-
-    def labels_group(self, prev, cur):
-        n = prev.shape[0]
-        order = np.lexsort((np.arange(n), cur, prev))
-        rank = np.empty(n, dtype=np.int64)
-        for p in np.unique(prev):
-            idx = np.flatnonzero(prev == p)
-            rank[idx] = np.arange(idx.size)
-        return order.astype(np.int64), rank[order]
-
-
-class OracleFitter(_fit.Fitter):
-    """`FitterB200`'s contract (`make_parameters` of the role, `fit` in place, `ctx`) on the oracle's BFS."""
-
-    def __init__(self):
-        self._neighbours_getter = _types.NeighboursGetterRadius()
-        self.ctx = OracleContext()
-
-    def fit(self, input_data, labels, cluster_params):
-        x = input_data.to_components_array()
-        row_ptr, col_idx = port.neighbours(x, cluster_params.radius_cutoff, method="brute")
-        port.fit_bfs(row_ptr, col_idx, cluster_params.n_member_cutoff, cluster_params.similarity_cutoff,
-                     cluster_params.current_start, labels=labels.labels, consider=labels.consider)
+def ours_on_stand_in(x, hierarchical=False):
+    """The package's own staged fitter (and hierarchical fitter) over a stand-in context."""
+    ctx = StandInContext()
+    fitter = _fit.FitterB200(ctx=ctx)
+    kw = {"hierarchical_fitter": _fit.HierarchicalFitterRepeat(fitter)} if hierarchical else {}
+    return cluster.Clustering(x, fitter=fitter, **kw)
 
 
 REF_KW = dict(fitter="bfs", fitter__ngetter="brute_force", fitter__na="vuset", fitter__nb="vuset", fitter__checker="switch",
@@ -83,7 +62,7 @@ def same_tree(a, b, count):
 def test_fit_records_and_frozen_labels_equal_reference():
     rmod = ref.module()
     x = datasets.blobs_2d(1200)
-    ours = cluster.Clustering(x, fitter=OracleFitter())
+    ours = ours_on_stand_in(x)
     theirs = reference_clustering(rmod, x)
     for cl in (ours, theirs):
         cl.fit(0.3, 10, member_cutoff=5, v=False)
@@ -109,7 +88,7 @@ def test_hierarchical_repeat_host_logic_equals_reference():
     kw = dict(radius_cutoff=[0.5, 0.25, 0.12, 0.08], cnn_cutoff=[5, 8, 8, 10], member_cutoff=5, v=False)
     theirs = reference_clustering(rmod, x, prefix="hierarchical_fitter__", hierarchical_fitter="repeat")
     theirs.fit_hierarchical(**kw)
-    ours = cluster.Clustering(x, fitter=OracleFitter(), hierarchical_fitter=_fit.HierarchicalFitterRepeat(OracleFitter()))
+    ours = ours_on_stand_in(x, hierarchical=True)
     ours.fit_hierarchical(**kw)
     count = [0]
     same_tree(ours._bundle, theirs._bundle, count)
@@ -130,7 +109,7 @@ def test_hierarchical_repeat_host_logic_equals_reference():
 def test_isolate_recluster_reel_host_logic_equals_reference():
     rmod = ref.module()
     x = datasets.blobs_2d(1500)
-    ours = cluster.Clustering(x, fitter=OracleFitter())
+    ours = ours_on_stand_in(x)
     theirs = reference_clustering(rmod, x)
     for cl in (ours, theirs):
         cl.fit(0.45, 5, member_cutoff=5, v=False)
@@ -148,7 +127,7 @@ def test_isolate_recluster_reel_host_logic_equals_reference():
 
 def test_stand_in_context_follows_the_device_contract():
     """labels_group: order by (prev, cur, index), rank within the previous cluster; sort_by_size: map old -> new."""
-    ctx = OracleContext()
+    ctx = StandInContext()
     prev = np.array([1, 2, 1, 0, 2, 1], dtype=np.int64)
     cur = np.array([2, 1, 1, 3, 1, 2], dtype=np.int64)
     order, rank = ctx.labels_group(prev, cur)

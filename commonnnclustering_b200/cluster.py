@@ -177,6 +177,15 @@ class Bundle:
             self._children[label] = child
 
 
+def bfs_leafs(root: Bundle):
+    """All bundles of a hierarchy, breadth first, the root included (reference ``_bundle.pyx:403-414``)."""
+    level = [root]
+    yield root
+    while level:
+        level = [child for node in level for child in (node._children or {}).values()]
+        yield from level
+
+
 class Clustering:
     """``Clustering(data).fit(radius_cutoff, cnn_cutoff, member_cutoff)`` on a B200."""
 
@@ -279,6 +288,51 @@ class Clustering:
 
             self._hierarchical_fitter = HierarchicalFitterRepeat(self._fitter)
         self._hierarchical_fitter.fit(bundle, **fitter_kwargs)
+
+    def trim_shrinking_leafs(self, bundle=None) -> None:
+        """Cuts the tails of a hierarchy in which a cluster only loses members (reference ``cluster.pyx:435-470``): a
+        bundle stays when its parent split into several clusters (it is one of them), when its own labels hold more
+        than one cluster, or when something below it is kept for one of these reasons; every other bundle loses its
+        labels and children."""
+        def visit(node, parent_splits: bool) -> bool:
+            splits = keeps_below = False
+            if node._children:
+                splits = len(node._labels.to_set() - {0}) > 1
+                kept = [visit(child, splits) for child in node._children.values()]   # every child is visited
+                keeps_below = any(kept)
+            keep = parent_splits or splits or keeps_below
+            if not keep:
+                node._labels = None
+                node._children = {}
+            return keep
+
+        visit(self._bundle if bundle is None else bundle, True)
+
+    def trim_trivial_leafs(self, bundle=None) -> None:
+        """Bundles whose labels are all noise lose their labels and children (reference ``cluster.pyx:472-500``)."""
+        pending = [self._bundle if bundle is None else bundle]
+        while pending:
+            node = pending.pop()
+            if node._labels is None:
+                continue
+            if node._labels.to_set() == {0}:
+                node._labels = None
+                node._children = {}
+            else:
+                pending.extend((node._children or {}).values())
+
+    def to_dtrajs(self, bundle=None) -> list:
+        """The labels cut into the parts the input data came in (``meta["edges"]``), e.g. one label sequence per
+        trajectory (reference ``cluster.pyx:1166-1188``)."""
+        bundle = self._bundle if bundle is None else bundle
+        labels = bundle.labels
+        if labels is None:
+            return []
+        edges = bundle._input_data.meta.get("edges") if bundle._input_data is not None else None
+        if edges is None:
+            return [labels]
+        parts = np.split(labels, np.cumsum(edges))
+        return parts[:-1] if len(parts[-1]) == 0 else parts
 
     def reel(self, depth=None, bundle=None) -> None:
         """Wrap up the label assignments of lower hierarchy levels (reference ``cluster.pyx:502-558``):

@@ -136,3 +136,46 @@ def test_stand_in_context_follows_the_device_contract():
     lab = np.array([3, 3, 1, 2, 2, 2, 0], dtype=np.int64)
     reassign = ctx.sort_by_size(lab, 1, None, return_map=True, max_label=3)
     assert lab.tolist() == [2, 2, 3, 1, 1, 1, 0] and reassign.tolist() == [0, 3, 1, 2]
+
+
+@needs_ref
+@pytest.mark.parametrize("trim", ["trim_shrinking_leafs", "trim_trivial_leafs"])
+def test_trimmed_hierarchies_equal_reference(trim):
+    """`trim_shrinking_leafs` / `trim_trivial_leafs` (cluster.pyx:435-500) on the same repeated-fit hierarchy."""
+    from cnnclustering import _bundle as rbundle
+
+    rmod = ref.module()
+    x = datasets.blobs_2d(1500)
+    # a ladder of ever harder parameters: clusters shrink for a while, split, and finally dissolve into noise
+    kw = dict(radius_cutoff=[0.5, 0.08, 0.075, 0.07, 0.065, 0.05], cnn_cutoff=[5, 10, 10, 10, 10, 60], member_cutoff=5,
+              v=False)
+    theirs = reference_clustering(rmod, x, prefix="hierarchical_fitter__", hierarchical_fitter="repeat")
+    ours = ours_on_stand_in(x, hierarchical=True)
+    for cl in (ours, theirs):
+        cl.fit_hierarchical(**kw)
+    before = sum(b._labels is not None for b in cluster.bfs_leafs(ours._bundle))
+    for cl in (ours, theirs):
+        getattr(cl, trim)()
+    count = [0]
+    same_tree(ours._bundle, theirs._bundle, count)
+    after = sum(b._labels is not None for b in cluster.bfs_leafs(ours._bundle))
+    assert after < before, "the ladder was meant to leave something to trim"
+    # the breadth-first walk visits the same bundles in the same order
+    assert [b.alias.split(" - ")[-1] for b in cluster.bfs_leafs(ours._bundle)][1:] == \
+        [str(k) for b in rbundle.bfs_leafs(theirs._bundle) for k in (b._children or {})]
+    ours.reel()
+    theirs.reel()
+    np.testing.assert_array_equal(ours.labels, np.asarray(theirs.labels))
+
+
+def test_to_dtrajs_follows_the_parts_of_the_input():
+    rng = np.random.default_rng(0)
+    parts = [rng.random((5, 2)), rng.random((3, 2)), rng.random((4, 2))]
+    cl = cluster.Clustering(parts)
+    assert cl.to_dtrajs() == []
+    cl.labels = np.arange(12) % 3
+    got = cl.to_dtrajs()
+    assert [len(p) for p in got] == [5, 3, 4] and np.concatenate(got).tolist() == (np.arange(12) % 3).tolist()
+    flat = cluster.Clustering(np.concatenate(parts))
+    flat.labels = np.arange(12) % 3
+    assert len(flat.to_dtrajs()) == 1

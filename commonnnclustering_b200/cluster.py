@@ -189,8 +189,10 @@ def bfs_leafs(root: Bundle):
 class Clustering:
     """``Clustering(data).fit(radius_cutoff, cnn_cutoff, member_cutoff)`` on a B200."""
 
-    def __init__(self, data=None, *, fitter=None, hierarchical_fitter=None, predictor=None, recipe=None, **recipe_kwargs):
+    def __init__(self, data=None, *, fitter=None, hierarchical_fitter=None, predictor=None, bundle_kwargs=None, recipe=None,
+                 **recipe_kwargs):
         builder = recipes.Builder(recipe, **recipe_kwargs)
+        bundle_kwargs = dict(bundle_kwargs or {})     # e.g. alias, summary, meta of the root bundle (cluster.pyx:102-131)
         self._hierarchical_fitter = hierarchical_fitter if isinstance(hierarchical_fitter, HierarchicalFitter) else None
         if hierarchical_fitter is not None and self._hierarchical_fitter is None:
             builder.set("hierarchical_fitter", hierarchical_fitter)
@@ -202,9 +204,9 @@ class Clustering:
         elif isinstance(data, Bundle):
             self._bundle = data
         elif isinstance(data, InputData):
-            self._bundle = Bundle(data)
+            self._bundle = Bundle(data, **bundle_kwargs)
         else:
-            self._bundle = Bundle(builder.make_input_data(data))
+            self._bundle = Bundle(builder.make_input_data(data), **bundle_kwargs)
         if isinstance(fitter, Fitter):
             self._fitter = fitter
         else:

@@ -85,6 +85,7 @@ def test_prepare_neighbourhoods_padding():
 def test_clustering_construction():
     c = cluster.Clustering(datasets.README_POINTS)
     assert c.root._input_data.n_points == 12 and c.labels is None
+    assert cluster.Clustering(datasets.README_POINTS, bundle_kwargs={"alias": "traj-7"}).root.alias == "traj-7" and c.root.alias == "root"
     assert isinstance(c.fitter, _fit.Fitter)
     with pytest.raises(TypeError):
         c.fitter = object()

@@ -179,3 +179,29 @@ def test_to_dtrajs_follows_the_parts_of_the_input():
     flat = cluster.Clustering(np.concatenate(parts))
     flat.labels = np.arange(12) % 3
     assert len(flat.to_dtrajs()) == 1
+
+
+@needs_ref
+def test_sort_by_size_rekeys_params_and_children_like_the_reference():
+    """`Labels.sort_by_size(..., bundle=...)` (_types.pyx:212-286): labels, `meta["params"]` and the bundle's children are
+    re-keyed together; clusters that fall under `member_cutoff` / beyond `max_clusters` lose their entry."""
+    from cnnclustering import _types as rtypes
+
+    from commonnnclustering_b200 import _types
+
+    rmod = ref.module()
+    rng = np.random.default_rng(8)
+    raw = rng.choice(np.arange(0, 8), size=400, p=[0.1, 0.05, 0.3, 0.02, 0.2, 0.01, 0.25, 0.07]).astype(np.int64)
+    for kw in ({}, {"member_cutoff": 10}, {"max_clusters": 3}, {"member_cutoff": 30, "max_clusters": 4}):
+        out = []
+        for mod, labels_type, extra in ((cluster, _types.Labels, {"ctx": StandInContext()}), (rmod, rtypes.Labels, {})):
+            cl = mod.Clustering(rng.random((400, 2)))
+            lab = labels_type(raw.copy())
+            lab.meta["params"] = {int(k): (0.1 * k, k) for k in np.unique(raw) if k != 0}
+            cl._bundle._labels = lab
+            cl._bundle._children = {int(k): f"child of {k}" for k in np.unique(raw) if k != 0}
+            lab.sort_by_size(bundle=cl._bundle, **kw, **extra)
+            out.append((np.asarray(lab.labels).tolist(), lab.meta["params"], cl._bundle._children))
+        assert out[0][0] == out[1][0], kw
+        assert out[0][1] == out[1][1], kw
+        assert out[0][2] == out[1][2] and list(out[0][2]) == list(out[1][2]), kw

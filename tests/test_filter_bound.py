@@ -184,3 +184,31 @@ def test_the_emulation_notices_a_band_that_is_too_narrow(monkeypatch):
     hit, miss, exact, worst = emulate(np.ascontiguousarray(x, dtype=np.float64), rc, sqrt_metric)
     assert np.any(hit & ~exact) or np.any(miss & exact)
     assert worst > 1.0
+
+
+EXTREME = {
+    # a bounding box 10^11 radii wide: the cells are coarsened to the 2^20-per-dimension cap, (x - lo) loses its low bits
+    "two_clusters_1e9_apart": lambda rng: (np.r_[rng.random((600, 2)) * 0.2, rng.random((600, 2)) * 0.2 + 1.0e9], 0.01 ** 2,
+                                           False),
+    "negative_far_corner": lambda rng: (np.r_[rng.random((800, 3)) * 0.3, [[-3.0e8, -3.0e8, -3.0e8]]], 0.02 ** 2, False),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES) + list(EXTREME))
+def test_candidate_windows_hold_every_neighbour(name):
+    """The cell list only ever tests pairs whose cells differ by at most one along every axis (cell edge = radius times
+    1 + 1e-6, read from grid.cu): no pair the reference's f64 expression accepts may lie outside, whatever the rounding
+    of (x - lo) / h does -- also when the box is so large that the cells are coarsened to the per-dimension cap."""
+    x, rc, sqrt_metric = (CASES.get(name) or EXTREME[name])(np.random.default_rng(7))
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    r = rc if sqrt_metric else np.sqrt(rc)
+    _, h, dims, cell = geometry(x, r)
+    assert np.all(dims <= 1048576) and h >= r
+    n, d = x.shape
+    s = np.zeros((n, n))
+    for k in range(d):
+        t = x[:, None, k] - x[None, :, k]
+        s = s + t * t if k else t * t
+    i, j = np.nonzero((np.sqrt(s) if sqrt_metric else s) <= rc)
+    assert i.size > n                                                   # more than the diagonal
+    assert np.abs(cell[i] - cell[j]).max() <= 1

@@ -119,13 +119,15 @@ class Labels:
         return cls(np.zeros(n, order="C", dtype=P_AINDEX), meta=meta)
 
     def to_mapping(self):
-        """label -> list of point indices (``_types.pyx:187-198``); vectorised."""
+        """label -> list of point indices, keys in the order in which the labels first occur (what the reference's
+        loop over the points yields, ``_types.pyx:187-198``); vectorised."""
         mapping = defaultdict(list)
         if self._labels.size:
             order = np.argsort(self._labels, kind="stable")
             sl = self._labels[order]
             bounds = np.flatnonzero(np.diff(sl)) + 1
-            for chunk in np.split(order, bounds):
+            chunks = np.split(order, bounds)           # each ascending: the sort is stable
+            for chunk in sorted(chunks, key=lambda c: c[0]):
                 mapping[int(self._labels[chunk[0]])] = chunk.tolist()
         return mapping
 

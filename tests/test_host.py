@@ -27,6 +27,7 @@ def test_labels_container():
     lab = _types.Labels.from_sequence([1, 1, 2, 2, 0, 1])
     assert lab.n_points == 6 and lab.set == {0, 1, 2}
     assert dict(lab.mapping) == {0: [4], 1: [0, 1, 5], 2: [2, 3]}
+    assert list(lab.mapping) == [1, 2, 0]           # keys in order of first occurrence, like the reference's loop
     assert lab.consider.tolist() == [1] * 6
     with pytest.raises(ValueError):
         _types.Labels(np.zeros(3, dtype=np.int64), consider=np.ones(2, dtype=np.uint8))

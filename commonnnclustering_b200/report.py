@@ -24,18 +24,20 @@ class Record:
         return f"{type(self).__name__}({attrs})"
 
     def __str__(self):
-        head = "-" * 95 + "\n" + "".join(f"{h:<10}" for h in (
-            "#points", "r", "c", "min", "max", "#clusters", "%largest", "%noise", "time")) + "\n"
-        vals = []
-        for a in self.__slots__:
-            v = getattr(self, a)
-            if v is None:
-                vals.append(f"{'None':<10}")
-            elif isinstance(v, float):
-                vals.append(f"{v:<10.3f}")
-            else:
-                vals.append(f"{v:<10}")
-        return head + "".join(vals) + "\n" + "-" * 95 + "\n"
+        """The table ``fit(v=True)`` prints, in the reference's layout (``report.py:142-176``): nine columns of width ten,
+        the execution time as hh:mm:s.mmm."""
+        titles = ("#points", "r", "c", "min", "max", "#clusters", "%largest", "%noise")
+        cells = []
+        for attr in self.__slots__[:-1]:
+            v = getattr(self, attr)
+            cells.append(f"{v:<10.3f}" if isinstance(v, float) else f"{v!r:<10}" if v is None else f"{v:<10}")
+        if self.execution_time is None:
+            clock = None
+        else:
+            minutes, seconds = divmod(self.execution_time, 60)
+            clock = f"{int(minutes // 60):0>2}:{int(minutes % 60):0>2}:{seconds:.3f}"
+        rule = "-" * 95
+        return f"{rule}\n{''.join(f'{t:<10}' for t in titles)}time     \n{''.join(cells)}{clock}\n{rule}\n"
 
     def to_dict(self):
         return {a: getattr(self, a) for a in self.__slots__}
@@ -73,6 +75,10 @@ class Summary(MutableSequence):
         return str(self._list)
 
     def to_DataFrame(self):
+        """One row per record; the integer columns are nullable (``member_cutoff`` / ``max_clusters`` may be None), as in
+        the reference's typed frame (``report.py:47-88``)."""
         import pandas as pd
 
-        return pd.DataFrame([r.to_dict() for r in self._list], columns=Record.__slots__)
+        frame = pd.DataFrame([r.to_dict() for r in self._list], columns=Record.__slots__)
+        integer = ("n_points", "cnn_cutoff", "member_cutoff", "max_clusters", "n_clusters")
+        return frame.astype({c: pd.Int64Dtype() if c in integer else "float64" for c in Record.__slots__})

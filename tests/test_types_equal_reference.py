@@ -104,3 +104,25 @@ def test_metrics_and_distance_getter(theirs):
     assert ours.MetricPrecomputed().adjust_radius(0.3) == theirs.MetricExtPrecomputed().adjust_radius(0.3) == 0.3
     lo, lr = ours.NeighboursGetterLookup(), theirs.NeighboursGetterExtLookup()
     assert (lo.is_sorted, lo.is_selfcounting) == (lr.is_sorted, lr.is_selfcounting) == (False, True)
+
+
+def test_records_print_and_tabulate_like_the_reference(theirs):
+    """`Record.__str__` (what `fit(v=True)` prints) and `Summary.to_DataFrame` (report.py:47-88, :142-176)."""
+    from cnnclustering import report as rreport
+
+    from commonnnclustering_b200 import report
+
+    rows = [dict(n_points=100, radius_cutoff=0.1, cnn_cutoff=5, member_cutoff=None, max_clusters=None, n_clusters=3,
+                 ratio_largest=0.5, ratio_noise=0.1, execution_time=0.01),
+            dict(n_points=100, radius_cutoff=0.2, cnn_cutoff=5, member_cutoff=2, max_clusters=4, n_clusters=1,
+                 ratio_largest=0.9, ratio_noise=0.0, execution_time=None),
+            dict(n_points=10 ** 7, radius_cutoff=2, cnn_cutoff=50, member_cutoff=10, max_clusters=None, n_clusters=167,
+                 ratio_largest=1 / 3, ratio_noise=2 / 3, execution_time=3725.0625)]
+    a = report.Summary([report.Record(**r) for r in rows])
+    b = rreport.Summary([rreport.Record(**r) for r in rows])
+    for x, y in zip(a, b):
+        assert str(x) == str(y) and repr(x) == repr(y) and x.to_dict() == y.to_dict()
+    fa, fb = a.to_DataFrame(), b.to_DataFrame()
+    assert fa.dtypes.to_dict() == fb.dtypes.to_dict() and fa.equals(fb)
+    with pytest.raises(TypeError):
+        a.append("not a record")

@@ -29,6 +29,35 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/cnnb200.h but not exported"
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """A foreign-function binding (cgo, Cython `cdef extern`, ctypes generators) reads the header as C, not C++: a
+    strict C99 translation unit that takes the address of EVERY declared entry point compiles without a warning, links
+    against the library and runs -- without a GPU `cnnb200_ctx_create` answers with an error code and a message, it
+    does not crash and nothing falls back."""
+    from commonnnclustering_b200 import build
+
+    lib_path = build.build()
+    syms = declared_symbols()
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "cnnb200.h"\n'
+        "typedef void (*any_fn)(void);\n"
+        "int main(void) {\n"
+        "    any_fn table[] = {" + ", ".join(f"(any_fn){name}" for name in syms) + "};\n"
+        "    cnnb200_ctx *ctx = NULL;\n"
+        "    int rc = cnnb200_ctx_create(0, &ctx);\n"
+        '    printf("%d %d %d %s\\n", (int)(sizeof table / sizeof table[0]), cnnb200_version(), rc, rc ? cnnb200_last_error() : "ok");\n'
+        "    if (rc == 0) cnnb200_ctx_destroy(ctx);\n"
+        "    return 0;\n}\n")
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic",
+                    "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), lib_path,
+                    f"-Wl,-rpath,{os.path.dirname(lib_path)}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split(None, 3)
+    assert int(out[0]) == len(syms) and int(out[1]) == 100
+    assert (int(out[2]) == 0 and out[3].strip() == "ok") or (int(out[2]) < 0 and len(out[3].strip()) > 0)
+
+
 def test_python_binding_covers_the_header():
     from commonnnclustering_b200 import _lib
 

@@ -215,3 +215,47 @@ def test_fused_and_staged_fitters_equal_live_reference():
             assert (a.n_clusters, a.ratio_largest, a.ratio_noise) == (b.n_clusters, b.ratio_largest, b.ratio_noise)
             assert cl.root._labels.meta["params"] == theirs._bundle._labels.meta["params"]
     assert "fit_points" not in ctx.calls and "sort_by_size" in ctx.calls
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_random_fit_sequences_equal_live_reference():
+    """Forty random sequences of calls on one object -- fresh fits, fits on frozen labels, with and without size sorting,
+    cut-offs, offsets, purges -- on small sets with ties: labels, records and parameter tables follow the reference's."""
+    rmod = ref.module()   # puts oracle/_ref on sys.path
+    from cnnclustering import recipes as rrecipes
+
+    rng = np.random.default_rng(2026)
+    for trial in range(40):
+        n = int(rng.integers(40, 300))
+        x = cases.lattice(n, int(rng.integers(1, 4)), 100 + trial) if trial % 3 == 0 else \
+            np.ascontiguousarray(rng.standard_normal((n, int(rng.integers(1, 6)))) * 0.5)
+        theirs = rmod.Clustering(x, recipe=dict(rrecipes.get_registered_recipe("coordinates")))
+        mine, _ = clustering(x, **({"fitter": "b200_staged"} if trial % 2 else {}))
+        for step in range(int(rng.integers(1, 4))):
+            kw = {"v": False}
+            if rng.random() < 0.5:
+                kw["member_cutoff"] = int(rng.integers(1, 8))
+            if rng.random() < 0.3:
+                kw["max_clusters"] = int(rng.integers(1, 4))
+            if rng.random() < 0.3:
+                kw["sort_by_size"] = False
+            if rng.random() < 0.2:
+                kw["cnn_offset"] = 1
+            if rng.random() < 0.2:
+                kw["purge"] = True
+            r = float(rng.choice([0.125, 0.25, 0.3, 0.5, 0.8]))
+            c = int(rng.integers(1 if "cnn_offset" in kw else 0, 7))
+            if step and rng.random() < 0.6:          # keep what was found, recluster the rest
+                for cl in (mine, theirs):
+                    cl._bundle._labels.meta["frozen"] = True
+                    lab = np.asarray(cl.labels)
+                    cl._bundle._labels.consider[:] = (lab == 0).astype(np.uint8)
+            for cl in (mine, theirs):
+                cl.fit(r, c, **kw)
+            what = f"trial {trial} step {step}: n={n} d={x.shape[1]} r={r} c={c} {kw}"
+            np.testing.assert_array_equal(mine.labels, np.asarray(theirs.labels), err_msg=what)
+            a, b = mine.summary[-1], theirs.summary[-1]
+            assert (a.n_clusters, a.ratio_largest, a.ratio_noise, a.cnn_cutoff) == \
+                (b.n_clusters, b.ratio_largest, b.ratio_noise, b.cnn_cutoff), what
+            assert mine._bundle._labels.meta["params"] == theirs._bundle._labels.meta["params"], what
+            assert mine._bundle._labels.consider.tolist() == np.asarray(theirs._bundle._labels.consider).tolist(), what

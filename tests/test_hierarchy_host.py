@@ -205,3 +205,36 @@ def test_sort_by_size_rekeys_params_and_children_like_the_reference():
         assert out[0][0] == out[1][0], kw
         assert out[0][1] == out[1][1], kw
         assert out[0][2] == out[1][2] and list(out[0][2]) == list(out[1][2]), kw
+
+
+@needs_ref
+def test_random_ladders_equal_reference():
+    """Fifteen random parameter ladders (2-5 steps, scalar or sequence arguments, with and without size sorting and
+    offsets): the trees, what the two trims leave of them, and the reeled labels follow the reference's."""
+    rmod = ref.module()
+    rng = np.random.default_rng(77)
+    for trial in range(15):
+        x = datasets.blobs_2d(int(rng.integers(300, 700)))
+        steps = int(rng.integers(2, 6))
+        radii = sorted((float(v) for v in rng.choice([0.5, 0.4, 0.3, 0.25, 0.2, 0.15, 0.1, 0.08], steps, replace=False)),
+                       reverse=True)
+        kw = dict(radius_cutoff=radii, cnn_cutoff=[int(v) for v in np.sort(rng.integers(2, 12, steps))], v=False)
+        if trial % 4 == 0:
+            kw["cnn_cutoff"] = int(kw["cnn_cutoff"][0])             # a scalar is repeated for every step
+        if trial % 3 == 0:
+            kw["member_cutoff"] = int(rng.integers(2, 10))
+        if trial % 5 == 0:
+            kw["sort_by_size"] = False
+        if trial % 7 == 0:
+            kw["cnn_offset"] = 1
+        for trim in (None, "trim_shrinking_leafs", "trim_trivial_leafs"):
+            theirs = reference_clustering(rmod, x, prefix="hierarchical_fitter__", hierarchical_fitter="repeat")
+            ours = ours_on_stand_in(x, hierarchical=True)
+            for cl in (ours, theirs):
+                cl.fit_hierarchical(**kw)
+                if trim:
+                    getattr(cl, trim)()
+            same_tree(ours._bundle, theirs._bundle, [0])
+            for cl in (ours, theirs):
+                cl.reel()
+            np.testing.assert_array_equal(ours.labels, np.asarray(theirs.labels), err_msg=f"trial {trial} {trim} {kw}")

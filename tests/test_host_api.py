@@ -259,3 +259,47 @@ def test_random_fit_sequences_equal_live_reference():
                 (b.n_clusters, b.ratio_largest, b.ratio_noise, b.cnn_cutoff), what
             assert mine._bundle._labels.meta["params"] == theirs._bundle._labels.meta["params"], what
             assert mine._bundle._labels.consider.tolist() == np.asarray(theirs._bundle._labels.consider).tolist(), what
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_random_predictions_equal_live_reference():
+    """`Clustering.predict` (cluster.pyx:560-653, PredictorFirstmatch) on twelve random configurations: a first call
+    restricted to some clusters, a second one on the same (now frozen) labels with other parameters."""
+    rmod = ref.module()   # puts oracle/_ref on sys.path
+    from cnnclustering import _fit as rfit, _types as rtypes, recipes as rrecipes
+
+    recipe = dict(rrecipes.get_registered_recipe("coordinates"))
+    # types instead of names: the reference's name table has no entry for the `*_other` / `neighbour_neighbours` keywords
+    recipe.update({"predictor": rfit.PredictorFirstmatch, "predictor.ngetter": rtypes.NeighboursGetterExtBruteForce,
+                   "predictor.ngetter.dgetter": rtypes.DistanceGetterExtMetric,
+                   "predictor.ngetter.dgetter.metric": rtypes.MetricExtEuclideanReduced,
+                   "predictor.ongetter": rtypes.NeighboursGetterExtBruteForce,
+                   "predictor.ongetter.dgetter": rtypes.DistanceGetterExtMetric,
+                   "predictor.ongetter.dgetter.metric": rtypes.MetricExtEuclideanReduced,
+                   "predictor.na": rtypes.NeighboursExtVectorCPPUnorderedSet,
+                   "predictor.nb": rtypes.NeighboursExtVectorCPPUnorderedSet,
+                   "predictor.checker": rtypes.SimilarityCheckerExtSwitchContains})
+    rng = np.random.default_rng(404)
+    seen = 0
+    for trial in range(12):
+        pts = datasets.blobs_2d(int(rng.integers(400, 900))) if trial % 2 else cases.lattice(500, 2, 300 + trial)
+        x, x_other = np.ascontiguousarray(pts[::2]), np.ascontiguousarray(pts[1::2])
+        r, c = (0.15, int(rng.integers(3, 9))) if trial % 2 else (0.25, int(rng.integers(1, 4)))
+        out = []
+        for mod in ("ours", "theirs"):
+            if mod == "ours":
+                cl, _ = clustering(x)
+                other = cluster.Clustering(x_other)
+            else:
+                cl, other = rmod.Clustering(x, recipe=dict(recipe)), rmod.Clustering(x_other, recipe=dict(recipe))
+            cl.fit(r, c, member_cutoff=3, v=False)
+            n_found = int(np.asarray(cl.labels).max())
+            first = [1] if n_found >= 1 else None
+            cl.predict(other._bundle, r * 1.2, max(c - 1, 0), clusters=first)
+            a = np.asarray(other.labels).copy()
+            cl.predict(other._bundle, r * 1.5, max(c - 2, 0))          # frozen: only the still-considered points move
+            out.append((a, np.asarray(other.labels).copy(), np.asarray(other._bundle._labels.consider).copy()))
+        for got, want in zip(out[0], out[1]):
+            np.testing.assert_array_equal(got, want, err_msg=f"trial {trial}")
+        seen += int(out[0][1].max() > 0)
+    assert seen >= 6
